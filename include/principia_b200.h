@@ -1,0 +1,317 @@
+/* principia_b200 -- C ABI of the B200-native batched gravitational-flow engine.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of
+ * mockingbirdnest/Principia's physics::Ephemeris.  The reference has no FFI
+ * seam on this path (it is C++ templates end to end); the entry points below
+ * are what a C-ABI replacement of the path binds, one per reference routine,
+ * each citing the reference interface it replaces.  The C++ facade
+ * `principia_b200/cpp/ephemeris.hpp` re-creates the reference's class surface
+ * on top of this header; INTEGRATION.md shows the reference-side change.
+ *
+ * Conventions
+ *  - Every quantity is one IEEE binary64 in SI units (m, s, m^3/s^2, rad), as
+ *    `Quantity<D>` is in the reference (quantities/quantities.hpp).  Instants
+ *    are seconds from J2000 (astronomy/epoch.hpp:16-24).
+ *  - Return values are absl::StatusCode numbers (pb_status_t); the reference
+ *    returns absl::Status on the same routines.
+ *  - Plain pointers and sizes only.  Functions without a `_device` suffix take
+ *    HOST pointers and perform the host<->device copies themselves; `_device`
+ *    variants take pointers into the ephemeris' CUDA device and run on the
+ *    given CUDA stream (a `cudaStream_t` cast to void*, NULL = default).
+ *  - There is no CPU fallback: every entry point fails with
+ *    PB_FAILED_PRECONDITION if no CUDA device is usable.
+ *  - Body indices in this API are the CALLER's indices (the order of the
+ *    `bodies` array given to pb_ephemeris_create), like `unowned_bodies_` in
+ *    the reference (physics/ephemeris.hpp:507-519).  Internally bodies are
+ *    reordered like the reference's constructor does
+ *    (physics/ephemeris_body.hpp:138-158): that order is the floating-point
+ *    summation order, pb_ephemeris_internal_order exposes it.
+ */
+#ifndef PRINCIPIA_B200_H_
+#define PRINCIPIA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t pb_status_t;
+enum {
+  PB_OK = 0,
+  PB_CANCELLED = 1,
+  PB_INVALID_ARGUMENT = 3,
+  PB_DEADLINE_EXCEEDED = 4,  /* FlowWithAdaptiveStep could not reach t. */
+  PB_RESOURCE_EXHAUSTED = 8, /* ReachedMaximalStepCount. */
+  PB_FAILED_PRECONDITION = 9,/* VanishingStepSize; also "no CUDA device". */
+  PB_ABORTED = 10,
+  PB_OUT_OF_RANGE = 11,      /* "Collision detected". */
+  PB_INTERNAL = 13           /* CUDA runtime error; see pb_last_error. */
+};
+
+/* integrators/methods.hpp; serialization kinds of the same names. */
+enum {
+  PB_BLANES_MOAN_2002_SRKN_14A = 0,
+  PB_MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL = 1,
+  PB_QUINLAN_1999_ORDER_8A = 2,
+  PB_QUINLAN_TREMAINE_1990_ORDER_12 = 3,
+  PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM = 16
+};
+
+/* One massive body: MassiveBody / RotatingBody / OblateBody parameters
+ * (physics/massive_body.hpp, rotating_body.hpp:45-77, oblate_body.hpp:39-75).
+ * `cos`/`sin` are the fully normalised coefficients, lower triangular,
+ * (n, m) -> n(n+1)/2 + m, (degree+1)(degree+2)/2 entries each
+ * (numerics/fixed_arrays_body.hpp:722). */
+typedef struct pb_body_t {
+  double gravitational_parameter;
+  double min_radius;           /* 0 for a non-rotating MassiveBody. */
+  double mean_radius;
+  double reference_angle;
+  double reference_instant;
+  double angular_frequency;
+  double right_ascension_of_pole;
+  double declination_of_pole;
+  double reference_radius;     /* Oblate bodies only. */
+  int32_t is_rotating;
+  int32_t is_oblate;
+  int32_t geopotential_degree; /* Oblate bodies only, 2..50. */
+  int32_t is_zonal;
+  const double* cos;
+  const double* sin;
+} pb_body_t;
+
+typedef struct pb_ephemeris pb_ephemeris_t;
+
+/* ---- Construction: Ephemeris::Ephemeris, physics/ephemeris.hpp:124-128,
+ * ephemeris_body.hpp:94-170 (body ordering) and Geopotential::Geopotential,
+ * geopotential_body.hpp:669-733 (damping thresholds from the tolerance). */
+pb_status_t pb_ephemeris_create(int32_t n_bodies,
+                                const pb_body_t* bodies,
+                                double geopotential_tolerance,
+                                int32_t cuda_device,
+                                pb_ephemeris_t** ephemeris);
+void pb_ephemeris_destroy(pb_ephemeris_t* ephemeris);
+const char* pb_last_error(void);
+
+/* order[i] = caller index of the body at internal position i; returns the
+ * number of oblate bodies through *n_oblate (may be NULL). */
+pb_status_t pb_ephemeris_internal_order(const pb_ephemeris_t* ephemeris,
+                                        int32_t* order,
+                                        int32_t* n_oblate);
+
+/* Geopotential::degree_damping() / sectoral_damping() of an oblate body:
+ * inner thresholds for degrees 0..*n_degrees-1 (geopotential.hpp:57-58).
+ * `inner_thresholds` needs room for 51 doubles. */
+pb_status_t pb_geopotential_damping(const pb_ephemeris_t* ephemeris,
+                                    int32_t body,
+                                    int32_t* n_degrees,
+                                    double* inner_thresholds,
+                                    double* sectoral_inner_threshold);
+
+/* ---- ContinuousTrajectory segments (physics/continuous_trajectory.hpp).
+ * Appends `n_segments` polynomials in the monomial basis to `body`'s
+ * trajectory; mirrors the growth of `polynomials_` in
+ * ContinuousTrajectory::Append (continuous_trajectory_body.hpp:82-127,758-858).
+ * Segment s covers ]t_max[s-1], t_max[s]], is evaluated at (t - origin[s]) by
+ * the Estrin scheme with FMA (numerics/polynomial_evaluators_body.hpp:72-160);
+ * coefficients[s][k][xyz], k = 0..17 (entries above degree[s] are ignored).
+ * `t_min` is only used by the first call for a body (first_time_). */
+pb_status_t pb_ephemeris_append_segments(pb_ephemeris_t* ephemeris,
+                                         int32_t body,
+                                         int32_t n_segments,
+                                         double t_min,
+                                         const double* t_max,
+                                         const double* origin,
+                                         const int32_t* degree,
+                                         const double* coefficients);
+double pb_ephemeris_t_min(const pb_ephemeris_t* ephemeris);
+double pb_ephemeris_t_max(const pb_ephemeris_t* ephemeris);
+
+/* Ephemeris::EvaluateAllPositions, ephemeris.hpp:154-155: positions[3*body]. */
+pb_status_t pb_ephemeris_evaluate_all_positions(pb_ephemeris_t* ephemeris,
+                                                double t,
+                                                double* positions);
+
+/* ---- Accelerations and potential.
+ * Ephemeris::ComputeGravitationalAccelerationOnMasslessBody (batched),
+ * ephemeris.hpp:253-264 -> ...ByAllMassiveBodiesOnMasslessBodies,
+ * ephemeris_body.hpp:1554-1591.  SoA: q = [x[n] y[n] z[n]], a likewise.
+ * *status receives PB_OK or PB_OUT_OF_RANGE (bitwise OR over bodies and
+ * probes, ephemeris_body.hpp:1437). */
+pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies(
+    pb_ephemeris_t* ephemeris, double t, int64_t n, const double* q, double* a,
+    pb_status_t* status);
+pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies_device(
+    pb_ephemeris_t* ephemeris, double t, int64_t n, const double* q, double* a,
+    int32_t* status_device, void* stream);
+
+/* Ephemeris::ComputeGravitationalPotential (batched), ephemeris.hpp:283-285. */
+pb_status_t pb_compute_gravitational_potential(pb_ephemeris_t* ephemeris,
+                                               double t, int64_t n,
+                                               const double* q,
+                                               double* potential);
+
+/* Ephemeris::ComputeGravitationalAccelerationOnMassiveBodies,
+ * ephemeris.hpp:276-280 (positions given, AoS [body][xyz], caller order) and
+ * ...OnMassiveBody, :268-271 (positions == NULL: evaluated at t from the
+ * trajectories).  accelerations[3*body]. */
+pb_status_t pb_compute_gravitational_acceleration_on_massive_bodies(
+    pb_ephemeris_t* ephemeris, double t, const double* positions,
+    double* accelerations);
+
+/* ---- Fixed-step massless flow: Ephemeris::NewInstance + FlowWithFixedStep,
+ * ephemeris.hpp:181-194,222-225, with
+ * SymplecticRungeKuttaNystromIntegrator::Instance::Solve
+ * (integrators/symplectic_runge_kutta_nyström_integrator_body.hpp:24-144).
+ *
+ * `state` is the integrator instance's ODE::State
+ * (integrators/ordinary_differential_equations.hpp:156-180) for n probes
+ * sharing one time, SoA of 12 planes of n doubles:
+ *   planes 0-2 q.value xyz, 3-5 q.error, 6-8 v.value, 9-11 v.error.
+ * `time` is the DoublePrecision<Instant> {value, error}; both are updated in
+ * place so that the call is restartable like Instance::Solve.
+ * Steps are taken while |step| <= |(t_final - time.value) - time.error|.
+ * Trajectory sink (AppendMasslessBodiesStateToTrajectories,
+ * ephemeris_body.hpp:1118-1131): if `samples` != NULL, every `sample_every`-th
+ * step (counted from this call) the time and the 6 value planes are appended:
+ * samples[s][6][n], sample_times[s]; at most `max_samples`.
+ * *n_steps receives the number of steps taken; *status the first non-OK RHS
+ * status (PB_OUT_OF_RANGE on collision; integration continues, as in the
+ * reference). */
+typedef struct pb_fixed_step_flow_t {
+  int32_t method;       /* PB_BLANES_MOAN_2002_SRKN_14A or PB_MCLACHLAN_... */
+  double step;
+  double t_final;
+  int64_t n;
+  double* state;        /* 12 * n */
+  double* time;         /* 2 */
+  int64_t sample_every; /* 0: no sampling. */
+  int64_t max_samples;
+  double* samples;      /* max_samples * 6 * n, or NULL. */
+  double* sample_times; /* max_samples, HOST memory in both variants. */
+  int64_t* n_samples;   /* out, may be NULL. */
+  int64_t* n_steps;     /* out, may be NULL. */
+  pb_status_t* status;  /* out, may be NULL. */
+} pb_fixed_step_flow_t;
+pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* ephemeris,
+                                    const pb_fixed_step_flow_t* flow);
+/* state/samples in device memory; time, sample_times and outs on the host. */
+pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* ephemeris,
+                                           const pb_fixed_step_flow_t* flow,
+                                           void* stream);
+
+/* ---- Adaptive massless flow: Ephemeris::FlowWithAdaptiveStep,
+ * ephemeris.hpp:201-207, ephemeris_body.hpp:415-444,1624-1717, with
+ * EmbeddedExplicitRungeKuttaNystromIntegrator::Instance::Solve
+ * (integrators/embedded_explicit_runge_kutta_nyström_integrator_body.hpp:
+ * 44-258), one independent trajectory per probe, batched.
+ * `state` as above (12 planes); `time` holds per-probe DoublePrecision times:
+ * planes time.value[n], time.error[n].  first_step = t_final - time.value,
+ * safety factor 0.9, last step exact.  Per-probe outputs (n entries each, may
+ * be NULL): status (PB_OK, PB_FAILED_PRECONDITION, PB_RESOURCE_EXHAUSTED;
+ * collisions are swallowed as in the reference), accepted steps, rejected
+ * attempts, RHS evaluations.  If `step_log` != NULL the times of the first
+ * `step_log_capacity` accepted steps of each probe are written to
+ * step_log[k * n + probe] (parity of the accepted-step sequence). */
+typedef struct pb_adaptive_step_flow_t {
+  int32_t method;       /* PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM */
+  double t_final;
+  double length_integration_tolerance;
+  double speed_integration_tolerance;
+  int64_t max_steps;
+  int64_t n;
+  double* state;        /* 12 * n */
+  double* time;         /* 2 * n */
+  int32_t* status;      /* n */
+  int64_t* accepted_steps;
+  int64_t* rejected_steps;
+  int64_t* evaluations;
+  int64_t step_log_capacity;
+  double* step_log;     /* step_log_capacity * n */
+} pb_adaptive_step_flow_t;
+pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* ephemeris,
+                                       const pb_adaptive_step_flow_t* flow);
+pb_status_t pb_flow_with_adaptive_step_device(
+    pb_ephemeris_t* ephemeris, const pb_adaptive_step_flow_t* flow,
+    void* stream);
+
+/* ---- Massive-body flow (Ephemeris::Prolong's integration,
+ * ephemeris_body.hpp:116-170,312-344,1503-1552) for ensembles of independent
+ * small systems sharing one gravity model (astronomy/trappist_dynamics_test.cpp
+ * :275-297: one Ephemeris per ensemble member), with
+ * SymmetricLinearMultistepIntegrator (…multistep_integrator_body.hpp:22-152),
+ * its SRKN14A starter (starter_body.hpp:23-93) and the
+ * Cohen-Hubbard-Oesterwinter velocities (:281-321), or plain SRKN.
+ *
+ * The ensemble uses the ephemeris' bodies (internal order, masses and
+ * geopotentials; trajectories are not used).  `state`: 12 planes as above,
+ * each plane [body (internal order)][system]: index (plane * n_bodies + body)
+ * * n_systems + system.  `time` {value, error} is shared.  Runs the startup if
+ * `history` is not yet started, then steps while
+ * step <= (t_final - time.value) - time.error. */
+typedef struct pb_nbody_ensemble pb_nbody_ensemble_t;
+pb_status_t pb_nbody_ensemble_create(pb_ephemeris_t* ephemeris,
+                                     int32_t method, double step,
+                                     int64_t n_systems,
+                                     const double* state, /* 12*n_bodies*n_sys */
+                                     double initial_time,
+                                     pb_nbody_ensemble_t** ensemble);
+void pb_nbody_ensemble_destroy(pb_nbody_ensemble_t* ensemble);
+/* Instance::Solve(t_final); *n_steps = steps appended by this call. */
+pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* ensemble,
+                                    double t_final, int64_t* n_steps);
+/* Current ODE::State (host copy): state 12*n_bodies*n_systems, time[2]. */
+pb_status_t pb_nbody_ensemble_get_state(pb_nbody_ensemble_t* ensemble,
+                                        double* state, double* time);
+
+/* ---- Large-N all-pairs point-mass system (synthetic; the same
+ * ComputeGravitationalAccelerationBetweenAllMassiveBodies with only spherical
+ * bodies, ephemeris_body.hpp:1342-1380,1503-1552), Quinlan-Tremaine / SRKN.
+ * Sharded by target block across ranks: this rank owns targets
+ * [i_begin, i_end) of n.  `exchange` (may be NULL when the rank owns every
+ * target) is called after every position update with the device pointer of
+ * the full position array (3 planes of n) whose [i_begin, i_end) slices this
+ * rank has just written; it must return once every other rank's slices are
+ * visible in that array (an NCCL all-gather on `stream`). */
+typedef void (*pb_exchange_positions_t)(void* user, double* positions_device,
+                                        int64_t n, int64_t i_begin,
+                                        int64_t i_end, void* stream);
+typedef struct pb_nbody_allpairs pb_nbody_allpairs_t;
+pb_status_t pb_nbody_allpairs_create(int32_t cuda_device, int32_t method,
+                                     double step, int64_t n, int64_t i_begin,
+                                     int64_t i_end,
+                                     const double* gravitational_parameters,
+                                     const double* q, /* 3 planes of n */
+                                     const double* v, /* 3 planes of n */
+                                     double initial_time,
+                                     pb_exchange_positions_t exchange,
+                                     void* exchange_user,
+                                     pb_nbody_allpairs_t** system);
+void pb_nbody_allpairs_destroy(pb_nbody_allpairs_t* system);
+pb_status_t pb_nbody_allpairs_solve(pb_nbody_allpairs_t* system, double t_final,
+                                    int64_t* n_steps,
+                                    int64_t* n_force_evaluations);
+/* Owned slice: q, v as 3 planes of (i_end - i_begin) values; time[2]. */
+pb_status_t pb_nbody_allpairs_get_state(pb_nbody_allpairs_t* system, double* q,
+                                        double* v, double* time);
+/* One force evaluation on the current positions (for measurement): the
+ * accelerations of the owned targets, 3 planes of (i_end - i_begin). */
+pb_status_t pb_nbody_allpairs_accelerations(pb_nbody_allpairs_t* system,
+                                            double* a);
+/* Milliseconds spent in the last solve's force kernels (CUDA events). */
+double pb_nbody_allpairs_last_force_ms(const pb_nbody_allpairs_t* system);
+
+/* ---- Measurement helpers. */
+/* Register-resident DFMA chain: returns the achieved FP64 FLOP/s on the
+ * device (2 flop per FMA) and the kernel time through *ms. */
+pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,
+                                 double* ms);
+/* Kernels launched by this library since load (all entry points). */
+int64_t pb_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}  /* extern "C" */
+#endif
+
+#endif  /* PRINCIPIA_B200_H_ */

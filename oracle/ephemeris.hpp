@@ -1,0 +1,435 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see numerics.hpp).
+//
+// CPU restatement of physics::Ephemeris for the hot path
+// (physics/ephemeris_body.hpp): body ordering, Prolong, the three acceleration
+// routines, the potential, FlowWithFixedStep and FlowWithAdaptiveStep.
+#pragma once
+
+#include <cstdint>
+#include <memory>
+#include <vector>
+
+#include "integrators.hpp"
+#include "numerics.hpp"
+#include "physics.hpp"
+
+namespace orc {
+
+enum FixedMethod : int32_t {
+  kBlanesMoan2002SRKN14A = 0,
+  kMcLachlanAtela1992Order5Optimal = 1,
+  kQuinlan1999Order8A = 2,
+  kQuinlanTremaine1990Order12 = 3,
+};
+
+// A fixed-step instance of either family.
+class FixedStepInstance {
+ public:
+  FixedStepInstance(int32_t method, RightHandSide rhs, State state,
+                    AppendState append_state, double step) {
+    switch (method) {
+      case kBlanesMoan2002SRKN14A:
+        srkn_ = std::make_unique<SrknInstance>(BlanesMoan2002SRKN14A(), rhs,
+                                               state, append_state, step);
+        break;
+      case kMcLachlanAtela1992Order5Optimal:
+        srkn_ = std::make_unique<SrknInstance>(
+            McLachlanAtela1992Order5Optimal(), rhs, state, append_state, step);
+        break;
+      case kQuinlan1999Order8A:
+        slms_ = std::make_unique<SlmsInstance>(Quinlan1999Order8A(), rhs, state,
+                                               append_state, step);
+        break;
+      default:
+        slms_ = std::make_unique<SlmsInstance>(QuinlanTremaine1990Order12(),
+                                               rhs, state, append_state, step);
+    }
+  }
+  int32_t Solve(double t_final) {
+    return srkn_ ? srkn_->Solve(t_final) : slms_->Solve(t_final);
+  }
+  State const& state() const { return srkn_ ? srkn_->state() : slms_->state(); }
+  std::int64_t evaluations() const {
+    return srkn_ ? srkn_->evaluations : slms_->evaluations;
+  }
+  SlmsInstance const* slms() const { return slms_.get(); }
+
+ private:
+  std::unique_ptr<SrknInstance> srkn_;
+  std::unique_ptr<SlmsInstance> slms_;
+};
+
+constexpr double min_radius_tolerance = 0.99;  // ephemeris_body.hpp:64.
+
+class Ephemeris {
+ public:
+  // ephemeris_body.hpp:94-170.  `bodies` in the caller's order (SolarSystem:
+  // alphabetical); internally oblate bodies are front-inserted.
+  Ephemeris(std::vector<Body> const& bodies, std::vector<Vec3> const& q,
+            std::vector<Vec3> const& v, double initial_time,
+            double fitting_tolerance, double geopotential_tolerance,
+            int32_t method, double step)
+      : step_(step) {
+    State state;
+    state.time.value = initial_time;
+    for (std::size_t i = 0; i < bodies.size(); ++i) {
+      auto body = std::make_unique<Body>(bodies[i]);
+      body->ComputeAxes();
+      auto trajectory =
+          std::make_unique<ContinuousTrajectory>(step, fitting_tolerance);
+      trajectory->Append(initial_time, q[i], v[i]);
+      DP qd[3], vd[3];
+      qd[0].value = q[i].x;
+      qd[1].value = q[i].y;
+      qd[2].value = q[i].z;
+      vd[0].value = v[i].x;
+      vd[1].value = v[i].y;
+      vd[2].value = v[i].z;
+      if (body->oblate) {
+        geopotentials_.emplace(geopotentials_.begin(), body.get(),
+                               geopotential_tolerance);
+        order_.insert(order_.begin(), static_cast<int>(i));
+        bodies_.insert(bodies_.begin(), std::move(body));
+        trajectories_.insert(trajectories_.begin(), std::move(trajectory));
+        state.positions.insert(state.positions.begin(), qd, qd + 3);
+        state.velocities.insert(state.velocities.begin(), vd, vd + 3);
+        ++number_of_oblate_bodies_;
+      } else {
+        order_.push_back(static_cast<int>(i));
+        bodies_.push_back(std::move(body));
+        trajectories_.push_back(std::move(trajectory));
+        state.positions.insert(state.positions.end(), qd, qd + 3);
+        state.velocities.insert(state.velocities.end(), vd, vd + 3);
+        ++number_of_spherical_bodies_;
+      }
+    }
+    instance_ = std::make_unique<FixedStepInstance>(
+        method,
+        [this](double t, std::vector<double> const& positions,
+               std::vector<double>& accelerations) {
+          return ComputeGravitationalAccelerationBetweenAllMassiveBodies(
+              t, positions, accelerations);
+        },
+        state,
+        [this](State const& s) { AppendMassiveBodiesState(s); }, step);
+  }
+
+  int size() const { return static_cast<int>(bodies_.size()); }
+  std::vector<int> const& order() const { return order_; }
+  Body const& body(int internal) const { return *bodies_[internal]; }
+  Geopotential const& geopotential(int internal) const {
+    return geopotentials_[internal];
+  }
+  int number_of_oblate_bodies() const { return number_of_oblate_bodies_; }
+  ContinuousTrajectory& trajectory(int internal) {
+    return *trajectories_[internal];
+  }
+  FixedStepInstance const& instance() const { return *instance_; }
+  int32_t last_severe_integration_status() const { return severe_status_; }
+
+  double t_min() const {
+    double t = trajectories_[0]->t_min();
+    for (auto const& trajectory : trajectories_) {
+      t = std::max(t, trajectory->t_min());
+    }
+    return t;
+  }
+  double t_max() const {
+    double t = trajectories_[0]->t_max();
+    for (auto const& trajectory : trajectories_) {
+      t = std::min(t, trajectory->t_max());
+    }
+    return t;
+  }
+
+  // :312-344.
+  void Prolong(double t, std::int64_t max_ephemeris_steps =
+                             std::numeric_limits<std::int64_t>::max()) {
+    double const instance_time = instance_->state().time.value;
+    double const desired_t_max =
+        std::min(t, instance_time + max_ephemeris_steps * step_);
+    double t_final;
+    if (desired_t_max <= instance_time) {
+      t_final = instance_time + step_;
+    } else {
+      t_final = desired_t_max;
+    }
+    while (t_max() < desired_t_max) {
+      instance_->Solve(t_final);
+      t_final += step_;
+    }
+  }
+
+  // :1503-1552.  Flat arrays in internal order.
+  int32_t ComputeGravitationalAccelerationBetweenAllMassiveBodies(
+      double t, std::vector<double> const& positions,
+      std::vector<double>& accelerations) const {
+    int const n = size();
+    std::vector<Vec3> q(n), a(n);
+    for (int i = 0; i < n; ++i) {
+      q[i] = {positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]};
+    }
+    int const n_oblate = number_of_oblate_bodies_;
+    for (int b1 = 0; b1 < n_oblate; ++b1) {
+      ByMassiveBodyOnMassiveBodies(true, true, t, b1, b1 + 1, n_oblate, q, a);
+      ByMassiveBodyOnMassiveBodies(true, false, t, b1, n_oblate, n, q, a);
+    }
+    for (int b1 = n_oblate; b1 < n; ++b1) {
+      ByMassiveBodyOnMassiveBodies(false, false, t, b1, b1 + 1, n, q, a);
+    }
+    for (int i = 0; i < n; ++i) {
+      accelerations[3 * i] = a[i].x;
+      accelerations[3 * i + 1] = a[i].y;
+      accelerations[3 * i + 2] = a[i].z;
+    }
+    return kOk;
+  }
+
+  // :1249-1315: acceleration on one massive body (internal index b1).
+  Vec3 ComputeGravitationalAccelerationOnMassiveBody(
+      int b1, std::vector<Vec3> const& q, double t) const {
+    int const n = size();
+    int const n_oblate = number_of_oblate_bodies_;
+    std::vector<Vec3> a(n);
+    if (bodies_[b1]->oblate) {
+      ByMassiveBodyOnMassiveBodies(true, true, t, b1, 0, b1, q, a);
+      ByMassiveBodyOnMassiveBodies(true, true, t, b1, b1 + 1, n_oblate, q, a);
+      ByMassiveBodyOnMassiveBodies(true, false, t, b1, n_oblate, n, q, a);
+    } else {
+      ByMassiveBodyOnMassiveBodies(false, true, t, b1, 0, n_oblate, q, a);
+      ByMassiveBodyOnMassiveBodies(false, false, t, b1, n_oblate, b1, q, a);
+      ByMassiveBodyOnMassiveBodies(false, false, t, b1, b1 + 1, n, q, a);
+    }
+    return a[b1];
+  }
+
+  std::vector<Vec3> EvaluateAllPositions(double t) const {
+    std::vector<Vec3> q;
+    for (auto const& trajectory : trajectories_) {
+      q.push_back(trajectory->EvaluatePosition(t));
+    }
+    return q;
+  }
+
+  // :1554-1591.
+  int32_t ComputeGravitationalAccelerationByAllMassiveBodiesOnMasslessBodies(
+      double t, std::vector<Vec3> const& positions,
+      std::vector<Vec3>& accelerations) const {
+    accelerations.assign(accelerations.size(), Vec3{});
+    int32_t error = kOk;
+    for (int b1 = 0; b1 < size(); ++b1) {
+      error |= ByMassiveBodyOnMasslessBodies(b1 < number_of_oblate_bodies_, t,
+                                             b1, positions, accelerations);
+    }
+    return error;
+  }
+
+  // :1593-1621, :1464-1501.
+  void ComputeGravitationalPotentialsOfAllMassiveBodies(
+      double t, std::vector<Vec3> const& positions,
+      std::vector<double>& potentials) const {
+    potentials.assign(potentials.size(), 0.0);
+    for (int b1 = 0; b1 < size(); ++b1) {
+      bool const oblate = b1 < number_of_oblate_bodies_;
+      double const mu1 = bodies_[b1]->mu;
+      Vec3 const position1 = trajectories_[b1]->EvaluatePosition(t);
+      for (std::size_t b2 = 0; b2 < positions.size(); ++b2) {
+        Vec3 const dq = position1 - positions[b2];
+        double const dq2 = Norm2(dq);
+        double const dq_norm = std::sqrt(dq2);
+        double const one_over_dq_norm = 1 / dq_norm;
+        potentials[b2] -= mu1 * one_over_dq_norm;
+        if (oblate) {
+          double const one_over_dq3 =
+              one_over_dq_norm * one_over_dq_norm * one_over_dq_norm;
+          double const effect =
+              geopotentials_[b1].GeneralSphericalHarmonicsPotential(
+                  t, -dq, dq_norm, dq2, one_over_dq3);
+          potentials[b2] += mu1 * effect;
+        }
+      }
+    }
+  }
+
+  // The massless right-hand side on flat arrays (:360-385, no intrinsic
+  // accelerations).
+  RightHandSide MasslessRightHandSide() const {
+    return [this](double t, std::vector<double> const& q,
+                  std::vector<double>& g) -> int32_t {
+      std::size_t const n = q.size() / 3;
+      std::vector<Vec3> positions(n), accelerations(n);
+      for (std::size_t i = 0; i < n; ++i) {
+        positions[i] = {q[3 * i], q[3 * i + 1], q[3 * i + 2]};
+      }
+      int32_t const error =
+          ComputeGravitationalAccelerationByAllMassiveBodiesOnMasslessBodies(
+              t, positions, accelerations);
+      for (std::size_t i = 0; i < n; ++i) {
+        g[3 * i] = accelerations[i].x;
+        g[3 * i + 1] = accelerations[i].y;
+        g[3 * i + 2] = accelerations[i].z;
+      }
+      return error == kOk ? kOk : kOutOfRange;
+    };
+  }
+
+  // :1698-1717.
+  static double ToleranceToErrorRatio(double length_tolerance,
+                                      double speed_tolerance,
+                                      StateError const& error) {
+    double max_length_error = 0;
+    double max_speed_error = 0;
+    for (std::size_t i = 0; i + 2 < error.position_error.size(); i += 3) {
+      Vec3 const e{error.position_error[i], error.position_error[i + 1],
+                   error.position_error[i + 2]};
+      max_length_error = std::max(max_length_error, Norm(e));
+    }
+    for (std::size_t i = 0; i + 2 < error.velocity_error.size(); i += 3) {
+      Vec3 const e{error.velocity_error[i], error.velocity_error[i + 1],
+                   error.velocity_error[i + 2]};
+      max_speed_error = std::max(max_speed_error, Norm(e));
+    }
+    return std::min(length_tolerance / max_length_error,
+                    speed_tolerance / max_speed_error);
+  }
+
+  // :1624-1696 for one massless trajectory; the ephemeris must already cover
+  // [state.time, t] (no Prolong here: the caller prolongs).  `append` receives
+  // every accepted state.
+  int32_t FlowWithAdaptiveStep(State& state, double t, double length_tolerance,
+                               double speed_tolerance, std::int64_t max_steps,
+                               AppendState append, std::int64_t* evaluations,
+                               std::int64_t* rejections) const {
+    if (state.time.value == t) {
+      return kOk;
+    }
+    double const t_final = std::min(t, t_max());
+    AdaptiveParameters parameters;
+    parameters.first_step = t_final - state.time.value;
+    parameters.safety_factor = 0.9;
+    parameters.max_steps = max_steps;
+    parameters.last_step_is_exact = true;
+    State last = state;
+    ErknInstance instance(
+        DormandElMikkawyPrince1986RKN434FM(), MasslessRightHandSide(), state,
+        [&](State const& s) {
+          last = s;
+          if (append) {
+            append(s);
+          }
+        },
+        [=](double, State const&, StateError const& error) {
+          return ToleranceToErrorRatio(length_tolerance, speed_tolerance,
+                                       error);
+        },
+        parameters);
+    int32_t status = instance.Solve(t_final);
+    state = last;
+    if (evaluations != nullptr) {
+      *evaluations = instance.evaluations;
+    }
+    if (rejections != nullptr) {
+      *rejections = instance.rejections;
+    }
+    if (status == kOutOfRange) {
+      status = kOk;
+    }
+    if (status != kOk || t_final == t) {
+      return status;
+    } else {
+      return kDeadlineExceeded;
+    }
+  }
+
+ private:
+  // :1342-1410.
+  void ByMassiveBodyOnMassiveBodies(bool body1_is_oblate, bool body2_is_oblate,
+                                    double t, int b1, int b2_begin, int b2_end,
+                                    std::vector<Vec3> const& positions,
+                                    std::vector<Vec3>& accelerations) const {
+    Vec3 const& position_of_b1 = positions[b1];
+    Vec3& acceleration_on_b1 = accelerations[b1];
+    double const mu1 = bodies_[b1]->mu;
+    for (int b2 = b2_begin; b2 < b2_end; ++b2) {
+      Vec3& acceleration_on_b2 = accelerations[b2];
+      double const mu2 = bodies_[b2]->mu;
+      Vec3 const dq = position_of_b1 - positions[b2];
+      double const dq2 = Norm2(dq);
+      double const dq_norm = std::sqrt(dq2);
+      double const one_over_dq3 = dq_norm / (dq2 * dq2);
+      double const mu1_over_dq3 = mu1 * one_over_dq3;
+      acceleration_on_b2 += dq * mu1_over_dq3;
+      double const mu2_over_dq3 = mu2 * one_over_dq3;
+      acceleration_on_b1 -= dq * mu2_over_dq3;
+      if (body1_is_oblate) {
+        Vec3 const effect =
+            geopotentials_[b1].GeneralSphericalHarmonicsAcceleration(
+                t, -dq, dq_norm, dq2, one_over_dq3);
+        acceleration_on_b1 -= mu2 * effect;
+        acceleration_on_b2 += mu1 * effect;
+      }
+      if (body2_is_oblate) {
+        Vec3 const effect =
+            geopotentials_[b2].GeneralSphericalHarmonicsAcceleration(
+                t, dq, dq_norm, dq2, one_over_dq3);
+        acceleration_on_b1 += mu2 * effect;
+        acceleration_on_b2 -= mu1 * effect;
+      }
+    }
+  }
+
+  // :1412-1462.
+  int32_t ByMassiveBodyOnMasslessBodies(bool body1_is_oblate, double t, int b1,
+                                        std::vector<Vec3> const& positions,
+                                        std::vector<Vec3>& accelerations) const {
+    double const mu1 = bodies_[b1]->mu;
+    Vec3 const position1 = trajectories_[b1]->EvaluatePosition(t);
+    double const body1_collision_radius =
+        min_radius_tolerance * bodies_[b1]->min_radius;
+    int32_t error = kOk;
+    for (std::size_t b2 = 0; b2 < positions.size(); ++b2) {
+      Vec3 const dq = position1 - positions[b2];
+      double const dq2 = Norm2(dq);
+      double const dq_norm = std::sqrt(dq2);
+      error |= dq_norm > body1_collision_radius ? kOk : kOutOfRange;
+      double const one_over_dq3 = dq_norm / (dq2 * dq2);
+      double const mu1_over_dq3 = mu1 * one_over_dq3;
+      accelerations[b2] += dq * mu1_over_dq3;
+      if (body1_is_oblate) {
+        Vec3 const effect =
+            geopotentials_[b1].GeneralSphericalHarmonicsAcceleration(
+                t, -dq, dq_norm, dq2, one_over_dq3);
+        accelerations[b2] += mu1 * effect;
+      }
+    }
+    return error;
+  }
+
+  // :1071-1096, :1098-1116.
+  void AppendMassiveBodiesState(State const& state) {
+    double const time = state.time.value;
+    for (int i = 0; i < size(); ++i) {
+      Vec3 const q{state.positions[3 * i].value, state.positions[3 * i + 1].value,
+                   state.positions[3 * i + 2].value};
+      Vec3 const v{state.velocities[3 * i].value,
+                   state.velocities[3 * i + 1].value,
+                   state.velocities[3 * i + 2].value};
+      int32_t const status = trajectories_[i]->Append(time, q, v);
+      if (status != kOk) {
+        severe_status_ = status;
+      }
+    }
+  }
+
+  double step_;
+  std::vector<std::unique_ptr<Body>> bodies_;
+  std::vector<std::unique_ptr<ContinuousTrajectory>> trajectories_;
+  std::vector<Geopotential> geopotentials_;
+  std::vector<int> order_;  // internal index -> caller index.
+  int number_of_oblate_bodies_ = 0;
+  int number_of_spherical_bodies_ = 0;
+  std::unique_ptr<FixedStepInstance> instance_;
+  int32_t severe_status_ = kOk;
+};
+
+}  // namespace orc

