@@ -1,0 +1,184 @@
+// Acceleration routines of physics::Ephemeris as host/device functions over an
+// EphemerisView and one stage-table entry (all massive bodies evaluated at one
+// instant).
+#pragma once
+
+#include "pb_geopotential.cuh"
+#include "pb_math.cuh"
+#include "pb_model.h"
+
+namespace pb {
+
+PB_HD GeopotentialBody MakeGeopotentialBody(EphemerisView const& e,
+                                            int const b) {
+  DeviceBody const* const body = e.bodies + b;
+  GeopotentialBody g;
+  g.body = body;
+  g.degree_damping = e.dampings + body->damping_offset;
+  g.cos = e.cos + body->coefficient_offset;
+  g.sin = e.sin + body->coefficient_offset;
+  g.normalization = e.normalization;
+  return g;
+}
+
+// ContinuousTrajectory::FindPolynomialForInstantLocked +
+// EvaluatePositionLocked, physics/continuous_trajectory_body.hpp:686-695,
+// 860-885: the first segment with t <= t_max, evaluated at t - origin.
+PB_HD int FindSegment(double const* t_max, int const begin, int const end,
+                      double const t) {
+  int lo = begin;
+  int hi = end;
+  while (lo < hi) {
+    int const mid = (lo + hi) / 2;
+    if (t_max[mid] < t) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo < end ? lo : end - 1;
+}
+
+PB_HD Vec3 EvaluateSegment(EphemerisView const& e, int const segment,
+                           double const t) {
+  double const x = t - e.segment_origin[segment];
+  double const* const c =
+      e.segment_coefficients + static_cast<long long>(segment) * 3 *
+                                   kSegmentCoefficients;
+  int const degree = e.segment_degree[segment];
+  return {EstrinEvaluate<3>(c, degree, x), EstrinEvaluate<3>(c + 1, degree, x),
+          EstrinEvaluate<3>(c + 2, degree, x)};
+}
+
+// Fills one stage-table entry for body b at time t.
+PB_HD void FillStageEntry(EphemerisView const& e, int const b, double const t,
+                          double* const entry) {
+  int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
+                                  e.segment_offset[b + 1], t);
+  Vec3 const position = EvaluateSegment(e, segment, t);
+  entry[3 * b] = position.x;
+  entry[3 * b + 1] = position.y;
+  entry[3 * b + 2] = position.z;
+  int const slot = e.bodies[b].frame_slot;
+  if (slot >= 0) {
+    Vec3 x_hat, y_hat;
+    SurfaceFrameAxes(e.bodies[b], t, x_hat, y_hat);
+    double* const frame = entry + 3 * e.n_bodies + 6 * slot;
+    frame[0] = x_hat.x;
+    frame[1] = x_hat.y;
+    frame[2] = x_hat.z;
+    frame[3] = y_hat.x;
+    frame[4] = y_hat.y;
+    frame[5] = y_hat.z;
+  }
+}
+
+// Ephemeris::ComputeGravitationalAccelerationByAllMassiveBodiesOnMasslessBodies
+// for one probe, physics/ephemeris_body.hpp:1554-1591 with the inner routine
+// :1412-1462.  Returns the OR of the status codes (0 or 11).
+template<bool kUnrolled>
+PB_HD int32_t AccelerationOnMasslessBody(EphemerisView const& e,
+                                         double const* const stage,
+                                         Vec3 const& q, Vec3& acceleration) {
+  acceleration = {0.0, 0.0, 0.0};
+  int32_t error = 0;
+  for (int b1 = 0; b1 < e.n_bodies; ++b1) {
+    DeviceBody const& body1 = e.bodies[b1];
+    double const mu1 = body1.mu;
+    Vec3 const position1{stage[3 * b1], stage[3 * b1 + 1], stage[3 * b1 + 2]};
+    Vec3 const dq = position1 - q;
+    double const dq2 = Norm2(dq);
+    double const dq_norm = sqrt(dq2);
+    error |= dq_norm > body1.collision_radius ? 0 : 11;
+    double const one_over_dq3 = dq_norm / (dq2 * dq2);
+    double const mu1_over_dq3 = mu1 * one_over_dq3;
+    acceleration += dq * mu1_over_dq3;
+    if (b1 < e.n_oblate) {
+      GeopotentialBody const g = MakeGeopotentialBody(e, b1);
+      double const* const frame =
+          body1.frame_slot >= 0
+              ? stage + 3 * e.n_bodies + 6 * body1.frame_slot
+              : nullptr;
+      Vec3 const effect = GeneralSphericalHarmonicsAcceleration<kUnrolled>(
+          g, frame, -dq, dq_norm, dq2, one_over_dq3);
+      acceleration += mu1 * effect;
+    }
+  }
+  return error;
+}
+
+// ComputeGravitationalPotentialsOfAllMassiveBodies for one point,
+// ephemeris_body.hpp:1464-1501,1593-1621.
+PB_HD double PotentialOnMasslessBody(EphemerisView const& e,
+                                     double const* const stage, Vec3 const& q) {
+  double potential = 0.0;
+  for (int b1 = 0; b1 < e.n_bodies; ++b1) {
+    DeviceBody const& body1 = e.bodies[b1];
+    double const mu1 = body1.mu;
+    Vec3 const position1{stage[3 * b1], stage[3 * b1 + 1], stage[3 * b1 + 2]};
+    Vec3 const dq = position1 - q;
+    double const dq2 = Norm2(dq);
+    double const dq_norm = sqrt(dq2);
+    double const one_over_dq_norm = 1 / dq_norm;
+    potential -= mu1 * one_over_dq_norm;
+    if (b1 < e.n_oblate) {
+      double const one_over_dq3 =
+          one_over_dq_norm * one_over_dq_norm * one_over_dq_norm;
+      GeopotentialBody const g = MakeGeopotentialBody(e, b1);
+      double const* const frame =
+          body1.frame_slot >= 0
+              ? stage + 3 * e.n_bodies + 6 * body1.frame_slot
+              : nullptr;
+      double const effect = GeneralSphericalHarmonicsPotential(
+          g, frame, -dq, dq_norm, dq2, one_over_dq3);
+      potential += mu1 * effect;
+    }
+  }
+  return potential;
+}
+
+// One (b1, b2) interaction of
+// ComputeGravitationalAccelerationByMassiveBodyOnMassiveBodies,
+// ephemeris_body.hpp:1342-1410, b1 < b2 in internal order.  `frames` holds the
+// surface-frame axes of the bodies with a frame slot (6 doubles per slot).
+// Updates both accelerations (Newton's third law) in the reference's order.
+template<bool kUnrolled>
+PB_HD void MassivePairInteraction(EphemerisView const& e, int const b1,
+                                  int const b2, double const* const frames,
+                                  Vec3 const& position_of_b1,
+                                  Vec3 const& position_of_b2,
+                                  Vec3& acceleration_on_b1,
+                                  Vec3& acceleration_on_b2) {
+  DeviceBody const& body1 = e.bodies[b1];
+  DeviceBody const& body2 = e.bodies[b2];
+  double const mu1 = body1.mu;
+  double const mu2 = body2.mu;
+  Vec3 const dq = position_of_b1 - position_of_b2;
+  double const dq2 = Norm2(dq);
+  double const dq_norm = sqrt(dq2);
+  double const one_over_dq3 = dq_norm / (dq2 * dq2);
+  double const mu1_over_dq3 = mu1 * one_over_dq3;
+  acceleration_on_b2 += dq * mu1_over_dq3;
+  double const mu2_over_dq3 = mu2 * one_over_dq3;
+  acceleration_on_b1 -= dq * mu2_over_dq3;
+  if (body1.is_oblate) {
+    GeopotentialBody const g = MakeGeopotentialBody(e, b1);
+    double const* const frame =
+        body1.frame_slot >= 0 ? frames + 6 * body1.frame_slot : nullptr;
+    Vec3 const effect = GeneralSphericalHarmonicsAcceleration<kUnrolled>(
+        g, frame, -dq, dq_norm, dq2, one_over_dq3);
+    acceleration_on_b1 -= mu2 * effect;
+    acceleration_on_b2 += mu1 * effect;
+  }
+  if (body2.is_oblate) {
+    GeopotentialBody const g = MakeGeopotentialBody(e, b2);
+    double const* const frame =
+        body2.frame_slot >= 0 ? frames + 6 * body2.frame_slot : nullptr;
+    Vec3 const effect = GeneralSphericalHarmonicsAcceleration<kUnrolled>(
+        g, frame, dq, dq_norm, dq2, one_over_dq3);
+    acceleration_on_b1 += mu2 * effect;
+    acceleration_on_b2 -= mu1 * effect;
+  }
+}
+
+}  // namespace pb

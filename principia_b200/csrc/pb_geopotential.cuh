@@ -1,0 +1,707 @@
+// Spherical-harmonics acceleration and potential of an oblate body:
+// Geopotential::GeneralSphericalHarmonicsAcceleration / ...Potential,
+// physics/geopotential_body.hpp:740-895, with the damping of
+// physics/harmonic_damping_body.hpp:33-82.  Notation follows the reference's
+// documentation/Geopotential.pdf.
+//
+// Two code paths with the same arithmetic, operation for operation:
+//  * `GeopotentialUnrolled<max_degree, zonal>`: compile-time (n, m) loops, all
+//    recurrence state in registers -- the hot path (Earth at degree/order 10
+//    for LEO probes); instantiated for max_degree 2..kMaxUnrolledDegree.
+//  * `GeopotentialGeneric`: run-time loops, state in local memory -- any degree
+//    up to 50 (the Moon's degree-30 field at close range, Jupiter/Saturn J12).
+//
+// Summation order (part of the contract): terms are *evaluated*
+// by increasing degree then order, and *summed* by unary right folds
+// `(accelerations[orders] + ...)`, geopotential_body.hpp:410,535, i.e.
+// a0 + (a1 + (... + a_last)).  The per-order recurrences of one degree are
+// independent of the order terms, so all updates of a degree run first and
+// the terms are then accumulated from the highest order down, which is the
+// right fold without storing the terms.
+#pragma once
+
+#include <utility>
+
+#include "pb_math.cuh"
+#include "pb_model.h"
+
+namespace pb {
+
+constexpr int kMaxUnrolledDegree = 10;
+
+struct GeopotentialBody {
+  DeviceBody const* body;
+  Damping const* degree_damping;  // [n_damping].
+  double const* cos;
+  double const* sin;
+  double const* normalization;
+};
+
+// HarmonicDamping::ComputeDampedRadialQuantities, harmonic_damping_body.hpp:
+// 33-61.
+PB_HD void ComputeDampedRadialQuantities(Damping const& d, double const r_norm,
+                                         double const r2,
+                                         Vec3 const& r_normalized,
+                                         double const R_over_r,
+                                         double const R_prime,
+                                         double& sigma_R_over_r,
+                                         Vec3& grad_sigma_R) {
+  if (r_norm <= d.inner_threshold) {
+    sigma_R_over_r = R_over_r;
+    grad_sigma_R = R_prime * r_normalized;
+  } else {
+    double const r3 = r2 * r_norm;
+    double const c3r3 = d.c3 * r3;
+    double const c2r2 = d.c2 * r2;
+    double const c1r = d.c1 * r_norm;
+    double const sigma = c3r3 + c2r2 + c1r;
+    double const sigma_prime_r = 3 * c3r3 + 2 * c2r2 + c1r;
+    sigma_R_over_r = sigma * R_over_r;
+    grad_sigma_R = (sigma_prime_r * R_over_r + R_prime * sigma) * r_normalized;
+  }
+}
+
+// :63-82.
+PB_HD void ComputeDampedRadialQuantities(Damping const& d, double const r_norm,
+                                         double const r2, double const R_over_r,
+                                         double& sigma_R_over_r) {
+  if (r_norm <= d.inner_threshold) {
+    sigma_R_over_r = R_over_r;
+  } else {
+    double const r3 = r2 * r_norm;
+    double const c3r3 = d.c3 * r3;
+    double const c2r2 = d.c2 * r2;
+    double const c1r = d.c1 * r_norm;
+    double const sigma = c3r3 + c2r2 + c1r;
+    sigma_R_over_r = sigma * R_over_r;
+  }
+}
+
+// Geopotential::LimitingDegree, geopotential_body.hpp:910-922: partition point
+// of r_norm < outer_threshold over non-increasing thresholds.
+PB_HD int LimitingDegree(Damping const* degree_damping, int const n_damping,
+                         double const r_norm) {
+  if (!(fabs(r_norm) <= 1.7976931348623157e308)) {
+    return 2;
+  }
+  int lo = 0;
+  int hi = n_damping;
+  while (lo < hi) {
+    int const mid = (lo + hi) / 2;
+    if (r_norm < degree_damping[mid].outer_threshold) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+
+// Surface-frame axes at time t: FromSurfaceFrame(t) applied to (1,0,0) and
+// (0,1,0), geopotential_body.hpp:621-624, geometry/rotation_body.hpp:67-71,
+// 155-164,355-363, geometry/quaternion_body.hpp:119-125.
+PB_HD void SurfaceFrameAxes(DeviceBody const& body, double const t, Vec3& x_hat,
+                            Vec3& y_hat) {
+  double const angle = body.reference_angle +
+                       (t - body.reference_instant) * body.angular_frequency;
+  double const half_angle = 0.5 * angle;
+  double s, c;
+  CrSinCos(half_angle, s, c);
+  // AngleAxis(angle, z) = (c, s * (0, 0, 1)).
+  double const r_real = c;
+  Vec3 const r_imaginary = s * Vec3{0.0, 0.0, 1.0};
+  // q = q_ab * r.
+  double const l_real = body.q_ab_real;
+  Vec3 const l_imaginary = body.q_ab_imaginary;
+  double const q_real = l_real * r_real - Dot(l_imaginary, r_imaginary);
+  Vec3 const q_imaginary = l_real * r_imaginary + r_real * l_imaginary +
+                           Cross(l_imaginary, r_imaginary);
+  Vec3 const ex{1.0, 0.0, 0.0};
+  Vec3 const ey{0.0, 1.0, 0.0};
+  x_hat = ex + 2 * Cross(q_imaginary, Cross(q_imaginary, ex) + q_real * ex);
+  y_hat = ey + 2 * Cross(q_imaginary, Cross(q_imaginary, ey) + q_real * ey);
+}
+
+// The quantities of AllDegrees::InitializePrecomputations that do not depend on
+// (n, m), geopotential_body.hpp:575-667.
+struct GeopotentialSetup {
+  double r_norm;
+  double r2;
+  Vec3 r_normalized;
+  double sin_beta;
+  double cos_beta;
+  double cos_lambda;
+  double sin_lambda;
+  Vec3 grad_B_vector;
+  Vec3 grad_L_vector;
+  double R1_over_r;
+};
+
+PB_HD void InitializeSetup(DeviceBody const& body, Vec3 const& x_hat,
+                           Vec3 const& y_hat, Vec3 const& r,
+                           double const r_norm, double const r2,
+                           double const one_over_r3, GeopotentialSetup& p) {
+  Vec3 const z_hat = body.polar_axis;
+  p.r_norm = r_norm;
+  p.r2 = r2;
+  double const x = Dot(r, x_hat);
+  double const y = Dot(r, y_hat);
+  double const z = Dot(r, z_hat);
+  double const x2_plus_y2 = x * x + y * y;
+  double const r_equatorial = sqrt(x2_plus_y2);
+  double cos_lambda = 1;
+  double sin_lambda = 0;
+  if (r_equatorial > 0) {
+    double const one_over_r_equatorial = 1 / r_equatorial;
+    cos_lambda = x * one_over_r_equatorial;
+    sin_lambda = y * one_over_r_equatorial;
+  }
+  double const one_over_r_norm = 1 / r_norm;
+  p.r_normalized = r * one_over_r_norm;
+  p.cos_beta = r_equatorial * one_over_r_norm;
+  p.sin_beta = z * one_over_r_norm;
+  p.cos_lambda = cos_lambda;
+  p.sin_lambda = sin_lambda;
+  p.grad_B_vector = (-p.sin_beta * cos_lambda) * x_hat -
+                    (p.sin_beta * sin_lambda) * y_hat + p.cos_beta * z_hat;
+  p.grad_L_vector = cos_lambda * y_hat - sin_lambda * x_hat;
+  p.R1_over_r = body.reference_radius * one_over_r3;
+}
+
+// ===========================================================================
+// Generic path: run-time loops.
+
+struct GenericPrecomputations {
+  double R_over_r[kGeopotentialSize];
+  double cos_m_lambda[kGeopotentialSize];
+  double sin_m_lambda[kGeopotentialSize];
+  double cos_beta_to_the_m[kGeopotentialSize];
+  // Rolling rows n, n-1, n-2 of DmPn_of_sin_beta.
+  double P[3][kGeopotentialSize + 1];
+};
+
+// DegreeNOrderM::UpdatePrecomputations, geopotential_body.hpp:249-331.
+PB_HD void GenericUpdateOrder(int const n, int const m, double const sin_beta,
+                              GenericPrecomputations& p) {
+  double* const Pn = p.P[n % 3];
+  double const* const Pn1 = p.P[(n + 2) % 3];
+  double const* const Pn2 = p.P[(n + 1) % 3];
+  if (n == 2 && m == 1) {
+    Pn[2] = 3;
+    return;
+  }
+  if (m == n) {
+    if (m % 2 == 0) {
+      int const h = m / 2;
+      double const cos_h = p.cos_m_lambda[h];
+      double const sin_h = p.sin_m_lambda[h];
+      double const cos_beta_to_the_h = p.cos_beta_to_the_m[h];
+      p.sin_m_lambda[m] = 2 * sin_h * cos_h;
+      p.cos_m_lambda[m] = (cos_h + sin_h) * (cos_h - sin_h);
+      p.cos_beta_to_the_m[m] = cos_beta_to_the_h * cos_beta_to_the_h;
+    } else {
+      int const h1 = m / 2;
+      int const h2 = m - h1;
+      double const cos_h1 = p.cos_m_lambda[h1];
+      double const sin_h1 = p.sin_m_lambda[h1];
+      double const cos_beta_to_the_h1 = p.cos_beta_to_the_m[h1];
+      double const cos_h2 = p.cos_m_lambda[h2];
+      double const sin_h2 = p.sin_m_lambda[h2];
+      double const cos_beta_to_the_h2 = p.cos_beta_to_the_m[h2];
+      p.sin_m_lambda[m] = sin_h1 * cos_h2 + cos_h1 * sin_h2;
+      p.cos_m_lambda[m] = cos_h1 * cos_h2 - sin_h1 * sin_h2;
+      p.cos_beta_to_the_m[m] = cos_beta_to_the_h1 * cos_beta_to_the_h2;
+    }
+  }
+  if (m == 0) {
+    Pn[0] = ((2 * n - 1) * sin_beta * Pn1[0] - (n - 1) * Pn2[0]) / n;
+  }
+  if (m == n) {
+  } else if (m == n - 1) {
+    Pn[m + 1] = ((2 * n - 1) * (m + 1) * Pn1[m]) / n;
+  } else if (m == n - 2) {
+    Pn[m + 1] =
+        ((2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m])) / n;
+  } else {
+    Pn[m + 1] = ((2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m]) -
+                 (n - 1) * Pn2[m + 1]) /
+                n;
+  }
+}
+
+// DegreeNOrderM::Acceleration without the update, :130-204.
+PB_HD Vec3 OrderTermAcceleration(int const n, int const m, double const Pnm,
+                                 double const Pnm1, double const cos_m_lambda,
+                                 double const sin_m_lambda,
+                                 double const cos_beta_to_the_m,
+                                 double const cos_beta_to_the_m_minus_1,
+                                 double const Cnm, double const Snm,
+                                 double const normalization_factor,
+                                 double const sigma_R_over_r,
+                                 Vec3 const& grad_sigma_R,
+                                 GeopotentialSetup const& s) {
+  double const B = cos_beta_to_the_m * Pnm;
+  double grad_B_polynomials = 0;
+  if (m < n) {
+    grad_B_polynomials = s.cos_beta * cos_beta_to_the_m * Pnm1;
+  }
+  if (m > 0) {
+    grad_B_polynomials -= m * s.sin_beta * cos_beta_to_the_m_minus_1 * Pnm;
+  }
+  double L;
+  if (m == 0) {
+    L = Cnm;
+  } else {
+    L = Cnm * cos_m_lambda + Snm * sin_m_lambda;
+  }
+  Vec3 const BL_grad_R = (B * L) * grad_sigma_R;
+  Vec3 const RL_grad_B =
+      (sigma_R_over_r * L * grad_B_polynomials) * s.grad_B_vector;
+  Vec3 grad_RBL = BL_grad_R + RL_grad_B;
+  if (m > 0) {
+    Vec3 const RB_grad_L = (sigma_R_over_r * cos_beta_to_the_m_minus_1 * Pnm *
+                            m * (Snm * cos_m_lambda - Cnm * sin_m_lambda)) *
+                           s.grad_L_vector;
+    grad_RBL += RB_grad_L;
+  }
+  return normalization_factor * grad_RBL;
+}
+
+// DegreeNOrderM::Potential without the update, :206-247.
+PB_HD double OrderTermPotential(int const m, double const Pnm,
+                                double const cos_m_lambda,
+                                double const sin_m_lambda,
+                                double const cos_beta_to_the_m,
+                                double const Cnm, double const Snm,
+                                double const normalization_factor,
+                                double const sigma_R_over_r,
+                                double const r_norm) {
+  double const sigma_R = r_norm * sigma_R_over_r;
+  double const B = cos_beta_to_the_m * Pnm;
+  double L;
+  if (m == 0) {
+    L = Cnm;
+  } else {
+    L = Cnm * cos_m_lambda + Snm * sin_m_lambda;
+  }
+  return -normalization_factor * sigma_R * B * L;
+}
+
+PB_HD Vec3 GenericTerm(GeopotentialBody const& g, int const n, int const m,
+                       double const sigma_R_over_r, Vec3 const& grad_sigma_R,
+                       GeopotentialSetup const& s,
+                       GenericPrecomputations const& p) {
+  double const* const Pn = p.P[n % 3];
+  int const k = n * (n + 1) / 2 + m;
+  return OrderTermAcceleration(
+      n, m, Pn[m], m < n ? Pn[m + 1] : 0.0, p.cos_m_lambda[m],
+      p.sin_m_lambda[m], p.cos_beta_to_the_m[m],
+      m > 0 ? p.cos_beta_to_the_m[m - 1] : 0.0, g.cos[k], g.sin[k],
+      g.normalization[k], sigma_R_over_r, grad_sigma_R, s);
+}
+
+PB_HD double GenericTermPotential(GeopotentialBody const& g, int const n,
+                                  int const m, double const sigma_R_over_r,
+                                  GeopotentialSetup const& s,
+                                  GenericPrecomputations const& p) {
+  double const* const Pn = p.P[n % 3];
+  int const k = n * (n + 1) / 2 + m;
+  return OrderTermPotential(m, Pn[m], p.cos_m_lambda[m], p.sin_m_lambda[m],
+                            p.cos_beta_to_the_m[m], g.cos[k], g.sin[k],
+                            g.normalization[k], sigma_R_over_r, s.r_norm);
+}
+
+PB_HD void GenericInitialize(GeopotentialSetup const& s,
+                             GenericPrecomputations& p) {
+  p.R_over_r[1] = s.R1_over_r;
+  p.cos_m_lambda[1] = s.cos_lambda;
+  p.sin_m_lambda[1] = s.sin_lambda;
+  p.cos_beta_to_the_m[0] = 1;
+  p.cos_beta_to_the_m[1] = s.cos_beta;
+  p.P[0][0] = 1;           // DmPn(0, 0).
+  p.P[1][0] = s.sin_beta;  // DmPn(1, 0).
+  p.P[1][1] = 1;           // DmPn(1, 1).
+}
+
+// DegreeNAllOrders::UpdatePrecomputations, :476-499.
+PB_HD void GenericUpdateDegree(int const n, double const r2, double* R_over_r) {
+  if (n % 2 == 0) {
+    int const h = n / 2;
+    R_over_r[n] = R_over_r[h] * R_over_r[h] * r2;
+  } else {
+    int const h1 = n / 2;
+    int const h2 = n - h1;
+    R_over_r[n] = R_over_r[h1] * R_over_r[h2] * r2;
+  }
+}
+
+// AllDegrees::Acceleration, :501-536, for max_degree >= 2.
+PB_HD_NOINLINE Vec3 GeopotentialGenericAcceleration(
+    GeopotentialBody const& g, int const max_degree, bool const is_zonal,
+    GeopotentialSetup const& s) {
+  GenericPrecomputations p;
+  GenericInitialize(s, p);
+  Vec3 degree_sum[kGeopotentialSize];
+  for (int n = 2; n <= max_degree; ++n) {
+    int const size = is_zonal ? 1 : n + 1;
+    GenericUpdateDegree(n, s.r2, p.R_over_r);
+    double const R_over_r = p.R_over_r[n];
+    double const R_prime = -(n + 1) * R_over_r;
+    double sigma_R_over_r;
+    Vec3 grad_sigma_R;
+    if (n == 2 && size > 1) {
+      ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
+                                    s.r_normalized, R_over_r, R_prime,
+                                    sigma_R_over_r, grad_sigma_R);
+      GenericUpdateOrder(2, 0, s.sin_beta, p);
+      Vec3 const j2_acceleration =
+          GenericTerm(g, 2, 0, sigma_R_over_r, grad_sigma_R, s, p);
+      ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2,
+                                    s.r_normalized, R_over_r, R_prime,
+                                    sigma_R_over_r, grad_sigma_R);
+      GenericUpdateOrder(2, 1, s.sin_beta, p);
+      GenericUpdateOrder(2, 2, s.sin_beta, p);
+      Vec3 const c22_s22_acceleration =
+          GenericTerm(g, 2, 2, sigma_R_over_r, grad_sigma_R, s, p);
+      degree_sum[n] = j2_acceleration + c22_s22_acceleration;
+    } else {
+      ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+                                    s.r_normalized, R_over_r, R_prime,
+                                    sigma_R_over_r, grad_sigma_R);
+      for (int m = 0; m < size; ++m) {
+        GenericUpdateOrder(n, m, s.sin_beta, p);
+      }
+      Vec3 sum = GenericTerm(g, n, size - 1, sigma_R_over_r, grad_sigma_R, s, p);
+      for (int m = size - 2; m >= 0; --m) {
+        sum = GenericTerm(g, n, m, sigma_R_over_r, grad_sigma_R, s, p) + sum;
+      }
+      degree_sum[n] = sum;
+    }
+  }
+  // Degrees 0 and 1 contribute zero vectors to the fold.
+  Vec3 sum = degree_sum[max_degree];
+  for (int n = max_degree - 1; n >= 2; --n) {
+    sum = degree_sum[n] + sum;
+  }
+  Vec3 const zero{0.0, 0.0, 0.0};
+  sum = zero + sum;
+  sum = zero + sum;
+  return sum;
+}
+
+PB_HD_NOINLINE double GeopotentialGenericPotential(
+    GeopotentialBody const& g, int const max_degree, bool const is_zonal,
+    GeopotentialSetup const& s) {
+  GenericPrecomputations p;
+  GenericInitialize(s, p);
+  double degree_sum[kGeopotentialSize];
+  for (int n = 2; n <= max_degree; ++n) {
+    int const size = is_zonal ? 1 : n + 1;
+    GenericUpdateDegree(n, s.r2, p.R_over_r);
+    double const R_over_r = p.R_over_r[n];
+    double sigma_R_over_r;
+    if (n == 2 && size > 1) {
+      ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
+                                    R_over_r, sigma_R_over_r);
+      GenericUpdateOrder(2, 0, s.sin_beta, p);
+      double const j2_potential =
+          GenericTermPotential(g, 2, 0, sigma_R_over_r, s, p);
+      ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2, R_over_r,
+                                    sigma_R_over_r);
+      GenericUpdateOrder(2, 1, s.sin_beta, p);
+      GenericUpdateOrder(2, 2, s.sin_beta, p);
+      double const c22_s22_potential =
+          GenericTermPotential(g, 2, 2, sigma_R_over_r, s, p);
+      degree_sum[n] = j2_potential + c22_s22_potential;
+    } else {
+      ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+                                    R_over_r, sigma_R_over_r);
+      for (int m = 0; m < size; ++m) {
+        GenericUpdateOrder(n, m, s.sin_beta, p);
+      }
+      double sum = GenericTermPotential(g, n, size - 1, sigma_R_over_r, s, p);
+      for (int m = size - 2; m >= 0; --m) {
+        sum = GenericTermPotential(g, n, m, sigma_R_over_r, s, p) + sum;
+      }
+      degree_sum[n] = sum;
+    }
+  }
+  double sum = degree_sum[max_degree];
+  for (int n = max_degree - 1; n >= 2; --n) {
+    sum = degree_sum[n] + sum;
+  }
+  sum = 0.0 + sum;
+  sum = 0.0 + sum;
+  return sum;
+}
+
+// ===========================================================================
+// Unrolled path: compile-time (n, m).
+
+template<int... Is, typename F>
+PB_HD void StaticFor(std::integer_sequence<int, Is...>, F&& f) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+template<int kBegin, int kEnd, typename F>
+PB_HD void StaticForRange(F&& f) {
+  if constexpr (kBegin < kEnd) {
+    StaticFor(std::make_integer_sequence<int, kEnd - kBegin>{}, [&](auto i) {
+      f(std::integral_constant<int, kBegin + decltype(i)::value>{});
+    });
+  }
+}
+
+template<int kMaxDegree>
+struct UnrolledPrecomputations {
+  double R_over_r[kMaxDegree + 1];
+  double cos_m_lambda[kMaxDegree + 1];
+  double sin_m_lambda[kMaxDegree + 1];
+  double cos_beta_to_the_m[kMaxDegree + 1];
+  // Full triangle; every index is a compile-time constant, so after unrolling
+  // these are plain values with short live ranges (rows n-1, n-2).
+  double P[(kMaxDegree + 1) * (kMaxDegree + 2) / 2 + 1];
+};
+
+PB_HD constexpr int Tri(int const n, int const m) {
+  return n * (n + 1) / 2 + m;
+}
+
+template<int n, int m, int kMaxDegree>
+PB_HD void UnrolledUpdateOrder(double const sin_beta,
+                               UnrolledPrecomputations<kMaxDegree>& p) {
+  if constexpr (n == 2 && m == 1) {
+    p.P[Tri(2, 2)] = 3;
+  } else {
+    if constexpr (m == n) {
+      if constexpr (m % 2 == 0) {
+        constexpr int h = m / 2;
+        double const cos_h = p.cos_m_lambda[h];
+        double const sin_h = p.sin_m_lambda[h];
+        double const cos_beta_to_the_h = p.cos_beta_to_the_m[h];
+        p.sin_m_lambda[m] = 2 * sin_h * cos_h;
+        p.cos_m_lambda[m] = (cos_h + sin_h) * (cos_h - sin_h);
+        p.cos_beta_to_the_m[m] = cos_beta_to_the_h * cos_beta_to_the_h;
+      } else {
+        constexpr int h1 = m / 2;
+        constexpr int h2 = m - h1;
+        double const cos_h1 = p.cos_m_lambda[h1];
+        double const sin_h1 = p.sin_m_lambda[h1];
+        double const cos_beta_to_the_h1 = p.cos_beta_to_the_m[h1];
+        double const cos_h2 = p.cos_m_lambda[h2];
+        double const sin_h2 = p.sin_m_lambda[h2];
+        double const cos_beta_to_the_h2 = p.cos_beta_to_the_m[h2];
+        p.sin_m_lambda[m] = sin_h1 * cos_h2 + cos_h1 * sin_h2;
+        p.cos_m_lambda[m] = cos_h1 * cos_h2 - sin_h1 * sin_h2;
+        p.cos_beta_to_the_m[m] = cos_beta_to_the_h1 * cos_beta_to_the_h2;
+      }
+    }
+    if constexpr (m == 0) {
+      p.P[Tri(n, 0)] = ((2 * n - 1) * sin_beta * p.P[Tri(n - 1, 0)] -
+                        (n - 1) * p.P[Tri(n - 2, 0)]) /
+                       n;
+    }
+    if constexpr (m == n) {
+    } else if constexpr (m == n - 1) {
+      p.P[Tri(n, m + 1)] = ((2 * n - 1) * (m + 1) * p.P[Tri(n - 1, m)]) / n;
+    } else if constexpr (m == n - 2) {
+      p.P[Tri(n, m + 1)] =
+          ((2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
+                          (m + 1) * p.P[Tri(n - 1, m)])) /
+          n;
+    } else {
+      p.P[Tri(n, m + 1)] =
+          ((2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
+                          (m + 1) * p.P[Tri(n - 1, m)]) -
+           (n - 1) * p.P[Tri(n - 2, m + 1)]) /
+          n;
+    }
+  }
+}
+
+template<int n, int m, int kMaxDegree>
+PB_HD Vec3 UnrolledTerm(GeopotentialBody const& g, double const sigma_R_over_r,
+                        Vec3 const& grad_sigma_R, GeopotentialSetup const& s,
+                        UnrolledPrecomputations<kMaxDegree> const& p) {
+  constexpr int k = Tri(n, m);
+  double Pnm1 = 0.0;
+  if constexpr (m < n) {
+    Pnm1 = p.P[Tri(n, m + 1)];
+  }
+  double cos_beta_to_the_m_minus_1 = 0.0;
+  if constexpr (m > 0) {
+    cos_beta_to_the_m_minus_1 = p.cos_beta_to_the_m[m - 1];
+  }
+  return OrderTermAcceleration(n, m, p.P[k], Pnm1, p.cos_m_lambda[m],
+                               p.sin_m_lambda[m], p.cos_beta_to_the_m[m],
+                               cos_beta_to_the_m_minus_1, g.cos[k], g.sin[k],
+                               g.normalization[k], sigma_R_over_r,
+                               grad_sigma_R, s);
+}
+
+template<int kMaxDegree, bool kZonal>
+PB_HD Vec3 GeopotentialUnrolledAcceleration(GeopotentialBody const& g,
+                                            GeopotentialSetup const& s) {
+  UnrolledPrecomputations<kMaxDegree> p;
+  p.R_over_r[1] = s.R1_over_r;
+  p.cos_m_lambda[1] = s.cos_lambda;
+  p.sin_m_lambda[1] = s.sin_lambda;
+  p.cos_beta_to_the_m[0] = 1;
+  p.cos_beta_to_the_m[1] = s.cos_beta;
+  p.P[Tri(0, 0)] = 1;
+  p.P[Tri(1, 0)] = s.sin_beta;
+  p.P[Tri(1, 1)] = 1;
+  Vec3 degree_sum[kMaxDegree + 1];
+  StaticForRange<2, kMaxDegree + 1>([&](auto n_constant) {
+    constexpr int n = decltype(n_constant)::value;
+    constexpr int size = kZonal ? 1 : n + 1;
+    if constexpr (n % 2 == 0) {
+      constexpr int h = n / 2;
+      p.R_over_r[n] = p.R_over_r[h] * p.R_over_r[h] * s.r2;
+    } else {
+      constexpr int h1 = n / 2;
+      constexpr int h2 = n - h1;
+      p.R_over_r[n] = p.R_over_r[h1] * p.R_over_r[h2] * s.r2;
+    }
+    double const R_over_r = p.R_over_r[n];
+    double const R_prime = -(n + 1) * R_over_r;
+    double sigma_R_over_r;
+    Vec3 grad_sigma_R;
+    if constexpr (n == 2 && size > 1) {
+      ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
+                                    s.r_normalized, R_over_r, R_prime,
+                                    sigma_R_over_r, grad_sigma_R);
+      UnrolledUpdateOrder<2, 0>(s.sin_beta, p);
+      Vec3 const j2_acceleration =
+          UnrolledTerm<2, 0>(g, sigma_R_over_r, grad_sigma_R, s, p);
+      ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2,
+                                    s.r_normalized, R_over_r, R_prime,
+                                    sigma_R_over_r, grad_sigma_R);
+      UnrolledUpdateOrder<2, 1>(s.sin_beta, p);
+      UnrolledUpdateOrder<2, 2>(s.sin_beta, p);
+      Vec3 const c22_s22_acceleration =
+          UnrolledTerm<2, 2>(g, sigma_R_over_r, grad_sigma_R, s, p);
+      degree_sum[n] = j2_acceleration + c22_s22_acceleration;
+    } else {
+      ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+                                    s.r_normalized, R_over_r, R_prime,
+                                    sigma_R_over_r, grad_sigma_R);
+      StaticForRange<0, size>([&](auto m_constant) {
+        UnrolledUpdateOrder<n, decltype(m_constant)::value>(s.sin_beta, p);
+      });
+      Vec3 sum = UnrolledTerm<n, size - 1>(g, sigma_R_over_r, grad_sigma_R, s, p);
+      StaticForRange<0, size - 1>([&](auto i_constant) {
+        constexpr int m = size - 2 - decltype(i_constant)::value;
+        sum = UnrolledTerm<n, m>(g, sigma_R_over_r, grad_sigma_R, s, p) + sum;
+      });
+      degree_sum[n] = sum;
+    }
+  });
+  Vec3 sum = degree_sum[kMaxDegree];
+  StaticForRange<0, kMaxDegree - 2>([&](auto i_constant) {
+    constexpr int n = kMaxDegree - 1 - decltype(i_constant)::value;
+    sum = degree_sum[n] + sum;
+  });
+  Vec3 const zero{0.0, 0.0, 0.0};
+  sum = zero + sum;
+  sum = zero + sum;
+  return sum;
+}
+
+template<bool kZonal>
+PB_HD Vec3 GeopotentialUnrolledDispatch(GeopotentialBody const& g,
+                                        int const max_degree,
+                                        GeopotentialSetup const& s) {
+  switch (max_degree) {
+    case 2: return GeopotentialUnrolledAcceleration<2, kZonal>(g, s);
+    case 3: return GeopotentialUnrolledAcceleration<3, kZonal>(g, s);
+    case 4: return GeopotentialUnrolledAcceleration<4, kZonal>(g, s);
+    case 5: return GeopotentialUnrolledAcceleration<5, kZonal>(g, s);
+    case 6: return GeopotentialUnrolledAcceleration<6, kZonal>(g, s);
+    case 7: return GeopotentialUnrolledAcceleration<7, kZonal>(g, s);
+    case 8: return GeopotentialUnrolledAcceleration<8, kZonal>(g, s);
+    case 9: return GeopotentialUnrolledAcceleration<9, kZonal>(g, s);
+    default: return GeopotentialUnrolledAcceleration<10, kZonal>(g, s);
+  }
+}
+
+// ===========================================================================
+// Entry points.
+
+// Geopotential::GeneralSphericalHarmonicsAcceleration, :740-813.  `frame` holds
+// the surface-frame x and y axes at the evaluation time (6 doubles) when the
+// body has a frame slot; zonal evaluation uses the body's fixed axes.
+// kUnrolled selects the register-resident path for max_degree <= 10.
+template<bool kUnrolled>
+PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
+                                                 double const* frame,
+                                                 Vec3 const& r,
+                                                 double const r_norm,
+                                                 double const r2,
+                                                 double const one_over_r3) {
+  if (r_norm != r_norm) {
+    double const nan = r_norm;
+    Vec3 const zero{0.0, 0.0, 0.0};
+    return nan * zero;
+  }
+  DeviceBody const& body = *g.body;
+  int const max_degree =
+      LimitingDegree(g.degree_damping, body.n_damping, r_norm) - 1;
+  if (max_degree == 1) {
+    return {0.0, 0.0, 0.0};
+  }
+  bool const is_zonal =
+      body.is_zonal || r_norm > body.sectoral.outer_threshold;
+  Vec3 x_hat, y_hat;
+  if (is_zonal) {
+    x_hat = body.equatorial;
+    y_hat = body.biequatorial;
+  } else {
+    x_hat = {frame[0], frame[1], frame[2]};
+    y_hat = {frame[3], frame[4], frame[5]};
+  }
+  GeopotentialSetup s;
+  InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
+  if constexpr (kUnrolled) {
+    if (max_degree <= kMaxUnrolledDegree) {
+      if (is_zonal) {
+        return GeopotentialUnrolledDispatch<true>(g, max_degree, s);
+      } else {
+        return GeopotentialUnrolledDispatch<false>(g, max_degree, s);
+      }
+    }
+  }
+  return GeopotentialGenericAcceleration(g, max_degree, is_zonal, s);
+}
+
+// Geopotential::GeneralSphericalHarmonicsPotential, :822-895.
+PB_HD double GeneralSphericalHarmonicsPotential(GeopotentialBody const& g,
+                                                double const* frame,
+                                                Vec3 const& r,
+                                                double const r_norm,
+                                                double const r2,
+                                                double const one_over_r3) {
+  if (r_norm != r_norm) {
+    return r_norm;
+  }
+  DeviceBody const& body = *g.body;
+  int const max_degree =
+      LimitingDegree(g.degree_damping, body.n_damping, r_norm) - 1;
+  if (max_degree == 1) {
+    return 0.0;
+  }
+  bool const is_zonal =
+      body.is_zonal || r_norm > body.sectoral.outer_threshold;
+  Vec3 x_hat, y_hat;
+  if (is_zonal) {
+    x_hat = body.equatorial;
+    y_hat = body.biequatorial;
+  } else {
+    x_hat = {frame[0], frame[1], frame[2]};
+    y_hat = {frame[3], frame[4], frame[5]};
+  }
+  GeopotentialSetup s;
+  InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
+  return GeopotentialGenericPotential(g, max_degree, is_zonal, s);
+}
+
+}  // namespace pb

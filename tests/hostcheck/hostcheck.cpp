@@ -1,0 +1,135 @@
+// TEST HARNESS (not shipped, not a fallback): compiles the product's
+// host/device headers for the HOST with g++ -ffp-contract=off so that the
+// arithmetic of the device functions can be compared bit for bit with the
+// oracle here, on the CPU-only build box, before GPU time is spent.  The
+// product library never links this file.
+#include <cstring>
+#include <vector>
+
+#include "../../principia_b200/csrc/pb_accel.cuh"
+#include "../../principia_b200/csrc/pb_host_model.hpp"
+
+using namespace pb;
+
+struct hc_model {
+  HostModel model;
+  std::vector<double> normalization;
+  std::vector<int32_t> segment_offset;
+  EphemerisView view;
+};
+
+extern "C" {
+
+void hc_cr_sincos(double x, double* s, double* c) { CrSinCos(x, *s, *c); }
+double hc_cr_root4(double x) { return CrRoot4(x); }
+double hc_estrin(double const* c, int32_t degree, double x) {
+  return EstrinEvaluate<1>(c, degree, x);
+}
+double hc_pow_int(double x, int32_t k) { return PowInt(x, k); }
+
+int32_t hc_model_create(int32_t n, pb_body_t const* bodies, double tolerance,
+                        hc_model** out) {
+  auto* m = new hc_model;
+  int32_t const status = BuildHostModel(n, bodies, tolerance, m->model);
+  if (status != PB_OK) {
+    delete m;
+    return status;
+  }
+  m->normalization.assign(pb_legendre_normalization_factor,
+                          pb_legendre_normalization_factor + 51 * 52 / 2);
+  m->segment_offset.assign(n + 1, 0);
+  EphemerisView& v = m->view;
+  std::memset(&v, 0, sizeof(v));
+  v.n_bodies = n;
+  v.n_oblate = m->model.n_oblate;
+  v.n_frames = m->model.n_frames;
+  v.stage_stride = StageStride(n, v.n_frames);
+  v.bodies = m->model.bodies.data();
+  v.dampings = m->model.dampings.data();
+  v.cos = m->model.cos.data();
+  v.sin = m->model.sin.data();
+  v.normalization = m->normalization.data();
+  *out = m;
+  return PB_OK;
+}
+void hc_model_destroy(hc_model* m) { delete m; }
+
+int32_t hc_model_order(hc_model const* m, int32_t* order, int32_t* n_oblate) {
+  std::memcpy(order, m->model.order.data(),
+              m->model.order.size() * sizeof(int32_t));
+  *n_oblate = m->model.n_oblate;
+  return PB_OK;
+}
+
+int32_t hc_model_damping(hc_model const* m, int32_t body, int32_t* n_degrees,
+                         double* inner, double* sectoral_inner) {
+  DeviceBody const& b = m->model.bodies[m->model.internal_of_caller[body]];
+  if (!b.is_oblate) {
+    return PB_INVALID_ARGUMENT;
+  }
+  *n_degrees = b.n_damping;
+  for (int i = 0; i < b.n_damping; ++i) {
+    inner[i] = m->model.dampings[b.damping_offset + i].inner_threshold;
+  }
+  *sectoral_inner = b.sectoral.inner_threshold;
+  return PB_OK;
+}
+
+// Geopotential acceleration of caller body `body` on displacement r at time t.
+int32_t hc_geopotential_acceleration(hc_model const* m, int32_t body, double t,
+                                     double const* r, int32_t unrolled,
+                                     double* out) {
+  int const b = m->model.internal_of_caller[body];
+  GeopotentialBody const g = MakeGeopotentialBody(m->view, b);
+  Vec3 x_hat, y_hat;
+  double frame[6] = {};
+  if (g.body->frame_slot >= 0) {
+    SurfaceFrameAxes(*g.body, t, x_hat, y_hat);
+    frame[0] = x_hat.x; frame[1] = x_hat.y; frame[2] = x_hat.z;
+    frame[3] = y_hat.x; frame[4] = y_hat.y; frame[5] = y_hat.z;
+  }
+  Vec3 const rv{r[0], r[1], r[2]};
+  double const r2 = Norm2(rv);
+  double const r_norm = sqrt(r2);
+  double const one_over_r3 = r_norm / (r2 * r2);
+  Vec3 const a =
+      unrolled ? GeneralSphericalHarmonicsAcceleration<true>(
+                     g, frame, rv, r_norm, r2, one_over_r3)
+               : GeneralSphericalHarmonicsAcceleration<false>(
+                     g, frame, rv, r_norm, r2, one_over_r3);
+  out[0] = a.x; out[1] = a.y; out[2] = a.z;
+  return PB_OK;
+}
+
+// Massless acceleration + potential given the massive positions (caller order)
+// at time t (frames computed here).
+int32_t hc_acceleration_on_massless_body(hc_model const* m, double t,
+                                         double const* positions,
+                                         double const* q, int32_t unrolled,
+                                         double* a, double* potential) {
+  EphemerisView const& v = m->view;
+  std::vector<double> stage(v.stage_stride);
+  for (int b = 0; b < v.n_bodies; ++b) {
+    int const caller = m->model.order[b];
+    for (int c = 0; c < 3; ++c) {
+      stage[3 * b + c] = positions[3 * caller + c];
+    }
+    if (v.bodies[b].frame_slot >= 0) {
+      Vec3 x_hat, y_hat;
+      SurfaceFrameAxes(v.bodies[b], t, x_hat, y_hat);
+      double* frame = stage.data() + 3 * v.n_bodies + 6 * v.bodies[b].frame_slot;
+      frame[0] = x_hat.x; frame[1] = x_hat.y; frame[2] = x_hat.z;
+      frame[3] = y_hat.x; frame[4] = y_hat.y; frame[5] = y_hat.z;
+    }
+  }
+  Vec3 acc;
+  Vec3 const qv{q[0], q[1], q[2]};
+  int32_t const error =
+      unrolled ? AccelerationOnMasslessBody<true>(v, stage.data(), qv, acc)
+               : AccelerationOnMasslessBody<false>(v, stage.data(), qv, acc);
+  a[0] = acc.x; a[1] = acc.y; a[2] = acc.z;
+  *potential = PotentialOnMasslessBody(v, stage.data(), qv);
+  return error;
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+"""CPU-only: the product's host/device arithmetic headers (compiled for the host
+by tests/hostcheck) against the oracle, bit for bit.  Catches logic and
+operation-order errors before GPU time is spent; the `-m gpu` tests then check
+the same functions as compiled by nvcc for sm_100a.
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from principia_b200 import _capi
+from principia_b200.solar_system import SolarSystem
+
+import oracle_lib
+from oracle_lib import OracleEphemeris
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_d, _i32, _vp = ctypes.c_double, ctypes.c_int32, ctypes.c_void_p
+_dp, _i32p = _capi.c_double_p, _capi.c_int32_p
+
+
+@pytest.fixture(scope='module')
+def hc():
+  directory = os.path.join(HERE, 'hostcheck')
+  subprocess.check_call(
+      ['/usr/bin/g++', '-std=c++17', '-O2', '-ffp-contract=off', '-mfma',
+       '-fPIC', '-shared', '-w', '-o', 'libhostcheck.so', 'hostcheck.cpp'],
+      cwd=directory)
+  lib = ctypes.CDLL(os.path.join(directory, 'libhostcheck.so'))
+  lib.hc_cr_sincos.argtypes = [_d, _dp, _dp]
+  lib.hc_cr_root4.restype = _d
+  lib.hc_cr_root4.argtypes = [_d]
+  lib.hc_estrin.restype = _d
+  lib.hc_estrin.argtypes = [_dp, _i32, _d]
+  lib.hc_pow_int.restype = _d
+  lib.hc_pow_int.argtypes = [_d, _i32]
+  lib.hc_model_create.argtypes = [_i32, ctypes.POINTER(_capi.Body), _d,
+                                  ctypes.POINTER(_vp)]
+  lib.hc_model_destroy.argtypes = [_vp]
+  lib.hc_model_order.argtypes = [_vp, _i32p, _i32p]
+  lib.hc_model_damping.argtypes = [_vp, _i32, _i32p, _dp, _dp]
+  lib.hc_geopotential_acceleration.argtypes = [_vp, _i32, _d, _dp, _i32, _dp]
+  lib.hc_acceleration_on_massless_body.argtypes = [_vp, _d, _dp, _dp, _i32,
+                                                   _dp, _dp]
+  return lib
+
+
+def make_model(hc, system, tolerance):
+  bodies, keep = system.c_bodies()
+  handle = _vp()
+  assert hc.hc_model_create(len(system.bodies), bodies, tolerance,
+                            ctypes.byref(handle)) == 0
+  return handle, keep
+
+
+def test_correctly_rounded_sincos_and_root(hc):
+  orc = oracle_lib.library()
+  rng = np.random.default_rng(7)
+  xs = np.concatenate([
+      rng.uniform(-10, 10, 50000), rng.uniform(-1e5, 1e5, 50000),
+      rng.uniform(-2e9, 2e9, 20000), 10.0**rng.uniform(-300, 0, 5000),
+      np.arange(0, 100) * (math.pi / 2), [0.0, -0.0]])
+  s, c = _d(), _d()
+  for x in xs:
+    hc.hc_cr_sincos(x, s, c)
+    assert s.value == orc.orc_cr_sin(x), x
+    assert c.value == orc.orc_cr_cos(x), x
+  for x in np.concatenate([10.0**rng.uniform(-30, 30, 100000),
+                           rng.uniform(0.5, 2, 20000), [1.0, 16.0, 81.0]]):
+    assert hc.hc_cr_root4(x) == orc.orc_root(4, x), x
+  assert hc.hc_cr_root4(0.0) == 0.0
+  assert hc.hc_cr_root4(math.inf) == math.inf
+
+
+def test_estrin_matches_oracle(hc):
+  orc = oracle_lib.library()
+  rng = np.random.default_rng(3)
+  for degree in range(0, 18):
+    for _ in range(200):
+      c = rng.normal(size=18) * 10.0**rng.uniform(-5, 5, 18)
+      x = rng.uniform(-3000, 3000)
+      assert (hc.hc_estrin(oracle_lib.dptr(c), degree, x) ==
+              orc.orc_estrin(oracle_lib.dptr(c), degree, x))
+  for k in range(0, 32):
+    x = rng.uniform(0.1, 3)
+    expected = x
+    # Russian peasant as the reference writes it.
+    def peasant(x, e):
+      if e == 0:
+        return 1.0
+      if e == 1:
+        return x
+      y = peasant(x, e // 2)
+      y2 = y * y
+      return y2 * x if e % 2 else y2
+    assert hc.hc_pow_int(x, k) == peasant(x, k)
+
+
+def test_model_order_and_dampings_match_oracle(hc):
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  oracle = OracleEphemeris(system)
+  handle, keep = make_model(hc, system, 2.0**-24)
+  order = np.zeros(len(system.bodies), dtype=np.int32)
+  n_oblate = _i32()
+  hc.hc_model_order(handle, order.ctypes.data_as(_i32p), n_oblate)
+  expected_order, expected_oblate = oracle.internal_order()
+  assert list(order) == list(expected_order)
+  assert n_oblate.value == expected_oblate
+  for i, b in enumerate(system.bodies):
+    if not b['oblate']:
+      continue
+    n = _i32()
+    inner = np.zeros(51)
+    sectoral = _d()
+    assert hc.hc_model_damping(handle, i, n, oracle_lib.dptr(inner),
+                               sectoral) == 0
+    expected_inner, expected_sectoral = oracle.damping(i)
+    assert list(inner[:n.value]) == list(expected_inner), b['name']
+    assert sectoral.value == expected_sectoral
+  hc.hc_model_destroy(handle)
+
+
+@pytest.mark.parametrize('unrolled', [0, 1])
+def test_geopotential_matches_oracle_bitwise(hc, unrolled):
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  oracle = OracleEphemeris(system)
+  handle, keep = make_model(hc, system, 2.0**-24)
+  rng = np.random.default_rng(42)
+  out = np.zeros(3)
+  checked = 0
+  for i, b in enumerate(system.bodies):
+    if not b['oblate']:
+      continue
+    inner, sectoral = oracle.damping(i)
+    radius = b['mean_radius']
+    # Distances from just above the surface to beyond every threshold, so that
+    # every limiting degree, the damped zones and the zonal switch are hit.
+    finite = [x for x in inner if math.isfinite(x)] + [radius]
+    far = 4 * max(finite)
+    n_points = 60 if b['degree'] > 12 else 150
+    for _ in range(n_points):
+      distance = math.exp(rng.uniform(math.log(1.01 * radius), math.log(far)))
+      direction = rng.normal(size=3)
+      r = distance * direction / np.linalg.norm(direction)
+      t = rng.uniform(-1e6, 1e8)
+      hc.hc_geopotential_acceleration(handle, i, t, oracle_lib.dptr(r),
+                                      unrolled, oracle_lib.dptr(out))
+      expected = oracle.geopotential_acceleration(i, t, r)
+      assert list(out) == list(expected), (b['name'], distance)
+      checked += 1
+    # Poles and equator (r_equatorial == 0 branch).
+    for r in ([0.0, 0.0, 2 * radius], [2 * radius, 0.0, 0.0]):
+      r = np.array(r)
+      hc.hc_geopotential_acceleration(handle, i, 0.0, oracle_lib.dptr(r),
+                                      unrolled, oracle_lib.dptr(out))
+      assert list(out) == list(oracle.geopotential_acceleration(i, 0.0, r))
+  assert checked > 1000
+  hc.hc_model_destroy(handle)
+
+
+@pytest.mark.parametrize('unrolled', [0, 1])
+def test_massless_acceleration_and_potential_match_oracle(hc, unrolled):
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  oracle = OracleEphemeris(system)
+  assert oracle.prolong(86400.0) == 0
+  handle, keep = make_model(hc, system, 2.0**-24)
+  rng = np.random.default_rng(5)
+  a = np.zeros(3)
+  potential = _d()
+  names = system.names()
+  for _ in range(300):
+    t = rng.uniform(0, 86400.0)
+    positions = oracle.evaluate_all_positions(t)
+    centre = positions[names.index(rng.choice(['Earth', 'Moon', 'Mars',
+                                                'Jupiter', 'Sun']))]
+    distance = math.exp(rng.uniform(math.log(7e6), math.log(1e9)))
+    direction = rng.normal(size=3)
+    q = centre + distance * direction / np.linalg.norm(direction)
+    error = hc.hc_acceleration_on_massless_body(
+        handle, t, oracle_lib.dptr(positions), oracle_lib.dptr(q), unrolled,
+        oracle_lib.dptr(a), potential)
+    expected, status = oracle.acceleration_on_massless_bodies(
+        t, q.reshape(3, 1))
+    assert list(a) == list(expected.ravel())
+    assert error == status
+    assert potential.value == oracle.potential(t, q.reshape(3, 1))[0]
+  # A collision: inside the Earth.
+  positions = oracle.evaluate_all_positions(0.0)
+  q = positions[names.index('Earth')] + np.array([1e6, 0.0, 0.0])
+  error = hc.hc_acceleration_on_massless_body(
+      handle, 0.0, oracle_lib.dptr(positions), oracle_lib.dptr(q), unrolled,
+      oracle_lib.dptr(a), potential)
+  assert error == _capi.PB_OUT_OF_RANGE
+  hc.hc_model_destroy(handle)
