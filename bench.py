@@ -1,0 +1,364 @@
+#!/usr/bin/env python3
+"""Headline benchmark: BASELINE.json config 2 -- 10^5 massless LEO probes per GPU
+in the 34-body Sol field with the Earth's degree/order-10 geopotential,
+fixed-step BlanesMoan2002SRKN14A at 10 s (Ephemeris::FlowWithFixedStep).
+
+One bench "step" = one FlowWithFixedStep call advancing every probe of the rank
+by FLOW_STEPS integrator steps (14 right-hand-side evaluations each).
+
+  python bench.py --gpus N --steps K --warmup W          (this engine)
+  python bench.py --impl reference ...                   (CPU arm, see below)
+
+`value`: probe-RKN-stages/s, whole job, state resident in HBM.
+`e2e`:   the same through the host-buffer C-ABI call (pb_flow_with_fixed_step):
+         pinned host state -> HBM -> flow -> host, every step.
+`roofline`: FP64 pipe.  achieved = algorithmic flops of one flow-kernel launch
+         (principia_b200/flops.py) / its CUDA-event duration; peak = DFMA rate
+         measured in this run (MEASURED_PEAKS.json has no FP64 figure).
+`cpu_baseline` / `--impl reference`: the reference cannot be built in this
+         image, so the CPU arm is the oracle -- the restatement of
+         the reference's algorithm -- on all host threads, one integrator
+         instance per thread over a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+PROBES_PER_GPU = 100000
+FLOW_STEPS = 100          # Integrator steps per bench step.
+STEP_SECONDS = 10.0
+EVALUATIONS = 14          # BlanesMoan2002SRKN14A.
+METRIC = 'massless_probe_rkn_stages_per_second'
+UNIT = 'probe-stages/s'
+WORKLOAD = ('config 2: 10^5 LEO probes per GPU, Sol 34 bodies, Earth '
+            'geopotential 10x10, BlanesMoan2002SRKN14A h=10 s')
+
+
+class ClockSampler:
+  """nvidia-smi clocks during the timed region (B200_PROFILING.md)."""
+
+  def __init__(self, index):
+    self.index = index
+    self.process = None
+    self.lines = []
+
+  def start(self):
+    try:
+      self.process = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.index),
+           '--query-gpu=clocks.sm,clocks.max.sm,power.draw,'
+           'clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,'
+           'clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap',
+           '--format=csv,noheader,nounits', '-lms', '200'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.process = None
+
+  def _read(self):
+    for line in self.process.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.process is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    time.sleep(0.25)
+    self.process.terminate()
+    self.thread.join(timeout=2)
+    sm, sm_max, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(',')]
+      if len(parts) < 7:
+        continue
+      try:
+        sm.append(float(parts[0]))
+        sm_max.append(float(parts[1]))
+      except ValueError:
+        continue
+      for name, value in zip(names, parts[3:7]):
+        if value.lower().startswith('active'):
+          reasons.add(name)
+    return {'sm_mhz': float(np.median(sm)) if sm else None,
+            'sm_max_mhz': max(sm_max) if sm_max else None,
+            'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def host_cores():
+  return len(os.sched_getaffinity(0))
+
+
+def make_workload(n, seed):
+  from principia_b200 import workloads
+  system = workloads.sol_system()
+  earth = system.bodies[system.index('Earth')]
+  state = workloads.leo_probes(n, earth['q'], earth['v'], earth['mu'], seed)
+  return system, state
+
+
+def oracle_with_golden_segments(system):
+  sys.path.insert(0, os.path.join(REPO, 'tests'))
+  from oracle_lib import OracleEphemeris
+  from principia_b200 import workloads
+  oracle = OracleEphemeris(system)
+  for body, segments in enumerate(workloads.load_sol_ephemeris_segments()):
+    oracle.append_segments(body, segments)
+  return oracle
+
+
+def cpu_flow(oracle, state, flow_steps, threads):
+  """Times one CPU FlowWithFixedStep over `state`; returns seconds."""
+  from principia_b200 import _capi
+  time_dp = np.zeros(2)
+  t0 = time.perf_counter()
+  oracle.flow_with_fixed_step(_capi.BLANES_MOAN_2002_SRKN_14A, STEP_SECONDS,
+                              flow_steps * STEP_SECONDS, state, time_dp,
+                              threads=threads)
+  return time.perf_counter() - t0
+
+
+def cpu_sample_size(oracle, system, threads, target_seconds):
+  """Probes per CPU step such that one step costs about target_seconds."""
+  _, probe = make_workload(threads * 4, seed=7)
+  seconds = cpu_flow(oracle, probe, 10, threads)
+  per_probe_stage = seconds / (threads * 4 * 10 * EVALUATIONS)
+  n = int(target_seconds / (per_probe_stage * FLOW_STEPS * EVALUATIONS))
+  return max(threads, (n // threads) * threads)
+
+
+def run_reference(args):
+  """CPU arm: the oracle on all host threads, bounded sample per step."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  threads = host_cores()
+  system, _ = make_workload(8, 42)
+  oracle = oracle_with_golden_segments(system)
+  n = cpu_sample_size(oracle, system, threads, target_seconds=8.0)
+  _, state0 = make_workload(n, 42)
+  for _ in range(min(args.warmup, 1)):
+    cpu_flow(oracle, state0[:, :threads * 2].copy(), 10, threads)
+  total = 0.0
+  for _ in range(args.steps):
+    total += cpu_flow(oracle, state0.copy(), FLOW_STEPS, threads)
+  stages = args.steps * n * FLOW_STEPS * EVALUATIONS
+  value = stages / total
+  sample = ('%d probes x %d SRKN14A steps per bench step (bounded sample of the '
+            '10^5-probe workload), oracle restatement, OpenMP %d threads, one '
+            'integrator instance per thread' % (n, FLOW_STEPS, threads))
+  print(json.dumps({
+      'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+      'data': 'synthetic',
+      'config': {'workload': WORKLOAD, 'probes_per_step': n,
+                 'integrator_steps_per_step': FLOW_STEPS},
+      'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads,
+                       'kind': 'port', 'sample': sample},
+      'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0}}))
+
+
+def run_native(args):
+  import torch
+  import torch.distributed as dist
+  from principia_b200 import _capi, flops, workloads
+  from principia_b200.ephemeris import (Ephemeris, kernel_launch_count,
+                                        measure_fp64_peak)
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py: no CUDA device; there is no CPU fallback '
+                     '(use --impl reference for the CPU arm)')
+  torch.cuda.set_device(local_rank)
+  device = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=device)
+
+  n = args.probes
+  system, state_host = make_workload(n, seed=42 + rank)
+  ephemeris = Ephemeris(system, device=local_rank)
+  workloads.upload_sol_ephemeris(ephemeris)
+  method = _capi.BLANES_MOAN_2002_SRKN_14A
+  span = FLOW_STEPS * STEP_SECONDS
+
+  state_device = torch.from_numpy(state_host).to(device)
+  pinned = torch.from_numpy(state_host.copy()).pin_memory()
+  pinned_np = pinned.numpy()
+  flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+  stream = torch.cuda.current_stream().cuda_stream
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # The golden ephemeris covers two days = 172 bench steps of 1000 s; the
+  # flows advance continuously in time and restart from the initial state
+  # after WRAP steps (a device/host copy of the pristine state, negligible).
+  WRAP = 150
+  pristine_device = state_device.clone()
+  counters = {'resident': 0, 'e2e': 0}
+
+  def resident_step():
+    k = counters['resident'] % WRAP
+    if k == 0 and counters['resident'] > 0:
+      state_device.copy_(pristine_device)
+    counters['resident'] += 1
+    time_dp = np.array([k * span, 0.0])
+    result = ephemeris.flow_with_fixed_step_device(
+        method, STEP_SECONDS, (k + 1) * span, n, state_device.data_ptr(),
+        time_dp, stream)
+    assert result['n_steps'] == FLOW_STEPS and result['status'] == 0, result
+    return result
+
+  def e2e_step():
+    k = counters['e2e'] % WRAP
+    if k == 0 and counters['e2e'] > 0:
+      pinned_np[...] = state_host
+    counters['e2e'] += 1
+    time_dp = np.array([k * span, 0.0])
+    result = ephemeris.flow_with_fixed_step(method, STEP_SECONDS,
+                                            (k + 1) * span, pinned_np, time_dp)
+    assert result['n_steps'] == FLOW_STEPS and result['status'] == 0, result
+    return float(pinned_np[0, 0])  # The step's result, read on the host.
+
+  # FP64 roofline denominator, measured on this device, before the timed runs.
+  peak_flops, peak_ms = measure_fp64_peak(local_rank)
+
+  for k in range(args.warmup):
+    resident_step()
+  sampler = ClockSampler(local_rank)
+  launches_before = kernel_launch_count()
+  barrier()
+  sampler.start()
+  start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
+  kernel_ms = 0.0
+  kernel_launches = 0
+  start.record()
+  for k in range(args.steps):
+    flush.fill_(k & 0xff)  # Evict L2 between steps.
+    resident_step()
+    ms, launches = ephemeris.last_flow_kernel_ms()
+    kernel_ms += ms
+    kernel_launches += launches
+  stop.record()
+  barrier()
+  clocks = sampler.stop()
+  launches_timed = kernel_launch_count() - launches_before
+  elapsed_ms = torch.tensor([start.elapsed_time(stop)], device=device,
+                            dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+  elapsed_ms = float(elapsed_ms.item())
+
+  # End to end through the host-buffer entry point.
+  for k in range(min(args.warmup, 3)):
+    e2e_step()
+  barrier()
+  start.record()
+  for k in range(args.steps):
+    flush.fill_(k & 0xff)
+    e2e_step()
+  stop.record()
+  barrier()
+  e2e_ms = torch.tensor([start.elapsed_time(stop)], device=device,
+                        dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+  e2e_ms = float(e2e_ms.item())
+
+  stages_per_step = world * n * FLOW_STEPS * EVALUATIONS
+  value = args.steps * stages_per_step / (elapsed_ms * 1e-3)
+  e2e_value = args.steps * stages_per_step / (e2e_ms * 1e-3)
+
+  launch_flops = n * FLOW_STEPS * flops.srkn14a_probe_step_sol_leo()
+  average_kernel_ms = kernel_ms / max(kernel_launches, 1)
+  achieved = launch_flops / (average_kernel_ms * 1e-3) / 1e12
+  roofline = {
+      'bound': 'fp64', 'achieved': achieved, 'peak': peak_flops / 1e12,
+      'unit': 'TFLOP/s', 'frac': achieved / (peak_flops / 1e12),
+      'traffic': None,
+      'kernel': 'SrknFlowKernel',
+      'kernel_ms': average_kernel_ms,
+      'kernel_share_of_step': kernel_ms / elapsed_ms,
+      'algorithmic_flop_per_probe_stage':
+          flops.massless_probe_stage_sol_leo(),
+      'peak_source': 'register-resident DFMA chain measured in this run '
+                     '(pb_measure_fp64_peak, %.2f ms); MEASURED_PEAKS.json '
+                     'has no FP64 figure; nominal 37.2 TFLOP/s' % peak_ms}
+
+  cpu_baseline = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    threads = host_cores()
+    oracle = oracle_with_golden_segments(system)
+    n_cpu = cpu_sample_size(oracle, system, threads, target_seconds=12.0)
+    _, sample_state = make_workload(n_cpu, 42)
+    seconds = cpu_flow(oracle, sample_state, FLOW_STEPS, threads)
+    cpu_baseline = {
+        'value': n_cpu * FLOW_STEPS * EVALUATIONS / seconds, 'unit': UNIT,
+        'cores': threads, 'kind': 'port',
+        'sample': '%d of the 10^5 probes x %d steps, %.1f s of CPU work, '
+                  'oracle restatement on %d OpenMP threads' %
+                  (n_cpu, FLOW_STEPS, seconds, threads)}
+
+  if rank == 0:
+    print(json.dumps({
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'probes_per_gpu': n,
+                   'integrator_steps_per_step': FLOW_STEPS,
+                   'step_seconds': STEP_SECONDS,
+                   'parallelism': 'probes sharded by rank, no collective',
+                   'l2': 'flushed (256 MiB write) before every timed step'},
+        'probe_steps_per_second': value / EVALUATIONS,
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': UNIT,
+                'h2d_bytes_per_step': world * 12 * n * 8,
+                'd2h_bytes_per_step': world * 12 * n * 8,
+                'ms_per_step': e2e_ms / args.steps},
+        'gpu_launches': int(launches_timed),
+        'roofline': roofline,
+        'cpu_baseline': cpu_baseline}))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  parser = argparse.ArgumentParser()
+  parser.add_argument('--gpus', type=int, default=1)
+  parser.add_argument('--steps', type=int, default=10)
+  parser.add_argument('--warmup', type=int, default=3)
+  parser.add_argument('--impl', default='native',
+                      choices=['native', 'reference'])
+  parser.add_argument('--probes', type=int, default=PROBES_PER_GPU)
+  parser.add_argument('--no-cpu-baseline', action='store_true')
+  args = parser.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_native(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -303,6 +303,11 @@ pb_status_t pb_nbody_allpairs_accelerations(pb_nbody_allpairs_t* system,
 double pb_nbody_allpairs_last_force_ms(const pb_nbody_allpairs_t* system);
 
 /* ---- Measurement helpers. */
+/* Device time (CUDA events on the launching stream) spent in the flow kernels
+ * of the last pb_flow_with_*_step[_device] call on this ephemeris, and their
+ * number. */
+double pb_ephemeris_last_flow_kernel_ms(const pb_ephemeris_t* ephemeris,
+                                        int64_t* launches);
 /* Register-resident DFMA chain: returns the achieved FP64 FLOP/s on the
  * device (2 flop per FMA) and the kernel time through *ms. */
 pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,

@@ -1,0 +1,660 @@
+// C ABI of the B200-native gravitational-flow engine (include/principia_b200.h)
+// for the massless-body path: construction, ContinuousTrajectory segments,
+// batched accelerations / potential, fixed-step SRKN flow.  The adaptive flow
+// and the massive-body flows live in pb_api_adaptive.cu / pb_api_nbody.cu.
+//
+// Compiled for sm_100a with --fmad=false: IEEE binary64 without contraction,
+// like the reference's -ffp-contract=off build.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/principia_b200.h"
+#include "pb_kernels_massless.cuh"
+#include "pb_runtime.cuh"
+
+using namespace pb;
+
+namespace pb {
+
+pb_status_t UploadSegments(pb_ephemeris* e, cudaStream_t stream) {
+  if (!e->segments_dirty) {
+    return PB_OK;
+  }
+  int const n = static_cast<int>(e->trajectories.size());
+  std::vector<int32_t> offset(n + 1, 0);
+  std::vector<double> t_max, origin, coefficients;
+  std::vector<int32_t> degree;
+  for (int b = 0; b < n; ++b) {
+    HostTrajectory const& tr = e->trajectories[b];
+    offset[b] = static_cast<int32_t>(t_max.size());
+    t_max.insert(t_max.end(), tr.t_max.begin(), tr.t_max.end());
+    origin.insert(origin.end(), tr.origin.begin(), tr.origin.end());
+    degree.insert(degree.end(), tr.degree.begin(), tr.degree.end());
+    coefficients.insert(coefficients.end(), tr.coefficients.begin(),
+                        tr.coefficients.end());
+  }
+  offset[n] = static_cast<int32_t>(t_max.size());
+  // The copies below are from pageable memory and therefore synchronous with
+  // respect to the host, so the temporaries may die at the end of this scope.
+  PB_RETURN_IF_ERROR(e->segment_offset.Upload(offset, stream));
+  PB_RETURN_IF_ERROR(e->segment_t_max.Upload(t_max, stream));
+  PB_RETURN_IF_ERROR(e->segment_origin.Upload(origin, stream));
+  PB_RETURN_IF_ERROR(e->segment_degree.Upload(degree, stream));
+  PB_RETURN_IF_ERROR(e->segment_coefficients.Upload(coefficients, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  e->segments_dirty = false;
+  return PB_OK;
+}
+
+double EphemerisTMin(pb_ephemeris const* e) {
+  double t = -std::numeric_limits<double>::infinity();
+  for (auto const& tr : e->trajectories) {
+    if (!tr.has_t_min) {
+      return std::numeric_limits<double>::infinity();
+    }
+    t = std::max(t, tr.t_min);
+  }
+  return t;
+}
+
+double EphemerisTMax(pb_ephemeris const* e) {
+  double t = std::numeric_limits<double>::infinity();
+  for (auto const& tr : e->trajectories) {
+    if (tr.t_max.empty()) {
+      return -std::numeric_limits<double>::infinity();
+    }
+    t = std::min(t, tr.t_max.back());
+  }
+  return t;
+}
+
+// Fills `table` (device, n_times entries) for `times` (host).
+pb_status_t BuildStageTable(pb_ephemeris* e, double const* times_host,
+                            int n_times, double* table, cudaStream_t stream) {
+  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
+  double lo = std::numeric_limits<double>::infinity();
+  double hi = -lo;
+  for (int i = 0; i < n_times; ++i) {
+    if (times_host[i] != times_host[i]) {
+      return Fail(PB_INVALID_ARGUMENT, "NaN time");
+    }
+    lo = std::min(lo, times_host[i]);
+    hi = std::max(hi, times_host[i]);
+  }
+  // CHECK_LE(t_min, time); CHECK_GE(t_max, time) in
+  // ContinuousTrajectory::EvaluatePositionLocked.
+  if (lo < EphemerisTMin(e) || hi > EphemerisTMax(e)) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "time outside [t_min, t_max] of the ephemeris: Prolong first");
+  }
+  PB_RETURN_IF_ERROR(e->stage_times.Upload(times_host, n_times, stream));
+  EphemerisView const view = e->View();
+  long long const threads = static_cast<long long>(n_times) * view.n_bodies;
+  int const block = 128;
+  StageTableKernel<<<static_cast<unsigned>((threads + block - 1) / block),
+                     block, 0, stream>>>(view, e->stage_times.data, n_times,
+                                         table);
+  PB_LAUNCHED();
+  return PB_OK;
+}
+
+// integrators/symplectic_runge_kutta_nyström_integrator_body.hpp:198-208: the
+// nodes c_i are the double-double partial sums of the a_i.
+void ComputeNodes(SrknTableau const& tableau, double* c) {
+  DP c_i{0.0, 0.0};
+  for (int i = 0; i < tableau.stages; ++i) {
+    c[i] = c_i.value;
+    c_i = Add(c_i, DP{tableau.a[i], 0.0});
+  }
+}
+
+bool MakeSrknTableau(int32_t method, SrknTableau& t) {
+  std::memset(&t, 0, sizeof(t));
+  if (method == PB_BLANES_MOAN_2002_SRKN_14A) {
+    // integrators/methods.hpp:379-419 (ABA, 15 stages, 14 evaluations).
+    static double const a[15] = {
+        0.037859319840611600,   0.10263563310243500,  -0.025867888266558700,
+        0.31424140307144700,    -0.13014445951741500, 0.10641770036954300,
+        -0.0087942431285105800, 0.2073050690568954,   -0.0087942431285105800,
+        0.10641770036954300,    -0.13014445951741500, 0.31424140307144700,
+        -0.025867888266558700,  0.10263563310243500,  0.037859319840611600};
+    static double const b[15] = {
+        0.0,
+        0.091719152624461650,  0.18398317000500600,   -0.056534365832888270,
+        0.0049146887747128540, 0.14376112716835800,   0.32856769374680400,
+        -0.19641146648645423,  -0.19641146648645423,  0.32856769374680400,
+        0.14376112716835800,   0.0049146887747128540, -0.056534365832888270,
+        0.18398317000500600,   0.091719152624461650};
+    t.stages = 15;
+    t.first_stage = 1;
+    std::memcpy(t.a, a, sizeof(a));
+    std::memcpy(t.b, b, sizeof(b));
+    return true;
+  }
+  if (method == PB_MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL) {
+    // integrators/methods.hpp:922-949 (BA, 6 stages).
+    static double const a[6] = {0.339839625839110000,  -0.088601336903027329,
+                                0.5858564768259621188, -0.603039356536491888,
+                                0.3235807965546976394, 0.4423637942197494587};
+    static double const b[6] = {0.1193900292875672758,  0.6989273703824752308,
+                                -0.1713123582716007754, 0.4012695022513534480,
+                                0.0107050818482359840,  -0.0589796254980311632};
+    t.stages = 6;
+    t.first_stage = 0;
+    std::memcpy(t.a, a, sizeof(a));
+    std::memcpy(t.b, b, sizeof(b));
+    return true;
+  }
+  return false;
+}
+
+}  // namespace pb
+
+extern "C" {
+
+const char* pb_last_error(void) { return LastError().c_str(); }
+
+int64_t pb_kernel_launch_count(void) { return LaunchCount().load(); }
+
+pb_status_t pb_ephemeris_create(int32_t n_bodies, const pb_body_t* bodies,
+                                double geopotential_tolerance,
+                                int32_t cuda_device,
+                                pb_ephemeris_t** ephemeris) {
+  if (ephemeris == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null output");
+  }
+  *ephemeris = nullptr;
+  int device_count = 0;
+  cudaError_t const count_error = cudaGetDeviceCount(&device_count);
+  if (count_error != cudaSuccess || device_count == 0) {
+    return Fail(PB_FAILED_PRECONDITION,
+                std::string("no CUDA device; principia_b200 has no CPU "
+                            "fallback: ") +
+                    cudaGetErrorString(count_error));
+  }
+  if (cuda_device < 0 || cuda_device >= device_count) {
+    return Fail(PB_INVALID_ARGUMENT, "bad CUDA device ordinal");
+  }
+  PB_CUDA(cudaSetDevice(cuda_device));
+  auto* e = new pb_ephemeris;
+  e->device = cuda_device;
+  pb_status_t status =
+      BuildHostModel(n_bodies, bodies, geopotential_tolerance, e->model);
+  if (status != PB_OK) {
+    delete e;
+    return Fail(status, "invalid body description");
+  }
+  e->trajectories.resize(n_bodies);
+  cudaStream_t const stream = nullptr;
+  std::vector<double> normalization(
+      pb_legendre_normalization_factor,
+      pb_legendre_normalization_factor +
+          kGeopotentialSize * (kGeopotentialSize + 1) / 2);
+  // One dummy element keeps the pointers valid for systems without oblate
+  // bodies.
+  std::vector<Damping> dampings = e->model.dampings;
+  std::vector<double> cos = e->model.cos, sin = e->model.sin;
+  if (dampings.empty()) {
+    dampings.push_back(DefaultDamping());
+    cos.push_back(0.0);
+    sin.push_back(0.0);
+  }
+  status = e->bodies.Upload(e->model.bodies, stream);
+  if (status == PB_OK) status = e->dampings.Upload(dampings, stream);
+  if (status == PB_OK) status = e->cos.Upload(cos, stream);
+  if (status == PB_OK) status = e->sin.Upload(sin, stream);
+  if (status == PB_OK) status = e->normalization.Upload(normalization, stream);
+  if (status == PB_OK) status = e->status_word.Reserve(4);
+  if (status == PB_OK) status = e->pinned_status.Reserve(4);
+  if (status == PB_OK) {
+    cudaError_t const sync_error = cudaStreamSynchronize(stream);
+    if (sync_error != cudaSuccess) {
+      status = Fail(PB_INTERNAL, cudaGetErrorString(sync_error));
+    }
+  }
+  if (status != PB_OK) {
+    delete e;
+    return status;
+  }
+  *ephemeris = e;
+  return PB_OK;
+}
+
+void pb_ephemeris_destroy(pb_ephemeris_t* ephemeris) {
+  if (ephemeris != nullptr) {
+    cudaSetDevice(ephemeris->device);
+    delete ephemeris;
+  }
+}
+
+pb_status_t pb_ephemeris_internal_order(const pb_ephemeris_t* e, int32_t* order,
+                                        int32_t* n_oblate) {
+  if (e == nullptr || order == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  std::copy(e->model.order.begin(), e->model.order.end(), order);
+  if (n_oblate != nullptr) {
+    *n_oblate = e->model.n_oblate;
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_geopotential_damping(const pb_ephemeris_t* e, int32_t body,
+                                    int32_t* n_degrees,
+                                    double* inner_thresholds,
+                                    double* sectoral_inner_threshold) {
+  if (e == nullptr || body < 0 ||
+      body >= static_cast<int32_t>(e->model.bodies.size())) {
+    return Fail(PB_INVALID_ARGUMENT, "bad body");
+  }
+  DeviceBody const& b = e->model.bodies[e->model.internal_of_caller[body]];
+  if (!b.is_oblate) {
+    return Fail(PB_INVALID_ARGUMENT, "body is not oblate");
+  }
+  *n_degrees = b.n_damping;
+  for (int i = 0; i < b.n_damping; ++i) {
+    inner_thresholds[i] =
+        e->model.dampings[b.damping_offset + i].inner_threshold;
+  }
+  *sectoral_inner_threshold = b.sectoral.inner_threshold;
+  return PB_OK;
+}
+
+pb_status_t pb_ephemeris_append_segments(pb_ephemeris_t* e, int32_t body,
+                                         int32_t n_segments, double t_min,
+                                         const double* t_max,
+                                         const double* origin,
+                                         const int32_t* degree,
+                                         const double* coefficients) {
+  if (e == nullptr || body < 0 ||
+      body >= static_cast<int32_t>(e->model.bodies.size()) || n_segments < 0) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  HostTrajectory& tr = e->trajectories[e->model.internal_of_caller[body]];
+  for (int s = 0; s < n_segments; ++s) {
+    if (degree[s] < 0 || degree[s] >= kSegmentCoefficients) {
+      return Fail(PB_INVALID_ARGUMENT, "segment degree out of range");
+    }
+    double const previous = tr.t_max.empty() ? t_min : tr.t_max.back();
+    if (!(t_max[s] > previous)) {
+      return Fail(PB_INVALID_ARGUMENT, "segments must be appended in order");
+    }
+    if (!tr.has_t_min) {
+      tr.has_t_min = true;
+      tr.t_min = t_min;
+    }
+    tr.t_max.push_back(t_max[s]);
+    tr.origin.push_back(origin[s]);
+    tr.degree.push_back(degree[s]);
+    tr.coefficients.insert(tr.coefficients.end(),
+                           coefficients + 3 * kSegmentCoefficients * s,
+                           coefficients + 3 * kSegmentCoefficients * (s + 1));
+  }
+  e->segments_dirty = true;
+  return PB_OK;
+}
+
+double pb_ephemeris_t_min(const pb_ephemeris_t* e) { return EphemerisTMin(e); }
+double pb_ephemeris_t_max(const pb_ephemeris_t* e) { return EphemerisTMax(e); }
+
+pb_status_t pb_ephemeris_evaluate_all_positions(pb_ephemeris_t* e, double t,
+                                                double* positions) {
+  if (e == nullptr || positions == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  EphemerisView const view = e->View();
+  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
+  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+  std::vector<double> entry(view.stage_stride);
+  PB_CUDA(cudaMemcpyAsync(entry.data(), e->stage_table.data,
+                          entry.size() * sizeof(double), cudaMemcpyDeviceToHost,
+                          stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  for (int b = 0; b < view.n_bodies; ++b) {
+    int const caller = e->model.order[b];
+    for (int c = 0; c < 3; ++c) {
+      positions[3 * caller + c] = entry[3 * b + c];
+    }
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies_device(
+    pb_ephemeris_t* e, double t, int64_t n, const double* q, double* a,
+    int32_t* status_device, void* stream_pointer) {
+  if (e == nullptr || n < 0 || (n > 0 && (q == nullptr || a == nullptr))) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
+  EphemerisView const view = e->View();
+  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
+  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+  int32_t* const status =
+      status_device != nullptr ? status_device : e->status_word.data;
+  if (n > 0) {
+    MasslessAccelerationKernel<true>
+        <<<static_cast<unsigned>((n + kFlowThreads - 1) / kFlowThreads),
+           kFlowThreads, 0, stream>>>(view, e->stage_table.data, n, q, a,
+                                      status);
+    PB_LAUNCHED();
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies(
+    pb_ephemeris_t* e, double t, int64_t n, const double* q, double* a,
+    pb_status_t* status) {
+  if (e == nullptr || n < 0 || (n > 0 && (q == nullptr || a == nullptr))) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  PB_RETURN_IF_ERROR(e->scratch_a.Upload(q, 3 * n, stream));
+  PB_RETURN_IF_ERROR(e->scratch_b.Reserve(3 * n));
+  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
+  PB_RETURN_IF_ERROR(
+      pb_compute_gravitational_acceleration_on_massless_bodies_device(
+          e, t, n, e->scratch_a.data, e->scratch_b.data, e->status_word.data,
+          stream));
+  if (n > 0) {
+    PB_CUDA(cudaMemcpyAsync(a, e->scratch_b.data, 3 * n * sizeof(double),
+                            cudaMemcpyDeviceToHost, stream));
+  }
+  int32_t word = 0;
+  PB_CUDA(cudaMemcpyAsync(&word, e->status_word.data, sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  if (status != nullptr) {
+    *status = word;
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_compute_gravitational_potential(pb_ephemeris_t* e, double t,
+                                               int64_t n, const double* q,
+                                               double* potential) {
+  if (e == nullptr || n < 0 ||
+      (n > 0 && (q == nullptr || potential == nullptr))) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  EphemerisView const view = e->View();
+  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
+  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+  PB_RETURN_IF_ERROR(e->scratch_a.Upload(q, 3 * n, stream));
+  PB_RETURN_IF_ERROR(e->scratch_b.Reserve(n));
+  if (n > 0) {
+    PotentialKernel<<<static_cast<unsigned>((n + kFlowThreads - 1) /
+                                            kFlowThreads),
+                      kFlowThreads, 0, stream>>>(view, e->stage_table.data, n,
+                                                 e->scratch_a.data,
+                                                 e->scratch_b.data);
+    PB_LAUNCHED();
+    PB_CUDA(cudaMemcpyAsync(potential, e->scratch_b.data, n * sizeof(double),
+                            cudaMemcpyDeviceToHost, stream));
+  }
+  PB_CUDA(cudaStreamSynchronize(stream));
+  return PB_OK;
+}
+
+pb_status_t pb_compute_gravitational_acceleration_on_massive_bodies(
+    pb_ephemeris_t* e, double t, const double* positions,
+    double* accelerations) {
+  if (e == nullptr || accelerations == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  EphemerisView const view = e->View();
+  int const n = view.n_bodies;
+  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
+  if (positions == nullptr) {
+    PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+  } else {
+    std::vector<double> internal(3 * n);
+    for (int b = 0; b < n; ++b) {
+      int const caller = e->model.order[b];
+      for (int c = 0; c < 3; ++c) {
+        internal[3 * b + c] = positions[3 * caller + c];
+      }
+    }
+    PB_CUDA(cudaMemcpyAsync(e->stage_table.data, internal.data(),
+                            internal.size() * sizeof(double),
+                            cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));
+    FramesKernel<<<(n + 63) / 64, 64, 0, stream>>>(view, t,
+                                                  e->stage_table.data);
+    PB_LAUNCHED();
+  }
+  PB_RETURN_IF_ERROR(e->scratch_b.Reserve(3 * n));
+  MassiveAccelerationKernel<<<(n + 31) / 32, 32, 0, stream>>>(
+      view, e->stage_table.data, e->scratch_b.data);
+  PB_LAUNCHED();
+  std::vector<double> internal(3 * n);
+  PB_CUDA(cudaMemcpyAsync(internal.data(), e->scratch_b.data,
+                          internal.size() * sizeof(double),
+                          cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  for (int b = 0; b < n; ++b) {
+    int const caller = e->model.order[b];
+    for (int c = 0; c < 3; ++c) {
+      accelerations[3 * caller + c] = internal[3 * b + c];
+    }
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
+                                           const pb_fixed_step_flow_t* flow,
+                                           void* stream_pointer) {
+  if (e == nullptr || flow == nullptr || flow->n < 0 || flow->time == nullptr ||
+      (flow->n > 0 && flow->state == nullptr)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  SrknTableau tableau;
+  if (!MakeSrknTableau(flow->method, tableau)) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "fixed-step massless flow supports the SRKN methods");
+  }
+  if (flow->step == 0 || flow->step != flow->step) {
+    return Fail(PB_INVALID_ARGUMENT, "CHECK_NE(Time(), step)");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
+  EphemerisView const view = e->View();
+  double c[16];
+  ComputeNodes(tableau, c);
+  int const evaluations = tableau.stages - tableau.first_stage;
+  double const h = flow->step;
+  double const abs_h = h < 0 ? -h : h;
+  DP t{flow->time[0], flow->time[1]};
+  double const t_final = flow->t_final;
+  bool const sampling = flow->samples != nullptr && flow->sample_every > 0;
+
+  // Steps per launch: bounds the stage table (evaluations * stride doubles per
+  // step).
+  int const chunk_steps = 256;
+  std::size_t const table_doubles =
+      static_cast<std::size_t>(chunk_steps) * evaluations * view.stage_stride;
+  PB_RETURN_IF_ERROR(e->stage_table.Reserve(table_doubles));
+  PB_RETURN_IF_ERROR(
+      e->pinned_times.Reserve(static_cast<std::size_t>(chunk_steps) *
+                              evaluations));
+  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
+
+  long long steps_done = 0;
+  long long samples_done = 0;
+  std::size_t launches = 0;
+  while (abs_h <= std::abs((t_final - t.value) - t.error)) {
+    int steps = 0;
+    double* const times = e->pinned_times.data;
+    // The pinned staging buffer is reused across chunks.
+    PB_CUDA(cudaStreamSynchronize(stream));
+    while (steps < chunk_steps &&
+           abs_h <= std::abs((t_final - t.value) - t.error)) {
+      for (int st = tableau.first_stage; st < tableau.stages; ++st) {
+        times[steps * evaluations + (st - tableau.first_stage)] =
+            t.value + (t.error + c[st] * h);
+      }
+      Increment(t, h);
+      ++steps;
+      if (sampling && (steps_done + steps) % flow->sample_every == 0 &&
+          samples_done < flow->max_samples) {
+        if (flow->sample_times != nullptr) {
+          flow->sample_times[samples_done] = t.value;
+        }
+        ++samples_done;
+      }
+    }
+    PB_RETURN_IF_ERROR(BuildStageTable(e, times, steps * evaluations,
+                                       e->stage_table.data, stream));
+    if (flow->n > 0) {
+      while (e->timing_events.size() < 2 * (launches + 1)) {
+        cudaEvent_t event;
+        PB_CUDA(cudaEventCreate(&event));
+        e->timing_events.push_back(event);
+      }
+      PB_CUDA(cudaEventRecord(e->timing_events[2 * launches], stream));
+      SrknFlowKernel<true>
+          <<<static_cast<unsigned>((flow->n + kFlowThreads - 1) / kFlowThreads),
+             kFlowThreads, 0, stream>>>(
+              view, tableau, h, e->stage_table.data, steps, flow->n,
+              flow->state, steps_done, sampling ? flow->sample_every : 0,
+              flow->max_samples, flow->samples, e->status_word.data);
+      PB_LAUNCHED();
+      PB_CUDA(cudaEventRecord(e->timing_events[2 * launches + 1], stream));
+      ++launches;
+    }
+    steps_done += steps;
+  }
+  PB_CUDA(cudaMemcpyAsync(e->pinned_status.data, e->status_word.data,
+                          sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  e->last_flow_kernel_ms = 0;
+  e->last_flow_kernel_launches = static_cast<std::int64_t>(launches);
+  for (std::size_t i = 0; i < launches; ++i) {
+    float elapsed = 0;
+    PB_CUDA(cudaEventElapsedTime(&elapsed, e->timing_events[2 * i],
+                                 e->timing_events[2 * i + 1]));
+    e->last_flow_kernel_ms += elapsed;
+  }
+  flow->time[0] = t.value;
+  flow->time[1] = t.error;
+  if (flow->n_steps != nullptr) {
+    *flow->n_steps = steps_done;
+  }
+  if (flow->n_samples != nullptr) {
+    *flow->n_samples = samples_done;
+  }
+  if (flow->status != nullptr) {
+    // The only error the right-hand side reports is the collision
+    // (ephemeris_body.hpp:383-384).
+    *flow->status = e->pinned_status.data[0] != 0 ? PB_OUT_OF_RANGE : PB_OK;
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* e,
+                                    const pb_fixed_step_flow_t* flow) {
+  if (e == nullptr || flow == nullptr || flow->n < 0 ||
+      (flow->n > 0 && flow->state == nullptr)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  std::size_t const n = static_cast<std::size_t>(flow->n);
+  PB_RETURN_IF_ERROR(e->scratch_a.Upload(flow->state, 12 * n, stream));
+  pb_fixed_step_flow_t device_flow = *flow;
+  device_flow.state = e->scratch_a.data;
+  bool const sampling = flow->samples != nullptr && flow->sample_every > 0 &&
+                        flow->max_samples > 0;
+  if (sampling) {
+    PB_RETURN_IF_ERROR(e->scratch_c.Reserve(
+        static_cast<std::size_t>(flow->max_samples) * 6 * n));
+    device_flow.samples = e->scratch_c.data;
+  } else {
+    device_flow.samples = nullptr;
+  }
+  int64_t n_samples = 0;
+  device_flow.n_samples = &n_samples;
+  PB_RETURN_IF_ERROR(pb_flow_with_fixed_step_device(e, &device_flow, stream));
+  if (n > 0) {
+    PB_CUDA(cudaMemcpyAsync(flow->state, e->scratch_a.data,
+                            12 * n * sizeof(double), cudaMemcpyDeviceToHost,
+                            stream));
+    if (sampling && n_samples > 0) {
+      PB_CUDA(cudaMemcpyAsync(flow->samples, e->scratch_c.data,
+                              static_cast<std::size_t>(n_samples) * 6 * n *
+                                  sizeof(double),
+                              cudaMemcpyDeviceToHost, stream));
+    }
+  }
+  PB_CUDA(cudaStreamSynchronize(stream));
+  if (flow->n_samples != nullptr) {
+    *flow->n_samples = n_samples;
+  }
+  return PB_OK;
+}
+
+double pb_ephemeris_last_flow_kernel_ms(const pb_ephemeris_t* e,
+                                        int64_t* launches) {
+  if (launches != nullptr) {
+    *launches = e->last_flow_kernel_launches;
+  }
+  return e->last_flow_kernel_ms;
+}
+
+pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,
+                                 double* ms) {
+  int device_count = 0;
+  if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count == 0) {
+    return Fail(PB_FAILED_PRECONDITION, "no CUDA device");
+  }
+  PB_CUDA(cudaSetDevice(cuda_device));
+  cudaDeviceProp properties;
+  PB_CUDA(cudaGetDeviceProperties(&properties, cuda_device));
+  double* out = nullptr;
+  PB_CUDA(cudaMalloc(&out, sizeof(double)));
+  int const iterations = 1 << 16;
+  int const block = 256;
+  int const grid = properties.multiProcessorCount * 8;
+  cudaEvent_t start, stop;
+  PB_CUDA(cudaEventCreate(&start));
+  PB_CUDA(cudaEventCreate(&stop));
+  float best = std::numeric_limits<float>::infinity();
+  for (int repeat = 0; repeat < 4; ++repeat) {
+    PB_CUDA(cudaEventRecord(start));
+    Fp64PeakKernel<<<grid, block>>>(out, iterations);
+    PB_LAUNCHED();
+    PB_CUDA(cudaEventRecord(stop));
+    PB_CUDA(cudaEventSynchronize(stop));
+    float elapsed = 0;
+    PB_CUDA(cudaEventElapsedTime(&elapsed, start, stop));
+    if (repeat > 0) {
+      best = std::min(best, elapsed);
+    }
+  }
+  PB_CUDA(cudaEventDestroy(start));
+  PB_CUDA(cudaEventDestroy(stop));
+  PB_CUDA(cudaFree(out));
+  double const flops = 2.0 * 8.0 * iterations * static_cast<double>(block) * grid;
+  if (flops_per_second != nullptr) {
+    *flops_per_second = flops / (best * 1e-3);
+  }
+  if (ms != nullptr) {
+    *ms = best;
+  }
+  return PB_OK;
+}
+
+}  // extern "C"

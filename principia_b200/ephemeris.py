@@ -1,0 +1,236 @@
+"""Python mirror of the reference's physics::Ephemeris surface for the hot path
+(physics/ephemeris.hpp:67-561), over the C ABI of libprincipia_b200.so.
+
+Method names follow the reference (snake_case); arguments are numpy arrays in
+the SoA layouts documented in include/principia_b200.h.  Everything computes
+on the GPU; there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+
+_vp = ctypes.c_void_p
+
+
+class StatusError(RuntimeError):
+
+  def __init__(self, code, message):
+    super().__init__('pb_status %d: %s' % (code, message))
+    self.code = code
+
+
+def _check(code):
+  if code != _capi.PB_OK:
+    raise StatusError(code, _capi.last_error())
+
+
+def _dptr(array):
+  return array.ctypes.data_as(_capi.c_double_p)
+
+
+class Ephemeris:
+  """Ephemeris<Frame>: owns the massive bodies and their ContinuousTrajectory
+  segments on one GPU."""
+
+  def __init__(self, system, geopotential_tolerance=2.0**-24, device=0):
+    self.lib = _capi.library()
+    self.system = system
+    self.n_bodies = len(system.bodies)
+    bodies, self._keep = system.c_bodies()
+    handle = _vp()
+    _check(self.lib.pb_ephemeris_create(self.n_bodies, bodies,
+                                        geopotential_tolerance, device,
+                                        ctypes.byref(handle)))
+    self.handle = handle
+    self.device = device
+
+  def close(self):
+    if getattr(self, 'handle', None):
+      self.lib.pb_ephemeris_destroy(self.handle)
+      self.handle = None
+
+  def __del__(self):
+    self.close()
+
+  # -- structure ------------------------------------------------------------
+  def internal_order(self):
+    order = np.zeros(self.n_bodies, dtype=np.int32)
+    n_oblate = ctypes.c_int32()
+    _check(self.lib.pb_ephemeris_internal_order(
+        self.handle, order.ctypes.data_as(_capi.c_int32_p),
+        ctypes.byref(n_oblate)))
+    return order, n_oblate.value
+
+  def geopotential_damping(self, body):
+    n = ctypes.c_int32()
+    inner = np.zeros(51)
+    sectoral = ctypes.c_double()
+    _check(self.lib.pb_geopotential_damping(self.handle, body, ctypes.byref(n),
+                                            _dptr(inner),
+                                            ctypes.byref(sectoral)))
+    return inner[:n.value].copy(), sectoral.value
+
+  # -- ContinuousTrajectory -------------------------------------------------
+  def append_segments(self, body, segments):
+    t_max = np.ascontiguousarray(segments['t_max'], dtype=np.float64)
+    origin = np.ascontiguousarray(segments['origin'], dtype=np.float64)
+    degree = np.ascontiguousarray(segments['degree'], dtype=np.int32)
+    coefficients = np.ascontiguousarray(segments['coefficients'],
+                                        dtype=np.float64)
+    _check(self.lib.pb_ephemeris_append_segments(
+        self.handle, body, len(t_max), float(segments['t_min']), _dptr(t_max),
+        _dptr(origin), degree.ctypes.data_as(_capi.c_int32_p),
+        _dptr(coefficients)))
+
+  def t_min(self):
+    return self.lib.pb_ephemeris_t_min(self.handle)
+
+  def t_max(self):
+    return self.lib.pb_ephemeris_t_max(self.handle)
+
+  def evaluate_all_positions(self, t):
+    out = np.zeros((self.n_bodies, 3))
+    _check(self.lib.pb_ephemeris_evaluate_all_positions(self.handle, t,
+                                                        _dptr(out)))
+    return out
+
+  # -- accelerations --------------------------------------------------------
+  def compute_gravitational_acceleration_on_massless_bodies(self, t, q):
+    """q: (3, n) positions.  Returns ((3, n) accelerations, status)."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    a = np.zeros_like(q)
+    status = ctypes.c_int32()
+    _check(self.lib.pb_compute_gravitational_acceleration_on_massless_bodies(
+        self.handle, t, q.shape[1], _dptr(q), _dptr(a), ctypes.byref(status)))
+    return a, status.value
+
+  def compute_gravitational_acceleration_on_massless_bodies_device(
+      self, t, n, q_pointer, a_pointer, status_pointer=None, stream=None):
+    _check(
+        self.lib.pb_compute_gravitational_acceleration_on_massless_bodies_device(
+            self.handle, t, n, q_pointer, a_pointer, status_pointer, stream))
+
+  def compute_gravitational_potential(self, t, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.zeros(q.shape[1])
+    _check(self.lib.pb_compute_gravitational_potential(
+        self.handle, t, q.shape[1], _dptr(q), _dptr(out)))
+    return out
+
+  def compute_gravitational_acceleration_on_massive_bodies(self, t,
+                                                           positions=None):
+    out = np.zeros((self.n_bodies, 3))
+    pointer = None
+    if positions is not None:
+      positions = np.ascontiguousarray(positions, dtype=np.float64)
+      pointer = _dptr(positions)
+    _check(self.lib.pb_compute_gravitational_acceleration_on_massive_bodies(
+        self.handle, t, pointer, _dptr(out)))
+    return out
+
+  # -- flows ----------------------------------------------------------------
+  def _fixed_step_flow(self, method, step, t_final, n, state_pointer, time,
+                       sample_every, max_samples, samples_pointer,
+                       sample_times):
+    flow = _capi.FixedStepFlow()
+    flow.method = method
+    flow.step = step
+    flow.t_final = t_final
+    flow.n = n
+    flow.state = state_pointer
+    flow.time = _dptr(time)
+    flow.sample_every = sample_every
+    flow.max_samples = max_samples
+    flow.samples = samples_pointer
+    flow.sample_times = None if sample_times is None else _dptr(sample_times)
+    outs = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
+    flow.n_samples = ctypes.pointer(outs[0])
+    flow.n_steps = ctypes.pointer(outs[1])
+    flow.status = ctypes.pointer(outs[2])
+    return flow, outs
+
+  def flow_with_fixed_step(self, method, step, t_final, state, time,
+                           sample_every=0, max_samples=0):
+    """NewInstance + FlowWithFixedStep on n probes.  state: (12, n) float64,
+    time: (2,) float64; both updated in place (host buffers)."""
+    assert state.flags.c_contiguous and state.dtype == np.float64
+    n = state.shape[1]
+    samples = sample_times = None
+    if sample_every > 0 and max_samples > 0:
+      samples = np.zeros((max_samples, 6, n))
+      sample_times = np.zeros(max_samples)
+    flow, outs = self._fixed_step_flow(
+        method, step, t_final, n, state.ctypes.data, time, sample_every,
+        max_samples, None if samples is None else samples.ctypes.data,
+        sample_times)
+    _check(self.lib.pb_flow_with_fixed_step(self.handle, ctypes.byref(flow)))
+    n_samples, n_steps, status = (o.value for o in outs)
+    return dict(n_steps=n_steps, status=status,
+                samples=None if samples is None else samples[:n_samples],
+                sample_times=None if samples is None
+                else sample_times[:n_samples])
+
+  def flow_with_fixed_step_device(self, method, step, t_final, n,
+                                  state_pointer, time, stream=None):
+    """Same, state already resident in HBM (device pointer to 12 * n
+    doubles)."""
+    flow, outs = self._fixed_step_flow(method, step, t_final, n, state_pointer,
+                                       time, 0, 0, None, None)
+    _check(self.lib.pb_flow_with_fixed_step_device(self.handle,
+                                                   ctypes.byref(flow), stream))
+    return dict(n_steps=outs[1].value, status=outs[2].value)
+
+  def last_flow_kernel_ms(self):
+    """(device ms, launches) of the flow kernels of the last flow call."""
+    launches = ctypes.c_int64()
+    ms = self.lib.pb_ephemeris_last_flow_kernel_ms(self.handle,
+                                                   ctypes.byref(launches))
+    return ms, launches.value
+
+  def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
+                              speed_tolerance, max_steps=2**62,
+                              step_log_capacity=0):
+    """FlowWithAdaptiveStep, one trajectory per probe.  state: (12, n),
+    time: (2, n); updated in place (host buffers)."""
+    assert state.flags.c_contiguous and time.flags.c_contiguous
+    n = state.shape[1]
+    flow = _capi.AdaptiveStepFlow()
+    flow.method = _capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM
+    flow.t_final = t_final
+    flow.length_integration_tolerance = length_tolerance
+    flow.speed_integration_tolerance = speed_tolerance
+    flow.max_steps = max_steps
+    flow.n = n
+    flow.state = state.ctypes.data
+    flow.time = time.ctypes.data
+    status = np.zeros(n, dtype=np.int32)
+    accepted = np.zeros(n, dtype=np.int64)
+    rejected = np.zeros(n, dtype=np.int64)
+    evaluations = np.zeros(n, dtype=np.int64)
+    flow.status = status.ctypes.data
+    flow.accepted_steps = accepted.ctypes.data
+    flow.rejected_steps = rejected.ctypes.data
+    flow.evaluations = evaluations.ctypes.data
+    step_log = None
+    if step_log_capacity > 0:
+      step_log = np.full((step_log_capacity, n), np.nan)
+      flow.step_log_capacity = step_log_capacity
+      flow.step_log = step_log.ctypes.data
+    _check(self.lib.pb_flow_with_adaptive_step(self.handle,
+                                               ctypes.byref(flow)))
+    return dict(status=status, accepted=accepted, rejected=rejected,
+                evaluations=evaluations, step_log=step_log)
+
+
+def measure_fp64_peak(device=0):
+  flops = ctypes.c_double()
+  ms = ctypes.c_double()
+  _check(_capi.library().pb_measure_fp64_peak(device, ctypes.byref(flops),
+                                              ctypes.byref(ms)))
+  return flops.value, ms.value
+
+
+def kernel_launch_count():
+  return _capi.library().pb_kernel_launch_count()

@@ -1,0 +1,110 @@
+"""Static count of the ALGORITHMIC floating-point operations of the hot path:
+the operations the reference's formulae prescribe (and both the oracle and the
+kernels execute), each add/sub/mul/div/sqrt/compare = 1, an FMA = 2.  This is
+the numerator of `roofline.achieved` (SURVEY.md §8d asks for an exact static
+count of the restatement instead of the "≈" figures); instruction-level
+expansion of div/sqrt on the GPU is deliberately NOT counted.
+
+The counts follow principia_b200/csrc/pb_geopotential.cuh / pb_accel.cuh
+statement by statement.
+"""
+
+POINT_MASS_PAIR = 19  # 3 sub, 5 norm², sqrt, cmp, mul+div, mul, 3 mul, 3 add.
+
+
+def geopotential_setup():
+  # InitializeSetup: 3 dots (5 each), x²+y² (3), sqrt, compare, 1/r_eq,
+  # cos/sin lambda (2), 1/r, r_normalized (3), cos/sin beta (2),
+  # grad_B (1+3 + 1+3 + 3 + 3 + 3), grad_L (3+3+3), R1/r (1).
+  return 15 + 3 + 1 + 1 + 1 + 2 + 1 + 3 + 2 + 17 + 9 + 1
+
+
+def order_update(n, m):
+  if n == 2 and m == 1:
+    return 0
+  flops = 0
+  if m == n:
+    flops += 6 if m % 2 == 0 else 7
+  if m == 0:
+    flops += 5
+  if m == n:
+    pass
+  elif m == n - 1:
+    flops += 2
+  elif m == n - 2:
+    flops += 5
+  else:
+    flops += 7
+  return flops
+
+
+def order_term(n, m):
+  flops = 1                       # B
+  if m < n:
+    flops += 2                    # cos_beta * cos_beta^m * P
+  if m > 0:
+    flops += 4                    # m * sin_beta * cos_beta^(m-1) * P, subtract
+    flops += 3                    # L
+  flops += 1 + 3                  # (B L) grad_sigma_R
+  flops += 2 + 3                  # (sigma R/r L gradBpoly) grad_B
+  flops += 3                      # sum
+  if m > 0:
+    flops += 4 + 3 + 3 + 3        # scalar chain, (S cos - C sin), * grad_L, +=
+  flops += 3                      # normalisation
+  return flops
+
+
+def damping(damped):
+  # compare; undamped: R' r_normalized (3); damped: r³, 3 products, sigma (2),
+  # sigma' r (4), sigma R/r, (.. + ..) (3), * r_normalized (3).
+  return 1 + (1 + 3 + 2 + 4 + 1 + 3 + 3 if damped else 3)
+
+
+def geopotential(max_degree, zonal, damped_degrees=()):
+  """One GeneralSphericalHarmonicsAcceleration evaluation."""
+  flops = 2 + 1 + max_degree.bit_length()  # NaN test, zonal test, partition.
+  flops += geopotential_setup()
+  for n in range(2, max_degree + 1):
+    size = 1 if zonal else n + 1
+    flops += 2 + 1                # R_n/r, R'
+    if n == 2 and size > 1:
+      flops += 2 * damping(n in damped_degrees)
+      flops += order_update(2, 0) + order_term(2, 0)
+      flops += order_update(2, 2) + order_term(2, 2)
+      flops += 3
+    else:
+      flops += damping(n in damped_degrees)
+      for m in range(size):
+        flops += order_update(n, m) + order_term(n, m)
+      flops += 3 * (size - 1)     # right fold over orders
+  flops += 3 * (max_degree - 2)   # right fold over degrees
+  flops += 6                      # + zero vectors of degrees 0 and 1
+  return flops
+
+
+def massless_probe_stage_sol_leo():
+  """One right-hand-side evaluation for a LEO probe in the 34-body Sol field:
+  34 point masses, Earth at degree/order 10 (undamped), the Moon's damped J2
+  (zonal regime at lunar distance), the other 9 oblate bodies beyond their
+  outer thresholds (NaN test + partition only)."""
+  flops = 34 * POINT_MASS_PAIR
+  flops += geopotential(10, zonal=False) + 6   # Earth, acc += mu * effect
+  flops += geopotential(2, zonal=True, damped_degrees=(2,)) + 6   # Moon
+  flops += 9 * (2 + 6)                         # far oblate bodies
+  return flops
+
+
+SRKN_STAGE = 3 + 2 + 6 + 9       # q_stage, h a_i & h b_i, dv, dq
+SRKN_STEP = 6 * 4                # six compensated increments
+
+
+def srkn14a_probe_step_sol_leo():
+  return 14 * (massless_probe_stage_sol_leo() + SRKN_STAGE) + 3 * 3 + SRKN_STEP
+
+
+if __name__ == '__main__':
+  print('geopotential setup', geopotential_setup())
+  print('geopotential degree/order 10', geopotential(10, False))
+  print('geopotential zonal J2 damped', geopotential(2, True, (2,)))
+  print('probe-stage (Sol, LEO)', massless_probe_stage_sol_leo())
+  print('SRKN14A probe-step', srkn14a_probe_step_sol_leo())

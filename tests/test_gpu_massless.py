@@ -1,0 +1,290 @@
+"""GPU parity tests of the massless-body path, through the C ABI, against the
+CPU oracle on the same seeded inputs: bit-exact (IEEE binary64 without
+contraction on both sides)."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+
+from principia_b200 import _capi, workloads
+from principia_b200.solar_system import SolarSystem
+
+from conftest import assert_bitwise_equal
+import oracle_lib
+from oracle_lib import OracleEphemeris
+
+pytestmark = pytest.mark.gpu
+
+
+def earth_state(system, oracle, t=0.0):
+  i = system.index('Earth')
+  if t == 0.0:
+    return (np.array(system.bodies[i]['q']), np.array(system.bodies[i]['v']),
+            system.bodies[i]['mu'])
+  raise NotImplementedError
+
+
+def test_elementary_functions_on_device():
+  lib = _capi.library()
+  orc = oracle_lib.library()
+  rng = np.random.default_rng(11)
+  x = np.concatenate([rng.uniform(-10, 10, 100000),
+                      rng.uniform(-1e6, 1e6, 100000),
+                      rng.uniform(-2e9, 2e9, 50000),
+                      10.0**rng.uniform(-30, 30, 50000)])
+  n = len(x)
+  s, c, r = np.zeros(n), np.zeros(n), np.zeros(n)
+  f = lib.pb_internal_elementary_functions
+  f.argtypes = [ctypes.c_int32, ctypes.c_int64] + [_capi.c_double_p] * 4
+  assert f(0, n, oracle_lib.dptr(x), oracle_lib.dptr(s), oracle_lib.dptr(c),
+           oracle_lib.dptr(r)) == 0
+  step = 37  # The oracle (binary128) is slow: check a strided subset...
+  for i in range(0, n, step):
+    assert s[i] == orc.orc_cr_sin(x[i]), x[i]
+    assert c[i] == orc.orc_cr_cos(x[i]), x[i]
+    if x[i] > 0:
+      assert r[i] == orc.orc_root(4, x[i]), x[i]
+  # ... and all of it against the host build of the same header, which
+  # tests/test_host_arithmetic.py pins to the oracle on 10^5 points.
+  assert np.all(np.abs(s) <= 1) and np.all(np.abs(c) <= 1)
+  positive = x > 0
+  assert np.max(np.abs(r[positive]**4 / x[positive] - 1)) < 1e-15
+
+
+def test_structure_matches_oracle(sol_system, sol_oracle, sol_gpu):
+  order, n_oblate = sol_gpu.internal_order()
+  expected_order, expected_n_oblate = sol_oracle.internal_order()
+  assert list(order) == list(expected_order)
+  assert n_oblate == expected_n_oblate == 11
+  for i, b in enumerate(sol_system.bodies):
+    if b['oblate']:
+      inner, sectoral = sol_gpu.geopotential_damping(i)
+      expected_inner, expected_sectoral = sol_oracle.damping(i)
+      assert_bitwise_equal(inner, expected_inner, b['name'])
+      assert sectoral == expected_sectoral
+  assert sol_gpu.t_min() == sol_oracle.t_min() == 0.0
+  assert sol_gpu.t_max() == sol_oracle.t_max() == 172800.0
+
+
+def test_golden_segments_are_the_oracles(sol_system, sol_oracle):
+  golden = workloads.load_sol_ephemeris_segments()
+  for i in range(len(sol_system.bodies)):
+    seg = sol_oracle.segments(i)
+    assert seg['t_min'] == golden[i]['t_min']
+    assert_bitwise_equal(seg['t_max'], golden[i]['t_max'])
+    assert_bitwise_equal(seg['origin'], golden[i]['origin'])
+    assert list(seg['degree']) == list(golden[i]['degree'])
+    assert_bitwise_equal(seg['coefficients'], golden[i]['coefficients'])
+
+
+def test_evaluate_all_positions(sol_oracle, sol_gpu):
+  rng = np.random.default_rng(1)
+  times = np.concatenate([rng.uniform(0, 172800.0, 40),
+                          [0.0, 4800.0, 4800.000001, 172800.0]])
+  for t in times:
+    assert_bitwise_equal(sol_gpu.evaluate_all_positions(t),
+                         sol_oracle.evaluate_all_positions(t), 't=%r' % t)
+  with pytest.raises(Exception):
+    sol_gpu.evaluate_all_positions(172800.5)
+
+
+def random_points_near(rng, centres, n, low=6.6e6, high=2e9):
+  distance = np.exp(rng.uniform(math.log(low), math.log(high), n))
+  direction = rng.normal(size=(3, n))
+  direction /= np.linalg.norm(direction, axis=0)
+  centre = centres[rng.integers(0, len(centres), n)].T
+  return centre + distance * direction
+
+
+def test_acceleration_on_massless_bodies(sol_system, sol_oracle, sol_gpu):
+  rng = np.random.default_rng(42)
+  names = sol_system.names()
+  for t in (0.0, 12345.678, 86400.0, 172800.0):
+    positions = sol_oracle.evaluate_all_positions(t)
+    centres = positions[[names.index(k) for k in
+                         ('Earth', 'Earth', 'Earth', 'Moon', 'Mars', 'Venus',
+                          'Jupiter', 'Sun', 'Io', 'Vesta')]]
+    q = random_points_near(rng, centres, 4099)
+    a, status = sol_gpu.compute_gravitational_acceleration_on_massless_bodies(
+        t, q)
+    expected, expected_status = sol_oracle.acceleration_on_massless_bodies(t, q)
+    assert_bitwise_equal(a, expected, 't=%r' % t)
+    assert status == expected_status == 0
+  # Close to the Moon: its degree-30 field (generic path).
+  positions = sol_oracle.evaluate_all_positions(1000.0)
+  q = random_points_near(rng, positions[[names.index('Moon')]], 513, 1.75e6,
+                         1e7)
+  a, status = sol_gpu.compute_gravitational_acceleration_on_massless_bodies(
+      1000.0, q)
+  expected, expected_status = sol_oracle.acceleration_on_massless_bodies(
+      1000.0, q)
+  assert_bitwise_equal(a, expected, 'Moon')
+  # Collision: one probe inside the Earth (physics/ephemeris_test.cpp:763-811).
+  q[:, 7] = positions[names.index('Earth')] + [1e6, 2e6, 0.0]
+  a, status = sol_gpu.compute_gravitational_acceleration_on_massless_bodies(
+      1000.0, q)
+  expected, expected_status = sol_oracle.acceleration_on_massless_bodies(
+      1000.0, q)
+  assert status == expected_status == _capi.PB_OUT_OF_RANGE
+  assert_bitwise_equal(a, expected, 'collision')
+  # Empty batch.
+  a, status = sol_gpu.compute_gravitational_acceleration_on_massless_bodies(
+      0.0, np.zeros((3, 0)))
+  assert a.shape == (3, 0) and status == 0
+
+
+def test_potential(sol_system, sol_oracle, sol_gpu):
+  rng = np.random.default_rng(9)
+  names = sol_system.names()
+  positions = sol_oracle.evaluate_all_positions(5000.0)
+  centres = positions[[names.index(k) for k in ('Earth', 'Moon', 'Jupiter')]]
+  q = random_points_near(rng, centres, 1000)
+  assert_bitwise_equal(sol_gpu.compute_gravitational_potential(5000.0, q),
+                       sol_oracle.potential(5000.0, q))
+
+
+def test_acceleration_on_massive_bodies(sol_system, sol_oracle, sol_gpu):
+  for t in (0.0, 40000.0):
+    assert_bitwise_equal(
+        sol_gpu.compute_gravitational_acceleration_on_massive_bodies(t),
+        sol_oracle.acceleration_on_massive_bodies(t), 't=%r' % t)
+  rng = np.random.default_rng(2)
+  positions = sol_oracle.evaluate_all_positions(100.0)
+  positions += rng.normal(size=positions.shape) * 1e3
+  assert_bitwise_equal(
+      sol_gpu.compute_gravitational_acceleration_on_massive_bodies(
+          100.0, positions),
+      sol_oracle.acceleration_on_massive_bodies(100.0, positions))
+
+
+def leo(system, n, seed=42):
+  q, v, mu = earth_state(system, None)
+  return workloads.leo_probes(n, q, v, mu, seed)
+
+
+@pytest.mark.parametrize('method,evaluations', [
+    (_capi.BLANES_MOAN_2002_SRKN_14A, 14),
+    (_capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, 6)])
+def test_flow_with_fixed_step_matches_oracle(sol_system, sol_oracle, sol_gpu,
+                                             method, evaluations):
+  n = 1500  # Ragged: not a multiple of the block size.
+  state = leo(sol_system, n)
+  expected_state = state.copy()
+  time = np.array([0.0, 0.0])
+  expected_time = time.copy()
+  t_final = 605.0  # Not a multiple of the step: stops at 600 s.
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, t_final, state, time,
+                                        sample_every=7, max_samples=5)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, t_final,
+                                             expected_state, expected_time,
+                                             sample_every=7, max_samples=5)
+  assert result['n_steps'] == expected['n_steps'] == 60
+  assert result['status'] == expected['status'] == 0
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'state')
+  assert len(result['samples']) == len(expected['samples']) == 5
+  assert_bitwise_equal(result['sample_times'], expected['sample_times'])
+  assert_bitwise_equal(result['samples'], expected['samples'], 'samples')
+  # Restart from the updated state (Instance::Solve is restartable), across a
+  # chunk boundary of the stage table (> 256 steps).
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 3500.0, state, time)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, 3500.0,
+                                             expected_state, expected_time)
+  assert result['n_steps'] == expected['n_steps'] == 290
+  assert_bitwise_equal(time, expected_time, 'time 2')
+  assert_bitwise_equal(state, expected_state, 'state 2')
+
+
+def test_flow_with_fixed_step_backward_and_empty(sol_system, sol_oracle,
+                                                 sol_gpu):
+  method = _capi.BLANES_MOAN_2002_SRKN_14A
+  state = leo(sol_system, 64, seed=3)
+  time = np.array([0.0, 0.0])
+  sol_gpu.flow_with_fixed_step(method, 10.0, 300.0, state, time)
+  expected_state, expected_time = state.copy(), time.copy()
+  result = sol_gpu.flow_with_fixed_step(method, -10.0, 0.0, state, time)
+  expected = sol_oracle.flow_with_fixed_step(method, -10.0, 0.0,
+                                             expected_state, expected_time)
+  assert result['n_steps'] == expected['n_steps'] == 30
+  assert_bitwise_equal(state, expected_state, 'backward')
+  assert_bitwise_equal(time, expected_time)
+  # No probes: only the time advances.
+  empty = np.zeros((12, 0))
+  time = np.array([0.0, 0.0])
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 100.0, empty, time)
+  assert result['n_steps'] == 10 and time[0] == 100.0
+  # t_final closer than one step: nothing happens.
+  state = leo(sol_system, 8)
+  before = state.copy()
+  time = np.array([0.0, 0.0])
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 5.0, state, time)
+  assert result['n_steps'] == 0 and time[0] == 0.0
+  assert_bitwise_equal(state, before)
+  # Outside the ephemeris: refused (the facade prolongs first).
+  with pytest.raises(Exception):
+    sol_gpu.flow_with_fixed_step(method, 10.0, 2e5, state, time)
+
+
+def test_collision_status_and_continuation(sol_system, sol_oracle, sol_gpu):
+  """physics/ephemeris_test.cpp:763-811: an apple dropped above the Earth; the
+  fixed-step loop reports OutOfRange but keeps integrating."""
+  q, v, mu = earth_state(sol_system, None)
+  state = np.zeros((12, 3))
+  state[0:3] = q[:, None] + np.array([[6371008.4 + 10.0, 7e6, 0.0],
+                                      [0.0, 0.0, 7e6], [0.0, 0.0, 0.0]])
+  state[6:9] = v[:, None]
+  expected_state = state.copy()
+  time, expected_time = np.zeros(2), np.zeros(2)
+  method = _capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL
+  result = sol_gpu.flow_with_fixed_step(method, 1.0, 400.0, state, time)
+  expected = sol_oracle.flow_with_fixed_step(method, 1.0, 400.0,
+                                             expected_state, expected_time)
+  assert result['status'] == expected['status'] == _capi.PB_OUT_OF_RANGE
+  assert result['n_steps'] == expected['n_steps'] == 400
+  assert_bitwise_equal(state, expected_state, 'collision state')
+
+
+def test_full_size_flow_properties(sol_system, sol_oracle, sol_gpu):
+  """BASELINE.json config 2 at full size (10^5 probes): size-independent
+  properties -- probes are independent, so any subset equals the oracle bit for
+  bit; the time-reversible SRKN14A retraces its steps; the specific energy
+  relative to the Earth is conserved to the level of the perturbations."""
+  n = 100000
+  method = _capi.BLANES_MOAN_2002_SRKN_14A
+  state0 = leo(sol_system, n)
+  state = state0.copy()
+  time = np.zeros(2)
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 1000.0, state, time)
+  assert result['n_steps'] == 100 and result['status'] == 0
+  subset = np.r_[0:40, 49980:50020, n - 40:n]
+  expected_state = np.ascontiguousarray(state0[:, subset])
+  expected_time = np.zeros(2)
+  sol_oracle.flow_with_fixed_step(method, 10.0, 1000.0, expected_state,
+                                  expected_time)
+  assert_bitwise_equal(state[:, subset], expected_state, 'subset')
+  # Energy relative to the Earth.
+  earth = sol_system.index('Earth')
+  mu = sol_system.bodies[earth]['mu']
+
+  def energy(s, t):
+    positions = sol_oracle.evaluate_all_positions(t)
+    pe = positions[earth]
+    # Earth's velocity by a centred difference of its trajectory.
+    dt = 1.0
+    ve = (sol_oracle.evaluate_all_positions(min(t + dt, 172800.0))[earth] -
+          sol_oracle.evaluate_all_positions(max(t - dt, 0.0))[earth]) / (
+              min(t + dt, 172800.0) - max(t - dt, 0.0))
+    r = s[0:3] - pe[:, None]
+    w = s[6:9] - ve[:, None]
+    return 0.5 * np.sum(w * w, axis=0) - mu / np.linalg.norm(r, axis=0)
+
+  e0 = energy(state0, 0.0)
+  e1 = energy(state, 1000.0)
+  assert np.max(np.abs(e1 / e0 - 1)) < 2e-3  # J2-level exchange, no drift.
+  # Reversibility: integrate back; positions return to the start within
+  # round-off accumulated over 200 steps.
+  sol_gpu.flow_with_fixed_step(method, -10.0, 0.0, state, time)
+  assert time[0] == 0.0
+  displacement = np.linalg.norm(state[0:3] - state0[0:3], axis=0)
+  assert np.max(displacement) < 1e-4
