@@ -95,10 +95,11 @@ PB_HD int32_t AccelerationOnMasslessBody(EphemerisView const& e,
     acceleration += dq * mu1_over_dq3;
     if (b1 < e.n_oblate) {
       GeopotentialBody const g = MakeGeopotentialBody(e, b1);
-      double const* const frame =
+      FrameSource const frame{
           body1.frame_slot >= 0
               ? stage + 3 * e.n_bodies + 6 * body1.frame_slot
-              : nullptr;
+              : nullptr,
+          0.0};
       Vec3 const effect = GeneralSphericalHarmonicsAcceleration<kUnrolled>(
           g, frame, -dq, dq_norm, dq2, one_over_dq3);
       acceleration += mu1 * effect;
@@ -125,10 +126,11 @@ PB_HD double PotentialOnMasslessBody(EphemerisView const& e,
       double const one_over_dq3 =
           one_over_dq_norm * one_over_dq_norm * one_over_dq_norm;
       GeopotentialBody const g = MakeGeopotentialBody(e, b1);
-      double const* const frame =
+      FrameSource const frame{
           body1.frame_slot >= 0
               ? stage + 3 * e.n_bodies + 6 * body1.frame_slot
-              : nullptr;
+              : nullptr,
+          0.0};
       double const effect = GeneralSphericalHarmonicsPotential(
           g, frame, -dq, dq_norm, dq2, one_over_dq3);
       potential += mu1 * effect;
@@ -163,8 +165,8 @@ PB_HD void MassivePairInteraction(EphemerisView const& e, int const b1,
   acceleration_on_b1 -= dq * mu2_over_dq3;
   if (body1.is_oblate) {
     GeopotentialBody const g = MakeGeopotentialBody(e, b1);
-    double const* const frame =
-        body1.frame_slot >= 0 ? frames + 6 * body1.frame_slot : nullptr;
+    FrameSource const frame{
+        body1.frame_slot >= 0 ? frames + 6 * body1.frame_slot : nullptr, 0.0};
     Vec3 const effect = GeneralSphericalHarmonicsAcceleration<kUnrolled>(
         g, frame, -dq, dq_norm, dq2, one_over_dq3);
     acceleration_on_b1 -= mu2 * effect;
@@ -172,8 +174,8 @@ PB_HD void MassivePairInteraction(EphemerisView const& e, int const b1,
   }
   if (body2.is_oblate) {
     GeopotentialBody const g = MakeGeopotentialBody(e, b2);
-    double const* const frame =
-        body2.frame_slot >= 0 ? frames + 6 * body2.frame_slot : nullptr;
+    FrameSource const frame{
+        body2.frame_slot >= 0 ? frames + 6 * body2.frame_slot : nullptr, 0.0};
     Vec3 const effect = GeneralSphericalHarmonicsAcceleration<kUnrolled>(
         g, frame, dq, dq_norm, dq2, one_over_dq3);
     acceleration_on_b1 += mu2 * effect;

@@ -1,0 +1,137 @@
+// C ABI: Ephemeris::FlowWithAdaptiveStep, batched (include/principia_b200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/principia_b200.h"
+#include "pb_kernels_adaptive.cuh"
+#include "pb_runtime.cuh"
+
+using namespace pb;
+
+extern "C" {
+
+pb_status_t pb_flow_with_adaptive_step_device(
+    pb_ephemeris_t* e, const pb_adaptive_step_flow_t* flow,
+    void* stream_pointer) {
+  if (e == nullptr || flow == nullptr || flow->n < 0 ||
+      (flow->n > 0 && (flow->state == nullptr || flow->time == nullptr))) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  if (flow->method != PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "adaptive massless flow supports "
+                "DormandElMikkawyPrince1986RKN434FM");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
+  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
+  AdaptiveParameters parameters;
+  parameters.t_requested = flow->t_final;
+  // FlowODEWithAdaptiveStep: t_final = min(t, t_max()) (after Prolong, which is
+  // the facade's job here).
+  parameters.t_final = std::min(flow->t_final, EphemerisTMax(e));
+  parameters.length_integration_tolerance = flow->length_integration_tolerance;
+  parameters.speed_integration_tolerance = flow->speed_integration_tolerance;
+  parameters.max_steps = flow->max_steps;
+  parameters.step_log_capacity =
+      flow->step_log != nullptr ? flow->step_log_capacity : 0;
+  if (flow->n == 0) {
+    return PB_OK;
+  }
+  while (e->timing_events.size() < 2) {
+    cudaEvent_t event;
+    PB_CUDA(cudaEventCreate(&event));
+    e->timing_events.push_back(event);
+  }
+  PB_CUDA(cudaEventRecord(e->timing_events[0], stream));
+  ErknFlowKernel<true>
+      <<<static_cast<unsigned>((flow->n + kAdaptiveThreads - 1) /
+                               kAdaptiveThreads),
+         kAdaptiveThreads, 0, stream>>>(
+          e->View(), parameters, flow->n, flow->state, flow->time, flow->status,
+          reinterpret_cast<long long*>(flow->accepted_steps),
+          reinterpret_cast<long long*>(flow->rejected_steps),
+          reinterpret_cast<long long*>(flow->evaluations), flow->step_log);
+  PB_LAUNCHED();
+  PB_CUDA(cudaEventRecord(e->timing_events[1], stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  float elapsed = 0;
+  PB_CUDA(cudaEventElapsedTime(&elapsed, e->timing_events[0],
+                               e->timing_events[1]));
+  e->last_flow_kernel_ms = elapsed;
+  e->last_flow_kernel_launches = 1;
+  return PB_OK;
+}
+
+pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
+                                       const pb_adaptive_step_flow_t* flow) {
+  if (e == nullptr || flow == nullptr || flow->n < 0 ||
+      (flow->n > 0 && (flow->state == nullptr || flow->time == nullptr))) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  std::size_t const n = static_cast<std::size_t>(flow->n);
+  DeviceBuffer<double> state, time, step_log;
+  DeviceBuffer<int32_t> status;
+  DeviceBuffer<long long> counters;
+  PB_RETURN_IF_ERROR(state.Upload(flow->state, 12 * n, stream));
+  PB_RETURN_IF_ERROR(time.Upload(flow->time, 2 * n, stream));
+  PB_RETURN_IF_ERROR(status.Reserve(n + 1));
+  PB_RETURN_IF_ERROR(counters.Reserve(3 * n + 1));
+  pb_adaptive_step_flow_t device_flow = *flow;
+  device_flow.state = state.data;
+  device_flow.time = time.data;
+  device_flow.status = status.data;
+  device_flow.accepted_steps = reinterpret_cast<int64_t*>(counters.data);
+  device_flow.rejected_steps = reinterpret_cast<int64_t*>(counters.data + n);
+  device_flow.evaluations = reinterpret_cast<int64_t*>(counters.data + 2 * n);
+  bool const logging = flow->step_log != nullptr && flow->step_log_capacity > 0;
+  if (logging) {
+    std::size_t const size = static_cast<std::size_t>(flow->step_log_capacity) * n;
+    PB_RETURN_IF_ERROR(step_log.Upload(flow->step_log, size, stream));
+    device_flow.step_log = step_log.data;
+  } else {
+    device_flow.step_log = nullptr;
+    device_flow.step_log_capacity = 0;
+  }
+  PB_RETURN_IF_ERROR(
+      pb_flow_with_adaptive_step_device(e, &device_flow, stream));
+  if (n > 0) {
+    PB_CUDA(cudaMemcpyAsync(flow->state, state.data, 12 * n * sizeof(double),
+                            cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaMemcpyAsync(flow->time, time.data, 2 * n * sizeof(double),
+                            cudaMemcpyDeviceToHost, stream));
+    if (flow->status != nullptr) {
+      PB_CUDA(cudaMemcpyAsync(flow->status, status.data, n * sizeof(int32_t),
+                              cudaMemcpyDeviceToHost, stream));
+    }
+    if (flow->accepted_steps != nullptr) {
+      PB_CUDA(cudaMemcpyAsync(flow->accepted_steps, counters.data,
+                              n * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                              stream));
+    }
+    if (flow->rejected_steps != nullptr) {
+      PB_CUDA(cudaMemcpyAsync(flow->rejected_steps, counters.data + n,
+                              n * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                              stream));
+    }
+    if (flow->evaluations != nullptr) {
+      PB_CUDA(cudaMemcpyAsync(flow->evaluations, counters.data + 2 * n,
+                              n * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                              stream));
+    }
+    if (logging) {
+      PB_CUDA(cudaMemcpyAsync(
+          flow->step_log, step_log.data,
+          static_cast<std::size_t>(flow->step_log_capacity) * n * sizeof(double),
+          cudaMemcpyDeviceToHost, stream));
+    }
+  }
+  PB_CUDA(cudaStreamSynchronize(stream));
+  return PB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,327 @@
+// C ABI: massive-body flows (include/principia_b200.h): ensembles of small
+// systems and the large-N all-pairs system.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/principia_b200.h"
+#include "pb_kernels_nbody.cuh"
+#include "pb_runtime.cuh"
+
+using namespace pb;
+
+namespace pb {
+
+bool MakeSrknTableau(int32_t method, SrknTableau& t);
+void ComputeNodes(SrknTableau const& tableau, double* c);
+
+bool MakeMultistepMethod(int32_t const method, MultistepMethod& m) {
+  std::memset(&m, 0, sizeof(m));
+  if (method == PB_QUINLAN_1999_ORDER_8A) {
+    // integrators/methods.hpp:998-1007.
+    m.order = 8;
+    double const alpha[] = {1.0, -2.0, 2.0, -2.0, 2.0};
+    double const beta[] = {0.0, 22081.0, -29418.0, 75183.0, -75212.0};
+    double const cho[] = {416173.0,  950684.0, -1025097.0, 1059430.0,
+                          -768805.0, 362112.0, -99359.0,   12062.0};
+    std::memcpy(m.alpha, alpha, sizeof(alpha));
+    std::memcpy(m.beta_numerator, beta, sizeof(beta));
+    std::memcpy(m.cho_numerators, cho, sizeof(cho));
+    m.beta_denominator = 15120.0;
+    m.cho_denominator = 1814400.0;
+    return true;
+  }
+  if (method == PB_QUINLAN_TREMAINE_1990_ORDER_12) {
+    // integrators/methods.hpp:1040-1055.
+    m.order = 12;
+    double const alpha[] = {1.0, -2.0, 2.0, -1.0, 0.0, 0.0, 0.0};
+    double const beta[] = {0.0,           90987349.0,   -229596838.0,
+                           812627169.0,   -1628539944.0, 2714971338.0,
+                           -3041896548.0};
+    double const cho[] = {92158447389.0,    301307140046.0,  -554452444015.0,
+                          1035372815340.0,  -1505150506950.0, 1655690777412.0,
+                          -1363696062582.0, 828085590240.0,  -360089099415.0,
+                          106193749950.0,   -19043781851.0,  1569102436.0};
+    std::memcpy(m.alpha, alpha, sizeof(alpha));
+    std::memcpy(m.beta_numerator, beta, sizeof(beta));
+    std::memcpy(m.cho_numerators, cho, sizeof(cho));
+    m.beta_denominator = 53222400.0;
+    m.cho_denominator = 435891456000.0;
+    return true;
+  }
+  return false;
+}
+
+}  // namespace pb
+
+struct pb_nbody_ensemble {
+  pb_ephemeris* ephemeris = nullptr;
+  int32_t method = 0;
+  bool is_multistep = false;
+  SrknTableau tableau;          // The method itself, or the SRKN14A starter.
+  double nodes[16];
+  MultistepMethod multistep;
+  double step = 0;
+  long long n_systems = 0;
+  int n_bodies = 0;
+  DP time{0.0, 0.0};
+  // Starter state.
+  int previous_steps = 0;       // previous_steps_.size().
+  long long startup_step_index = 0;
+  int oldest = 0;               // Ring slot of previous_steps_.front().
+  DeviceBuffer<double> state;
+  DeviceBuffer<double> displacement_value, displacement_error, acceleration;
+  DeviceBuffer<double> frame_times, frames;
+  MultistepHistory History() {
+    return {displacement_value.data, displacement_error.data,
+            acceleration.data};
+  }
+};
+
+namespace {
+
+unsigned EnsembleGrid(long long const n_systems) {
+  return static_cast<unsigned>((n_systems + kEnsembleThreads - 1) /
+                               kEnsembleThreads);
+}
+
+// Surface-frame axes at the given times -> ensemble->frames.
+pb_status_t BuildFrames(pb_nbody_ensemble* s, std::vector<double> const& times,
+                        cudaStream_t stream) {
+  EphemerisView const view = s->ephemeris->View();
+  std::size_t const size =
+      std::max<std::size_t>(1, times.size() * 6 * view.n_frames);
+  PB_RETURN_IF_ERROR(s->frames.Reserve(size));
+  if (view.n_frames == 0) {
+    return PB_OK;
+  }
+  PB_RETURN_IF_ERROR(s->frame_times.Upload(times, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  int const threads = static_cast<int>(times.size()) * view.n_bodies;
+  FrameTableKernel<<<(threads + 63) / 64, 64, 0, stream>>>(
+      view, s->frame_times.data, static_cast<int>(times.size()),
+      s->frames.data);
+  PB_LAUNCHED();
+  return PB_OK;
+}
+
+template<typename Launch8, typename LaunchGeneric>
+pb_status_t Dispatch(int const n_bodies, Launch8 launch8,
+                     LaunchGeneric launch_generic) {
+  if (n_bodies == 8) {
+    launch8();
+  } else {
+    launch_generic();
+  }
+  PB_LAUNCHED();
+  return PB_OK;
+}
+
+// One SRKN step of size h from the current time; updates the time.
+pb_status_t SrknStep(pb_nbody_ensemble* s, double const h,
+                     cudaStream_t stream) {
+  EphemerisView const view = s->ephemeris->View();
+  std::vector<double> times;
+  for (int st = s->tableau.first_stage; st < s->tableau.stages; ++st) {
+    times.push_back(s->time.value + (s->time.error + s->nodes[st] * h));
+  }
+  PB_RETURN_IF_ERROR(BuildFrames(s, times, stream));
+  unsigned const grid = EnsembleGrid(s->n_systems);
+  PB_RETURN_IF_ERROR(Dispatch(
+      s->n_bodies,
+      [&] {
+        EnsembleSrknStepKernel<8><<<grid, kEnsembleThreads, 0, stream>>>(
+            view, s->tableau, h, s->frames.data, s->n_systems, s->state.data);
+      },
+      [&] {
+        EnsembleSrknStepKernel<0><<<grid, kEnsembleThreads, 0, stream>>>(
+            view, s->tableau, h, s->frames.data, s->n_systems, s->state.data);
+      }));
+  Increment(s->time, h);
+  return PB_OK;
+}
+
+// FillStepFromState into ring slot `slot`.
+pb_status_t FillStep(pb_nbody_ensemble* s, int const slot,
+                     cudaStream_t stream) {
+  EphemerisView const view = s->ephemeris->View();
+  PB_RETURN_IF_ERROR(BuildFrames(s, {s->time.value}, stream));
+  unsigned const grid = EnsembleGrid(s->n_systems);
+  MultistepHistory const history = s->History();
+  return Dispatch(
+      s->n_bodies,
+      [&] {
+        EnsembleFillStepKernel<8><<<grid, kEnsembleThreads, 0, stream>>>(
+            view, s->frames.data, s->n_systems, s->state.data, history, slot);
+      },
+      [&] {
+        EnsembleFillStepKernel<0><<<grid, kEnsembleThreads, 0, stream>>>(
+            view, s->frames.data, s->n_systems, s->state.data, history, slot);
+      });
+}
+
+pb_status_t MultistepStep(pb_nbody_ensemble* s, cudaStream_t stream) {
+  EphemerisView const view = s->ephemeris->View();
+  DP t = s->time;
+  Increment(t, s->step);
+  PB_RETURN_IF_ERROR(BuildFrames(s, {t.value}, stream));
+  unsigned const grid = EnsembleGrid(s->n_systems);
+  MultistepHistory const history = s->History();
+  PB_RETURN_IF_ERROR(Dispatch(
+      s->n_bodies,
+      [&] {
+        EnsembleMultistepStepKernel<8><<<grid, kEnsembleThreads, 0, stream>>>(
+            view, s->multistep, s->step, s->frames.data, s->n_systems,
+            s->state.data, history, s->oldest);
+      },
+      [&] {
+        EnsembleMultistepStepKernel<0><<<grid, kEnsembleThreads, 0, stream>>>(
+            view, s->multistep, s->step, s->frames.data, s->n_systems,
+            s->state.data, history, s->oldest);
+      }));
+  s->oldest = (s->oldest + 1) % s->multistep.order;
+  s->time = t;
+  return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+pb_status_t pb_nbody_ensemble_create(pb_ephemeris_t* e, int32_t method,
+                                     double step, int64_t n_systems,
+                                     const double* state, double initial_time,
+                                     pb_nbody_ensemble_t** ensemble) {
+  if (e == nullptr || ensemble == nullptr || n_systems <= 0 ||
+      state == nullptr || !(step > 0)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  *ensemble = nullptr;
+  int const n_bodies = static_cast<int>(e->model.bodies.size());
+  if (n_bodies > kMaxEnsembleBodies) {
+    return Fail(PB_INVALID_ARGUMENT, "too many bodies for an ensemble");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  auto* s = new pb_nbody_ensemble;
+  s->ephemeris = e;
+  s->method = method;
+  s->step = step;
+  s->n_systems = n_systems;
+  s->n_bodies = n_bodies;
+  s->time = {initial_time, 0.0};
+  if (MakeMultistepMethod(method, s->multistep)) {
+    s->is_multistep = true;
+    MakeSrknTableau(PB_BLANES_MOAN_2002_SRKN_14A, s->tableau);
+  } else if (!MakeSrknTableau(method, s->tableau)) {
+    delete s;
+    return Fail(PB_INVALID_ARGUMENT, "unsupported fixed-step method");
+  }
+  ComputeNodes(s->tableau, s->nodes);
+  std::size_t const planes =
+      static_cast<std::size_t>(n_bodies) * static_cast<std::size_t>(n_systems);
+  pb_status_t status = s->state.Upload(state, 12 * planes, nullptr);
+  if (status == PB_OK && s->is_multistep) {
+    std::size_t const size = 3 * planes * s->multistep.order;
+    status = s->displacement_value.Reserve(size);
+    if (status == PB_OK) status = s->displacement_error.Reserve(size);
+    if (status == PB_OK) status = s->acceleration.Reserve(size);
+  }
+  if (status == PB_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) {
+    status = Fail(PB_INTERNAL, "upload failed");
+  }
+  if (status != PB_OK) {
+    delete s;
+    return status;
+  }
+  *ensemble = s;
+  return PB_OK;
+}
+
+void pb_nbody_ensemble_destroy(pb_nbody_ensemble_t* ensemble) {
+  if (ensemble != nullptr) {
+    cudaSetDevice(ensemble->ephemeris->device);
+    delete ensemble;
+  }
+}
+
+pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* s, double t_final,
+                                    int64_t* n_steps) {
+  if (s == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null ensemble");
+  }
+  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  cudaStream_t const stream = nullptr;
+  int64_t steps = 0;
+  double const h = s->step;
+  if (!s->is_multistep) {
+    // SymplecticRungeKuttaNyströmIntegrator::Instance::Solve.
+    while (h <= std::abs((t_final - s->time.value) - s->time.error)) {
+      PB_RETURN_IF_ERROR(SrknStep(s, h, stream));
+      ++steps;
+    }
+  } else {
+    int const order = s->multistep.order;
+    if (s->previous_steps < order) {
+      // Starter::Solve, integrators/starter_body.hpp:23-74.
+      if (s->previous_steps == 0) {
+        PB_RETURN_IF_ERROR(FillStep(s, 0, stream));
+        s->previous_steps = 1;
+      }
+      double const startup_step = h / kStartupStepDivisor;
+      double const target =
+          std::min(s->time.value + (order - s->previous_steps) * h + h / 2.0,
+                   t_final);
+      // A fresh startup instance integrates from the current state; its own
+      // time is the instance's current time.
+      while (startup_step <=
+                 std::abs((target - s->time.value) - s->time.error) &&
+             s->previous_steps < order) {
+        PB_RETURN_IF_ERROR(SrknStep(s, startup_step, stream));
+        if (++s->startup_step_index % kStartupStepDivisor == 0) {
+          PB_RETURN_IF_ERROR(FillStep(s, s->previous_steps, stream));
+          ++s->previous_steps;
+          ++steps;  // instance_->append_state()(state).
+        }
+      }
+      if (s->previous_steps < order) {
+        PB_CUDA(cudaStreamSynchronize(stream));
+        if (n_steps != nullptr) {
+          *n_steps = steps;
+        }
+        return PB_OK;  // "we'll continue the next time Solve is called".
+      }
+      s->oldest = 0;
+    }
+    while (h <= (t_final - s->time.value) - s->time.error) {
+      PB_RETURN_IF_ERROR(MultistepStep(s, stream));
+      ++steps;
+    }
+  }
+  PB_CUDA(cudaStreamSynchronize(stream));
+  if (n_steps != nullptr) {
+    *n_steps = steps;
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_nbody_ensemble_get_state(pb_nbody_ensemble_t* s, double* state,
+                                        double* time) {
+  if (s == nullptr || state == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  std::size_t const size = 12 * static_cast<std::size_t>(s->n_bodies) *
+                           static_cast<std::size_t>(s->n_systems);
+  PB_CUDA(cudaMemcpy(state, s->state.data, size * sizeof(double),
+                     cudaMemcpyDeviceToHost));
+  if (time != nullptr) {
+    time[0] = s->time.value;
+    time[1] = s->time.error;
+  }
+  return PB_OK;
+}
+
+}  // extern "C"

@@ -182,6 +182,7 @@ struct GenericPrecomputations {
 
 // DegreeNOrderM::UpdatePrecomputations, geopotential_body.hpp:249-331.
 PB_HD void GenericUpdateOrder(int const n, int const m, double const sin_beta,
+                              double const one_over_n,
                               GenericPrecomputations& p) {
   double* const Pn = p.P[n % 3];
   double const* const Pn1 = p.P[(n + 2) % 3];
@@ -213,19 +214,24 @@ PB_HD void GenericUpdateOrder(int const n, int const m, double const sin_beta,
       p.cos_beta_to_the_m[m] = cos_beta_to_the_h1 * cos_beta_to_the_h2;
     }
   }
+  // The divisions by n are correctly rounded (DivideBySmallInteger).
   if (m == 0) {
-    Pn[0] = ((2 * n - 1) * sin_beta * Pn1[0] - (n - 1) * Pn2[0]) / n;
+    Pn[0] = DivideBySmallInteger(
+        (2 * n - 1) * sin_beta * Pn1[0] - (n - 1) * Pn2[0], n, one_over_n);
   }
   if (m == n) {
   } else if (m == n - 1) {
-    Pn[m + 1] = ((2 * n - 1) * (m + 1) * Pn1[m]) / n;
-  } else if (m == n - 2) {
     Pn[m + 1] =
-        ((2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m])) / n;
+        DivideBySmallInteger((2 * n - 1) * (m + 1) * Pn1[m], n, one_over_n);
+  } else if (m == n - 2) {
+    Pn[m + 1] = DivideBySmallInteger(
+        (2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m]), n,
+        one_over_n);
   } else {
-    Pn[m + 1] = ((2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m]) -
-                 (n - 1) * Pn2[m + 1]) /
-                n;
+    Pn[m + 1] = DivideBySmallInteger(
+        (2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m]) -
+            (n - 1) * Pn2[m + 1],
+        n, one_over_n);
   }
 }
 
@@ -344,6 +350,7 @@ PB_HD_NOINLINE Vec3 GeopotentialGenericAcceleration(
   Vec3 degree_sum[kGeopotentialSize];
   for (int n = 2; n <= max_degree; ++n) {
     int const size = is_zonal ? 1 : n + 1;
+    double const one_over_n = 1.0 / n;
     GenericUpdateDegree(n, s.r2, p.R_over_r);
     double const R_over_r = p.R_over_r[n];
     double const R_prime = -(n + 1) * R_over_r;
@@ -353,14 +360,14 @@ PB_HD_NOINLINE Vec3 GeopotentialGenericAcceleration(
       ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
-      GenericUpdateOrder(2, 0, s.sin_beta, p);
+      GenericUpdateOrder(2, 0, s.sin_beta, one_over_n, p);
       Vec3 const j2_acceleration =
           GenericTerm(g, 2, 0, sigma_R_over_r, grad_sigma_R, s, p);
       ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
-      GenericUpdateOrder(2, 1, s.sin_beta, p);
-      GenericUpdateOrder(2, 2, s.sin_beta, p);
+      GenericUpdateOrder(2, 1, s.sin_beta, one_over_n, p);
+      GenericUpdateOrder(2, 2, s.sin_beta, one_over_n, p);
       Vec3 const c22_s22_acceleration =
           GenericTerm(g, 2, 2, sigma_R_over_r, grad_sigma_R, s, p);
       degree_sum[n] = j2_acceleration + c22_s22_acceleration;
@@ -369,7 +376,7 @@ PB_HD_NOINLINE Vec3 GeopotentialGenericAcceleration(
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
       for (int m = 0; m < size; ++m) {
-        GenericUpdateOrder(n, m, s.sin_beta, p);
+        GenericUpdateOrder(n, m, s.sin_beta, one_over_n, p);
       }
       Vec3 sum = GenericTerm(g, n, size - 1, sigma_R_over_r, grad_sigma_R, s, p);
       for (int m = size - 2; m >= 0; --m) {
@@ -397,19 +404,20 @@ PB_HD_NOINLINE double GeopotentialGenericPotential(
   double degree_sum[kGeopotentialSize];
   for (int n = 2; n <= max_degree; ++n) {
     int const size = is_zonal ? 1 : n + 1;
+    double const one_over_n = 1.0 / n;
     GenericUpdateDegree(n, s.r2, p.R_over_r);
     double const R_over_r = p.R_over_r[n];
     double sigma_R_over_r;
     if (n == 2 && size > 1) {
       ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
                                     R_over_r, sigma_R_over_r);
-      GenericUpdateOrder(2, 0, s.sin_beta, p);
+      GenericUpdateOrder(2, 0, s.sin_beta, one_over_n, p);
       double const j2_potential =
           GenericTermPotential(g, 2, 0, sigma_R_over_r, s, p);
       ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2, R_over_r,
                                     sigma_R_over_r);
-      GenericUpdateOrder(2, 1, s.sin_beta, p);
-      GenericUpdateOrder(2, 2, s.sin_beta, p);
+      GenericUpdateOrder(2, 1, s.sin_beta, one_over_n, p);
+      GenericUpdateOrder(2, 2, s.sin_beta, one_over_n, p);
       double const c22_s22_potential =
           GenericTermPotential(g, 2, 2, sigma_R_over_r, s, p);
       degree_sum[n] = j2_potential + c22_s22_potential;
@@ -417,7 +425,7 @@ PB_HD_NOINLINE double GeopotentialGenericPotential(
       ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
                                     R_over_r, sigma_R_over_r);
       for (int m = 0; m < size; ++m) {
-        GenericUpdateOrder(n, m, s.sin_beta, p);
+        GenericUpdateOrder(n, m, s.sin_beta, one_over_n, p);
       }
       double sum = GenericTermPotential(g, n, size - 1, sigma_R_over_r, s, p);
       for (int m = size - 2; m >= 0; --m) {
@@ -495,25 +503,28 @@ PB_HD void UnrolledUpdateOrder(double const sin_beta,
         p.cos_beta_to_the_m[m] = cos_beta_to_the_h1 * cos_beta_to_the_h2;
       }
     }
+    constexpr double one_over_n = 1.0 / n;
     if constexpr (m == 0) {
-      p.P[Tri(n, 0)] = ((2 * n - 1) * sin_beta * p.P[Tri(n - 1, 0)] -
-                        (n - 1) * p.P[Tri(n - 2, 0)]) /
-                       n;
+      p.P[Tri(n, 0)] = DivideBySmallInteger(
+          (2 * n - 1) * sin_beta * p.P[Tri(n - 1, 0)] -
+              (n - 1) * p.P[Tri(n - 2, 0)],
+          n, one_over_n);
     }
     if constexpr (m == n) {
     } else if constexpr (m == n - 1) {
-      p.P[Tri(n, m + 1)] = ((2 * n - 1) * (m + 1) * p.P[Tri(n - 1, m)]) / n;
+      p.P[Tri(n, m + 1)] = DivideBySmallInteger(
+          (2 * n - 1) * (m + 1) * p.P[Tri(n - 1, m)], n, one_over_n);
     } else if constexpr (m == n - 2) {
-      p.P[Tri(n, m + 1)] =
-          ((2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
-                          (m + 1) * p.P[Tri(n - 1, m)])) /
-          n;
+      p.P[Tri(n, m + 1)] = DivideBySmallInteger(
+          (2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
+                         (m + 1) * p.P[Tri(n - 1, m)]),
+          n, one_over_n);
     } else {
-      p.P[Tri(n, m + 1)] =
-          ((2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
-                          (m + 1) * p.P[Tri(n - 1, m)]) -
-           (n - 1) * p.P[Tri(n - 2, m + 1)]) /
-          n;
+      p.P[Tri(n, m + 1)] = DivideBySmallInteger(
+          (2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
+                         (m + 1) * p.P[Tri(n - 1, m)]) -
+              (n - 1) * p.P[Tri(n - 2, m + 1)],
+          n, one_over_n);
     }
   }
 }
@@ -627,13 +638,21 @@ PB_HD Vec3 GeopotentialUnrolledDispatch(GeopotentialBody const& g,
 // ===========================================================================
 // Entry points.
 
+// Where the surface-frame axes of a non-zonal evaluation come from: a stage
+// table entry (6 doubles, computed once per stage time for all probes) or, for
+// per-probe times (adaptive flow), the time itself.
+struct FrameSource {
+  double const* axes;
+  double t;
+};
+
 // Geopotential::GeneralSphericalHarmonicsAcceleration, :740-813.  `frame` holds
 // the surface-frame x and y axes at the evaluation time (6 doubles) when the
 // body has a frame slot; zonal evaluation uses the body's fixed axes.
 // kUnrolled selects the register-resident path for max_degree <= 10.
 template<bool kUnrolled>
 PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
-                                                 double const* frame,
+                                                 FrameSource const frame,
                                                  Vec3 const& r,
                                                  double const r_norm,
                                                  double const r2,
@@ -655,9 +674,11 @@ PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
   if (is_zonal) {
     x_hat = body.equatorial;
     y_hat = body.biequatorial;
+  } else if (frame.axes != nullptr) {
+    x_hat = {frame.axes[0], frame.axes[1], frame.axes[2]};
+    y_hat = {frame.axes[3], frame.axes[4], frame.axes[5]};
   } else {
-    x_hat = {frame[0], frame[1], frame[2]};
-    y_hat = {frame[3], frame[4], frame[5]};
+    SurfaceFrameAxes(body, frame.t, x_hat, y_hat);
   }
   GeopotentialSetup s;
   InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
@@ -675,7 +696,7 @@ PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
 
 // Geopotential::GeneralSphericalHarmonicsPotential, :822-895.
 PB_HD double GeneralSphericalHarmonicsPotential(GeopotentialBody const& g,
-                                                double const* frame,
+                                                FrameSource const frame,
                                                 Vec3 const& r,
                                                 double const r_norm,
                                                 double const r2,
@@ -695,9 +716,11 @@ PB_HD double GeneralSphericalHarmonicsPotential(GeopotentialBody const& g,
   if (is_zonal) {
     x_hat = body.equatorial;
     y_hat = body.biequatorial;
+  } else if (frame.axes != nullptr) {
+    x_hat = {frame.axes[0], frame.axes[1], frame.axes[2]};
+    y_hat = {frame.axes[3], frame.axes[4], frame.axes[5]};
   } else {
-    x_hat = {frame[0], frame[1], frame[2]};
-    y_hat = {frame[3], frame[4], frame[5]};
+    SurfaceFrameAxes(body, frame.t, x_hat, y_hat);
   }
   GeopotentialSetup s;
   InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);

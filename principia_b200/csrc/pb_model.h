@@ -75,4 +75,12 @@ PB_HD int StageStride(int const n_bodies, int const n_frames) {
   return 3 * n_bodies + 6 * n_frames;
 }
 
+// Tableau of a symplectic Runge-Kutta-Nyström method, integrators/methods.hpp.
+struct SrknTableau {
+  int stages;
+  int first_stage;  // 0 for BA, 1 for ABA.
+  double a[16];
+  double b[16];
+};
+
 }  // namespace pb

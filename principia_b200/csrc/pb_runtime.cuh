@@ -193,3 +193,12 @@ struct pb_ephemeris {
     return v;
   }
 };
+
+namespace pb {
+// Defined in principia_b200.cu.
+pb_status_t UploadSegments(pb_ephemeris* e, cudaStream_t stream);
+double EphemerisTMin(pb_ephemeris const* e);
+double EphemerisTMax(pb_ephemeris const* e);
+pb_status_t BuildStageTable(pb_ephemeris* e, double const* times_host,
+                            int n_times, double* table, cudaStream_t stream);
+}  // namespace pb

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -112,6 +113,17 @@ void ComputeNodes(SrknTableau const& tableau, double* c) {
     c[i] = c_i.value;
     c_i = Add(c_i, DP{tableau.a[i], 0.0});
   }
+}
+
+// Resident blocks per SM the flow kernel is compiled for (register budget
+// 65536 / (128 * blocks)); PB_SRKN_MIN_BLOCKS overrides it for experiments.
+int SrknMinBlocks() {
+  static int const value = [] {
+    char const* const text = std::getenv("PB_SRKN_MIN_BLOCKS");
+    int const v = text != nullptr ? std::atoi(text) : 3;
+    return v == 2 || v == 4 ? v : 3;
+  }();
+  return value;
 }
 
 bool MakeSrknTableau(int32_t method, SrknTableau& t) {
@@ -525,12 +537,20 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
         e->timing_events.push_back(event);
       }
       PB_CUDA(cudaEventRecord(e->timing_events[2 * launches], stream));
-      SrknFlowKernel<true>
-          <<<static_cast<unsigned>((flow->n + kFlowThreads - 1) / kFlowThreads),
-             kFlowThreads, 0, stream>>>(
-              view, tableau, h, e->stage_table.data, steps, flow->n,
-              flow->state, steps_done, sampling ? flow->sample_every : 0,
-              flow->max_samples, flow->samples, e->status_word.data);
+      unsigned const grid =
+          static_cast<unsigned>((flow->n + kFlowThreads - 1) / kFlowThreads);
+      long long const every = sampling ? flow->sample_every : 0;
+#define PB_LAUNCH_SRKN(kMinBlocks)                                            \
+  SrknFlowKernel<true, kMinBlocks><<<grid, kFlowThreads, 0, stream>>>(        \
+      view, tableau, h, e->stage_table.data, steps, flow->n, flow->state,     \
+      steps_done, every, flow->max_samples, flow->samples,                    \
+      e->status_word.data)
+      switch (SrknMinBlocks()) {
+        case 2: PB_LAUNCH_SRKN(2); break;
+        case 4: PB_LAUNCH_SRKN(4); break;
+        default: PB_LAUNCH_SRKN(3); break;
+      }
+#undef PB_LAUNCH_SRKN
       PB_LAUNCHED();
       PB_CUDA(cudaEventRecord(e->timing_events[2 * launches + 1], stream));
       ++launches;

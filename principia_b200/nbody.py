@@ -1,0 +1,110 @@
+"""Python mirror of the massive-body flows of the C ABI: ensembles of small
+systems sharing one gravity model (the reference runs one Ephemeris per
+ensemble member, astronomy/trappist_dynamics_test.cpp:275-297) and the
+large-N all-pairs system sharded by target block."""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from .ephemeris import _check, _dptr
+
+_vp = ctypes.c_void_p
+
+
+class NBodyEnsemble:
+  """pb_nbody_ensemble_t: n_systems copies of the ephemeris' bodies, advanced
+  by a fixed-step integrator instance (Integrator::Instance::Solve)."""
+
+  def __init__(self, ephemeris, method, step, state, initial_time):
+    """state: (12, n_bodies, n_systems) float64, bodies in INTERNAL order."""
+    self.lib = _capi.library()
+    self.ephemeris = ephemeris
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    assert state.shape[0] == 12 and state.shape[1] == ephemeris.n_bodies
+    self.shape = state.shape
+    handle = _vp()
+    _check(self.lib.pb_nbody_ensemble_create(
+        ephemeris.handle, method, step, state.shape[2], _dptr(state),
+        initial_time, ctypes.byref(handle)))
+    self.handle = handle
+
+  def close(self):
+    if getattr(self, 'handle', None):
+      self.lib.pb_nbody_ensemble_destroy(self.handle)
+      self.handle = None
+
+  def __del__(self):
+    self.close()
+
+  def solve(self, t_final):
+    n_steps = ctypes.c_int64()
+    _check(self.lib.pb_nbody_ensemble_solve(self.handle, t_final,
+                                            ctypes.byref(n_steps)))
+    return n_steps.value
+
+  def state(self):
+    state = np.zeros(self.shape)
+    time = np.zeros(2)
+    _check(self.lib.pb_nbody_ensemble_get_state(self.handle, _dptr(state),
+                                                _dptr(time)))
+    return state, time
+
+
+class NBodyAllPairs:
+  """pb_nbody_allpairs_t: n point masses, this rank owning targets
+  [i_begin, i_end)."""
+
+  def __init__(self, method, step, mu, q, v, initial_time, i_begin=0,
+               i_end=None, device=0, exchange=None):
+    """mu: (n,), q, v: (3, n).  `exchange(positions_device_pointer, n, i_begin,
+    i_end, stream)` is called after every position update when given."""
+    self.lib = _capi.library()
+    mu = np.ascontiguousarray(mu, dtype=np.float64)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    self.n = len(mu)
+    self.i_begin = i_begin
+    self.i_end = self.n if i_end is None else i_end
+    if exchange is None:
+      self._callback = ctypes.cast(None, _capi.EXCHANGE_POSITIONS)
+    else:
+      def trampoline(user, positions, n, begin, end, stream):
+        exchange(positions, n, begin, end, stream)
+      self._callback = _capi.EXCHANGE_POSITIONS(trampoline)
+    handle = _vp()
+    _check(self.lib.pb_nbody_allpairs_create(
+        device, method, step, self.n, self.i_begin, self.i_end, _dptr(mu),
+        _dptr(q), _dptr(v), initial_time, self._callback, None,
+        ctypes.byref(handle)))
+    self.handle = handle
+
+  def close(self):
+    if getattr(self, 'handle', None):
+      self.lib.pb_nbody_allpairs_destroy(self.handle)
+      self.handle = None
+
+  def __del__(self):
+    self.close()
+
+  def solve(self, t_final):
+    n_steps, n_forces = ctypes.c_int64(), ctypes.c_int64()
+    _check(self.lib.pb_nbody_allpairs_solve(self.handle, t_final,
+                                            ctypes.byref(n_steps),
+                                            ctypes.byref(n_forces)))
+    return n_steps.value, n_forces.value
+
+  def state(self):
+    n_local = self.i_end - self.i_begin
+    q, v, time = np.zeros((3, n_local)), np.zeros((3, n_local)), np.zeros(2)
+    _check(self.lib.pb_nbody_allpairs_get_state(self.handle, _dptr(q),
+                                                _dptr(v), _dptr(time)))
+    return q, v, time
+
+  def accelerations(self):
+    a = np.zeros((3, self.i_end - self.i_begin))
+    _check(self.lib.pb_nbody_allpairs_accelerations(self.handle, _dptr(a)))
+    return a
+
+  def last_force_ms(self):
+    return self.lib.pb_nbody_allpairs_last_force_ms(self.handle)

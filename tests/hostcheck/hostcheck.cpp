@@ -94,9 +94,9 @@ int32_t hc_geopotential_acceleration(hc_model const* m, int32_t body, double t,
   double const one_over_r3 = r_norm / (r2 * r2);
   Vec3 const a =
       unrolled ? GeneralSphericalHarmonicsAcceleration<true>(
-                     g, frame, rv, r_norm, r2, one_over_r3)
+                     g, FrameSource{frame, 0.0}, rv, r_norm, r2, one_over_r3)
                : GeneralSphericalHarmonicsAcceleration<false>(
-                     g, frame, rv, r_norm, r2, one_over_r3);
+                     g, FrameSource{nullptr, t}, rv, r_norm, r2, one_over_r3);
   out[0] = a.x; out[1] = a.y; out[2] = a.z;
   return PB_OK;
 }

@@ -1,0 +1,98 @@
+"""GPU parity of the adaptive massless flow (Ephemeris::FlowWithAdaptiveStep,
+DormandElMikkawyPrince1986RKN434FM) against the CPU oracle: identical
+accepted-step sequence, rejection counts, evaluation counts and final state,
+bit for bit (both sides use a correctly-rounded fourth root in the step-size
+control; BASELINE.json asks for an identical accepted-step sequence)."""
+import numpy as np
+import pytest
+
+from principia_b200 import _capi, workloads
+
+from conftest import assert_bitwise_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def probes(system, n, seed=42):
+  earth = system.bodies[system.index('Earth')]
+  return workloads.eccentric_probes(n, earth['q'], earth['v'], earth['mu'],
+                                    seed)
+
+
+def test_adaptive_flow_matches_oracle(sol_system, sol_oracle, sol_gpu):
+  n = 333
+  state = probes(sol_system, n)
+  expected_state = state.copy()
+  time = np.zeros((2, n))
+  expected_time = time.copy()
+  t_final = 20000.0
+  result = sol_gpu.flow_with_adaptive_step(t_final, state, time, 1e-3, 1e-3,
+                                           step_log_capacity=64)
+  expected = sol_oracle.flow_with_adaptive_step(
+      t_final, expected_state, expected_time, 1e-3, 1e-3,
+      step_log_capacity=64)
+  assert np.all(expected['status'] == 0)
+  assert list(result['status']) == list(expected['status'])
+  assert list(result['accepted']) == list(expected['accepted'])
+  assert list(result['rejected']) == list(expected['rejected'])
+  assert list(result['evaluations']) == list(expected['evaluations'])
+  assert expected['accepted'].min() >= 3 and expected['rejected'].min() >= 1
+  assert_bitwise_equal(result['step_log'], expected['step_log'], 'step log')
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert np.all(time[0] == t_final)
+  assert_bitwise_equal(state, expected_state, 'state')
+  # FSAL: 4 evaluations per attempt until the first acceptance, 3 afterwards.
+  attempts = result['accepted'] + result['rejected']
+  assert np.all(result['evaluations'] <= 3 * attempts + attempts.clip(max=50))
+
+
+def test_adaptive_flow_statuses(sol_system, sol_oracle, sol_gpu):
+  n = 40
+  # ReachedMaximalStepCount.
+  state, time = probes(sol_system, n, 7), np.zeros((2, n))
+  expected_state, expected_time = state.copy(), time.copy()
+  result = sol_gpu.flow_with_adaptive_step(50000.0, state, time, 1e-3, 1e-3,
+                                           max_steps=5)
+  expected = sol_oracle.flow_with_adaptive_step(
+      50000.0, expected_state, expected_time, 1e-3, 1e-3, max_steps=5)
+  assert list(result['status']) == list(expected['status'])
+  assert np.all(result['status'] == _capi.PB_RESOURCE_EXHAUSTED)
+  assert np.all(result['accepted'] == 5)
+  assert_bitwise_equal(state, expected_state, 'state after 5 steps')
+  assert_bitwise_equal(time, expected_time)
+  # Beyond the ephemeris: integrates to t_max and reports DeadlineExceeded.
+  state, time = probes(sol_system, n, 8), np.full((2, n), 0.0)
+  time[0] = 170000.0
+  expected_state, expected_time = state.copy(), time.copy()
+  result = sol_gpu.flow_with_adaptive_step(180000.0, state, time, 1e-3, 1e-3)
+  expected = sol_oracle.flow_with_adaptive_step(
+      180000.0, expected_state, expected_time, 1e-3, 1e-3)
+  assert np.all(result['status'] == _capi.PB_DEADLINE_EXCEEDED)
+  assert list(result['status']) == list(expected['status'])
+  assert np.all(time[0] == 172800.0)
+  assert_bitwise_equal(state, expected_state, 'deadline state')
+  # Already there: nothing to do.
+  before = state.copy()
+  result = sol_gpu.flow_with_adaptive_step(172800.0, state, time, 1e-3, 1e-3)
+  assert np.all(result['status'] == 0) and np.all(result['accepted'] == 0)
+  assert_bitwise_equal(state, before)
+  # A probe falling into the Earth: the collision is swallowed
+  # (ephemeris_body.hpp:1681-1683), the flow carries on.
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  state = np.zeros((12, 2))
+  state[0:3] = np.array(earth['q'])[:, None] + np.array([[6.4e6, 7e6],
+                                                         [0.0, 0.0],
+                                                         [0.0, 0.0]])
+  state[6:9] = np.array(earth['v'])[:, None]
+  time = np.zeros((2, 2))
+  expected_state, expected_time = state.copy(), time.copy()
+  result = sol_gpu.flow_with_adaptive_step(300.0, state, time, 1e-3, 1e-3,
+                                           max_steps=2000)
+  expected = sol_oracle.flow_with_adaptive_step(
+      300.0, expected_state, expected_time, 1e-3, 1e-3, max_steps=2000)
+  assert list(result['status']) == list(expected['status'])
+  assert list(result['accepted']) == list(expected['accepted'])
+  assert_bitwise_equal(state, expected_state, 'collision state')
+  # No probes.
+  sol_gpu.flow_with_adaptive_step(100.0, np.zeros((12, 0)), np.zeros((2, 0)),
+                                  1e-3, 1e-3)
