@@ -229,6 +229,10 @@ typedef struct pb_adaptive_step_flow_t {
   int64_t* evaluations;
   int64_t step_log_capacity;
   double* step_log;     /* step_log_capacity * n */
+  /* If != NULL, the q and v values of the first step_log_capacity accepted
+   * states of each probe (what append_state hands to
+   * DiscreteTrajectory::Append): state_log[k][6][n]. */
+  double* state_log;    /* step_log_capacity * 6 * n */
 } pb_adaptive_step_flow_t;
 pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* ephemeris,
                                        const pb_adaptive_step_flow_t* flow);
@@ -261,6 +265,16 @@ void pb_nbody_ensemble_destroy(pb_nbody_ensemble_t* ensemble);
 /* Instance::Solve(t_final); *n_steps = steps appended by this call. */
 pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* ensemble,
                                     double t_final, int64_t* n_steps);
+/* Same, with the instance's append_state callback (integrators.hpp:60-66)
+ * materialised: the time and the 6 value planes (q, v) of every appended state
+ * are written to times[r], states[r][6][n_bodies][n_systems] (host).  Returns
+ * once `capacity` states have been recorded or t_final is reached; call again
+ * to continue.  This is how the facade's Prolong feeds
+ * ContinuousTrajectory::Append (ephemeris_body.hpp:1071-1116). */
+pb_status_t pb_nbody_ensemble_solve_recording(pb_nbody_ensemble_t* ensemble,
+                                              double t_final, int64_t capacity,
+                                              double* times, double* states,
+                                              int64_t* n_recorded);
 /* Current ODE::State (host copy): state 12*n_bodies*n_systems, time[2]. */
 pb_status_t pb_nbody_ensemble_get_state(pb_nbody_ensemble_t* ensemble,
                                         double* state, double* time);

@@ -84,6 +84,7 @@ class AdaptiveStepFlow(ctypes.Structure):
       ('evaluations', ctypes.c_void_p),
       ('step_log_capacity', ctypes.c_int64),
       ('step_log', ctypes.c_void_p),
+      ('state_log', ctypes.c_void_p),
   ]
 
 
@@ -129,6 +130,8 @@ SYMBOLS = [
      [_vp, _i32, _d, _i64, c_double_p, _d, ctypes.POINTER(_vp)]),
     ('pb_nbody_ensemble_destroy', None, [_vp]),
     ('pb_nbody_ensemble_solve', _i32, [_vp, _d, c_int64_p]),
+    ('pb_nbody_ensemble_solve_recording', _i32,
+     [_vp, _d, _i64, c_double_p, c_double_p, c_int64_p]),
     ('pb_nbody_ensemble_get_state', _i32, [_vp, c_double_p, c_double_p]),
     ('pb_nbody_allpairs_create', _i32,
      [_i32, _i32, _d, _i64, _i64, _i64, c_double_p, c_double_p, c_double_p, _d,

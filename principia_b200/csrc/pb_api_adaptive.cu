@@ -36,7 +36,9 @@ pb_status_t pb_flow_with_adaptive_step_device(
   parameters.speed_integration_tolerance = flow->speed_integration_tolerance;
   parameters.max_steps = flow->max_steps;
   parameters.step_log_capacity =
-      flow->step_log != nullptr ? flow->step_log_capacity : 0;
+      flow->step_log != nullptr || flow->state_log != nullptr
+          ? flow->step_log_capacity
+          : 0;
   if (flow->n == 0) {
     return PB_OK;
   }
@@ -53,7 +55,8 @@ pb_status_t pb_flow_with_adaptive_step_device(
           e->View(), parameters, flow->n, flow->state, flow->time, flow->status,
           reinterpret_cast<long long*>(flow->accepted_steps),
           reinterpret_cast<long long*>(flow->rejected_steps),
-          reinterpret_cast<long long*>(flow->evaluations), flow->step_log);
+          reinterpret_cast<long long*>(flow->evaluations), flow->step_log,
+          flow->state_log);
   PB_LAUNCHED();
   PB_CUDA(cudaEventRecord(e->timing_events[1], stream));
   PB_CUDA(cudaStreamSynchronize(stream));
@@ -74,7 +77,7 @@ pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
   PB_CUDA(cudaSetDevice(e->device));
   cudaStream_t const stream = nullptr;
   std::size_t const n = static_cast<std::size_t>(flow->n);
-  DeviceBuffer<double> state, time, step_log;
+  DeviceBuffer<double> state, time, step_log, state_log;
   DeviceBuffer<int32_t> status;
   DeviceBuffer<long long> counters;
   PB_RETURN_IF_ERROR(state.Upload(flow->state, 12 * n, stream));
@@ -95,6 +98,17 @@ pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
     device_flow.step_log = step_log.data;
   } else {
     device_flow.step_log = nullptr;
+  }
+  bool const logging_states =
+      flow->state_log != nullptr && flow->step_log_capacity > 0;
+  if (logging_states) {
+    PB_RETURN_IF_ERROR(state_log.Reserve(
+        static_cast<std::size_t>(flow->step_log_capacity) * 6 * n));
+    device_flow.state_log = state_log.data;
+  } else {
+    device_flow.state_log = nullptr;
+  }
+  if (!logging && !logging_states) {
     device_flow.step_log_capacity = 0;
   }
   PB_RETURN_IF_ERROR(
@@ -127,6 +141,13 @@ pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
       PB_CUDA(cudaMemcpyAsync(
           flow->step_log, step_log.data,
           static_cast<std::size_t>(flow->step_log_capacity) * n * sizeof(double),
+          cudaMemcpyDeviceToHost, stream));
+    }
+    if (logging_states) {
+      PB_CUDA(cudaMemcpyAsync(
+          flow->state_log, state_log.data,
+          static_cast<std::size_t>(flow->step_log_capacity) * 6 * n *
+              sizeof(double),
           cudaMemcpyDeviceToHost, stream));
     }
   }

@@ -72,6 +72,8 @@ struct pb_nbody_ensemble {
   int previous_steps = 0;       // previous_steps_.size().
   long long startup_step_index = 0;
   int oldest = 0;               // Ring slot of previous_steps_.front().
+  bool startup_target_valid = false;
+  double startup_target = 0;
   DeviceBuffer<double> state;
   DeviceBuffer<double> displacement_value, displacement_error, acceleration;
   DeviceBuffer<double> frame_times, frames;
@@ -247,19 +249,51 @@ void pb_nbody_ensemble_destroy(pb_nbody_ensemble_t* ensemble) {
   }
 }
 
-pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* s, double t_final,
-                                    int64_t* n_steps) {
-  if (s == nullptr) {
-    return Fail(PB_INVALID_ARGUMENT, "null ensemble");
+// The append_state callback of the instance: optionally copies the appended
+// ODE::State values (6 planes) and its time to the host.
+struct EnsembleRecorder {
+  int64_t capacity;
+  double* times;   // capacity.
+  double* states;  // capacity * 6 * n_bodies * n_systems.
+  int64_t count;
+};
+
+static pb_status_t RecordStep(pb_nbody_ensemble* s, EnsembleRecorder* recorder,
+                              cudaStream_t stream) {
+  if (recorder == nullptr) {
+    return PB_OK;
   }
+  std::size_t const plane =
+      static_cast<std::size_t>(s->n_bodies) * static_cast<std::size_t>(s->n_systems);
+  double* const out = recorder->states + recorder->count * 6 * plane;
+  PB_CUDA(cudaMemcpyAsync(out, s->state.data, 3 * plane * sizeof(double),
+                          cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(cudaMemcpyAsync(out + 3 * plane, s->state.data + 6 * plane,
+                          3 * plane * sizeof(double), cudaMemcpyDeviceToHost,
+                          stream));
+  recorder->times[recorder->count] = s->time.value;
+  ++recorder->count;
+  return PB_OK;
+}
+
+// Integrator::Instance::Solve(t_final); with a recorder, returns as soon as
+// the recorder is full (call again to continue).
+static pb_status_t SolveEnsemble(pb_nbody_ensemble* s, double t_final,
+                                 int64_t* n_steps,
+                                 EnsembleRecorder* recorder) {
   PB_CUDA(cudaSetDevice(s->ephemeris->device));
   cudaStream_t const stream = nullptr;
   int64_t steps = 0;
   double const h = s->step;
+  auto full = [&] {
+    return recorder != nullptr && recorder->count >= recorder->capacity;
+  };
   if (!s->is_multistep) {
     // SymplecticRungeKuttaNyströmIntegrator::Instance::Solve.
-    while (h <= std::abs((t_final - s->time.value) - s->time.error)) {
+    while (!full() &&
+           h <= std::abs((t_final - s->time.value) - s->time.error)) {
       PB_RETURN_IF_ERROR(SrknStep(s, h, stream));
+      PB_RETURN_IF_ERROR(RecordStep(s, recorder, stream));
       ++steps;
     }
   } else {
@@ -271,21 +305,34 @@ pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* s, double t_final,
         s->previous_steps = 1;
       }
       double const startup_step = h / kStartupStepDivisor;
-      double const target =
-          std::min(s->time.value + (order - s->previous_steps) * h + h / 2.0,
-                   t_final);
-      // A fresh startup instance integrates from the current state; its own
-      // time is the instance's current time.
-      while (startup_step <=
+      if (!s->startup_target_valid) {
+        // The target of the startup instance is fixed when Starter::Solve is
+        // entered; a recorder-full return resumes the same call.
+        s->startup_target = std::min(
+            s->time.value + (order - s->previous_steps) * h + h / 2.0, t_final);
+        s->startup_target_valid = true;
+      }
+      double const target = s->startup_target;
+      while (!full() &&
+             startup_step <=
                  std::abs((target - s->time.value) - s->time.error) &&
              s->previous_steps < order) {
         PB_RETURN_IF_ERROR(SrknStep(s, startup_step, stream));
         if (++s->startup_step_index % kStartupStepDivisor == 0) {
           PB_RETURN_IF_ERROR(FillStep(s, s->previous_steps, stream));
           ++s->previous_steps;
+          PB_RETURN_IF_ERROR(RecordStep(s, recorder, stream));
           ++steps;  // instance_->append_state()(state).
         }
       }
+      if (full() && s->previous_steps < order) {
+        PB_CUDA(cudaStreamSynchronize(stream));
+        if (n_steps != nullptr) {
+          *n_steps = steps;
+        }
+        return PB_OK;
+      }
+      s->startup_target_valid = false;
       if (s->previous_steps < order) {
         PB_CUDA(cudaStreamSynchronize(stream));
         if (n_steps != nullptr) {
@@ -295,8 +342,9 @@ pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* s, double t_final,
       }
       s->oldest = 0;
     }
-    while (h <= (t_final - s->time.value) - s->time.error) {
+    while (!full() && h <= (t_final - s->time.value) - s->time.error) {
       PB_RETURN_IF_ERROR(MultistepStep(s, stream));
+      PB_RETURN_IF_ERROR(RecordStep(s, recorder, stream));
       ++steps;
     }
   }
@@ -305,6 +353,28 @@ pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* s, double t_final,
     *n_steps = steps;
   }
   return PB_OK;
+}
+
+pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* s, double t_final,
+                                    int64_t* n_steps) {
+  if (s == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null ensemble");
+  }
+  return SolveEnsemble(s, t_final, n_steps, nullptr);
+}
+
+pb_status_t pb_nbody_ensemble_solve_recording(pb_nbody_ensemble_t* s,
+                                              double t_final, int64_t capacity,
+                                              double* times, double* states,
+                                              int64_t* n_recorded) {
+  if (s == nullptr || capacity <= 0 || times == nullptr ||
+      states == nullptr || n_recorded == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  EnsembleRecorder recorder{capacity, times, states, 0};
+  pb_status_t const status = SolveEnsemble(s, t_final, nullptr, &recorder);
+  *n_recorded = recorder.count;
+  return status;
 }
 
 pb_status_t pb_nbody_ensemble_get_state(pb_nbody_ensemble_t* s, double* state,

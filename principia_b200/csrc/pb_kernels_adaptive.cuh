@@ -84,7 +84,8 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                long long* __restrict__ accepted_out,
                long long* __restrict__ rejected_out,
                long long* __restrict__ evaluations_out,
-               double* __restrict__ step_log) {
+               double* __restrict__ step_log,
+               double* __restrict__ state_log) {
   long long const i =
       static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) {
@@ -246,8 +247,18 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
         Increment(v[1], dv_hat.y);
         Increment(v[2], dv_hat.z);
         // append_state.
-        if (step_log != nullptr && accepted < parameters.step_log_capacity) {
-          step_log[accepted * n + i] = t.value;
+        if (accepted < parameters.step_log_capacity) {
+          if (step_log != nullptr) {
+            step_log[accepted * n + i] = t.value;
+          }
+          if (state_log != nullptr) {
+            double* const out = state_log + accepted * 6 * n;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              out[k * n + i] = q[k].value;
+              out[(3 + k) * n + i] = v[k].value;
+            }
+          }
         }
         ++accepted;
         ++step_count;

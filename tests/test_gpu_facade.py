@@ -1,0 +1,143 @@
+"""GPU: the C++ facade (principia_b200/cpp/ephemeris.hpp) -- the reference's
+Ephemeris surface over the C ABI -- against the oracle: Prolong (device
+massive-body flow + host Newhall fit) produces the oracle's polynomials bit for
+bit; FlowWithFixedStep / FlowWithAdaptiveStep append the oracle's points."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from principia_b200 import _capi, workloads
+
+from conftest import assert_bitwise_equal
+import oracle_lib
+from oracle_lib import OracleEphemeris
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_d, _i32, _i64, _vp = (ctypes.c_double, ctypes.c_int32, ctypes.c_int64,
+                       ctypes.c_void_p)
+_dp, _i32p, _i64p = _capi.c_double_p, _capi.c_int32_p, _capi.c_int64_p
+
+
+@pytest.fixture(scope='module')
+def shim():
+  directory = os.path.join(HERE, 'cpp')
+  subprocess.check_call(
+      ['/usr/bin/g++', '-std=c++17', '-O2', '-ffp-contract=off', '-fPIC',
+       '-shared', '-o', 'libfacadetest.so', 'facade_capi.cpp',
+       '-L../../principia_b200', '-lprincipia_b200',
+       '-Wl,-rpath,$ORIGIN/../../principia_b200'], cwd=directory)
+  lib = ctypes.CDLL(os.path.join(directory, 'libfacadetest.so'))
+  lib.ft_create.restype = _vp
+  lib.ft_create.argtypes = [_i32, ctypes.POINTER(_capi.Body), _dp, _dp, _d, _d,
+                            _d, _i32, _d]
+  lib.ft_destroy.argtypes = [_vp]
+  lib.ft_prolong.argtypes = [_vp, _d]
+  lib.ft_t_max.restype = _d
+  lib.ft_t_max.argtypes = [_vp]
+  lib.ft_segment_count.argtypes = [_vp, _i32]
+  lib.ft_get_segments.argtypes = [_vp, _i32, _dp, _dp, _i32p, _dp]
+  lib.ft_flow_with_fixed_step.argtypes = [_vp, _i32, _dp, _dp, _d, _i32, _d,
+                                          _d, _i32p, _dp, _dp]
+  lib.ft_flow_with_adaptive_step.argtypes = [_vp, _dp, _dp, _d, _d, _d, _d,
+                                             _i64, _i64, _i64p, _dp, _dp]
+  lib.ft_acceleration_on_massless_body.argtypes = [_vp, _dp, _d, _dp]
+  return lib
+
+
+def test_facade_prolong_and_flows(shim, sol_system):
+  system = sol_system
+  bodies, keep = system.c_bodies()
+  q0 = np.ascontiguousarray(system.initial_positions())
+  v0 = np.ascontiguousarray(system.initial_velocities())
+  handle = shim.ft_create(len(system.bodies), bodies, oracle_lib.dptr(q0),
+                          oracle_lib.dptr(v0), 0.0, 1e-3, 2.0**-24,
+                          _capi.QUINLAN_TREMAINE_1990_ORDER_12, 600.0)
+  assert handle
+  oracle = OracleEphemeris(system)
+  t = 0.4 * 86400.0
+  assert shim.ft_prolong(handle, t) == 0
+  assert oracle.prolong(t) == 0
+  assert shim.ft_t_max(handle) == oracle.t_max() >= t
+  for body in range(len(system.bodies)):
+    expected = oracle.segments(body)
+    count = shim.ft_segment_count(handle, body)
+    assert count == len(expected['t_max'])
+    t_max, origin = np.zeros(count), np.zeros(count)
+    degree = np.zeros(count, dtype=np.int32)
+    coefficients = np.zeros((count, 18, 3))
+    shim.ft_get_segments(handle, body, oracle_lib.dptr(t_max),
+                         oracle_lib.dptr(origin),
+                         degree.ctypes.data_as(_i32p),
+                         oracle_lib.dptr(coefficients))
+    assert_bitwise_equal(t_max, expected['t_max'])
+    assert_bitwise_equal(origin, expected['origin'])
+    assert list(degree) == list(expected['degree']), system.names()[body]
+    assert_bitwise_equal(coefficients, expected['coefficients'],
+                         system.names()[body])
+
+  # FlowWithFixedStep through NewInstance, beyond the current t_max (the facade
+  # prolongs), every step appended.
+  n = 37
+  earth = system.bodies[system.index('Earth')]
+  state = workloads.leo_probes(n, earth['q'], earth['v'], earth['mu'], 5)
+  q = np.ascontiguousarray(state[0:3].T)
+  v = np.ascontiguousarray(state[6:9].T)
+  points = np.zeros(n, dtype=np.int32)
+  last = np.zeros((n, 6))
+  last_time = _d()
+  t_flow = 40000.0
+  status = shim.ft_flow_with_fixed_step(
+      handle, n, oracle_lib.dptr(q), oracle_lib.dptr(v), 0.0,
+      _capi.BLANES_MOAN_2002_SRKN_14A, 10.0, t_flow,
+      points.ctypes.data_as(_i32p), oracle_lib.dptr(last), last_time)
+  assert status == 0
+  assert shim.ft_t_max(handle) >= t_flow
+  oracle.prolong(t_flow)
+  expected_state = state.copy()
+  expected_time = np.zeros(2)
+  oracle.flow_with_fixed_step(_capi.BLANES_MOAN_2002_SRKN_14A, 10.0, t_flow,
+                              expected_state, expected_time)
+  assert np.all(points == 4001)
+  assert last_time.value == expected_time[0] == t_flow
+  assert_bitwise_equal(last[:, 0:3].T, expected_state[0:3], 'positions')
+  assert_bitwise_equal(last[:, 3:6].T, expected_state[6:9], 'velocities')
+
+  # FlowWithAdaptiveStep: every accepted step appended.
+  probe = workloads.eccentric_probes(4, earth['q'], earth['v'], earth['mu'], 9)
+  k = 2
+  q1 = np.ascontiguousarray(probe[0:3, k])
+  v1 = np.ascontiguousarray(probe[6:9, k])
+  capacity = 5000
+  n_points = _i64()
+  times = np.zeros(capacity)
+  dofs = np.zeros((capacity, 6))
+  status = shim.ft_flow_with_adaptive_step(
+      handle, oracle_lib.dptr(q1), oracle_lib.dptr(v1), 0.0, 30000.0, 1e-3,
+      1e-3, 2**62, capacity, n_points, oracle_lib.dptr(times),
+      oracle_lib.dptr(dofs))
+  assert status == 0
+  expected_state = np.ascontiguousarray(probe[:, k:k + 1])
+  expected_time = np.zeros((2, 1))
+  expected = oracle.flow_with_adaptive_step(30000.0, expected_state,
+                                            expected_time, 1e-3, 1e-3,
+                                            step_log_capacity=capacity)
+  count = int(expected['accepted'][0])
+  assert n_points.value == count > 5
+  assert_bitwise_equal(times[:count], expected['step_log'][:count, 0])
+  assert times[count - 1] == 30000.0
+  assert_bitwise_equal(dofs[count - 1, 0:3], expected_state[0:3, 0])
+  assert_bitwise_equal(dofs[count - 1, 3:6], expected_state[6:9, 0])
+
+  # Point query.
+  a = np.zeros(3)
+  assert shim.ft_acceleration_on_massless_body(handle, oracle_lib.dptr(q1),
+                                               100.0, oracle_lib.dptr(a)) == 0
+  expected_a, _ = oracle.acceleration_on_massless_bodies(100.0,
+                                                         q1.reshape(3, 1))
+  assert_bitwise_equal(a, expected_a.ravel())
+  shim.ft_destroy(handle)
