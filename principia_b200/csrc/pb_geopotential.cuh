@@ -529,8 +529,24 @@ PB_HD void UnrolledUpdateOrder(double const sin_beta,
   }
 }
 
-template<int n, int m, int kMaxDegree>
-PB_HD Vec3 UnrolledTerm(GeopotentialBody const& g, double const sigma_R_over_r,
+// Where the unrolled path reads a body's tables from.  PointerTables: global
+// memory through pointers (any body).  A kernel may instead provide a type
+// with the same interface backed by __constant__ memory, so that with
+// compile-time (n, m) every coefficient becomes a constant-bank operand of the
+// FP64 instruction that uses it (no load instruction, no scoreboard wait).
+struct PointerTables {
+  GeopotentialBody const& g;
+  PB_HD double Cos(int const k) const { return g.cos[k]; }
+  PB_HD double Sin(int const k) const { return g.sin[k]; }
+  PB_HD double Normalization(int const k) const { return g.normalization[k]; }
+  PB_HD Damping const& DegreeDamping(int const n) const {
+    return g.degree_damping[n];
+  }
+  PB_HD Damping const& SectoralDamping() const { return g.body->sectoral; }
+};
+
+template<int n, int m, int kMaxDegree, typename Tables>
+PB_HD Vec3 UnrolledTerm(Tables const& g, double const sigma_R_over_r,
                         Vec3 const& grad_sigma_R, GeopotentialSetup const& s,
                         UnrolledPrecomputations<kMaxDegree> const& p) {
   constexpr int k = Tri(n, m);
@@ -544,13 +560,13 @@ PB_HD Vec3 UnrolledTerm(GeopotentialBody const& g, double const sigma_R_over_r,
   }
   return OrderTermAcceleration(n, m, p.P[k], Pnm1, p.cos_m_lambda[m],
                                p.sin_m_lambda[m], p.cos_beta_to_the_m[m],
-                               cos_beta_to_the_m_minus_1, g.cos[k], g.sin[k],
-                               g.normalization[k], sigma_R_over_r,
+                               cos_beta_to_the_m_minus_1, g.Cos(k), g.Sin(k),
+                               g.Normalization(k), sigma_R_over_r,
                                grad_sigma_R, s);
 }
 
-template<int kMaxDegree, bool kZonal>
-PB_HD Vec3 GeopotentialUnrolledAcceleration(GeopotentialBody const& g,
+template<int kMaxDegree, bool kZonal, typename Tables>
+PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
                                             GeopotentialSetup const& s) {
   UnrolledPrecomputations<kMaxDegree> p;
   p.R_over_r[1] = s.R1_over_r;
@@ -578,13 +594,13 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(GeopotentialBody const& g,
     double sigma_R_over_r;
     Vec3 grad_sigma_R;
     if constexpr (n == 2 && size > 1) {
-      ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
+      ComputeDampedRadialQuantities(g.DegreeDamping(2), s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
       UnrolledUpdateOrder<2, 0>(s.sin_beta, p);
       Vec3 const j2_acceleration =
           UnrolledTerm<2, 0>(g, sigma_R_over_r, grad_sigma_R, s, p);
-      ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2,
+      ComputeDampedRadialQuantities(g.SectoralDamping(), s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
       UnrolledUpdateOrder<2, 1>(s.sin_beta, p);
@@ -593,7 +609,7 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(GeopotentialBody const& g,
           UnrolledTerm<2, 2>(g, sigma_R_over_r, grad_sigma_R, s, p);
       degree_sum[n] = j2_acceleration + c22_s22_acceleration;
     } else {
-      ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+      ComputeDampedRadialQuantities(g.DegreeDamping(n), s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
       StaticForRange<0, size>([&](auto m_constant) {
@@ -618,8 +634,8 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(GeopotentialBody const& g,
   return sum;
 }
 
-template<bool kZonal>
-PB_HD Vec3 GeopotentialUnrolledDispatch(GeopotentialBody const& g,
+template<bool kZonal, typename Tables>
+PB_HD Vec3 GeopotentialUnrolledDispatch(Tables const& g,
                                         int const max_degree,
                                         GeopotentialSetup const& s) {
   switch (max_degree) {
@@ -684,10 +700,11 @@ PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
   InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
   if constexpr (kUnrolled) {
     if (max_degree <= kMaxUnrolledDegree) {
+      PointerTables const tables{g};
       if (is_zonal) {
-        return GeopotentialUnrolledDispatch<true>(g, max_degree, s);
+        return GeopotentialUnrolledDispatch<true>(tables, max_degree, s);
       } else {
-        return GeopotentialUnrolledDispatch<false>(g, max_degree, s);
+        return GeopotentialUnrolledDispatch<false>(tables, max_degree, s);
       }
     }
   }

@@ -115,6 +115,103 @@ void ComputeNodes(SrknTableau const& tableau, double* c) {
   }
 }
 
+// Uploads the constant-bank tables of the flow kernel: per-body scalars and the
+// tables of the "hot" oblate body -- the body of degree <= kHotDegree with the
+// highest limiting degree at the distance of the first probe (the Earth for
+// LEO probes).  The choice only affects speed: both paths compute the same
+// bits.
+pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
+                                long long const n, double const* state_device,
+                                cudaStream_t stream) {
+  int const n_bodies = static_cast<int>(e->model.bodies.size());
+  if (n_bodies > kMaxConstantBodies) {
+    return Fail(PB_INVALID_ARGUMENT, "too many bodies for the flow kernel");
+  }
+  static pb_ephemeris const* uploaded_for = nullptr;
+  static int uploaded_hot = -2;
+  // Position of the first probe.
+  double probe[3] = {0.0, 0.0, 0.0};
+  if (n > 0) {
+    for (int c = 0; c < 3; ++c) {
+      PB_CUDA(cudaMemcpyAsync(&probe[c], state_device + c * n, sizeof(double),
+                              cudaMemcpyDeviceToHost, stream));
+    }
+    PB_CUDA(cudaStreamSynchronize(stream));
+  }
+  int hot = -1;
+  int best_degree = 2;
+  for (int b = 0; b < e->model.n_oblate; ++b) {
+    DeviceBody const& body = e->model.bodies[b];
+    if (body.degree > kHotDegree) {
+      continue;
+    }
+    HostTrajectory const& tr = e->trajectories[b];
+    if (tr.t_max.empty()) {
+      continue;
+    }
+    std::size_t segment =
+        std::lower_bound(tr.t_max.begin(), tr.t_max.end(), t) -
+        tr.t_max.begin();
+    segment = std::min(segment, tr.t_max.size() - 1);
+    double const x = t - tr.origin[segment];
+    double const* const c = &tr.coefficients[segment * 3 * kSegmentCoefficients];
+    double d2 = 0;
+    for (int k = 0; k < 3; ++k) {
+      double const p = EstrinEvaluate<3>(c + k, tr.degree[segment], x);
+      d2 += (p - probe[k]) * (p - probe[k]);
+    }
+    int const limiting = LimitingDegree(
+        e->model.dampings.data() + body.damping_offset, body.n_damping,
+        std::sqrt(d2));
+    if (limiting - 1 > best_degree) {
+      best_degree = limiting - 1;
+      hot = b;
+    }
+  }
+  if (uploaded_for == e && uploaded_hot == hot) {
+    return PB_OK;
+  }
+  static BodyScalars scalars;
+  static HotBody hot_body;
+  for (int b = 0; b < n_bodies; ++b) {
+    DeviceBody const& body = e->model.bodies[b];
+    scalars.mu[b] = body.mu;
+    scalars.collision_radius[b] = body.collision_radius;
+    scalars.outer_threshold_degree_2[b] =
+        body.is_oblate && body.n_damping > 2
+            ? e->model.dampings[body.damping_offset + 2].outer_threshold
+            : -std::numeric_limits<double>::infinity();
+  }
+  std::memset(&hot_body, 0, sizeof(hot_body));
+  hot_body.body = hot;
+  if (hot >= 0) {
+    DeviceBody const& body = e->model.bodies[hot];
+    int const size = (body.degree + 1) * (body.degree + 2) / 2;
+    hot_body.n_damping = body.n_damping;
+    for (int k = 0; k < size; ++k) {
+      hot_body.cos[k] = e->model.cos[body.coefficient_offset + k];
+      hot_body.sin[k] = e->model.sin[body.coefficient_offset + k];
+    }
+    for (int k = 0; k < kHotSize; ++k) {
+      hot_body.normalization[k] = pb_legendre_normalization_factor[k];
+    }
+    for (int d = 0; d < body.n_damping; ++d) {
+      hot_body.degree_damping[d] = e->model.dampings[body.damping_offset + d];
+    }
+    hot_body.sectoral = body.sectoral;
+  }
+  // The previous launch may still read the symbols on this stream: the copies
+  // are stream-ordered.
+  PB_CUDA(cudaMemcpyToSymbolAsync(c_bodies, &scalars, sizeof(scalars), 0,
+                                  cudaMemcpyHostToDevice, stream));
+  PB_CUDA(cudaMemcpyToSymbolAsync(c_hot, &hot_body, sizeof(hot_body), 0,
+                                  cudaMemcpyHostToDevice, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  uploaded_for = e;
+  uploaded_hot = hot;
+  return PB_OK;
+}
+
 // Resident blocks per SM the flow kernel is compiled for (register budget
 // 65536 / (128 * blocks)); PB_SRKN_MIN_BLOCKS overrides it for experiments.
 int SrknMinBlocks() {
@@ -503,6 +600,8 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
       e->pinned_times.Reserve(static_cast<std::size_t>(chunk_steps) *
                               evaluations));
   PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
+  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
+  PB_RETURN_IF_ERROR(UploadFlowConstants(e, t.value, flow->n, flow->state, stream));
 
   long long steps_done = 0;
   long long samples_done = 0;
