@@ -462,45 +462,72 @@ PB_HD void StaticForRange(F&& f) {
 template<int kMaxDegree>
 struct UnrolledPrecomputations {
   double R_over_r[kMaxDegree + 1];
-  double cos_m_lambda[kMaxDegree + 1];
-  double sin_m_lambda[kMaxDegree + 1];
-  double cos_beta_to_the_m[kMaxDegree + 1];
   // Full triangle; every index is a compile-time constant, so after unrolling
   // these are plain values with short live ranges (rows n-1, n-2).
   double P[(kMaxDegree + 1) * (kMaxDegree + 2) / 2 + 1];
+};
+
+// The long-lived state of one evaluation -- cos mλ, sin mλ, cos^m β (created at
+// degree m, used by every later degree) and the per-degree sums (kept for the
+// final right fold) -- lives behind a Scratch policy: thread-local arrays here,
+// shared memory in the flow kernel (108 registers' worth of state that would
+// otherwise be spilled).
+template<int kMaxDegree>
+struct LocalScratch {
+  double cos_m_lambda[kMaxDegree + 1];
+  double sin_m_lambda[kMaxDegree + 1];
+  double cos_beta_to_the_m[kMaxDegree + 1];
+  Vec3 degree_sum[kMaxDegree + 1];
+  template<int m> PB_HD double CosMLambda() const { return cos_m_lambda[m]; }
+  template<int m> PB_HD double SinMLambda() const { return sin_m_lambda[m]; }
+  template<int m> PB_HD double CosBetaToTheM() const {
+    return cos_beta_to_the_m[m];
+  }
+  template<int m> PB_HD void SetCosMLambda(double const x) {
+    cos_m_lambda[m] = x;
+  }
+  template<int m> PB_HD void SetSinMLambda(double const x) {
+    sin_m_lambda[m] = x;
+  }
+  template<int m> PB_HD void SetCosBetaToTheM(double const x) {
+    cos_beta_to_the_m[m] = x;
+  }
+  template<int n> PB_HD Vec3 DegreeSum() const { return degree_sum[n]; }
+  template<int n> PB_HD void SetDegreeSum(Vec3 const& x) { degree_sum[n] = x; }
 };
 
 PB_HD constexpr int Tri(int const n, int const m) {
   return n * (n + 1) / 2 + m;
 }
 
-template<int n, int m, int kMaxDegree>
+template<int n, int m, int kMaxDegree, typename Scratch>
 PB_HD void UnrolledUpdateOrder(double const sin_beta,
-                               UnrolledPrecomputations<kMaxDegree>& p) {
+                               UnrolledPrecomputations<kMaxDegree>& p,
+                               Scratch& w) {
   if constexpr (n == 2 && m == 1) {
     p.P[Tri(2, 2)] = 3;
   } else {
     if constexpr (m == n) {
       if constexpr (m % 2 == 0) {
         constexpr int h = m / 2;
-        double const cos_h = p.cos_m_lambda[h];
-        double const sin_h = p.sin_m_lambda[h];
-        double const cos_beta_to_the_h = p.cos_beta_to_the_m[h];
-        p.sin_m_lambda[m] = 2 * sin_h * cos_h;
-        p.cos_m_lambda[m] = (cos_h + sin_h) * (cos_h - sin_h);
-        p.cos_beta_to_the_m[m] = cos_beta_to_the_h * cos_beta_to_the_h;
+        double const cos_h = w.template CosMLambda<h>();
+        double const sin_h = w.template SinMLambda<h>();
+        double const cos_beta_to_the_h = w.template CosBetaToTheM<h>();
+        w.template SetSinMLambda<m>(2 * sin_h * cos_h);
+        w.template SetCosMLambda<m>((cos_h + sin_h) * (cos_h - sin_h));
+        w.template SetCosBetaToTheM<m>(cos_beta_to_the_h * cos_beta_to_the_h);
       } else {
         constexpr int h1 = m / 2;
         constexpr int h2 = m - h1;
-        double const cos_h1 = p.cos_m_lambda[h1];
-        double const sin_h1 = p.sin_m_lambda[h1];
-        double const cos_beta_to_the_h1 = p.cos_beta_to_the_m[h1];
-        double const cos_h2 = p.cos_m_lambda[h2];
-        double const sin_h2 = p.sin_m_lambda[h2];
-        double const cos_beta_to_the_h2 = p.cos_beta_to_the_m[h2];
-        p.sin_m_lambda[m] = sin_h1 * cos_h2 + cos_h1 * sin_h2;
-        p.cos_m_lambda[m] = cos_h1 * cos_h2 - sin_h1 * sin_h2;
-        p.cos_beta_to_the_m[m] = cos_beta_to_the_h1 * cos_beta_to_the_h2;
+        double const cos_h1 = w.template CosMLambda<h1>();
+        double const sin_h1 = w.template SinMLambda<h1>();
+        double const cos_beta_to_the_h1 = w.template CosBetaToTheM<h1>();
+        double const cos_h2 = w.template CosMLambda<h2>();
+        double const sin_h2 = w.template SinMLambda<h2>();
+        double const cos_beta_to_the_h2 = w.template CosBetaToTheM<h2>();
+        w.template SetSinMLambda<m>(sin_h1 * cos_h2 + cos_h1 * sin_h2);
+        w.template SetCosMLambda<m>(cos_h1 * cos_h2 - sin_h1 * sin_h2);
+        w.template SetCosBetaToTheM<m>(cos_beta_to_the_h1 * cos_beta_to_the_h2);
       }
     }
     constexpr double one_over_n = 1.0 / n;
@@ -545,39 +572,44 @@ struct PointerTables {
   PB_HD Damping const& SectoralDamping() const { return g.body->sectoral; }
 };
 
-template<int n, int m, int kMaxDegree, typename Tables>
+template<int n, int m, int kMaxDegree, typename Tables, typename Scratch>
 PB_HD Vec3 UnrolledTerm(Tables const& g, double const sigma_R_over_r,
                         Vec3 const& grad_sigma_R, GeopotentialSetup const& s,
-                        UnrolledPrecomputations<kMaxDegree> const& p) {
+                        UnrolledPrecomputations<kMaxDegree> const& p,
+                        Scratch const& w) {
   constexpr int k = Tri(n, m);
   double Pnm1 = 0.0;
   if constexpr (m < n) {
     Pnm1 = p.P[Tri(n, m + 1)];
   }
   double cos_beta_to_the_m_minus_1 = 0.0;
+  double cos_m_lambda = 0.0;
+  double sin_m_lambda = 0.0;
   if constexpr (m > 0) {
-    cos_beta_to_the_m_minus_1 = p.cos_beta_to_the_m[m - 1];
+    cos_beta_to_the_m_minus_1 = w.template CosBetaToTheM<m - 1>();
+    cos_m_lambda = w.template CosMLambda<m>();
+    sin_m_lambda = w.template SinMLambda<m>();
   }
-  return OrderTermAcceleration(n, m, p.P[k], Pnm1, p.cos_m_lambda[m],
-                               p.sin_m_lambda[m], p.cos_beta_to_the_m[m],
+  return OrderTermAcceleration(n, m, p.P[k], Pnm1, cos_m_lambda, sin_m_lambda,
+                               w.template CosBetaToTheM<m>(),
                                cos_beta_to_the_m_minus_1, g.Cos(k), g.Sin(k),
                                g.Normalization(k), sigma_R_over_r,
                                grad_sigma_R, s);
 }
 
-template<int kMaxDegree, bool kZonal, typename Tables>
+template<int kMaxDegree, bool kZonal, typename Tables, typename Scratch>
 PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
-                                            GeopotentialSetup const& s) {
+                                            GeopotentialSetup const& s,
+                                            Scratch& w) {
   UnrolledPrecomputations<kMaxDegree> p;
   p.R_over_r[1] = s.R1_over_r;
-  p.cos_m_lambda[1] = s.cos_lambda;
-  p.sin_m_lambda[1] = s.sin_lambda;
-  p.cos_beta_to_the_m[0] = 1;
-  p.cos_beta_to_the_m[1] = s.cos_beta;
+  w.template SetCosMLambda<1>(s.cos_lambda);
+  w.template SetSinMLambda<1>(s.sin_lambda);
+  w.template SetCosBetaToTheM<0>(1);
+  w.template SetCosBetaToTheM<1>(s.cos_beta);
   p.P[Tri(0, 0)] = 1;
   p.P[Tri(1, 0)] = s.sin_beta;
   p.P[Tri(1, 1)] = 1;
-  Vec3 degree_sum[kMaxDegree + 1];
   StaticForRange<2, kMaxDegree + 1>([&](auto n_constant) {
     constexpr int n = decltype(n_constant)::value;
     constexpr int size = kZonal ? 1 : n + 1;
@@ -597,36 +629,37 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
       ComputeDampedRadialQuantities(g.DegreeDamping(2), s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
-      UnrolledUpdateOrder<2, 0>(s.sin_beta, p);
+      UnrolledUpdateOrder<2, 0>(s.sin_beta, p, w);
       Vec3 const j2_acceleration =
-          UnrolledTerm<2, 0>(g, sigma_R_over_r, grad_sigma_R, s, p);
+          UnrolledTerm<2, 0>(g, sigma_R_over_r, grad_sigma_R, s, p, w);
       ComputeDampedRadialQuantities(g.SectoralDamping(), s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
-      UnrolledUpdateOrder<2, 1>(s.sin_beta, p);
-      UnrolledUpdateOrder<2, 2>(s.sin_beta, p);
+      UnrolledUpdateOrder<2, 1>(s.sin_beta, p, w);
+      UnrolledUpdateOrder<2, 2>(s.sin_beta, p, w);
       Vec3 const c22_s22_acceleration =
-          UnrolledTerm<2, 2>(g, sigma_R_over_r, grad_sigma_R, s, p);
-      degree_sum[n] = j2_acceleration + c22_s22_acceleration;
+          UnrolledTerm<2, 2>(g, sigma_R_over_r, grad_sigma_R, s, p, w);
+      w.template SetDegreeSum<n>(j2_acceleration + c22_s22_acceleration);
     } else {
       ComputeDampedRadialQuantities(g.DegreeDamping(n), s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
       StaticForRange<0, size>([&](auto m_constant) {
-        UnrolledUpdateOrder<n, decltype(m_constant)::value>(s.sin_beta, p);
+        UnrolledUpdateOrder<n, decltype(m_constant)::value>(s.sin_beta, p, w);
       });
-      Vec3 sum = UnrolledTerm<n, size - 1>(g, sigma_R_over_r, grad_sigma_R, s, p);
+      Vec3 sum =
+          UnrolledTerm<n, size - 1>(g, sigma_R_over_r, grad_sigma_R, s, p, w);
       StaticForRange<0, size - 1>([&](auto i_constant) {
         constexpr int m = size - 2 - decltype(i_constant)::value;
-        sum = UnrolledTerm<n, m>(g, sigma_R_over_r, grad_sigma_R, s, p) + sum;
+        sum = UnrolledTerm<n, m>(g, sigma_R_over_r, grad_sigma_R, s, p, w) + sum;
       });
-      degree_sum[n] = sum;
+      w.template SetDegreeSum<n>(sum);
     }
   });
-  Vec3 sum = degree_sum[kMaxDegree];
+  Vec3 sum = w.template DegreeSum<kMaxDegree>();
   StaticForRange<0, kMaxDegree - 2>([&](auto i_constant) {
     constexpr int n = kMaxDegree - 1 - decltype(i_constant)::value;
-    sum = degree_sum[n] + sum;
+    sum = w.template DegreeSum<n>() + sum;
   });
   Vec3 const zero{0.0, 0.0, 0.0};
   sum = zero + sum;
@@ -634,21 +667,61 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
   return sum;
 }
 
-template<bool kZonal, typename Tables>
+// With thread-local scratch.
+template<int kMaxDegree, bool kZonal, typename Tables>
+PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
+                                            GeopotentialSetup const& s) {
+  LocalScratch<kMaxDegree> scratch;
+  return GeopotentialUnrolledAcceleration<kMaxDegree, kZonal>(g, s, scratch);
+}
+
+// Dispatch on the run-time degree; only degrees <= kLimit are instantiated
+// (callers guarantee max_degree <= kLimit).
+template<bool kZonal, typename Tables, int kLimit = kMaxUnrolledDegree>
 PB_HD Vec3 GeopotentialUnrolledDispatch(Tables const& g,
                                         int const max_degree,
                                         GeopotentialSetup const& s) {
-  switch (max_degree) {
-    case 2: return GeopotentialUnrolledAcceleration<2, kZonal>(g, s);
-    case 3: return GeopotentialUnrolledAcceleration<3, kZonal>(g, s);
-    case 4: return GeopotentialUnrolledAcceleration<4, kZonal>(g, s);
-    case 5: return GeopotentialUnrolledAcceleration<5, kZonal>(g, s);
-    case 6: return GeopotentialUnrolledAcceleration<6, kZonal>(g, s);
-    case 7: return GeopotentialUnrolledAcceleration<7, kZonal>(g, s);
-    case 8: return GeopotentialUnrolledAcceleration<8, kZonal>(g, s);
-    case 9: return GeopotentialUnrolledAcceleration<9, kZonal>(g, s);
-    default: return GeopotentialUnrolledAcceleration<10, kZonal>(g, s);
+#define PB_UNROLLED_CASE(d)                                        \
+  if constexpr (kLimit > (d)) {                                    \
+    if (max_degree == (d)) {                                       \
+      return GeopotentialUnrolledAcceleration<(d), kZonal>(g, s);  \
+    }                                                              \
   }
+  PB_UNROLLED_CASE(2)
+  PB_UNROLLED_CASE(3)
+  PB_UNROLLED_CASE(4)
+  PB_UNROLLED_CASE(5)
+  PB_UNROLLED_CASE(6)
+  PB_UNROLLED_CASE(7)
+  PB_UNROLLED_CASE(8)
+  PB_UNROLLED_CASE(9)
+#undef PB_UNROLLED_CASE
+  return GeopotentialUnrolledAcceleration<kLimit, kZonal>(g, s);
+}
+
+// Same, with the caller's scratch storage (sized for kLimit).
+template<bool kZonal, typename Tables, typename Scratch,
+         int kLimit = kMaxUnrolledDegree>
+PB_HD Vec3 GeopotentialUnrolledDispatchWithScratch(Tables const& g,
+                                                   int const max_degree,
+                                                   GeopotentialSetup const& s,
+                                                   Scratch& w) {
+#define PB_UNROLLED_CASE(d)                                           \
+  if constexpr (kLimit > (d)) {                                       \
+    if (max_degree == (d)) {                                          \
+      return GeopotentialUnrolledAcceleration<(d), kZonal>(g, s, w);  \
+    }                                                                 \
+  }
+  PB_UNROLLED_CASE(2)
+  PB_UNROLLED_CASE(3)
+  PB_UNROLLED_CASE(4)
+  PB_UNROLLED_CASE(5)
+  PB_UNROLLED_CASE(6)
+  PB_UNROLLED_CASE(7)
+  PB_UNROLLED_CASE(8)
+  PB_UNROLLED_CASE(9)
+#undef PB_UNROLLED_CASE
+  return GeopotentialUnrolledAcceleration<kLimit, kZonal>(g, s, w);
 }
 
 // ===========================================================================
@@ -666,7 +739,7 @@ struct FrameSource {
 // the surface-frame x and y axes at the evaluation time (6 doubles) when the
 // body has a frame slot; zonal evaluation uses the body's fixed axes.
 // kUnrolled selects the register-resident path for max_degree <= 10.
-template<bool kUnrolled>
+template<bool kUnrolled, int kUnrolledLimit = kMaxUnrolledDegree>
 PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
                                                  FrameSource const frame,
                                                  Vec3 const& r,
@@ -699,12 +772,16 @@ PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
   GeopotentialSetup s;
   InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
   if constexpr (kUnrolled) {
-    if (max_degree <= kMaxUnrolledDegree) {
+    if (max_degree <= kUnrolledLimit) {
       PointerTables const tables{g};
       if (is_zonal) {
-        return GeopotentialUnrolledDispatch<true>(tables, max_degree, s);
+        return GeopotentialUnrolledDispatch<true, PointerTables,
+                                            kUnrolledLimit>(tables, max_degree,
+                                                            s);
       } else {
-        return GeopotentialUnrolledDispatch<false>(tables, max_degree, s);
+        return GeopotentialUnrolledDispatch<false, PointerTables,
+                                            kUnrolledLimit>(tables, max_degree,
+                                                            s);
       }
     }
   }

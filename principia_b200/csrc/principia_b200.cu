@@ -640,10 +640,11 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
           static_cast<unsigned>((flow->n + kFlowThreads - 1) / kFlowThreads);
       long long const every = sampling ? flow->sample_every : 0;
 #define PB_LAUNCH_SRKN(kMinBlocks)                                            \
-  SrknFlowKernel<true, kMinBlocks><<<grid, kFlowThreads, 0, stream>>>(        \
-      view, tableau, h, e->stage_table.data, steps, flow->n, flow->state,     \
-      steps_done, every, flow->max_samples, flow->samples,                    \
-      e->status_word.data)
+  SrknFlowKernel<true, kMinBlocks>                                            \
+      <<<grid, kFlowThreads, 0, stream>>>(                                    \
+          view, tableau, h, e->stage_table.data, steps, flow->n, flow->state, \
+          steps_done, every, flow->max_samples, flow->samples,                \
+          e->status_word.data)
       switch (SrknMinBlocks()) {
         case 2: PB_LAUNCH_SRKN(2); break;
         case 4: PB_LAUNCH_SRKN(4); break;
