@@ -291,3 +291,19 @@ def test_full_size_flow_properties(sol_system, sol_oracle, sol_gpu):
   assert time[0] == 0.0
   displacement = np.linalg.norm(state[0:3] - state0[0:3], axis=0)
   assert np.max(displacement) < 1e-2
+
+
+def test_branch_free_sqrt_and_division_are_ieee():
+  """FastSqrt / FastDivide (pb_math.cuh) against the IEEE operators on the
+  device: 2e9 operand sets, no mismatch allowed."""
+  lib = _capi.library()
+  f = lib.pb_internal_fast_math_check
+  f.argtypes = [ctypes.c_int32, ctypes.c_int64,
+                ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+  total = 0
+  for seed in (1, 2, 3):
+    checked, bad = ctypes.c_int64(), ctypes.c_int64()
+    assert f(0, seed, ctypes.byref(checked), ctypes.byref(bad)) == 0
+    assert bad.value == 0
+    total += checked.value
+  assert total > 2e9
