@@ -256,6 +256,9 @@ def run_native(args):
   for k in range(args.steps):
     flush.fill_(k & 0xff)  # Evict L2 between steps.
     resident_step()
+    # Device time (CUDA events on the launching stream) of the flow kernels of
+    # this call: the call slices the batch into launches that overlap on
+    # helper streams, so the figure is per call, not per launch.
     ms, launches = ephemeris.last_flow_kernel_ms()
     kernel_ms += ms
     kernel_launches += launches
@@ -289,15 +292,16 @@ def run_native(args):
   value = args.steps * stages_per_step / (elapsed_ms * 1e-3)
   e2e_value = args.steps * stages_per_step / (e2e_ms * 1e-3)
 
-  launch_flops = n * FLOW_STEPS * flops.srkn14a_probe_step_sol_leo()
-  average_kernel_ms = kernel_ms / max(kernel_launches, 1)
-  achieved = launch_flops / (average_kernel_ms * 1e-3) / 1e12
+  call_flops = n * FLOW_STEPS * flops.srkn14a_probe_step_sol_leo()
+  average_kernel_ms = kernel_ms / args.steps
+  achieved = call_flops / (average_kernel_ms * 1e-3) / 1e12
   roofline = {
       'bound': 'fp64', 'achieved': achieved, 'peak': peak_flops / 1e12,
       'unit': 'TFLOP/s', 'frac': achieved / (peak_flops / 1e12),
       'traffic': None,
       'kernel': 'SrknFlowKernel',
       'kernel_ms': average_kernel_ms,
+      'kernel_launches_per_step': kernel_launches / args.steps,
       'kernel_share_of_step': kernel_ms / elapsed_ms,
       'algorithmic_flop_per_probe_stage':
           flops.massless_probe_stage_sol_leo(),

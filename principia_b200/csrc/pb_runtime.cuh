@@ -168,9 +168,19 @@ struct pb_ephemeris {
   double last_flow_kernel_ms = 0;
   std::int64_t last_flow_kernel_launches = 0;
 
+  // Helper streams of the sliced flow launches and their join events.
+  std::vector<cudaStream_t> flow_streams;
+  std::vector<cudaEvent_t> flow_events;
+
   ~pb_ephemeris() {
     for (cudaEvent_t event : timing_events) {
       cudaEventDestroy(event);
+    }
+    for (cudaEvent_t event : flow_events) {
+      cudaEventDestroy(event);
+    }
+    for (cudaStream_t helper : flow_streams) {
+      cudaStreamDestroy(helper);
     }
   }
 

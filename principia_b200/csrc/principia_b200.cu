@@ -212,6 +212,25 @@ pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
   return PB_OK;
 }
 
+// Slicing of a flow launch across helper streams (PB_FLOW_GROUPS = 1 disables
+// it) and steps per sliced launch.
+int FlowGroups() {
+  static int const value = [] {
+    char const* const text = std::getenv("PB_FLOW_GROUPS");
+    int const v = text != nullptr ? std::atoi(text) : 4;
+    return std::max(1, std::min(v, 16));
+  }();
+  return value;
+}
+int FlowSubSteps() {
+  static int const value = [] {
+    char const* const text = std::getenv("PB_FLOW_SUB_STEPS");
+    int const v = text != nullptr ? std::atoi(text) : 10;
+    return std::max(1, v);
+  }();
+  return value;
+}
+
 // Resident blocks per SM the flow kernel is compiled for (register budget
 // 65536 / (128 * blocks)); PB_SRKN_MIN_BLOCKS overrides it for experiments.
 int SrknMinBlocks() {
@@ -606,6 +625,7 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
   long long steps_done = 0;
   long long samples_done = 0;
   std::size_t launches = 0;
+  std::size_t phases = 0;
   while (abs_h <= std::abs((t_final - t.value) - t.error)) {
     int steps = 0;
     double* const times = e->pinned_times.data;
@@ -630,30 +650,68 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
     PB_RETURN_IF_ERROR(BuildStageTable(e, times, steps * evaluations,
                                        e->stage_table.data, stream));
     if (flow->n > 0) {
-      while (e->timing_events.size() < 2 * (launches + 1)) {
+      while (e->timing_events.size() < 2 * (phases + 1)) {
         cudaEvent_t event;
         PB_CUDA(cudaEventCreate(&event));
         e->timing_events.push_back(event);
       }
-      PB_CUDA(cudaEventRecord(e->timing_events[2 * launches], stream));
-      unsigned const grid =
-          static_cast<unsigned>((flow->n + kFlowThreads - 1) / kFlowThreads);
-      long long const every = sampling ? flow->sample_every : 0;
-#define PB_LAUNCH_SRKN(kMinBlocks)                                            \
-  SrknFlowKernel<true, kMinBlocks>                                            \
-      <<<grid, kFlowThreads, 0, stream>>>(                                    \
-          view, tableau, h, e->stage_table.data, steps, flow->n, flow->state, \
-          steps_done, every, flow->max_samples, flow->samples,                \
-          e->status_word.data)
-      switch (SrknMinBlocks()) {
-        case 2: PB_LAUNCH_SRKN(2); break;
-        case 4: PB_LAUNCH_SRKN(4); break;
-        default: PB_LAUNCH_SRKN(3); break;
+      // The probes are cut into `groups` slices and the steps into sub-chunks;
+      // slice g runs its sub-chunks in order on helper stream g.  Whole
+      // launches of 10^5 probes leave 12 % of the SM slots idle in their last
+      // wave (782 CTAs on 444 slots); short launches from several streams keep
+      // the slots full, and no kernel ever waits on another one.
+      long long const blocks = (flow->n + kFlowThreads - 1) / kFlowThreads;
+      int const groups = static_cast<int>(
+          std::min<long long>(FlowGroups(), std::max<long long>(1, blocks / 64)));
+      int const sub_steps = groups > 1 ? FlowSubSteps() : steps;
+      while (static_cast<int>(e->flow_streams.size()) < groups) {
+        cudaStream_t helper;
+        PB_CUDA(cudaStreamCreateWithFlags(&helper, cudaStreamNonBlocking));
+        e->flow_streams.push_back(helper);
+        cudaEvent_t event;
+        PB_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+        e->flow_events.push_back(event);
       }
+      cudaEvent_t const fork = e->timing_events[2 * phases];
+      cudaEvent_t const join = e->timing_events[2 * phases + 1];
+      PB_CUDA(cudaEventRecord(fork, stream));
+      long long const every = sampling ? flow->sample_every : 0;
+      for (int g = 0; g < groups; ++g) {
+        cudaStream_t const helper = groups > 1 ? e->flow_streams[g] : stream;
+        if (groups > 1) {
+          PB_CUDA(cudaStreamWaitEvent(helper, fork, 0));
+        }
+        long long const i_begin = blocks * g / groups * kFlowThreads;
+        long long const i_end = std::min<long long>(
+            flow->n, blocks * (g + 1) / groups * kFlowThreads);
+        unsigned const grid = static_cast<unsigned>(
+            (i_end - i_begin + kFlowThreads - 1) / kFlowThreads);
+        for (int s0 = 0; s0 < steps; s0 += sub_steps) {
+          int const n_sub = std::min(sub_steps, steps - s0);
+          double const* const table =
+              e->stage_table.data +
+              static_cast<std::size_t>(s0) * evaluations * view.stage_stride;
+#define PB_LAUNCH_SRKN(kMinBlocks)                                            \
+  SrknFlowKernel<true, kMinBlocks><<<grid, kFlowThreads, 0, helper>>>(        \
+      view, tableau, h, table, n_sub, flow->n, i_begin, i_end, flow->state,   \
+      steps_done + s0, every, flow->max_samples, flow->samples,               \
+      e->status_word.data)
+          switch (SrknMinBlocks()) {
+            case 2: PB_LAUNCH_SRKN(2); break;
+            case 4: PB_LAUNCH_SRKN(4); break;
+            default: PB_LAUNCH_SRKN(3); break;
+          }
 #undef PB_LAUNCH_SRKN
-      PB_LAUNCHED();
-      PB_CUDA(cudaEventRecord(e->timing_events[2 * launches + 1], stream));
-      ++launches;
+          PB_LAUNCHED();
+          ++launches;
+        }
+        if (groups > 1) {
+          PB_CUDA(cudaEventRecord(e->flow_events[g], helper));
+          PB_CUDA(cudaStreamWaitEvent(stream, e->flow_events[g], 0));
+        }
+      }
+      PB_CUDA(cudaEventRecord(join, stream));
+      ++phases;
     }
     steps_done += steps;
   }
@@ -662,7 +720,9 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
   PB_CUDA(cudaStreamSynchronize(stream));
   e->last_flow_kernel_ms = 0;
   e->last_flow_kernel_launches = static_cast<std::int64_t>(launches);
-  for (std::size_t i = 0; i < launches; ++i) {
+  // Device time of the flow-kernel phases (fork to join on the caller's
+  // stream; the kernels of one phase overlap each other).
+  for (std::size_t i = 0; i < phases; ++i) {
     float elapsed = 0;
     PB_CUDA(cudaEventElapsedTime(&elapsed, e->timing_events[2 * i],
                                  e->timing_events[2 * i + 1]));
