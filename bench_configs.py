@@ -1,0 +1,215 @@
+#!/usr/bin/env python3
+"""Secondary measurements: BASELINE.json configs 3, 4 and 5 (bench.py is the
+headline, config 2).  One JSON line per config.
+
+  python bench_configs.py [--config adaptive|ensemble|allpairs|all]
+  torchrun --nproc-per-node N ... bench_configs.py      (weak scaling; the
+      all-pairs config is i-block sharded with an NCCL all-gather)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, 'tests'))
+
+
+def dist_setup():
+  import torch
+  import torch.distributed as dist
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local_rank)
+  if world > 1 and not dist.is_initialized():
+    dist.init_process_group('nccl',
+                            device_id=torch.device('cuda', local_rank))
+  return torch, dist, world, rank, local_rank
+
+
+def max_over_ranks(torch, dist, world, value, device):
+  t = torch.tensor([value], dtype=torch.float64, device=device)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  return float(t.item())
+
+
+def sum_over_ranks(torch, dist, world, value, device):
+  t = torch.tensor([value], dtype=torch.float64, device=device)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+  return float(t.item())
+
+
+def bench_adaptive(args):
+  """Config 3: eccentric probes, DormandElMikkawyPrince1986RKN434FM,
+  1 mm / 1 mm/s, per-probe step control; probes sharded by rank."""
+  torch, dist, world, rank, local_rank = dist_setup()
+  from principia_b200 import workloads
+  from principia_b200.ephemeris import Ephemeris
+  device = torch.device('cuda', local_rank)
+  system = workloads.sol_system()
+  ephemeris = Ephemeris(system, device=local_rank)
+  workloads.upload_sol_ephemeris(ephemeris)
+  earth = system.bodies[system.index('Earth')]
+  n = args.probes
+  state0 = workloads.eccentric_probes(n, earth['q'], earth['v'], earth['mu'],
+                                      42 + rank)
+  t_final = args.span
+  results = []
+  for repeat in range(2):
+    state, times = state0.copy(), np.zeros((2, n))
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    result = ephemeris.flow_with_adaptive_step(t_final, state, times, 1e-3,
+                                               1e-3)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    kernel_ms, _ = ephemeris.last_flow_kernel_ms()
+    results.append((wall, kernel_ms, result))
+  wall, kernel_ms, result = results[-1]
+  assert np.all(result['status'] == 0)
+  kernel_s = max_over_ranks(torch, dist, world, kernel_ms * 1e-3, device)
+  wall = max_over_ranks(torch, dist, world, wall, device)
+  steps = sum_over_ranks(torch, dist, world, float(result['accepted'].sum()),
+                         device)
+  evaluations = sum_over_ranks(torch, dist, world,
+                               float(result['evaluations'].sum()), device)
+  if rank == 0:
+    print(json.dumps({
+        'config': 'config 3: eccentric probes, adaptive RKN434FM, 1 mm, 1 mm/s',
+        'n_gpus': world, 'probes_per_gpu': n, 'span_seconds': t_final,
+        'accepted_steps': steps, 'rhs_evaluations': evaluations,
+        'kernel_seconds': kernel_s, 'e2e_seconds': wall,
+        'probe_steps_per_second': steps / kernel_s,
+        'probe_rkn_stages_per_second': evaluations / kernel_s,
+        'e2e_probe_rkn_stages_per_second': evaluations / wall,
+        'mean_steps_per_probe': steps / (n * world),
+        'max_steps_per_probe': int(result['accepted'].max())}))
+
+
+def bench_ensemble(args):
+  """Config 4: perturbed TRAPPIST-1 systems, Quinlan1999Order8A, 30 min."""
+  torch, dist, world, rank, local_rank = dist_setup()
+  from principia_b200 import _capi
+  from principia_b200.ephemeris import Ephemeris
+  from principia_b200.nbody import NBodyEnsemble
+  from principia_b200.solar_system import SolarSystem
+  from test_gpu_nbody import ensemble_state
+  device = torch.device('cuda', local_rank)
+  system = SolarSystem.from_fixture('trappist_jd2457000')
+  ephemeris = Ephemeris(system, device=local_rank)
+  order, _ = ephemeris.internal_order()
+  n = args.systems
+  state0 = ensemble_state(system, order, n, 1e-6, seed=42 + rank)
+  t0 = system.epoch
+  step = 1800.0
+  ensemble = NBodyEnsemble(ephemeris, _capi.QUINLAN_1999_ORDER_8A, step,
+                           state0, t0)
+  torch.cuda.synchronize()
+  start = time.perf_counter()
+  startup_steps = ensemble.solve(t0 + 7 * step)  # The SRKN14A startup.
+  torch.cuda.synchronize()
+  startup = time.perf_counter() - start
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  start = time.perf_counter()
+  steps = ensemble.solve(t0 + (7 + args.steps) * step)
+  torch.cuda.synchronize()
+  seconds = max_over_ranks(torch, dist, world, time.perf_counter() - start,
+                           device)
+  pairs = 28
+  if rank == 0:
+    print(json.dumps({
+        'config': 'config 4: TRAPPIST-1 ensemble, Quinlan1999Order8A, 30 min',
+        'n_gpus': world, 'systems_per_gpu': n, 'steady_steps': steps,
+        'startup_steps': startup_steps, 'startup_seconds': startup,
+        'seconds': seconds,
+        'system_steps_per_second': world * n * steps / seconds,
+        'pair_interactions_per_second': world * n * steps * pairs / seconds}))
+
+
+def bench_allpairs(args):
+  """Config 5: N point masses, all pairs; i-block sharded, NCCL all-gather of
+  the positions before every force evaluation."""
+  torch, dist, world, rank, local_rank = dist_setup()
+  from principia_b200 import _capi, sharding
+  from principia_b200.nbody import NBodyAllPairs
+  from test_gpu_nbody import random_cluster
+  device = torch.device('cuda', local_rank)
+  n = args.bodies
+  mu, q, v = random_cluster(n, seed=42)
+  begin, end = sharding.equal_block_range(n, rank, world)
+  exchange = None
+  if world > 1:
+    exchange = sharding.AllGatherExchange(n, dist, device)
+  system = NBodyAllPairs(_capi.BLANES_MOAN_2002_SRKN_14A, 3600.0, mu, q, v,
+                         0.0, i_begin=begin, i_end=end, device=local_rank,
+                         exchange=exchange)
+  system.accelerations()  # Warm-up.
+  torch.cuda.synchronize()
+  force_ms = []
+  walls = []
+  for _ in range(args.steps):
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    system.accelerations()
+    torch.cuda.synchronize()
+    walls.append(time.perf_counter() - t0)
+    force_ms.append(system.last_force_ms())
+  kernel_s = max_over_ranks(torch, dist, world, float(np.mean(force_ms)) * 1e-3,
+                            device)
+  wall = max_over_ranks(torch, dist, world, float(np.mean(walls)), device)
+  interactions = float(n) * (n - 1)
+  flops = interactions * 18
+  # One SRKN14A step of the flow (14 force evaluations + all-gathers).
+  if world > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  steps, forces = system.solve(3600.0)
+  torch.cuda.synchronize()
+  flow_seconds = max_over_ranks(torch, dist, world, time.perf_counter() - t0,
+                                device)
+  if rank == 0:
+    print(json.dumps({
+        'config': 'config 5: all-pairs point masses, i-block sharded',
+        'n_gpus': world, 'n_bodies': n,
+        'force_kernel_seconds': kernel_s,
+        'force_call_seconds_with_exchange': wall,
+        'pair_interactions_per_second': interactions / kernel_s,
+        'algorithmic_tflops': flops / kernel_s / 1e12,
+        'srkn14a_step_seconds': flow_seconds, 'force_evaluations': forces,
+        'flow_pair_interactions_per_second':
+            forces * interactions / flow_seconds}))
+
+
+def main():
+  parser = argparse.ArgumentParser()
+  parser.add_argument('--config', default='all')
+  parser.add_argument('--probes', type=int, default=100000)
+  parser.add_argument('--span', type=float, default=86400.0)
+  parser.add_argument('--systems', type=int, default=100000)
+  parser.add_argument('--steps', type=int, default=20)
+  parser.add_argument('--bodies', type=int, default=2**17)
+  args = parser.parse_args()
+  if args.config in ('adaptive', 'all'):
+    bench_adaptive(args)
+  if args.config in ('ensemble', 'all'):
+    bench_ensemble(args)
+  if args.config in ('allpairs', 'all'):
+    bench_allpairs(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -258,14 +258,21 @@ def test_full_size_flow_properties(sol_system, sol_oracle, sol_gpu):
   state0 = leo(sol_system, n)
   state = state0.copy()
   time = np.zeros(2)
-  result = sol_gpu.flow_with_fixed_step(method, 10.0, 1000.0, state, time)
+  # At this size the call is sliced over helper streams and sub-chunks of
+  # steps; samples cross slice boundaries.
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 1000.0, state, time,
+                                        sample_every=33, max_samples=3)
   assert result['n_steps'] == 100 and result['status'] == 0
-  subset = np.r_[0:40, 49980:50020, n - 40:n]
+  subset = np.r_[0:40, 24990:25010, 49980:50020, n - 40:n]
   expected_state = np.ascontiguousarray(state0[:, subset])
   expected_time = np.zeros(2)
-  sol_oracle.flow_with_fixed_step(method, 10.0, 1000.0, expected_state,
-                                  expected_time)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, 1000.0,
+                                             expected_state, expected_time,
+                                             sample_every=33, max_samples=3)
   assert_bitwise_equal(state[:, subset], expected_state, 'subset')
+  assert_bitwise_equal(result['sample_times'], expected['sample_times'])
+  assert_bitwise_equal(result['samples'][:, :, subset], expected['samples'],
+                       'subset samples')
   # Energy relative to the Earth.
   earth = sol_system.index('Earth')
   mu = sol_system.bodies[earth]['mu']
