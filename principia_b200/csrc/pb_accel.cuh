@@ -50,6 +50,49 @@ PB_HD Vec3 EvaluateSegment(EphemerisView const& e, int const segment,
           EstrinEvaluate<3>(c + 2, degree, x)};
 }
 
+// EvaluateSegment with the Estrin tree of each Newhall degree (3..17,
+// continuous_trajectory_body.hpp:35-37) instantiated at compile time; any other
+// degree takes the run-time tree.  Same operations, same bits.
+PB_HD Vec3 EvaluateSegmentUnrolled(EphemerisView const& e, int const segment,
+                                   double const t) {
+  double const x = t - e.segment_origin[segment];
+  double const* const c =
+      e.segment_coefficients + static_cast<long long>(segment) * 3 *
+                                   kSegmentCoefficients;
+  int const degree = e.segment_degree[segment];
+  double const x2 = x * x;
+  double const x4 = x2 * x2;
+  double const x8 = x4 * x4;
+  double const x16 = x8 * x8;
+  switch (degree) {
+#define PB_ESTRIN_CASE(d)                                               \
+  case d:                                                               \
+    return {EstrinFixedNode<3, 0, d>(c, x, x2, x4, x8, x16),            \
+            EstrinFixedNode<3, 0, d>(c + 1, x, x2, x4, x8, x16),        \
+            EstrinFixedNode<3, 0, d>(c + 2, x, x2, x4, x8, x16)};
+    PB_ESTRIN_CASE(3)
+    PB_ESTRIN_CASE(4)
+    PB_ESTRIN_CASE(5)
+    PB_ESTRIN_CASE(6)
+    PB_ESTRIN_CASE(7)
+    PB_ESTRIN_CASE(8)
+    PB_ESTRIN_CASE(9)
+    PB_ESTRIN_CASE(10)
+    PB_ESTRIN_CASE(11)
+    PB_ESTRIN_CASE(12)
+    PB_ESTRIN_CASE(13)
+    PB_ESTRIN_CASE(14)
+    PB_ESTRIN_CASE(15)
+    PB_ESTRIN_CASE(16)
+    PB_ESTRIN_CASE(17)
+#undef PB_ESTRIN_CASE
+    default:
+      return {EstrinEvaluate<3>(c, degree, x),
+              EstrinEvaluate<3>(c + 1, degree, x),
+              EstrinEvaluate<3>(c + 2, degree, x)};
+  }
+}
+
 // Fills one stage-table entry for body b at time t.
 PB_HD void FillStageEntry(EphemerisView const& e, int const b, double const t,
                           double* const entry) {

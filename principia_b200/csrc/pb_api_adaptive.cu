@@ -2,13 +2,31 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <limits>
 #include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/principia_b200.h"
 #include "pb_kernels_adaptive.cuh"
 #include "pb_runtime.cuh"
 
 using namespace pb;
+
+namespace {
+
+// Resident blocks per SM of the adaptive kernel (register budget 168 / 255).
+int AdaptiveMinBlocks() {
+  static int const value = [] {
+    char const* const text = std::getenv("PB_ADAPTIVE_MIN_BLOCKS");
+    int const v = text != nullptr ? std::atoi(text) : 3;
+    return v == 2 ? 2 : 3;
+  }();
+  return value;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -42,21 +60,73 @@ pb_status_t pb_flow_with_adaptive_step_device(
   if (flow->n == 0) {
     return PB_OK;
   }
+  if (flow->n > std::numeric_limits<int>::max()) {
+    return Fail(PB_INVALID_ARGUMENT, "too many trajectories in one call");
+  }
+  int const n = static_cast<int>(flow->n);
+  int const n_bodies = static_cast<int>(e->model.bodies.size());
+  if (n_bodies > kMaxConstantBodies) {
+    return Fail(PB_INVALID_ARGUMENT, "too many bodies for the flow kernel");
+  }
+  static BodyScalars scalars;
+  for (int b = 0; b < n_bodies; ++b) {
+    DeviceBody const& body = e->model.bodies[b];
+    scalars.mu[b] = body.mu;
+    scalars.collision_radius[b] = body.collision_radius;
+    scalars.outer_threshold_degree_2[b] =
+        body.is_oblate && body.n_damping > 2
+            ? e->model.dampings[body.damping_offset + 2].outer_threshold
+            : -std::numeric_limits<double>::infinity();
+  }
+  PB_CUDA(cudaMemcpyToSymbolAsync(c_adaptive_bodies, &scalars, sizeof(scalars),
+                                  0, cudaMemcpyHostToDevice, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+
+  // Execution order: decreasing estimated cost.
+  PB_RETURN_IF_ERROR(e->adaptive_cost.Reserve(2 * static_cast<std::size_t>(n)));
+  PB_RETURN_IF_ERROR(e->adaptive_order.Reserve(2 * static_cast<std::size_t>(n)));
+  PB_RETURN_IF_ERROR(e->adaptive_queue.Reserve(1));
+  float* const cost_in = e->adaptive_cost.data;
+  float* const cost_out = cost_in + n;
+  int* const index_in = e->adaptive_order.data;
+  int* const order = index_in + n;
+  std::size_t sort_bytes = 0;
+  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
+      nullptr, sort_bytes, cost_in, cost_out, index_in, order, n, 0, 32,
+      stream));
+  PB_RETURN_IF_ERROR(e->adaptive_sort_storage.Reserve(sort_bytes));
+  sort_bytes = e->adaptive_sort_storage.capacity;
+  AdaptiveCostKernel<<<(n + 127) / 128, 128, 0, stream>>>(
+      e->View(), parameters.t_final, flow->n, flow->state, flow->time, cost_in,
+      index_in);
+  PB_LAUNCHED();
+  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
+      e->adaptive_sort_storage.data, sort_bytes, cost_in, cost_out, index_in,
+      order, n, 0, 32, stream));
+  PB_CUDA(cudaMemsetAsync(e->adaptive_queue.data, 0,
+                          sizeof(unsigned long long), stream));
+  int sm_count = 0;
+  PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
+                                 e->device));
+  int const min_blocks = AdaptiveMinBlocks();
+  unsigned const blocks = static_cast<unsigned>(
+      std::min<long long>((flow->n + kAdaptiveThreads - 1) / kAdaptiveThreads,
+                          static_cast<long long>(sm_count) * min_blocks));
   while (e->timing_events.size() < 2) {
     cudaEvent_t event;
     PB_CUDA(cudaEventCreate(&event));
     e->timing_events.push_back(event);
   }
   PB_CUDA(cudaEventRecord(e->timing_events[0], stream));
-  ErknFlowKernel<true>
-      <<<static_cast<unsigned>((flow->n + kAdaptiveThreads - 1) /
-                               kAdaptiveThreads),
-         kAdaptiveThreads, 0, stream>>>(
-          e->View(), parameters, flow->n, flow->state, flow->time, flow->status,
-          reinterpret_cast<long long*>(flow->accepted_steps),
-          reinterpret_cast<long long*>(flow->rejected_steps),
-          reinterpret_cast<long long*>(flow->evaluations), flow->step_log,
-          flow->state_log);
+  auto const kernel =
+      min_blocks == 2 ? ErknFlowKernel<2> : ErknFlowKernel<3>;
+  kernel<<<blocks, kAdaptiveThreads, 0, stream>>>(
+      e->View(), parameters, flow->n, order, e->adaptive_queue.data,
+      flow->state, flow->time, flow->status,
+      reinterpret_cast<long long*>(flow->accepted_steps),
+      reinterpret_cast<long long*>(flow->rejected_steps),
+      reinterpret_cast<long long*>(flow->evaluations), flow->step_log,
+      flow->state_log);
   PB_LAUNCHED();
   PB_CUDA(cudaEventRecord(e->timing_events[1], stream));
   PB_CUDA(cudaStreamSynchronize(stream));

@@ -3,8 +3,10 @@
 // integrator_body.hpp:44-258) with DormandالمكاوىPrince1986RKN434FM
 // (integrators/methods.hpp:574-597), driven like
 // Ephemeris::FlowODEWithAdaptiveStep (physics/ephemeris_body.hpp:1624-1717):
-// one independent trajectory per thread; step size, error control, rejection
-// loop and FSAL state all in registers.
+// one independent trajectory per lane; step size, error control, rejection
+// loop and FSAL state all in registers.  The lanes are persistent: a lane that
+// finishes its trajectory takes the next one from a queue ordered by decreasing
+// estimated cost, so a warp never idles behind its longest trajectory.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -14,7 +16,9 @@
 
 namespace pb {
 
-constexpr int kAdaptiveThreads = 64;
+constexpr int kAdaptiveThreads = 128;
+
+static __constant__ BodyScalars c_adaptive_bodies;
 
 // Right-hand side at a per-probe time: every massive body's polynomial is
 // evaluated here (the stage-table trick of the fixed-step kernel needs a time
@@ -75,25 +79,158 @@ __device__ __forceinline__ double StdMin(double const a, double const b) {
   return (b < a) ? b : a;
 }
 
-// state: 12 planes of n; time: 2 planes of n (value, error).
-template<bool kUnrolled>
-__global__ void __launch_bounds__(kAdaptiveThreads)
-ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
-               long long const n, double* __restrict__ state,
-               double* __restrict__ time, int32_t* __restrict__ status_out,
-               long long* __restrict__ accepted_out,
-               long long* __restrict__ rejected_out,
-               long long* __restrict__ evaluations_out,
-               double* __restrict__ step_log,
-               double* __restrict__ state_log) {
+// The reference formulation with the IEEE operators, out of line: taken when
+// a distance leaves the range of the branch-free square root / division.
+__device__ __noinline__ int32_t SlowAccelerationAtTime(EphemerisView const& e,
+                                                       double const t,
+                                                       Vec3 const& q,
+                                                       Vec3& acceleration) {
+  int hint = 0;
+  return AccelerationOnMasslessBodyAtTime<false>(e, t, q, acceleration, hint);
+}
+
+__device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
+                                               int const b1, double const t,
+                                               Vec3 const& dq,
+                                               double const dq_norm,
+                                               double const dq2,
+                                               double const one_over_dq3) {
+  GeopotentialBody const g = MakeGeopotentialBody(e, b1);
+  FrameSource const frame{nullptr, t};
+  return GeneralSphericalHarmonicsAcceleration<true>(g, frame, -dq, dq_norm,
+                                                     dq2, one_over_dq3);
+}
+
+// AccelerationOnMasslessBodyAtTime with the Estrin trees in registers, the
+// branch-free square root and division (pb_math.cuh) and the early exit for
+// oblate bodies beyond their degree-2 outer threshold: the same arithmetic,
+// body by body in the same order.
+__device__ __forceinline__ int32_t FastAccelerationAtTime(
+    EphemerisView const& e, double const t, Vec3 const& q, Vec3& acceleration,
+    int& hint) {
+  double ax = 0.0, ay = 0.0, az = 0.0;
+  int32_t error = 0;
+  bool in_range = true;
+  int const n_bodies = e.n_bodies;
+  int const n_oblate = e.n_oblate;
+#pragma unroll 1
+  for (int b1 = 0; b1 < n_bodies; ++b1) {
+    int const begin = __ldg(e.segment_offset + b1);
+    int const end = __ldg(e.segment_offset + b1 + 1);
+    int segment = begin + hint;
+    // First segment with t <= t_max (continuous_trajectory_body.hpp:860-885).
+    if (!(segment < end && t <= __ldg(e.segment_t_max + segment) &&
+          (segment == begin || __ldg(e.segment_t_max + segment - 1) < t))) {
+      segment = FindSegment(e.segment_t_max, begin, end, t);
+      hint = segment - begin;
+    }
+    Vec3 const position1 = EvaluateSegmentUnrolled(e, segment, t);
+    double const mu1 = c_adaptive_bodies.mu[b1];
+    double const dx = position1.x - q.x;
+    double const dy = position1.y - q.y;
+    double const dz = position1.z - q.z;
+    double const dq2 = dx * dx + dy * dy + dz * dz;
+    in_range = in_range && InFastRange(dq2);
+    double const dq_norm = FastSqrt(dq2);
+    error |= dq_norm > c_adaptive_bodies.collision_radius[b1] ? 0 : 11;
+    double const one_over_dq3 = FastDivide(dq_norm, dq2 * dq2);
+    double const mu1_over_dq3 = mu1 * one_over_dq3;
+    ax += dx * mu1_over_dq3;
+    ay += dy * mu1_over_dq3;
+    az += dz * mu1_over_dq3;
+    if (b1 < n_oblate) {
+      // A NaN distance fails the comparison and takes the full path.
+      if (!(dq_norm >= c_adaptive_bodies.outer_threshold_degree_2[b1])) {
+        Vec3 const effect = AdaptiveHarmonics(e, b1, t, Vec3{dx, dy, dz},
+                                              dq_norm, dq2, one_over_dq3);
+        ax += mu1 * effect.x;
+        ay += mu1 * effect.y;
+        az += mu1 * effect.z;
+      } else {
+        // The reference adds mu1 * (zero vector) here.
+        double const zero = mu1 * 0.0;
+        ax += zero;
+        ay += zero;
+        az += zero;
+      }
+    }
+  }
+  if (!in_range) {
+    return SlowAccelerationAtTime(e, t, q, acceleration);
+  }
+  acceleration = {ax, ay, az};
+  return error;
+}
+
+// Scheduling key of a trajectory: an estimate of its number of steps, from the
+// osculating orbit around the body with the strongest tide at the initial
+// state.  With a 4th-order error estimate the step scales like
+// (tolerance / a)^(1/4) / n (n the mean motion), so the cost over a span is
+// proportional to span * n * a^(1/4).  Only the order of execution depends on
+// it, never a result.
+static __global__ void AdaptiveCostKernel(EphemerisView const e,
+                                          double const t_final,
+                                          long long const n,
+                                          double const* __restrict__ state,
+                                          double const* __restrict__ time,
+                                          float* __restrict__ cost,
+                                          int* __restrict__ index) {
   long long const i =
       static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) {
     return;
   }
+  double const t = time[i];
+  Vec3 const q{state[i], state[n + i], state[2 * n + i]};
+  Vec3 const v{state[6 * n + i], state[7 * n + i], state[8 * n + i]};
+  double best_tide = -1.0;
+  double best_mu = 0.0;
+  Vec3 best_dq{0.0, 0.0, 0.0}, best_dv{0.0, 0.0, 0.0};
+  for (int b = 0; b < e.n_bodies; ++b) {
+    int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
+                                    e.segment_offset[b + 1], t);
+    Vec3 const p0 = EvaluateSegment(e, segment, t);
+    Vec3 const dq = q - p0;
+    double const r2 = Norm2(dq);
+    double const mu = e.bodies[b].mu;
+    double const tide = mu / (r2 * sqrt(r2));
+    if (tide > best_tide) {
+      Vec3 const p1 = EvaluateSegment(e, segment, t + 1.0);
+      best_tide = tide;
+      best_mu = mu;
+      best_dq = dq;
+      best_dv = v - (p1 - p0);
+    }
+  }
+  double const r = sqrt(Norm2(best_dq));
+  double const energy = 0.5 * Norm2(best_dv) - best_mu / r;
+  double a = r;
+  if (energy < 0.0) {
+    a = -0.5 * best_mu / energy;
+  }
+  double const mean_motion = sqrt(best_mu / (a * a * a));
+  double const steps = fabs(t_final - t) * mean_motion * sqrt(sqrt(a));
+  cost[i] = steps == steps ? static_cast<float>(steps) : 0.0f;
+  index[i] = static_cast<int>(i);
+}
+
+// state: 12 planes of n; time: 2 planes of n (value, error).  `order` lists
+// the trajectories in the order in which the lanes take them; `queue` is the
+// number of trajectories taken so far (zeroed by the host).
+template<int kMinBlocks>
+__global__ void __launch_bounds__(kAdaptiveThreads, kMinBlocks)
+ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
+               long long const n, int const* __restrict__ order,
+               unsigned long long* __restrict__ queue,
+               double* __restrict__ state, double* __restrict__ time,
+               int32_t* __restrict__ status_out,
+               long long* __restrict__ accepted_out,
+               long long* __restrict__ rejected_out,
+               long long* __restrict__ evaluations_out,
+               double* __restrict__ step_log,
+               double* __restrict__ state_log) {
   // DormandالمكاوىPrince1986RKN434FM, methods.hpp:574-597.
-  constexpr int stages = 4;
-  constexpr double c[4] = {0.0, 1.0 / 4.0, 7.0 / 10.0, 1.0};
+  constexpr double c1 = 1.0 / 4.0, c2 = 7.0 / 10.0, c3 = 1.0;
   constexpr double a10 = 1.0 / 32.0;
   constexpr double a20 = 7.0 / 1000.0, a21 = 119.0 / 500.0;
   constexpr double a30 = 1.0 / 14.0, a31 = 8.0 / 27.0, a32 = 25.0 / 189.0;
@@ -104,148 +241,168 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
   constexpr double b_prime[4] = {13.0 / 21.0, -20.0 / 27.0, 275.0 / 189.0,
                                  -1.0 / 3.0};
   constexpr double safety_factor = 0.9;
-
-  DP t{time[i], time[n + i]};
-  DP q[3], v[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    q[k].value = state[(0 + k) * n + i];
-    q[k].error = state[(3 + k) * n + i];
-    v[k].value = state[(6 + k) * n + i];
-    v[k].error = state[(9 + k) * n + i];
-  }
-  long long accepted = 0, rejected = 0, evaluations = 0;
-  int32_t final_status = PB_OK;
   double const t_final = parameters.t_final;
 
-  // FlowODEWithAdaptiveStep, ephemeris_body.hpp:1634-1637.
-  if (t.value != parameters.t_requested) {
-    double h = t_final - t.value;  // first_step.
-    if (!(h > 0.0)) {
-      // CHECK_GT(first_step, 0): "Flow back to the future".
-      final_status = PB_INVALID_ARGUMENT;
-    } else {
-      Vec3 g[4];
-      bool at_end = false;
-      double tolerance_to_error_ratio = 0.0;
-      int first_stage = 0;
-      long long step_count = 0;
-      int32_t status = PB_OK;
-      int32_t step_status = PB_OK;
-      bool first_iteration = true;
-      int hint = 0;
-      bool done = false;
-      Vec3 dq_hat, dv_hat;
-      while (!at_end && !done) {
-        do {
-          if (!first_iteration) {
-            step_status = PB_OK;
-            // Root<lower_order + 1> = x^(1/4).
-            h *= safety_factor * CrRoot4(tolerance_to_error_ratio);
-            if (t.value + (t.error + h) == t.value) {
-              final_status = PB_FAILED_PRECONDITION;  // VanishingStepSize.
-              done = true;
-              break;
-            }
-          }
-          first_iteration = false;
-          // last_step_is_exact.
-          double const time_to_end = (t_final - t.value) - t.error;
-          at_end = h >= time_to_end;
-          if (at_end) {
-            h = time_to_end;
-          }
-          double const h2 = h * h;
-          for (int s = first_stage; s < stages; ++s) {
-            double const t_stage = (at_end && c[s] == 1.0)
-                                       ? t_final
-                                       : t.value + (t.error + c[s] * h);
-            double qs[3];
+  // The trajectory of this lane.
+  bool busy = false;
+  long long i = 0;
+  DP t{0.0, 0.0};
+  DP q[3], v[3];
+  double h = 0.0;
+  double tolerance_to_error_ratio = 0.0;
+  Vec3 g0{0.0, 0.0, 0.0}, g1 = g0, g2 = g0, g3 = g0;
+  bool first_iteration = true;
+  int first_stage = 0;
+  int hint = 0;
+  long long accepted = 0, rejected = 0, evaluations = 0;
+  int32_t status = PB_OK, step_status = PB_OK, final_status = PB_OK;
+
+  for (;;) {
+    bool finished = false;
+    // Whether the exit goes through the epilogue of FlowODEWithAdaptiveStep.
+    bool flowed = true;
+    if (!busy) {
+      unsigned long long const ticket = atomicAdd(queue, 1ULL);
+      if (ticket >= static_cast<unsigned long long>(n)) {
+        break;
+      }
+      i = order != nullptr ? order[ticket] : static_cast<long long>(ticket);
+      t = {time[i], time[n + i]};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              double const g0 = k == 0 ? g[0].x : (k == 1 ? g[0].y : g[0].z);
-              double const g1 = k == 0 ? g[1].x : (k == 1 ? g[1].y : g[1].z);
-              double const g2 = k == 0 ? g[2].x : (k == 1 ? g[2].y : g[2].z);
-              double sum = 0.0;
-              if (s == 1) {
-                sum += a10 * g0;
-              } else if (s == 2) {
-                sum += a20 * g0;
-                sum += a21 * g1;
-              } else if (s == 3) {
-                sum += a30 * g0;
-                sum += a31 * g1;
-                sum += a32 * g2;
-              }
-              qs[k] = q[k].value + h * c[s] * v[k].value + h2 * sum;
-            }
-            Vec3 const q_stage{qs[0], qs[1], qs[2]};
-            Vec3 acceleration;
-            int32_t const rhs_error = AccelerationOnMasslessBodyAtTime<kUnrolled>(
-                e, t_stage, q_stage, acceleration, hint);
-            g[s] = acceleration;
-            ++evaluations;
-            if (step_status == PB_OK && rhs_error != 0) {
-              step_status = PB_OUT_OF_RANGE;
-            }
-          }
-          double position_error[3], velocity_error[3];
-          double dqh[3], dvh[3];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            double sum_b_hat = 0.0, sum_b = 0.0, sum_b_hat_prime = 0.0,
-                   sum_b_prime = 0.0;
-#pragma unroll
-            for (int s = 0; s < stages; ++s) {
-              double const gs = k == 0 ? g[s].x : (k == 1 ? g[s].y : g[s].z);
-              sum_b_hat += b_hat[s] * gs;
-              sum_b += b[s] * gs;
-              sum_b_hat_prime += b_hat_prime[s] * gs;
-              sum_b_prime += b_prime[s] * gs;
-            }
-            dqh[k] = h * v[k].value + h2 * sum_b_hat;
-            double const dq_low = h * v[k].value + h2 * sum_b;
-            dvh[k] = h * sum_b_hat_prime;
-            double const dv_low = h * sum_b_prime;
-            position_error[k] = dq_low - dqh[k];
-            velocity_error[k] = dv_low - dvh[k];
-          }
-          dq_hat = {dqh[0], dqh[1], dqh[2]};
-          dv_hat = {dvh[0], dvh[1], dvh[2]};
-          // Ephemeris::ToleranceToErrorRatio, ephemeris_body.hpp:1698-1717.
-          Vec3 const pe{position_error[0], position_error[1],
-                        position_error[2]};
-          Vec3 const ve{velocity_error[0], velocity_error[1],
-                        velocity_error[2]};
-          double const max_length_error = StdMax(0.0, sqrt(Norm2(pe)));
-          double const max_speed_error = StdMax(0.0, sqrt(Norm2(ve)));
-          tolerance_to_error_ratio = StdMin(
-              parameters.length_integration_tolerance / max_length_error,
-              parameters.speed_integration_tolerance / max_speed_error);
-          if (tolerance_to_error_ratio < 1.0) {
-            ++rejected;
-          }
-        } while (tolerance_to_error_ratio < 1.0);
-        if (done) {
-          break;
+      for (int k = 0; k < 3; ++k) {
+        q[k].value = state[(0 + k) * n + i];
+        q[k].error = state[(3 + k) * n + i];
+        v[k].value = state[(6 + k) * n + i];
+        v[k].error = state[(9 + k) * n + i];
+      }
+      accepted = rejected = evaluations = 0;
+      status = step_status = final_status = PB_OK;
+      first_iteration = true;
+      first_stage = 0;
+      hint = 0;
+      tolerance_to_error_ratio = 0.0;
+      busy = true;
+      // FlowODEWithAdaptiveStep, ephemeris_body.hpp:1634-1637.
+      if (t.value == parameters.t_requested) {
+        finished = true;
+        flowed = false;
+      } else {
+        h = t_final - t.value;  // first_step.
+        if (!(h > 0.0)) {
+          // CHECK_GT(first_step, 0): "Flow back to the future".
+          final_status = PB_INVALID_ARGUMENT;
+          finished = true;
+          flowed = false;
         }
+      }
+    }
+    if (!finished && !first_iteration) {
+      step_status = PB_OK;
+      // Root<lower_order + 1> = x^(1/4).
+      h *= safety_factor * CrRoot4(tolerance_to_error_ratio);
+      if (t.value + (t.error + h) == t.value) {
+        final_status = PB_FAILED_PRECONDITION;  // VanishingStepSize.
+        finished = true;
+      }
+    }
+    if (!finished) {
+      first_iteration = false;
+      // last_step_is_exact.
+      double const time_to_end = (t_final - t.value) - t.error;
+      bool const at_end = h >= time_to_end;
+      if (at_end) {
+        h = time_to_end;
+      }
+      double const h2 = h * h;
+#pragma unroll 1
+      for (int s = first_stage; s < 4; ++s) {
+        double const c_s = s == 0 ? 0.0 : (s == 1 ? c1 : (s == 2 ? c2 : c3));
+        double const t_stage = (at_end && c_s == 1.0)
+                                   ? t_final
+                                   : t.value + (t.error + c_s * h);
+        Vec3 sum{0.0, 0.0, 0.0};
+        if (s == 1) {
+          sum += a10 * g0;
+        } else if (s == 2) {
+          sum += a20 * g0;
+          sum += a21 * g1;
+        } else if (s == 3) {
+          sum += a30 * g0;
+          sum += a31 * g1;
+          sum += a32 * g2;
+        }
+        Vec3 const q_stage{q[0].value + h * c_s * v[0].value + h2 * sum.x,
+                           q[1].value + h * c_s * v[1].value + h2 * sum.y,
+                           q[2].value + h * c_s * v[2].value + h2 * sum.z};
+        Vec3 acceleration;
+        int32_t const rhs_error =
+            FastAccelerationAtTime(e, t_stage, q_stage, acceleration, hint);
+        if (s == 0) {
+          g0 = acceleration;
+        } else if (s == 1) {
+          g1 = acceleration;
+        } else if (s == 2) {
+          g2 = acceleration;
+        } else {
+          g3 = acceleration;
+        }
+        ++evaluations;
+        if (step_status == PB_OK && rhs_error != 0) {
+          step_status = PB_OUT_OF_RANGE;
+        }
+      }
+      double const gx[4] = {g0.x, g1.x, g2.x, g3.x};
+      double const gy[4] = {g0.y, g1.y, g2.y, g3.y};
+      double const gz[4] = {g0.z, g1.z, g2.z, g3.z};
+      double position_error[3], velocity_error[3];
+      double dqh[3], dvh[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double sum_b_hat = 0.0, sum_b = 0.0, sum_b_hat_prime = 0.0,
+               sum_b_prime = 0.0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          double const gs = k == 0 ? gx[s] : (k == 1 ? gy[s] : gz[s]);
+          sum_b_hat += b_hat[s] * gs;
+          sum_b += b[s] * gs;
+          sum_b_hat_prime += b_hat_prime[s] * gs;
+          sum_b_prime += b_prime[s] * gs;
+        }
+        dqh[k] = h * v[k].value + h2 * sum_b_hat;
+        double const dq_low = h * v[k].value + h2 * sum_b;
+        dvh[k] = h * sum_b_hat_prime;
+        double const dv_low = h * sum_b_prime;
+        position_error[k] = dq_low - dqh[k];
+        velocity_error[k] = dv_low - dvh[k];
+      }
+      // Ephemeris::ToleranceToErrorRatio, ephemeris_body.hpp:1698-1717.
+      Vec3 const pe{position_error[0], position_error[1], position_error[2]};
+      Vec3 const ve{velocity_error[0], velocity_error[1], velocity_error[2]};
+      double const max_length_error = StdMax(0.0, sqrt(Norm2(pe)));
+      double const max_speed_error = StdMax(0.0, sqrt(Norm2(ve)));
+      tolerance_to_error_ratio =
+          StdMin(parameters.length_integration_tolerance / max_length_error,
+                 parameters.speed_integration_tolerance / max_speed_error);
+      if (tolerance_to_error_ratio < 1.0) {
+        ++rejected;
+      } else {
         if (status == PB_OK) {
           status = step_status;
         }
         // first_same_as_last: swap(g.front(), g.back()).
         {
-          Vec3 const front = g[0];
-          g[0] = g[3];
-          g[3] = front;
+          Vec3 const front = g0;
+          g0 = g3;
+          g3 = front;
           first_stage = 1;
         }
         Increment(t, h);
-        Increment(q[0], dq_hat.x);
-        Increment(q[1], dq_hat.y);
-        Increment(q[2], dq_hat.z);
-        Increment(v[0], dv_hat.x);
-        Increment(v[1], dv_hat.y);
-        Increment(v[2], dv_hat.z);
+        Increment(q[0], dqh[0]);
+        Increment(q[1], dqh[1]);
+        Increment(q[2], dqh[2]);
+        Increment(v[0], dvh[0]);
+        Increment(v[1], dvh[1]);
+        Increment(v[2], dvh[2]);
         // append_state.
         if (accepted < parameters.step_log_capacity) {
           if (step_log != nullptr) {
@@ -261,46 +418,52 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
           }
         }
         ++accepted;
-        ++step_count;
-        if (step_count == parameters.max_steps && !at_end) {
+        if (at_end) {
+          finished = true;
+        } else if (accepted == parameters.max_steps) {
           final_status = PB_RESOURCE_EXHAUSTED;  // ReachedMaximalStepCount.
-          done = true;
+          finished = true;
         }
       }
-      if (final_status == PB_OK) {
-        final_status = status;
-      }
-      // ephemeris_body.hpp:1676-1695: collisions are swallowed; not reaching t
-      // is DeadlineExceeded.
-      if (final_status == PB_OUT_OF_RANGE) {
-        final_status = PB_OK;
-      }
-      if (final_status == PB_OK && t_final != parameters.t_requested) {
-        final_status = PB_DEADLINE_EXCEEDED;
-      }
     }
-  }
-  // The last appended state (the trajectory's back()).
-  time[i] = t.value;
-  time[n + i] = t.error;
+    if (finished) {
+      if (flowed) {
+        if (final_status == PB_OK) {
+          final_status = status;
+        }
+        // ephemeris_body.hpp:1676-1695: collisions are swallowed; not reaching
+        // t is DeadlineExceeded.
+        if (final_status == PB_OUT_OF_RANGE) {
+          final_status = PB_OK;
+        }
+        if (final_status == PB_OK && t_final != parameters.t_requested) {
+          final_status = PB_DEADLINE_EXCEEDED;
+        }
+      }
+      // The last appended state (the trajectory's back()).
+      time[i] = t.value;
+      time[n + i] = t.error;
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    state[(0 + k) * n + i] = q[k].value;
-    state[(3 + k) * n + i] = q[k].error;
-    state[(6 + k) * n + i] = v[k].value;
-    state[(9 + k) * n + i] = v[k].error;
-  }
-  if (status_out != nullptr) {
-    status_out[i] = final_status;
-  }
-  if (accepted_out != nullptr) {
-    accepted_out[i] = accepted;
-  }
-  if (rejected_out != nullptr) {
-    rejected_out[i] = rejected;
-  }
-  if (evaluations_out != nullptr) {
-    evaluations_out[i] = evaluations;
+      for (int k = 0; k < 3; ++k) {
+        state[(0 + k) * n + i] = q[k].value;
+        state[(3 + k) * n + i] = q[k].error;
+        state[(6 + k) * n + i] = v[k].value;
+        state[(9 + k) * n + i] = v[k].error;
+      }
+      if (status_out != nullptr) {
+        status_out[i] = final_status;
+      }
+      if (accepted_out != nullptr) {
+        accepted_out[i] = accepted;
+      }
+      if (rejected_out != nullptr) {
+        rejected_out[i] = rejected;
+      }
+      if (evaluations_out != nullptr) {
+        evaluations_out[i] = evaluations;
+      }
+      busy = false;
+    }
   }
 }
 

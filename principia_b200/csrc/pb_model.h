@@ -83,4 +83,16 @@ struct SrknTableau {
   double b[16];
 };
 
+// Per-body scalars that every thread of a flow kernel reads at the same
+// address; kernels keep a copy in the constant bank.
+constexpr int kMaxConstantBodies = 64;
+
+struct BodyScalars {
+  double mu[kMaxConstantBodies];
+  double collision_radius[kMaxConstantBodies];
+  // Geopotential::LimitingDegree returns 2 (no harmonics) iff
+  // !(r < degree_damping[2].outer_threshold); -infinity for spherical bodies.
+  double outer_threshold_degree_2[kMaxConstantBodies];
+};
+
 }  // namespace pb

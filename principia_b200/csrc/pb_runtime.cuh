@@ -26,6 +26,11 @@ inline std::atomic<std::int64_t>& LaunchCount() {
   return count;
 }
 
+inline std::uint64_t NextSerial() {
+  static std::atomic<std::uint64_t> serial{0};
+  return ++serial;
+}
+
 inline pb_status_t Fail(pb_status_t const status, std::string const& message) {
   LastError() = message;
   return status;
@@ -143,6 +148,9 @@ struct HostTrajectory {
 // The opaque handle of the C ABI.
 struct pb_ephemeris {
   int device = 0;
+  // Distinguishes handles whose storage the allocator reuses (caches of
+  // constant-bank uploads are keyed by it).
+  std::uint64_t const serial = pb::NextSerial();
   pb::HostModel model;
   std::vector<pb::HostTrajectory> trajectories;  // Internal order.
   bool segments_dirty = true;
@@ -162,6 +170,12 @@ struct pb_ephemeris {
   pb::DeviceBuffer<long long> counters;
   pb::PinnedBuffer<double> pinned_times;
   pb::PinnedBuffer<int32_t> pinned_status;
+
+  // Adaptive flow: scheduling keys, execution order, sort storage, queue head.
+  pb::DeviceBuffer<float> adaptive_cost;
+  pb::DeviceBuffer<int> adaptive_order;
+  pb::DeviceBuffer<unsigned char> adaptive_sort_storage;
+  pb::DeviceBuffer<unsigned long long> adaptive_queue;
 
   // CUDA-event timing of the dominant kernel of the last flow call.
   std::vector<cudaEvent_t> timing_events;

@@ -127,7 +127,7 @@ pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
   if (n_bodies > kMaxConstantBodies) {
     return Fail(PB_INVALID_ARGUMENT, "too many bodies for the flow kernel");
   }
-  static pb_ephemeris const* uploaded_for = nullptr;
+  static std::uint64_t uploaded_for = 0;
   static int uploaded_hot = -2;
   // Position of the first probe.
   double probe[3] = {0.0, 0.0, 0.0};
@@ -168,7 +168,7 @@ pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
       hot = b;
     }
   }
-  if (uploaded_for == e && uploaded_hot == hot) {
+  if (uploaded_for == e->serial && uploaded_hot == hot) {
     return PB_OK;
   }
   static BodyScalars scalars;
@@ -207,7 +207,7 @@ pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
   PB_CUDA(cudaMemcpyToSymbolAsync(c_hot, &hot_body, sizeof(hot_body), 0,
                                   cudaMemcpyHostToDevice, stream));
   PB_CUDA(cudaStreamSynchronize(stream));
-  uploaded_for = e;
+  uploaded_for = e->serial;
   uploaded_hot = hot;
   return PB_OK;
 }
