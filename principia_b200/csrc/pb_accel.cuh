@@ -50,11 +50,35 @@ PB_HD Vec3 EvaluateSegment(EphemerisView const& e, int const segment,
           EstrinEvaluate<3>(c + 2, degree, x)};
 }
 
-// EvaluateSegment with the Estrin tree of each Newhall degree (3..17,
-// continuous_trajectory_body.hpp:35-37) instantiated at compile time; any other
-// degree takes the run-time tree.  Same operations, same bits.
-PB_HD Vec3 EvaluateSegmentUnrolled(EphemerisView const& e, int const segment,
-                                   double const t) {
+// EvaluateSegment as ONE straight-line tree over blocks of 8 coefficient
+// slots, whatever the degree: compact code for kernels whose lanes evaluate
+// segments of different degrees at once.  It relies on the slots above the
+// degree holding -0.0 (pb_ephemeris_append_segments pads them): the reference's
+// tree (polynomial_evaluators_body.hpp:131-160) carries a lone trailing block up
+// unchanged, and fma(-0.0, x^m, low) == low for every low, signed zeros
+// included, as long as x^m is finite.  Only the leaves need care, because x
+// itself may be negative: a leaf whose odd slot is padding returns its even
+// slot.  Same operations on the real coefficients, same bits.
+PB_HD double EstrinLeaf(double const* const c, int const k, int const degree,
+                        double const x) {
+  double const even = c[3 * k];
+  double const odd = c[3 * (k + 1)];
+  return k + 1 <= degree ? fma(odd, x, even) : even;
+}
+
+PB_HD double EstrinBlock8(double const* const c, int const base,
+                          int const degree, double const x, double const x2,
+                          double const x4) {
+  double const l0 = EstrinLeaf(c, base, degree, x);
+  double const l1 = EstrinLeaf(c, base + 2, degree, x);
+  double const l2 = EstrinLeaf(c, base + 4, degree, x);
+  double const l3 = EstrinLeaf(c, base + 6, degree, x);
+  return fma(fma(l3, x2, l2), x4, fma(l1, x2, l0));
+}
+
+PB_HD Vec3 EvaluateSegmentPadded(EphemerisView const& e, int const segment,
+                                 double const t) {
+  static_assert(kSegmentCoefficients == 18, "two blocks of 8 and one leaf");
   double const x = t - e.segment_origin[segment];
   double const* const c =
       e.segment_coefficients + static_cast<long long>(segment) * 3 *
@@ -62,35 +86,22 @@ PB_HD Vec3 EvaluateSegmentUnrolled(EphemerisView const& e, int const segment,
   int const degree = e.segment_degree[segment];
   double const x2 = x * x;
   double const x4 = x2 * x2;
-  double const x8 = x4 * x4;
-  double const x16 = x8 * x8;
-  switch (degree) {
-#define PB_ESTRIN_CASE(d)                                               \
-  case d:                                                               \
-    return {EstrinFixedNode<3, 0, d>(c, x, x2, x4, x8, x16),            \
-            EstrinFixedNode<3, 0, d>(c + 1, x, x2, x4, x8, x16),        \
-            EstrinFixedNode<3, 0, d>(c + 2, x, x2, x4, x8, x16)};
-    PB_ESTRIN_CASE(3)
-    PB_ESTRIN_CASE(4)
-    PB_ESTRIN_CASE(5)
-    PB_ESTRIN_CASE(6)
-    PB_ESTRIN_CASE(7)
-    PB_ESTRIN_CASE(8)
-    PB_ESTRIN_CASE(9)
-    PB_ESTRIN_CASE(10)
-    PB_ESTRIN_CASE(11)
-    PB_ESTRIN_CASE(12)
-    PB_ESTRIN_CASE(13)
-    PB_ESTRIN_CASE(14)
-    PB_ESTRIN_CASE(15)
-    PB_ESTRIN_CASE(16)
-    PB_ESTRIN_CASE(17)
-#undef PB_ESTRIN_CASE
-    default:
-      return {EstrinEvaluate<3>(c, degree, x),
-              EstrinEvaluate<3>(c + 1, degree, x),
-              EstrinEvaluate<3>(c + 2, degree, x)};
+  Vec3 p{EstrinBlock8(c, 0, degree, x, x2, x4),
+         EstrinBlock8(c + 1, 0, degree, x, x2, x4),
+         EstrinBlock8(c + 2, 0, degree, x, x2, x4)};
+  if (degree >= 8) {
+    double const x8 = x4 * x4;
+    p.x = fma(EstrinBlock8(c, 8, degree, x, x2, x4), x8, p.x);
+    p.y = fma(EstrinBlock8(c + 1, 8, degree, x, x2, x4), x8, p.y);
+    p.z = fma(EstrinBlock8(c + 2, 8, degree, x, x2, x4), x8, p.z);
+    if (degree >= 16) {
+      double const x16 = x8 * x8;
+      p.x = fma(EstrinLeaf(c, 16, degree, x), x16, p.x);
+      p.y = fma(EstrinLeaf(c + 1, 16, degree, x), x16, p.y);
+      p.z = fma(EstrinLeaf(c + 2, 16, degree, x), x16, p.z);
+    }
   }
+  return p;
 }
 
 // Fills one stage-table entry for body b at time t.

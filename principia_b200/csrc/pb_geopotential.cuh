@@ -171,19 +171,23 @@ PB_HD void InitializeSetup(DeviceBody const& body, Vec3 const& x_hat,
 // ===========================================================================
 // Generic path: run-time loops.
 
+// kSize = largest degree + 1: the thread-local arrays are sized for it, so that
+// a kernel whose bodies have small models (degree <= 10) keeps a small frame.
+template<int kSize>
 struct GenericPrecomputations {
-  double R_over_r[kGeopotentialSize];
-  double cos_m_lambda[kGeopotentialSize];
-  double sin_m_lambda[kGeopotentialSize];
-  double cos_beta_to_the_m[kGeopotentialSize];
+  double R_over_r[kSize];
+  double cos_m_lambda[kSize];
+  double sin_m_lambda[kSize];
+  double cos_beta_to_the_m[kSize];
   // Rolling rows n, n-1, n-2 of DmPn_of_sin_beta.
-  double P[3][kGeopotentialSize + 1];
+  double P[3][kSize + 1];
 };
 
 // DegreeNOrderM::UpdatePrecomputations, geopotential_body.hpp:249-331.
+template<int kSize>
 PB_HD void GenericUpdateOrder(int const n, int const m, double const sin_beta,
                               double const one_over_n,
-                              GenericPrecomputations& p) {
+                              GenericPrecomputations<kSize>& p) {
   double* const Pn = p.P[n % 3];
   double const* const Pn1 = p.P[(n + 2) % 3];
   double const* const Pn2 = p.P[(n + 1) % 3];
@@ -293,10 +297,11 @@ PB_HD double OrderTermPotential(int const m, double const Pnm,
   return -normalization_factor * sigma_R * B * L;
 }
 
+template<int kSize>
 PB_HD Vec3 GenericTerm(GeopotentialBody const& g, int const n, int const m,
                        double const sigma_R_over_r, Vec3 const& grad_sigma_R,
                        GeopotentialSetup const& s,
-                       GenericPrecomputations const& p) {
+                       GenericPrecomputations<kSize> const& p) {
   double const* const Pn = p.P[n % 3];
   int const k = n * (n + 1) / 2 + m;
   return OrderTermAcceleration(
@@ -306,10 +311,11 @@ PB_HD Vec3 GenericTerm(GeopotentialBody const& g, int const n, int const m,
       g.normalization[k], sigma_R_over_r, grad_sigma_R, s);
 }
 
+template<int kSize>
 PB_HD double GenericTermPotential(GeopotentialBody const& g, int const n,
                                   int const m, double const sigma_R_over_r,
                                   GeopotentialSetup const& s,
-                                  GenericPrecomputations const& p) {
+                                  GenericPrecomputations<kSize> const& p) {
   double const* const Pn = p.P[n % 3];
   int const k = n * (n + 1) / 2 + m;
   return OrderTermPotential(m, Pn[m], p.cos_m_lambda[m], p.sin_m_lambda[m],
@@ -317,8 +323,9 @@ PB_HD double GenericTermPotential(GeopotentialBody const& g, int const n,
                             g.normalization[k], sigma_R_over_r, s.r_norm);
 }
 
+template<int kSize>
 PB_HD void GenericInitialize(GeopotentialSetup const& s,
-                             GenericPrecomputations& p) {
+                             GenericPrecomputations<kSize>& p) {
   p.R_over_r[1] = s.R1_over_r;
   p.cos_m_lambda[1] = s.cos_lambda;
   p.sin_m_lambda[1] = s.sin_lambda;
@@ -342,12 +349,13 @@ PB_HD void GenericUpdateDegree(int const n, double const r2, double* R_over_r) {
 }
 
 // AllDegrees::Acceleration, :501-536, for max_degree >= 2.
+template<int kSize = kGeopotentialSize>
 PB_HD_NOINLINE Vec3 GeopotentialGenericAcceleration(
     GeopotentialBody const& g, int const max_degree, bool const is_zonal,
     GeopotentialSetup const& s) {
-  GenericPrecomputations p;
+  GenericPrecomputations<kSize> p;
   GenericInitialize(s, p);
-  Vec3 degree_sum[kGeopotentialSize];
+  Vec3 degree_sum[kSize];
   for (int n = 2; n <= max_degree; ++n) {
     int const size = is_zonal ? 1 : n + 1;
     double const one_over_n = 1.0 / n;
@@ -399,7 +407,7 @@ PB_HD_NOINLINE Vec3 GeopotentialGenericAcceleration(
 PB_HD_NOINLINE double GeopotentialGenericPotential(
     GeopotentialBody const& g, int const max_degree, bool const is_zonal,
     GeopotentialSetup const& s) {
-  GenericPrecomputations p;
+  GenericPrecomputations<kGeopotentialSize> p;
   GenericInitialize(s, p);
   double degree_sum[kGeopotentialSize];
   for (int n = 2; n <= max_degree; ++n) {
@@ -785,7 +793,45 @@ PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
       }
     }
   }
-  return GeopotentialGenericAcceleration(g, max_degree, is_zonal, s);
+  return GeopotentialGenericAcceleration<>(g, max_degree, is_zonal, s);
+}
+
+// GeneralSphericalHarmonicsAcceleration for kernels whose warps evaluate many
+// different (body, degree) combinations at once (the adaptive flow): run-time
+// loops only, a few kB of code that stay in the instruction cache, where the
+// unrolled path has one large straight-line body per degree.  The lanes of a
+// warp walk the (n, m) loops together and drop out at their own max_degree.
+// Surface-frame axes from the time.
+PB_HD Vec3 GeneralSphericalHarmonicsAccelerationRolled(
+    GeopotentialBody const& g, double const t, Vec3 const& r,
+    double const r_norm, double const r2, double const one_over_r3) {
+  if (r_norm != r_norm) {
+    double const nan = r_norm;
+    Vec3 const zero{0.0, 0.0, 0.0};
+    return nan * zero;
+  }
+  DeviceBody const& body = *g.body;
+  int const max_degree =
+      LimitingDegree(g.degree_damping, body.n_damping, r_norm) - 1;
+  if (max_degree == 1) {
+    return {0.0, 0.0, 0.0};
+  }
+  bool const is_zonal =
+      body.is_zonal || r_norm > body.sectoral.outer_threshold;
+  Vec3 x_hat, y_hat;
+  if (is_zonal) {
+    x_hat = body.equatorial;
+    y_hat = body.biequatorial;
+  } else {
+    SurfaceFrameAxes(body, t, x_hat, y_hat);
+  }
+  GeopotentialSetup s;
+  InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
+  if (max_degree <= kMaxUnrolledDegree) {
+    return GeopotentialGenericAcceleration<kMaxUnrolledDegree + 1>(
+        g, max_degree, is_zonal, s);
+  }
+  return GeopotentialGenericAcceleration<>(g, max_degree, is_zonal, s);
 }
 
 // Geopotential::GeneralSphericalHarmonicsPotential, :822-895.

@@ -89,6 +89,11 @@ __device__ __noinline__ int32_t SlowAccelerationAtTime(EphemerisView const& e,
   return AccelerationOnMasslessBodyAtTime<false>(e, t, q, acceleration, hint);
 }
 
+// The code of the right-hand side is kept SMALL (run-time loops, one tree for
+// all polynomial degrees): the lanes of the resident warps sit at different
+// bodies, degrees and step-control branches, and a multi-hundred-kB unrolled
+// body (the fixed-step kernel's choice, where all warps run the same code)
+// measured 80 % of the issue slots lost to instruction fetch here.
 __device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
                                                int const b1, double const t,
                                                Vec3 const& dq,
@@ -96,15 +101,15 @@ __device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
                                                double const dq2,
                                                double const one_over_dq3) {
   GeopotentialBody const g = MakeGeopotentialBody(e, b1);
-  FrameSource const frame{nullptr, t};
-  return GeneralSphericalHarmonicsAcceleration<true>(g, frame, -dq, dq_norm,
-                                                     dq2, one_over_dq3);
+  return GeneralSphericalHarmonicsAccelerationRolled(g, t, -dq, dq_norm, dq2,
+                                                     one_over_dq3);
 }
 
-// AccelerationOnMasslessBodyAtTime with the Estrin trees in registers, the
+// AccelerationOnMasslessBodyAtTime with the padded Estrin tree, the
 // branch-free square root and division (pb_math.cuh) and the early exit for
 // oblate bodies beyond their degree-2 outer threshold: the same arithmetic,
-// body by body in the same order.
+// body by body in the same order.  `hint` is the index of the segment of the
+// previous evaluation (relative to the body's first segment).
 __device__ __forceinline__ int32_t FastAccelerationAtTime(
     EphemerisView const& e, double const t, Vec3 const& q, Vec3& acceleration,
     int& hint) {
@@ -113,18 +118,29 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
   bool in_range = true;
   int const n_bodies = e.n_bodies;
   int const n_oblate = e.n_oblate;
+  bool const uniform = e.uniform_segments != 0;
+  if (uniform) {
+    // One lookup for all bodies: first segment with t <= t_max
+    // (continuous_trajectory_body.hpp:860-885).
+    int const end = __ldg(e.segment_offset + 1);
+    if (!(hint < end && t <= __ldg(e.segment_t_max + hint) &&
+          (hint == 0 || __ldg(e.segment_t_max + hint - 1) < t))) {
+      hint = FindSegment(e.segment_t_max, 0, end, t);
+    }
+  }
 #pragma unroll 1
   for (int b1 = 0; b1 < n_bodies; ++b1) {
     int const begin = __ldg(e.segment_offset + b1);
-    int const end = __ldg(e.segment_offset + b1 + 1);
     int segment = begin + hint;
-    // First segment with t <= t_max (continuous_trajectory_body.hpp:860-885).
-    if (!(segment < end && t <= __ldg(e.segment_t_max + segment) &&
-          (segment == begin || __ldg(e.segment_t_max + segment - 1) < t))) {
-      segment = FindSegment(e.segment_t_max, begin, end, t);
-      hint = segment - begin;
+    if (!uniform) {
+      int const end = __ldg(e.segment_offset + b1 + 1);
+      if (!(segment < end && t <= __ldg(e.segment_t_max + segment) &&
+            (segment == begin || __ldg(e.segment_t_max + segment - 1) < t))) {
+        segment = FindSegment(e.segment_t_max, begin, end, t);
+        hint = segment - begin;
+      }
     }
-    Vec3 const position1 = EvaluateSegmentUnrolled(e, segment, t);
+    Vec3 const position1 = EvaluateSegmentPadded(e, segment, t);
     double const mu1 = c_adaptive_bodies.mu[b1];
     double const dx = position1.x - q.x;
     double const dy = position1.y - q.y;

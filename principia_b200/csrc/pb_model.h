@@ -52,6 +52,8 @@ struct EphemerisView {
   int32_t n_oblate;
   int32_t n_frames;  // Oblate, non-zonal bodies.
   int32_t stage_stride;  // Doubles per time in a stage table.
+  // 1 if all bodies have the same segment boundaries (t_max arrays).
+  int32_t uniform_segments;
   DeviceBody const* bodies;
   Damping const* dampings;
   double const* cos;  // Normalised, (n, m) -> n(n+1)/2 + m per body.

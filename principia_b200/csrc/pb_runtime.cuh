@@ -154,6 +154,7 @@ struct pb_ephemeris {
   pb::HostModel model;
   std::vector<pb::HostTrajectory> trajectories;  // Internal order.
   bool segments_dirty = true;
+  bool uniform_segments = false;  // Set by UploadSegments.
 
   pb::DeviceBuffer<pb::DeviceBody> bodies;
   pb::DeviceBuffer<pb::Damping> dampings;
@@ -204,6 +205,7 @@ struct pb_ephemeris {
     v.n_oblate = model.n_oblate;
     v.n_frames = model.n_frames;
     v.stage_stride = pb::StageStride(v.n_bodies, v.n_frames);
+    v.uniform_segments = uniform_segments ? 1 : 0;
     v.bodies = bodies.data;
     v.dampings = dampings.data;
     v.cos = cos.data;

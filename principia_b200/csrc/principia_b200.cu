@@ -41,6 +41,14 @@ pb_status_t UploadSegments(pb_ephemeris* e, cudaStream_t stream) {
                         tr.coefficients.end());
   }
   offset[n] = static_cast<int32_t>(t_max.size());
+  // Bodies appended in lock step (Ephemeris::Prolong) share their segment
+  // boundaries; kernels then look a time up once for all bodies.
+  e->uniform_segments = n > 0;
+  for (int b = 1; b < n; ++b) {
+    if (e->trajectories[b].t_max != e->trajectories[0].t_max) {
+      e->uniform_segments = false;
+    }
+  }
   // The copies below are from pageable memory and therefore synchronous with
   // respect to the host, so the temporaries may die at the end of this scope.
   PB_RETURN_IF_ERROR(e->segment_offset.Upload(offset, stream));
@@ -423,6 +431,14 @@ pb_status_t pb_ephemeris_append_segments(pb_ephemeris_t* e, int32_t body,
     tr.coefficients.insert(tr.coefficients.end(),
                            coefficients + 3 * kSegmentCoefficients * s,
                            coefficients + 3 * kSegmentCoefficients * (s + 1));
+    // The slots above the degree are padding: -0.0, the neutral element that
+    // EvaluateSegmentPadded relies on (pb_accel.cuh).
+    double* const slots =
+        tr.coefficients.data() + tr.coefficients.size() -
+        3 * kSegmentCoefficients;
+    for (int k = 3 * (degree[s] + 1); k < 3 * kSegmentCoefficients; ++k) {
+      slots[k] = -0.0;
+    }
   }
   e->segments_dirty = true;
   return PB_OK;

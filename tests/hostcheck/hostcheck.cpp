@@ -27,6 +27,21 @@ double hc_estrin(double const* c, int32_t degree, double x) {
 }
 double hc_pow_int(double x, int32_t k) { return PowInt(x, k); }
 
+// One segment [18][3] of the given degree, evaluated by the run-time tree and by
+// the padded tree (whose slots above the degree must hold -0.0).
+void hc_estrin_padded(double const* c, int32_t degree, double origin, double t,
+                      double* reference, double* padded) {
+  EphemerisView view{};
+  int32_t segment_degree = degree;
+  view.segment_origin = &origin;
+  view.segment_degree = &segment_degree;
+  view.segment_coefficients = c;
+  Vec3 const a = EvaluateSegment(view, 0, t);
+  Vec3 const b = EvaluateSegmentPadded(view, 0, t);
+  reference[0] = a.x; reference[1] = a.y; reference[2] = a.z;
+  padded[0] = b.x; padded[1] = b.y; padded[2] = b.z;
+}
+
 int32_t hc_model_create(int32_t n, pb_body_t const* bodies, double tolerance,
                         hc_model** out) {
   auto* m = new hc_model;
@@ -93,10 +108,15 @@ int32_t hc_geopotential_acceleration(hc_model const* m, int32_t body, double t,
   double const r_norm = sqrt(r2);
   double const one_over_r3 = r_norm / (r2 * r2);
   Vec3 const a =
-      unrolled ? GeneralSphericalHarmonicsAcceleration<true>(
-                     g, FrameSource{frame, 0.0}, rv, r_norm, r2, one_over_r3)
-               : GeneralSphericalHarmonicsAcceleration<false>(
-                     g, FrameSource{nullptr, t}, rv, r_norm, r2, one_over_r3);
+      unrolled == 2
+          ? GeneralSphericalHarmonicsAccelerationRolled(g, t, rv, r_norm, r2,
+                                                        one_over_r3)
+          : unrolled
+                ? GeneralSphericalHarmonicsAcceleration<true>(
+                      g, FrameSource{frame, 0.0}, rv, r_norm, r2, one_over_r3)
+                : GeneralSphericalHarmonicsAcceleration<false>(
+                      g, FrameSource{nullptr, t}, rv, r_norm, r2,
+                      one_over_r3);
   out[0] = a.x; out[1] = a.y; out[2] = a.z;
   return PB_OK;
 }

@@ -35,6 +35,7 @@ def hc():
   lib.hc_cr_root4.argtypes = [_d]
   lib.hc_estrin.restype = _d
   lib.hc_estrin.argtypes = [_dp, _i32, _d]
+  lib.hc_estrin_padded.argtypes = [_dp, _i32, _d, _d, _dp, _dp]
   lib.hc_pow_int.restype = _d
   lib.hc_pow_int.argtypes = [_d, _i32]
   lib.hc_model_create.argtypes = [_i32, ctypes.POINTER(_capi.Body), _d,
@@ -99,6 +100,30 @@ def test_estrin_matches_oracle(hc):
     assert hc.hc_pow_int(x, k) == peasant(x, k)
 
 
+def test_padded_estrin_tree_equals_the_reference_tree(hc):
+  """EvaluateSegmentPadded (one tree for all degrees, -0.0 padding) against
+  the run-time tree, bit for bit: every degree, both signs of x, zero and
+  negative-zero coefficients."""
+  rng = np.random.default_rng(11)
+  reference = np.zeros(3)
+  padded = np.zeros(3)
+  for degree in range(0, 18):
+    for trial in range(300):
+      c = rng.normal(size=(18, 3)) * 10.0**rng.uniform(-8, 8, (18, 3))
+      if trial % 3 == 1:
+        # Exact zeros of both signs among the coefficients.
+        mask = rng.random((18, 3)) < 0.5
+        c[mask] = rng.choice([0.0, -0.0], size=int(mask.sum()))
+      if trial % 3 == 2:
+        c[:] = rng.choice([0.0, -0.0], size=(18, 3))
+      c[degree + 1:, :] = -0.0
+      origin = rng.uniform(-1e6, 1e6)
+      t = origin + rng.choice([-1.0, 1.0, 0.0]) * rng.uniform(0, 3000)
+      hc.hc_estrin_padded(oracle_lib.dptr(c), degree, origin, t,
+                          oracle_lib.dptr(reference), oracle_lib.dptr(padded))
+      assert reference.tobytes() == padded.tobytes(), (degree, trial)
+
+
 def test_model_order_and_dampings_match_oracle(hc):
   system = SolarSystem.from_fixture('sol_jd2451545')
   oracle = OracleEphemeris(system)
@@ -123,7 +148,7 @@ def test_model_order_and_dampings_match_oracle(hc):
   hc.hc_model_destroy(handle)
 
 
-@pytest.mark.parametrize('unrolled', [0, 1])
+@pytest.mark.parametrize('unrolled', [0, 1, 2])
 def test_geopotential_matches_oracle_bitwise(hc, unrolled):
   system = SolarSystem.from_fixture('sol_jd2451545')
   oracle = OracleEphemeris(system)
