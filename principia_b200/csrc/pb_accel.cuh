@@ -46,8 +46,9 @@ PB_HD Vec3 EvaluateSegment(EphemerisView const& e, int const segment,
       e.segment_coefficients + static_cast<long long>(segment) * 3 *
                                    kSegmentCoefficients;
   int const degree = e.segment_degree[segment];
-  return {EstrinEvaluate<3>(c, degree, x), EstrinEvaluate<3>(c + 1, degree, x),
-          EstrinEvaluate<3>(c + 2, degree, x)};
+  return {EstrinEvaluate<1>(c, degree, x),
+          EstrinEvaluate<1>(c + kSegmentCoefficients, degree, x),
+          EstrinEvaluate<1>(c + 2 * kSegmentCoefficients, degree, x)};
 }
 
 // EvaluateSegment as ONE straight-line tree over blocks of 8 coefficient
@@ -61,8 +62,15 @@ PB_HD Vec3 EvaluateSegment(EphemerisView const& e, int const segment,
 // slot.  Same operations on the real coefficients, same bits.
 PB_HD double EstrinLeaf(double const* const c, int const k, int const degree,
                         double const x) {
-  double const even = c[3 * k];
-  double const odd = c[3 * (k + 1)];
+  // Slots k (even) and k + 1 of one coordinate: one 16-byte load.
+#if defined(__CUDA_ARCH__)
+  double2 const pair = __ldg(reinterpret_cast<double2 const*>(c + k));
+  double const even = pair.x;
+  double const odd = pair.y;
+#else
+  double const even = c[k];
+  double const odd = c[k + 1];
+#endif
   return k + 1 <= degree ? fma(odd, x, even) : even;
 }
 
@@ -80,25 +88,27 @@ PB_HD Vec3 EvaluateSegmentPadded(EphemerisView const& e, int const segment,
                                  double const t) {
   static_assert(kSegmentCoefficients == 18, "two blocks of 8 and one leaf");
   double const x = t - e.segment_origin[segment];
-  double const* const c =
+  double const* const cx =
       e.segment_coefficients + static_cast<long long>(segment) * 3 *
                                    kSegmentCoefficients;
+  double const* const cy = cx + kSegmentCoefficients;
+  double const* const cz = cy + kSegmentCoefficients;
   int const degree = e.segment_degree[segment];
   double const x2 = x * x;
   double const x4 = x2 * x2;
-  Vec3 p{EstrinBlock8(c, 0, degree, x, x2, x4),
-         EstrinBlock8(c + 1, 0, degree, x, x2, x4),
-         EstrinBlock8(c + 2, 0, degree, x, x2, x4)};
+  Vec3 p{EstrinBlock8(cx, 0, degree, x, x2, x4),
+         EstrinBlock8(cy, 0, degree, x, x2, x4),
+         EstrinBlock8(cz, 0, degree, x, x2, x4)};
   if (degree >= 8) {
     double const x8 = x4 * x4;
-    p.x = fma(EstrinBlock8(c, 8, degree, x, x2, x4), x8, p.x);
-    p.y = fma(EstrinBlock8(c + 1, 8, degree, x, x2, x4), x8, p.y);
-    p.z = fma(EstrinBlock8(c + 2, 8, degree, x, x2, x4), x8, p.z);
+    p.x = fma(EstrinBlock8(cx, 8, degree, x, x2, x4), x8, p.x);
+    p.y = fma(EstrinBlock8(cy, 8, degree, x, x2, x4), x8, p.y);
+    p.z = fma(EstrinBlock8(cz, 8, degree, x, x2, x4), x8, p.z);
     if (degree >= 16) {
       double const x16 = x8 * x8;
-      p.x = fma(EstrinLeaf(c, 16, degree, x), x16, p.x);
-      p.y = fma(EstrinLeaf(c + 1, 16, degree, x), x16, p.y);
-      p.z = fma(EstrinLeaf(c + 2, 16, degree, x), x16, p.z);
+      p.x = fma(EstrinLeaf(cx, 16, degree, x), x16, p.x);
+      p.y = fma(EstrinLeaf(cy, 16, degree, x), x16, p.y);
+      p.z = fma(EstrinLeaf(cz, 16, degree, x), x16, p.z);
     }
   }
   return p;

@@ -796,6 +796,160 @@ PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
   return GeopotentialGenericAcceleration<>(g, max_degree, is_zonal, s);
 }
 
+// AllDegrees::Acceleration with run-time loops, tuned for instruction count:
+// the same operations as GeopotentialGenericAcceleration (and therefore the
+// same bits), with the special orders (m = 0, n - 2, n - 1, n) peeled off the
+// loops, rotating row pointers instead of n % 3, and running table indices.
+// RN(1 / n) for DivideBySmallInteger.
+template<int kSize>
+PB_HD_NOINLINE Vec3 GeopotentialRolledAcceleration(
+    GeopotentialBody const& g, int const max_degree, bool const is_zonal,
+    GeopotentialSetup const& s) {
+  double R_over_r_[kSize];
+  double cos_m_lambda[kSize];
+  double sin_m_lambda[kSize];
+  double cos_beta_to_the_m[kSize];
+  double rows[3][kSize + 1];
+  Vec3 degree_sum[kSize];
+  R_over_r_[1] = s.R1_over_r;
+  cos_m_lambda[1] = s.cos_lambda;
+  sin_m_lambda[1] = s.sin_lambda;
+  cos_beta_to_the_m[0] = 1;
+  cos_beta_to_the_m[1] = s.cos_beta;
+  double* Pn2 = rows[0];
+  double* Pn1 = rows[1];
+  double* Pn = rows[2];
+  Pn2[0] = 1;           // DmPn(0, 0).
+  Pn1[0] = s.sin_beta;  // DmPn(1, 0).
+  Pn1[1] = 1;           // DmPn(1, 1).
+  double const sin_beta = s.sin_beta;
+  // Index of (n, 0) in the triangular tables.
+  int row = 3;
+  for (int n = 2; n <= max_degree; ++n) {
+    double const one_over_n = 1.0 / n;
+    {
+      int const h1 = n / 2;
+      int const h2 = n - h1;
+      R_over_r_[n] = R_over_r_[h1] * R_over_r_[h2] * s.r2;
+    }
+    double const R_over_r = R_over_r_[n];
+    double const R_prime = -(n + 1) * R_over_r;
+    double const* const cos_n = g.cos + row;
+    double const* const sin_n = g.sin + row;
+    double const* const normalization_n = g.normalization + row;
+    double sigma_R_over_r;
+    Vec3 grad_sigma_R;
+    // One term; `m`'s relation to 0 and n is known at each call site.
+    auto const term = [&](int const m, double const Pnm1,
+                          double const cos_beta_to_the_m_minus_1) {
+      return OrderTermAcceleration(
+          n, m, Pn[m], Pnm1, cos_m_lambda[m], sin_m_lambda[m],
+          cos_beta_to_the_m[m], cos_beta_to_the_m_minus_1, cos_n[m], sin_n[m],
+          normalization_n[m], sigma_R_over_r, grad_sigma_R, s);
+    };
+    // m = 0 of DegreeNOrderM::UpdatePrecomputations: DmPn(n, 0), DmPn(n, 1).
+    Pn[0] = DivideBySmallInteger(
+        (2 * n - 1) * sin_beta * Pn1[0] - (n - 1) * Pn2[0], n, one_over_n);
+    if (n == 2) {
+      Pn[1] = DivideBySmallInteger(
+          (2 * n - 1) * (sin_beta * Pn1[1] + 1 * Pn1[0]), n, one_over_n);
+    } else {
+      Pn[1] = DivideBySmallInteger(
+          (2 * n - 1) * (sin_beta * Pn1[1] + 1 * Pn1[0]) - (n - 1) * Pn2[1], n,
+          one_over_n);
+    }
+    if (is_zonal) {
+      ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+                                    s.r_normalized, R_over_r, R_prime,
+                                    sigma_R_over_r, grad_sigma_R);
+      degree_sum[n] = OrderTermAcceleration(
+          n, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0, cos_n[0], sin_n[0],
+          normalization_n[0], sigma_R_over_r, grad_sigma_R, s);
+    } else {
+      // Orders 1 .. n - 3 (general recurrence), n - 2, n - 1.
+      for (int m = 1; m <= n - 3; ++m) {
+        Pn[m + 1] = DivideBySmallInteger(
+            (2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m]) -
+                (n - 1) * Pn2[m + 1],
+            n, one_over_n);
+      }
+      if (n >= 3) {
+        int const m = n - 2;
+        Pn[m + 1] = DivideBySmallInteger(
+            (2 * n - 1) * (sin_beta * Pn1[m + 1] + (m + 1) * Pn1[m]), n,
+            one_over_n);
+      }
+      if (n == 2) {
+        Pn[2] = 3;
+      } else {
+        int const m = n - 1;
+        Pn[m + 1] = DivideBySmallInteger((2 * n - 1) * (m + 1) * Pn1[m], n,
+                                         one_over_n);
+      }
+      // m = n: cos nλ, sin nλ, cos^n β from the halves.
+      {
+        int const h1 = n / 2;
+        int const h2 = n - h1;
+        double const cos_h1 = cos_m_lambda[h1];
+        double const sin_h1 = sin_m_lambda[h1];
+        double const cos_beta_to_the_h1 = cos_beta_to_the_m[h1];
+        if (h1 == h2) {
+          sin_m_lambda[n] = 2 * sin_h1 * cos_h1;
+          cos_m_lambda[n] = (cos_h1 + sin_h1) * (cos_h1 - sin_h1);
+          cos_beta_to_the_m[n] = cos_beta_to_the_h1 * cos_beta_to_the_h1;
+        } else {
+          double const cos_h2 = cos_m_lambda[h2];
+          double const sin_h2 = sin_m_lambda[h2];
+          double const cos_beta_to_the_h2 = cos_beta_to_the_m[h2];
+          sin_m_lambda[n] = sin_h1 * cos_h2 + cos_h1 * sin_h2;
+          cos_m_lambda[n] = cos_h1 * cos_h2 - sin_h1 * sin_h2;
+          cos_beta_to_the_m[n] = cos_beta_to_the_h1 * cos_beta_to_the_h2;
+        }
+      }
+      if (n == 2) {
+        ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
+                                      s.r_normalized, R_over_r, R_prime,
+                                      sigma_R_over_r, grad_sigma_R);
+        Vec3 const j2_acceleration = OrderTermAcceleration(
+            2, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0, cos_n[0], sin_n[0],
+            normalization_n[0], sigma_R_over_r, grad_sigma_R, s);
+        ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2,
+                                      s.r_normalized, R_over_r, R_prime,
+                                      sigma_R_over_r, grad_sigma_R);
+        Vec3 const c22_s22_acceleration = term(2, 0.0, cos_beta_to_the_m[1]);
+        degree_sum[n] = j2_acceleration + c22_s22_acceleration;
+      } else {
+        ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+                                      s.r_normalized, R_over_r, R_prime,
+                                      sigma_R_over_r, grad_sigma_R);
+        Vec3 sum = term(n, 0.0, cos_beta_to_the_m[n - 1]);
+        for (int m = n - 1; m >= 1; --m) {
+          sum = term(m, Pn[m + 1], cos_beta_to_the_m[m - 1]) + sum;
+        }
+        sum = OrderTermAcceleration(n, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0,
+                                    cos_n[0], sin_n[0], normalization_n[0],
+                                    sigma_R_over_r, grad_sigma_R, s) +
+              sum;
+        degree_sum[n] = sum;
+      }
+    }
+    row += n + 1;
+    double* const recycled = Pn2;
+    Pn2 = Pn1;
+    Pn1 = Pn;
+    Pn = recycled;
+  }
+  // Degrees 0 and 1 contribute zero vectors to the fold.
+  Vec3 sum = degree_sum[max_degree];
+  for (int n = max_degree - 1; n >= 2; --n) {
+    sum = degree_sum[n] + sum;
+  }
+  Vec3 const zero{0.0, 0.0, 0.0};
+  sum = zero + sum;
+  sum = zero + sum;
+  return sum;
+}
+
 // GeneralSphericalHarmonicsAcceleration for kernels whose warps evaluate many
 // different (body, degree) combinations at once (the adaptive flow): run-time
 // loops only, a few kB of code that stay in the instruction cache, where the
@@ -828,10 +982,11 @@ PB_HD Vec3 GeneralSphericalHarmonicsAccelerationRolled(
   GeopotentialSetup s;
   InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
   if (max_degree <= kMaxUnrolledDegree) {
-    return GeopotentialGenericAcceleration<kMaxUnrolledDegree + 1>(
+    return GeopotentialRolledAcceleration<kMaxUnrolledDegree + 1>(
         g, max_degree, is_zonal, s);
   }
-  return GeopotentialGenericAcceleration<>(g, max_degree, is_zonal, s);
+  return GeopotentialRolledAcceleration<kGeopotentialSize>(g, max_degree,
+                                                           is_zonal, s);
 }
 
 // Geopotential::GeneralSphericalHarmonicsPotential, :822-895.

@@ -66,7 +66,9 @@ struct EphemerisView {
   double const* segment_t_max;
   double const* segment_origin;
   int32_t const* segment_degree;
-  double const* segment_coefficients;  // [segment][18][3].
+  // [segment][xyz][18]: the host API's [segment][18][3] transposed, so that the
+  // coefficients of one coordinate are contiguous (16-byte loads of pairs).
+  double const* segment_coefficients;
 };
 
 // Layout of one entry of a stage table (all bodies evaluated at one time):

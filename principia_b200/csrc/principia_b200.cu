@@ -37,8 +37,21 @@ pb_status_t UploadSegments(pb_ephemeris* e, cudaStream_t stream) {
     t_max.insert(t_max.end(), tr.t_max.begin(), tr.t_max.end());
     origin.insert(origin.end(), tr.origin.begin(), tr.origin.end());
     degree.insert(degree.end(), tr.degree.begin(), tr.degree.end());
-    coefficients.insert(coefficients.end(), tr.coefficients.begin(),
-                        tr.coefficients.end());
+    // Host [segment][18][3] -> device [segment][3][18].
+    std::size_t const n_segments = tr.t_max.size();
+    std::size_t const base = coefficients.size();
+    coefficients.resize(base + n_segments * 3 * kSegmentCoefficients);
+    for (std::size_t segment = 0; segment < n_segments; ++segment) {
+      double const* const in =
+          tr.coefficients.data() + segment * 3 * kSegmentCoefficients;
+      double* const out =
+          coefficients.data() + base + segment * 3 * kSegmentCoefficients;
+      for (int k = 0; k < kSegmentCoefficients; ++k) {
+        for (int c = 0; c < 3; ++c) {
+          out[c * kSegmentCoefficients + k] = in[3 * k + c];
+        }
+      }
+    }
   }
   offset[n] = static_cast<int32_t>(t_max.size());
   // Bodies appended in lock step (Ephemeris::Prolong) share their segment

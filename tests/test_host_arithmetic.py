@@ -119,6 +119,8 @@ def test_padded_estrin_tree_equals_the_reference_tree(hc):
       c[degree + 1:, :] = -0.0
       origin = rng.uniform(-1e6, 1e6)
       t = origin + rng.choice([-1.0, 1.0, 0.0]) * rng.uniform(0, 3000)
+      # The device layout is [xyz][18].
+      c = np.ascontiguousarray(c.T)
       hc.hc_estrin_padded(oracle_lib.dptr(c), degree, origin, t,
                           oracle_lib.dptr(reference), oracle_lib.dptr(padded))
       assert reference.tobytes() == padded.tobytes(), (degree, trial)
