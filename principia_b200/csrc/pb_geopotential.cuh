@@ -982,6 +982,10 @@ PB_HD Vec3 GeneralSphericalHarmonicsAccelerationRolled(
   GeopotentialSetup s;
   InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
   if (max_degree <= kMaxUnrolledDegree) {
+    // (A variant with the degrees rolled and the orders unrolled, per-order
+    // state in registers, was measured 5 % slower here and 50 % slower than
+    // the fully unrolled body in the fixed-step kernel: its 19 kB loop body
+    // misses the instruction cache next to the rest of the kernel.)
     return GeopotentialRolledAcceleration<kMaxUnrolledDegree + 1>(
         g, max_degree, is_zonal, s);
   }

@@ -56,8 +56,12 @@ def main():
       line = int(row[0])
     except ValueError:
       continue
-    samples, inst, thread_inst = int(row[6] or 0), int(row[7] or 0), int(
-        row[8] or 0)
+    def number(text):
+      try:
+        return int(text)
+      except ValueError:
+        return 0
+    samples, inst, thread_inst = number(row[6]), number(row[7]), number(row[8])
     lines[(current, line)] = (samples, inst, thread_inst, row[1].strip()[:72])
     total_samples += samples
     total_inst += inst
