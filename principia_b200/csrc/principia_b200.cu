@@ -263,6 +263,24 @@ int SrknMinBlocks() {
   return value;
 }
 
+// Shape of the flow kernel: 0 = 128 threads x SrknMinBlocks() blocks per SM;
+// 1 = the same with a barrier per stage; 2 = 384 threads x 1 block with the
+// barrier; 3 = 384 x 1 without.  Measured on 10^5 probes: 56.2, 55.5, 53.5,
+// 52.4 ms per 100 steps, so a launch that fills every SM with a 384-thread
+// block takes shape 3, a smaller one shape 0 (more, smaller blocks).
+// PB_SRKN_VARIANT overrides the choice.
+int SrknVariant(long long const n_probes, int const sm_count) {
+  static int const forced = [] {
+    char const* const text = std::getenv("PB_SRKN_VARIANT");
+    int const v = text != nullptr ? std::atoi(text) : -1;
+    return v >= 0 && v <= 3 ? v : -1;
+  }();
+  if (forced >= 0) {
+    return forced;
+  }
+  return n_probes >= 384LL * sm_count ? 3 : 0;
+}
+
 bool MakeSrknTableau(int32_t method, SrknTableau& t) {
   std::memset(&t, 0, sizeof(t));
   if (method == PB_BLANES_MOAN_2002_SRKN_14A) {
@@ -689,7 +707,12 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
       // launches of 10^5 probes leave 12 % of the SM slots idle in their last
       // wave (782 CTAs on 444 slots); short launches from several streams keep
       // the slots full, and no kernel ever waits on another one.
-      long long const blocks = (flow->n + kFlowThreads - 1) / kFlowThreads;
+      int sm_count = 0;
+      PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
+                                     e->device));
+      int const variant = SrknVariant(flow->n, sm_count);
+      int const threads = variant >= 2 ? 384 : kFlowThreads;
+      long long const blocks = (flow->n + threads - 1) / threads;
       int const groups = static_cast<int>(
           std::min<long long>(FlowGroups(), std::max<long long>(1, blocks / 64)));
       int const sub_steps = groups > 1 ? FlowSubSteps() : steps;
@@ -710,25 +733,38 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
         if (groups > 1) {
           PB_CUDA(cudaStreamWaitEvent(helper, fork, 0));
         }
-        long long const i_begin = blocks * g / groups * kFlowThreads;
+        long long const i_begin = blocks * g / groups * threads;
         long long const i_end = std::min<long long>(
-            flow->n, blocks * (g + 1) / groups * kFlowThreads);
+            flow->n, blocks * (g + 1) / groups * threads);
         unsigned const grid = static_cast<unsigned>(
-            (i_end - i_begin + kFlowThreads - 1) / kFlowThreads);
+            (i_end - i_begin + threads - 1) / threads);
         for (int s0 = 0; s0 < steps; s0 += sub_steps) {
           int const n_sub = std::min(sub_steps, steps - s0);
           double const* const table =
               e->stage_table.data +
               static_cast<std::size_t>(s0) * evaluations * view.stage_stride;
-#define PB_LAUNCH_SRKN(kMinBlocks)                                            \
-  SrknFlowKernel<true, kMinBlocks><<<grid, kFlowThreads, 0, helper>>>(        \
+#define PB_LAUNCH_SRKN(kThreads, kMinBlocks, kSync)                           \
+  SrknFlowKernel<kThreads, kMinBlocks, kSync><<<grid, kThreads, 0, helper>>>( \
       view, tableau, h, table, n_sub, flow->n, i_begin, i_end, flow->state,   \
       steps_done + s0, every, flow->max_samples, flow->samples,               \
       e->status_word.data)
-          switch (SrknMinBlocks()) {
-            case 2: PB_LAUNCH_SRKN(2); break;
-            case 4: PB_LAUNCH_SRKN(4); break;
-            default: PB_LAUNCH_SRKN(3); break;
+          switch (variant) {
+            case 1:
+              switch (SrknMinBlocks()) {
+                case 2: PB_LAUNCH_SRKN(128, 2, true); break;
+                case 4: PB_LAUNCH_SRKN(128, 4, true); break;
+                default: PB_LAUNCH_SRKN(128, 3, true); break;
+              }
+              break;
+            case 2: PB_LAUNCH_SRKN(384, 1, true); break;
+            case 3: PB_LAUNCH_SRKN(384, 1, false); break;
+            default:
+              switch (SrknMinBlocks()) {
+                case 2: PB_LAUNCH_SRKN(128, 2, false); break;
+                case 4: PB_LAUNCH_SRKN(128, 4, false); break;
+                default: PB_LAUNCH_SRKN(128, 3, false); break;
+              }
+              break;
           }
 #undef PB_LAUNCH_SRKN
           PB_LAUNCHED();
