@@ -85,9 +85,25 @@ struct pb_nbody_ensemble {
 
 namespace {
 
-unsigned EnsembleGrid(long long const n_systems) {
-  return static_cast<unsigned>((n_systems + kEnsembleThreads - 1) /
-                               kEnsembleThreads);
+// Launch geometry of the ensemble kernels (pb_kernels_nbody.cuh): 32 systems
+// per block, one warp per body (or per two bodies).
+struct EnsembleLaunch {
+  unsigned grid;
+  unsigned block;
+  std::size_t shared_bytes;
+  int own;
+};
+
+EnsembleLaunch MakeEnsembleLaunch(pb_nbody_ensemble const* s) {
+  EnsembleShape const shape = MakeEnsembleShape(s->n_bodies);
+  EnsembleLaunch launch;
+  launch.grid = static_cast<unsigned>((s->n_systems + kEnsembleLanes - 1) /
+                                      kEnsembleLanes);
+  launch.block = static_cast<unsigned>(shape.warps * kEnsembleLanes);
+  launch.shared_bytes = static_cast<std::size_t>(3) * s->n_bodies *
+                        kEnsembleLanes * sizeof(double);
+  launch.own = shape.own;
+  return launch;
 }
 
 // Surface-frame axes at the given times -> ensemble->frames.
@@ -110,18 +126,6 @@ pb_status_t BuildFrames(pb_nbody_ensemble* s, std::vector<double> const& times,
   return PB_OK;
 }
 
-template<typename Launch8, typename LaunchGeneric>
-pb_status_t Dispatch(int const n_bodies, Launch8 launch8,
-                     LaunchGeneric launch_generic) {
-  if (n_bodies == 8) {
-    launch8();
-  } else {
-    launch_generic();
-  }
-  PB_LAUNCHED();
-  return PB_OK;
-}
-
 // One SRKN step of size h from the current time; updates the time.
 pb_status_t SrknStep(pb_nbody_ensemble* s, double const h,
                      cudaStream_t stream) {
@@ -131,17 +135,13 @@ pb_status_t SrknStep(pb_nbody_ensemble* s, double const h,
     times.push_back(s->time.value + (s->time.error + s->nodes[st] * h));
   }
   PB_RETURN_IF_ERROR(BuildFrames(s, times, stream));
-  unsigned const grid = EnsembleGrid(s->n_systems);
-  PB_RETURN_IF_ERROR(Dispatch(
-      s->n_bodies,
-      [&] {
-        EnsembleSrknStepKernel<8><<<grid, kEnsembleThreads, 0, stream>>>(
-            view, s->tableau, h, s->frames.data, s->n_systems, s->state.data);
-      },
-      [&] {
-        EnsembleSrknStepKernel<0><<<grid, kEnsembleThreads, 0, stream>>>(
-            view, s->tableau, h, s->frames.data, s->n_systems, s->state.data);
-      }));
+  EnsembleLaunch const launch = MakeEnsembleLaunch(s);
+  auto const kernel = launch.own == 4       ? EnsembleSrknStepKernel<4, 512>
+                      : launch.block <= 256 ? EnsembleSrknStepKernel<1, 256>
+                                            : EnsembleSrknStepKernel<1, 512>;
+  kernel<<<launch.grid, launch.block, launch.shared_bytes, stream>>>(
+      view, s->tableau, h, s->frames.data, s->n_systems, s->state.data);
+  PB_LAUNCHED();
   Increment(s->time, h);
   return PB_OK;
 }
@@ -151,18 +151,14 @@ pb_status_t FillStep(pb_nbody_ensemble* s, int const slot,
                      cudaStream_t stream) {
   EphemerisView const view = s->ephemeris->View();
   PB_RETURN_IF_ERROR(BuildFrames(s, {s->time.value}, stream));
-  unsigned const grid = EnsembleGrid(s->n_systems);
-  MultistepHistory const history = s->History();
-  return Dispatch(
-      s->n_bodies,
-      [&] {
-        EnsembleFillStepKernel<8><<<grid, kEnsembleThreads, 0, stream>>>(
-            view, s->frames.data, s->n_systems, s->state.data, history, slot);
-      },
-      [&] {
-        EnsembleFillStepKernel<0><<<grid, kEnsembleThreads, 0, stream>>>(
-            view, s->frames.data, s->n_systems, s->state.data, history, slot);
-      });
+  EnsembleLaunch const launch = MakeEnsembleLaunch(s);
+  auto const kernel = launch.own == 4       ? EnsembleFillStepKernel<4, 512>
+                      : launch.block <= 256 ? EnsembleFillStepKernel<1, 256>
+                                            : EnsembleFillStepKernel<1, 512>;
+  kernel<<<launch.grid, launch.block, launch.shared_bytes, stream>>>(
+      view, s->frames.data, s->n_systems, s->state.data, s->History(), slot);
+  PB_LAUNCHED();
+  return PB_OK;
 }
 
 pb_status_t MultistepStep(pb_nbody_ensemble* s, cudaStream_t stream) {
@@ -170,20 +166,19 @@ pb_status_t MultistepStep(pb_nbody_ensemble* s, cudaStream_t stream) {
   DP t = s->time;
   Increment(t, s->step);
   PB_RETURN_IF_ERROR(BuildFrames(s, {t.value}, stream));
-  unsigned const grid = EnsembleGrid(s->n_systems);
-  MultistepHistory const history = s->History();
-  PB_RETURN_IF_ERROR(Dispatch(
-      s->n_bodies,
-      [&] {
-        EnsembleMultistepStepKernel<8><<<grid, kEnsembleThreads, 0, stream>>>(
-            view, s->multistep, s->step, s->frames.data, s->n_systems,
-            s->state.data, history, s->oldest);
-      },
-      [&] {
-        EnsembleMultistepStepKernel<0><<<grid, kEnsembleThreads, 0, stream>>>(
-            view, s->multistep, s->step, s->frames.data, s->n_systems,
-            s->state.data, history, s->oldest);
-      }));
+  EnsembleLaunch const launch = MakeEnsembleLaunch(s);
+  auto const kernel =
+      s->multistep.order == 8
+          ? (launch.own == 4         ? EnsembleMultistepStepKernel<4, 512, 8>
+             : launch.block <= 256   ? EnsembleMultistepStepKernel<1, 256, 8>
+                                     : EnsembleMultistepStepKernel<1, 512, 8>)
+          : (launch.own == 4         ? EnsembleMultistepStepKernel<4, 512, 12>
+             : launch.block <= 256   ? EnsembleMultistepStepKernel<1, 256, 12>
+                                     : EnsembleMultistepStepKernel<1, 512, 12>);
+  kernel<<<launch.grid, launch.block, launch.shared_bytes, stream>>>(
+      view, s->multistep, s->step, s->frames.data, s->n_systems, s->state.data,
+      s->History(), s->oldest);
+  PB_LAUNCHED();
   s->oldest = (s->oldest + 1) % s->multistep.order;
   s->time = t;
   return PB_OK;

@@ -1,5 +1,5 @@
-// Massive-body flows: ensembles of small independent systems (one thread per
-// system, the reference's pair order and third-law updates preserved) and the
+// Massive-body flows: ensembles of small independent systems (a warp per body,
+// a lane per system, the reference's accumulation order preserved) and the
 // large-N all-pairs system (tiled, one thread per target).
 #pragma once
 
@@ -10,32 +10,100 @@
 
 namespace pb {
 
-constexpr int kEnsembleThreads = 64;
 constexpr int kMaxEnsembleBodies = 64;
 constexpr int kMaxMultistepOrder = 12;
 // symmetric_linear_multistep_integrator_body.hpp:20.
 constexpr int kStartupStepDivisor = 16;
 
-// Ephemeris::ComputeGravitationalAccelerationBetweenAllMassiveBodies,
-// physics/ephemeris_body.hpp:1503-1552, for one system held in arrays.
-template<int kBodies>
-__device__ __forceinline__ void AccelerationsBetweenAllMassiveBodies(
-    EphemerisView const& e, double const* const frames, Vec3 const* const q,
-    Vec3* const a) {
-  int const n = kBodies > 0 ? kBodies : e.n_bodies;
-  for (int b = 0; b < n; ++b) {
-    a[b] = {0.0, 0.0, 0.0};
-  }
-  // Not unrolled: one inlined copy of the pair interaction (with its
-  // geopotential code) per kernel.
+// Thread layout of the ensemble kernels: a block integrates 32 systems; warp w
+// owns the bodies w, w + W, ... (W warps) of all of them and lane l is system
+// l of the block.  The positions of a stage are exchanged through shared
+// memory, [body][xyz][lane].  Within a warp the body is uniform, so the
+// branches on oblateness and pair order are uniform and every load of the
+// [plane][body][system] arrays is one contiguous 256-byte line.
+//
+// Every thread evaluates ALL the interactions of its body (each unordered pair
+// is computed by both of its bodies, from the same operands, hence with the
+// same bits) and accumulates them in the order in which the reference updates
+// that body: Ephemeris::ComputeGravitationalAccelerationBetweenAllMassiveBodies
+// (physics/ephemeris_body.hpp:1503-1552) visits the pairs b1 < b2 in
+// lexicographic order, so body b sees j = 0, 1, ... b - 1 (as b2), then
+// b + 1, ... (as b1), and within a pair the point-mass term, the harmonics of
+// b1, the harmonics of b2 (:1342-1410).  Twice the arithmetic of the
+// third-law formulation, no scatter, n times the parallelism.
+constexpr int kEnsembleLanes = 32;
+// Bodies per warp: 1 up to 16 bodies, 4 up to kMaxEnsembleBodies, so that a
+// block has at most 16 warps; the kernels are compiled for 8 warps (255
+// registers: the TRAPPIST-1 shape) and for 16.
+
+struct EnsembleShape {
+  int warps;  // W.
+  int own;    // Bodies per warp.
+};
+
+inline EnsembleShape MakeEnsembleShape(int const n_bodies) {
+  EnsembleShape shape;
+  shape.own = n_bodies <= 16 ? 1 : 4;
+  shape.warps = (n_bodies + shape.own - 1) / shape.own;
+  return shape;
+}
+
+// Acceleration on body b of this lane's system.
+static __device__ __noinline__ Vec3 AccelerationOnBodyOfSystem(
+    EphemerisView const& e, double const* const frames,
+    double const* const positions, int const b, int const lane) {
+  int const n = e.n_bodies;
+  DeviceBody const& body_b = e.bodies[b];
+  Vec3 const q_b{positions[(3 * b + 0) * kEnsembleLanes + lane],
+                 positions[(3 * b + 1) * kEnsembleLanes + lane],
+                 positions[(3 * b + 2) * kEnsembleLanes + lane]};
+  Vec3 a{0.0, 0.0, 0.0};
 #pragma unroll 1
-  for (int b1 = 0; b1 < n; ++b1) {
+  for (int j = 0; j < n; ++j) {
+    if (j == b) {
+      continue;
+    }
+    DeviceBody const& body_j = e.bodies[j];
+    Vec3 const q_j{positions[(3 * j + 0) * kEnsembleLanes + lane],
+                   positions[(3 * j + 1) * kEnsembleLanes + lane],
+                   positions[(3 * j + 2) * kEnsembleLanes + lane]};
+    // The pair is (b1, b2) = (j, b) if j < b, (b, j) otherwise.
+    bool const b_is_b2 = j < b;
+    Vec3 const dq = b_is_b2 ? q_j - q_b : q_b - q_j;  // q_b1 - q_b2.
+    double const dq2 = Norm2(dq);
+    double const dq_norm = sqrt(dq2);
+    double const one_over_dq3 = dq_norm / (dq2 * dq2);
+    double const mu_j = body_j.mu;
+    // a2 += dq * (mu1 / dq^3); a1 -= dq * (mu2 / dq^3): for body b the other
+    // body's mu either way.
+    double const mu_j_over_dq3 = mu_j * one_over_dq3;
+    Vec3 const point_mass = dq * mu_j_over_dq3;
+    a = b_is_b2 ? a + point_mass : a - point_mass;
+    // Harmonics of b1, then of b2.
 #pragma unroll 1
-    for (int b2 = b1 + 1; b2 < n; ++b2) {
-      MassivePairInteraction<true>(e, b1, b2, frames, q[b1], q[b2], a[b1],
-                                   a[b2]);
+    for (int which = 0; which < 2; ++which) {
+      bool const source_is_b = (which == 0) != b_is_b2;
+      int const source = source_is_b ? b : j;
+      DeviceBody const& source_body = source_is_b ? body_b : body_j;
+      if (!source_body.is_oblate) {
+        continue;
+      }
+      GeopotentialBody const g = MakeGeopotentialBody(e, source);
+      FrameSource const frame{source_body.frame_slot >= 0
+                                  ? frames + 6 * source_body.frame_slot
+                                  : nullptr,
+                              0.0};
+      // b1's field at b2: r = -dq; b2's field at b1: r = dq.
+      Vec3 const effect = GeneralSphericalHarmonicsAcceleration<true, 3>(
+          g, frame, which == 0 ? -dq : dq, dq_norm, dq2, one_over_dq3);
+      // b1 oblate: a1 -= mu2 effect, a2 += mu1 effect;
+      // b2 oblate: a1 += mu2 effect, a2 -= mu1 effect.
+      Vec3 const scaled = mu_j * effect;
+      bool const subtract = (which == 0) != b_is_b2;
+      a = subtract ? a - scaled : a + scaled;
     }
   }
+  return a;
 }
 
 // Index into an ensemble plane set: [plane][body][system].
@@ -51,71 +119,101 @@ __device__ __forceinline__ long long EnsembleIndex(int const plane,
 // (symplectic_runge_kutta_nyström_integrator_body.hpp:97-135) for every
 // system; the ODE::State (12 planes) is advanced in place.  `frames` holds the
 // surface-frame axes at each evaluation time of the step (6 n_frames doubles
-// per evaluation).
-template<int kBodies>
-__global__ void __launch_bounds__(kEnsembleThreads)
-EnsembleSrknStepKernel(EphemerisView const e, SrknTableau const tableau,
-                       double const h, double const* __restrict__ frames,
-                       long long const n_systems, double* __restrict__ state) {
-  long long const s =
-      static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (s >= n_systems) {
-    return;
-  }
-  constexpr int kCapacity = kBodies > 0 ? kBodies : kMaxEnsembleBodies;
-  int const n = kBodies > 0 ? kBodies : e.n_bodies;
-  Vec3 dq[kCapacity], dv[kCapacity], q_stage[kCapacity], g[kCapacity];
-  auto value = [&](int const plane, int const b) {
-    return state[EnsembleIndex(plane, b, n, n_systems, s)];
-  };
-  for (int b = 0; b < n; ++b) {
-    dq[b] = {0.0, 0.0, 0.0};
-    dv[b] = {0.0, 0.0, 0.0};
-  }
-  if (tableau.first_stage == 1) {
-    double const ha = h * tableau.a[0];
-    for (int b = 0; b < n; ++b) {
-      dq[b].x += ha * (value(6, b) + dv[b].x);
-      dq[b].y += ha * (value(7, b) + dv[b].y);
-      dq[b].z += ha * (value(8, b) + dv[b].z);
+// per evaluation).  Dynamic shared memory: 3 n_bodies kEnsembleLanes doubles.
+template<int kOwn, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads)
+EnsembleSrknStepKernel(EphemerisView const e,
+                                       SrknTableau const tableau,
+                                       double const h,
+                                       double const* __restrict__ frames,
+                                       long long const n_systems,
+                                       double* __restrict__ state) {
+  extern __shared__ double positions[];
+  int const lane = threadIdx.x % kEnsembleLanes;
+  int const warp = threadIdx.x / kEnsembleLanes;
+  int const warps = blockDim.x / kEnsembleLanes;
+  int const n = e.n_bodies;
+  long long const system =
+      static_cast<long long>(blockIdx.x) * kEnsembleLanes + lane;
+  bool const active = system < n_systems;
+  // A lane beyond the end shadows the last system and stores nothing.
+  long long const s = active ? system : n_systems - 1;
+  Vec3 q[kOwn], v[kOwn], dq[kOwn], dv[kOwn];
+#pragma unroll
+  for (int o = 0; o < kOwn; ++o) {
+    int const b = warp + o * warps;
+    dq[o] = {0.0, 0.0, 0.0};
+    dv[o] = {0.0, 0.0, 0.0};
+    if (b < n) {
+      q[o] = {state[EnsembleIndex(0, b, n, n_systems, s)],
+              state[EnsembleIndex(1, b, n, n_systems, s)],
+              state[EnsembleIndex(2, b, n, n_systems, s)]};
+      v[o] = {state[EnsembleIndex(6, b, n, n_systems, s)],
+              state[EnsembleIndex(7, b, n, n_systems, s)],
+              state[EnsembleIndex(8, b, n, n_systems, s)]};
+      if (tableau.first_stage == 1) {
+        double const ha = h * tableau.a[0];
+        dq[o].x += ha * (v[o].x + dv[o].x);
+        dq[o].y += ha * (v[o].y + dv[o].y);
+        dq[o].z += ha * (v[o].z + dv[o].z);
+      }
     }
   }
   int const frame_stride = 6 * e.n_frames;
   for (int st = tableau.first_stage; st < tableau.stages; ++st) {
-    for (int b = 0; b < n; ++b) {
-      q_stage[b] = {value(0, b) + dq[b].x, value(1, b) + dq[b].y,
-                    value(2, b) + dq[b].z};
+#pragma unroll
+    for (int o = 0; o < kOwn; ++o) {
+      int const b = warp + o * warps;
+      if (b < n) {
+        positions[(3 * b + 0) * kEnsembleLanes + lane] = q[o].x + dq[o].x;
+        positions[(3 * b + 1) * kEnsembleLanes + lane] = q[o].y + dq[o].y;
+        positions[(3 * b + 2) * kEnsembleLanes + lane] = q[o].z + dq[o].z;
+      }
     }
-    AccelerationsBetweenAllMassiveBodies<kBodies>(
-        e, frames + (st - tableau.first_stage) * frame_stride, q_stage, g);
+    __syncthreads();
     double const hb = h * tableau.b[st];
     double const ha = h * tableau.a[st];
-    for (int b = 0; b < n; ++b) {
-      dv[b].x += hb * g[b].x;
-      dv[b].y += hb * g[b].y;
-      dv[b].z += hb * g[b].z;
-      dq[b].x += ha * (value(6, b) + dv[b].x);
-      dq[b].y += ha * (value(7, b) + dv[b].y);
-      dq[b].z += ha * (value(8, b) + dv[b].z);
-    }
-  }
-  for (int b = 0; b < n; ++b) {
-    double const increments[6] = {dq[b].x, dq[b].y, dq[b].z,
-                                  dv[b].x, dv[b].y, dv[b].z};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      long long const qi = EnsembleIndex(c, b, n, n_systems, s);
-      long long const qe = EnsembleIndex(3 + c, b, n, n_systems, s);
-      DP qd{state[qi], state[qe]};
-      Increment(qd, increments[c]);
-      state[qi] = qd.value;
-      state[qe] = qd.error;
-      long long const vi = EnsembleIndex(6 + c, b, n, n_systems, s);
-      long long const ve = EnsembleIndex(9 + c, b, n, n_systems, s);
-      DP vd{state[vi], state[ve]};
-      Increment(vd, increments[3 + c]);
-      state[vi] = vd.value;
-      state[ve] = vd.error;
+    for (int o = 0; o < kOwn; ++o) {
+      int const b = warp + o * warps;
+      if (b < n) {
+        Vec3 const g = AccelerationOnBodyOfSystem(
+            e, frames + (st - tableau.first_stage) * frame_stride, positions, b,
+            lane);
+        dv[o].x += hb * g.x;
+        dv[o].y += hb * g.y;
+        dv[o].z += hb * g.z;
+        dq[o].x += ha * (v[o].x + dv[o].x);
+        dq[o].y += ha * (v[o].y + dv[o].y);
+        dq[o].z += ha * (v[o].z + dv[o].z);
+      }
+    }
+    __syncthreads();
+  }
+  if (!active) {
+    return;
+  }
+#pragma unroll
+  for (int o = 0; o < kOwn; ++o) {
+    int const b = warp + o * warps;
+    if (b < n) {
+      double const increments[6] = {dq[o].x, dq[o].y, dq[o].z,
+                                    dv[o].x, dv[o].y, dv[o].z};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        long long const qi = EnsembleIndex(c, b, n, n_systems, s);
+        long long const qe = EnsembleIndex(3 + c, b, n, n_systems, s);
+        DP qd{state[qi], state[qe]};
+        Increment(qd, increments[c]);
+        state[qi] = qd.value;
+        state[qe] = qd.error;
+        long long const vi = EnsembleIndex(6 + c, b, n, n_systems, s);
+        long long const ve = EnsembleIndex(9 + c, b, n, n_systems, s);
+        DP vd{state[vi], state[ve]};
+        Increment(vd, increments[3 + c]);
+        state[vi] = vd.value;
+        state[ve] = vd.error;
+      }
     }
   }
 }
@@ -143,40 +241,53 @@ __device__ __forceinline__ long long HistoryIndex(int const slot,
 // Starter::FillStepFromState, symmetric_linear_multistep_integrator_body.hpp:
 // 246-263: displacement = position - DoublePrecision<Position>() (a
 // renormalisation), acceleration = RHS at the state's positions.
-template<int kBodies>
-__global__ void __launch_bounds__(kEnsembleThreads)
+template<int kOwn, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads)
 EnsembleFillStepKernel(EphemerisView const e,
-                       double const* __restrict__ frames,
-                       long long const n_systems,
-                       double const* __restrict__ state,
-                       MultistepHistory const history, int const slot) {
-  long long const s =
-      static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (s >= n_systems) {
-    return;
-  }
-  constexpr int kCapacity = kBodies > 0 ? kBodies : kMaxEnsembleBodies;
-  int const n = kBodies > 0 ? kBodies : e.n_bodies;
-  Vec3 q[kCapacity], a[kCapacity];
-  for (int b = 0; b < n; ++b) {
-    double position[3];
+                                       double const* __restrict__ frames,
+                                       long long const n_systems,
+                                       double const* __restrict__ state,
+                                       MultistepHistory const history,
+                                       int const slot) {
+  extern __shared__ double positions[];
+  int const lane = threadIdx.x % kEnsembleLanes;
+  int const warp = threadIdx.x / kEnsembleLanes;
+  int const warps = blockDim.x / kEnsembleLanes;
+  int const n = e.n_bodies;
+  long long const system =
+      static_cast<long long>(blockIdx.x) * kEnsembleLanes + lane;
+  bool const active = system < n_systems;
+  long long const s = active ? system : n_systems - 1;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      DP const p{state[EnsembleIndex(c, b, n, n_systems, s)],
-                 state[EnsembleIndex(3 + c, b, n, n_systems, s)]};
-      DP const displacement = Subtract(p, DP{0.0, 0.0});
-      long long const hi = HistoryIndex(slot, c, b, n, n_systems, s);
-      history.displacement_value[hi] = displacement.value;
-      history.displacement_error[hi] = displacement.error;
-      position[c] = p.value;
+  for (int o = 0; o < kOwn; ++o) {
+    int const b = warp + o * warps;
+    if (b < n) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        DP const p{state[EnsembleIndex(c, b, n, n_systems, s)],
+                   state[EnsembleIndex(3 + c, b, n, n_systems, s)]};
+        DP const displacement = Subtract(p, DP{0.0, 0.0});
+        if (active) {
+          long long const hi = HistoryIndex(slot, c, b, n, n_systems, s);
+          history.displacement_value[hi] = displacement.value;
+          history.displacement_error[hi] = displacement.error;
+        }
+        positions[(3 * b + c) * kEnsembleLanes + lane] = p.value;
+      }
     }
-    q[b] = {position[0], position[1], position[2]};
   }
-  AccelerationsBetweenAllMassiveBodies<kBodies>(e, frames, q, a);
-  for (int b = 0; b < n; ++b) {
-    history.acceleration[HistoryIndex(slot, 0, b, n, n_systems, s)] = a[b].x;
-    history.acceleration[HistoryIndex(slot, 1, b, n, n_systems, s)] = a[b].y;
-    history.acceleration[HistoryIndex(slot, 2, b, n, n_systems, s)] = a[b].z;
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < kOwn; ++o) {
+    int const b = warp + o * warps;
+    if (b < n) {
+      Vec3 const a = AccelerationOnBodyOfSystem(e, frames, positions, b, lane);
+      if (active) {
+        history.acceleration[HistoryIndex(slot, 0, b, n, n_systems, s)] = a.x;
+        history.acceleration[HistoryIndex(slot, 1, b, n, n_systems, s)] = a.y;
+        history.acceleration[HistoryIndex(slot, 2, b, n, n_systems, s)] = a.z;
+      }
+    }
   }
 }
 
@@ -194,94 +305,113 @@ struct MultistepMethod {
 // One step of SymmetricLinearMultistepIntegrator::Instance::Solve,
 // symmetric_linear_multistep_integrator_body.hpp:69-149, with the velocity of
 // ComputeVelocityUsingCohenHubbardOesterwinter (:281-321).  `oldest` is the
-// ring slot of previous_steps.front(); the new step overwrites it.
-template<int kBodies>
-__global__ void __launch_bounds__(kEnsembleThreads)
-EnsembleMultistepStepKernel(EphemerisView const e, MultistepMethod const method,
-                            double const h, double const* __restrict__ frames,
-                            long long const n_systems,
-                            double* __restrict__ state,
-                            MultistepHistory const history, int const oldest) {
-  long long const s =
-      static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (s >= n_systems) {
-    return;
-  }
-  constexpr int kCapacity = kBodies > 0 ? kBodies : kMaxEnsembleBodies;
-  int const n = kBodies > 0 ? kBodies : e.n_bodies;
-  int const k = method.order;
-  auto slot_of = [&](int const j) { return (oldest + j) % k; };
-  Vec3 positions[kCapacity], accelerations[kCapacity];
-  // The new displacements are kept until the old slot may be overwritten.
-  DP new_displacement[3 * kCapacity];
-  for (int b = 0; b < n; ++b) {
-    double position[3];
+// ring slot of previous_steps.front(); the new step overwrites it.  kOrder is
+// method.order (loops over the history unrolled, its loads issued together).
+template<int kOwn, int kMaxThreads, int kOrder>
+__global__ void __launch_bounds__(kMaxThreads)
+EnsembleMultistepStepKernel(
+    EphemerisView const e, MultistepMethod const method, double const h,
+    double const* __restrict__ frames, long long const n_systems,
+    double* __restrict__ state, MultistepHistory const history,
+    int const oldest) {
+  extern __shared__ double positions[];
+  int const lane = threadIdx.x % kEnsembleLanes;
+  int const warp = threadIdx.x / kEnsembleLanes;
+  int const warps = blockDim.x / kEnsembleLanes;
+  int const n = e.n_bodies;
+  long long const system =
+      static_cast<long long>(blockIdx.x) * kEnsembleLanes + lane;
+  bool const active = system < n_systems;
+  long long const s = active ? system : n_systems - 1;
+  constexpr int k = kOrder;
+  auto slot_of = [&](int const j) {
+    int const slot = oldest + j;
+    return slot >= k ? slot - k : slot;
+  };
+  // The new displacements are kept until the old slot may be overwritten; the
+  // accelerations of the history feed both the position and the velocity.
+  DP new_displacement[kOwn][3];
+  double old_acceleration[kOwn][3][k];
+  DP previous_displacement[kOwn][3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      auto displacement = [&](int const j) {
-        long long const hi = HistoryIndex(slot_of(j), c, b, n, n_systems, s);
-        return DP{history.displacement_value[hi], history.displacement_error[hi]};
-      };
-      auto acceleration = [&](int const j) {
-        return history.acceleration[HistoryIndex(slot_of(j), c, b, n,
-                                                 n_systems, s)];
-      };
-      // j = 0.
-      DP sum = Scale(-method.alpha[0], displacement(0));
-      double weighted = method.beta_numerator[0] * acceleration(0);
-      // Generic j paired with k - j.
-      for (int j = 1; j < k / 2; ++j) {
-        sum = Subtract(sum, Scale(method.alpha[j], displacement(j)));
-        sum = Subtract(sum, Scale(method.alpha[j], displacement(k - j)));
-        weighted += method.beta_numerator[j] *
-                    (acceleration(j) + acceleration(k - j));
+  for (int o = 0; o < kOwn; ++o) {
+    int const b = warp + o * warps;
+    if (b < n) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        DP displacement[k];
+#pragma unroll
+        for (int j = 0; j < k; ++j) {
+          long long const hi = HistoryIndex(slot_of(j), c, b, n, n_systems, s);
+          displacement[j] = {history.displacement_value[hi],
+                             history.displacement_error[hi]};
+          old_acceleration[o][c][j] = history.acceleration[hi];
+        }
+        previous_displacement[o][c] = displacement[k - 1];
+        double const* const acceleration = old_acceleration[o][c];
+        // j = 0.
+        DP sum = Scale(-method.alpha[0], displacement[0]);
+        double weighted = method.beta_numerator[0] * acceleration[0];
+        // Generic j paired with k - j.
+#pragma unroll
+        for (int j = 1; j < k / 2; ++j) {
+          sum = Subtract(sum, Scale(method.alpha[j], displacement[j]));
+          sum = Subtract(sum, Scale(method.alpha[j], displacement[k - j]));
+          weighted += method.beta_numerator[j] *
+                      (acceleration[j] + acceleration[k - j]);
+        }
+        // j = k / 2.
+        sum = Subtract(sum, Scale(method.alpha[k / 2], displacement[k / 2]));
+        weighted += method.beta_numerator[k / 2] * acceleration[k / 2];
+        Increment(sum, h * h * weighted / method.beta_denominator);
+        new_displacement[o][c] = sum;
+        DP const current_position = Add(DP{0.0, 0.0}, sum);
+        positions[(3 * b + c) * kEnsembleLanes + lane] =
+            current_position.value;
+        if (active) {
+          state[EnsembleIndex(c, b, n, n_systems, s)] = current_position.value;
+          state[EnsembleIndex(3 + c, b, n, n_systems, s)] =
+              current_position.error;
+        }
       }
-      // j = k / 2.
-      sum = Subtract(sum, Scale(method.alpha[k / 2], displacement(k / 2)));
-      weighted += method.beta_numerator[k / 2] * acceleration(k / 2);
-      Increment(sum, h * h * weighted / method.beta_denominator);
-      new_displacement[3 * b + c] = sum;
-      DP const current_position = Add(DP{0.0, 0.0}, sum);
-      position[c] = current_position.value;
-      state[EnsembleIndex(c, b, n, n_systems, s)] = current_position.value;
-      state[EnsembleIndex(3 + c, b, n, n_systems, s)] = current_position.error;
     }
-    positions[b] = {position[0], position[1], position[2]};
   }
-  AccelerationsBetweenAllMassiveBodies<kBodies>(e, frames, positions,
-                                                accelerations);
+  __syncthreads();
   // Push: the new step replaces the oldest one and becomes previous_steps.back.
   int const newest = oldest;
-  int const previous = (oldest + k - 1) % k;
-  for (int b = 0; b < n; ++b) {
-    double const a[3] = {accelerations[b].x, accelerations[b].y,
-                         accelerations[b].z};
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      long long const hi = HistoryIndex(newest, c, b, n, n_systems, s);
-      DP const displacement = new_displacement[3 * b + c];
-      history.displacement_value[hi] = displacement.value;
-      history.displacement_error[hi] = displacement.error;
-      history.acceleration[hi] = a[c];
-      // Velocity.
-      long long const pi = HistoryIndex(previous, c, b, n, n_systems, s);
-      DP const displacement_change = Subtract(
-          displacement,
-          DP{history.displacement_value[pi], history.displacement_error[pi]});
-      double velocity =
-          (displacement_change.value + displacement_change.error) / h;
-      double weighted_accelerations = 0.0;
-      for (int i = 0; i < k; ++i) {
-        // it = previous_steps.rbegin() + i: the newest step first.
-        int const slot = (newest + k - i) % k;
-        double const ai = i == 0 ? a[c]
-                                 : history.acceleration[HistoryIndex(
-                                       slot, c, b, n, n_systems, s)];
-        weighted_accelerations += method.cho_numerators[i] * ai;
+  for (int o = 0; o < kOwn; ++o) {
+    int const b = warp + o * warps;
+    if (b < n) {
+      Vec3 const acceleration =
+          AccelerationOnBodyOfSystem(e, frames, positions, b, lane);
+      double const a[3] = {acceleration.x, acceleration.y, acceleration.z};
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          long long const hi = HistoryIndex(newest, c, b, n, n_systems, s);
+          DP const displacement = new_displacement[o][c];
+          history.displacement_value[hi] = displacement.value;
+          history.displacement_error[hi] = displacement.error;
+          history.acceleration[hi] = a[c];
+          // Velocity; previous_steps.back() before the push is j = k - 1.
+          DP const displacement_change =
+              Subtract(displacement, previous_displacement[o][c]);
+          double velocity =
+              (displacement_change.value + displacement_change.error) / h;
+          double weighted_accelerations = 0.0;
+#pragma unroll
+          for (int i = 0; i < k; ++i) {
+            // it = previous_steps.rbegin() + i: the newest step first, then
+            // the old steps j = k - 1, k - 2, ... 1 (j = 0 was overwritten).
+            double const ai = i == 0 ? a[c] : old_acceleration[o][c][k - i];
+            weighted_accelerations += method.cho_numerators[i] * ai;
+          }
+          velocity += weighted_accelerations * h / method.cho_denominator;
+          state[EnsembleIndex(6 + c, b, n, n_systems, s)] = velocity;
+          state[EnsembleIndex(9 + c, b, n, n_systems, s)] = 0.0;
+        }
       }
-      velocity += weighted_accelerations * h / method.cho_denominator;
-      state[EnsembleIndex(6 + c, b, n, n_systems, s)] = velocity;
-      state[EnsembleIndex(9 + c, b, n, n_systems, s)] = 0.0;
     }
   }
 }
