@@ -33,8 +33,10 @@ constexpr int kStartupStepDivisor = 16;
 // third-law formulation, no scatter, n times the parallelism.
 constexpr int kEnsembleLanes = 32;
 // Bodies per warp: 1 up to 16 bodies, 4 up to kMaxEnsembleBodies, so that a
-// block has at most 16 warps; the kernels are compiled for 8 warps (255
-// registers: the TRAPPIST-1 shape) and for 16.
+// block has at most 16 warps; the kernels are compiled for 8 warps (the
+// TRAPPIST-1 shape) and for 16.  (ptxas settles on 128 registers, two blocks of
+// 8 warps per SM; forcing one block with up to 255 registers was measured 1.6x
+// slower on the SRKN startup and no faster on the multistep step.)
 
 struct EnsembleShape {
   int warps;  // W.
@@ -48,7 +50,9 @@ inline EnsembleShape MakeEnsembleShape(int const n_bodies) {
   return shape;
 }
 
-// Acceleration on body b of this lane's system.
+// Acceleration on body b of this lane's system.  A template so that every
+// kernel shape gets a copy compiled for its own register budget.
+template<int kMaxThreads>
 static __device__ __noinline__ Vec3 AccelerationOnBodyOfSystem(
     EphemerisView const& e, double const* const frames,
     double const* const positions, int const b, int const lane) {
@@ -177,7 +181,7 @@ EnsembleSrknStepKernel(EphemerisView const e,
     for (int o = 0; o < kOwn; ++o) {
       int const b = warp + o * warps;
       if (b < n) {
-        Vec3 const g = AccelerationOnBodyOfSystem(
+        Vec3 const g = AccelerationOnBodyOfSystem<kMaxThreads>(
             e, frames + (st - tableau.first_stage) * frame_stride, positions, b,
             lane);
         dv[o].x += hb * g.x;
@@ -281,7 +285,8 @@ EnsembleFillStepKernel(EphemerisView const e,
   for (int o = 0; o < kOwn; ++o) {
     int const b = warp + o * warps;
     if (b < n) {
-      Vec3 const a = AccelerationOnBodyOfSystem(e, frames, positions, b, lane);
+      Vec3 const a = AccelerationOnBodyOfSystem<kMaxThreads>(e, frames,
+                                                             positions, b, lane);
       if (active) {
         history.acceleration[HistoryIndex(slot, 0, b, n, n_systems, s)] = a.x;
         history.acceleration[HistoryIndex(slot, 1, b, n, n_systems, s)] = a.y;
@@ -383,8 +388,8 @@ EnsembleMultistepStepKernel(
   for (int o = 0; o < kOwn; ++o) {
     int const b = warp + o * warps;
     if (b < n) {
-      Vec3 const acceleration =
-          AccelerationOnBodyOfSystem(e, frames, positions, b, lane);
+      Vec3 const acceleration = AccelerationOnBodyOfSystem<kMaxThreads>(
+          e, frames, positions, b, lane);
       double const a[3] = {acceleration.x, acceleration.y, acceleration.z};
       if (active) {
 #pragma unroll
