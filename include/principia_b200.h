@@ -316,6 +316,23 @@ pb_status_t pb_nbody_allpairs_accelerations(pb_nbody_allpairs_t* system,
 /* Milliseconds spent in the last solve's force kernels (CUDA events). */
 double pb_nbody_allpairs_last_force_ms(const pb_nbody_allpairs_t* system);
 
+/* ---- Series in the Чебышёв basis.
+ * PolynomialInЧебышёвBasis<Value, Instant, degree>::operator() and
+ * EvaluateDerivative, numerics/polynomial_in_чебышёв_basis_body.hpp:151-202
+ * (Clenshaw; the representation of pre-Cardano ContinuousTrajectory segments),
+ * batched: series i has `dimension` components, degree[i] <=
+ * PB_MAX_CHEBYSHEV_DEGREE and bounds [lower_bound[i], upper_bound[i]];
+ * coefficients[i][k][c] with PB_MAX_CHEBYSHEV_DEGREE + 1 slots of k.
+ * Evaluation j is of series series_index[j] at arguments[j].  values and
+ * derivatives are [n_evaluations][dimension]; either may be NULL. */
+#define PB_MAX_CHEBYSHEV_DEGREE 20
+pb_status_t pb_chebyshev_series_evaluate(
+    int32_t cuda_device, int64_t n_series, int32_t dimension,
+    const int32_t* degree, const double* lower_bound,
+    const double* upper_bound, const double* coefficients,
+    int64_t n_evaluations, const int32_t* series_index,
+    const double* arguments, double* values, double* derivatives);
+
 /* ---- Measurement helpers. */
 /* Device time (CUDA events on the launching stream) spent in the flow kernels
  * of the last pb_flow_with_*_step[_device] call on this ephemeris, and their

@@ -220,4 +220,61 @@ inline Vec3 Rotate(Quaternion const& q, Vec3 const& v) {
   return v + 2 * Cross(q.imaginary, Cross(q.imaginary, v) + q.real * v);
 }
 
+// PolynomialInЧебышёвBasis::operator() and EvaluateDerivative,
+// numerics/polynomial_in_чебышёв_basis_body.hpp:151-202 (Clenshaw).  The
+// reference stores one_over_width_ = 1 / (upper - lower) at construction
+// (:139-147).  `coefficients` has stride `stride`.
+inline double ЧебышёвEvaluate(double const* coefficients, int stride,
+                               int degree, double lower_bound,
+                               double upper_bound, double argument) {
+  double const width = upper_bound - lower_bound;
+  double const one_over_width = 1 / width;
+  double const scaled_argument =
+      ((argument - upper_bound) + (argument - lower_bound)) * one_over_width;
+  double const two_scaled_argument = scaled_argument + scaled_argument;
+  double const c0 = coefficients[0];
+  switch (degree) {
+    case 0:
+      return c0;
+    case 1:
+      return c0 + scaled_argument * coefficients[stride];
+    default: {
+      double b_k2 = coefficients[degree * stride];
+      double b_k1 =
+          coefficients[(degree - 1) * stride] + two_scaled_argument * b_k2;
+      for (int k = degree - 2; k >= 1; --k) {
+        double const b_k =
+            coefficients[k * stride] + two_scaled_argument * b_k1 - b_k2;
+        b_k2 = b_k1;
+        b_k1 = b_k;
+      }
+      return c0 + scaled_argument * b_k1 - b_k2;
+    }
+  }
+}
+
+inline double ЧебышёвEvaluateDerivative(double const* coefficients, int stride,
+                                         int degree, double lower_bound,
+                                         double upper_bound, double argument) {
+  double const width = upper_bound - lower_bound;
+  double const one_over_width = 1 / width;
+  double const scaled_argument =
+      ((argument - upper_bound) + (argument - lower_bound)) * one_over_width;
+  double const two_scaled_argument = scaled_argument + scaled_argument;
+  double b_k2 = 0;
+  double b_k1 = 0;
+  for (int k = degree - 1; k >= 1; --k) {
+    double const b_k = coefficients[(k + 1) * stride] * (k + 1) +
+                       two_scaled_argument * b_k1 - b_k2;
+    b_k2 = b_k1;
+    b_k1 = b_k;
+  }
+  // Degree 0 has no coefficients_[1]; the reference's template is only
+  // instantiated so for degree >= 1 series in practice, a constant has
+  // derivative 0.
+  double const c1 = degree >= 1 ? coefficients[stride] : 0.0;
+  return (c1 + two_scaled_argument * b_k1 - b_k2) *
+         (one_over_width + one_over_width);
+}
+
 }  // namespace orc

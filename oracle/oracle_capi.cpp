@@ -194,6 +194,20 @@ double orc_estrin(double const* coefficients, int32_t degree, double x) {
   return EstrinEvaluate(coefficients, 1, 0, degree, x);
 }
 
+// Чебышёв series (numerics/polynomial_in_чебышёв_basis_body.hpp:151-202).
+double orc_chebyshev_evaluate(double const* coefficients, int32_t degree,
+                              double lower_bound, double upper_bound,
+                              double argument) {
+  return ЧебышёвEvaluate(coefficients, 1, degree, lower_bound, upper_bound,
+                         argument);
+}
+double orc_chebyshev_evaluate_derivative(double const* coefficients,
+                                         int32_t degree, double lower_bound,
+                                         double upper_bound, double argument) {
+  return ЧебышёвEvaluateDerivative(coefficients, 1, degree, lower_bound,
+                                   upper_bound, argument);
+}
+
 // Newhall fit of 9 equally spaced (q, v) pairs: returns the monomial
 // coefficients (numerics/newhall_body.hpp:259-287) through a one-shot
 // ContinuousTrajectory.

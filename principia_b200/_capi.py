@@ -142,6 +142,9 @@ SYMBOLS = [
      [_vp, c_double_p, c_double_p, c_double_p]),
     ('pb_nbody_allpairs_accelerations', _i32, [_vp, c_double_p]),
     ('pb_nbody_allpairs_last_force_ms', _d, [_vp]),
+    ('pb_chebyshev_series_evaluate', _i32,
+     [_i32, _i64, _i32, c_int32_p, c_double_p, c_double_p, c_double_p, _i64,
+      c_int32_p, c_double_p, c_double_p, c_double_p]),
     ('pb_ephemeris_last_flow_kernel_ms', _d, [_vp, c_int64_p]),
     ('pb_measure_fp64_peak', _i32, [_i32, c_double_p, c_double_p]),
     ('pb_kernel_launch_count', _i64, []),

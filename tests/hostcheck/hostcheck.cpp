@@ -26,6 +26,13 @@ double hc_estrin(double const* c, int32_t degree, double x) {
   return EstrinEvaluate<1>(c, degree, x);
 }
 double hc_pow_int(double x, int32_t k) { return PowInt(x, k); }
+void hc_chebyshev(double const* c, int32_t degree, double lower, double upper,
+                  double t, double* value, double* derivative) {
+  double const one_over_width = 1 / (upper - lower);
+  *value = ChebyshevEvaluate<1>(c, degree, lower, upper, one_over_width, t);
+  *derivative =
+      ChebyshevEvaluateDerivative<1>(c, degree, lower, upper, one_over_width, t);
+}
 
 // One segment [18][3] of the given degree, evaluated by the run-time tree and by
 // the padded tree (whose slots above the degree must hold -0.0).

@@ -36,6 +36,7 @@ def hc():
   lib.hc_estrin.restype = _d
   lib.hc_estrin.argtypes = [_dp, _i32, _d]
   lib.hc_estrin_padded.argtypes = [_dp, _i32, _d, _d, _dp, _dp]
+  lib.hc_chebyshev.argtypes = [_dp, _i32, _d, _d, _d, _dp, _dp]
   lib.hc_pow_int.restype = _d
   lib.hc_pow_int.argtypes = [_d, _i32]
   lib.hc_model_create.argtypes = [_i32, ctypes.POINTER(_capi.Body), _d,
@@ -98,6 +99,24 @@ def test_estrin_matches_oracle(hc):
       y2 = y * y
       return y2 * x if e % 2 else y2
     assert hc.hc_pow_int(x, k) == peasant(x, k)
+
+
+def test_chebyshev_series_match_oracle(hc):
+  orc = oracle_lib.library()
+  rng = np.random.default_rng(5)
+  value, derivative = _d(), _d()
+  for degree in range(0, 21):
+    for _ in range(100):
+      c = rng.normal(size=21) * 10.0**rng.uniform(-3, 3, 21)
+      lower = rng.uniform(-1e6, 1e6)
+      upper = lower + rng.uniform(1.0, 1e5)
+      t = rng.uniform(lower, upper)
+      hc.hc_chebyshev(oracle_lib.dptr(c), degree, lower, upper, t,
+                      ctypes.byref(value), ctypes.byref(derivative))
+      assert value.value == orc.orc_chebyshev_evaluate(
+          oracle_lib.dptr(c), degree, lower, upper, t)
+      assert derivative.value == orc.orc_chebyshev_evaluate_derivative(
+          oracle_lib.dptr(c), degree, lower, upper, t)
 
 
 def test_padded_estrin_tree_equals_the_reference_tree(hc):

@@ -330,6 +330,21 @@ def test_acceleration_on_massive_bodies_with_j2(method):
 
 
 # physics/ephemeris_body.hpp:138-158: oblate bodies front-inserted.
+# numerics/polynomial_in_чебышёв_basis_test.cpp:63-137.
+def test_chebyshev_series_known_answers():
+  from chebyshev_kats import KATS
+  orc = oracle_lib.library()
+  for coefficients, lower, upper, values, derivatives in KATS:
+    c = np.array(coefficients)
+    degree = len(coefficients) - 1
+    for argument, expected in values:
+      assert orc.orc_chebyshev_evaluate(oracle_lib.dptr(c), degree, lower,
+                                        upper, argument) == expected
+    for argument, expected in derivatives:
+      assert orc.orc_chebyshev_evaluate_derivative(
+          oracle_lib.dptr(c), degree, lower, upper, argument) == expected
+
+
 def test_internal_body_order():
   system = SolarSystem.from_fixture('sol_jd2451545')
   ephemeris = OracleEphemeris(system)
