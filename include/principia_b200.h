@@ -180,7 +180,12 @@ pb_status_t pb_compute_gravitational_acceleration_on_massive_bodies(
  * status (PB_OUT_OF_RANGE on collision; integration continues, as in the
  * reference). */
 typedef struct pb_fixed_step_flow_t {
-  int32_t method;       /* PB_BLANES_MOAN_2002_SRKN_14A or PB_MCLACHLAN_... */
+  int32_t method;       /* An SRKN method, or PB_QUINLAN_1999_ORDER_8A /
+                         * PB_QUINLAN_TREMAINE_1990_ORDER_12 (step > 0): the
+                         * instance, with the history it would keep, then
+                         * lives for this call only (the startup runs again
+                         * at the next call); use pb_fixed_step_instance_*
+                         * to keep it. */
   double step;
   double t_final;
   int64_t n;
@@ -200,6 +205,38 @@ pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* ephemeris,
 pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* ephemeris,
                                            const pb_fixed_step_flow_t* flow,
                                            void* stream);
+
+/* ---- Ephemeris::NewInstance (ephemeris.hpp:181-194) + FlowWithFixedStep
+ * (:222-225) with a persistent integrator instance over n massless
+ * trajectories: Integrator<NewtonianMotionEquation>::Instance
+ * (integrators/integrators.hpp:40-94).  The ODE::State lives on the device;
+ * for the symmetric linear multistep methods
+ * (integrators/symmetric_linear_multistep_integrator_body.hpp:22-152; the
+ * plugin's history integrator is Quinlan1999Order8A at 10 s,
+ * ksp_plugin/integrators.cpp:66-72) the instance keeps previous_steps_, is
+ * started by BlanesMoan2002SRKN14A at step / 16 (starter_body.hpp:23-93) and
+ * computes velocities with Cohen-Hubbard-Oesterwinter (:281-321).  `state`
+ * and `time` as in pb_fixed_step_flow_t. */
+typedef struct pb_fixed_step_instance pb_fixed_step_instance_t;
+pb_status_t pb_fixed_step_instance_create(pb_ephemeris_t* ephemeris,
+                                          int32_t method, double step,
+                                          int64_t n, const double* state,
+                                          const double* time,
+                                          pb_fixed_step_instance_t** instance);
+void pb_fixed_step_instance_destroy(pb_fixed_step_instance_t* instance);
+/* FlowWithFixedStep(t_final, instance) = Instance::Solve(t_final).  Every
+ * `sample_every`-th state appended by this call goes to samples[s][6][n]
+ * (host), sample_times[s]; *n_steps = states appended; *flow_status as in
+ * pb_fixed_step_flow_t.  Outs may be NULL. */
+pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* instance,
+                                        double t_final, int64_t sample_every,
+                                        int64_t max_samples, double* samples,
+                                        double* sample_times,
+                                        int64_t* n_steps, int64_t* n_samples,
+                                        pb_status_t* flow_status);
+/* instance.state(): 12 planes of n and the time {value, error}. */
+pb_status_t pb_fixed_step_instance_get_state(
+    pb_fixed_step_instance_t* instance, double* state, double* time);
 
 /* ---- Adaptive massless flow: Ephemeris::FlowWithAdaptiveStep,
  * ephemeris.hpp:201-207, ephemeris_body.hpp:415-444,1624-1717, with

@@ -122,6 +122,13 @@ SYMBOLS = [
     ('pb_flow_with_fixed_step', _i32, [_vp, ctypes.POINTER(FixedStepFlow)]),
     ('pb_flow_with_fixed_step_device', _i32,
      [_vp, ctypes.POINTER(FixedStepFlow), _vp]),
+    ('pb_fixed_step_instance_create', _i32,
+     [_vp, _i32, _d, _i64, c_double_p, c_double_p, ctypes.POINTER(_vp)]),
+    ('pb_fixed_step_instance_destroy', None, [_vp]),
+    ('pb_fixed_step_instance_flow', _i32,
+     [_vp, _d, _i64, _i64, c_double_p, c_double_p, c_int64_p, c_int64_p,
+      c_int32_p]),
+    ('pb_fixed_step_instance_get_state', _i32, [_vp, c_double_p, c_double_p]),
     ('pb_flow_with_adaptive_step', _i32,
      [_vp, ctypes.POINTER(AdaptiveStepFlow)]),
     ('pb_flow_with_adaptive_step_device', _i32,

@@ -11,9 +11,6 @@
 namespace pb {
 
 constexpr int kMaxEnsembleBodies = 64;
-constexpr int kMaxMultistepOrder = 12;
-// symmetric_linear_multistep_integrator_body.hpp:20.
-constexpr int kStartupStepDivisor = 16;
 
 // Thread layout of the ensemble kernels: a block integrates 32 systems; warp w
 // owns the bodies w, w + W, ... (W warps) of all of them and lane l is system
@@ -295,17 +292,6 @@ EnsembleFillStepKernel(EphemerisView const e,
     }
   }
 }
-
-// integrators/methods.hpp:998-1007,1040-1055 and
-// cohen_hubbard_oesterwinter_body.hpp.
-struct MultistepMethod {
-  int order;
-  double alpha[kMaxMultistepOrder / 2 + 1];
-  double beta_numerator[kMaxMultistepOrder / 2 + 1];
-  double beta_denominator;
-  double cho_numerators[kMaxMultistepOrder];
-  double cho_denominator;
-};
 
 // One step of SymmetricLinearMultistepIntegrator::Instance::Solve,
 // symmetric_linear_multistep_integrator_body.hpp:69-149, with the velocity of

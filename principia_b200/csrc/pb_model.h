@@ -99,4 +99,20 @@ struct BodyScalars {
   double outer_threshold_degree_2[kMaxConstantBodies];
 };
 
+constexpr int kMaxMultistepOrder = 12;
+// symmetric_linear_multistep_integrator_body.hpp:20.
+constexpr int kStartupStepDivisor = 16;
+
+// A symmetric linear multistep method with its velocity formula,
+// integrators/methods.hpp:998-1007,1040-1055 and
+// cohen_hubbard_oesterwinter_body.hpp.
+struct MultistepMethod {
+  int order;
+  double alpha[kMaxMultistepOrder / 2 + 1];
+  double beta_numerator[kMaxMultistepOrder / 2 + 1];
+  double beta_denominator;
+  double cho_numerators[kMaxMultistepOrder];
+  double cho_denominator;
+};
+
 }  // namespace pb

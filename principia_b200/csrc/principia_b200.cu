@@ -17,6 +17,7 @@
 
 #include "../../include/principia_b200.h"
 #include "pb_kernels_massless.cuh"
+#include "pb_kernels_massless_multistep.cuh"
 #include "pb_runtime.cuh"
 
 using namespace pb;
@@ -125,6 +126,9 @@ pb_status_t BuildStageTable(pb_ephemeris* e, double const* times_host,
   PB_LAUNCHED();
   return PB_OK;
 }
+
+// Defined in pb_api_nbody.cu.
+bool MakeMultistepMethod(int32_t method, MultistepMethod& m);
 
 // integrators/symplectic_runge_kutta_nyström_integrator_body.hpp:198-208: the
 // nodes c_i are the double-double partial sums of the a_i.
@@ -629,17 +633,21 @@ pb_status_t pb_compute_gravitational_acceleration_on_massive_bodies(
   return PB_OK;
 }
 
-pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
-                                           const pb_fixed_step_flow_t* flow,
-                                           void* stream_pointer) {
-  if (e == nullptr || flow == nullptr || flow->n < 0 || flow->time == nullptr ||
-      (flow->n > 0 && flow->state == nullptr)) {
-    return Fail(PB_INVALID_ARGUMENT, "bad argument");
-  }
+}  // extern "C"
+
+namespace {
+
+pb_status_t MultistepFlowDevice(pb_ephemeris_t* e,
+                                const pb_fixed_step_flow_t* flow,
+                                cudaStream_t stream);
+
+// pb_flow_with_fixed_step_device for the SRKN methods, at most `max_steps`
+// steps (the Starter of the multistep integrators runs it in groups of 16).
+pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
+                           void* stream_pointer, long long const max_steps) {
   SrknTableau tableau;
   if (!MakeSrknTableau(flow->method, tableau)) {
-    return Fail(PB_INVALID_ARGUMENT,
-                "fixed-step massless flow supports the SRKN methods");
+    return Fail(PB_INVALID_ARGUMENT, "unsupported fixed-step method");
   }
   if (flow->step == 0 || flow->step != flow->step) {
     return Fail(PB_INVALID_ARGUMENT, "CHECK_NE(Time(), step)");
@@ -673,12 +681,13 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
   long long samples_done = 0;
   std::size_t launches = 0;
   std::size_t phases = 0;
-  while (abs_h <= std::abs((t_final - t.value) - t.error)) {
+  while (steps_done < max_steps &&
+         abs_h <= std::abs((t_final - t.value) - t.error)) {
     int steps = 0;
     double* const times = e->pinned_times.data;
     // The pinned staging buffer is reused across chunks.
     PB_CUDA(cudaStreamSynchronize(stream));
-    while (steps < chunk_steps &&
+    while (steps < chunk_steps && steps_done + steps < max_steps &&
            abs_h <= std::abs((t_final - t.value) - t.error)) {
       for (int st = tableau.first_stage; st < tableau.stages; ++st) {
         times[steps * evaluations + (st - tableau.first_stage)] =
@@ -807,6 +816,435 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
     *flow->status = e->pinned_status.data[0] != 0 ? PB_OUT_OF_RANGE : PB_OK;
   }
   return PB_OK;
+}
+
+}  // namespace
+
+// Ephemeris::NewInstance for massless trajectories (ephemeris.hpp:181-194): the
+// integrator instance with its ODE::State on the device and, for the
+// multistep integrators, previous_steps_.
+struct pb_fixed_step_instance {
+  pb_ephemeris* ephemeris = nullptr;
+  int32_t method = 0;
+  bool is_multistep = false;
+  MultistepMethod multistep;
+  double step = 0;
+  long long n = 0;
+  DP time{0.0, 0.0};
+  double* state = nullptr;  // 12 planes of n: owned_state or the caller's.
+  DeviceBuffer<double> owned_state;
+  // previous_steps_: a ring of `order` steps.
+  DeviceBuffer<double> displacement_value, displacement_error, acceleration;
+  int previous_steps = 0;  // previous_steps_.size().
+  long long startup_step_index = 0;
+  int oldest = 0;  // Ring slot of previous_steps_.front().
+  bool startup_target_valid = false;
+  double startup_target = 0;
+  MasslessHistory History() {
+    return {displacement_value.data, displacement_error.data,
+            acceleration.data};
+  }
+};
+
+namespace {
+
+struct InstanceSink {
+  long long sample_every;
+  long long max_samples;
+  double* samples;       // Device.
+  double* sample_times;  // Host.
+  long long appended = 0;  // States appended by this call.
+  long long recorded = 0;
+};
+
+pb_status_t PrepareInstance(pb_fixed_step_instance* s) {
+  if (s->is_multistep && s->displacement_value.data == nullptr) {
+    std::size_t const size =
+        3 * static_cast<std::size_t>(s->n) * s->multistep.order;
+    PB_RETURN_IF_ERROR(s->displacement_value.Reserve(size));
+    PB_RETURN_IF_ERROR(s->displacement_error.Reserve(size));
+    PB_RETURN_IF_ERROR(s->acceleration.Reserve(size));
+  }
+  return PB_OK;
+}
+
+// Starter::FillStepFromState at the instance's current state and time.
+pb_status_t MasslessFillStep(pb_fixed_step_instance* s, int const slot,
+                             cudaStream_t stream) {
+  pb_ephemeris* const e = s->ephemeris;
+  EphemerisView const view = e->View();
+  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
+  double const t = s->time.value;
+  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+  if (s->n > 0) {
+    MasslessFillStepKernel<<<static_cast<unsigned>((s->n + kFlowThreads - 1) /
+                                                   kFlowThreads),
+                             kFlowThreads, 0, stream>>>(
+        view, e->stage_table.data, s->n, s->state, s->History(), slot,
+        e->status_word.data);
+    PB_LAUNCHED();
+  }
+  return PB_OK;
+}
+
+// append_state of the instance: the sink sees every appended state.
+pb_status_t AppendInstanceState(pb_fixed_step_instance* s, InstanceSink* sink,
+                                cudaStream_t stream) {
+  ++sink->appended;
+  if (sink->samples != nullptr && sink->sample_every > 0 &&
+      sink->appended % sink->sample_every == 0 &&
+      sink->recorded < sink->max_samples) {
+    std::size_t const n = static_cast<std::size_t>(s->n);
+    double* const out = sink->samples + sink->recorded * 6 * n;
+    if (n > 0) {
+      PB_CUDA(cudaMemcpyAsync(out, s->state, 3 * n * sizeof(double),
+                              cudaMemcpyDeviceToDevice, stream));
+      PB_CUDA(cudaMemcpyAsync(out + 3 * n, s->state + 6 * n,
+                              3 * n * sizeof(double), cudaMemcpyDeviceToDevice,
+                              stream));
+    }
+    if (sink->sample_times != nullptr) {
+      sink->sample_times[sink->recorded] = s->time.value;
+    }
+    ++sink->recorded;
+  }
+  return PB_OK;
+}
+
+// Integrator::Instance::Solve(t_final) for a massless multistep instance:
+// integrators/starter_body.hpp:23-74, then
+// symmetric_linear_multistep_integrator_body.hpp:69-149.
+pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
+                                   double const t_final, InstanceSink* sink,
+                                   cudaStream_t stream) {
+  pb_ephemeris* const e = s->ephemeris;
+  PB_RETURN_IF_ERROR(PrepareInstance(s));
+  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
+  PB_RETURN_IF_ERROR(
+      UploadFlowConstants(e, s->time.value, s->n, s->state, stream));
+  EphemerisView const view = e->View();
+  double const h = s->step;
+  int const order = s->multistep.order;
+  if (s->previous_steps < order) {
+    if (s->previous_steps == 0) {
+      PB_RETURN_IF_ERROR(MasslessFillStep(s, 0, stream));
+      s->previous_steps = 1;
+    }
+    double const startup_step = h / kStartupStepDivisor;
+    if (!s->startup_target_valid) {
+      s->startup_target = std::min(
+          s->time.value + (order - s->previous_steps) * h + h / 2.0, t_final);
+      s->startup_target_valid = true;
+    }
+    double const target = s->startup_target;
+    // The startup instance: BlanesMoan2002SRKN14A at step / 16; every 16th
+    // step becomes a step of the history and is appended.
+    while (s->previous_steps < order &&
+           startup_step <=
+               std::abs((target - s->time.value) - s->time.error)) {
+      long long const wanted =
+          kStartupStepDivisor - s->startup_step_index % kStartupStepDivisor;
+      double time[2] = {s->time.value, s->time.error};
+      int64_t steps_taken = 0;
+      pb_status_t flow_status = PB_OK;
+      pb_fixed_step_flow_t flow{};
+      flow.method = PB_BLANES_MOAN_2002_SRKN_14A;
+      flow.step = startup_step;
+      flow.t_final = target;
+      flow.n = s->n;
+      flow.state = s->state;
+      flow.time = time;
+      flow.n_steps = &steps_taken;
+      flow.status = &flow_status;
+      PB_RETURN_IF_ERROR(SrknFlowDevice(e, &flow, stream, wanted));
+      s->time = {time[0], time[1]};
+      s->startup_step_index += steps_taken;
+      if (steps_taken == wanted) {
+        PB_RETURN_IF_ERROR(MasslessFillStep(s, s->previous_steps, stream));
+        ++s->previous_steps;
+        PB_RETURN_IF_ERROR(AppendInstanceState(s, sink, stream));
+      } else {
+        break;  // The target was reached between two steps of the history.
+      }
+    }
+    s->startup_target_valid = false;
+    if (s->previous_steps < order) {
+      return PB_OK;  // "we'll continue the next time Solve is called".
+    }
+    s->oldest = 0;
+  }
+  // The reference ignores the status of the startup
+  // (startup_instance->Solve(...).IgnoreError(), starter_body.hpp:68-73) and of
+  // FillStepFromState (symmetric_linear_multistep_integrator_body.hpp:258-261):
+  // only the steps below report collisions.
+  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
+  // Multistep steps, fused `chunk_steps` at a time.
+  int const chunk_steps = 256;
+  PB_RETURN_IF_ERROR(e->stage_table.Reserve(
+      static_cast<std::size_t>(chunk_steps) * view.stage_stride));
+  PB_RETURN_IF_ERROR(e->pinned_times.Reserve(chunk_steps));
+  std::size_t phases = 0;
+  e->last_flow_kernel_launches = 0;
+  while (h <= (t_final - s->time.value) - s->time.error) {
+    int steps = 0;
+    double* const times = e->pinned_times.data;
+    PB_CUDA(cudaStreamSynchronize(stream));
+    long long const appended_before = sink->appended;
+    DP t = s->time;
+    while (steps < chunk_steps && h <= (t_final - t.value) - t.error) {
+      Increment(t, h);
+      times[steps] = t.value;
+      ++steps;
+      // The kernel writes the sample; the host mirrors the bookkeeping.
+      ++sink->appended;
+      if (sink->samples != nullptr && sink->sample_every > 0 &&
+          sink->appended % sink->sample_every == 0 &&
+          sink->recorded < sink->max_samples) {
+        if (sink->sample_times != nullptr) {
+          sink->sample_times[sink->recorded] = t.value;
+        }
+        ++sink->recorded;
+      }
+    }
+    PB_RETURN_IF_ERROR(
+        BuildStageTable(e, times, steps, e->stage_table.data, stream));
+    if (s->n > 0) {
+      while (e->timing_events.size() < 2 * (phases + 1)) {
+        cudaEvent_t event;
+        PB_CUDA(cudaEventCreate(&event));
+        e->timing_events.push_back(event);
+      }
+      PB_CUDA(cudaEventRecord(e->timing_events[2 * phases], stream));
+      unsigned const grid =
+          static_cast<unsigned>((s->n + kFlowThreads - 1) / kFlowThreads);
+      bool const sampling = sink->samples != nullptr && sink->sample_every > 0;
+      auto const kernel = order == 8 ? MasslessMultistepFlowKernel<8>
+                                     : MasslessMultistepFlowKernel<12>;
+      kernel<<<grid, kFlowThreads, 0, stream>>>(
+          view, s->multistep, h, e->stage_table.data, steps, s->n, s->state,
+          s->History(), s->oldest, appended_before,
+          sampling ? sink->sample_every : 0, sink->max_samples, sink->samples,
+          e->status_word.data);
+      PB_LAUNCHED();
+      ++e->last_flow_kernel_launches;
+      PB_CUDA(cudaEventRecord(e->timing_events[2 * phases + 1], stream));
+      ++phases;
+    }
+    s->oldest = (s->oldest + steps) % order;
+    s->time = t;
+  }
+  PB_CUDA(cudaStreamSynchronize(stream));
+  e->last_flow_kernel_ms = 0;
+  for (std::size_t i = 0; i < phases; ++i) {
+    float elapsed = 0;
+    PB_CUDA(cudaEventElapsedTime(&elapsed, e->timing_events[2 * i],
+                                 e->timing_events[2 * i + 1]));
+    e->last_flow_kernel_ms += elapsed;
+  }
+  return PB_OK;
+}
+
+// Instance::Solve(t_final) for either family; the outs of `flow` are filled.
+pb_status_t SolveInstance(pb_fixed_step_instance* s,
+                          const pb_fixed_step_flow_t* flow,
+                          cudaStream_t stream) {
+  pb_ephemeris* const e = s->ephemeris;
+  if (!s->is_multistep) {
+    pb_fixed_step_flow_t srkn = *flow;
+    srkn.method = s->method;
+    srkn.step = s->step;
+    srkn.n = s->n;
+    srkn.state = s->state;
+    double time[2] = {s->time.value, s->time.error};
+    srkn.time = time;
+    PB_RETURN_IF_ERROR(SrknFlowDevice(e, &srkn, stream,
+                                      std::numeric_limits<long long>::max()));
+    s->time = {time[0], time[1]};
+    return PB_OK;
+  }
+  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
+  InstanceSink sink{flow->sample_every, flow->max_samples, flow->samples,
+                    flow->sample_times};
+  PB_RETURN_IF_ERROR(SolveMultistepInstance(s, flow->t_final, &sink, stream));
+  PB_CUDA(cudaMemcpyAsync(e->pinned_status.data, e->status_word.data,
+                          sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  if (flow->n_steps != nullptr) {
+    *flow->n_steps = sink.appended;
+  }
+  if (flow->n_samples != nullptr) {
+    *flow->n_samples = sink.recorded;
+  }
+  if (flow->status != nullptr) {
+    *flow->status = e->pinned_status.data[0] != 0 ? PB_OUT_OF_RANGE : PB_OK;
+  }
+  return PB_OK;
+}
+
+pb_status_t MultistepFlowDevice(pb_ephemeris_t* e,
+                                const pb_fixed_step_flow_t* flow,
+                                cudaStream_t stream) {
+  if (!(flow->step > 0)) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "the multistep massless flow integrates forward");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  pb_fixed_step_instance instance;
+  instance.ephemeris = e;
+  instance.method = flow->method;
+  instance.is_multistep = true;
+  MakeMultistepMethod(flow->method, instance.multistep);
+  instance.step = flow->step;
+  instance.n = flow->n;
+  instance.time = {flow->time[0], flow->time[1]};
+  instance.state = flow->state;
+  PB_RETURN_IF_ERROR(e->pinned_status.Reserve(1));
+  PB_RETURN_IF_ERROR(e->status_word.Reserve(1));
+  PB_RETURN_IF_ERROR(SolveInstance(&instance, flow, stream));
+  flow->time[0] = instance.time.value;
+  flow->time[1] = instance.time.error;
+  return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+pb_status_t pb_fixed_step_instance_create(pb_ephemeris_t* e, int32_t method,
+                                          double step, int64_t n,
+                                          const double* state,
+                                          const double* time,
+                                          pb_fixed_step_instance_t** instance) {
+  if (e == nullptr || instance == nullptr || n < 0 || time == nullptr ||
+      (n > 0 && state == nullptr)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  *instance = nullptr;
+  if (step == 0 || step != step) {
+    return Fail(PB_INVALID_ARGUMENT, "CHECK_NE(Time(), step)");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  auto* s = new pb_fixed_step_instance;
+  s->ephemeris = e;
+  s->method = method;
+  s->step = step;
+  s->n = n;
+  s->time = {time[0], time[1]};
+  SrknTableau tableau;
+  if (MakeMultistepMethod(method, s->multistep)) {
+    s->is_multistep = true;
+    if (!(step > 0)) {
+      delete s;
+      return Fail(PB_INVALID_ARGUMENT,
+                  "the multistep massless flow integrates forward");
+    }
+  } else if (!MakeSrknTableau(method, tableau)) {
+    delete s;
+    return Fail(PB_INVALID_ARGUMENT, "unsupported fixed-step method");
+  }
+  pb_status_t status =
+      s->owned_state.Upload(state, 12 * static_cast<std::size_t>(n), nullptr);
+  if (status == PB_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) {
+    status = Fail(PB_INTERNAL, "upload failed");
+  }
+  if (status != PB_OK) {
+    delete s;
+    return status;
+  }
+  s->state = s->owned_state.data;
+  *instance = s;
+  return PB_OK;
+}
+
+void pb_fixed_step_instance_destroy(pb_fixed_step_instance_t* instance) {
+  if (instance != nullptr) {
+    cudaSetDevice(instance->ephemeris->device);
+    delete instance;
+  }
+}
+
+pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* s,
+                                        double t_final, int64_t sample_every,
+                                        int64_t max_samples, double* samples,
+                                        double* sample_times,
+                                        int64_t* n_steps, int64_t* n_samples,
+                                        pb_status_t* flow_status) {
+  if (s == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null instance");
+  }
+  pb_ephemeris* const e = s->ephemeris;
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  std::size_t const n = static_cast<std::size_t>(s->n);
+  bool const sampling =
+      samples != nullptr && sample_every > 0 && max_samples > 0;
+  pb_fixed_step_flow_t flow{};
+  flow.t_final = t_final;
+  flow.sample_every = sampling ? sample_every : 0;
+  flow.max_samples = max_samples;
+  flow.sample_times = sample_times;
+  int64_t recorded = 0;
+  flow.n_samples = &recorded;
+  flow.n_steps = n_steps;
+  flow.status = flow_status;
+  if (sampling) {
+    PB_RETURN_IF_ERROR(
+        e->scratch_c.Reserve(static_cast<std::size_t>(max_samples) * 6 * n));
+    flow.samples = e->scratch_c.data;
+  }
+  PB_RETURN_IF_ERROR(e->pinned_status.Reserve(1));
+  PB_RETURN_IF_ERROR(e->status_word.Reserve(1));
+  PB_RETURN_IF_ERROR(SolveInstance(s, &flow, stream));
+  if (sampling && recorded > 0 && n > 0) {
+    PB_CUDA(cudaMemcpyAsync(
+        samples, e->scratch_c.data,
+        static_cast<std::size_t>(recorded) * 6 * n * sizeof(double),
+        cudaMemcpyDeviceToHost, stream));
+  }
+  PB_CUDA(cudaStreamSynchronize(stream));
+  if (n_samples != nullptr) {
+    *n_samples = recorded;
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_fixed_step_instance_get_state(pb_fixed_step_instance_t* s,
+                                             double* state, double* time) {
+  if (s == nullptr || (s->n > 0 && state == nullptr)) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  if (s->n > 0) {
+    PB_CUDA(cudaMemcpy(state, s->state,
+                       12 * static_cast<std::size_t>(s->n) * sizeof(double),
+                       cudaMemcpyDeviceToHost));
+  }
+  if (time != nullptr) {
+    time[0] = s->time.value;
+    time[1] = s->time.error;
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
+                                           const pb_fixed_step_flow_t* flow,
+                                           void* stream_pointer) {
+  if (e == nullptr || flow == nullptr || flow->n < 0 || flow->time == nullptr ||
+      (flow->n > 0 && flow->state == nullptr)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  if (flow->step == 0 || flow->step != flow->step) {
+    return Fail(PB_INVALID_ARGUMENT, "CHECK_NE(Time(), step)");
+  }
+  MultistepMethod multistep;
+  if (MakeMultistepMethod(flow->method, multistep)) {
+    // NewInstance + FlowWithFixedStep in one call: the instance (and the
+    // history it would keep) lives for this call only.
+    return MultistepFlowDevice(e, flow,
+                               static_cast<cudaStream_t>(stream_pointer));
+  }
+  return SrknFlowDevice(e, flow, stream_pointer,
+                        std::numeric_limits<long long>::max());
 }
 
 pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* e,

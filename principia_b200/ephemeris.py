@@ -182,6 +182,11 @@ class Ephemeris:
                                                    ctypes.byref(flow), stream))
     return dict(n_steps=outs[1].value, status=outs[2].value)
 
+  def new_instance(self, method, step, state, time):
+    """Ephemeris::NewInstance over n massless trajectories (state (12, n),
+    time (2,)); the instance keeps its state on the device."""
+    return FixedStepInstance(self, method, step, state, time)
+
   def last_flow_kernel_ms(self):
     """(device ms, launches) of the flow kernels of the last flow call."""
     launches = ctypes.c_int64()
@@ -222,6 +227,54 @@ class Ephemeris:
                                                ctypes.byref(flow)))
     return dict(status=status, accepted=accepted, rejected=rejected,
                 evaluations=evaluations, step_log=step_log)
+
+
+class FixedStepInstance:
+  """Integrator<NewtonianMotionEquation>::Instance of the reference for a
+  fixed-step method (integrators/integrators.hpp:40-94): flow(t) is
+  Ephemeris::FlowWithFixedStep(t, instance)."""
+
+  def __init__(self, ephemeris, method, step, state, time):
+    self.ephemeris = ephemeris  # Keeps the ephemeris alive.
+    self.lib = ephemeris.lib
+    self.n = state.shape[1]
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    time = np.ascontiguousarray(time, dtype=np.float64)
+    self.handle = ctypes.c_void_p()
+    _check(self.lib.pb_fixed_step_instance_create(
+        ephemeris.handle, method, step, self.n, _dptr(state), _dptr(time),
+        ctypes.byref(self.handle)))
+
+  def __del__(self):
+    if getattr(self, 'handle', None):
+      self.lib.pb_fixed_step_instance_destroy(self.handle)
+      self.handle = None
+
+  def flow(self, t_final, sample_every=0, max_samples=0):
+    samples = sample_times = None
+    if sample_every > 0 and max_samples > 0:
+      samples = np.zeros((max_samples, 6, self.n))
+      sample_times = np.zeros(max_samples)
+    n_steps, n_samples = ctypes.c_int64(), ctypes.c_int64()
+    status = ctypes.c_int32()
+    _check(self.lib.pb_fixed_step_instance_flow(
+        self.handle, t_final, sample_every, max_samples,
+        None if samples is None else _dptr(samples),
+        None if samples is None else _dptr(sample_times),
+        ctypes.byref(n_steps), ctypes.byref(n_samples), ctypes.byref(status)))
+    return dict(n_steps=n_steps.value, status=status.value,
+                samples=None if samples is None
+                else samples[:n_samples.value],
+                sample_times=None if samples is None
+                else sample_times[:n_samples.value])
+
+  def state(self):
+    """(state (12, n), time (2,)) of the instance."""
+    state = np.zeros((12, self.n))
+    time = np.zeros(2)
+    _check(self.lib.pb_fixed_step_instance_get_state(self.handle, _dptr(state),
+                                                     _dptr(time)))
+    return state, time
 
 
 def measure_fp64_peak(device=0):

@@ -1,0 +1,156 @@
+"""GPU parity of the fixed-step flow of massless bodies with the symmetric
+linear multistep integrators (the plugin's history
+integrator is Quinlan1999Order8A at 10 s, ksp_plugin/integrators.cpp:66-72):
+bit for bit against the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from principia_b200 import _capi
+from principia_b200 import workloads
+
+from conftest import assert_bitwise_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def leo(system, n, seed=42):
+  earth = system.bodies[system.index('Earth')]
+  return workloads.leo_probes(n, earth['q'], earth['v'], earth['mu'], seed)
+
+
+@pytest.mark.parametrize('method,order', [
+    (_capi.QUINLAN_1999_ORDER_8A, 8),
+    (_capi.QUINLAN_TREMAINE_1990_ORDER_12, 12),
+])
+def test_multistep_flow_matches_oracle(sol_system, sol_oracle, sol_gpu, method,
+                                       order):
+  n = 700  # Ragged.
+  state = leo(sol_system, n)
+  expected_state = state.copy()
+  time = np.zeros(2)
+  expected_time = time.copy()
+  # 10 s steps; the startup (order - 1 steps of 16 SRKN14A substeps) and then
+  # more than one chunk of the stage table (> 256 steps); t_final is not a
+  # multiple of the step.
+  t_final = 3005.0
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, t_final, state, time,
+                                        sample_every=7, max_samples=50)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, t_final,
+                                             expected_state, expected_time,
+                                             sample_every=7, max_samples=50)
+  assert result['n_steps'] == expected['n_steps'] == 300
+  assert result['status'] == expected['status'] == 0
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'state')
+  assert len(result['samples']) == len(expected['samples']) == 42
+  assert_bitwise_equal(result['sample_times'], expected['sample_times'])
+  assert_bitwise_equal(result['samples'], expected['samples'], 'samples')
+
+
+def test_instance_keeps_its_history(sol_system, sol_oracle, sol_gpu):
+  """FlowWithFixedStep called repeatedly on one instance (the plugin's
+  pattern) equals one Solve to the final time: the calls stop in the middle of
+  the startup, right after it, and in the multistep regime."""
+  method = _capi.QUINLAN_1999_ORDER_8A
+  n = 96
+  state0 = leo(sol_system, n, seed=5)
+  instance = sol_gpu.new_instance(method, 10.0, state0, np.zeros(2))
+  appended = 0
+  for t in (4.0, 33.0, 70.0, 75.0, 400.0, 1000.0):
+    appended += instance.flow(t)['n_steps']
+  state, time = instance.state()
+  expected_state = state0.copy()
+  expected_time = np.zeros(2)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, 1000.0,
+                                             expected_state, expected_time)
+  assert appended == expected['n_steps'] == 100
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'state')
+  # An SRKN instance goes through the same entry points.
+  method = _capi.BLANES_MOAN_2002_SRKN_14A
+  instance = sol_gpu.new_instance(method, 10.0, state0, np.zeros(2))
+  instance.flow(300.0)
+  result = instance.flow(600.0, sample_every=10, max_samples=3)
+  state, time = instance.state()
+  expected_state = state0.copy()
+  expected_time = np.zeros(2)
+  sol_oracle.flow_with_fixed_step(method, 10.0, 600.0, expected_state,
+                                  expected_time)
+  assert result['n_steps'] == 30 and len(result['samples']) == 3
+  assert_bitwise_equal(state, expected_state, 'SRKN instance')
+  assert_bitwise_equal(result['samples'][-1][:3], expected_state[:3])
+
+
+def test_multistep_collision_status(sol_system, sol_oracle, sol_gpu):
+  """Collisions are reported by the multistep steps only: the reference ignores
+  the status of the startup and of FillStepFromState (starter_body.hpp:68-73,
+  symmetric_linear_multistep_integrator_body.hpp:258-261).  One probe starts
+  deep inside the Earth and is flung out during the startup; another one skims
+  the surface (6300 km, inside 0.99 times the minimal radius) all along."""
+  method = _capi.QUINLAN_1999_ORDER_8A
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  for radius, expected_status in ((1.0e6, None), (6.30e6, _capi.PB_OUT_OF_RANGE)):
+    state = leo(sol_system, 8, seed=9)
+    r = state[0:3, 3] - np.asarray(earth['q'])
+    state[0:3, 3] = np.asarray(earth['q']) + r * (radius / np.linalg.norm(r))
+    expected_state = state.copy()
+    time, expected_time = np.zeros(2), np.zeros(2)
+    result = sol_gpu.flow_with_fixed_step(method, 10.0, 200.0, state, time)
+    expected = sol_oracle.flow_with_fixed_step(method, 10.0, 200.0,
+                                               expected_state, expected_time)
+    assert result['status'] == expected['status']
+    if expected_status is not None:
+      assert result['status'] == expected_status
+    assert result['n_steps'] == expected['n_steps'] == 20
+    assert_bitwise_equal(state, expected_state, 'radius %g' % radius)
+
+
+def test_reference_collision_detection_apple(sol_system):
+  """physics/ephemeris_test.cpp:763-811 (CollisionDetection): an apple 10 m
+  above the Earth (alone, at rest at the origin), Quinlan1999Order8A at 1 ms.
+  OK after 1 s, OutOfRange when the same instance is flowed to 354.8 s; the
+  product agrees with the oracle bit for bit at both times."""
+  from principia_b200.ephemeris import Ephemeris
+  from oracle_lib import OracleEphemeris
+  system = sol_system.copy()
+  for name in list(system.names()):
+    if name != 'Earth':
+      system.remove_massive_body(name)
+  zeros = np.zeros((1, 3))
+  oracle = OracleEphemeris(system, step=0.01, fitting_tolerance=5e-3,
+                           initial_positions=zeros, initial_velocities=zeros,
+                           initial_time=0.0)
+  assert oracle.prolong(355.0) == 0
+  gpu = Ephemeris(system)
+  gpu.append_segments(0, oracle.segments(0))
+  earth = system.bodies[0]
+  state0 = np.zeros((12, 1))
+  state0[2, 0] = earth['mean_radius'] + 10.0
+  method = _capi.QUINLAN_1999_ORDER_8A
+  instance = gpu.new_instance(method, 1e-3, state0, np.zeros(2))
+  expected_state, expected_time = state0.copy(), np.zeros(2)
+  result = instance.flow(1.0)
+  expected = oracle.flow_with_fixed_step(method, 1e-3, 1.0, expected_state,
+                                         expected_time)
+  assert result['status'] == expected['status'] == 0
+  assert result['n_steps'] == expected['n_steps']
+  state, time = instance.state()
+  assert_bitwise_equal(state, expected_state, 'after 1 s')
+  # The oracle's instance lives for one call: compare with one Solve from the
+  # start to 354.8 s.
+  result = instance.flow(354.8)
+  expected_state, expected_time = state0.copy(), np.zeros(2)
+  expected = oracle.flow_with_fixed_step(method, 1e-3, 354.8, expected_state,
+                                         expected_time)
+  assert result['status'] == _capi.PB_OUT_OF_RANGE
+  assert expected['status'] == _capi.PB_OUT_OF_RANGE
+  state, time = instance.state()
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'after 354.8 s')
+
+
+def test_multistep_flow_rejects_backward_steps(sol_system, sol_gpu):
+  state = leo(sol_system, 4)
+  with pytest.raises(Exception):
+    sol_gpu.flow_with_fixed_step(_capi.QUINLAN_1999_ORDER_8A, -10.0, -100.0,
+                                 state, np.zeros(2))
