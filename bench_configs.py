@@ -2,7 +2,7 @@
 """Secondary measurements: BASELINE.json configs 3, 4 and 5 (bench.py is the
 headline, config 2).  One JSON line per config.
 
-  python bench_configs.py [--config adaptive|ensemble|allpairs|all]
+  python bench_configs.py [--config adaptive|history|ensemble|allpairs|all]
   torchrun --nproc-per-node N ... bench_configs.py      (weak scaling; the
       all-pairs config is i-block sharded with an NCCL all-gather)
 """
@@ -93,6 +93,55 @@ def bench_adaptive(args):
         'e2e_probe_rkn_stages_per_second': evaluations / wall,
         'mean_steps_per_probe': steps / (n * world),
         'max_steps_per_probe': int(result['accepted'].max())}))
+
+
+def bench_history(args):
+  """The plugin's history integrator on the config-2 probes: 10^5 LEO probes,
+  Quinlan1999Order8A at 10 s (ksp_plugin/integrators.cpp:66-72), one
+  right-hand-side evaluation per step; probes sharded by rank."""
+  torch, dist, world, rank, local_rank = dist_setup()
+  from principia_b200 import _capi
+  from principia_b200 import workloads
+  from principia_b200.ephemeris import Ephemeris
+  device = torch.device('cuda', local_rank)
+  system = workloads.sol_system()
+  ephemeris = Ephemeris(system, device=local_rank)
+  workloads.upload_sol_ephemeris(ephemeris)
+  earth = system.bodies[system.index('Earth')]
+  n = args.probes
+  state = workloads.leo_probes(n, earth['q'], earth['v'], earth['mu'],
+                               42 + rank)
+  instance = ephemeris.new_instance(_capi.QUINLAN_1999_ORDER_8A, 10.0, state,
+                                    np.zeros(2))
+  instance.flow(100.0)  # Startup and warm-up.
+  t = 100.0
+  results = []
+  for repeat in range(3):
+    t += 10.0 * args.steps
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    result = instance.flow(t)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    kernel_ms, launches = ephemeris.last_flow_kernel_ms()
+    results.append((wall, kernel_ms, result['n_steps']))
+  wall, kernel_ms, steps = results[-1]
+  assert steps == args.steps
+  kernel_s = max_over_ranks(torch, dist, world, kernel_ms * 1e-3, device)
+  wall = max_over_ranks(torch, dist, world, wall, device)
+  if rank == 0:
+    from principia_b200 import flops
+    per_step = flops.massless_probe_stage_sol_leo()
+    print(json.dumps({
+        'config': 'history integrator: LEO probes, Quinlan1999Order8A, 10 s',
+        'n_gpus': world, 'probes_per_gpu': n, 'steps': steps,
+        'kernel_seconds': kernel_s, 'seconds': wall,
+        'probe_steps_per_second': n * world * steps / kernel_s,
+        'e2e_probe_steps_per_second': n * world * steps / wall,
+        'algorithmic_tflops_rhs_only':
+            n * world * steps * per_step / kernel_s / 1e12}))
 
 
 def bench_ensemble(args):
@@ -205,6 +254,8 @@ def main():
   args = parser.parse_args()
   if args.config in ('adaptive', 'all'):
     bench_adaptive(args)
+  if args.config in ('history', 'all'):
+    bench_history(args)
   if args.config in ('ensemble', 'all'):
     bench_ensemble(args)
   if args.config in ('allpairs', 'all'):
