@@ -234,7 +234,8 @@ pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* instance,
                                         double* sample_times,
                                         int64_t* n_steps, int64_t* n_samples,
                                         pb_status_t* flow_status);
-/* instance.state(): 12 planes of n and the time {value, error}. */
+/* instance.state(): 12 planes of n and the time {value, error}; either may be
+ * NULL. */
 pb_status_t pb_fixed_step_instance_get_state(
     pb_fixed_step_instance_t* instance, double* state, double* time);
 

@@ -81,13 +81,19 @@ class Ephemeris {
   // trajectories it advances.
   class Instance {
    public:
+    Instance() = default;
+    Instance(Instance const&) = delete;
+    Instance& operator=(Instance const&) = delete;
+    ~Instance() { pb_fixed_step_instance_destroy(handle_); }
     double time() const { return time_[0]; }
 
    private:
     friend class Ephemeris;
     FixedStepParameters parameters_;
     std::vector<DiscreteTrajectory*> trajectories_;
-    std::vector<double> state_;  // 12 planes of n.
+    // The integrator instance of the C ABI: its ODE::State and, for the
+    // multistep integrators, its previous steps live on the device.
+    pb_fixed_step_instance_t* handle_ = nullptr;
     double time_[2] = {0.0, 0.0};
   };
 
@@ -194,7 +200,7 @@ class Ephemeris {
     instance->parameters_ = parameters;
     instance->trajectories_ = trajectories;
     std::size_t const n = trajectories.size();
-    instance->state_.assign(12 * n, 0.0);
+    std::vector<double> state(12 * n, 0.0);
     double const last_time = trajectories.front()->back_time();
     for (std::size_t i = 0; i < n; ++i) {
       if (trajectories[i]->back_time() != last_time) {
@@ -202,11 +208,18 @@ class Ephemeris {
       }
       DegreesOfFreedom const& dof = trajectories[i]->back();
       for (int c = 0; c < 3; ++c) {
-        instance->state_[(0 + c) * n + i] = dof.q[c];
-        instance->state_[(6 + c) * n + i] = dof.v[c];
+        state[(0 + c) * n + i] = dof.q[c];
+        state[(6 + c) * n + i] = dof.v[c];
       }
     }
     instance->time_[0] = last_time;
+    pb_status_t const call = pb_fixed_step_instance_create(
+        ephemeris_, parameters.integrator, parameters.step,
+        static_cast<std::int64_t>(n), state.data(), instance->time_,
+        &instance->handle_);
+    if (call != PB_OK) {
+      throw std::invalid_argument(pb_last_error());
+    }
     Prolong(last_time + parameters.step);
     return instance;
   }
@@ -232,21 +245,13 @@ class Ephemeris {
     std::vector<double> sample_times(max_samples);
     std::int64_t n_samples = 0, n_steps = 0;
     pb_status_t flow_status = PB_OK;
-    pb_fixed_step_flow_t flow{};
-    flow.method = instance.parameters_.integrator;
-    flow.step = step;
-    flow.t_final = t;
-    flow.n = n;
-    flow.state = instance.state_.data();
-    flow.time = instance.time_;
-    flow.sample_every = 1;
-    flow.max_samples = max_samples;
-    flow.samples = samples.data();
-    flow.sample_times = sample_times.data();
-    flow.n_samples = &n_samples;
-    flow.n_steps = &n_steps;
-    flow.status = &flow_status;
-    pb_status_t const call = pb_flow_with_fixed_step(ephemeris_, &flow);
+    pb_status_t call = pb_fixed_step_instance_flow(
+        instance.handle_, t, /*sample_every=*/1, max_samples, samples.data(),
+        sample_times.data(), &n_steps, &n_samples, &flow_status);
+    if (call == PB_OK) {
+      call = pb_fixed_step_instance_get_state(instance.handle_, nullptr,
+                                              instance.time_);
+    }
     if (call != PB_OK) {
       return Status::FromCall(call);
     }

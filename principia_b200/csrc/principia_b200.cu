@@ -1210,11 +1210,11 @@ pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* s,
 
 pb_status_t pb_fixed_step_instance_get_state(pb_fixed_step_instance_t* s,
                                              double* state, double* time) {
-  if (s == nullptr || (s->n > 0 && state == nullptr)) {
-    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  if (s == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null instance");
   }
   PB_CUDA(cudaSetDevice(s->ephemeris->device));
-  if (s->n > 0) {
+  if (s->n > 0 && state != nullptr) {
     PB_CUDA(cudaMemcpy(state, s->state,
                        12 * static_cast<std::size_t>(s->n) * sizeof(double),
                        cudaMemcpyDeviceToHost));

@@ -87,6 +87,40 @@ int32_t ft_flow_with_fixed_step(void* e, int32_t n, double const* q,
   return status.code;
 }
 
+// NewInstance, then FlowWithFixedStep(t_mid) and FlowWithFixedStep(t) on the
+// same instance (the plugin's pattern for vessel histories).
+int32_t ft_flow_with_fixed_step_twice(void* e, int32_t n, double const* q,
+                                      double const* v, double t0,
+                                      int32_t method, double step, double t_mid,
+                                      double t, int32_t* points, double* last,
+                                      double* last_time) {
+  auto* ephemeris = static_cast<Ephemeris*>(e);
+  std::vector<DiscreteTrajectory> trajectories(n);
+  std::vector<DiscreteTrajectory*> pointers;
+  for (int i = 0; i < n; ++i) {
+    DegreesOfFreedom dof;
+    for (int c = 0; c < 3; ++c) {
+      dof.q[c] = q[3 * i + c];
+      dof.v[c] = v[3 * i + c];
+    }
+    trajectories[i].Append(t0, dof);
+    pointers.push_back(&trajectories[i]);
+  }
+  auto instance =
+      ephemeris->NewInstance(pointers, FixedStepParameters{method, step});
+  Status status = ephemeris->FlowWithFixedStep(t_mid, *instance);
+  if (status.ok()) {
+    status = ephemeris->FlowWithFixedStep(t, *instance);
+  }
+  for (int i = 0; i < n; ++i) {
+    points[i] = static_cast<int32_t>(trajectories[i].times.size());
+    std::memcpy(last + 6 * i, trajectories[i].back().q, 3 * sizeof(double));
+    std::memcpy(last + 6 * i + 3, trajectories[i].back().v, 3 * sizeof(double));
+  }
+  *last_time = trajectories[0].back_time();
+  return status.code;
+}
+
 // FlowWithAdaptiveStep on one probe; returns the status; the appended points
 // (up to capacity) in times / dofs[k][6].
 int32_t ft_flow_with_adaptive_step(void* e, double const* q, double const* v,

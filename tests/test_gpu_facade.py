@@ -43,6 +43,8 @@ def shim():
   lib.ft_get_segments.argtypes = [_vp, _i32, _dp, _dp, _i32p, _dp]
   lib.ft_flow_with_fixed_step.argtypes = [_vp, _i32, _dp, _dp, _d, _i32, _d,
                                           _d, _i32p, _dp, _dp]
+  lib.ft_flow_with_fixed_step_twice.argtypes = [_vp, _i32, _dp, _dp, _d, _i32,
+                                                _d, _d, _d, _i32p, _dp, _dp]
   lib.ft_flow_with_adaptive_step.argtypes = [_vp, _dp, _dp, _d, _d, _d, _d,
                                              _i64, _i64, _i64p, _dp, _dp]
   lib.ft_acceleration_on_massless_body.argtypes = [_vp, _dp, _d, _dp]
@@ -106,6 +108,23 @@ def test_facade_prolong_and_flows(shim, sol_system):
   assert last_time.value == expected_time[0] == t_flow
   assert_bitwise_equal(last[:, 0:3].T, expected_state[0:3], 'positions')
   assert_bitwise_equal(last[:, 3:6].T, expected_state[6:9], 'velocities')
+
+  # The history integrator (Quinlan1999Order8A at 10 s) on one instance flowed
+  # twice: the instance keeps its previous steps between the calls.
+  points[:] = 0
+  status = shim.ft_flow_with_fixed_step_twice(
+      handle, n, oracle_lib.dptr(q), oracle_lib.dptr(v), 0.0,
+      _capi.QUINLAN_1999_ORDER_8A, 10.0, 45.0, 2000.0,
+      points.ctypes.data_as(_i32p), oracle_lib.dptr(last), last_time)
+  assert status == 0
+  expected_state = state.copy()
+  expected_time = np.zeros(2)
+  oracle.flow_with_fixed_step(_capi.QUINLAN_1999_ORDER_8A, 10.0, 2000.0,
+                              expected_state, expected_time)
+  assert np.all(points == 201)
+  assert last_time.value == expected_time[0] == 2000.0
+  assert_bitwise_equal(last[:, 0:3].T, expected_state[0:3], 'history q')
+  assert_bitwise_equal(last[:, 3:6].T, expected_state[6:9], 'history v')
 
   # FlowWithAdaptiveStep: every accepted step appended.
   probe = workloads.eccentric_probes(4, earth['q'], earth['v'], earth['mu'], 9)
