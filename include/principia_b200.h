@@ -354,6 +354,47 @@ pb_status_t pb_nbody_allpairs_accelerations(pb_nbody_allpairs_t* system,
 /* Milliseconds spent in the last solve's force kernels (CUDA events). */
 double pb_nbody_allpairs_last_force_ms(const pb_nbody_allpairs_t* system);
 
+/* ---- The trajectory sink: DiscreteTrajectorySegment::SetDownsampling +
+ * Append (physics/discrete_trajectory_segment_body.hpp:414-479; tolerances in
+ * ksp_plugin/integrators.cpp:23-36) for n trajectories on the device, so that
+ * the states appended by a flow need not all travel to the host.  A new point
+ * replaces the last one of a timeline as long as the accumulated bound on the
+ * error of the Hermite interpolation (numerics/hermite3_body.hpp:154-194)
+ * stays below `tolerance` (negative: no downsampling).  Each timeline holds at
+ * most `capacity` points. */
+typedef struct pb_downsampler pb_downsampler_t;
+pb_status_t pb_downsampler_create(int32_t cuda_device, int64_t n,
+                                  double tolerance, int64_t capacity,
+                                  pb_downsampler_t** downsampler);
+void pb_downsampler_destroy(pb_downsampler_t* downsampler);
+/* Appends n_samples states, in order, to every trajectory:
+ * samples[s][6][n] (q xyz, v xyz: the `samples` of the fixed-step flows) at
+ * sample_times[s] (host).  `samples` on the host, or on the device. */
+pb_status_t pb_downsampler_append(pb_downsampler_t* downsampler,
+                                  int64_t n_samples,
+                                  const double* sample_times,
+                                  const double* samples);
+pb_status_t pb_downsampler_append_device(pb_downsampler_t* downsampler,
+                                         int64_t n_samples,
+                                         const double* sample_times,
+                                         const double* samples, void* stream);
+/* Appends the logs of an adaptive flow (device memory, as filled by
+ * pb_flow_with_adaptive_step_device): trajectory i gets its first
+ * min(accepted_steps[i], log_capacity) states, step_log[s][n],
+ * state_log[s][6][n]. */
+pb_status_t pb_downsampler_append_logs_device(pb_downsampler_t* downsampler,
+                                              int64_t log_capacity,
+                                              const double* step_log,
+                                              const int64_t* accepted_steps,
+                                              const double* state_log,
+                                              void* stream);
+/* The timelines: counts[n]; times[capacity][n]; points[capacity][6][n];
+ * errors[capacity][n] (the downsampling error recorded with each
+ * interpolation).  Any may be NULL.  PB_RESOURCE_EXHAUSTED if a timeline
+ * outgrew `capacity` (its later points were dropped). */
+pb_status_t pb_downsampler_get(pb_downsampler_t* downsampler, int64_t* counts,
+                               double* times, double* points, double* errors);
+
 /* ---- Series in the Чебышёв basis.
  * PolynomialInЧебышёвBasis<Value, Instant, degree>::operator() and
  * EvaluateDerivative, numerics/polynomial_in_чебышёв_basis_body.hpp:151-202

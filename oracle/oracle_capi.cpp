@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../include/principia_b200.h"
+#include "discrete_trajectory.hpp"
 #include "ephemeris.hpp"
 
 using namespace orc;
@@ -206,6 +207,53 @@ double orc_chebyshev_evaluate_derivative(double const* coefficients,
                                          double upper_bound, double argument) {
   return ЧебышёвEvaluateDerivative(coefficients, 1, degree, lower_bound,
                                    upper_bound, argument);
+}
+
+// DiscreteTrajectorySegment::Append with SetDownsampling({tolerance})
+// (physics/discrete_trajectory_segment_body.hpp:414-479) on one trajectory of
+// n_points (q, v: [n_points][3]).  Returns the size of the timeline; the
+// retained points go to kept_* (room for n_points), with the downsampling
+// error recorded with each interpolation.  If n_evaluations > 0 the segment is
+// then evaluated (EvaluatePosition / EvaluateVelocity, :132-155).
+int64_t orc_downsample(int64_t n_points, double const* times, double const* q,
+                       double const* v, double tolerance, double* kept_times,
+                       double* kept_q, double* kept_v, double* kept_errors,
+                       int64_t n_evaluations, double const* evaluation_times,
+                       double* evaluated_q, double* evaluated_v) {
+  DownsamplingSegment segment(tolerance);
+  for (int64_t i = 0; i < n_points; ++i) {
+    segment.Append(times[i], Vec3{q[3 * i], q[3 * i + 1], q[3 * i + 2]},
+                   Vec3{v[3 * i], v[3 * i + 1], v[3 * i + 2]});
+  }
+  auto const& timeline = segment.timeline();
+  for (std::size_t k = 0; k < timeline.size(); ++k) {
+    kept_times[k] = timeline[k].time;
+    kept_q[3 * k] = timeline[k].q.x;
+    kept_q[3 * k + 1] = timeline[k].q.y;
+    kept_q[3 * k + 2] = timeline[k].q.z;
+    kept_v[3 * k] = timeline[k].v.x;
+    kept_v[3 * k + 1] = timeline[k].v.y;
+    kept_v[3 * k + 2] = timeline[k].v.z;
+    if (kept_errors != nullptr) {
+      kept_errors[k] = timeline[k].error;
+    }
+  }
+  for (int64_t j = 0; j < n_evaluations; ++j) {
+    Vec3 eq{NAN, NAN, NAN}, ev{NAN, NAN, NAN};
+    segment.Evaluate(evaluation_times[j], eq, ev);
+    evaluated_q[3 * j] = eq.x;
+    evaluated_q[3 * j + 1] = eq.y;
+    evaluated_q[3 * j + 2] = eq.z;
+    evaluated_v[3 * j] = ev.x;
+    evaluated_v[3 * j + 1] = ev.y;
+    evaluated_v[3 * j + 2] = ev.z;
+  }
+  return static_cast<int64_t>(timeline.size());
+}
+
+void orc_cr_sin_cos(double x, double* s, double* c) {
+  *s = CrSin(x);
+  *c = CrCos(x);
 }
 
 // Newhall fit of 9 equally spaced (q, v) pairs: returns the monomial

@@ -149,6 +149,16 @@ SYMBOLS = [
      [_vp, c_double_p, c_double_p, c_double_p]),
     ('pb_nbody_allpairs_accelerations', _i32, [_vp, c_double_p]),
     ('pb_nbody_allpairs_last_force_ms', _d, [_vp]),
+    ('pb_downsampler_create', _i32,
+     [_i32, _i64, _d, _i64, ctypes.POINTER(_vp)]),
+    ('pb_downsampler_destroy', None, [_vp]),
+    ('pb_downsampler_append', _i32, [_vp, _i64, c_double_p, c_double_p]),
+    ('pb_downsampler_append_device', _i32,
+     [_vp, _i64, c_double_p, _vp, _vp]),
+    ('pb_downsampler_append_logs_device', _i32,
+     [_vp, _i64, _vp, _vp, _vp, _vp]),
+    ('pb_downsampler_get', _i32,
+     [_vp, c_int64_p, c_double_p, c_double_p, c_double_p]),
     ('pb_chebyshev_series_evaluate', _i32,
      [_i32, _i64, _i32, c_int32_p, c_double_p, c_double_p, c_double_p, _i64,
       c_int32_p, c_double_p, c_double_p, c_double_p]),

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../principia_b200/csrc/pb_accel.cuh"
+#include "../../principia_b200/csrc/pb_downsampling.cuh"
 #include "../../principia_b200/csrc/pb_host_model.hpp"
 
 using namespace pb;
@@ -26,6 +27,42 @@ double hc_estrin(double const* c, int32_t degree, double x) {
   return EstrinEvaluate<1>(c, degree, x);
 }
 double hc_pow_int(double x, int32_t k) { return PowInt(x, k); }
+
+// DownsamplerAppend on one trajectory (q, v: [n_points][3]); returns the size
+// of the timeline, the retained points in kept_* (room for n_points).
+int64_t hc_downsample(int64_t n_points, double const* times, double const* q,
+                      double const* v, double tolerance, double* kept_times,
+                      double* kept_q, double* kept_v, double* kept_errors) {
+  std::vector<double> timeline_times(n_points), points(6 * n_points),
+      errors(n_points), a2a3(6);
+  long long count = 0;
+  double downsampling_error = 0;
+  int32_t overflow = 0;
+  DownsamplerView const view{1,
+                             n_points,
+                             tolerance,
+                             timeline_times.data(),
+                             points.data(),
+                             errors.data(),
+                             &count,
+                             &downsampling_error,
+                             a2a3.data(),
+                             &overflow};
+  for (int64_t i = 0; i < n_points; ++i) {
+    DownsamplerAppend(view, 0, times[i],
+                      Vec3{q[3 * i], q[3 * i + 1], q[3 * i + 2]},
+                      Vec3{v[3 * i], v[3 * i + 1], v[3 * i + 2]});
+  }
+  for (long long k = 0; k < count; ++k) {
+    kept_times[k] = timeline_times[k];
+    for (int c = 0; c < 3; ++c) {
+      kept_q[3 * k + c] = points[6 * k + c];
+      kept_v[3 * k + c] = points[6 * k + 3 + c];
+    }
+    kept_errors[k] = errors[k];
+  }
+  return overflow != 0 ? -1 : count;
+}
 void hc_chebyshev(double const* c, int32_t degree, double lower, double upper,
                   double t, double* value, double* derivative) {
   double const one_over_width = 1 / (upper - lower);

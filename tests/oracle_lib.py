@@ -26,6 +26,8 @@ _SYMBOLS = [
     ('orc_cr_cos', _d, [_d]),
     ('orc_root', _d, [_i32, _d]),
     ('orc_estrin', _d, [_dp, _i32, _d]),
+    ('orc_downsample', _i64,
+     [_i64, _dp, _dp, _dp, _d, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp]),
     ('orc_chebyshev_evaluate', _d, [_dp, _i32, _d, _d, _d]),
     ('orc_chebyshev_evaluate_derivative', _d, [_dp, _i32, _d, _d, _d]),
     ('orc_newhall_fit', _i32,

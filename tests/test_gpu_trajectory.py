@@ -1,0 +1,93 @@
+"""GPU parity of the trajectory sink:
+DiscreteTrajectorySegment::Append with downsampling on the device against the
+oracle, bit for bit, on the reference's own test trajectories and on the states
+appended by the flows."""
+import numpy as np
+import pytest
+
+from principia_b200 import _capi
+from principia_b200 import workloads
+from principia_b200.trajectory import Downsampler
+
+import trajectory_factories
+from conftest import assert_bitwise_equal
+from test_oracle_kats import oracle_downsample
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_circle_and_straight_line():
+  """physics/discrete_trajectory_segment_test.cpp:252-324: 1001 points on a
+  circle are downsampled to 49, on a straight line to 2 (tolerance 1 mm); both
+  trajectories go through one batch."""
+  circle = trajectory_factories.circular_timeline(3.0, 2.0, 10e-3, 0.0, 10.0)
+  line = trajectory_factories.linear_timeline([1.0, 2.0, 3.0], 10e-3, 0.0,
+                                              10.0)
+  assert_bitwise_equal(circle[0], line[0])  # The same times.
+  times = circle[0]
+  samples = np.zeros((len(times), 6, 2))
+  for k, (_, q, v) in enumerate((circle, line)):
+    samples[:, 0:3, k] = q
+    samples[:, 3:6, k] = v
+  downsampler = Downsampler(2, 1e-3, 64)
+  # In three calls: the state of the segments persists on the device.
+  for begin, end in ((0, 1), (1, 400), (400, len(times))):
+    downsampler.append(times[begin:end], samples[begin:end])
+  counts, kept_times, points, errors = downsampler.timelines()
+  assert list(counts) == [49, 2]
+  for k, (_, q, v) in enumerate((circle, line)):
+    expected = oracle_downsample(times, q, v, 1e-3)
+    c = counts[k]
+    assert_bitwise_equal(kept_times[:c, k], expected['times'])
+    assert_bitwise_equal(points[:c, 0:3, k], expected['q'])
+    assert_bitwise_equal(points[:c, 3:6, k], expected['v'])
+    assert_bitwise_equal(errors[:c, k], expected['errors'])
+
+
+def test_flow_samples_are_downsampled_like_the_oracle(sol_system, sol_gpu):
+  """The plugin's history: Quinlan1999Order8A at 10 s, downsampled with the
+  default tolerance of 10 m (ksp_plugin/integrators.cpp:23-29)."""
+  n = 300
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  state = workloads.leo_probes(n, earth['q'], earth['v'], earth['mu'], 77)
+  time = np.zeros(2)
+  first = np.concatenate([state[0:3], state[6:9]])[None]
+  result = sol_gpu.flow_with_fixed_step(_capi.QUINLAN_1999_ORDER_8A, 10.0,
+                                        6000.0, state, time, sample_every=1,
+                                        max_samples=600)
+  assert len(result['samples']) == 600
+  times = np.concatenate([[0.0], result['sample_times']])
+  samples = np.concatenate([first, result['samples']])
+  downsampler = Downsampler(n, 10.0, 601)
+  downsampler.append(times, samples)
+  counts, kept_times, points, errors = downsampler.timelines()
+  assert 10 < counts.min() and counts.max() < 300
+  for k in range(0, n, 7):
+    expected = oracle_downsample(
+        times, np.ascontiguousarray(samples[:, 0:3, k]),
+        np.ascontiguousarray(samples[:, 3:6, k]), 10.0)
+    c = counts[k]
+    assert c == len(expected['times'])
+    assert_bitwise_equal(kept_times[:c, k], expected['times'])
+    assert_bitwise_equal(points[:c, 0:3, k], expected['q'])
+    assert_bitwise_equal(points[:c, 3:6, k], expected['v'])
+    assert_bitwise_equal(errors[:c, k], expected['errors'])
+
+
+def test_capacity_overflow_is_reported():
+  circle = trajectory_factories.circular_timeline(3.0, 2.0, 10e-3, 0.0, 10.0)
+  times, q, v = circle
+  samples = np.zeros((len(times), 6, 1))
+  samples[:, 0:3, 0] = q
+  samples[:, 3:6, 0] = v
+  downsampler = Downsampler(1, 1e-3, 20)
+  downsampler.append(times, samples)
+  from principia_b200.ephemeris import StatusError
+  with pytest.raises(StatusError):
+    downsampler.timelines()
+  # No downsampling: every point is kept.
+  downsampler = Downsampler(1, -1.0, 1001)
+  downsampler.append(times, samples)
+  counts, kept_times, _, _ = downsampler.timelines()
+  assert counts[0] == 1001
+  assert_bitwise_equal(kept_times[:, 0], times)

@@ -37,6 +37,9 @@ def hc():
   lib.hc_estrin.argtypes = [_dp, _i32, _d]
   lib.hc_estrin_padded.argtypes = [_dp, _i32, _d, _d, _dp, _dp]
   lib.hc_chebyshev.argtypes = [_dp, _i32, _d, _d, _d, _dp, _dp]
+  lib.hc_downsample.restype = ctypes.c_int64
+  lib.hc_downsample.argtypes = [ctypes.c_int64, _dp, _dp, _dp, _d, _dp, _dp,
+                                _dp, _dp]
   lib.hc_pow_int.restype = _d
   lib.hc_pow_int.argtypes = [_d, _i32]
   lib.hc_model_create.argtypes = [_i32, ctypes.POINTER(_capi.Body), _d,
@@ -117,6 +120,54 @@ def test_chebyshev_series_match_oracle(hc):
           oracle_lib.dptr(c), degree, lower, upper, t)
       assert derivative.value == orc.orc_chebyshev_evaluate_derivative(
           oracle_lib.dptr(c), degree, lower, upper, t)
+
+
+def test_downsampling_matches_oracle(hc):
+  """DownsamplerAppend (pb_downsampling.cuh, compiled for the host) against the
+  oracle's DiscreteTrajectorySegment, bit for bit: the reference's circle and
+  straight line, a Kepler ellipse with an uneven cadence, several tolerances."""
+  import trajectory_factories
+  from test_oracle_kats import oracle_downsample
+  cases = [trajectory_factories.circular_timeline(3.0, 2.0, 10e-3, 0.0, 10.0),
+           trajectory_factories.linear_timeline([1.0, 2.0, 3.0], 10e-3, 0.0,
+                                                10.0)]
+  rng = np.random.default_rng(21)
+  mu, a, e = 3.986e14, 8.0e6, 0.3
+  mean_motion = math.sqrt(mu / a**3)
+  times = np.cumsum(rng.uniform(5.0, 15.0, 600))
+  q, v = [], []
+  for t in times:
+    M = mean_motion * t
+    E = M
+    for _ in range(50):
+      E = M + e * math.sin(E)
+    r = a * (1 - e * math.cos(E))
+    q.append([a * (math.cos(E) - e), a * math.sqrt(1 - e * e) * math.sin(E),
+              0.1 * t])
+    v.append([-a * a * mean_motion / r * math.sin(E),
+              a * a * mean_motion / r * math.sqrt(1 - e * e) * math.cos(E),
+              0.1])
+  cases.append((times, np.array(q), np.array(v)))
+  sizes = []
+  for times, q, v in cases:
+    for tolerance in (1e-3, 10.0, 1e4, -1.0):
+      expected = oracle_downsample(times, q, v, tolerance)
+      n = len(times)
+      kept_times, kept_errors = np.zeros(n), np.zeros(n)
+      kept_q, kept_v = np.zeros((n, 3)), np.zeros((n, 3))
+      dptr = oracle_lib.dptr
+      count = hc.hc_downsample(
+          n, dptr(np.ascontiguousarray(times)), dptr(np.ascontiguousarray(q)),
+          dptr(np.ascontiguousarray(v)), tolerance, dptr(kept_times),
+          dptr(kept_q), dptr(kept_v), dptr(kept_errors))
+      assert count == len(expected['times'])
+      sizes.append(count)
+      assert kept_times[:count].tobytes() == expected['times'].tobytes()
+      assert kept_q[:count].tobytes() == expected['q'].tobytes()
+      assert kept_v[:count].tobytes() == expected['v'].tobytes()
+      assert kept_errors[:count].tobytes() == expected['errors'].tobytes()
+  assert sizes[0] == 49 and sizes[3] == 1001 and sizes[4] == 2
+  assert sizes[11] == 600 and 2 < sizes[9] < 600
 
 
 def test_padded_estrin_tree_equals_the_reference_tree(hc):

@@ -345,6 +345,56 @@ def test_chebyshev_series_known_answers():
           oracle_lib.dptr(c), degree, lower, upper, argument) == expected
 
 
+def oracle_downsample(times, q, v, tolerance, evaluation_times=None):
+  orc = oracle_lib.library()
+  n = len(times)
+  times = np.ascontiguousarray(times)
+  q = np.ascontiguousarray(q)
+  v = np.ascontiguousarray(v)
+  kept_times, kept_errors = np.zeros(n), np.zeros(n)
+  kept_q, kept_v = np.zeros((n, 3)), np.zeros((n, 3))
+  m = 0 if evaluation_times is None else len(evaluation_times)
+  evaluation_times = np.ascontiguousarray(
+      np.zeros(1) if evaluation_times is None else evaluation_times)
+  evaluated_q, evaluated_v = np.zeros((max(m, 1), 3)), np.zeros((max(m, 1), 3))
+  dptr = oracle_lib.dptr
+  count = orc.orc_downsample(n, dptr(times), dptr(q), dptr(v), tolerance,
+                             dptr(kept_times), dptr(kept_q), dptr(kept_v),
+                             dptr(kept_errors), m, dptr(evaluation_times),
+                             dptr(evaluated_q), dptr(evaluated_v))
+  return dict(times=kept_times[:count], q=kept_q[:count], v=kept_v[:count],
+              errors=kept_errors[:count], evaluated_q=evaluated_q[:m],
+              evaluated_v=evaluated_v[:m])
+
+
+def is_near(value, expected, digits=2):
+  """IsNear(x_(1)): equal when rounded to the digits given."""
+  return float('%.*g' % (digits, value)) == float('%.*g' % (digits, expected))
+
+
+# physics/discrete_trajectory_segment_test.cpp:252-324.
+def test_downsampling_circle_and_straight_line():
+  import trajectory_factories
+  times, q, v = trajectory_factories.circular_timeline(3.0, 2.0, 10e-3, 0.0,
+                                                       10.0)
+  assert len(times) == 1001
+  result = oracle_downsample(times, q, v, 1e-3, evaluation_times=times)
+  assert len(result['times']) == 49
+  position_errors = np.linalg.norm(result['evaluated_q'] - q, axis=1)
+  velocity_errors = np.linalg.norm(result['evaluated_v'] - v, axis=1)
+  assert is_near(position_errors.max(), 0.81e-3)
+  assert is_near(velocity_errors.max(), 12e-3)
+  times, q, v = trajectory_factories.linear_timeline([1.0, 2.0, 3.0], 10e-3,
+                                                     0.0, 10.0)
+  assert len(times) == 1001
+  result = oracle_downsample(times, q, v, 1e-3, evaluation_times=times)
+  assert len(result['times']) == 2
+  position_errors = np.linalg.norm(result['evaluated_q'] - q, axis=1)
+  velocity_errors = np.linalg.norm(result['evaluated_v'] - v, axis=1)
+  assert is_near(position_errors.max(), 1.1e-14)
+  assert is_near(velocity_errors.max(), 2.2e-15)
+
+
 def test_internal_body_order():
   system = SolarSystem.from_fixture('sol_jd2451545')
   ephemeris = OracleEphemeris(system)
