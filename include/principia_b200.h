@@ -234,6 +234,15 @@ pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* instance,
                                         double* sample_times,
                                         int64_t* n_steps, int64_t* n_samples,
                                         pb_status_t* flow_status);
+/* FlowWithFixedStep(t_final, instance) with a trajectory sink on the device:
+ * every appended state goes to `downsampler` (pb_downsampler_*, below) in
+ * chunks, nothing travels to the host.  Append the initial state first if the
+ * timelines are to start with it. */
+typedef struct pb_downsampler pb_downsampler_t;
+pb_status_t pb_fixed_step_instance_flow_to_downsampler(
+    pb_fixed_step_instance_t* instance, double t_final,
+    pb_downsampler_t* downsampler, int64_t* n_steps,
+    pb_status_t* flow_status);
 /* instance.state(): 12 planes of n and the time {value, error}; either may be
  * NULL. */
 pb_status_t pb_fixed_step_instance_get_state(
@@ -362,7 +371,6 @@ double pb_nbody_allpairs_last_force_ms(const pb_nbody_allpairs_t* system);
  * error of the Hermite interpolation (numerics/hermite3_body.hpp:154-194)
  * stays below `tolerance` (negative: no downsampling).  Each timeline holds at
  * most `capacity` points. */
-typedef struct pb_downsampler pb_downsampler_t;
 pb_status_t pb_downsampler_create(int32_t cuda_device, int64_t n,
                                   double tolerance, int64_t capacity,
                                   pb_downsampler_t** downsampler);

@@ -128,6 +128,8 @@ SYMBOLS = [
     ('pb_fixed_step_instance_flow', _i32,
      [_vp, _d, _i64, _i64, c_double_p, c_double_p, c_int64_p, c_int64_p,
       c_int32_p]),
+    ('pb_fixed_step_instance_flow_to_downsampler', _i32,
+     [_vp, _d, _vp, c_int64_p, c_int32_p]),
     ('pb_fixed_step_instance_get_state', _i32, [_vp, c_double_p, c_double_p]),
     ('pb_flow_with_adaptive_step', _i32,
      [_vp, ctypes.POINTER(AdaptiveStepFlow)]),

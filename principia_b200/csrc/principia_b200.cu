@@ -1208,6 +1208,82 @@ pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* s,
   return PB_OK;
 }
 
+pb_status_t pb_fixed_step_instance_flow_to_downsampler(
+    pb_fixed_step_instance_t* s, double t_final,
+    pb_downsampler_t* downsampler, int64_t* n_steps,
+    pb_status_t* flow_status) {
+  if (s == nullptr || downsampler == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  pb_ephemeris* const e = s->ephemeris;
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = nullptr;
+  std::size_t const n = static_cast<std::size_t>(s->n);
+  // States per chunk: at most 64 MiB of samples on the device.
+  long long const chunk = std::max<long long>(
+      1, std::min<long long>(256, (64LL << 20) / (48 * std::max<long long>(
+                                                           1, s->n))));
+  // Two spare slots: the time bound below admits one more state when the
+  // instance sits between two steps of a multistep startup.
+  long long const slots = chunk + 2;
+  PB_RETURN_IF_ERROR(
+      e->scratch_c.Reserve(static_cast<std::size_t>(slots) * 6 * n + 1));
+  PB_RETURN_IF_ERROR(e->pinned_status.Reserve(1));
+  PB_RETURN_IF_ERROR(e->status_word.Reserve(1));
+  std::vector<double> sample_times(slots);
+  int64_t total_steps = 0;
+  pb_status_t overall = PB_OK;
+  double const abs_step = std::abs(s->step);
+  for (;;) {
+    // Instance::Solve(t) for the next `chunk` steps at most; during the startup
+    // of a multistep instance only every 16th step of the starter is appended,
+    // hence the bound on the time rather than on the steps.
+    double const remaining = (t_final - s->time.value) - s->time.error;
+    if (!(abs_step <= std::abs(remaining))) {
+      break;
+    }
+    double t_chunk = s->time.value + (s->step > 0 ? 1 : -1) *
+                                         (static_cast<double>(chunk) + 0.5) *
+                                         abs_step;
+    if (s->step > 0 ? t_chunk > t_final : t_chunk < t_final) {
+      t_chunk = t_final;
+    }
+    pb_fixed_step_flow_t flow{};
+    flow.t_final = t_chunk;
+    flow.sample_every = 1;
+    flow.max_samples = slots;
+    flow.samples = e->scratch_c.data;
+    flow.sample_times = sample_times.data();
+    int64_t steps = 0, recorded = 0;
+    pb_status_t status = PB_OK;
+    flow.n_steps = &steps;
+    flow.n_samples = &recorded;
+    flow.status = &status;
+    DP const before = s->time;
+    PB_RETURN_IF_ERROR(SolveInstance(s, &flow, stream));
+    if (recorded != steps) {
+      return Fail(PB_INTERNAL, "more states appended than the chunk holds");
+    }
+    PB_RETURN_IF_ERROR(pb_downsampler_append_device(
+        downsampler, recorded, sample_times.data(), e->scratch_c.data,
+        stream));
+    total_steps += steps;
+    if (overall == PB_OK) {
+      overall = status;
+    }
+    if (s->time.value == before.value && s->time.error == before.error) {
+      break;  // No progress: t_final is closer than one step.
+    }
+  }
+  if (n_steps != nullptr) {
+    *n_steps = total_steps;
+  }
+  if (flow_status != nullptr) {
+    *flow_status = overall;
+  }
+  return PB_OK;
+}
+
 pb_status_t pb_fixed_step_instance_get_state(pb_fixed_step_instance_t* s,
                                              double* state, double* time) {
   if (s == nullptr) {

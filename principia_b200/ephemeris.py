@@ -268,6 +268,16 @@ class FixedStepInstance:
                 sample_times=None if samples is None
                 else sample_times[:n_samples.value])
 
+  def flow_to_downsampler(self, t_final, downsampler):
+    """flow(t_final) with every appended state going to a
+    trajectory.Downsampler on the device."""
+    n_steps = ctypes.c_int64()
+    status = ctypes.c_int32()
+    _check(self.lib.pb_fixed_step_instance_flow_to_downsampler(
+        self.handle, t_final, downsampler.handle, ctypes.byref(n_steps),
+        ctypes.byref(status)))
+    return dict(n_steps=n_steps.value, status=status.value)
+
   def state(self):
     """(state (12, n), time (2,)) of the instance."""
     state = np.zeros((12, self.n))

@@ -74,6 +74,47 @@ def test_flow_samples_are_downsampled_like_the_oracle(sol_system, sol_gpu):
     assert_bitwise_equal(errors[:c, k], expected['errors'])
 
 
+@pytest.mark.parametrize('method', [_capi.QUINLAN_1999_ORDER_8A,
+                                    _capi.BLANES_MOAN_2002_SRKN_14A])
+def test_instance_flows_into_the_device_sink(sol_system, sol_gpu, method):
+  """FlowWithFixedStep with the sink on the device (nothing travels to the
+  host) gives the timelines of flow-then-append."""
+  n = 200
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  state = workloads.leo_probes(n, earth['q'], earth['v'], earth['mu'], 78)
+  first = np.concatenate([state[0:3], state[6:9]])[None]
+  t_final = 5005.0
+  # Reference: all the samples through the host.
+  instance = sol_gpu.new_instance(method, 10.0, state, np.zeros(2))
+  result = instance.flow(t_final, sample_every=1, max_samples=1000)
+  assert result['n_steps'] == 500
+  expected = Downsampler(n, 10.0, 501)
+  expected.append(np.concatenate([[0.0], result['sample_times']]),
+                  np.concatenate([first, result['samples']]))
+  # Device sink, in two calls (the second one crosses chunk boundaries).
+  instance = sol_gpu.new_instance(method, 10.0, state, np.zeros(2))
+  sink = Downsampler(n, 10.0, 501)
+  sink.append([0.0], first)
+  steps = instance.flow_to_downsampler(45.0, sink)['n_steps']
+  steps += instance.flow_to_downsampler(t_final, sink)['n_steps']
+  assert steps == 500
+  counts, times, points, errors = sink.timelines()
+  wanted_counts, wanted_times, wanted_points, wanted_errors = (
+      expected.timelines())
+  assert list(counts) == list(wanted_counts)
+  # Slots beyond the size of a timeline are unspecified.
+  valid = np.arange(501)[:, None] < counts[None, :]
+  assert_bitwise_equal(np.where(valid, times, 0.0),
+                       np.where(valid, wanted_times, 0.0), 'times')
+  assert_bitwise_equal(np.where(valid, errors, 0.0),
+                       np.where(valid, wanted_errors, 0.0), 'errors')
+  assert_bitwise_equal(np.where(valid[:, None, :], points, 0.0),
+                       np.where(valid[:, None, :], wanted_points, 0.0),
+                       'points')
+  final_state, final_time = instance.state()
+  assert final_time[0] == 5000.0
+
+
 def test_capacity_overflow_is_reported():
   circle = trajectory_factories.circular_timeline(3.0, 2.0, 10e-3, 0.0, 10.0)
   times, q, v = circle
