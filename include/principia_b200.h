@@ -280,6 +280,10 @@ typedef struct pb_adaptive_step_flow_t {
    * states of each probe (what append_state hands to
    * DiscreteTrajectory::Append): state_log[k][6][n]. */
   double* state_log;    /* step_log_capacity * 6 * n */
+  /* If != NULL, every accepted state of probe i is appended to timeline i of
+   * this trajectory sink (pb_downsampler_*, n trajectories) inside the kernel:
+   * the DiscreteTrajectory the reference flows. */
+  struct pb_downsampler* sink;
 } pb_adaptive_step_flow_t;
 pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* ephemeris,
                                        const pb_adaptive_step_flow_t* flow);

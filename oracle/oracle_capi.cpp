@@ -583,6 +583,13 @@ int32_t orc_flow_with_adaptive_step(orc_ephemeris* e,
       if (flow->step_log != nullptr && accepted < flow->step_log_capacity) {
         flow->step_log[accepted * n + i] = s.time.value;
       }
+      if (flow->state_log != nullptr && accepted < flow->step_log_capacity) {
+        double* const out = flow->state_log + accepted * 6 * n;
+        for (int c = 0; c < 3; ++c) {
+          out[c * n + i] = s.positions[c].value;
+          out[(3 + c) * n + i] = s.velocities[c].value;
+        }
+      }
       ++accepted;
     };
     int32_t const status = e->e->FlowWithAdaptiveStep(

@@ -85,6 +85,7 @@ class AdaptiveStepFlow(ctypes.Structure):
       ('step_log_capacity', ctypes.c_int64),
       ('step_log', ctypes.c_void_p),
       ('state_log', ctypes.c_void_p),
+      ('sink', ctypes.c_void_p),
   ]
 
 

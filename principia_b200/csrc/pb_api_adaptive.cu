@@ -119,6 +119,14 @@ pb_status_t pb_flow_with_adaptive_step_device(
     e->timing_events.push_back(event);
   }
   PB_CUDA(cudaEventRecord(e->timing_events[0], stream));
+  DownsamplerView sink{};
+  if (flow->sink != nullptr) {
+    sink = PbDownsamplerView(flow->sink);
+    if (sink.n != flow->n) {
+      return Fail(PB_INVALID_ARGUMENT,
+                  "the sink must have one timeline per trajectory");
+    }
+  }
   auto const kernel =
       min_blocks == 2 ? ErknFlowKernel<2> : ErknFlowKernel<3>;
   kernel<<<blocks, kAdaptiveThreads, 0, stream>>>(
@@ -127,7 +135,7 @@ pb_status_t pb_flow_with_adaptive_step_device(
       reinterpret_cast<long long*>(flow->accepted_steps),
       reinterpret_cast<long long*>(flow->rejected_steps),
       reinterpret_cast<long long*>(flow->evaluations), flow->step_log,
-      flow->state_log);
+      flow->state_log, sink);
   PB_LAUNCHED();
   PB_CUDA(cudaEventRecord(e->timing_events[1], stream));
   PB_CUDA(cudaStreamSynchronize(stream));

@@ -29,6 +29,10 @@ struct pb_downsampler {
   }
 };
 
+pb::DownsamplerView PbDownsamplerView(pb_downsampler* const downsampler) {
+  return downsampler->View();
+}
+
 namespace {
 
 // One thread per trajectory; the samples of a trajectory are appended in

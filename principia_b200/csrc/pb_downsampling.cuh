@@ -240,3 +240,8 @@ PB_HD void DownsamplerAppend(DownsamplerView const& d, long long const i,
 }
 
 }  // namespace pb
+
+// Defined in pb_api_trajectory.cu: the view of a pb_downsampler_t for kernels
+// of other translation units.
+struct pb_downsampler;
+pb::DownsamplerView PbDownsamplerView(pb_downsampler* downsampler);

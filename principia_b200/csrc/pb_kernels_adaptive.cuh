@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #include "pb_accel.cuh"
+#include "pb_downsampling.cuh"
 #include "pb_model.h"
 
 namespace pb {
@@ -178,6 +179,14 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
   return error;
 }
 
+// append_state into the trajectory sink, out of line (a few hundred
+// instructions that run once per accepted step).
+__device__ __noinline__ void AppendToSink(DownsamplerView const& sink,
+                                          long long const i, double const t,
+                                          Vec3 const& q, Vec3 const& v) {
+  DownsamplerAppend(sink, i, t, q, v);
+}
+
 // Scheduling key of a trajectory: an estimate of its number of steps, from the
 // osculating orbit around the body with the strongest tide at the initial
 // state.  With a 4th-order error estimate the step scales like
@@ -244,7 +253,7 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                long long* __restrict__ rejected_out,
                long long* __restrict__ evaluations_out,
                double* __restrict__ step_log,
-               double* __restrict__ state_log) {
+               double* __restrict__ state_log, DownsamplerView const sink) {
   // DormandالمكاوىPrince1986RKN434FM, methods.hpp:574-597.
   constexpr double c1 = 1.0 / 4.0, c2 = 7.0 / 10.0, c3 = 1.0;
   constexpr double a10 = 1.0 / 32.0;
@@ -432,6 +441,10 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
               out[(3 + k) * n + i] = v[k].value;
             }
           }
+        }
+        if (sink.n > 0) {
+          AppendToSink(sink, i, t.value, Vec3{q[0].value, q[1].value, q[2].value},
+                       Vec3{v[0].value, v[1].value, v[2].value});
         }
         ++accepted;
         if (at_end) {

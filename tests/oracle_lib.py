@@ -253,7 +253,8 @@ class OracleEphemeris:
 
   def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
                               speed_tolerance, max_steps=2**62,
-                              step_log_capacity=0, threads=0):
+                              step_log_capacity=0, threads=0,
+                              state_log=False):
     """state: (12, n), time: (2, n); updated in place."""
     n = state.shape[1]
     flow = _capi.AdaptiveStepFlow()
@@ -278,10 +279,14 @@ class OracleEphemeris:
       step_log = np.full((step_log_capacity, n), np.nan)
       flow.step_log_capacity = step_log_capacity
       flow.step_log = step_log.ctypes.data
+    states = None
+    if state_log and step_log_capacity > 0:
+      states = np.full((step_log_capacity, 6, n), np.nan)
+      flow.state_log = states.ctypes.data
     self.lib.orc_flow_with_adaptive_step(self.handle, ctypes.byref(flow),
                                          threads)
     return dict(status=status, accepted=accepted, rejected=rejected,
-                evaluations=evaluations, step_log=step_log)
+                evaluations=evaluations, step_log=step_log, state_log=states)
 
   def nbody_ensemble_flow(self, method, step, state, time, t_final, threads=0):
     """state: (12, n_bodies, n_systems) internal order; in place."""

@@ -9,6 +9,7 @@ from principia_b200 import _capi
 from principia_b200 import workloads
 from principia_b200.trajectory import Downsampler
 
+import oracle_lib
 import trajectory_factories
 from conftest import assert_bitwise_equal
 from test_oracle_kats import oracle_downsample
@@ -113,6 +114,53 @@ def test_instance_flows_into_the_device_sink(sol_system, sol_gpu, method):
                        'points')
   final_state, final_time = instance.state()
   assert final_time[0] == 5000.0
+
+
+def test_adaptive_flow_appends_to_the_sink_in_the_kernel(sol_system,
+                                                         sol_oracle, sol_gpu):
+  """FlowWithAdaptiveStep into a DiscreteTrajectory with the plugin's default
+  downsampling: every accepted state goes through Append inside the kernel.
+  Expected: the oracle's accepted states (its step log) through the oracle's
+  DiscreteTrajectorySegment."""
+  n = 64
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  state = workloads.eccentric_probes(n, earth['q'], earth['v'], earth['mu'],
+                                     13)
+  first = np.concatenate([state[0:3], state[6:9]])[None]
+  t_final = 20000.0
+  capacity = 4000
+  sink = Downsampler(n, 10.0, capacity)
+  sink.append([0.0], first)
+  gpu_state, gpu_time = state.copy(), np.zeros((2, n))
+  result = sol_gpu.flow_with_adaptive_step(t_final, gpu_state, gpu_time, 1e-3,
+                                           1e-3, sink=sink)
+  assert np.all(result['status'] == 0)
+  counts, times, points, errors = sink.timelines()
+  # The oracle, one probe at a time, with the states of its accepted steps.
+  orc = oracle_lib.library()
+  checked = 0
+  for k in range(0, n, 5):
+    accepted = int(result['accepted'][k])
+    expected_state = np.ascontiguousarray(state[:, k:k + 1])
+    expected_time = np.zeros((2, 1))
+    flow = sol_oracle.flow_with_adaptive_step(
+        t_final, expected_state, expected_time, 1e-3, 1e-3,
+        step_log_capacity=accepted, state_log=True)
+    assert int(flow['accepted'][0]) == accepted
+    log_times = np.concatenate([[0.0], flow['step_log'][:accepted, 0]])
+    log_q = np.concatenate([first[0, 0:3, k][None],
+                            flow['state_log'][:accepted, 0:3, 0]])
+    log_v = np.concatenate([first[0, 3:6, k][None],
+                            flow['state_log'][:accepted, 3:6, 0]])
+    expected = oracle_downsample(log_times, log_q, log_v, 10.0)
+    c = counts[k]
+    assert c == len(expected['times']) < accepted + 1
+    assert_bitwise_equal(times[:c, k], expected['times'])
+    assert_bitwise_equal(points[:c, 0:3, k], expected['q'])
+    assert_bitwise_equal(points[:c, 3:6, k], expected['v'])
+    assert_bitwise_equal(errors[:c, k], expected['errors'])
+    checked += 1
+  assert checked == 13
 
 
 def test_capacity_overflow_is_reported():
