@@ -68,14 +68,24 @@ def bench_adaptive(args):
       dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    sink = None
+    if args.sink_capacity > 0:
+      # The plugin's default downsampling (10 m) applied inside the kernel.
+      from principia_b200.trajectory import Downsampler
+      sink = Downsampler(n, 10.0, args.sink_capacity, device=local_rank)
+      sink.append([0.0], np.concatenate([state[0:3], state[6:9]])[None])
     result = ephemeris.flow_with_adaptive_step(t_final, state, times, 1e-3,
-                                               1e-3)
+                                               1e-3, sink=sink)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     kernel_ms, _ = ephemeris.last_flow_kernel_ms()
     results.append((wall, kernel_ms, result))
   wall, kernel_ms, result = results[-1]
   assert np.all(result['status'] == 0)
+  timeline_points = None
+  if sink is not None:
+    counts = sink.timelines()[0]
+    timeline_points = float(counts.mean())
   kernel_s = max_over_ranks(torch, dist, world, kernel_ms * 1e-3, device)
   wall = max_over_ranks(torch, dist, world, wall, device)
   steps = sum_over_ranks(torch, dist, world, float(result['accepted'].sum()),
@@ -92,7 +102,8 @@ def bench_adaptive(args):
         'probe_rkn_stages_per_second': evaluations / kernel_s,
         'e2e_probe_rkn_stages_per_second': evaluations / wall,
         'mean_steps_per_probe': steps / (n * world),
-        'max_steps_per_probe': int(result['accepted'].max())}))
+        'max_steps_per_probe': int(result['accepted'].max()),
+        'sink_mean_timeline_points': timeline_points}))
 
 
 def bench_history(args):
@@ -251,6 +262,7 @@ def main():
   parser.add_argument('--systems', type=int, default=100000)
   parser.add_argument('--steps', type=int, default=20)
   parser.add_argument('--bodies', type=int, default=2**17)
+  parser.add_argument('--sink-capacity', type=int, default=0)
   args = parser.parse_args()
   if args.config in ('adaptive', 'all'):
     bench_adaptive(args)
