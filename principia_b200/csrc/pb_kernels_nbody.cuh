@@ -319,11 +319,11 @@ EnsembleMultistepStepKernel(
     int const slot = oldest + j;
     return slot >= k ? slot - k : slot;
   };
-  // The new displacements are kept until the old slot may be overwritten; the
-  // accelerations of the history feed both the position and the velocity.
-  DP new_displacement[kOwn][3];
-  double old_acceleration[kOwn][3][k];
-  DP previous_displacement[kOwn][3];
+  // Nothing but indices is live across the right-hand side: the new
+  // displacement goes straight into the ring slot of the oldest step (whose
+  // data this thread has just consumed), and the velocity formula reads the
+  // history again (L2) instead of holding 36 doubles in spilled registers.
+  int const newest = oldest;
 #pragma unroll
   for (int o = 0; o < kOwn; ++o) {
     int const b = warp + o * warps;
@@ -331,15 +331,14 @@ EnsembleMultistepStepKernel(
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         DP displacement[k];
+        double acceleration[k];
 #pragma unroll
         for (int j = 0; j < k; ++j) {
           long long const hi = HistoryIndex(slot_of(j), c, b, n, n_systems, s);
           displacement[j] = {history.displacement_value[hi],
                              history.displacement_error[hi]};
-          old_acceleration[o][c][j] = history.acceleration[hi];
+          acceleration[j] = history.acceleration[hi];
         }
-        previous_displacement[o][c] = displacement[k - 1];
-        double const* const acceleration = old_acceleration[o][c];
         // j = 0.
         DP sum = Scale(-method.alpha[0], displacement[0]);
         double weighted = method.beta_numerator[0] * acceleration[0];
@@ -355,11 +354,13 @@ EnsembleMultistepStepKernel(
         sum = Subtract(sum, Scale(method.alpha[k / 2], displacement[k / 2]));
         weighted += method.beta_numerator[k / 2] * acceleration[k / 2];
         Increment(sum, h * h * weighted / method.beta_denominator);
-        new_displacement[o][c] = sum;
         DP const current_position = Add(DP{0.0, 0.0}, sum);
         positions[(3 * b + c) * kEnsembleLanes + lane] =
             current_position.value;
         if (active) {
+          long long const hi = HistoryIndex(newest, c, b, n, n_systems, s);
+          history.displacement_value[hi] = sum.value;
+          history.displacement_error[hi] = sum.error;
           state[EnsembleIndex(c, b, n, n_systems, s)] = current_position.value;
           state[EnsembleIndex(3 + c, b, n, n_systems, s)] =
               current_position.error;
@@ -369,7 +370,6 @@ EnsembleMultistepStepKernel(
   }
   __syncthreads();
   // Push: the new step replaces the oldest one and becomes previous_steps.back.
-  int const newest = oldest;
 #pragma unroll
   for (int o = 0; o < kOwn; ++o) {
     int const b = warp + o * warps;
@@ -381,24 +381,29 @@ EnsembleMultistepStepKernel(
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           long long const hi = HistoryIndex(newest, c, b, n, n_systems, s);
-          DP const displacement = new_displacement[o][c];
-          history.displacement_value[hi] = displacement.value;
-          history.displacement_error[hi] = displacement.error;
-          history.acceleration[hi] = a[c];
+          DP const displacement{history.displacement_value[hi],
+                                history.displacement_error[hi]};
           // Velocity; previous_steps.back() before the push is j = k - 1.
-          DP const displacement_change =
-              Subtract(displacement, previous_displacement[o][c]);
+          long long const pi =
+              HistoryIndex(slot_of(k - 1), c, b, n, n_systems, s);
+          DP const displacement_change = Subtract(
+              displacement, DP{history.displacement_value[pi],
+                               history.displacement_error[pi]});
           double velocity =
               (displacement_change.value + displacement_change.error) / h;
           double weighted_accelerations = 0.0;
 #pragma unroll
           for (int i = 0; i < k; ++i) {
             // it = previous_steps.rbegin() + i: the newest step first, then
-            // the old steps j = k - 1, k - 2, ... 1 (j = 0 was overwritten).
-            double const ai = i == 0 ? a[c] : old_acceleration[o][c][k - i];
+            // the old steps j = k - 1, k - 2, ... 1 (j = 0 is overwritten).
+            double const ai =
+                i == 0 ? a[c]
+                       : history.acceleration[HistoryIndex(
+                             slot_of(k - i), c, b, n, n_systems, s)];
             weighted_accelerations += method.cho_numerators[i] * ai;
           }
           velocity += weighted_accelerations * h / method.cho_denominator;
+          history.acceleration[hi] = a[c];
           state[EnsembleIndex(6 + c, b, n, n_systems, s)] = velocity;
           state[EnsembleIndex(9 + c, b, n, n_systems, s)] = 0.0;
         }
