@@ -248,6 +248,24 @@ def test_collision_status_and_continuation(sol_system, sol_oracle, sol_gpu):
   assert_bitwise_equal(state, expected_state, 'collision state')
 
 
+def test_ten_thousand_fixed_steps_match_oracle(sol_system, sol_oracle,
+                                               sol_gpu):
+  """BASELINE.json's tolerance is a relative position error <= 1e-12 after
+  10^4 fixed steps; the flow is bit-identical to the oracle's after 10^4 steps
+  of SRKN14A at 10 s (27.8 h, 1.4e5 right-hand sides per probe, 40 launches)."""
+  method = _capi.BLANES_MOAN_2002_SRKN_14A
+  n = 48
+  state = leo(sol_system, n, seed=11)
+  expected_state = state.copy()
+  time, expected_time = np.zeros(2), np.zeros(2)
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 1.0e5, state, time)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, 1.0e5,
+                                             expected_state, expected_time)
+  assert result['n_steps'] == expected['n_steps'] == 10000
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'state after 10^4 steps')
+
+
 def test_full_size_flow_properties(sol_system, sol_oracle, sol_gpu):
   """BASELINE.json config 2 at full size (10^5 probes): size-independent
   properties -- probes are independent, so any subset equals the oracle bit for
