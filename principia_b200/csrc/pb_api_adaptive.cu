@@ -34,6 +34,7 @@ extern "C" {
 pb_status_t pb_flow_with_adaptive_step_device(
     pb_ephemeris_t* e, const pb_adaptive_step_flow_t* flow,
     void* stream_pointer) {
+  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
   if (e == nullptr || flow == nullptr || flow->n < 0 ||
       (flow->n > 0 && (flow->state == nullptr || flow->time == nullptr))) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
@@ -149,6 +150,7 @@ pb_status_t pb_flow_with_adaptive_step_device(
 
 pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
                                        const pb_adaptive_step_flow_t* flow) {
+  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
   if (e == nullptr || flow == nullptr || flow->n < 0 ||
       (flow->n > 0 && (flow->state == nullptr || flow->time == nullptr))) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");

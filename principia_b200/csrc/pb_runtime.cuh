@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,15 @@ inline std::atomic<std::int64_t>& LaunchCount() {
 inline std::uint64_t NextSerial() {
   static std::atomic<std::uint64_t> serial{0};
   return ++serial;
+}
+
+// The flow entry points share the constant bank of their kernels (per-body
+// scalars, hot-body tables) and the scratch buffers of the ephemeris: they are
+// serialised.  (The reference lets flows on distinct objects run concurrently,
+// ephemeris.hpp:64-66; here concurrency is inside a call, across the probes.)
+inline std::recursive_mutex& FlowMutex() {
+  static std::recursive_mutex mutex;
+  return mutex;
 }
 
 inline pb_status_t Fail(pb_status_t const status, std::string const& message) {

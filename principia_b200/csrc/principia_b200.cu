@@ -1169,6 +1169,7 @@ pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* s,
                                         double* sample_times,
                                         int64_t* n_steps, int64_t* n_samples,
                                         pb_status_t* flow_status) {
+  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
   if (s == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null instance");
   }
@@ -1212,6 +1213,7 @@ pb_status_t pb_fixed_step_instance_flow_to_downsampler(
     pb_fixed_step_instance_t* s, double t_final,
     pb_downsampler_t* downsampler, int64_t* n_steps,
     pb_status_t* flow_status) {
+  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
   if (s == nullptr || downsampler == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null argument");
   }
@@ -1305,6 +1307,7 @@ pb_status_t pb_fixed_step_instance_get_state(pb_fixed_step_instance_t* s,
 pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
                                            const pb_fixed_step_flow_t* flow,
                                            void* stream_pointer) {
+  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
   if (e == nullptr || flow == nullptr || flow->n < 0 || flow->time == nullptr ||
       (flow->n > 0 && flow->state == nullptr)) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
@@ -1325,6 +1328,7 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
 
 pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* e,
                                     const pb_fixed_step_flow_t* flow) {
+  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
   if (e == nullptr || flow == nullptr || flow->n < 0 ||
       (flow->n > 0 && flow->state == nullptr)) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
