@@ -284,7 +284,18 @@ typedef struct pb_adaptive_step_flow_t {
    * this trajectory sink (pb_downsampler_*, n trajectories) inside the kernel:
    * the DiscreteTrajectory the reference flows. */
   struct pb_downsampler* sink;
+  /* The IntrinsicAcceleration of the reference (a host function of t,
+   * ephemeris.hpp:72-74, added to the gravitational acceleration,
+   * ephemeris_body.hpp:430-432) in tabulated form: if != NULL, probe i fires an
+   * inertially fixed burn, Manoeuvre::ComputeIntrinsicAcceleration
+   * (ksp_plugin/manœuvre_body.hpp:395-406):
+   *   direction * thrust / (initial_mass - (t - initial_time) * mass_flow)
+   * for initial_time <= t <= final_time, the zero vector elsewhere.
+   * 8 planes of n: direction xyz, thrust, initial_mass, mass_flow,
+   * initial_time, final_time (SI). */
+  const double* burns;
 } pb_adaptive_step_flow_t;
+enum { PB_BURN_PLANES = 8 };
 pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* ephemeris,
                                        const pb_adaptive_step_flow_t* flow);
 pb_status_t pb_flow_with_adaptive_step_device(

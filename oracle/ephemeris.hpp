@@ -296,10 +296,26 @@ class Ephemeris {
   // :1624-1696 for one massless trajectory; the ephemeris must already cover
   // [state.time, t] (no Prolong here: the caller prolongs).  `append` receives
   // every accepted state.
+  // An inertially fixed burn, Manœuvre::ComputeIntrinsicAcceleration,
+  // ksp_plugin/manœuvre_body.hpp:395-406.
+  struct Burn {
+    Vec3 direction;
+    double thrust, initial_mass, mass_flow, initial_time, final_time;
+    Vec3 IntrinsicAcceleration(double const t) const {
+      if (t >= initial_time && t <= final_time) {
+        return direction * thrust /
+               (initial_mass - (t - initial_time) * mass_flow);
+      } else {
+        return {0.0, 0.0, 0.0};
+      }
+    }
+  };
+
   int32_t FlowWithAdaptiveStep(State& state, double t, double length_tolerance,
                                double speed_tolerance, std::int64_t max_steps,
                                AppendState append, std::int64_t* evaluations,
-                               std::int64_t* rejections) const {
+                               std::int64_t* rejections,
+                               Burn const* burn = nullptr) const {
     if (state.time.value == t) {
       return kOk;
     }
@@ -310,8 +326,24 @@ class Ephemeris {
     parameters.max_steps = max_steps;
     parameters.last_step_is_exact = true;
     State last = state;
+    // ephemeris_body.hpp:422-436: accelerations[0] += intrinsic_acceleration(t).
+    RightHandSide const gravitation = MasslessRightHandSide();
+    RightHandSide const rhs =
+        burn == nullptr
+            ? gravitation
+            : RightHandSide([&gravitation, burn](
+                                double const t, std::vector<double> const& q,
+                                std::vector<double>& g) -> int32_t {
+                int32_t const error = gravitation(t, q, g);
+                Vec3 acceleration{g[0], g[1], g[2]};
+                acceleration += burn->IntrinsicAcceleration(t);
+                g[0] = acceleration.x;
+                g[1] = acceleration.y;
+                g[2] = acceleration.z;
+                return error;
+              });
     ErknInstance instance(
-        DormandElMikkawyPrince1986RKN434FM(), MasslessRightHandSide(), state,
+        DormandElMikkawyPrince1986RKN434FM(), rhs, state,
         [&](State const& s) {
           last = s;
           if (append) {

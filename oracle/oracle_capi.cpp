@@ -592,10 +592,16 @@ int32_t orc_flow_with_adaptive_step(orc_ephemeris* e,
       }
       ++accepted;
     };
+    Ephemeris::Burn burn;
+    if (flow->burns != nullptr) {
+      double const* const b = flow->burns + i;
+      burn = {{b[0], b[n], b[2 * n]}, b[3 * n], b[4 * n], b[5 * n], b[6 * n],
+              b[7 * n]};
+    }
     int32_t const status = e->e->FlowWithAdaptiveStep(
         state, flow->t_final, flow->length_integration_tolerance,
         flow->speed_integration_tolerance, flow->max_steps, append,
-        &evaluations, &rejections);
+        &evaluations, &rejections, flow->burns != nullptr ? &burn : nullptr);
     PlanesFromState(state, flow->state, n, i, 1);
     flow->time[i] = state.time.value;
     flow->time[n + i] = state.time.error;

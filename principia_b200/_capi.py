@@ -86,6 +86,7 @@ class AdaptiveStepFlow(ctypes.Structure):
       ('step_log', ctypes.c_void_p),
       ('state_log', ctypes.c_void_p),
       ('sink', ctypes.c_void_p),
+      ('burns', ctypes.c_void_p),
   ]
 
 

@@ -15,7 +15,8 @@
 //   ComputeGravitationalAccelerationOnMasslessBody, ...OnMassiveBody,
 //   ...OnMassiveBodies, ComputeGravitationalPotential, EvaluateAllPositions,
 //   t_min, t_max: same names.
-// Intrinsic accelerations (host callbacks) are not supported: pass none.
+// Intrinsic accelerations: none, or a tabulated inertially fixed burn (host
+// callbacks are not supported).
 #pragma once
 
 #include <algorithm>
@@ -270,10 +271,34 @@ class Ephemeris {
   }
 
   // physics/ephemeris_body.hpp:415-444,1624-1696.
+  // The IntrinsicAcceleration of the reference is a host function of t
+  // (ephemeris.hpp:72-74); here it is tabulated: an inertially fixed burn,
+  // Manœuvre::ComputeIntrinsicAcceleration (ksp_plugin/manœuvre_body.hpp:
+  // 395-406), or none (NoIntrinsicAcceleration).
+  struct IntrinsicAcceleration {
+    double direction[3];
+    double thrust;
+    double initial_mass;
+    double mass_flow;
+    double initial_time;
+    double final_time;
+  };
+  static constexpr IntrinsicAcceleration const* NoIntrinsicAcceleration =
+      nullptr;
+
   Status FlowWithAdaptiveStep(DiscreteTrajectory* const trajectory,
                               double const t,
                               AdaptiveStepParameters const& parameters,
                               std::int64_t const max_ephemeris_steps) {
+    return FlowWithAdaptiveStep(trajectory, NoIntrinsicAcceleration, t,
+                                parameters, max_ephemeris_steps);
+  }
+
+  Status FlowWithAdaptiveStep(
+      DiscreteTrajectory* const trajectory,
+      IntrinsicAcceleration const* const intrinsic_acceleration,
+      double const t, AdaptiveStepParameters const& parameters,
+      std::int64_t const max_ephemeris_steps) {
     double const last_time = trajectory->back_time();
     if (last_time == t) {
       return Status{};
@@ -311,6 +336,18 @@ class Ephemeris {
       flow.step_log_capacity = capacity;
       flow.step_log = times.data();
       flow.state_log = states.data();
+      double burn[PB_BURN_PLANES];
+      if (intrinsic_acceleration != nullptr) {
+        for (int c = 0; c < 3; ++c) {
+          burn[c] = intrinsic_acceleration->direction[c];
+        }
+        burn[3] = intrinsic_acceleration->thrust;
+        burn[4] = intrinsic_acceleration->initial_mass;
+        burn[5] = intrinsic_acceleration->mass_flow;
+        burn[6] = intrinsic_acceleration->initial_time;
+        burn[7] = intrinsic_acceleration->final_time;
+        flow.burns = burn;
+      }
       pb_status_t const call = pb_flow_with_adaptive_step(ephemeris_, &flow);
       if (call != PB_OK) {
         return Status::FromCall(call);

@@ -136,7 +136,7 @@ pb_status_t pb_flow_with_adaptive_step_device(
       reinterpret_cast<long long*>(flow->accepted_steps),
       reinterpret_cast<long long*>(flow->rejected_steps),
       reinterpret_cast<long long*>(flow->evaluations), flow->step_log,
-      flow->state_log, sink);
+      flow->state_log, sink, flow->burns);
   PB_LAUNCHED();
   PB_CUDA(cudaEventRecord(e->timing_events[1], stream));
   PB_CUDA(cudaStreamSynchronize(stream));
@@ -166,6 +166,11 @@ pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
   PB_RETURN_IF_ERROR(status.Reserve(n + 1));
   PB_RETURN_IF_ERROR(counters.Reserve(3 * n + 1));
   pb_adaptive_step_flow_t device_flow = *flow;
+  DeviceBuffer<double> burns;
+  if (flow->burns != nullptr) {
+    PB_RETURN_IF_ERROR(burns.Upload(flow->burns, PB_BURN_PLANES * n, stream));
+    device_flow.burns = burns.data;
+  }
   device_flow.state = state.data;
   device_flow.time = time.data;
   device_flow.status = status.data;

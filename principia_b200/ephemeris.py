@@ -196,7 +196,7 @@ class Ephemeris:
 
   def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
                               speed_tolerance, max_steps=2**62,
-                              step_log_capacity=0, sink=None):
+                              step_log_capacity=0, sink=None, burns=None):
     """FlowWithAdaptiveStep, one trajectory per probe.  state: (12, n),
     time: (2, n); updated in place (host buffers)."""
     assert state.flags.c_contiguous and time.flags.c_contiguous
@@ -223,6 +223,12 @@ class Ephemeris:
       step_log = np.full((step_log_capacity, n), np.nan)
       flow.step_log_capacity = step_log_capacity
       flow.step_log = step_log.ctypes.data
+    if burns is not None:
+      # (8, n): direction xyz, thrust, initial mass, mass flow, initial and
+      # final time of an inertially fixed burn per probe.
+      burns = np.ascontiguousarray(burns, dtype=np.float64)
+      assert burns.shape == (8, n)
+      flow.burns = burns.ctypes.data
     if sink is not None:
       # A trajectory.Downsampler: every accepted state is appended to it inside
       # the kernel.

@@ -254,7 +254,7 @@ class OracleEphemeris:
   def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
                               speed_tolerance, max_steps=2**62,
                               step_log_capacity=0, threads=0,
-                              state_log=False):
+                              state_log=False, burns=None):
     """state: (12, n), time: (2, n); updated in place."""
     n = state.shape[1]
     flow = _capi.AdaptiveStepFlow()
@@ -279,6 +279,10 @@ class OracleEphemeris:
       step_log = np.full((step_log_capacity, n), np.nan)
       flow.step_log_capacity = step_log_capacity
       flow.step_log = step_log.ctypes.data
+    if burns is not None:
+      burns = np.ascontiguousarray(burns, dtype=np.float64)
+      assert burns.shape == (8, n)
+      flow.burns = burns.ctypes.data
     states = None
     if state_log and step_log_capacity > 0:
       states = np.full((step_log_capacity, 6, n), np.nan)

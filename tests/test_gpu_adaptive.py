@@ -96,3 +96,52 @@ def test_adaptive_flow_statuses(sol_system, sol_oracle, sol_gpu):
   # No probes.
   sol_gpu.flow_with_adaptive_step(100.0, np.zeros((12, 0)), np.zeros((2, 0)),
                                   1e-3, 1e-3)
+
+
+def test_inertially_fixed_burns_match_oracle(sol_system, sol_oracle, sol_gpu):
+  """FlowWithAdaptiveStep with an IntrinsicAcceleration (ephemeris_body.hpp:
+  415-444): a tabulated inertially fixed burn per probe
+  (ksp_plugin/manœuvre_body.hpp:395-406), starting and ending inside the flow,
+  covering it, or outside it.  Same accepted steps and states as the oracle."""
+  n = 40
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  state = workloads.eccentric_probes(n, earth['q'], earth['v'], earth['mu'],
+                                     17)
+  rng = np.random.default_rng(4)
+  burns = np.zeros((8, n))
+  direction = rng.normal(size=(3, n))
+  burns[0:3] = direction / np.linalg.norm(direction, axis=0)
+  burns[3] = rng.uniform(1e3, 5e5, n)        # Thrust, N.
+  burns[4] = rng.uniform(5e3, 5e4, n)        # Initial mass, kg.
+  burns[5] = burns[3] / (9.80665 * 320.0)    # Mass flow at 320 s.
+  burns[6] = rng.uniform(-500.0, 4000.0, n)  # Initial time.
+  burns[7] = burns[6] + rng.uniform(10.0, 600.0, n)
+  burns[6, 0], burns[7, 0] = -1e9, 1e9       # Always on ...
+  burns[5, 0] = 0.0                          # ... without losing mass.
+  burns[6, 1], burns[7, 1] = 1e8, 2e8        # Never on.
+  t_final = 6000.0
+  capacity = 3000
+  expected_state, expected_time = state.copy(), np.zeros((2, n))
+  time = np.zeros((2, n))
+  result = sol_gpu.flow_with_adaptive_step(t_final, state, time, 1e-3, 1e-3,
+                                           step_log_capacity=capacity,
+                                           burns=burns)
+  expected = sol_oracle.flow_with_adaptive_step(
+      t_final, expected_state, expected_time, 1e-3, 1e-3,
+      step_log_capacity=capacity, burns=burns)
+  assert np.all(result['status'] == expected['status'])
+  assert list(result['accepted']) == list(expected['accepted'])
+  assert list(result['rejected']) == list(expected['rejected'])
+  assert list(result['evaluations']) == list(expected['evaluations'])
+  assert result['accepted'].max() < capacity
+  assert_bitwise_equal(result['step_log'], expected['step_log'], 'step log')
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'state')
+  # The burns change the trajectories.
+  free_state, free_time = expected_state.copy(), np.zeros((2, n))
+  free_state[:] = workloads.eccentric_probes(n, earth['q'], earth['v'],
+                                             earth['mu'], 17)
+  sol_oracle.flow_with_adaptive_step(t_final, free_state, free_time, 1e-3,
+                                     1e-3)
+  moved = np.linalg.norm(free_state[0:3] - state[0:3], axis=0)
+  assert moved[1] == 0.0 and moved[0] > 1e3
