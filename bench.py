@@ -303,12 +303,13 @@ def run_native(args):
       # profiles/r01f_ncu_srkn_flow.txt: 2.70 MB + 0.40 MB for 24 960 probes x
       # 10 steps): the kernel is FP64-pipe bound, HBM traffic is negligible.
       'traffic': 3.1e6,
-      # The same capture: FP64 pipe 62.9 % active; 5 370 FP64-pipe
-      # instructions per probe-stage for 3 739 algorithmic flops (the reference
-      # forbids contraction: an add or a multiply takes a DFMA slot for one
-      # flop), so 100 % of the pipe would be frac 0.348.
+      # The same capture: FP64 pipe 62.9 % active; 4 379 FP64-pipe
+      # instructions (2 497 DMUL, 1 260 DADD, 550 DFMA, 72 DSETP) per
+      # probe-stage for 3 739 algorithmic flops (the reference forbids
+      # contraction: an add or a multiply takes a DFMA slot for one flop), so
+      # 100 % of the pipe would be frac 0.427.
       'fp64_pipe_active_ncu': 0.629,
-      'frac_at_full_fp64_pipe': 0.348,
+      'frac_at_full_fp64_pipe': 0.427,
       'kernel': 'SrknFlowKernel',
       'kernel_ms': average_kernel_ms,
       'kernel_launches_per_step': kernel_launches / args.steps,
