@@ -72,8 +72,12 @@ static __device__ __noinline__ Vec3 AccelerationOnBodyOfSystem(
     bool const b_is_b2 = j < b;
     Vec3 const dq = b_is_b2 ? q_j - q_b : q_b - q_j;  // q_b1 - q_b2.
     double const dq2 = Norm2(dq);
-    double const dq_norm = sqrt(dq2);
-    double const one_over_dq3 = dq_norm / (dq2 * dq2);
+    // The correctly rounded branch-free square root and division
+    // (pb_math.cuh) inside their range, the IEEE operators outside.
+    bool const in_range = InFastRange(dq2);
+    double const dq_norm = in_range ? FastSqrt(dq2) : sqrt(dq2);
+    double const one_over_dq3 = in_range ? FastDivide(dq_norm, dq2 * dq2)
+                                         : dq_norm / (dq2 * dq2);
     double const mu_j = body_j.mu;
     // a2 += dq * (mu1 / dq^3); a1 -= dq * (mu2 / dq^3): for body b the other
     // body's mu either way.
