@@ -203,6 +203,14 @@ class Ephemeris {
     return a[b1];
   }
 
+  std::vector<Vec3> EvaluateAllVelocities(double t) const {
+    std::vector<Vec3> v;
+    for (auto const& trajectory : trajectories_) {
+      v.push_back(trajectory->EvaluateVelocity(t));
+    }
+    return v;
+  }
+
   std::vector<Vec3> EvaluateAllPositions(double t) const {
     std::vector<Vec3> q;
     for (auto const& trajectory : trajectories_) {

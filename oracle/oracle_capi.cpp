@@ -420,6 +420,19 @@ int32_t orc_ephemeris_evaluate_all_positions(orc_ephemeris* e, double t,
   return kOk;
 }
 
+// ContinuousTrajectory::EvaluateVelocity of every body, caller order.
+int32_t orc_ephemeris_evaluate_all_velocities(orc_ephemeris* e, double t,
+                                              double* velocities) {
+  auto const v = e->e->EvaluateAllVelocities(t);
+  for (int i = 0; i < e->e->size(); ++i) {
+    int const caller = e->e->order()[i];
+    velocities[3 * caller] = v[i].x;
+    velocities[3 * caller + 1] = v[i].y;
+    velocities[3 * caller + 2] = v[i].z;
+  }
+  return kOk;
+}
+
 int32_t orc_compute_gravitational_acceleration_on_massless_bodies(
     orc_ephemeris* e, double t, std::int64_t n, double const* q, double* a,
     int32_t* status) {

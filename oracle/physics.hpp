@@ -579,6 +579,35 @@ struct Segment {
   double c[18][3];  // Coefficient k of (t - origin)^k, xyz.
 };
 
+// InternalEstrinEvaluator<..., fma = true>::EvaluateDerivative,
+// numerics/polynomial_evaluators_body.hpp:104-129,162-192, entered with low = 1,
+// subdegree = degree - 1 (:304-330).
+inline double EstrinEvaluateDerivative(double const* c, int stride, int low,
+                                       int subdegree, double x) {
+  if (subdegree == -1) {
+    return 0.0;
+  }
+  if (subdegree == 0) {
+    return low * c[low * stride];
+  }
+  if (subdegree == 1) {
+    return std::fma((low + 1) * c[(low + 1) * stride], x,
+                    low * c[low * stride]);
+  }
+  int m = 1;
+  while (m * 2 <= subdegree) {
+    m *= 2;
+  }
+  double const a =
+      EstrinEvaluateDerivative(c, stride, low + m, subdegree - m, x);
+  double const b = EstrinEvaluateDerivative(c, stride, low, m - 1, x);
+  double xm = x;
+  for (int k = 1; k < m; k *= 2) {
+    xm = xm * xm;
+  }
+  return std::fma(a, xm, b);
+}
+
 // InternalEstrinEvaluator<..., fma = true>::Evaluate, :72-160.
 inline double EstrinEvaluate(double const* c, int stride, int low,
                              int subdegree, double x) {
@@ -641,6 +670,19 @@ class ContinuousTrajectory {
     }
     last_points_.push_back({time, q, v});
     return status;
+  }
+
+  // EvaluateVelocity / EvaluateDegreesOfFreedom: the derivative of the same
+  // polynomial, continuous_trajectory_body.hpp:697-722.
+  Vec3 EvaluateVelocity(double const time) const {
+    auto const it = std::lower_bound(
+        segments_.begin(), segments_.end(), time,
+        [](Segment const& left, double right) { return left.t_max < right; });
+    Segment const& s = *it;
+    double const x = time - s.origin;
+    return {EstrinEvaluateDerivative(&s.c[0][0], 3, 1, s.degree - 1, x),
+            EstrinEvaluateDerivative(&s.c[0][1], 3, 1, s.degree - 1, x),
+            EstrinEvaluateDerivative(&s.c[0][2], 3, 1, s.degree - 1, x)};
   }
 
   // :686-695, :860-885 (first polynomial with time <= t_max).

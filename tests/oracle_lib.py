@@ -49,6 +49,7 @@ _SYMBOLS = [
     ('orc_ephemeris_t_min', _d, [_vp]),
     ('orc_ephemeris_t_max', _d, [_vp]),
     ('orc_ephemeris_evaluate_all_positions', _i32, [_vp, _d, _dp]),
+    ('orc_ephemeris_evaluate_all_velocities', _i32, [_vp, _d, _dp]),
     ('orc_compute_gravitational_acceleration_on_massless_bodies', _i32,
      [_vp, _d, _i64, _dp, _dp, _i32p]),
     ('orc_compute_gravitational_potential', _i32, [_vp, _d, _i64, _dp, _dp]),
@@ -184,6 +185,11 @@ class OracleEphemeris:
   def evaluate_all_positions(self, t):
     out = np.zeros((self.n, 3))
     self.lib.orc_ephemeris_evaluate_all_positions(self.handle, t, dptr(out))
+    return out
+
+  def evaluate_all_velocities(self, t):
+    out = np.zeros((self.n, 3))
+    self.lib.orc_ephemeris_evaluate_all_velocities(self.handle, t, dptr(out))
     return out
 
   def acceleration_on_massless_bodies(self, t, q):

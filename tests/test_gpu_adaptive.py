@@ -145,3 +145,52 @@ def test_inertially_fixed_burns_match_oracle(sol_system, sol_oracle, sol_gpu):
                                      1e-3)
   moved = np.linalg.norm(free_state[0:3] - state[0:3], axis=0)
   assert moved[1] == 0.0 and moved[0] > 1e3
+
+
+@pytest.mark.parametrize('integrator,expected_size', [
+    (_capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, 379),
+    (_capi.QUINLAN_1999_ORDER_8A, 406),
+])
+def test_reference_earth_probe(sol_system, integrator, expected_size):
+  """EphemerisTest.EarthProbe of the reference (physics/ephemeris_test.cpp:
+  374-497; tests/earth_probe.py) on the GPU: a flow made of rounding errors.
+  The trajectory has one of the sizes the reference pins (379: its "Ubuntu AVX"
+  value) and every accepted time and the final state equal the oracle's."""
+  import earth_probe
+  from principia_b200.ephemeris import Ephemeris
+  from oracle_lib import OracleEphemeris
+  earth_only, period, v1 = earth_probe.set_up(sol_system)
+  t0 = earth_probe.T0
+  oracle = OracleEphemeris(earth_only, method=integrator, step=period / 100,
+                           fitting_tolerance=5e-3,
+                           initial_positions=np.zeros((1, 3)),
+                           initial_velocities=np.array([[v1, 0.0, 0.0]]),
+                           initial_time=t0)
+  assert oracle.prolong(t0 + period) == 0
+  gpu = Ephemeris(earth_only)
+  gpu.append_segments(0, oracle.segments(0))
+  state, time, burns = earth_probe.probe(sol_system, v1)
+  expected_state, expected_time = state.copy(), time.copy()
+  capacity = 512
+  result = gpu.flow_with_adaptive_step(t0 + period, state, time, 1e-9, 2.6e-15,
+                                       max_steps=1000000,
+                                       step_log_capacity=capacity, burns=burns)
+  expected = oracle.flow_with_adaptive_step(
+      t0 + period, expected_state, expected_time, 1e-9, 2.6e-15,
+      max_steps=1000000, step_log_capacity=capacity, burns=burns)
+  size = int(result['accepted'][0]) + 1
+  assert size == int(expected['accepted'][0]) + 1 == expected_size
+  assert size in earth_probe.REFERENCE_TRAJECTORY_SIZES
+  assert result['status'][0] == expected['status'][0] == 0
+  assert list(result['rejected']) == list(expected['rejected'])
+  assert_bitwise_equal(result['step_log'], expected['step_log'], 'step log')
+  assert_bitwise_equal(state, expected_state, 'state')
+  low, high = earth_probe.REFERENCE_PROBE_ULPS
+  assert low <= earth_probe.ulp_distance(state[0, 0],
+                                         period * state[6, 0]) <= high
+  assert state[1, 0] == earth_probe.DISTANCE
+  # Without prolonging, flowing to infinity stops at t_max: DeadlineExceeded.
+  t_max = gpu.t_max()
+  result = gpu.flow_with_adaptive_step(np.inf, state, time, 1e-9, 2.6e-15,
+                                       max_steps=1000000, burns=burns)
+  assert result['status'][0] == 4 and time[0, 0] == t_max

@@ -395,6 +395,63 @@ def test_downsampling_circle_and_straight_line():
   assert is_near(velocity_errors.max(), 2.2e-15)
 
 
+# physics/ephemeris_test.cpp:374-497.
+@pytest.mark.parametrize('integrator,expected_size', [
+    (_capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, 379),  # "Ubuntu AVX".
+    (_capi.QUINLAN_1999_ORDER_8A, 406),                 # "MSVC all FMA/1".
+])
+def test_earth_probe(integrator, expected_size):
+  """The reference's EarthProbe test, made of rounding errors from end to end:
+  Prolong with either integrator, the Newhall fit, the evaluation of the
+  polynomials and of their derivative, the adaptive flow with an intrinsic
+  acceleration, the fourth root of its step control."""
+  import earth_probe
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  earth_only, period, v1 = earth_probe.set_up(system)
+  t0 = earth_probe.T0
+  oracle = OracleEphemeris(earth_only, method=integrator, step=period / 100,
+                           fitting_tolerance=5e-3,
+                           initial_positions=np.zeros((1, 3)),
+                           initial_velocities=np.array([[v1, 0.0, 0.0]]),
+                           initial_time=t0)
+  assert oracle.prolong(t0 + period) == 0
+  state, time, burns = earth_probe.probe(system, v1)
+  result = oracle.flow_with_adaptive_step(t0 + period, state, time, 1e-9,
+                                          2.6e-15, max_steps=1000000,
+                                          burns=burns)
+  assert result['status'][0] == 0
+  size = int(result['accepted'][0]) + 1
+  assert size in earth_probe.REFERENCE_TRAJECTORY_SIZES
+  assert size == expected_size
+  # The Earth: degrees of freedom at t0 + period from its last polynomial
+  # (EvaluateDegreesOfFreedom: Estrin on the derivative), positions at
+  # t0 + i period / 100.
+  t = t0 + period
+  assert set(oracle.segments(0)['degree']) == {3}
+  v_earth = oracle.evaluate_all_velocities(t)[0][0]
+  q_earth = oracle.evaluate_all_positions(t)[0][1]
+  for i, (low, high) in earth_probe.REFERENCE_EARTH_ULPS.items():
+    position = oracle.evaluate_all_positions(t0 + i * period / 100)[0]
+    distance = earth_probe.ulp_distance(position[0],
+                                        (i / 100) * period * v_earth)
+    assert low <= distance <= high, (i, distance)
+    assert position[1] == q_earth
+  # The probe.
+  v_probe = state[6, 0]
+  low, high = earth_probe.REFERENCE_PROBE_ULPS
+  assert low <= earth_probe.ulp_distance(state[0, 0],
+                                         1.00 * period * v_probe) <= high
+  assert state[1, 0] == earth_probe.DISTANCE
+  # Flowing to infinity without prolonging: DeadlineExceeded at t_max.
+  old_t_max = oracle.t_max()
+  assert time[0, 0] < old_t_max
+  result = oracle.flow_with_adaptive_step(math.inf, state, time, 1e-9,
+                                          2.6e-15, max_steps=1000000,
+                                          burns=burns)
+  assert result['status'][0] == 4  # absl::StatusCode::kDeadlineExceeded.
+  assert time[0, 0] == old_t_max
+
+
 def test_internal_body_order():
   system = SolarSystem.from_fixture('sol_jd2451545')
   ephemeris = OracleEphemeris(system)
