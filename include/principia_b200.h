@@ -198,6 +198,11 @@ typedef struct pb_fixed_step_flow_t {
   int64_t* n_samples;   /* out, may be NULL. */
   int64_t* n_steps;     /* out, may be NULL. */
   pb_status_t* status;  /* out, may be NULL. */
+  /* The IntrinsicAccelerations of NewInstance (ephemeris.hpp:181-194, added to
+   * the gravitational accelerations, ephemeris_body.hpp:376-382) in tabulated
+   * form: NULL, or an inertially fixed burn per probe, 8 planes of n laid out
+   * as in pb_adaptive_step_flow_t.burns. */
+  const double* burns;
 } pb_fixed_step_flow_t;
 pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* ephemeris,
                                     const pb_fixed_step_flow_t* flow);

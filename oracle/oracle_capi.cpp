@@ -552,8 +552,31 @@ int32_t orc_flow_with_fixed_step(orc_ephemeris* e,
         ++local_samples;
       }
     };
-    FixedStepInstance instance(flow->method, e->e->MasslessRightHandSide(),
-                               state, append, flow->step);
+    // ephemeris_body.hpp:366-385: accelerations[i] += intrinsic_acceleration(t).
+    RightHandSide const gravitation = e->e->MasslessRightHandSide();
+    RightHandSide rhs = gravitation;
+    std::vector<Ephemeris::Burn> burns;
+    if (flow->burns != nullptr) {
+      for (std::int64_t i = 0; i < count; ++i) {
+        double const* const b = flow->burns + first + i;
+        burns.push_back({{b[0], b[n], b[2 * n]}, b[3 * n], b[4 * n], b[5 * n],
+                         b[6 * n], b[7 * n]});
+      }
+      rhs = [&gravitation, &burns](double const t,
+                                   std::vector<double> const& q,
+                                   std::vector<double>& g) -> int32_t {
+        int32_t const error = gravitation(t, q, g);
+        for (std::size_t i = 0; i < burns.size(); ++i) {
+          Vec3 acceleration{g[3 * i], g[3 * i + 1], g[3 * i + 2]};
+          acceleration += burns[i].IntrinsicAcceleration(t);
+          g[3 * i] = acceleration.x;
+          g[3 * i + 1] = acceleration.y;
+          g[3 * i + 2] = acceleration.z;
+        }
+        return error;
+      };
+    }
+    FixedStepInstance instance(flow->method, rhs, state, append, flow->step);
     chunk_status[chunk] = instance.Solve(flow->t_final);
     PlanesFromState(instance.state(), flow->state, n, first, count);
     if (chunk == 0) {

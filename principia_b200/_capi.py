@@ -64,6 +64,7 @@ class FixedStepFlow(ctypes.Structure):
       ('n_samples', c_int64_p),
       ('n_steps', c_int64_p),
       ('status', c_int32_p),
+      ('burns', ctypes.c_void_p),
   ]
 
 

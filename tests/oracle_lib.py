@@ -228,7 +228,8 @@ class OracleEphemeris:
     return out
 
   def flow_with_fixed_step(self, method, step, t_final, state, time,
-                           sample_every=0, max_samples=0, threads=0):
+                           sample_every=0, max_samples=0, threads=0,
+                           burns=None):
     """state: (12, n) array, time: (2,) array; both updated in place."""
     assert state.flags.c_contiguous and state.dtype == np.float64
     n = state.shape[1]
@@ -251,6 +252,10 @@ class OracleEphemeris:
     flow.n_samples = ctypes.pointer(n_samples)
     flow.n_steps = ctypes.pointer(n_steps)
     flow.status = ctypes.pointer(status)
+    if burns is not None:
+      burns = np.ascontiguousarray(burns, dtype=np.float64)
+      assert burns.shape == (8, n)
+      flow.burns = burns.ctypes.data
     self.lib.orc_flow_with_fixed_step(self.handle, ctypes.byref(flow), threads)
     return dict(n_steps=n_steps.value, status=status.value,
                 samples=None if samples is None else samples[:n_samples.value],
