@@ -229,6 +229,10 @@ pb_status_t pb_fixed_step_instance_create(pb_ephemeris_t* ephemeris,
                                           const double* time,
                                           pb_fixed_step_instance_t** instance);
 void pb_fixed_step_instance_destroy(pb_fixed_step_instance_t* instance);
+/* The intrinsic_accelerations of NewInstance, tabulated: 8 planes of n as in
+ * pb_fixed_step_flow_t.burns (host memory, copied), or NULL for none. */
+pb_status_t pb_fixed_step_instance_set_intrinsic_accelerations(
+    pb_fixed_step_instance_t* instance, const double* burns);
 /* FlowWithFixedStep(t_final, instance) = Instance::Solve(t_final).  Every
  * `sample_every`-th state appended by this call goes to samples[s][6][n]
  * (host), sample_times[s]; *n_steps = states appended; *flow_status as in

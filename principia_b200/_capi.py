@@ -128,6 +128,8 @@ SYMBOLS = [
     ('pb_fixed_step_instance_create', _i32,
      [_vp, _i32, _d, _i64, c_double_p, c_double_p, ctypes.POINTER(_vp)]),
     ('pb_fixed_step_instance_destroy', None, [_vp]),
+    ('pb_fixed_step_instance_set_intrinsic_accelerations', _i32,
+     [_vp, c_double_p]),
     ('pb_fixed_step_instance_flow', _i32,
      [_vp, _d, _i64, _i64, c_double_p, c_double_p, c_int64_p, c_int64_p,
       c_int32_p]),

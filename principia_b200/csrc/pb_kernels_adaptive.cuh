@@ -187,25 +187,6 @@ __device__ __noinline__ void AppendToSink(DownsamplerView const& sink,
   DownsamplerAppend(sink, i, t, q, v);
 }
 
-// The tabulated intrinsic acceleration of trajectory i at time t: an inertially
-// fixed burn, Manœuvre::ComputeIntrinsicAcceleration,
-// ksp_plugin/manœuvre_body.hpp:395-406.  burns: 8 planes of n.
-__device__ __forceinline__ Vec3 BurnIntrinsicAcceleration(
-    double const* __restrict__ const burns, long long const n,
-    long long const i, double const t) {
-  double const initial_time = burns[6 * n + i];
-  double const final_time = burns[7 * n + i];
-  if (t >= initial_time && t <= final_time) {
-    Vec3 const direction{burns[i], burns[n + i], burns[2 * n + i]};
-    double const thrust = burns[3 * n + i];
-    double const initial_mass = burns[4 * n + i];
-    double const mass_flow = burns[5 * n + i];
-    return direction * thrust / (initial_mass - (t - initial_time) * mass_flow);
-  } else {
-    return {0.0, 0.0, 0.0};
-  }
-}
-
 // Scheduling key of a trajectory: an estimate of its number of steps, from the
 // osculating orbit around the body with the strongest tide at the initial
 // state.  With a 4th-order error estimate the step scales like

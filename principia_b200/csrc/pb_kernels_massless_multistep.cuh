@@ -34,6 +34,7 @@ __device__ __forceinline__ long long MasslessHistoryIndex(
 // entry of the state's time.
 static __global__ void __launch_bounds__(kFlowThreads)
 MasslessFillStepKernel(EphemerisView const e, double const* __restrict__ stage,
+                       double const time, double const* __restrict__ burns,
                        long long const n, double const* __restrict__ state,
                        MasslessHistory const history, int const slot,
                        int32_t* status) {
@@ -55,6 +56,9 @@ MasslessFillStepKernel(EphemerisView const e, double const* __restrict__ stage,
   Vec3 a;
   int32_t const error = AccelerationOnMasslessBodyHot(
       e, stage, Vec3{position[0], position[1], position[2]}, a);
+  if (burns != nullptr) {
+    a += BurnIntrinsicAcceleration(burns, n, i, time);
+  }
   history.acceleration[MasslessHistoryIndex(slot, 0, n, i)] = a.x;
   history.acceleration[MasslessHistoryIndex(slot, 1, n, i)] = a.y;
   history.acceleration[MasslessHistoryIndex(slot, 2, n, i)] = a.z;
@@ -74,6 +78,8 @@ __global__ void __launch_bounds__(kFlowThreads, 3)
 MasslessMultistepFlowKernel(EphemerisView const e, MultistepMethod const method,
                             double const h,
                             double const* __restrict__ stage_table,
+                            double const* __restrict__ stage_times,
+                            double const* __restrict__ burns,
                             int const n_steps, long long const n,
                             double* __restrict__ state,
                             MasslessHistory const history, int const oldest,
@@ -135,6 +141,9 @@ MasslessMultistepFlowKernel(EphemerisView const e, MultistepMethod const method,
     error |= AccelerationOnMasslessBodyHot(
         e, stage_table + static_cast<long long>(s) * e.stage_stride,
         Vec3{position[0], position[1], position[2]}, a);
+    if (burns != nullptr) {
+      a += BurnIntrinsicAcceleration(burns, n, i, stage_times[s]);
+    }
     double const a_new[3] = {a.x, a.y, a.z};
     // Push: the new step replaces the oldest one and becomes
     // previous_steps.back(); the velocity uses the history newest first.

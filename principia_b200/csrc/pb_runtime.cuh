@@ -177,6 +177,7 @@ struct pb_ephemeris {
   pb::DeviceBuffer<double> stage_times;
   pb::DeviceBuffer<double> stage_table;
   pb::DeviceBuffer<double> scratch_a, scratch_b, scratch_c;
+  pb::DeviceBuffer<double> burns_scratch;
   pb::DeviceBuffer<int32_t> status_word;
   pb::DeviceBuffer<long long> counters;
   pb::PinnedBuffer<double> pinned_times;

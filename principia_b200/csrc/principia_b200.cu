@@ -268,11 +268,10 @@ int SrknMinBlocks() {
 }
 
 // Shape of the flow kernel: 0 = 128 threads x SrknMinBlocks() blocks per SM;
-// 1 = the same with a barrier per stage; 2 = 384 threads x 1 block with the
-// barrier; 3 = 384 x 1 without.  Measured on 10^5 probes: 56.2, 55.5, 53.5,
-// 52.4 ms per 100 steps, so a launch that fills every SM with a 384-thread
-// block takes shape 3, a smaller one shape 0 (more, smaller blocks).
-// PB_SRKN_VARIANT overrides the choice.
+// 3 = 384 threads x 1 block.  Measured on 10^5 probes: 56.2 and 52.4 ms per 100
+// steps (a block barrier per stage did not help either shape), so a launch that
+// fills every SM with a 384-thread block takes shape 3, a smaller one shape 0
+// (more, smaller blocks).  PB_SRKN_VARIANT overrides the choice.
 int SrknVariant(long long const n_probes, int const sm_count) {
   static int const forced = [] {
     char const* const text = std::getenv("PB_SRKN_VARIANT");
@@ -752,28 +751,23 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
           double const* const table =
               e->stage_table.data +
               static_cast<std::size_t>(s0) * evaluations * view.stage_stride;
-#define PB_LAUNCH_SRKN(kThreads, kMinBlocks, kSync)                           \
-  SrknFlowKernel<kThreads, kMinBlocks, kSync><<<grid, kThreads, 0, helper>>>( \
-      view, tableau, h, table, n_sub, flow->n, i_begin, i_end, flow->state,   \
-      steps_done + s0, every, flow->max_samples, flow->samples,               \
-      e->status_word.data)
-          switch (variant) {
-            case 1:
-              switch (SrknMinBlocks()) {
-                case 2: PB_LAUNCH_SRKN(128, 2, true); break;
-                case 4: PB_LAUNCH_SRKN(128, 4, true); break;
-                default: PB_LAUNCH_SRKN(128, 3, true); break;
-              }
-              break;
-            case 2: PB_LAUNCH_SRKN(384, 1, true); break;
-            case 3: PB_LAUNCH_SRKN(384, 1, false); break;
-            default:
-              switch (SrknMinBlocks()) {
-                case 2: PB_LAUNCH_SRKN(128, 2, false); break;
-                case 4: PB_LAUNCH_SRKN(128, 4, false); break;
-                default: PB_LAUNCH_SRKN(128, 3, false); break;
-              }
-              break;
+          double const* const times =
+              e->stage_times.data + static_cast<std::size_t>(s0) * evaluations;
+#define PB_LAUNCH_SRKN(kThreads, kMinBlocks)                                  \
+  (flow->burns != nullptr ? SrknFlowKernel<kThreads, kMinBlocks, true>        \
+                          : SrknFlowKernel<kThreads, kMinBlocks, false>)      \
+      <<<grid, kThreads, 0, helper>>>(                                        \
+          view, tableau, h, table, times, flow->burns, n_sub, flow->n,        \
+          i_begin, i_end, flow->state, steps_done + s0, every,                \
+          flow->max_samples, flow->samples, e->status_word.data)
+          if (variant >= 2) {
+            PB_LAUNCH_SRKN(384, 1);
+          } else {
+            switch (SrknMinBlocks()) {
+              case 2: PB_LAUNCH_SRKN(128, 2); break;
+              case 4: PB_LAUNCH_SRKN(128, 4); break;
+              default: PB_LAUNCH_SRKN(128, 3); break;
+            }
           }
 #undef PB_LAUNCH_SRKN
           PB_LAUNCHED();
@@ -833,6 +827,9 @@ struct pb_fixed_step_instance {
   DP time{0.0, 0.0};
   double* state = nullptr;  // 12 planes of n: owned_state or the caller's.
   DeviceBuffer<double> owned_state;
+  // Tabulated intrinsic accelerations (8 planes of n), or null.
+  double const* burns = nullptr;
+  DeviceBuffer<double> owned_burns;
   // previous_steps_: a ring of `order` steps.
   DeviceBuffer<double> displacement_value, displacement_error, acceleration;
   int previous_steps = 0;  // previous_steps_.size().
@@ -880,8 +877,8 @@ pb_status_t MasslessFillStep(pb_fixed_step_instance* s, int const slot,
     MasslessFillStepKernel<<<static_cast<unsigned>((s->n + kFlowThreads - 1) /
                                                    kFlowThreads),
                              kFlowThreads, 0, stream>>>(
-        view, e->stage_table.data, s->n, s->state, s->History(), slot,
-        e->status_word.data);
+        view, e->stage_table.data, t, s->burns, s->n, s->state, s->History(),
+        slot, e->status_word.data);
     PB_LAUNCHED();
   }
   return PB_OK;
@@ -956,6 +953,7 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
       flow.time = time;
       flow.n_steps = &steps_taken;
       flow.status = &flow_status;
+      flow.burns = s->burns;
       PB_RETURN_IF_ERROR(SrknFlowDevice(e, &flow, stream, wanted));
       s->time = {time[0], time[1]};
       s->startup_step_index += steps_taken;
@@ -1021,7 +1019,8 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
       auto const kernel = order == 8 ? MasslessMultistepFlowKernel<8>
                                      : MasslessMultistepFlowKernel<12>;
       kernel<<<grid, kFlowThreads, 0, stream>>>(
-          view, s->multistep, h, e->stage_table.data, steps, s->n, s->state,
+          view, s->multistep, h, e->stage_table.data, e->stage_times.data,
+          s->burns, steps, s->n, s->state,
           s->History(), s->oldest, appended_before,
           sampling ? sink->sample_every : 0, sink->max_samples, sink->samples,
           e->status_word.data);
@@ -1055,6 +1054,7 @@ pb_status_t SolveInstance(pb_fixed_step_instance* s,
     srkn.step = s->step;
     srkn.n = s->n;
     srkn.state = s->state;
+    srkn.burns = s->burns;
     double time[2] = {s->time.value, s->time.error};
     srkn.time = time;
     PB_RETURN_IF_ERROR(SrknFlowDevice(e, &srkn, stream,
@@ -1098,6 +1098,7 @@ pb_status_t MultistepFlowDevice(pb_ephemeris_t* e,
   instance.n = flow->n;
   instance.time = {flow->time[0], flow->time[1]};
   instance.state = flow->state;
+  instance.burns = flow->burns;
   PB_RETURN_IF_ERROR(e->pinned_status.Reserve(1));
   PB_RETURN_IF_ERROR(e->status_word.Reserve(1));
   PB_RETURN_IF_ERROR(SolveInstance(&instance, flow, stream));
@@ -1161,6 +1162,23 @@ void pb_fixed_step_instance_destroy(pb_fixed_step_instance_t* instance) {
     cudaSetDevice(instance->ephemeris->device);
     delete instance;
   }
+}
+
+pb_status_t pb_fixed_step_instance_set_intrinsic_accelerations(
+    pb_fixed_step_instance_t* s, const double* burns) {
+  if (s == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null instance");
+  }
+  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  if (burns == nullptr) {
+    s->burns = nullptr;
+    return PB_OK;
+  }
+  PB_RETURN_IF_ERROR(s->owned_burns.Upload(
+      burns, PB_BURN_PLANES * static_cast<std::size_t>(s->n), nullptr));
+  PB_CUDA(cudaStreamSynchronize(nullptr));
+  s->burns = s->owned_burns.data;
+  return PB_OK;
 }
 
 pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* s,
@@ -1339,6 +1357,11 @@ pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* e,
   PB_RETURN_IF_ERROR(e->scratch_a.Upload(flow->state, 12 * n, stream));
   pb_fixed_step_flow_t device_flow = *flow;
   device_flow.state = e->scratch_a.data;
+  if (flow->burns != nullptr) {
+    PB_RETURN_IF_ERROR(
+        e->burns_scratch.Upload(flow->burns, PB_BURN_PLANES * n, stream));
+    device_flow.burns = e->burns_scratch.data;
+  }
   bool const sampling = flow->samples != nullptr && flow->sample_every > 0 &&
                         flow->max_samples > 0;
   if (sampling) {

@@ -152,9 +152,10 @@ class Ephemeris:
     return flow, outs
 
   def flow_with_fixed_step(self, method, step, t_final, state, time,
-                           sample_every=0, max_samples=0):
+                           sample_every=0, max_samples=0, burns=None):
     """NewInstance + FlowWithFixedStep on n probes.  state: (12, n) float64,
-    time: (2,) float64; both updated in place (host buffers)."""
+    time: (2,) float64; both updated in place (host buffers).  burns: the
+    intrinsic accelerations, tabulated (8, n), or None."""
     assert state.flags.c_contiguous and state.dtype == np.float64
     n = state.shape[1]
     samples = sample_times = None
@@ -165,6 +166,10 @@ class Ephemeris:
         method, step, t_final, n, state.ctypes.data, time, sample_every,
         max_samples, None if samples is None else samples.ctypes.data,
         sample_times)
+    if burns is not None:
+      burns = np.ascontiguousarray(burns, dtype=np.float64)
+      assert burns.shape == (8, n)
+      flow.burns = burns.ctypes.data
     _check(self.lib.pb_flow_with_fixed_step(self.handle, ctypes.byref(flow)))
     n_samples, n_steps, status = (o.value for o in outs)
     return dict(n_steps=n_steps, status=status,
@@ -259,6 +264,14 @@ class FixedStepInstance:
     if getattr(self, 'handle', None):
       self.lib.pb_fixed_step_instance_destroy(self.handle)
       self.handle = None
+
+  def set_intrinsic_accelerations(self, burns):
+    """The intrinsic_accelerations of NewInstance, tabulated: (8, n) or None."""
+    if burns is not None:
+      burns = np.ascontiguousarray(burns, dtype=np.float64)
+      assert burns.shape == (8, self.n)
+    _check(self.lib.pb_fixed_step_instance_set_intrinsic_accelerations(
+        self.handle, None if burns is None else _dptr(burns)))
 
   def flow(self, t_final, sample_every=0, max_samples=0):
     samples = sample_times = None

@@ -248,6 +248,39 @@ def test_collision_status_and_continuation(sol_system, sol_oracle, sol_gpu):
   assert_bitwise_equal(state, expected_state, 'collision state')
 
 
+def test_fixed_step_flow_with_intrinsic_accelerations(sol_system, sol_oracle,
+                                                      sol_gpu):
+  """NewInstance with intrinsic accelerations (ephemeris_body.hpp:346-412): a
+  tabulated inertially fixed burn per probe, SRKN14A, against the oracle."""
+  method = _capi.BLANES_MOAN_2002_SRKN_14A
+  n = 300
+  state = leo(sol_system, n, seed=23)
+  rng = np.random.default_rng(8)
+  burns = np.zeros((8, n))
+  direction = rng.normal(size=(3, n))
+  burns[0:3] = direction / np.linalg.norm(direction, axis=0)
+  burns[3] = rng.uniform(1e3, 5e5, n)
+  burns[4] = rng.uniform(5e3, 5e4, n)
+  burns[5] = burns[3] / (9.80665 * 320.0)
+  burns[6] = rng.uniform(-100.0, 2000.0, n)
+  burns[7] = burns[6] + rng.uniform(10.0, 600.0, n)
+  expected_state = state.copy()
+  time, expected_time = np.zeros(2), np.zeros(2)
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 3000.0, state, time,
+                                        sample_every=50, max_samples=6,
+                                        burns=burns)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, 3000.0,
+                                             expected_state, expected_time,
+                                             sample_every=50, max_samples=6,
+                                             burns=burns)
+  assert result['n_steps'] == expected['n_steps'] == 300
+  assert_bitwise_equal(state, expected_state, 'state')
+  assert_bitwise_equal(result['samples'], expected['samples'], 'samples')
+  free = leo(sol_system, n, seed=23)
+  sol_gpu.flow_with_fixed_step(method, 10.0, 3000.0, free, np.zeros(2))
+  assert np.linalg.norm(free[0:3] - state[0:3], axis=0).min() > 1.0
+
+
 def test_ten_thousand_fixed_steps_match_oracle(sol_system, sol_oracle,
                                                sol_gpu):
   """BASELINE.json's tolerance is a relative position error <= 1e-12 after

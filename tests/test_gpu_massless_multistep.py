@@ -149,6 +149,64 @@ def test_reference_collision_detection_apple(sol_system):
   assert_bitwise_equal(state, expected_state, 'after 354.8 s')
 
 
+@pytest.mark.parametrize('integrator', [
+    _capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, _capi.QUINLAN_1999_ORDER_8A])
+def test_reference_earth_two_probes(sol_system, integrator):
+  """EphemerisTest.EarthTwoProbes of the reference (physics/ephemeris_test.cpp:
+  501-620): the Earth alone in uniform motion, two probes whose constant
+  intrinsic accelerations cancel its pull, flowed with a fixed step of
+  period / 1000 through NewInstance.  1001 points each; the abscissae lie
+  25-70 and 2-13 ULPs from period * v, the ordinates are exactly constant; the
+  product agrees with the oracle bit for bit."""
+  import earth_probe
+  from principia_b200.ephemeris import Ephemeris
+  from oracle_lib import OracleEphemeris
+  earth_only, period, v1 = earth_probe.set_up(sol_system)
+  t0 = earth_probe.T0
+  mu = sol_system.bodies[sol_system.index('Earth')]['mu']
+  oracle = OracleEphemeris(earth_only, method=integrator, step=period / 100,
+                           fitting_tolerance=5e-3,
+                           initial_positions=np.zeros((1, 3)),
+                           initial_velocities=np.array([[v1, 0.0, 0.0]]),
+                           initial_time=t0)
+  assert oracle.prolong(t0 + period) == 0
+  gpu = Ephemeris(earth_only)
+  gpu.append_segments(0, oracle.segments(0))
+  state = np.zeros((12, 2))
+  state[1] = [1e9, -3e9]
+  state[6] = v1
+  burns = np.zeros((8, 2))
+  burns[1] = 1.0
+  burns[3] = [mu / (1e9 * 1e9), -mu / (3e9 * 3e9)]
+  burns[4] = 1.0
+  burns[6], burns[7] = -1e30, 1e30
+  expected_state = state.copy()
+  expected_time = np.array([t0, 0.0])
+  expected = oracle.flow_with_fixed_step(integrator, period / 1000,
+                                         t0 + period, expected_state,
+                                         expected_time, burns=burns)
+  instance = gpu.new_instance(integrator, period / 1000, state,
+                              np.array([t0, 0.0]))
+  instance.set_intrinsic_accelerations(burns)
+  # In two calls, like a plugin that advances its vessels frame by frame.
+  steps = instance.flow(t0 + 0.3 * period)['n_steps']
+  steps += instance.flow(t0 + period)['n_steps']
+  assert steps == expected['n_steps'] == 1000
+  final_state, final_time = instance.state()
+  assert_bitwise_equal(final_time, expected_time, 'time')
+  assert_bitwise_equal(final_state, expected_state, 'state')
+  for k, (low, high) in enumerate(((25, 70), (2, 13))):
+    distance = earth_probe.ulp_distance(final_state[0, k],
+                                        1.00 * period * final_state[6, k])
+    assert low <= distance <= high, (k, distance)
+  assert list(final_state[1]) == [1e9, -3e9]
+  # The stateless entry point takes the same table.
+  state2, time2 = state.copy(), np.array([t0, 0.0])
+  gpu.flow_with_fixed_step(integrator, period / 1000, t0 + period, state2,
+                           time2, burns=burns)
+  assert_bitwise_equal(state2, expected_state, 'stateless')
+
+
 def test_multistep_flow_rejects_backward_steps(sol_system, sol_gpu):
   state = leo(sol_system, 4)
   with pytest.raises(Exception):
