@@ -189,11 +189,43 @@ class Ephemeris {
     return Status{};
   }
 
+  // The IntrinsicAcceleration of the reference is a host function of t
+  // (ephemeris.hpp:72-74); here it is tabulated: an inertially fixed burn,
+  // Manœuvre::ComputeIntrinsicAcceleration (ksp_plugin/manœuvre_body.hpp:
+  // 395-406), or none (NoIntrinsicAcceleration).
+  struct IntrinsicAcceleration {
+    double direction[3];
+    double thrust;
+    double initial_mass;
+    double mass_flow;
+    double initial_time;
+    double final_time;
+  };
+  static constexpr IntrinsicAcceleration const* NoIntrinsicAcceleration =
+      nullptr;
+
+  using IntrinsicAccelerations = std::vector<IntrinsicAcceleration const*>;
+
   // physics/ephemeris_body.hpp:346-412.  All trajectories must end at the same
   // time (CHECK_EQ there).
   std::unique_ptr<Instance> NewInstance(
       std::vector<DiscreteTrajectory*> const& trajectories,
       FixedStepParameters const& parameters) {
+    return NewInstance(trajectories, IntrinsicAccelerations{}, parameters);
+  }
+
+  // `intrinsic_accelerations` is empty (NoIntrinsicAccelerations) or has one
+  // entry per trajectory, null for none.
+  std::unique_ptr<Instance> NewInstance(
+      std::vector<DiscreteTrajectory*> const& trajectories,
+      IntrinsicAccelerations const& intrinsic_accelerations,
+      FixedStepParameters const& parameters) {
+    if (!intrinsic_accelerations.empty() &&
+        intrinsic_accelerations.size() != trajectories.size()) {
+      throw std::invalid_argument(
+          "CHECK(intrinsic_accelerations.empty() || "
+          "intrinsic_accelerations.size() == trajectories.size())");
+    }
     if (trajectories.empty()) {
       throw std::invalid_argument("CHECK(!trajectories.empty())");
     }
@@ -220,6 +252,32 @@ class Ephemeris {
         &instance->handle_);
     if (call != PB_OK) {
       throw std::invalid_argument(pb_last_error());
+    }
+    if (!intrinsic_accelerations.empty()) {
+      // A trajectory without intrinsic acceleration gets a burn that never
+      // fires: the reference adds nothing for a null function, the table adds
+      // the zero vector (the same bits unless an acceleration is -0.0).
+      std::vector<double> burns(PB_BURN_PLANES * n, 0.0);
+      for (std::size_t i = 0; i < n; ++i) {
+        IntrinsicAcceleration const* const a = intrinsic_accelerations[i];
+        if (a == nullptr) {
+          burns[6 * n + i] = std::numeric_limits<double>::infinity();
+          burns[7 * n + i] = -std::numeric_limits<double>::infinity();
+          continue;
+        }
+        for (int c = 0; c < 3; ++c) {
+          burns[c * n + i] = a->direction[c];
+        }
+        burns[3 * n + i] = a->thrust;
+        burns[4 * n + i] = a->initial_mass;
+        burns[5 * n + i] = a->mass_flow;
+        burns[6 * n + i] = a->initial_time;
+        burns[7 * n + i] = a->final_time;
+      }
+      if (pb_fixed_step_instance_set_intrinsic_accelerations(
+              instance->handle_, burns.data()) != PB_OK) {
+        throw std::invalid_argument(pb_last_error());
+      }
     }
     Prolong(last_time + parameters.step);
     return instance;
@@ -271,21 +329,6 @@ class Ephemeris {
   }
 
   // physics/ephemeris_body.hpp:415-444,1624-1696.
-  // The IntrinsicAcceleration of the reference is a host function of t
-  // (ephemeris.hpp:72-74); here it is tabulated: an inertially fixed burn,
-  // Manœuvre::ComputeIntrinsicAcceleration (ksp_plugin/manœuvre_body.hpp:
-  // 395-406), or none (NoIntrinsicAcceleration).
-  struct IntrinsicAcceleration {
-    double direction[3];
-    double thrust;
-    double initial_mass;
-    double mass_flow;
-    double initial_time;
-    double final_time;
-  };
-  static constexpr IntrinsicAcceleration const* NoIntrinsicAcceleration =
-      nullptr;
-
   Status FlowWithAdaptiveStep(DiscreteTrajectory* const trajectory,
                               double const t,
                               AdaptiveStepParameters const& parameters,
