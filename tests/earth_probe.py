@@ -35,6 +35,54 @@ def ulp_distance(a, b):
   return abs(ia - ib)
 
 
+# EphemerisTest.Moon, :330-372: AlmostEquals(i / 100 * period * v, min, max).
+REFERENCE_MOON_ULPS = {25: (343, 345), 50: (151, 153), 75: (512, 516),
+                       100: (401, 403)}
+# EphemerisTest.EarthMoon, :262-318: bounds in metres on the coordinate that
+# vanishes on a circular orbit, relative to the centre of mass.
+REFERENCE_EARTH_MOON_BOUNDS = {
+    'Earth': {25: ('y', 6e-4), 50: ('x', 7e-3), 75: ('y', 2e-2),
+              100: ('x', 3e-2)},
+    'Moon': {25: ('y', 5e-2), 50: ('x', 6e-1), 75: ('y', 2.0),
+             100: ('x', 2.0)}}
+
+
+def set_up_earth_moon(sol_system):
+  """SetUpEarthMoonSystem, :134-174: returns (system of the non-oblate Earth
+  and Moon, initial positions, initial velocities, centre of mass (y), period).
+  """
+  mu_earth = sol_system.bodies[sol_system.index('Earth')]['mu']
+  mu_moon = sol_system.bodies[sol_system.index('Moon')]['mu']
+  m_earth = mu_earth / GRAVITATIONAL_CONSTANT
+  m_moon = mu_moon / GRAVITATIONAL_CONSTANT
+  semi_major_axis = math.sqrt(0.0 * 0.0 + (0.0 - 4e8) * (0.0 - 4e8) +
+                              0.0 * 0.0)
+  period = 2 * math.pi * math.sqrt(
+      (semi_major_axis * semi_major_axis * semi_major_axis) /
+      (mu_earth + mu_moon))
+  weighted_sum_y = (0.0 - 0.0) * m_earth
+  weighted_sum_y += (4e8 - 0.0) * m_moon
+  centre_of_mass_y = 0.0 + weighted_sum_y / (m_earth + m_moon)
+  norm1 = math.sqrt(0.0 + (0.0 - centre_of_mass_y) *
+                    (0.0 - centre_of_mass_y) + 0.0)
+  norm2 = math.sqrt(0.0 + (4e8 - centre_of_mass_y) *
+                    (4e8 - centre_of_mass_y) + 0.0)
+  v1 = -2 * math.pi * norm1 / period
+  v2 = 2 * math.pi * norm2 / period
+  system = sol_system.copy()
+  for name in list(system.names()):
+    if name not in ('Earth', 'Moon'):
+      system.remove_massive_body(name)
+  system.remove_oblateness('Earth')
+  system.remove_oblateness('Moon')
+  positions = np.zeros((2, 3))
+  velocities = np.zeros((2, 3))
+  positions[system.index('Moon'), 1] = 4e8
+  velocities[system.index('Earth'), 0] = v1
+  velocities[system.index('Moon'), 0] = v2
+  return system, positions, velocities, centre_of_mass_y, period
+
+
 def set_up(sol_system):
   """Returns (earth_only_system, period, earth_velocity_x)."""
   mu_earth = sol_system.bodies[sol_system.index('Earth')]['mu']

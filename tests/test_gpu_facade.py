@@ -160,3 +160,48 @@ def test_facade_prolong_and_flows(shim, sol_system):
                                                          q1.reshape(3, 1))
   assert_bitwise_equal(a, expected_a.ravel())
   shim.ft_destroy(handle)
+
+
+@pytest.mark.parametrize('integrator', [
+    _capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, _capi.QUINLAN_1999_ORDER_8A])
+def test_facade_prolongs_the_reference_earth_moon_system(shim, sol_system,
+                                                         integrator):
+  """The Earth-Moon system of the reference's EphemerisTest
+  (physics/ephemeris_test.cpp:134-174, epoch 1950) prolonged over one period
+  through the facade: the polynomials are the oracle's, bit for bit -- and the
+  oracle's lie inside the reference's windows (tests/test_oracle_kats.py)."""
+  import earth_probe
+  system, positions, velocities, _, period = earth_probe.set_up_earth_moon(
+      sol_system)
+  t0 = earth_probe.T0
+  bodies, keep = system.c_bodies()
+  q0 = np.ascontiguousarray(positions)
+  v0 = np.ascontiguousarray(velocities)
+  handle = shim.ft_create(len(system.bodies), bodies, oracle_lib.dptr(q0),
+                          oracle_lib.dptr(v0), t0, 5e-3, 2.0**-24, integrator,
+                          period / 100)
+  assert handle
+  oracle = OracleEphemeris(system, method=integrator, step=period / 100,
+                           fitting_tolerance=5e-3, initial_positions=positions,
+                           initial_velocities=velocities, initial_time=t0)
+  assert shim.ft_prolong(handle, t0 + period) == 0
+  assert oracle.prolong(t0 + period) == 0
+  assert shim.ft_t_max(handle) == oracle.t_max()
+  for body in range(2):
+    expected = oracle.segments(body)
+    count = shim.ft_segment_count(handle, body)
+    assert count == len(expected['t_max']) == 13
+    t_max, origin = np.zeros(count), np.zeros(count)
+    degree = np.zeros(count, dtype=np.int32)
+    coefficients = np.zeros((count, 18, 3))
+    shim.ft_get_segments(handle, body, oracle_lib.dptr(t_max),
+                         oracle_lib.dptr(origin),
+                         degree.ctypes.data_as(_i32p),
+                         oracle_lib.dptr(coefficients))
+    assert_bitwise_equal(t_max, expected['t_max'])
+    assert_bitwise_equal(origin, expected['origin'])
+    assert list(degree) == list(expected['degree'])
+    valid = np.arange(18)[None, :, None] <= degree[:, None, None]
+    assert_bitwise_equal(np.where(valid, coefficients, 0.0),
+                         np.where(valid, expected['coefficients'], 0.0))
+  shim.ft_destroy(handle)

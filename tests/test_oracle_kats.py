@@ -452,6 +452,49 @@ def test_earth_probe(integrator, expected_size):
   assert time[0, 0] == old_t_max
 
 
+# physics/ephemeris_test.cpp:330-372 and :262-318.
+@pytest.mark.parametrize('integrator', [
+    _capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, _capi.QUINLAN_1999_ORDER_8A])
+def test_moon_alone_and_earth_moon(integrator):
+  import earth_probe
+  sol = SolarSystem.from_fixture('sol_jd2451545')
+  system, positions, velocities, centre_of_mass_y, period = (
+      earth_probe.set_up_earth_moon(sol))
+  t0 = earth_probe.T0
+  # The Moon alone moves in a straight line.
+  moon_only = system.copy()
+  moon_only.remove_massive_body('Earth')
+  moon = system.index('Moon')
+  oracle = OracleEphemeris(moon_only, method=integrator, step=period / 100,
+                           fitting_tolerance=5e-3,
+                           initial_positions=positions[moon:moon + 1],
+                           initial_velocities=velocities[moon:moon + 1],
+                           initial_time=t0)
+  assert oracle.prolong(t0 + period) == 0
+  v = oracle.evaluate_all_velocities(t0 + period)[0][0]
+  q = oracle.evaluate_all_positions(t0 + period)[0][1]
+  for i, (low, high) in earth_probe.REFERENCE_MOON_ULPS.items():
+    position = oracle.evaluate_all_positions(t0 + i * period / 100)[0]
+    distance = earth_probe.ulp_distance(position[0], (i / 100) * period * v)
+    assert low <= distance <= high, (i, distance)
+    assert position[1] == q
+  # The Earth and the Moon on their circular orbits.
+  oracle = OracleEphemeris(system, method=integrator, step=period / 100,
+                           fitting_tolerance=5e-3,
+                           initial_positions=positions,
+                           initial_velocities=velocities, initial_time=t0)
+  assert oracle.prolong(t0 + period) == 0
+  for name, bounds in earth_probe.REFERENCE_EARTH_MOON_BOUNDS.items():
+    body = system.index(name)
+    for i, (coordinate, bound) in bounds.items():
+      position = oracle.evaluate_all_positions(t0 + i * period / 100)[body]
+      relative = position - np.array([0.0, centre_of_mass_y, 0.0])
+      value = relative['xyz'.index(coordinate)]
+      assert abs(value) < bound, (name, i, value)
+      # Not vacuous: the body is where the circular orbit puts it.
+      assert np.linalg.norm(relative) > 4e6
+
+
 def test_internal_body_order():
   system = SolarSystem.from_fixture('sol_jd2451545')
   ephemeris = OracleEphemeris(system)
