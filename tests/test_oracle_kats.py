@@ -272,61 +272,84 @@ def test_geopotential_threshold_computation():
 
 
 # physics/ephemeris_test.cpp:1041-1170: closed-form accelerations on 4 massive
-# bodies, body 0 with a huge J2, within 0-4 ULP.
-@pytest.mark.parametrize('method', [_capi.QUINLAN_1999_ORDER_8A,
-                                    _capi.BLANES_MOAN_2002_SRKN_14A])
+# bodies, body 0 with a huge J2; the expected values are formed in the
+# reference's expression order and the distances are inside its windows
+# (AlmostEquals(expected, n): at most n ULPs).
+@pytest.mark.parametrize('method', [_capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL,
+                                    _capi.QUINLAN_1999_ORDER_8A])
 def test_acceleration_on_massive_bodies_with_j2(method):
+  import earth_probe
+  t0 = earth_probe.T0  # The fixture's epoch.
   j2 = 1e6
   radius = 1 * R_EARTH
   mu = [1 * GM_SUN, 2 * GM_SUN, 3 * GM_SUN, 4 * GM_SUN]
   norm20 = math.sqrt(5.0)
   bodies = [dict(name='b0', mu=mu[0], rotating=True, min_radius=1.0,
-                 mean_radius=1.0, reference_angle=1.0, reference_instant=0.0,
+                 mean_radius=1.0, reference_angle=1.0, reference_instant=t0,
                  angular_frequency=4.0, right_ascension=0.0,
                  declination=math.pi / 2, oblate=True, degree=2, zonal=True,
                  reference_radius=radius,
                  cos=[0.0, 0.0, 0.0, -j2 / norm20, 0.0, 0.0], sin=[0.0] * 6)]
   for i in (1, 2, 3):
     bodies.append(dict(name='b%d' % i, mu=mu[i], rotating=False, oblate=False))
-  q = np.array([[0, 0, 0], [1, 0, 0], [1, 0, 1], [0, 0, 1]],
-               dtype=np.float64) * AU
+  q = [[0 * AU, 0 * AU, 0 * AU], [1 * AU, 0 * AU, 0 * AU],
+       [1 * AU, 0 * AU, 1 * AU], [0 * AU, 0 * AU, 1 * AU]]
   for b, qq in zip(bodies, q):
     b['q'] = list(qq)
     b['v'] = [0.0, 0.0, 0.0]
-  system = SolarSystem(bodies, 0.0)
-  ephemeris = OracleEphemeris(system, method=method, step=0.01,
+  system = SolarSystem(bodies, t0)
+  ephemeris = OracleEphemeris(system, method=method, step=1.0 / 100,
                               fitting_tolerance=5e-3,
                               geopotential_tolerance=2.0**-24)
-  assert ephemeris.prolong(1.0) == 0
-  actual = ephemeris.acceleration_on_massive_bodies(0.0)
+  assert ephemeris.prolong(t0 + 1.0) == 0
+  actual = ephemeris.acceleration_on_massive_bodies(t0)
+
+  def sub(a, b):
+    return [a[0] - b[0], a[1] - b[1], a[2] - b[2]]
+
+  def norm(a):
+    return math.sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2])
+
+  def pow3(x):
+    return x * x * x
+
+  def pow4(x):
+    return (x * x) * (x * x)
 
   def point(mu_other, q_other, q_self):
-    d = q_other - q_self
-    return mu_other * d / np.linalg.norm(d)**3
+    # mu * (q_other - q_self) / Pow<3>((q_other - q_self).Norm()).
+    d = sub(q_other, q_self)
+    n3 = pow3(norm(d))
+    return [mu_other * d[0] / n3, mu_other * d[1] / n3, mu_other * d[2] / n3]
 
-  r4 = AU**4
+  def add(*vectors):
+    total = list(vectors[0])
+    for v in vectors[1:]:
+      total = [total[0] + v[0], total[1] + v[1], total[2] + v[2]]
+    return total
+
+  r4 = pow4(norm(sub(q[0], q[1])))
   s512 = math.sqrt(512)
-  expected0 = (point(mu[1], q[1], q[0]) + point(mu[2], q[2], q[0]) +
-               point(mu[3], q[3], q[0]) + np.array([
-                   (1.5 * mu[1] - (9 / s512) * mu[2]) * radius**2 * j2 / r4, 0,
-                   (-3 * mu[3] + (3 / s512) * mu[2]) * radius**2 * j2 / r4]))
-  expected1 = (point(mu[0], q[0], q[1]) + point(mu[2], q[2], q[1]) +
-               point(mu[3], q[3], q[1]) +
-               np.array([-1.5 * mu[0] * radius**2 * j2 / r4, 0, 0]))
-  expected2 = (point(mu[0], q[0], q[2]) + point(mu[1], q[1], q[2]) +
-               point(mu[3], q[3], q[2]) + np.array([
-                   (9 / s512) * mu[0] * radius**2 * j2 / r4, 0,
-                   (-3 / s512) * mu[0] * radius**2 * j2 / r4]))
-  expected3 = (point(mu[0], q[0], q[3]) + point(mu[1], q[1], q[3]) +
-               point(mu[2], q[2], q[3]) +
-               np.array([0, 0, 3 * mu[0] * radius**2 * j2 / r4]))
-  # The reference's bounds are 0-4 ULP with its own expression order for the
-  # expected values; numpy's order differs slightly, so allow 8.
-  for actual_i, expected_i in zip(actual, (expected0, expected1, expected2,
-                                           expected3)):
-    assert ulp_distance(actual_i[0], expected_i[0]) <= 8
+  r2 = radius * radius
+  expected = [
+      add(add(point(mu[1], q[1], q[0]), point(mu[2], q[2], q[0]),
+              point(mu[3], q[3], q[0])),
+          [(1.5 * mu[1] - (9 / s512) * mu[2]) * r2 * j2 / r4, 0.0,
+           (-3 * mu[3] + (3 / s512) * mu[2]) * r2 * j2 / r4]),
+      add(point(mu[0], q[0], q[1]), point(mu[2], q[2], q[1]),
+          point(mu[3], q[3], q[1]), [-1.5 * mu[0] * r2 * j2 / r4, 0.0, 0.0]),
+      add(point(mu[0], q[0], q[2]), point(mu[1], q[1], q[2]),
+          point(mu[3], q[3], q[2]),
+          [(9 / s512) * mu[0] * r2 * j2 / r4, 0.0,
+           (-3 / s512) * mu[0] * r2 * j2 / r4]),
+      add(point(mu[0], q[0], q[3]), point(mu[1], q[1], q[3]),
+          point(mu[2], q[2], q[3]), [0.0, 0.0, 3 * mu[0] * r2 * j2 / r4])]
+  # (x, z) windows of the reference, :1112-1169.
+  windows = [(1, 2), (2, 0), (4, 1), (3, 0)]
+  for actual_i, expected_i, (x_ulps, z_ulps) in zip(actual, expected, windows):
+    assert ulp_distance(actual_i[0], expected_i[0]) <= x_ulps
     assert abs(actual_i[1]) < 1e-16 * abs(expected_i[0])
-    assert ulp_distance(actual_i[2], expected_i[2]) <= 8
+    assert ulp_distance(actual_i[2], expected_i[2]) <= z_ulps
 
 
 # physics/ephemeris_body.hpp:138-158: oblate bodies front-inserted.
