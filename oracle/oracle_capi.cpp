@@ -277,6 +277,49 @@ int32_t orc_newhall_fit(double const* times, double const* q, double const* v,
   return status;
 }
 
+// A ContinuousTrajectory of its own (physics/continuous_trajectory_body.hpp):
+// Append, t_min / t_max, EvaluatePosition / EvaluateVelocity.
+struct orc_continuous_trajectory {
+  ContinuousTrajectory trajectory;
+};
+orc_continuous_trajectory* orc_continuous_trajectory_create(double step,
+                                                            double tolerance) {
+  return new orc_continuous_trajectory{ContinuousTrajectory(step, tolerance)};
+}
+void orc_continuous_trajectory_destroy(orc_continuous_trajectory* t) {
+  delete t;
+}
+int32_t orc_continuous_trajectory_append(orc_continuous_trajectory* t,
+                                         double time, double const* q,
+                                         double const* v) {
+  return t->trajectory.Append(time, {q[0], q[1], q[2]}, {v[0], v[1], v[2]});
+}
+double orc_continuous_trajectory_t_min(orc_continuous_trajectory const* t) {
+  return t->trajectory.t_min();
+}
+double orc_continuous_trajectory_t_max(orc_continuous_trajectory const* t) {
+  return t->trajectory.t_max();
+}
+int32_t orc_continuous_trajectory_segment_count(
+    orc_continuous_trajectory const* t) {
+  return static_cast<int32_t>(t->trajectory.segments().size());
+}
+int32_t orc_continuous_trajectory_degree(orc_continuous_trajectory const* t,
+                                         int32_t segment) {
+  return t->trajectory.segments()[segment].degree;
+}
+void orc_continuous_trajectory_evaluate(orc_continuous_trajectory const* t,
+                                        double time, double* q, double* v) {
+  Vec3 const position = t->trajectory.EvaluatePosition(time);
+  Vec3 const velocity = t->trajectory.EvaluateVelocity(time);
+  q[0] = position.x;
+  q[1] = position.y;
+  q[2] = position.z;
+  v[0] = velocity.x;
+  v[1] = velocity.y;
+  v[2] = velocity.z;
+}
+
 // ------------------------------------------------------------ Ephemeris ----
 
 int32_t orc_ephemeris_create(int32_t n_bodies, pb_body_t const* bodies,

@@ -28,6 +28,14 @@ _SYMBOLS = [
     ('orc_estrin', _d, [_dp, _i32, _d]),
     ('orc_downsample', _i64,
      [_i64, _dp, _dp, _dp, _d, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp]),
+    ('orc_continuous_trajectory_create', _vp, [_d, _d]),
+    ('orc_continuous_trajectory_destroy', None, [_vp]),
+    ('orc_continuous_trajectory_append', _i32, [_vp, _d, _dp, _dp]),
+    ('orc_continuous_trajectory_t_min', _d, [_vp]),
+    ('orc_continuous_trajectory_t_max', _d, [_vp]),
+    ('orc_continuous_trajectory_segment_count', _i32, [_vp]),
+    ('orc_continuous_trajectory_degree', _i32, [_vp, _i32]),
+    ('orc_continuous_trajectory_evaluate', None, [_vp, _d, _dp, _dp]),
     ('orc_chebyshev_evaluate', _d, [_dp, _i32, _d, _d, _d]),
     ('orc_chebyshev_evaluate_derivative', _d, [_dp, _i32, _d, _d, _d]),
     ('orc_newhall_fit', _i32,

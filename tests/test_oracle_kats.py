@@ -391,8 +391,12 @@ def oracle_downsample(times, q, v, tolerance, evaluation_times=None):
 
 
 def is_near(value, expected, digits=2):
-  """IsNear(x_(1)): equal when rounded to the digits given."""
-  return float('%.*g' % (digits, value)) == float('%.*g' % (digits, expected))
+  """IsNear(x_(1)) of the reference (testing_utilities/approximate_quantity.hpp):
+  x written with `digits` significant digits, give or take one unit of the
+  last one."""
+  exponent = math.floor(math.log10(abs(expected))) - (digits - 1)
+  unit = 10.0**exponent
+  return expected - unit * (1 + 1e-9) <= value <= expected + unit * (1 + 1e-9)
 
 
 # physics/discrete_trajectory_segment_test.cpp:252-324.
@@ -548,6 +552,99 @@ def test_potential_against_acceleration_by_finite_differences():
               np.linalg.norm(actual, axis=0))
   assert 5e-8 < relative.min() and relative.max() < 2e-5, (relative.min(),
                                                             relative.max())
+
+
+def fill_trajectory(orc, number_of_steps, step, position, velocity, t0,
+                    tolerance):
+  """ContinuousTrajectoryTest::FillTrajectory,
+  physics/continuous_trajectory_test.cpp:155-172."""
+  trajectory = orc.orc_continuous_trajectory_create(step, tolerance)
+  for i in range(number_of_steps):
+    ti = t0 + (i + 1) * step
+    q = np.array(position(ti), dtype=np.float64)
+    v = np.array(velocity(ti), dtype=np.float64)
+    assert orc.orc_continuous_trajectory_append(
+        trajectory, ti, oracle_lib.dptr(q), oracle_lib.dptr(v)) == 0
+  return trajectory
+
+
+# physics/continuous_trajectory_test.cpp:443-488: a trajectory defined by a
+# degree-1 polynomial is reproduced within 11 ULPs (positions) and 4 ULPs
+# (velocities).
+def test_continuous_trajectory_polynomial():
+  orc = oracle_lib.library()
+  step = 0.01
+  position = lambda t: [(t - 0.0) * 3, (t - 0.0) * 5, (t - 0.0) * (-2)]
+  velocity = lambda t: [3.0, 5.0, -2.0]
+  trajectory = fill_trajectory(orc, 20, step, position, velocity, 0.0, 0.1)
+  assert orc.orc_continuous_trajectory_t_min(trajectory) == 0.0 + step
+  t_max = orc.orc_continuous_trajectory_t_max(trajectory)
+  assert t_max == 0.0 + (((20 - 1) // 8) * 8 + 1) * step
+  q, v = np.zeros(3), np.zeros(3)
+  time = orc.orc_continuous_trajectory_t_min(trajectory)
+  checked = 0
+  while time <= t_max:
+    orc.orc_continuous_trajectory_evaluate(trajectory, time,
+                                           oracle_lib.dptr(q),
+                                           oracle_lib.dptr(v))
+    assert ulp_distance(q, position(time)).max() <= 11
+    assert ulp_distance(v, velocity(time)).max() <= 4
+    time += step / 50
+    checked += 1
+  assert checked > 700
+  orc.orc_continuous_trajectory_destroy(trajectory)
+
+
+# physics/continuous_trajectory_test.cpp:490-566: an approximation of the
+# trajectory of Io, tolerance 5 mm: the errors are IsNear(31_(1) mm) and
+# IsNear(1.40e-5_(1) m/s).
+def test_continuous_trajectory_io():
+  orc = oracle_lib.library()
+  sun_jupiter_distance = 778500000 * 1e3
+  jupiter_io_distance = 421700 * 1e3
+  jupiter_period = 11.8618 * (365.25 * 86400.0)
+  io_period = 152853.5047
+  step = 3600.0
+  t0 = 0.0
+  sin, cos = orc.orc_cr_sin, orc.orc_cr_cos
+
+  def position(t):
+    jupiter_angle = 2 * math.pi * (t - t0) / jupiter_period
+    io_angle = 2 * math.pi * (t - t0) / io_period
+    return [sun_jupiter_distance * cos(jupiter_angle) +
+            jupiter_io_distance * cos(io_angle),
+            sun_jupiter_distance * sin(jupiter_angle) +
+            jupiter_io_distance * sin(io_angle), 0.0]
+
+  def velocity(t):
+    jupiter_omega = 2 * math.pi / jupiter_period
+    io_omega = 2 * math.pi / io_period
+    jupiter_angle = jupiter_omega * (t - t0)
+    io_angle = io_omega * (t - t0)
+    return [(-jupiter_omega * sun_jupiter_distance * sin(jupiter_angle) -
+             io_omega * jupiter_io_distance * sin(io_angle)),
+            (jupiter_omega * sun_jupiter_distance * cos(jupiter_angle) +
+             io_omega * jupiter_io_distance * cos(io_angle)), 0.0]
+
+  trajectory = fill_trajectory(orc, 200, step, position, velocity, t0, 5e-3)
+  assert orc.orc_continuous_trajectory_t_min(trajectory) == t0 + step
+  t_max = orc.orc_continuous_trajectory_t_max(trajectory)
+  assert t_max == t0 + (((200 - 1) // 8) * 8 + 1) * step
+  q, v = np.zeros(3), np.zeros(3)
+  max_position_error = max_velocity_error = 0.0
+  time = orc.orc_continuous_trajectory_t_min(trajectory)
+  while time <= t_max:
+    orc.orc_continuous_trajectory_evaluate(trajectory, time,
+                                           oracle_lib.dptr(q),
+                                           oracle_lib.dptr(v))
+    max_position_error = max(max_position_error,
+                             np.linalg.norm(q - np.array(position(time))))
+    max_velocity_error = max(max_velocity_error,
+                             np.linalg.norm(v - np.array(velocity(time))))
+    time += step / 50
+  assert is_near(max_position_error, 31e-3, digits=2)
+  assert is_near(max_velocity_error, 1.40e-5, digits=3)
+  orc.orc_continuous_trajectory_destroy(trajectory)
 
 
 def test_internal_body_order():
