@@ -252,6 +252,18 @@ pb_status_t pb_fixed_step_instance_flow_to_downsampler(
     pb_fixed_step_instance_t* instance, double t_final,
     pb_downsampler_t* downsampler, int64_t* n_steps,
     pb_status_t* flow_status);
+/* Instance::WriteToMessage / ReadFromMessage (integrators/integrators.hpp:
+ * 66-78) as a flat array of doubles: the state, the time, the intrinsic
+ * accelerations and, for a multistep instance, its previous steps and the
+ * progress of its startup.  A restored instance continues bit for bit like the
+ * original.  `checkpoint` has room for ..._checkpoint_size() doubles. */
+int64_t pb_fixed_step_instance_checkpoint_size(
+    const pb_fixed_step_instance_t* instance);
+pb_status_t pb_fixed_step_instance_write_checkpoint(
+    pb_fixed_step_instance_t* instance, double* checkpoint);
+pb_status_t pb_fixed_step_instance_read_checkpoint(
+    pb_ephemeris_t* ephemeris, const double* checkpoint, int64_t size,
+    pb_fixed_step_instance_t** instance);
 /* instance.state(): 12 planes of n and the time {value, error}; either may be
  * NULL. */
 pb_status_t pb_fixed_step_instance_get_state(

@@ -135,6 +135,10 @@ SYMBOLS = [
       c_int32_p]),
     ('pb_fixed_step_instance_flow_to_downsampler', _i32,
      [_vp, _d, _vp, c_int64_p, c_int32_p]),
+    ('pb_fixed_step_instance_checkpoint_size', _i64, [_vp]),
+    ('pb_fixed_step_instance_write_checkpoint', _i32, [_vp, c_double_p]),
+    ('pb_fixed_step_instance_read_checkpoint', _i32,
+     [_vp, c_double_p, _i64, ctypes.POINTER(_vp)]),
     ('pb_fixed_step_instance_get_state', _i32, [_vp, c_double_p, c_double_p]),
     ('pb_flow_with_adaptive_step', _i32,
      [_vp, ctypes.POINTER(AdaptiveStepFlow)]),

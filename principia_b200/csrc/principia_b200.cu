@@ -1304,6 +1304,142 @@ pb_status_t pb_fixed_step_instance_flow_to_downsampler(
   return PB_OK;
 }
 
+// The checkpoint of an instance: a header of kCheckpointHeader doubles, the
+// 12 planes of the state, the 8 planes of the burns if any, and for a multistep
+// instance the three history rings (3 n order doubles each).
+namespace {
+constexpr int kCheckpointHeader = 16;
+constexpr double kCheckpointMagic = 20261019.0;
+
+std::size_t CheckpointDoubles(pb_fixed_step_instance const* s) {
+  std::size_t const n = static_cast<std::size_t>(s->n);
+  std::size_t size = kCheckpointHeader + 12 * n;
+  if (s->burns != nullptr) {
+    size += PB_BURN_PLANES * n;
+  }
+  if (s->is_multistep && s->displacement_value.data != nullptr) {
+    size += 3 * (3 * n * s->multistep.order);
+  }
+  return size;
+}
+}  // namespace
+
+int64_t pb_fixed_step_instance_checkpoint_size(
+    const pb_fixed_step_instance_t* s) {
+  return s == nullptr ? 0 : static_cast<int64_t>(CheckpointDoubles(s));
+}
+
+pb_status_t pb_fixed_step_instance_write_checkpoint(
+    pb_fixed_step_instance_t* s, double* checkpoint) {
+  if (s == nullptr || checkpoint == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
+  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  std::size_t const n = static_cast<std::size_t>(s->n);
+  bool const has_history =
+      s->is_multistep && s->displacement_value.data != nullptr;
+  double* out = checkpoint;
+  double const header[kCheckpointHeader] = {
+      kCheckpointMagic,
+      static_cast<double>(s->method),
+      s->step,
+      static_cast<double>(s->n),
+      s->time.value,
+      s->time.error,
+      static_cast<double>(s->previous_steps),
+      static_cast<double>(s->startup_step_index),
+      static_cast<double>(s->oldest),
+      s->startup_target_valid ? 1.0 : 0.0,
+      s->startup_target,
+      s->burns != nullptr ? 1.0 : 0.0,
+      has_history ? 1.0 : 0.0,
+      0.0, 0.0, 0.0};
+  std::memcpy(out, header, sizeof(header));
+  out += kCheckpointHeader;
+  auto download = [&](double const* device, std::size_t const count) {
+    if (count == 0) {
+      return cudaSuccess;
+    }
+    cudaError_t const error = cudaMemcpy(out, device, count * sizeof(double),
+                                         cudaMemcpyDeviceToHost);
+    out += count;
+    return error;
+  };
+  PB_CUDA(download(s->state, 12 * n));
+  if (s->burns != nullptr) {
+    PB_CUDA(download(s->burns, PB_BURN_PLANES * n));
+  }
+  if (has_history) {
+    std::size_t const ring = 3 * n * s->multistep.order;
+    PB_CUDA(download(s->displacement_value.data, ring));
+    PB_CUDA(download(s->displacement_error.data, ring));
+    PB_CUDA(download(s->acceleration.data, ring));
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_fixed_step_instance_read_checkpoint(
+    pb_ephemeris_t* e, const double* checkpoint, int64_t size,
+    pb_fixed_step_instance_t** instance) {
+  if (e == nullptr || checkpoint == nullptr || instance == nullptr ||
+      size < kCheckpointHeader || checkpoint[0] != kCheckpointMagic) {
+    return Fail(PB_INVALID_ARGUMENT, "not a checkpoint of an instance");
+  }
+  *instance = nullptr;
+  double const time[2] = {checkpoint[4], checkpoint[5]};
+  int64_t const n = static_cast<int64_t>(checkpoint[3]);
+  bool const has_burns = checkpoint[11] != 0.0;
+  bool const has_history = checkpoint[12] != 0.0;
+  if (n < 0 || size < kCheckpointHeader + 12 * n) {
+    return Fail(PB_INVALID_ARGUMENT, "truncated checkpoint");
+  }
+  double const* in = checkpoint + kCheckpointHeader;
+  pb_fixed_step_instance_t* s = nullptr;
+  PB_RETURN_IF_ERROR(pb_fixed_step_instance_create(
+      e, static_cast<int32_t>(checkpoint[1]), checkpoint[2], n, in, time, &s));
+  in += 12 * n;
+  std::size_t const count = static_cast<std::size_t>(n);
+  std::size_t expected = kCheckpointHeader + 12 * count +
+                         (has_burns ? PB_BURN_PLANES * count : 0);
+  if (has_history) {
+    expected += 3 * (3 * count * s->multistep.order);
+  }
+  pb_status_t status = PB_OK;
+  if (static_cast<std::size_t>(size) != expected ||
+      (has_history && !s->is_multistep)) {
+    status = Fail(PB_INVALID_ARGUMENT, "inconsistent checkpoint");
+  }
+  if (status == PB_OK && has_burns) {
+    status = pb_fixed_step_instance_set_intrinsic_accelerations(s, in);
+    in += PB_BURN_PLANES * count;
+  }
+  if (status == PB_OK && has_history) {
+    std::size_t const ring = 3 * count * s->multistep.order;
+    status = s->displacement_value.Upload(in, ring, nullptr);
+    if (status == PB_OK) {
+      status = s->displacement_error.Upload(in + ring, ring, nullptr);
+    }
+    if (status == PB_OK) {
+      status = s->acceleration.Upload(in + 2 * ring, ring, nullptr);
+    }
+    if (status == PB_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) {
+      status = Fail(PB_INTERNAL, "upload failed");
+    }
+  }
+  if (status != PB_OK) {
+    pb_fixed_step_instance_destroy(s);
+    return status;
+  }
+  s->previous_steps = static_cast<int>(checkpoint[6]);
+  s->startup_step_index = static_cast<long long>(checkpoint[7]);
+  s->oldest = static_cast<int>(checkpoint[8]);
+  s->startup_target_valid = checkpoint[9] != 0.0;
+  s->startup_target = checkpoint[10];
+  *instance = s;
+  return PB_OK;
+}
+
 pb_status_t pb_fixed_step_instance_get_state(pb_fixed_step_instance_t* s,
                                              double* state, double* time) {
   if (s == nullptr) {

@@ -249,6 +249,28 @@ class FixedStepInstance:
   fixed-step method (integrators/integrators.hpp:40-94): flow(t) is
   Ephemeris::FlowWithFixedStep(t, instance)."""
 
+  @classmethod
+  def from_checkpoint(cls, ephemeris, checkpoint):
+    """Instance::ReadFromMessage."""
+    checkpoint = np.ascontiguousarray(checkpoint, dtype=np.float64)
+    self = cls.__new__(cls)
+    self.ephemeris = ephemeris
+    self.lib = ephemeris.lib
+    self.handle = ctypes.c_void_p()
+    _check(self.lib.pb_fixed_step_instance_read_checkpoint(
+        ephemeris.handle, _dptr(checkpoint), len(checkpoint),
+        ctypes.byref(self.handle)))
+    self.n = int(checkpoint[3])
+    return self
+
+  def checkpoint(self):
+    """Instance::WriteToMessage: a flat array of doubles."""
+    size = self.lib.pb_fixed_step_instance_checkpoint_size(self.handle)
+    out = np.zeros(size)
+    _check(self.lib.pb_fixed_step_instance_write_checkpoint(self.handle,
+                                                            _dptr(out)))
+    return out
+
   def __init__(self, ephemeris, method, step, state, time):
     self.ephemeris = ephemeris  # Keeps the ephemeris alive.
     self.lib = ephemeris.lib

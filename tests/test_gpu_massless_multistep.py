@@ -207,6 +207,45 @@ def test_reference_earth_two_probes(sol_system, integrator):
   assert_bitwise_equal(state2, expected_state, 'stateless')
 
 
+@pytest.mark.parametrize('method,stops', [
+    (_capi.QUINLAN_1999_ORDER_8A, (33.0, 500.0)),   # Mid-startup, multistep.
+    (_capi.QUINLAN_TREMAINE_1990_ORDER_12, (700.0,)),
+    (_capi.BLANES_MOAN_2002_SRKN_14A, (300.0,)),
+])
+def test_instance_checkpoint_and_restore(sol_system, sol_gpu, method, stops):
+  """WriteToMessage / ReadFromMessage of an instance: a restored instance (the
+  original destroyed) continues bit for bit like an uninterrupted one, from the
+  middle of the startup and from the multistep regime, burns included."""
+  n = 50
+  state0 = leo(sol_system, n, seed=31)
+  rng = np.random.default_rng(2)
+  burns = np.zeros((8, n))
+  burns[0] = 1.0
+  burns[3] = rng.uniform(1e3, 1e5, n)
+  burns[4] = 2e4
+  burns[5] = 1.0
+  burns[6], burns[7] = 100.0, 900.0
+  t_final = 1500.0
+  uninterrupted = sol_gpu.new_instance(method, 10.0, state0, np.zeros(2))
+  uninterrupted.set_intrinsic_accelerations(burns)
+  uninterrupted.flow(t_final)
+  expected_state, expected_time = uninterrupted.state()
+  instance = sol_gpu.new_instance(method, 10.0, state0, np.zeros(2))
+  instance.set_intrinsic_accelerations(burns)
+  for stop in stops:
+    instance.flow(stop)
+    checkpoint = instance.checkpoint()
+    del instance
+    instance = type(uninterrupted).from_checkpoint(sol_gpu, checkpoint)
+  instance.flow(t_final)
+  state, time = instance.state()
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'state')
+  from principia_b200.ephemeris import StatusError
+  with pytest.raises(StatusError):
+    type(uninterrupted).from_checkpoint(sol_gpu, checkpoint[:-1])
+
+
 def test_multistep_flow_rejects_backward_steps(sol_system, sol_gpu):
   state = leo(sol_system, 4)
   with pytest.raises(Exception):
