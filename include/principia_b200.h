@@ -55,7 +55,9 @@ enum {
   PB_MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL = 1,
   PB_QUINLAN_1999_ORDER_8A = 2,
   PB_QUINLAN_TREMAINE_1990_ORDER_12 = 3,
-  PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM = 16
+  PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM = 16,
+  /* integrators/methods.hpp:543-570, embedded explicit generalized RKN. */
+  PB_FINE_1987_RKNG_34 = 17
 };
 
 /* One massive body: MassiveBody / RotatingBody / OblateBody parameters
@@ -283,7 +285,10 @@ pb_status_t pb_fixed_step_instance_get_state(
  * `step_log_capacity` accepted steps of each probe are written to
  * step_log[k * n + probe] (parity of the accepted-step sequence). */
 typedef struct pb_adaptive_step_flow_t {
-  int32_t method;       /* PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM */
+  int32_t method;       /* PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM, or
+                         * PB_FINE_1987_RKNG_34 (the generalized overload,
+                         * ephemeris_body.hpp:446-478, with a velocity-
+                         * independent intrinsic acceleration). */
   double t_final;
   double length_integration_tolerance;
   double speed_integration_tolerance;

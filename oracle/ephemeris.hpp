@@ -323,7 +323,8 @@ class Ephemeris {
                                double speed_tolerance, std::int64_t max_steps,
                                AppendState append, std::int64_t* evaluations,
                                std::int64_t* rejections,
-                               Burn const* burn = nullptr) const {
+                               Burn const* burn = nullptr,
+                               bool generalized = false) const {
     if (state.time.value == t) {
       return kOk;
     }
@@ -350,8 +351,11 @@ class Ephemeris {
                 g[2] = acceleration.z;
                 return error;
               });
+    // The generalized overload (ephemeris_body.hpp:446-478) with Fine1987RKNG34
+    // (the plugin's burn integrator, ksp_plugin/integrators.cpp:54-63).
     ErknInstance instance(
-        DormandElMikkawyPrince1986RKN434FM(), rhs, state,
+        generalized ? Fine1987RKNG34() : DormandElMikkawyPrince1986RKN434FM(),
+        rhs, state,
         [&](State const& s) {
           last = s;
           if (append) {

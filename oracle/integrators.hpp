@@ -127,6 +127,40 @@ inline ErknMethod const& DormandElMikkawyPrince1986RKN434FM() {
   return m;
 }
 
+// Fine1987RKNG34, methods.hpp:543-570: an embedded explicit *generalized*
+// Runge-Kutta-Nyström method (the right-hand side may depend on the velocity,
+// integrators/embedded_explicit_generalized_runge_kutta_nyström_integrator_
+// body.hpp:44-300).  With a right-hand side that ignores the velocity -- the
+// ephemeris with no or time-only intrinsic acceleration -- the generalized
+// Solve performs exactly the operations of the ErknInstance below with this
+// tableau (the velocity stages, built with a', feed nothing).  5 stages, no
+// FSAL; b = b_hat - delta as the reference forms them.
+inline ErknMethod const& Fine1987RKNG34() {
+  static ErknMethod const m = [] {
+    ErknMethod m;
+    m.stages = 5;
+    m.lower_order = 3;
+    m.first_same_as_last = false;
+    m.c = {0.0, 2 / 9.0, 1 / 3.0, 3 / 4.0, 1.0};
+    m.a = {2 / 81.0,
+           1 / 36.0,   1 / 36.0,
+           9 / 128.0,  0.0,        27 / 128.0,
+           11 / 60.0,  -3 / 20.0,  9 / 25.0,  8 / 75.0};
+    m.b_hat = {19 / 180.0, 0.0, 63 / 200.0, 16 / 225.0, 1 / 120.0};
+    m.b_hat_prime = {1 / 9.0, 0.0, 9 / 20.0, 16 / 45.0, 1 / 12.0};
+    std::vector<double> const delta = {25 / 1116.0, 0.0, -63 / 1240.0,
+                                       64 / 1395.0, -13 / 744.0};
+    std::vector<double> const delta_prime = {2 / 125.0, 0.0, -27 / 625.0,
+                                             32 / 625.0, -3 / 125.0};
+    for (int i = 0; i < 5; ++i) {
+      m.b.push_back(m.b_hat[i] - delta[i]);
+      m.b_prime.push_back(m.b_hat_prime[i] - delta_prime[i]);
+    }
+    return m;
+  }();
+  return m;
+}
+
 // methods.hpp:998-1007, :1040-1055 and
 // integrators/cohen_hubbard_oesterwinter_body.hpp (orders 8 and 12).
 struct SlmsMethod {

@@ -680,7 +680,8 @@ int32_t orc_flow_with_adaptive_step(orc_ephemeris* e,
     int32_t const status = e->e->FlowWithAdaptiveStep(
         state, flow->t_final, flow->length_integration_tolerance,
         flow->speed_integration_tolerance, flow->max_steps, append,
-        &evaluations, &rejections, flow->burns != nullptr ? &burn : nullptr);
+        &evaluations, &rejections, flow->burns != nullptr ? &burn : nullptr,
+        /*generalized=*/flow->method == PB_FINE_1987_RKNG_34);
     PlanesFromState(state, flow->state, n, i, 1);
     flow->time[i] = state.time.value;
     flow->time[n + i] = state.time.error;

@@ -25,6 +25,7 @@ MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL = 1
 QUINLAN_1999_ORDER_8A = 2
 QUINLAN_TREMAINE_1990_ORDER_12 = 3
 DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM = 16
+FINE_1987_RKNG_34 = 17
 
 
 class Body(ctypes.Structure):

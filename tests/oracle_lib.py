@@ -273,11 +273,12 @@ class OracleEphemeris:
   def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
                               speed_tolerance, max_steps=2**62,
                               step_log_capacity=0, threads=0,
-                              state_log=False, burns=None):
+                              state_log=False, burns=None,
+                              method=_capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM):
     """state: (12, n), time: (2, n); updated in place."""
     n = state.shape[1]
     flow = _capi.AdaptiveStepFlow()
-    flow.method = _capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM
+    flow.method = method
     flow.t_final = t_final
     flow.length_integration_tolerance = length_tolerance
     flow.speed_integration_tolerance = speed_tolerance

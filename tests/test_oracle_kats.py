@@ -647,6 +647,51 @@ def test_continuous_trajectory_io():
   orc.orc_continuous_trajectory_destroy(trajectory)
 
 
+# physics/ephemeris_test.cpp:682-759: "the gravitational acceleration on an
+# elephant located at the pole": a J2-only Earth at rest, the generalized
+# adaptive flow (Fine1987RKNG34) over 1 s with tolerances of 1 nm, 2.6 fm/s.
+@pytest.mark.parametrize('integrator', [
+    _capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, _capi.QUINLAN_1999_ORDER_8A])
+def test_elephant_at_the_pole(integrator):
+  import earth_probe
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  t0 = earth_probe.T0
+  polar_radius = 6.3568e6  # TerrestrialPolarRadius, quantities/astronomy.hpp:50.
+  earth_only = system.copy()
+  for name in list(earth_only.names()):
+    if name != 'Earth':
+      earth_only.remove_massive_body(name)
+  earth_only.limit_oblateness_to_degree('Earth', 2)
+  earth_only.limit_oblateness_to_zonal('Earth')
+  oracle = OracleEphemeris(earth_only, method=integrator, step=1.0 / 100,
+                           fitting_tolerance=5e-3,
+                           initial_positions=np.zeros((1, 3)),
+                           initial_velocities=np.zeros((1, 3)),
+                           initial_time=t0)
+  assert oracle.prolong(t0 + 1.0) == 0
+  state = np.zeros((12, 1))
+  state[2, 0] = polar_radius
+  time = np.zeros((2, 1))
+  time[0, 0] = t0
+  result = oracle.flow_with_adaptive_step(
+      t0 + 1.0, state, time, 1e-9, 2.6e-15, max_steps=1000000,
+      method=_capi.FINE_1987_RKNG_34)
+  assert result['status'][0] == 0
+  assert int(result['accepted'][0]) + 1 == 5  # elephant_positions.size().
+  x, y, z = state[0:3, 0]
+  # The axis of the Earth is slightly tilted because the cosine of the
+  # declination of its pole (90 degrees) is not exactly zero.
+  assert is_near(x, -9.8e-19)
+  assert is_near(y, 6.0e-35) or y == 0.0
+  assert abs(z - polar_radius) / polar_radius < 8e-7
+  acceleration, _ = oracle.acceleration_on_massless_bodies(
+      time[0, 0], np.ascontiguousarray(state[0:3]))
+  ax, ay, az = acceleration[:, 0]
+  assert is_near(ax, -2.0e-18)
+  assert is_near(ay, 1.2e-34) or ay == 0.0
+  assert abs(az - (-9.832)) / 9.832 < 6.7e-6
+
+
 def test_internal_body_order():
   system = SolarSystem.from_fixture('sol_jd2451545')
   ephemeris = OracleEphemeris(system)
