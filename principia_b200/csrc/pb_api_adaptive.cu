@@ -39,10 +39,11 @@ pb_status_t pb_flow_with_adaptive_step_device(
       (flow->n > 0 && (flow->state == nullptr || flow->time == nullptr))) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
   }
-  if (flow->method != PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM) {
+  if (flow->method != PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM &&
+      flow->method != PB_FINE_1987_RKNG_34) {
     return Fail(PB_INVALID_ARGUMENT,
                 "adaptive massless flow supports "
-                "DormandElMikkawyPrince1986RKN434FM");
+                "DormandElMikkawyPrince1986RKN434FM and Fine1987RKNG34");
   }
   PB_CUDA(cudaSetDevice(e->device));
   cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
@@ -129,7 +130,12 @@ pb_status_t pb_flow_with_adaptive_step_device(
     }
   }
   auto const kernel =
-      min_blocks == 2 ? ErknFlowKernel<2> : ErknFlowKernel<3>;
+      flow->method == PB_FINE_1987_RKNG_34
+          ? (min_blocks == 2 ? ErknFlowKernel<Fine1987RKNG34, 2>
+                             : ErknFlowKernel<Fine1987RKNG34, 3>)
+          : (min_blocks == 2
+                 ? ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 2>
+                 : ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 3>);
   kernel<<<blocks, kAdaptiveThreads, 0, stream>>>(
       e->View(), parameters, flow->n, order, e->adaptive_queue.data,
       flow->state, flow->time, flow->status,

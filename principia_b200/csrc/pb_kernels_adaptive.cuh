@@ -239,10 +239,64 @@ static __global__ void AdaptiveCostKernel(EphemerisView const e,
   index[i] = static_cast<int>(i);
 }
 
+// The embedded methods, integrators/methods.hpp.  a is strictly lower
+// triangular, (i, j) -> i (i - 1) / 2 + j.
+// DormandالمكاوىPrince1986RKN434FM, :574-597: 4 stages, first same as last.
+#define PB_METHOD_TABLE(name, size, ...)                              \
+  __device__ __forceinline__ static double name(int const index) {    \
+    constexpr double table[size] = {__VA_ARGS__};                     \
+    return table[index];                                              \
+  }
+
+struct DormandElMikkawyPrince1986RKN434FM {
+  static constexpr int kStages = 4;
+  static constexpr bool kFirstSameAsLast = true;
+  PB_METHOD_TABLE(c, 4, 0.0, 1.0 / 4.0, 7.0 / 10.0, 1.0)
+  PB_METHOD_TABLE(a, 6, 1.0 / 32.0,
+                  7.0 / 1000.0, 119.0 / 500.0,
+                  1.0 / 14.0, 8.0 / 27.0, 25.0 / 189.0)
+  PB_METHOD_TABLE(b_hat, 4, 1.0 / 14.0, 8.0 / 27.0, 25.0 / 189.0, 0.0)
+  PB_METHOD_TABLE(b_hat_prime, 4, 1.0 / 14.0, 32.0 / 81.0, 250.0 / 567.0,
+                  5.0 / 54.0)
+  PB_METHOD_TABLE(b, 4, -7.0 / 150.0, 67.0 / 150.0, 3.0 / 20.0, -1.0 / 20.0)
+  PB_METHOD_TABLE(b_prime, 4, 13.0 / 21.0, -20.0 / 27.0, 275.0 / 189.0,
+                  -1.0 / 3.0)
+};
+
+// Fine1987RKNG34, :543-570: an embedded explicit *generalized* method (the
+// right-hand side may depend on the velocity), the integrator of the
+// generalized FlowWithAdaptiveStep (ephemeris_body.hpp:446-478; the plugin's
+// burn integrator, ksp_plugin/integrators.cpp:54-63).  The right-hand side of
+// this library never depends on the velocity, so the velocity stages (built
+// with a') feed nothing and the generalized Solve
+// (embedded_explicit_generalized_runge_kutta_nyström_integrator_body.hpp:
+// 44-300) performs exactly the operations below.  5 stages, no FSAL;
+// b = b_hat - delta as the reference forms them.
+struct Fine1987RKNG34 {
+  static constexpr int kStages = 5;
+  static constexpr bool kFirstSameAsLast = false;
+  PB_METHOD_TABLE(c, 5, 0.0, 2 / 9.0, 1 / 3.0, 3 / 4.0, 1.0)
+  PB_METHOD_TABLE(a, 10, 2 / 81.0,
+                  1 / 36.0, 1 / 36.0,
+                  9 / 128.0, 0.0, 27 / 128.0,
+                  11 / 60.0, -3 / 20.0, 9 / 25.0, 8 / 75.0)
+  PB_METHOD_TABLE(b_hat, 5, 19 / 180.0, 0.0, 63 / 200.0, 16 / 225.0,
+                  1 / 120.0)
+  PB_METHOD_TABLE(b_hat_prime, 5, 1 / 9.0, 0.0, 9 / 20.0, 16 / 45.0, 1 / 12.0)
+  PB_METHOD_TABLE(b, 5, 19 / 180.0 - 25 / 1116.0, 0.0 - 0.0,
+                  63 / 200.0 - (-63 / 1240.0), 16 / 225.0 - 64 / 1395.0,
+                  1 / 120.0 - (-13 / 744.0))
+  PB_METHOD_TABLE(b_prime, 5, 1 / 9.0 - 2 / 125.0, 0.0 - 0.0,
+                  9 / 20.0 - (-27 / 625.0), 16 / 45.0 - 32 / 625.0,
+                  1 / 12.0 - (-3 / 125.0))
+};
+
+#undef PB_METHOD_TABLE
+
 // state: 12 planes of n; time: 2 planes of n (value, error).  `order` lists
 // the trajectories in the order in which the lanes take them; `queue` is the
 // number of trajectories taken so far (zeroed by the host).
-template<int kMinBlocks>
+template<typename Method, int kMinBlocks>
 __global__ void __launch_bounds__(kAdaptiveThreads, kMinBlocks)
 ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                long long const n, int const* __restrict__ order,
@@ -255,17 +309,7 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                double* __restrict__ step_log,
                double* __restrict__ state_log, DownsamplerView const sink,
                double const* __restrict__ burns) {
-  // DormandالمكاوىPrince1986RKN434FM, methods.hpp:574-597.
-  constexpr double c1 = 1.0 / 4.0, c2 = 7.0 / 10.0, c3 = 1.0;
-  constexpr double a10 = 1.0 / 32.0;
-  constexpr double a20 = 7.0 / 1000.0, a21 = 119.0 / 500.0;
-  constexpr double a30 = 1.0 / 14.0, a31 = 8.0 / 27.0, a32 = 25.0 / 189.0;
-  constexpr double b_hat[4] = {1.0 / 14.0, 8.0 / 27.0, 25.0 / 189.0, 0.0};
-  constexpr double b_hat_prime[4] = {1.0 / 14.0, 32.0 / 81.0, 250.0 / 567.0,
-                                     5.0 / 54.0};
-  constexpr double b[4] = {-7.0 / 150.0, 67.0 / 150.0, 3.0 / 20.0, -1.0 / 20.0};
-  constexpr double b_prime[4] = {13.0 / 21.0, -20.0 / 27.0, 275.0 / 189.0,
-                                 -1.0 / 3.0};
+  constexpr int kStages = Method::kStages;
   constexpr double safety_factor = 0.9;
   double const t_final = parameters.t_final;
 
@@ -276,7 +320,13 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
   DP q[3], v[3];
   double h = 0.0;
   double tolerance_to_error_ratio = 0.0;
-  Vec3 g0{0.0, 0.0, 0.0}, g1 = g0, g2 = g0, g3 = g0;
+  // The stage accelerations; every index is a compile-time constant after
+  // unrolling, so that they stay in registers.
+  Vec3 g[kStages];
+#pragma unroll
+  for (int j = 0; j < kStages; ++j) {
+    g[j] = {0.0, 0.0, 0.0};
+  }
   bool first_iteration = true;
   int first_stage = 0;
   int hint = 0;
@@ -341,21 +391,19 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
       }
       double const h2 = h * h;
 #pragma unroll 1
-      for (int s = first_stage; s < 4; ++s) {
-        double const c_s = s == 0 ? 0.0 : (s == 1 ? c1 : (s == 2 ? c2 : c3));
+      for (int s = first_stage; s < kStages; ++s) {
+        double const c_s = Method::c(s);
         double const t_stage = (at_end && c_s == 1.0)
                                    ? t_final
                                    : t.value + (t.error + c_s * h);
+        // sum_j a(s, j) g_j over j < s, in increasing j.
         Vec3 sum{0.0, 0.0, 0.0};
-        if (s == 1) {
-          sum += a10 * g0;
-        } else if (s == 2) {
-          sum += a20 * g0;
-          sum += a21 * g1;
-        } else if (s == 3) {
-          sum += a30 * g0;
-          sum += a31 * g1;
-          sum += a32 * g2;
+        int const row = s * (s - 1) / 2;
+#pragma unroll
+        for (int j = 0; j < kStages - 1; ++j) {
+          if (j < s) {
+            sum += Method::a(row + j) * g[j];
+          }
         }
         Vec3 const q_stage{q[0].value + h * c_s * v[0].value + h2 * sum.x,
                            q[1].value + h * c_s * v[1].value + h2 * sum.y,
@@ -367,23 +415,17 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
           // ephemeris_body.hpp:430-432.
           acceleration += BurnIntrinsicAcceleration(burns, n, i, t_stage);
         }
-        if (s == 0) {
-          g0 = acceleration;
-        } else if (s == 1) {
-          g1 = acceleration;
-        } else if (s == 2) {
-          g2 = acceleration;
-        } else {
-          g3 = acceleration;
+#pragma unroll
+        for (int j = 0; j < kStages; ++j) {
+          if (j == s) {
+            g[j] = acceleration;
+          }
         }
         ++evaluations;
         if (step_status == PB_OK && rhs_error != 0) {
           step_status = PB_OUT_OF_RANGE;
         }
       }
-      double const gx[4] = {g0.x, g1.x, g2.x, g3.x};
-      double const gy[4] = {g0.y, g1.y, g2.y, g3.y};
-      double const gz[4] = {g0.z, g1.z, g2.z, g3.z};
       double position_error[3], velocity_error[3];
       double dqh[3], dvh[3];
 #pragma unroll
@@ -391,12 +433,12 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
         double sum_b_hat = 0.0, sum_b = 0.0, sum_b_hat_prime = 0.0,
                sum_b_prime = 0.0;
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          double const gs = k == 0 ? gx[s] : (k == 1 ? gy[s] : gz[s]);
-          sum_b_hat += b_hat[s] * gs;
-          sum_b += b[s] * gs;
-          sum_b_hat_prime += b_hat_prime[s] * gs;
-          sum_b_prime += b_prime[s] * gs;
+        for (int s = 0; s < kStages; ++s) {
+          double const gs = k == 0 ? g[s].x : (k == 1 ? g[s].y : g[s].z);
+          sum_b_hat += Method::b_hat(s) * gs;
+          sum_b += Method::b(s) * gs;
+          sum_b_hat_prime += Method::b_hat_prime(s) * gs;
+          sum_b_prime += Method::b_prime(s) * gs;
         }
         dqh[k] = h * v[k].value + h2 * sum_b_hat;
         double const dq_low = h * v[k].value + h2 * sum_b;
@@ -419,11 +461,11 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
         if (status == PB_OK) {
           status = step_status;
         }
-        // first_same_as_last: swap(g.front(), g.back()).
-        {
-          Vec3 const front = g0;
-          g0 = g3;
-          g3 = front;
+        if constexpr (Method::kFirstSameAsLast) {
+          // swap(g.front(), g.back()).
+          Vec3 const front = g[0];
+          g[0] = g[kStages - 1];
+          g[kStages - 1] = front;
           first_stage = 1;
         }
         Increment(t, h);

@@ -201,13 +201,14 @@ class Ephemeris:
 
   def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
                               speed_tolerance, max_steps=2**62,
-                              step_log_capacity=0, sink=None, burns=None):
+                              step_log_capacity=0, sink=None, burns=None,
+                              method=_capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM):
     """FlowWithAdaptiveStep, one trajectory per probe.  state: (12, n),
     time: (2, n); updated in place (host buffers)."""
     assert state.flags.c_contiguous and time.flags.c_contiguous
     n = state.shape[1]
     flow = _capi.AdaptiveStepFlow()
-    flow.method = _capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM
+    flow.method = method
     flow.t_final = t_final
     flow.length_integration_tolerance = length_tolerance
     flow.speed_integration_tolerance = speed_tolerance

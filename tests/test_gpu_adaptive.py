@@ -194,3 +194,87 @@ def test_reference_earth_probe(sol_system, integrator, expected_size):
   result = gpu.flow_with_adaptive_step(np.inf, state, time, 1e-9, 2.6e-15,
                                        max_steps=1000000, burns=burns)
   assert result['status'][0] == 4 and time[0, 0] == t_max
+
+
+def test_generalized_flow_fine1987rkng34_matches_oracle(sol_system, sol_oracle,
+                                                        sol_gpu):
+  """The generalized FlowWithAdaptiveStep (ephemeris_body.hpp:446-478) with
+  Fine1987RKNG34, the plugin's burn integrator, with and without (time-only)
+  intrinsic accelerations: the oracle's accepted steps and states."""
+  n = 48
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  state = workloads.eccentric_probes(n, earth['q'], earth['v'], earth['mu'],
+                                     19)
+  rng = np.random.default_rng(6)
+  burns = np.zeros((8, n))
+  burns[2] = 1.0
+  burns[3] = rng.uniform(1e3, 5e5, n)
+  burns[4] = 2e4
+  burns[5] = burns[3] / (9.80665 * 300.0)
+  burns[6] = rng.uniform(0.0, 2000.0, n)
+  burns[7] = burns[6] + 300.0
+  method = _capi.FINE_1987_RKNG_34
+  for table in (None, burns):
+    gpu_state, gpu_time = state.copy(), np.zeros((2, n))
+    expected_state, expected_time = state.copy(), np.zeros((2, n))
+    capacity = 3000
+    result = sol_gpu.flow_with_adaptive_step(
+        5000.0, gpu_state, gpu_time, 1e-3, 1e-3, step_log_capacity=capacity,
+        burns=table, method=method)
+    expected = sol_oracle.flow_with_adaptive_step(
+        5000.0, expected_state, expected_time, 1e-3, 1e-3,
+        step_log_capacity=capacity, burns=table, method=method)
+    assert list(result['accepted']) == list(expected['accepted'])
+    assert list(result['rejected']) == list(expected['rejected'])
+    # 5 stages, no FSAL: 5 evaluations per attempt.
+    assert list(result['evaluations']) == list(
+        5 * (expected['accepted'] + expected['rejected']))
+    assert result['accepted'].max() < capacity
+    assert_bitwise_equal(result['step_log'], expected['step_log'], 'step log')
+    assert_bitwise_equal(gpu_state, expected_state, 'state')
+
+
+@pytest.mark.parametrize('integrator', [
+    _capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, _capi.QUINLAN_1999_ORDER_8A])
+def test_reference_elephant_at_the_pole(sol_system, integrator):
+  """physics/ephemeris_test.cpp:682-759 on the GPU: 5 points, the abscissa of
+  the elephant -9.8(1)e-19 m because the cosine of 90 degrees is not zero."""
+  import earth_probe
+  from principia_b200.ephemeris import Ephemeris
+  from oracle_lib import OracleEphemeris
+  t0 = earth_probe.T0
+  polar_radius = 6.3568e6
+  earth_only = sol_system.copy()
+  for name in list(earth_only.names()):
+    if name != 'Earth':
+      earth_only.remove_massive_body(name)
+  earth_only.limit_oblateness_to_degree('Earth', 2)
+  earth_only.limit_oblateness_to_zonal('Earth')
+  oracle = OracleEphemeris(earth_only, method=integrator, step=1.0 / 100,
+                           fitting_tolerance=5e-3,
+                           initial_positions=np.zeros((1, 3)),
+                           initial_velocities=np.zeros((1, 3)),
+                           initial_time=t0)
+  assert oracle.prolong(t0 + 1.0) == 0
+  gpu = Ephemeris(earth_only)
+  gpu.append_segments(0, oracle.segments(0))
+  state = np.zeros((12, 1))
+  state[2, 0] = polar_radius
+  time = np.zeros((2, 1))
+  time[0, 0] = t0
+  expected_state, expected_time = state.copy(), time.copy()
+  result = gpu.flow_with_adaptive_step(
+      t0 + 1.0, state, time, 1e-9, 2.6e-15, max_steps=1000000,
+      method=_capi.FINE_1987_RKNG_34)
+  oracle.flow_with_adaptive_step(
+      t0 + 1.0, expected_state, expected_time, 1e-9, 2.6e-15,
+      max_steps=1000000, method=_capi.FINE_1987_RKNG_34)
+  assert int(result['accepted'][0]) + 1 == 5
+  assert_bitwise_equal(state, expected_state, 'elephant')
+  assert -9.9e-19 <= state[0, 0] <= -9.7e-19
+  assert 5.9e-35 <= state[1, 0] <= 6.1e-35
+  assert abs(state[2, 0] - polar_radius) / polar_radius < 8e-7
+  acceleration, _ = gpu.compute_gravitational_acceleration_on_massless_bodies(
+      time[0, 0], np.ascontiguousarray(state[0:3]))
+  assert -2.1e-18 <= acceleration[0, 0] <= -1.9e-18
+  assert abs(acceleration[2, 0] + 9.832) / 9.832 < 6.7e-6
