@@ -277,6 +277,31 @@ int32_t orc_newhall_fit(double const* times, double const* q, double const* v,
   return status;
 }
 
+// Newhall fit of a given degree to 9 equally spaced samples of one scalar
+// function and its derivative, evaluated (value and derivative, Estrin) at n
+// times: the shape of NewhallTest::CheckNewhallApproximationErrors with the
+// MonomialAdapter, numerics/newhall_test.cpp:181-230.
+int32_t orc_newhall_fixed_degree(int32_t degree, double const* q,
+                                 double const* v, double t_min, double t_max,
+                                 double* error_estimate, int64_t n,
+                                 double const* times, double* values,
+                                 double* derivatives) {
+  ContinuousTrajectory trajectory((t_max - t_min) / 8, 0.0);
+  std::vector<std::pair<Vec3, Vec3>> qvs;
+  for (int i = 0; i < 9; ++i) {
+    qvs.push_back({Vec3{q[i], 0, 0}, Vec3{v[i], 0, 0}});
+  }
+  Vec3 estimate;
+  Segment const s = trajectory.Newhall(degree, qvs, t_min, t_max, estimate);
+  *error_estimate = estimate.x;
+  for (int64_t i = 0; i < n; ++i) {
+    double const x = times[i] - s.origin;
+    values[i] = EstrinEvaluate(&s.c[0][0], 3, 0, s.degree, x);
+    derivatives[i] = EstrinEvaluateDerivative(&s.c[0][0], 3, 1, s.degree - 1, x);
+  }
+  return kOk;
+}
+
 // A ContinuousTrajectory of its own (physics/continuous_trajectory_body.hpp):
 // Append, t_min / t_max, EvaluatePosition / EvaluateVelocity.
 struct orc_continuous_trajectory {

@@ -703,6 +703,7 @@ class ContinuousTrajectory {
     Vec3 q, v;
   };
 
+ public:
   // numerics/newhall_body.hpp:52-117,259-287.
   Segment Newhall(int degree, std::vector<std::pair<Vec3, Vec3>> const& qvs,
                   double t_min, double t_max, Vec3& error_estimate) const {

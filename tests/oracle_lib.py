@@ -40,6 +40,8 @@ _SYMBOLS = [
     ('orc_chebyshev_evaluate_derivative', _d, [_dp, _i32, _d, _d, _d]),
     ('orc_newhall_fit', _i32,
      [_dp, _dp, _dp, _d, _d, _dp, _dp, _i32p, _dp]),
+    ('orc_newhall_fixed_degree', _i32,
+     [_i32, _dp, _dp, _d, _d, _dp, _i64, _dp, _dp, _dp]),
     ('orc_ephemeris_create', _i32,
      [_i32, ctypes.POINTER(_capi.Body), _dp, _dp, _d, _d, _d, _i32, _d,
       ctypes.POINTER(_vp)]),

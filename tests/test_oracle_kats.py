@@ -702,3 +702,66 @@ def test_internal_body_order():
       [b['name'] for b in system.bodies if b['oblate']], reverse=True)
   assert names[11:] == sorted(
       [b['name'] for b in system.bodies if not b['oblate']])
+
+
+# numerics/newhall_test.cpp:147-240 (fixture), :511-780 (the
+# ApproximationInMonomialBasis_<function>_<degree> figures, extracted into
+# tests/golden/newhall_kats.json by tools/make_newhall_kats.py).
+def _newhall_cases():
+  import json
+  import os
+  path = os.path.join(os.path.dirname(__file__), 'golden', 'newhall_kats.json')
+  return json.load(open(path))['cases']
+
+
+@pytest.mark.parametrize(
+    'case', _newhall_cases(),
+    ids=lambda c: 'function%d_degree%d' % (c['function'], c['degree']))
+def test_newhall_approximation_in_monomial_basis(case):
+  t_min, t_max = -1.0, 3.0
+  if case['function'] == 1:
+    length = lambda t: 0.5 + 2 * math.sin((t - t_min) / 0.3) * math.exp(
+        (t - t_min) / 1)
+    speed = lambda t: ((2 / 0.3) * math.cos((t - t_min) / 0.3) + 2 * math.sin(
+        (t - t_min) / 0.3)) * math.exp((t - t_min) / 1)
+  else:
+    length = lambda t: 5 * (1 + (t - t_min) / 0.3 + math.pow(
+        (t - t_min) / 4, 7))
+    speed = lambda t: 5 * (1 / 0.3 + (7 / 4) * math.pow((t - t_min) / 4, 6))
+
+  def instants(step):
+    result = []
+    t = t_min
+    while t <= t_max:
+      result.append(t)
+      t += step
+    return result
+
+  nodes = instants(0.5)
+  assert len(nodes) == 9
+  q = np.array([length(t) for t in nodes])
+  v = np.array([speed(t) for t in nodes])
+  times = np.array(instants(0.05))
+  values = np.empty_like(times)
+  derivatives = np.empty_like(times)
+  estimate = ctypes.c_double()
+  dptr = oracle_lib.dptr
+  status = oracle_lib.library().orc_newhall_fixed_degree(
+      case['degree'], dptr(q), dptr(v), t_min, t_max, ctypes.byref(estimate),
+      len(times), dptr(times), dptr(values), dptr(derivatives))
+  assert status == 0
+  value_error = max(abs(length(t) - x) for t, x in zip(times, values))
+  variation_error = max(abs(speed(t) - x) for t, x in zip(times, derivatives))
+
+  def near(value, figure):
+    text, ulp = figure
+    assert ulp == 1
+    mantissa = text.split('e')[0]
+    digits = len(mantissa.replace('.', '').replace('-', ''))
+    return is_near(value, float(text), digits=digits)
+
+  assert near(abs(estimate.value), case['error_estimate'])
+  # The oracle adopts the FMA-present semantics.
+  expected = case['value_error_with_fma'] or case['value_error']
+  assert near(value_error, expected), (value_error, expected)
+  assert near(variation_error, case['variation_error']), variation_error
