@@ -203,6 +203,87 @@ class Ephemeris {
     return a[b1];
   }
 
+  // The point-mass tidal form −𝟙/‖Δq‖³ + 3 Δq⊗Δq/‖Δq‖⁵ of :546-553,
+  // :1196-1203, :1234-1241, as the R3x3Matrix arithmetic it expands to
+  // (geometry/symmetric_bilinear_form_body.hpp:279-357,406-412;
+  // geometry/r3x3_matrix_body.hpp:277-306,354-398): (−𝟙)/n³ entry by entry
+  // (the off-diagonal ones are −0/n³), (3·(Δq_i·Δq_j))/n⁵, then the sum.
+  struct Form {
+    double m[3][3];
+  };
+  static Form TidalForm(Vec3 const& dq) {
+    double const dq2 = Norm2(dq);
+    double const dq_norm = std::sqrt(dq2);
+    double const dq_norm3 = dq2 * dq_norm;
+    double const dq_norm5 = dq_norm3 * dq2;
+    double const c[3] = {dq.x, dq.y, dq.z};
+    Form form;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        double const identity = (i == j ? -1.0 : -0.0) / dq_norm3;
+        double const square = (3 * (c[i] * c[j])) / dq_norm5;
+        form.m[i][j] = identity + square;
+      }
+    }
+    return form;
+  }
+  // form * Δv: a Dot per row (r3x3_matrix_body.hpp:327-337).
+  static Vec3 Apply(Form const& f, Vec3 const& v) {
+    return {f.m[0][0] * v.x + f.m[0][1] * v.y + f.m[0][2] * v.z,
+            f.m[1][0] * v.x + f.m[1][1] * v.y + f.m[1][2] * v.z,
+            f.m[2][0] * v.x + f.m[2][1] * v.y + f.m[2][2] * v.z};
+  }
+
+  // ComputeGravitationalJerkOnMasslessBody, :524-561 (point masses only).
+  Vec3 ComputeGravitationalJerkOnMasslessBody(Vec3 const& q, Vec3 const& v,
+                                              double t) const {
+    Vec3 jerk{};
+    for (int b2 = 0; b2 < size(); ++b2) {
+      Vec3 const q2 = trajectories_[b2]->EvaluatePosition(t);
+      Vec3 const v2 = trajectories_[b2]->EvaluateVelocity(t);
+      Vec3 const dq = q - q2;
+      Vec3 const dv = v - v2;
+      Vec3 const vector = Apply(TidalForm(dq), dv);
+      jerk += bodies_[b2]->mu * vector;
+    }
+    return jerk;
+  }
+
+  // ComputeGravitationalJerkOnMassiveBody, :1317-1340 with :1211-1247: the
+  // bodies before b1, then those after it (internal order).
+  Vec3 ComputeGravitationalJerkOnMassiveBody(int b1, std::vector<Vec3> const& q,
+                                             std::vector<Vec3> const& v) const {
+    Vec3 jerk{};
+    for (int b2 = 0; b2 < size(); ++b2) {
+      if (b2 == b1) {
+        continue;
+      }
+      Vec3 const dq = q[b1] - q[b2];
+      Vec3 const dv = v[b1] - v[b2];
+      Vec3 const vector = Apply(TidalForm(dq), dv);
+      jerk += bodies_[b2]->mu * vector;
+    }
+    return jerk;
+  }
+
+  // ComputeJacobianOnMassiveBody, :495-522 with :1174-1209.
+  Form ComputeJacobianOnMassiveBody(int b1, std::vector<Vec3> const& q) const {
+    Form jacobian{};
+    for (int b2 = 0; b2 < size(); ++b2) {
+      if (b2 == b1) {
+        continue;
+      }
+      Form const form = TidalForm(q[b1] - q[b2]);
+      double const mu2 = bodies_[b2]->mu;
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) {
+          jacobian.m[i][j] = jacobian.m[i][j] + mu2 * form.m[i][j];
+        }
+      }
+    }
+    return jacobian;
+  }
+
   std::vector<Vec3> EvaluateAllVelocities(double t) const {
     std::vector<Vec3> v;
     for (auto const& trajectory : trajectories_) {

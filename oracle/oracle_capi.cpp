@@ -566,6 +566,81 @@ int32_t orc_compute_gravitational_acceleration_on_massive_bodies(
   return kOk;
 }
 
+// Ephemeris::ComputeGravitationalJerkOnMasslessBody (batched),
+// ephemeris_body.hpp:524-561.  SoA q, v, jerk.
+int32_t orc_compute_gravitational_jerk_on_massless_bodies(
+    orc_ephemeris* e, double t, std::int64_t n, double const* q,
+    double const* v, double* jerk) {
+#pragma omp parallel for schedule(static)
+  for (std::int64_t i = 0; i < n; ++i) {
+    Vec3 const j = e->e->ComputeGravitationalJerkOnMasslessBody(
+        {q[i], q[n + i], q[2 * n + i]}, {v[i], v[n + i], v[2 * n + i]}, t);
+    jerk[i] = j.x;
+    jerk[n + i] = j.y;
+    jerk[2 * n + i] = j.z;
+  }
+  return kOk;
+}
+
+namespace {
+void DegreesOfFreedomInInternalOrder(orc_ephemeris* e, double t,
+                                     double const* positions,
+                                     double const* velocities,
+                                     std::vector<Vec3>& q,
+                                     std::vector<Vec3>& v) {
+  int const n = e->e->size();
+  q.resize(n);
+  v.resize(n);
+  if (positions == nullptr) {
+    q = e->e->EvaluateAllPositions(t);
+    v = e->e->EvaluateAllVelocities(t);
+  } else {
+    for (int i = 0; i < n; ++i) {
+      int const caller = e->e->order()[i];
+      q[i] = {positions[3 * caller], positions[3 * caller + 1],
+              positions[3 * caller + 2]};
+      if (velocities != nullptr) {
+        v[i] = {velocities[3 * caller], velocities[3 * caller + 1],
+                velocities[3 * caller + 2]};
+      }
+    }
+  }
+}
+}  // namespace
+
+// Ephemeris::ComputeGravitationalJerkOnMassiveBody(body, t) (positions ==
+// nullptr) / ...OnMassiveBodies(bodies, degrees of freedom),
+// ephemeris_body.hpp:563-605: jerks[3 * body], caller order.
+int32_t orc_compute_gravitational_jerk_on_massive_bodies(
+    orc_ephemeris* e, double t, double const* positions,
+    double const* velocities, double* jerks) {
+  std::vector<Vec3> q, v;
+  DegreesOfFreedomInInternalOrder(e, t, positions, velocities, q, v);
+  for (int i = 0; i < e->e->size(); ++i) {
+    Vec3 const j = e->e->ComputeGravitationalJerkOnMassiveBody(i, q, v);
+    int const caller = e->e->order()[i];
+    jerks[3 * caller] = j.x;
+    jerks[3 * caller + 1] = j.y;
+    jerks[3 * caller + 2] = j.z;
+  }
+  return kOk;
+}
+
+// Ephemeris::ComputeJacobianOnMassiveBody, ephemeris_body.hpp:495-522:
+// jacobians[9 * body], row-major, caller order.
+int32_t orc_compute_jacobian_on_massive_bodies(orc_ephemeris* e, double t,
+                                               double const* positions,
+                                               double* jacobians) {
+  std::vector<Vec3> q, v;
+  DegreesOfFreedomInInternalOrder(e, t, positions, nullptr, q, v);
+  for (int i = 0; i < e->e->size(); ++i) {
+    auto const form = e->e->ComputeJacobianOnMassiveBody(i, q);
+    int const caller = e->e->order()[i];
+    std::memcpy(jacobians + 9 * caller, form.m, 9 * sizeof(double));
+  }
+  return kOk;
+}
+
 // The RHS of the massive-body equation on a full position set (internal
 // order, AoS), ephemeris_body.hpp:1503-1552.
 int32_t orc_compute_gravitational_acceleration_between_all_massive_bodies(

@@ -42,6 +42,11 @@ _SYMBOLS = [
      [_dp, _dp, _dp, _d, _d, _dp, _dp, _i32p, _dp]),
     ('orc_newhall_fixed_degree', _i32,
      [_i32, _dp, _dp, _d, _d, _dp, _i64, _dp, _dp, _dp]),
+    ('orc_compute_gravitational_jerk_on_massless_bodies', _i32,
+     [_vp, _d, _i64, _dp, _dp, _dp]),
+    ('orc_compute_gravitational_jerk_on_massive_bodies', _i32,
+     [_vp, _d, _dp, _dp, _dp]),
+    ('orc_compute_jacobian_on_massive_bodies', _i32, [_vp, _d, _dp, _dp]),
     ('orc_ephemeris_create', _i32,
      [_i32, ctypes.POINTER(_capi.Body), _dp, _dp, _d, _d, _d, _i32, _d,
       ctypes.POINTER(_vp)]),
@@ -228,6 +233,35 @@ class OracleEphemeris:
       p = dptr(positions)
     self.lib.orc_compute_gravitational_acceleration_on_massive_bodies(
         self.handle, t, p, dptr(out))
+    return out
+
+  def jerk_on_massless_bodies(self, t, q, v):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros_like(q)
+    self.lib.orc_compute_gravitational_jerk_on_massless_bodies(
+        self.handle, t, q.shape[1], dptr(q), dptr(v), dptr(out))
+    return out
+
+  def jerk_on_massive_bodies(self, t, positions=None, velocities=None):
+    out = np.zeros((self.n, 3))
+    p = v = None
+    if positions is not None:
+      positions = np.ascontiguousarray(positions, dtype=np.float64)
+      velocities = np.ascontiguousarray(velocities, dtype=np.float64)
+      p, v = dptr(positions), dptr(velocities)
+    self.lib.orc_compute_gravitational_jerk_on_massive_bodies(
+        self.handle, t, p, v, dptr(out))
+    return out
+
+  def jacobian_on_massive_bodies(self, t, positions=None):
+    out = np.zeros((self.n, 3, 3))
+    p = None
+    if positions is not None:
+      positions = np.ascontiguousarray(positions, dtype=np.float64)
+      p = dptr(positions)
+    self.lib.orc_compute_jacobian_on_massive_bodies(self.handle, t, p,
+                                                    dptr(out))
     return out
 
   def acceleration_between_all_massive_bodies(self, t, positions_internal):

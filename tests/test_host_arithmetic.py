@@ -292,3 +292,13 @@ def test_massless_acceleration_and_potential_match_oracle(hc, unrolled):
       oracle_lib.dptr(a), potential)
   assert error == _capi.PB_OUT_OF_RANGE
   hc.hc_model_destroy(handle)
+
+
+def test_std_mt19937_64():
+  """[rand.predef]: the 10000th consecutive invocation of a default-constructed
+  std::mt19937_64 produces 9981545732273789042."""
+  from std_random import Mt19937_64
+  random = Mt19937_64()
+  for _ in range(9999):
+    random()
+  assert random() == 9981545732273789042
