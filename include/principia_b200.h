@@ -154,6 +154,34 @@ pb_status_t pb_compute_gravitational_potential(pb_ephemeris_t* ephemeris,
                                                const double* q,
                                                double* potential);
 
+/* trajectory(body)->EvaluateVelocity(t) for every body
+ * (continuous_trajectory_body.hpp:697-706, with EvaluateAllPositions the
+ * EvaluateDegreesOfFreedom the jerk routines use): velocities[3*body]. */
+pb_status_t pb_ephemeris_evaluate_all_velocities(pb_ephemeris_t* ephemeris,
+                                                 double t,
+                                                 double* velocities);
+
+/* Ephemeris::ComputeGravitationalJerkOnMasslessBody (batched),
+ * ephemeris.hpp:233-237, ephemeris_body.hpp:524-561: point masses only, like
+ * the reference.  SoA: q, v, jerk = [x[n] y[n] z[n]]. */
+pb_status_t pb_compute_gravitational_jerk_on_massless_bodies(
+    pb_ephemeris_t* ephemeris, double t, int64_t n, const double* q,
+    const double* v, double* jerk);
+pb_status_t pb_compute_gravitational_jerk_on_massless_bodies_device(
+    pb_ephemeris_t* ephemeris, double t, int64_t n, const double* q,
+    const double* v, double* jerk, void* stream);
+
+/* Ephemeris::ComputeGravitationalJerkOnMassiveBody(body, t) (positions ==
+ * NULL: degrees of freedom evaluated at t from the trajectories) and
+ * ...OnMassiveBodies(bodies, degrees of freedom) (positions, velocities AoS
+ * [body][xyz], caller order), ephemeris.hpp:239-250,
+ * ephemeris_body.hpp:563-605,1317-1340; Ephemeris::ComputeJacobianOnMassiveBody,
+ * ephemeris.hpp:226-231, ephemeris_body.hpp:495-522.  For every body:
+ * jerks[3*body] and jacobians[9*body] (row-major); either may be NULL. */
+pb_status_t pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies(
+    pb_ephemeris_t* ephemeris, double t, const double* positions,
+    const double* velocities, double* jerks, double* jacobians);
+
 /* Ephemeris::ComputeGravitationalAccelerationOnMassiveBodies,
  * ephemeris.hpp:276-280 (positions given, AoS [body][xyz], caller order) and
  * ...OnMassiveBody, :268-271 (positions == NULL: evaluated at t from the

@@ -123,6 +123,13 @@ SYMBOLS = [
      [_vp, _d, _i64, c_double_p, c_double_p]),
     ('pb_compute_gravitational_acceleration_on_massive_bodies', _i32,
      [_vp, _d, c_double_p, c_double_p]),
+    ('pb_ephemeris_evaluate_all_velocities', _i32, [_vp, _d, c_double_p]),
+    ('pb_compute_gravitational_jerk_on_massless_bodies', _i32,
+     [_vp, _d, _i64, c_double_p, c_double_p, c_double_p]),
+    ('pb_compute_gravitational_jerk_on_massless_bodies_device', _i32,
+     [_vp, _d, _i64, _vp, _vp, _vp, _vp]),
+    ('pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies', _i32,
+     [_vp, _d, c_double_p, c_double_p, c_double_p, c_double_p]),
     ('pb_flow_with_fixed_step', _i32, [_vp, ctypes.POINTER(FixedStepFlow)]),
     ('pb_flow_with_fixed_step_device', _i32,
      [_vp, ctypes.POINTER(FixedStepFlow), _vp]),

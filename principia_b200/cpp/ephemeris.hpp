@@ -14,6 +14,8 @@
 //       t, AdaptiveStepParameters, max_steps)         AdaptiveStepParameters, max_steps)
 //   ComputeGravitationalAccelerationOnMasslessBody, ...OnMassiveBody,
 //   ...OnMassiveBodies, ComputeGravitationalPotential, EvaluateAllPositions,
+//   ComputeGravitationalJerkOnMasslessBody, ...OnMassiveBody/Bodies,
+//   ComputeJacobianOnMassiveBody,
 //   t_min, t_max: same names.
 // Intrinsic accelerations: none, or a tabulated inertially fixed burn (host
 // callbacks are not supported).
@@ -454,6 +456,70 @@ class Ephemeris {
                                        double& potential) {
     return Status::FromCall(pb_compute_gravitational_potential(
         ephemeris_, t, 1, position, &potential));
+  }
+
+  // physics/ephemeris_body.hpp:524-561 (point masses only, like the
+  // reference).
+  Status ComputeGravitationalJerkOnMasslessBody(
+      DegreesOfFreedom const& degrees_of_freedom, double const t,
+      double (&jerk)[3]) {
+    return Status::FromCall(pb_compute_gravitational_jerk_on_massless_bodies(
+        ephemeris_, t, 1, degrees_of_freedom.q, degrees_of_freedom.v, jerk));
+  }
+
+  // Batched form: q, v and jerk are 3 planes of n.
+  Status ComputeGravitationalJerkOnMasslessBodies(
+      double const t, std::int64_t const n, double const* const q,
+      double const* const v, double* const jerk) {
+    return Status::FromCall(pb_compute_gravitational_jerk_on_massless_bodies(
+        ephemeris_, t, n, q, v, jerk));
+  }
+
+  // physics/ephemeris_body.hpp:563-583: the jerk on the massive `body` (caller
+  // index) at t.
+  Status ComputeGravitationalJerkOnMassiveBody(int32_t const body,
+                                               double const t,
+                                               double (&jerk)[3]) {
+    std::vector<double> jerks(3 * static_cast<std::size_t>(n_bodies_));
+    Status const status = Status::FromCall(
+        pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies(
+            ephemeris_, t, nullptr, nullptr, jerks.data(), nullptr));
+    for (int c = 0; c < 3; ++c) {
+      jerk[c] = jerks[3 * body + c];
+    }
+    return status;
+  }
+
+  // physics/ephemeris_body.hpp:585-605: every body, on degrees of freedom
+  // precomputed by the caller ([3 * body], caller order).
+  Status ComputeGravitationalJerkOnMassiveBodies(
+      std::vector<double> const& positions,
+      std::vector<double> const& velocities, std::vector<double>& jerks) {
+    jerks.assign(3 * static_cast<std::size_t>(n_bodies_), 0.0);
+    return Status::FromCall(
+        pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies(
+            ephemeris_, 0.0, positions.data(), velocities.data(), jerks.data(),
+            nullptr));
+  }
+
+  // physics/ephemeris_body.hpp:495-522: row-major 3x3.
+  Status ComputeJacobianOnMassiveBody(int32_t const body, double const t,
+                                      double (&jacobian)[9]) {
+    std::vector<double> jacobians(9 * static_cast<std::size_t>(n_bodies_));
+    Status const status = Status::FromCall(
+        pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies(
+            ephemeris_, t, nullptr, nullptr, nullptr, jacobians.data()));
+    for (int k = 0; k < 9; ++k) {
+      jacobian[k] = jacobians[9 * body + k];
+    }
+    return status;
+  }
+
+  // trajectory(body)->EvaluateVelocity(t) for every body; [3 * body].
+  Status EvaluateAllVelocities(double const t, std::vector<double>& velocities) {
+    velocities.assign(3 * static_cast<std::size_t>(n_bodies_), 0.0);
+    return Status::FromCall(
+        pb_ephemeris_evaluate_all_velocities(ephemeris_, t, velocities.data()));
   }
 
   // physics/ephemeris_body.hpp:226-236; [3 * body], caller order.

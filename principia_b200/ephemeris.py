@@ -130,6 +130,56 @@ class Ephemeris:
         self.handle, t, pointer, _dptr(out)))
     return out
 
+  def evaluate_all_velocities(self, t):
+    out = np.zeros((self.n_bodies, 3))
+    _check(self.lib.pb_ephemeris_evaluate_all_velocities(self.handle, t,
+                                                         _dptr(out)))
+    return out
+
+  def compute_gravitational_jerk_on_massless_bodies(self, t, q, v):
+    """q, v: (3, n) degrees of freedom.  Returns the (3, n) jerks
+    (Ephemeris::ComputeGravitationalJerkOnMasslessBody, batched)."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    assert q.shape == v.shape
+    out = np.zeros_like(q)
+    _check(self.lib.pb_compute_gravitational_jerk_on_massless_bodies(
+        self.handle, t, q.shape[1], _dptr(q), _dptr(v), _dptr(out)))
+    return out
+
+  def compute_gravitational_jerk_on_massless_bodies_device(
+      self, t, n, q_pointer, v_pointer, jerk_pointer, stream=None):
+    _check(self.lib.pb_compute_gravitational_jerk_on_massless_bodies_device(
+        self.handle, t, n, q_pointer, v_pointer, jerk_pointer, stream))
+
+  def _jerk_and_jacobian(self, t, positions, velocities, want_jerks,
+                         want_jacobians):
+    jerks = np.zeros((self.n_bodies, 3)) if want_jerks else None
+    jacobians = np.zeros((self.n_bodies, 3, 3)) if want_jacobians else None
+    p = v = None
+    if positions is not None:
+      positions = np.ascontiguousarray(positions, dtype=np.float64)
+      p = _dptr(positions)
+      if velocities is not None:
+        velocities = np.ascontiguousarray(velocities, dtype=np.float64)
+        v = _dptr(velocities)
+    _check(
+        self.lib.pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies(
+            self.handle, t, p, v, None if jerks is None else _dptr(jerks),
+            None if jacobians is None else _dptr(jacobians)))
+    return jerks, jacobians
+
+  def compute_gravitational_jerk_on_massive_bodies(self, t, positions=None,
+                                                   velocities=None):
+    """Ephemeris::ComputeGravitationalJerkOnMassiveBody for every body: at t
+    from the trajectories, or on the given degrees of freedom ((n, 3), caller
+    order)."""
+    return self._jerk_and_jacobian(t, positions, velocities, True, False)[0]
+
+  def compute_jacobian_on_massive_bodies(self, t, positions=None):
+    """Ephemeris::ComputeJacobianOnMassiveBody for every body: (n, 3, 3)."""
+    return self._jerk_and_jacobian(t, positions, None, False, True)[1]
+
   # -- flows ----------------------------------------------------------------
   def _fixed_step_flow(self, method, step, t_final, n, state_pointer, time,
                        sample_every, max_samples, samples_pointer,

@@ -164,4 +164,29 @@ int32_t ft_acceleration_on_massless_body(void* e, double const* position,
   return status.code;
 }
 
+int32_t ft_jerk_and_jacobian(void* e, double const* q, double const* v,
+                             int32_t body, double t, double* massless_jerk,
+                             double* massive_jerk, double* jacobian) {
+  Ephemeris* const ephemeris = static_cast<Ephemeris*>(e);
+  DegreesOfFreedom dof;
+  for (int c = 0; c < 3; ++c) {
+    dof.q[c] = q[c];
+    dof.v[c] = v[c];
+  }
+  double j1[3], j2[3], jac[9];
+  Status status = ephemeris->ComputeGravitationalJerkOnMasslessBody(dof, t, j1);
+  if (status.code != 0) {
+    return status.code;
+  }
+  status = ephemeris->ComputeGravitationalJerkOnMassiveBody(body, t, j2);
+  if (status.code != 0) {
+    return status.code;
+  }
+  status = ephemeris->ComputeJacobianOnMassiveBody(body, t, jac);
+  std::memcpy(massless_jerk, j1, sizeof(j1));
+  std::memcpy(massive_jerk, j2, sizeof(j2));
+  std::memcpy(jacobian, jac, sizeof(jac));
+  return status.code;
+}
+
 }  // extern "C"

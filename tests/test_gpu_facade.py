@@ -48,6 +48,7 @@ def shim():
   lib.ft_flow_with_adaptive_step.argtypes = [_vp, _dp, _dp, _d, _d, _d, _d,
                                              _i64, _i64, _i64p, _dp, _dp]
   lib.ft_acceleration_on_massless_body.argtypes = [_vp, _dp, _d, _dp]
+  lib.ft_jerk_and_jacobian.argtypes = [_vp, _dp, _dp, _i32, _d, _dp, _dp, _dp]
   return lib
 
 
@@ -159,6 +160,23 @@ def test_facade_prolong_and_flows(shim, sol_system):
   expected_a, _ = oracle.acceleration_on_massless_bodies(100.0,
                                                          q1.reshape(3, 1))
   assert_bitwise_equal(a, expected_a.ravel())
+
+  # Jerk and Jacobian queries.
+  v1 = np.array([1.0e3, -2.0e3, 0.5e3])
+  earth = system.index('Earth')
+  massless_jerk, massive_jerk, jacobian = np.zeros(3), np.zeros(3), np.zeros(9)
+  assert shim.ft_jerk_and_jacobian(
+      handle, oracle_lib.dptr(q1), oracle_lib.dptr(v1), earth, 100.0,
+      oracle_lib.dptr(massless_jerk), oracle_lib.dptr(massive_jerk),
+      oracle_lib.dptr(jacobian)) == 0
+  assert_bitwise_equal(
+      massless_jerk,
+      oracle.jerk_on_massless_bodies(100.0, q1.reshape(3, 1),
+                                     v1.reshape(3, 1)).ravel())
+  assert_bitwise_equal(massive_jerk,
+                       oracle.jerk_on_massive_bodies(100.0)[earth])
+  assert_bitwise_equal(jacobian.reshape(3, 3),
+                       oracle.jacobian_on_massive_bodies(100.0)[earth])
   shim.ft_destroy(handle)
 
 
