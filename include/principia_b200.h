@@ -395,6 +395,66 @@ pb_status_t pb_nbody_ensemble_solve_recording(pb_nbody_ensemble_t* ensemble,
 pb_status_t pb_nbody_ensemble_get_state(pb_nbody_ensemble_t* ensemble,
                                         double* state, double* time);
 
+/* ---- ContinuousTrajectory production on the device.
+ * A batch of n ContinuousTrajectory objects appended in lockstep with equally
+ * spaced degrees of freedom -- the bodies of one ephemeris, or of every member
+ * of an ensemble: ContinuousTrajectory::Append with
+ * ComputeBestNewhallApproximation (physics/continuous_trajectory_body.hpp
+ * :82-127,758-858) and NewhallApproximationInMonomialBasis
+ * (numerics/newhall_body.hpp:52-117,259-287) run in one kernel every 8 points,
+ * one thread per trajectory; the polynomials stay in device memory
+ * ([segment][xyz][18][n], sized for `max_segments`) and are evaluated there
+ * (EvaluatePosition / EvaluateVelocity, :686-722).
+ * `step` and `tolerance` are the constructor's (:60-80). */
+typedef struct pb_continuous_trajectories pb_continuous_trajectories_t;
+pb_status_t pb_continuous_trajectories_create(
+    int32_t device, int64_t n_trajectories, double step, double tolerance,
+    int64_t max_segments, pb_continuous_trajectories_t** trajectories);
+void pb_continuous_trajectories_destroy(
+    pb_continuous_trajectories_t* trajectories);
+/* Append(time, degrees of freedom) for every trajectory; q, v: 3 planes of n.
+ * The host variant returns PB_INVALID_ARGUMENT if any trajectory hit the
+ * "apocalypse" (:851-857); the device variant is asynchronous on `stream`
+ * (q, v in device memory) and leaves that to ..._status. */
+pb_status_t pb_continuous_trajectories_append(
+    pb_continuous_trajectories_t* trajectories, double time, const double* q,
+    const double* v);
+pb_status_t pb_continuous_trajectories_append_device(
+    pb_continuous_trajectories_t* trajectories, double time, const double* q,
+    const double* v, void* stream);
+pb_status_t pb_continuous_trajectories_status(
+    pb_continuous_trajectories_t* trajectories);
+double pb_continuous_trajectories_t_min(
+    const pb_continuous_trajectories_t* trajectories);
+double pb_continuous_trajectories_t_max(
+    const pb_continuous_trajectories_t* trajectories);
+int64_t pb_continuous_trajectories_segment_count(
+    const pb_continuous_trajectories_t* trajectories);
+/* The polynomials of one trajectory, in the layout of
+ * pb_ephemeris_append_segments: t_max[s], origin[s], degree[s],
+ * coefficients[s][18][3] (zero above the degree); any may be NULL. */
+pb_status_t pb_continuous_trajectories_get_segments(
+    pb_continuous_trajectories_t* trajectories, int64_t trajectory,
+    double* t_min, double* t_max, double* origin, int32_t* degree,
+    double* coefficients);
+/* EvaluatePosition / EvaluateVelocity of every trajectory at t: 3 planes of n
+ * each; either may be NULL. */
+pb_status_t pb_continuous_trajectories_evaluate(
+    pb_continuous_trajectories_t* trajectories, double t, double* positions,
+    double* velocities);
+pb_status_t pb_continuous_trajectories_evaluate_device(
+    pb_continuous_trajectories_t* trajectories, double t, double* positions,
+    double* velocities, void* stream);
+/* Instance::Solve(t_final) of the ensemble with append_state =
+ * Ephemeris::AppendMassiveBodiesState (ephemeris_body.hpp:1071-1116) on the
+ * device: every appended state goes to `trajectories` (n = n_bodies *
+ * n_systems, trajectory = body (internal order) * n_systems + system) without
+ * leaving the GPU.  If the trajectories are empty the current state is
+ * appended first (the Ephemeris constructor, :136). */
+pb_status_t pb_nbody_ensemble_solve_to_trajectories(
+    pb_nbody_ensemble_t* ensemble, double t_final,
+    pb_continuous_trajectories_t* trajectories, int64_t* n_steps);
+
 /* ---- Large-N all-pairs point-mass system (synthetic; the same
  * ComputeGravitationalAccelerationBetweenAllMassiveBodies with only spherical
  * bodies, ephemeris_body.hpp:1342-1380,1503-1552), Quinlan-Tremaine / SRKN.

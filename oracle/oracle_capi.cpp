@@ -333,6 +333,16 @@ int32_t orc_continuous_trajectory_degree(orc_continuous_trajectory const* t,
                                          int32_t segment) {
   return t->trajectory.segments()[segment].degree;
 }
+void orc_continuous_trajectory_get_segment(orc_continuous_trajectory const* t,
+                                           int32_t segment, double* t_max,
+                                           double* origin, int32_t* degree,
+                                           double* coefficients) {
+  Segment const& s = t->trajectory.segments()[segment];
+  *t_max = s.t_max;
+  *origin = s.origin;
+  *degree = s.degree;
+  std::memcpy(coefficients, s.c, sizeof(s.c));
+}
 void orc_continuous_trajectory_evaluate(orc_continuous_trajectory const* t,
                                         double time, double* q, double* v) {
   Vec3 const position = t->trajectory.EvaluatePosition(time);

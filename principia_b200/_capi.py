@@ -130,6 +130,25 @@ SYMBOLS = [
      [_vp, _d, _i64, _vp, _vp, _vp, _vp]),
     ('pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies', _i32,
      [_vp, _d, c_double_p, c_double_p, c_double_p, c_double_p]),
+    ('pb_continuous_trajectories_create', _i32,
+     [_i32, _i64, _d, _d, _i64, ctypes.POINTER(_vp)]),
+    ('pb_continuous_trajectories_destroy', None, [_vp]),
+    ('pb_continuous_trajectories_append', _i32,
+     [_vp, _d, c_double_p, c_double_p]),
+    ('pb_continuous_trajectories_append_device', _i32,
+     [_vp, _d, _vp, _vp, _vp]),
+    ('pb_continuous_trajectories_status', _i32, [_vp]),
+    ('pb_continuous_trajectories_t_min', _d, [_vp]),
+    ('pb_continuous_trajectories_t_max', _d, [_vp]),
+    ('pb_continuous_trajectories_segment_count', _i64, [_vp]),
+    ('pb_continuous_trajectories_get_segments', _i32,
+     [_vp, _i64, c_double_p, c_double_p, c_double_p, c_int32_p, c_double_p]),
+    ('pb_continuous_trajectories_evaluate', _i32,
+     [_vp, _d, c_double_p, c_double_p]),
+    ('pb_continuous_trajectories_evaluate_device', _i32,
+     [_vp, _d, _vp, _vp, _vp]),
+    ('pb_nbody_ensemble_solve_to_trajectories', _i32,
+     [_vp, _d, _vp, ctypes.POINTER(_i64)]),
     ('pb_flow_with_fixed_step', _i32, [_vp, ctypes.POINTER(FixedStepFlow)]),
     ('pb_flow_with_fixed_step_device', _i32,
      [_vp, ctypes.POINTER(FixedStepFlow), _vp]),

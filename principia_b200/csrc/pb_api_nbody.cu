@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <vector>
 
 #include "../../include/principia_b200.h"
@@ -251,6 +252,10 @@ struct EnsembleRecorder {
   double* times;   // capacity.
   double* states;  // capacity * 6 * n_bodies * n_systems.
   int64_t count;
+  // Or, instead of the host arrays: ContinuousTrajectory::Append on the device
+  // for every body of every system (Ephemeris::AppendMassiveBodiesState,
+  // ephemeris_body.hpp:1071-1116).
+  pb_continuous_trajectories* sink = nullptr;
 };
 
 static pb_status_t RecordStep(pb_nbody_ensemble* s, EnsembleRecorder* recorder,
@@ -260,6 +265,12 @@ static pb_status_t RecordStep(pb_nbody_ensemble* s, EnsembleRecorder* recorder,
   }
   std::size_t const plane =
       static_cast<std::size_t>(s->n_bodies) * static_cast<std::size_t>(s->n_systems);
+  if (recorder->sink != nullptr) {
+    ++recorder->count;
+    return ContinuousTrajectoriesAppendDevice(
+        recorder->sink, s->time.value, s->state.data,
+        s->state.data + 6 * plane, stream);
+  }
   double* const out = recorder->states + recorder->count * 6 * plane;
   PB_CUDA(cudaMemcpyAsync(out, s->state.data, 3 * plane * sizeof(double),
                           cudaMemcpyDeviceToHost, stream));
@@ -370,6 +381,35 @@ pb_status_t pb_nbody_ensemble_solve_recording(pb_nbody_ensemble_t* s,
   pb_status_t const status = SolveEnsemble(s, t_final, nullptr, &recorder);
   *n_recorded = recorder.count;
   return status;
+}
+
+pb_status_t pb_nbody_ensemble_solve_to_trajectories(
+    pb_nbody_ensemble_t* s, double t_final,
+    pb_continuous_trajectories_t* trajectories, int64_t* n_steps) {
+  if (s == nullptr || trajectories == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  long long const plane =
+      static_cast<long long>(s->n_bodies) * static_cast<long long>(s->n_systems);
+  if (ContinuousTrajectoriesSize(trajectories) != plane) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "one trajectory per body of every system is needed");
+  }
+  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  if (ContinuousTrajectoriesEmpty(trajectories)) {
+    // The initial state, as the Ephemeris constructor appends it
+    // (ephemeris_body.hpp:136).
+    PB_RETURN_IF_ERROR(ContinuousTrajectoriesAppendDevice(
+        trajectories, s->time.value, s->state.data, s->state.data + 6 * plane,
+        nullptr));
+  }
+  EnsembleRecorder recorder{std::numeric_limits<int64_t>::max(), nullptr,
+                            nullptr, 0, trajectories};
+  pb_status_t const status = SolveEnsemble(s, t_final, n_steps, &recorder);
+  if (status != PB_OK) {
+    return status;
+  }
+  return pb_continuous_trajectories_status(trajectories);
 }
 
 pb_status_t pb_nbody_ensemble_get_state(pb_nbody_ensemble_t* s, double* state,

@@ -238,4 +238,11 @@ double EphemerisTMin(pb_ephemeris const* e);
 double EphemerisTMax(pb_ephemeris const* e);
 pb_status_t BuildStageTable(pb_ephemeris* e, double const* times_host,
                             int n_times, double* table, cudaStream_t stream);
+// Defined in pb_api_continuous_trajectory.cu.
+pb_status_t ContinuousTrajectoriesAppendDevice(pb_continuous_trajectories* h,
+                                               double time, double const* q,
+                                               double const* v,
+                                               cudaStream_t stream);
+long long ContinuousTrajectoriesSize(pb_continuous_trajectories const* h);
+bool ContinuousTrajectoriesEmpty(pb_continuous_trajectories const* h);
 }  // namespace pb

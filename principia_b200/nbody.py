@@ -43,12 +43,93 @@ class NBodyEnsemble:
                                             ctypes.byref(n_steps)))
     return n_steps.value
 
+  def solve_to_trajectories(self, t_final, trajectories):
+    """Solve(t_final) with every appended state going to `trajectories` (a
+    ContinuousTrajectories of n_bodies * n_systems) on the device."""
+    n_steps = ctypes.c_int64()
+    _check(self.lib.pb_nbody_ensemble_solve_to_trajectories(
+        self.handle, t_final, trajectories.handle, ctypes.byref(n_steps)))
+    return n_steps.value
+
   def state(self):
     state = np.zeros(self.shape)
     time = np.zeros(2)
     _check(self.lib.pb_nbody_ensemble_get_state(self.handle, _dptr(state),
                                                 _dptr(time)))
     return state, time
+
+
+class ContinuousTrajectories:
+  """pb_continuous_trajectories_t: n ContinuousTrajectory objects appended in
+  lockstep, fitted (Newhall) and evaluated on the device."""
+
+  def __init__(self, n, step, tolerance, max_segments, device=0):
+    self.lib = _capi.library()
+    self.n = n
+    handle = _vp()
+    _check(self.lib.pb_continuous_trajectories_create(
+        device, n, step, tolerance, max_segments, ctypes.byref(handle)))
+    self.handle = handle
+
+  def close(self):
+    if getattr(self, 'handle', None):
+      self.lib.pb_continuous_trajectories_destroy(self.handle)
+      self.handle = None
+
+  def __del__(self):
+    self.close()
+
+  def append(self, time, q, v):
+    """q, v: (3, n).  Raises StatusError(PB_INVALID_ARGUMENT) on the
+    "apocalypse" of any trajectory."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    assert q.shape == v.shape == (3, self.n)
+    _check(self.lib.pb_continuous_trajectories_append(self.handle, time,
+                                                      _dptr(q), _dptr(v)))
+
+  def append_device(self, time, q_pointer, v_pointer, stream=None):
+    _check(self.lib.pb_continuous_trajectories_append_device(
+        self.handle, time, q_pointer, v_pointer, stream))
+
+  def status(self):
+    return self.lib.pb_continuous_trajectories_status(self.handle)
+
+  def t_min(self):
+    return self.lib.pb_continuous_trajectories_t_min(self.handle)
+
+  def t_max(self):
+    return self.lib.pb_continuous_trajectories_t_max(self.handle)
+
+  def segment_count(self):
+    return self.lib.pb_continuous_trajectories_segment_count(self.handle)
+
+  def segments(self, trajectory):
+    count = self.segment_count()
+    t_min = ctypes.c_double()
+    t_max = np.zeros(count)
+    origin = np.zeros(count)
+    degree = np.zeros(count, dtype=np.int32)
+    coefficients = np.zeros((count, 18, 3))
+    _check(self.lib.pb_continuous_trajectories_get_segments(
+        self.handle, trajectory, ctypes.byref(t_min), _dptr(t_max),
+        _dptr(origin), degree.ctypes.data_as(_capi.c_int32_p),
+        _dptr(coefficients)))
+    return dict(t_min=t_min.value, t_max=t_max, origin=origin, degree=degree,
+                coefficients=coefficients)
+
+  def evaluate(self, t):
+    """((3, n) positions, (3, n) velocities) at t."""
+    positions = np.zeros((3, self.n))
+    velocities = np.zeros((3, self.n))
+    _check(self.lib.pb_continuous_trajectories_evaluate(
+        self.handle, t, _dptr(positions), _dptr(velocities)))
+    return positions, velocities
+
+  def evaluate_device(self, t, positions_pointer, velocities_pointer,
+                      stream=None):
+    _check(self.lib.pb_continuous_trajectories_evaluate_device(
+        self.handle, t, positions_pointer, velocities_pointer, stream))
 
 
 class NBodyAllPairs:

@@ -36,6 +36,8 @@ _SYMBOLS = [
     ('orc_continuous_trajectory_segment_count', _i32, [_vp]),
     ('orc_continuous_trajectory_degree', _i32, [_vp, _i32]),
     ('orc_continuous_trajectory_evaluate', None, [_vp, _d, _dp, _dp]),
+    ('orc_continuous_trajectory_get_segment', None,
+     [_vp, _i32, _dp, _dp, _i32p, _dp]),
     ('orc_chebyshev_evaluate', _d, [_dp, _i32, _d, _d, _d]),
     ('orc_chebyshev_evaluate_derivative', _d, [_dp, _i32, _d, _d, _d]),
     ('orc_newhall_fit', _i32,
