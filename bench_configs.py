@@ -8,6 +8,7 @@ headline, config 2).  One JSON line per config.
 """
 import argparse
 import json
+import math
 import os
 import sys
 import time
@@ -197,6 +198,113 @@ def bench_ensemble(args):
         'pair_interactions_per_second': world * n * steps * pairs / seconds}))
 
 
+def bench_trajectories(args):
+  """ContinuousTrajectory production on the device.  (a) The
+  fit alone: n trajectories appended from device memory, one Newhall fit per 8
+  appends; HBM-bound (per trajectory and segment: 8 appended points copied
+  into the ring, 96 B read + 96 B written each; the fit reads 9 points = 432 B
+  and 20 B of state, writes 18 x 3 coefficients + degree = 436 B and the state).
+  (b) The TRAPPIST ensemble flow with and without the trajectories as its
+  append_state sink."""
+  torch, dist, world, rank, local_rank = dist_setup()
+  from principia_b200 import _capi
+  from principia_b200.ephemeris import Ephemeris
+  from principia_b200.nbody import ContinuousTrajectories, NBodyEnsemble
+  from principia_b200.solar_system import SolarSystem
+  from test_gpu_nbody import ensemble_state
+  device = torch.device('cuda', local_rank)
+  torch.cuda.set_device(device)
+  system = SolarSystem.from_fixture('trappist_jd2457000')
+  ephemeris = Ephemeris(system, device=local_rank)
+  order, _ = ephemeris.internal_order()
+  n_systems = args.systems
+  n = n_systems * len(order)
+  step = 1800.0
+  segments = 8
+  # (a) Synthetic circular motions of varied period, already on the device.
+  generator = torch.Generator(device=device).manual_seed(42 + rank)
+  period = step * 10.0**(1.3 + 3.0 * torch.rand(n, device=device,
+                                                dtype=torch.float64,
+                                                generator=generator))
+  radius = 10.0**(7 + 4 * torch.rand(n, device=device, dtype=torch.float64,
+                                     generator=generator))
+  omega = 2 * math.pi / period
+  trajectories = ContinuousTrajectories(n, step, 1e-3, segments + 1,
+                                        device=local_rank)
+  points = []
+  for k in range(8 * segments + 1):
+    angle = omega * (k * step)
+    q = torch.stack([radius * torch.cos(angle), radius * torch.sin(angle),
+                     torch.zeros_like(angle)]).contiguous()
+    v = torch.stack([-radius * omega * torch.sin(angle),
+                     radius * omega * torch.cos(angle),
+                     torch.zeros_like(angle)]).contiguous()
+    points.append((q, v))
+  start_event = torch.cuda.Event(enable_timing=True)
+  stop_event = torch.cuda.Event(enable_timing=True)
+  for k in range(9):  # Warm-up: the first segment.
+    q, v = points[k]
+    trajectories.append_device(k * step, q.data_ptr(), v.data_ptr())
+  torch.cuda.synchronize()
+  start_event.record()
+  for k in range(9, 8 * segments + 1):
+    q, v = points[k]
+    trajectories.append_device(k * step, q.data_ptr(), v.data_ptr())
+  stop_event.record()
+  torch.cuda.synchronize()
+  fit_seconds = max_over_ranks(torch, dist, world,
+                               start_event.elapsed_time(stop_event) / 1e3,
+                               device)
+  assert trajectories.status() == 0
+  fits = (segments - 1) * n
+  bytes_per_fit = 8 * 192 + 432 + 436 + 2 * 20
+  degrees = trajectories.segments(0)['degree']
+  trajectories.close()
+  # (b) The ensemble flow into the trajectories.
+  state0 = ensemble_state(system, order, n_systems, 1e-6, seed=42 + rank)
+  t0 = system.epoch
+  seconds = {}
+  for sink in (False, True):
+    ensemble = NBodyEnsemble(ephemeris, _capi.QUINLAN_1999_ORDER_8A, step,
+                             state0, t0)
+    sunk = (ContinuousTrajectories(n, step, 1e-3, 4, device=local_rank)
+            if sink else None)
+    if sink:
+      ensemble.solve_to_trajectories(t0 + 8 * step, sunk)
+    else:
+      ensemble.solve(t0 + 8 * step)  # Startup and the first segment.
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    start = time.perf_counter()
+    if sink:
+      steps = ensemble.solve_to_trajectories(t0 + 24 * step, sunk)
+    else:
+      steps = ensemble.solve(t0 + 24 * step)
+    torch.cuda.synchronize()
+    seconds[sink] = max_over_ranks(torch, dist, world,
+                                   time.perf_counter() - start, device)
+    assert steps == 16
+    ensemble.close()
+  if rank == 0:
+    print(json.dumps({
+        'config': 'SURVEY 8f rank 1: ContinuousTrajectory production on the '
+                  'device (Newhall fit every 8 appended points)',
+        'n_gpus': world, 'trajectories_per_gpu': n,
+        'timed_segments': segments - 1, 'fit_seconds': fit_seconds,
+        'trajectory_fits_per_second': world * fits / fit_seconds,
+        'appended_points_per_second': world * fits * 8 / fit_seconds,
+        'algorithmic_bytes_per_fit': bytes_per_fit,
+        'hbm_gb_per_second': fits * bytes_per_fit / fit_seconds / 1e9,
+        'hbm_fraction_of_measured_peak_6553':
+            fits * bytes_per_fit / fit_seconds / 1e9 / 6553.0,
+        'degrees_of_trajectory_0': [int(d) for d in degrees],
+        'ensemble_16_steps_seconds_without_sink': seconds[False],
+        'ensemble_16_steps_seconds_with_sink': seconds[True],
+        'ensemble_system_steps_per_second_with_sink':
+            world * n_systems * 16 / seconds[True]}))
+
+
 def bench_allpairs(args):
   """Config 5: N point masses, all pairs; i-block sharded, NCCL all-gather of
   the positions before every force evaluation."""
@@ -270,6 +378,8 @@ def main():
     bench_history(args)
   if args.config in ('ensemble', 'all'):
     bench_ensemble(args)
+  if args.config in ('trajectories', 'all'):
+    bench_trajectories(args)
   if args.config in ('allpairs', 'all'):
     bench_allpairs(args)
 
