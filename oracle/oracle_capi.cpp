@@ -411,6 +411,24 @@ int32_t orc_geopotential_damping(orc_ephemeris const* e, int32_t body,
 }
 
 // Geopotential::GeneralSphericalHarmonicsAcceleration on one displacement.
+// RotatingBody::FromSurfaceFrame(t) (inverse == 0) or ToSurfaceFrame(t)
+// (inverse != 0: the conjugate quaternion, geometry/rotation_body.hpp:198-201)
+// applied to a vector, physics/rotating_body.hpp:181-198.
+int32_t orc_surface_frame_rotate(orc_ephemeris const* e, int32_t body, double t,
+                                 int32_t inverse, double const* in,
+                                 double* out) {
+  int const internal = e->internal_of_caller[body];
+  Quaternion q = e->e->body(internal).FromSurfaceFrame(t);
+  if (inverse != 0) {
+    q.imaginary = -q.imaginary;
+  }
+  Vec3 const v = Rotate(q, {in[0], in[1], in[2]});
+  out[0] = v.x;
+  out[1] = v.y;
+  out[2] = v.z;
+  return kOk;
+}
+
 int32_t orc_geopotential_acceleration(orc_ephemeris const* e, int32_t body,
                                       double t, double const* r, double* out) {
   int const internal = e->internal_of_caller[body];

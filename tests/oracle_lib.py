@@ -56,6 +56,7 @@ _SYMBOLS = [
     ('orc_ephemeris_internal_order', _i32, [_vp, _i32p, _i32p]),
     ('orc_geopotential_damping', _i32, [_vp, _i32, _i32p, _dp, _dp]),
     ('orc_geopotential_acceleration', _i32, [_vp, _i32, _d, _dp, _dp]),
+    ('orc_surface_frame_rotate', _i32, [_vp, _i32, _d, _i32, _dp, _dp]),
     ('orc_ephemeris_prolong', _i32, [_vp, _d]),
     ('orc_ephemeris_instance_state', _i32, [_vp, _dp, _dp, _dp]),
     ('orc_ephemeris_segment_count', _i32, [_vp, _i32]),
@@ -157,6 +158,13 @@ class OracleEphemeris:
     out = np.zeros(3)
     self.lib.orc_geopotential_acceleration(self.handle, body, t, dptr(r),
                                            dptr(out))
+    return out
+
+  def surface_frame_rotate(self, body, t, v, inverse=False):
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    out = np.zeros(3)
+    self.lib.orc_surface_frame_rotate(self.handle, body, t, int(inverse),
+                                      dptr(v), dptr(out))
     return out
 
   def prolong(self, t):
