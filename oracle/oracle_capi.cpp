@@ -411,6 +411,19 @@ int32_t orc_geopotential_damping(orc_ephemeris const* e, int32_t body,
 }
 
 // Geopotential::GeneralSphericalHarmonicsAcceleration on one displacement.
+// Geopotential::GeneralSphericalHarmonicsPotential with the arguments the
+// reference's tests form (physics/geopotential_test.cpp:109-119).
+double orc_geopotential_potential(orc_ephemeris const* e, int32_t body, double t,
+                                  double const* r) {
+  int const internal = e->internal_of_caller[body];
+  Vec3 const rv{r[0], r[1], r[2]};
+  double const r2 = Norm2(rv);
+  double const r_norm = std::sqrt(r2);
+  double const one_over_r3 = r_norm / (r2 * r2);
+  return e->e->geopotential(internal).GeneralSphericalHarmonicsPotential(
+      t, rv, r_norm, r2, one_over_r3);
+}
+
 // RotatingBody::FromSurfaceFrame(t) (inverse == 0) or ToSurfaceFrame(t)
 // (inverse != 0: the conjugate quaternion, geometry/rotation_body.hpp:198-201)
 // applied to a vector, physics/rotating_body.hpp:181-198.

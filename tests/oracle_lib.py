@@ -57,6 +57,7 @@ _SYMBOLS = [
     ('orc_geopotential_damping', _i32, [_vp, _i32, _i32p, _dp, _dp]),
     ('orc_geopotential_acceleration', _i32, [_vp, _i32, _d, _dp, _dp]),
     ('orc_surface_frame_rotate', _i32, [_vp, _i32, _d, _i32, _dp, _dp]),
+    ('orc_geopotential_potential', _d, [_vp, _i32, _d, _dp]),
     ('orc_ephemeris_prolong', _i32, [_vp, _d]),
     ('orc_ephemeris_instance_state', _i32, [_vp, _dp, _dp, _dp]),
     ('orc_ephemeris_segment_count', _i32, [_vp, _i32]),
@@ -159,6 +160,10 @@ class OracleEphemeris:
     self.lib.orc_geopotential_acceleration(self.handle, body, t, dptr(r),
                                            dptr(out))
     return out
+
+  def geopotential_potential(self, body, t, r):
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    return self.lib.orc_geopotential_potential(self.handle, body, t, dptr(r))
 
   def surface_frame_rotate(self, body, t, v, inverse=False):
     v = np.ascontiguousarray(v, dtype=np.float64)

@@ -261,6 +261,131 @@ def test_geopotential_against_lear_on_the_reference_sample():
   assert worst >= 570, worst
 
 
+def _world_body(cos, sin, degree, zonal):
+  """The body of GeopotentialTest (physics/geopotential_test.cpp:84-91,162-168):
+  mu = 17 m^3/s^2, radius 1 m, reference angle 3 rad at t = 4 s, angular
+  frequency -1.5 rad/s, pole along z; reference radius 1 m."""
+  size = (degree + 1) * (degree + 2) // 2
+  c, s = [0.0] * size, [0.0] * size
+  for (n, m), value in cos.items():
+    c[n * (n + 1) // 2 + m] = value
+  for (n, m), value in sin.items():
+    s[n * (n + 1) // 2 + m] = value
+  body = dict(name='World', mu=17.0, rotating=True, min_radius=1.0,
+              mean_radius=1.0, reference_angle=3.0, reference_instant=4.0,
+              angular_frequency=-1.5, right_ascension=0.0,
+              declination=90 * (math.pi / 180), oblate=True, degree=degree,
+              zonal=zonal, reference_radius=1.0, cos=c, sin=s,
+              q=[0.0, 0.0, 0.0], v=[0.0, 0.0, 0.0])
+  return OracleEphemeris(SolarSystem([body], 0.0), geopotential_tolerance=0.0)
+
+
+def _vanishes_before(reference, value):
+  """VanishesBefore(reference, 0): reference + value == reference."""
+  return reference + value == reference
+
+
+def _normalization(n, m):
+  import os
+  from test_tables import parse_generated
+  gen = parse_generated(os.path.join(os.path.dirname(__file__), '..', 'oracle',
+                                     'generated_tables.h'))
+  return gen['pb_legendre_normalization_factor'][n * (n + 1) // 2 + m]
+
+
+# physics/geopotential_test.cpp:175-218.
+def test_geopotential_j2():
+  # OblateBody::Parameters(j2, reference_radius), oblate_body_body.hpp:30-33.
+  ephemeris = _world_body({(2, 0): -6 / _normalization(2, 0)}, {}, 2, True)
+  a = ephemeris.geopotential_acceleration(0, 0.0, [0.0, 0.0, 10.0])
+  assert _vanishes_before(1.0, a[0]) and _vanishes_before(1.0, a[1])
+  assert a[2] != 0
+  a = ephemeris.geopotential_acceleration(0, 0.0, [30.0, 40.0, 0.0])
+  assert a[0] / a[1] == 0.75  # AlmostEquals(0.75, 0).
+  assert _vanishes_before(1.0, a[2])
+  a = ephemeris.geopotential_acceleration(0, 0.0, [1e2, 0.0, 1e2])
+  assert a[0] > 0 and a[2] < 0
+
+
+# physics/geopotential_test.cpp:220-266.
+def test_geopotential_c22_s22():
+  ephemeris = _world_body(
+      {(2, 0): -6 / _normalization(2, 0), (2, 2): 10 / _normalization(2, 2)},
+      {(2, 2): -13 / _normalization(2, 2)}, 2, False)
+  a = ephemeris.geopotential_acceleration(0, 0.0, [0.0, 0.0, 10.0])
+  assert _vanishes_before(1.0, a[0]) and _vanishes_before(1.0, a[1])
+  assert a[2] != 0
+  a = ephemeris.geopotential_acceleration(0, 0.0, [30.0, 40.0, 0.0])
+  assert not is_near(a[0] / a[1], 0.75)
+  assert _vanishes_before(1.0, a[2])
+
+
+# physics/geopotential_test.cpp:268-320.
+def test_geopotential_j3():
+  ephemeris = _world_body(
+      {(2, 0): -6 / _normalization(2, 0), (2, 2): 1e-20 / _normalization(2, 2),
+       (3, 0): 5 / _normalization(3, 0)},
+      {(2, 2): 1e-20 / _normalization(2, 2)}, 3, False)
+  a = ephemeris.geopotential_acceleration(0, 0.0, [0.0, 0.0, 10.0])
+  assert _vanishes_before(1.0, a[0]) and _vanishes_before(1.0, a[1])
+  assert a[2] != 0
+  a = ephemeris.geopotential_acceleration(0, 0.0, [30.0, 40.0, 0.0])
+  assert a[0] / a[1] == 0.75  # AlmostEquals(0.75, 0).
+  assert not _vanishes_before(1.0, a[2])
+  assert a[2] < 0
+
+
+# physics/geopotential_test.cpp:802-858 (GeopotentialTest.Potential): the
+# degree-9 Earth with tolerance 2^-24, potential against acceleration by finite
+# differences at the reference's own 1000 points; relative errors pinned in
+# (3.3e-9, 8.4e-6).
+def test_geopotential_potential_against_acceleration_on_the_reference_sample():
+  from std_random import Mt19937_64, uniform_real
+  sol = SolarSystem.from_fixture('sol_jd2451545')
+  sol.limit_oblateness_to_degree('Earth', 9)
+  earth = dict(sol.bodies[sol.index('Earth')])
+  earth['q'] = [0.0, 0.0, 0.0]
+  earth['v'] = [0.0, 0.0, 0.0]
+  ephemeris = OracleEphemeris(SolarSystem([earth], sol.epoch),
+                              geopotential_tolerance=2.0**-24)
+  mu = earth['mu']
+  t = sol.epoch
+
+  def potential(itrs):  # geopotential_test.cpp:150-159.
+    icrs = ephemeris.surface_frame_rotate(0, t, itrs)
+    norm = math.sqrt(icrs[0] * icrs[0] + icrs[1] * icrs[1] +
+                     icrs[2] * icrs[2])
+    return mu * (ephemeris.geopotential_potential(0, t, icrs) - 1 / norm)
+
+  def acceleration(itrs):  # AccelerationCpp, :121-133.
+    icrs = ephemeris.surface_frame_rotate(0, t, itrs)
+    g = ephemeris.geopotential_acceleration(0, t, icrs)
+    norm = math.sqrt(icrs[0] * icrs[0] + icrs[1] * icrs[1] +
+                     icrs[2] * icrs[2])
+    return ephemeris.surface_frame_rotate(
+        0, t, mu * (g - icrs / (norm * norm * norm)), inverse=True)
+
+  random = Mt19937_64(42)
+  low, high = np.inf, 0.0
+  for _ in range(1000):
+    displacement = np.array(
+        [uniform_real(random, -1e7, 1e7) for c in range(3)])
+    shifts = [uniform_real(random, 1, 2) for c in range(3)]
+    base = potential(displacement)
+    finite_difference = np.zeros(3)
+    for c in range(3):
+      shifted = displacement.copy()
+      shifted[c] += shifts[c]
+      finite_difference[c] = -(potential(shifted) - base) / shifts[c]
+    actual = acceleration(displacement)
+    relative = (np.linalg.norm(finite_difference - actual) /
+                np.linalg.norm(actual))
+    low, high = min(low, relative), max(high, relative)
+  assert 3.3e-9 < low and high < 8.4e-6, (low, high)
+  # The extremes (3.37e-9, 8.32e-6) sit at the bounds the reference pins.
+  assert low < 3.5e-9 and high > 8.2e-6, (low, high)
+
+
 # physics/geopotential_test.cpp:398-560.
 def test_geopotential_threshold_computation():
   system = _test_earth(5)
