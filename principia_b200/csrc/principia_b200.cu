@@ -268,20 +268,22 @@ int SrknMinBlocks() {
 }
 
 // Shape of the flow kernel: 0 = 128 threads x SrknMinBlocks() blocks per SM;
-// 3 = 384 threads x 1 block.  Measured on 10^5 probes: 56.2 and 52.4 ms per 100
-// steps (a block barrier per stage did not help either shape), so a launch that
-// fills every SM with a 384-thread block takes shape 3, a smaller one shape 0
-// (more, smaller blocks).  PB_SRKN_VARIANT overrides the choice.
+// 3 = 384 threads x 1 block (168 registers, 12 warps per SM); 5 = 256 threads x
+// 2 blocks (128 registers, 16 warps per SM).  Measured on 10^5 probes: 56.2,
+// 50.7 and 48.4 ms per 100 steps (a block barrier per stage did not help; 18,
+// 20 and 24 warps per SM at 96 and 80 registers: 69, 66 and 74 ms), so a launch
+// that fills every SM takes shape 5, a smaller one shape 3 or 0 (more, smaller
+// blocks).  PB_SRKN_VARIANT overrides the choice (tools/flow_variants.sh).
 int SrknVariant(long long const n_probes, int const sm_count) {
   static int const forced = [] {
     char const* const text = std::getenv("PB_SRKN_VARIANT");
     int const v = text != nullptr ? std::atoi(text) : -1;
-    return v >= 0 && v <= 3 ? v : -1;
+    return v >= 0 && v <= 5 ? v : -1;
   }();
   if (forced >= 0) {
     return forced;
   }
-  return n_probes >= 384LL * sm_count ? 3 : 0;
+  return n_probes >= 512LL * sm_count ? 5 : n_probes >= 384LL * sm_count ? 3 : 0;
 }
 
 bool MakeSrknTableau(int32_t method, SrknTableau& t) {
@@ -719,7 +721,8 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
       PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
                                      e->device));
       int const variant = SrknVariant(flow->n, sm_count);
-      int const threads = variant >= 2 ? 384 : kFlowThreads;
+      int const threads =
+          variant == 5 ? 256 : variant >= 2 ? 384 : kFlowThreads;
       long long const blocks = (flow->n + threads - 1) / threads;
       int const groups = static_cast<int>(
           std::min<long long>(FlowGroups(), std::max<long long>(1, blocks / 64)));
@@ -760,7 +763,9 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
           view, tableau, h, table, times, flow->burns, n_sub, flow->n,        \
           i_begin, i_end, flow->state, steps_done + s0, every,                \
           flow->max_samples, flow->samples, e->status_word.data)
-          if (variant >= 2) {
+          if (variant == 5) {
+            PB_LAUNCH_SRKN(256, 2);
+          } else if (variant >= 2) {
             PB_LAUNCH_SRKN(384, 1);
           } else {
             switch (SrknMinBlocks()) {
