@@ -298,17 +298,22 @@ def run_native(args):
   roofline = {
       'bound': 'fp64', 'achieved': achieved, 'peak': peak_flops / 1e12,
       'unit': 'TFLOP/s', 'frac': achieved / (peak_flops / 1e12),
-      # DRAM bytes of one SrknFlowKernel launch (dram__bytes_read.sum +
-      # dram__bytes_write.sum of the ncu --set full capture summarised in
-      # profiles/r01f_ncu_srkn_flow.txt: 2.70 MB + 0.40 MB for 24 960 probes x
-      # 10 steps): the kernel is FP64-pipe bound, HBM traffic is negligible.
-      'traffic': 3.1e6,
-      # The same capture: FP64 pipe 62.9 % active; 4 379 FP64-pipe
-      # instructions (2 497 DMUL, 1 260 DADD, 550 DFMA, 72 DSETP) per
-      # probe-stage for 3 739 algorithmic flops (the reference forbids
-      # contraction: an add or a multiply takes a DFMA slot for one flop), so
-      # 100 % of the pipe would be frac 0.427.
-      'fp64_pipe_active_ncu': 0.629,
+      # DRAM bytes of one SrknFlowKernel launch as bench.py issues them
+      # (dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full
+      # capture summarised in profiles/r01h_ncu_srkn_flow.txt: 2.71 MB + 2.17 MB
+      # for 25 088 probes x 10 steps; algorithmic 4.8 MB of state): the kernel
+      # is FP64-pipe bound, HBM traffic is negligible.  (A single launch of
+      # 75 776 probes x 100 steps, whose thread-local scratch no longer fits
+      # the L2, writes 10.5 GB in 37.9 ms = 0.28 TB/s:
+      # profiles/r01h_ncu_srkn_flow_full_wave.txt.)
+      'traffic': 4.88e6,
+      # The full-wave capture: FP64 pipe 67.8 % active at 16 warps per SM;
+      # 4 379 FP64-pipe instructions (2 497 DMUL, 1 260 DADD, 550 DFMA,
+      # 72 DSETP; profiles/r01f_ncu_srkn_flow.txt) per probe-stage for 3 739
+      # algorithmic flops (the reference forbids contraction: an add or a
+      # multiply takes a DFMA slot for one flop), so 100 % of the pipe would be
+      # frac 0.427.
+      'fp64_pipe_active_ncu': 0.678,
       'frac_at_full_fp64_pipe': 0.427,
       'kernel': 'SrknFlowKernel',
       'kernel_ms': average_kernel_ms,
