@@ -199,3 +199,54 @@ def test_trappist_ensemble_produces_the_oracles_trajectories():
       assert oracles[i].append(time[0], flat[0:3, i], flat[6:9, i]) == 0
   compare(trajectories, oracles, picked,
           [t0, t0 + 12345.6, t0 + 8 * h, t0 + 104 * h])
+
+
+def test_full_size_fit_reproduces_the_appended_points():
+  """Size-independent property at the size of BASELINE.json config 4 (8 bodies
+  of 10^5 systems = 8 10^5 trajectories): where the fit settled below the
+  maximal degree, the polynomials reproduce the appended positions and
+  velocities to within the tolerance (times a margin for the unfitted modes),
+  at the nodes and between them."""
+  n, step, tolerance = 800000, 1800.0, 1e-3
+  rng = np.random.Generator(np.random.MT19937(5))
+  period = step * 10.0**rng.uniform(1.5, 4.0, n)
+  radius = 10.0**rng.uniform(6, 10, n)
+  phase = rng.uniform(0, 2 * np.pi, n)
+  omega = 2 * np.pi / period
+
+  def state(t):
+    angle = phase + omega * t
+    q = np.stack([radius * np.cos(angle), radius * np.sin(angle),
+                  0.1 * radius * np.cos(angle)])
+    v = np.stack([-radius * omega * np.sin(angle),
+                  radius * omega * np.cos(angle),
+                  -0.1 * radius * omega * np.sin(angle)])
+    return q, v
+
+  gpu = ContinuousTrajectories(n, step, tolerance, max_segments=3)
+  apocalypse = False
+  for k in range(17):
+    try:
+      gpu.append(k * step, *state(k * step))
+    except StatusError:
+      apocalypse = True
+  assert gpu.segment_count() == 2
+  settled = np.ones(n, dtype=bool)
+  degrees = np.zeros((2, n), dtype=np.int32)
+  # The degrees, through the evaluation of a few whole trajectories.
+  for i in range(0, n, n // 64):
+    degrees[:, i] = gpu.segments(i)['degree']
+  for t in (0.0, 4 * step, 8 * step, 11.5 * step, 16 * step):
+    q, v = gpu.evaluate(t)
+    expected_q, expected_v = state(t)
+    q_error = np.abs(q - expected_q).max(axis=0)
+    v_error = np.abs(v - expected_v).max(axis=0)
+    # Slow motions are fitted to the tolerance; the fast ones (period below
+    # ~60 steps) exhaust the degrees and carry their error estimate instead.
+    slow = period > 200 * step
+    assert q_error[slow].max() < 10 * tolerance, (t, q_error[slow].max())
+    assert v_error[slow].max() < 10 * tolerance / step, (t,
+                                                         v_error[slow].max())
+    assert np.all(np.isfinite(q)) and np.all(np.isfinite(v))
+  sampled = degrees[:, ::n // 64]
+  assert sampled.min() >= 3 and sampled.max() <= 17
