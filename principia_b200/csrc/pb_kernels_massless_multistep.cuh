@@ -73,23 +73,28 @@ MasslessFillStepKernel(EphemerisView const e, double const* __restrict__ stage,
 // the oldest slot.  stage_table: one entry per step (the time after the
 // increment).  The ODE::State (12 planes) is left at the last step; sampling as
 // in SrknFlowKernel.
-template<int kOrder>
-__global__ void __launch_bounds__(kFlowThreads, 3)
+// Probes [i_begin, i_end) of n (the planes have n entries): the host cuts a
+// launch into probe slices and step sub-chunks on helper streams, like the SRKN
+// flow (principia_b200.cu).
+template<int kOrder, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 MasslessMultistepFlowKernel(EphemerisView const e, MultistepMethod const method,
                             double const h,
                             double const* __restrict__ stage_table,
                             double const* __restrict__ stage_times,
                             double const* __restrict__ burns,
                             int const n_steps, long long const n,
+                            long long const i_begin, long long const i_end,
                             double* __restrict__ state,
                             MasslessHistory const history, int const oldest,
                             long long const steps_before,
                             long long const sample_every,
                             long long const max_samples,
                             double* __restrict__ samples, int32_t* status) {
-  long long const i =
-      static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) {
+  long long const i = i_begin +
+                      static_cast<long long>(blockIdx.x) * blockDim.x +
+                      threadIdx.x;
+  if (i >= i_end) {
     return;
   }
   constexpr int k = kOrder;

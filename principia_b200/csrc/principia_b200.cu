@@ -286,6 +286,19 @@ int SrknVariant(long long const n_probes, int const sm_count) {
   return n_probes >= 512LL * sm_count ? 5 : n_probes >= 384LL * sm_count ? 3 : 0;
 }
 
+// Shape of the massless multistep flow kernel: 128 threads x 3 blocks per SM
+// (168 registers).  256 x 2 at 128 registers, the better shape of the SRKN
+// kernel, is slower here (10^5 probes, Quinlan1999Order8A: 1.72 against
+// 2.04 10^9 probe-steps/s): the history sums add to the live state.
+// PB_MULTISTEP_WIDE=1 selects it for experiments.
+bool MultistepWide(long long const n_probes, int const sm_count) {
+  static int const forced = [] {
+    char const* const text = std::getenv("PB_MULTISTEP_WIDE");
+    return text != nullptr ? std::atoi(text) : 0;
+  }();
+  return forced != 0 && n_probes >= 512LL * sm_count;
+}
+
 bool MakeSrknTableau(int32_t method, SrknTableau& t) {
   std::memset(&t, 0, sizeof(t));
   if (method == PB_BLANES_MOAN_2002_SRKN_14A) {
@@ -1017,20 +1030,72 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
         PB_CUDA(cudaEventCreate(&event));
         e->timing_events.push_back(event);
       }
-      PB_CUDA(cudaEventRecord(e->timing_events[2 * phases], stream));
-      unsigned const grid =
-          static_cast<unsigned>((s->n + kFlowThreads - 1) / kFlowThreads);
+      // Probe slices x step sub-chunks on helper streams, as in the SRKN flow
+      // (no last-wave tail: 1.91 -> 2.04 10^9 probe-steps/s on 10^5 probes).
+      int sm_count = 0;
+      PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
+                                     e->device));
+      bool const wide = MultistepWide(s->n, sm_count);
+      int const threads = wide ? 256 : kFlowThreads;
+      long long const blocks = (s->n + threads - 1) / threads;
+      int const groups = static_cast<int>(
+          std::min<long long>(FlowGroups(), std::max<long long>(1, blocks / 64)));
+      int const sub_steps = groups > 1 ? FlowSubSteps() : steps;
+      while (static_cast<int>(e->flow_streams.size()) < groups) {
+        cudaStream_t helper;
+        PB_CUDA(cudaStreamCreateWithFlags(&helper, cudaStreamNonBlocking));
+        e->flow_streams.push_back(helper);
+        cudaEvent_t event;
+        PB_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+        e->flow_events.push_back(event);
+      }
+      cudaEvent_t const fork = e->timing_events[2 * phases];
+      PB_CUDA(cudaEventRecord(fork, stream));
       bool const sampling = sink->samples != nullptr && sink->sample_every > 0;
-      auto const kernel = order == 8 ? MasslessMultistepFlowKernel<8>
-                                     : MasslessMultistepFlowKernel<12>;
-      kernel<<<grid, kFlowThreads, 0, stream>>>(
-          view, s->multistep, h, e->stage_table.data, e->stage_times.data,
-          s->burns, steps, s->n, s->state,
-          s->History(), s->oldest, appended_before,
-          sampling ? sink->sample_every : 0, sink->max_samples, sink->samples,
-          e->status_word.data);
-      PB_LAUNCHED();
-      ++e->last_flow_kernel_launches;
+      for (int g = 0; g < groups; ++g) {
+        cudaStream_t const helper = groups > 1 ? e->flow_streams[g] : stream;
+        if (groups > 1) {
+          PB_CUDA(cudaStreamWaitEvent(helper, fork, 0));
+        }
+        long long const i_begin = blocks * g / groups * threads;
+        long long const i_end =
+            std::min<long long>(s->n, blocks * (g + 1) / groups * threads);
+        unsigned const grid = static_cast<unsigned>(
+            (i_end - i_begin + threads - 1) / threads);
+        for (int s0 = 0; s0 < steps; s0 += sub_steps) {
+          int const n_sub = std::min(sub_steps, steps - s0);
+#define PB_LAUNCH_MULTISTEP(kOrder, kThreads, kMinBlocks)                     \
+  MasslessMultistepFlowKernel<kOrder, kThreads, kMinBlocks>                   \
+      <<<grid, kThreads, 0, helper>>>(                                        \
+          view, s->multistep, h,                                              \
+          e->stage_table.data +                                               \
+              static_cast<std::size_t>(s0) * view.stage_stride,               \
+          e->stage_times.data + s0, s->burns, n_sub, s->n, i_begin, i_end,    \
+          s->state, s->History(), (s->oldest + s0) % order,                   \
+          appended_before + s0, sampling ? sink->sample_every : 0,            \
+          sink->max_samples, sink->samples, e->status_word.data)
+          if (order == 8) {
+            if (wide) {
+              PB_LAUNCH_MULTISTEP(8, 256, 2);
+            } else {
+              PB_LAUNCH_MULTISTEP(8, 128, 3);
+            }
+          } else {
+            if (wide) {
+              PB_LAUNCH_MULTISTEP(12, 256, 2);
+            } else {
+              PB_LAUNCH_MULTISTEP(12, 128, 3);
+            }
+          }
+#undef PB_LAUNCH_MULTISTEP
+          PB_LAUNCHED();
+          ++e->last_flow_kernel_launches;
+        }
+        if (groups > 1) {
+          PB_CUDA(cudaEventRecord(e->flow_events[g], helper));
+          PB_CUDA(cudaStreamWaitEvent(stream, e->flow_events[g], 0));
+        }
+      }
       PB_CUDA(cudaEventRecord(e->timing_events[2 * phases + 1], stream));
       ++phases;
     }
