@@ -365,3 +365,73 @@ def test_branch_free_sqrt_and_division_are_ieee():
     assert bad.value == 0
     total += checked.value
   assert total > 2e9
+
+
+def _world_system(cos, sin, degree, zonal):
+  """The 17 m^3/s^2 body of GeopotentialTest (physics/geopotential_test.cpp
+  :84-91,162-168) alone at the origin."""
+  import test_oracle_kats as kats
+  size = (degree + 1) * (degree + 2) // 2
+  c, s = [0.0] * size, [0.0] * size
+  for (n, m), value in cos.items():
+    c[n * (n + 1) // 2 + m] = value / kats._normalization(n, m)
+  for (n, m), value in sin.items():
+    s[n * (n + 1) // 2 + m] = value / kats._normalization(n, m)
+  body = dict(name='World', mu=17.0, rotating=True, min_radius=1.0,
+              mean_radius=1.0, reference_angle=3.0, reference_instant=4.0,
+              angular_frequency=-1.5, right_ascension=0.0,
+              declination=90 * (math.pi / 180), oblate=True, degree=degree,
+              zonal=zonal, reference_radius=1.0, cos=c, sin=s,
+              q=[0.0, 0.0, 0.0], v=[0.0, 0.0, 0.0])
+  return SolarSystem([body], 0.0)
+
+
+@pytest.mark.parametrize('tolerance', [0.0, 2.0**-24])
+@pytest.mark.parametrize('shape', ['j2', 'c22s22', 'j3', 'degree6'])
+def test_geopotential_test_bodies_on_the_device(shape, tolerance):
+  """The bodies of GeopotentialTest.J2 / C22S22 / J3 (geopotential_test.cpp
+  :175-320) and a dense degree-6 one, as one-body ephemerides at rest: the
+  accelerations and potentials on the device are the oracle's, bit for bit, at
+  the test's special points (on the axis, in the equatorial plane) and at
+  random ones, and the exact symmetries the reference pins hold on the GPU."""
+  from principia_b200.ephemeris import Ephemeris
+  if shape == 'j2':
+    system = _world_system({(2, 0): -6.0}, {}, 2, True)
+  elif shape == 'c22s22':
+    system = _world_system({(2, 0): -6.0, (2, 2): 10.0}, {(2, 2): -13.0}, 2,
+                           False)
+  elif shape == 'j3':
+    system = _world_system({(2, 0): -6.0, (2, 2): 1e-20, (3, 0): 5.0},
+                           {(2, 2): 1e-20}, 3, False)
+  else:
+    rng = np.random.Generator(np.random.MT19937(6))
+    cos = {(n, m): rng.normal() for n in range(2, 7) for m in range(n + 1)}
+    sin = {(n, m): rng.normal() for n in range(2, 7) for m in range(1, n + 1)}
+    system = _world_system(cos, sin, 6, False)
+  gpu = Ephemeris(system, geopotential_tolerance=tolerance)
+  oracle = OracleEphemeris(system, geopotential_tolerance=tolerance)
+  segment = dict(t_min=-100.0, t_max=np.array([100.0]), origin=np.array([0.0]),
+                 degree=np.array([3], dtype=np.int32),
+                 coefficients=np.zeros((1, 18, 3)))
+  gpu.append_segments(0, segment)
+  oracle.append_segments(0, segment)
+  rng = np.random.Generator(np.random.MT19937(8))
+  special = np.array([[0.0, 0.0, 10.0], [30.0, 40.0, 0.0], [1e2, 0.0, 1e2],
+                      [0.0, 0.0, -3.0], [5.0, 0.0, 0.0], [0.0, 7.0, 0.0]]).T
+  direction = rng.normal(size=(3, 3000))
+  direction /= np.linalg.norm(direction, axis=0)
+  q = np.concatenate(
+      [special, direction * 10.0**rng.uniform(0.2, 4.0, 3000)], axis=1)
+  for t in (0.0, 4.0, -37.5, 99.0):
+    a, status = gpu.compute_gravitational_acceleration_on_massless_bodies(t, q)
+    expected, expected_status = oracle.acceleration_on_massless_bodies(t, q)
+    assert status == expected_status
+    assert_bitwise_equal(a, expected, '%s t=%r' % (shape, t))
+    assert_bitwise_equal(gpu.compute_gravitational_potential(t, q),
+                         oracle.potential(t, q), '%s potential' % shape)
+  if tolerance == 0.0 and shape in ('j2', 'j3'):
+    # In the equatorial plane the acceleration of a zonal field points to the
+    # axis: a_x / a_y == 0.75 exactly (AlmostEquals(0.75, 0)), point mass
+    # included.
+    a, _ = gpu.compute_gravitational_acceleration_on_massless_bodies(0.0, q)
+    assert a[0, 1] / a[1, 1] == 0.75
