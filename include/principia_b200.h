@@ -531,6 +531,17 @@ pb_status_t pb_downsampler_append_logs_device(pb_downsampler_t* downsampler,
  * outgrew `capacity` (its later points were dropped). */
 pb_status_t pb_downsampler_get(pb_downsampler_t* downsampler, int64_t* counts,
                                double* times, double* points, double* errors);
+/* DiscreteTrajectorySegment::EvaluatePosition / EvaluateVelocity
+ * (physics/discrete_trajectory_segment_body.hpp:132-155) of every timeline at
+ * t: the point at t if there is one, else the Hermite interpolation between
+ * its neighbours (numerics/hermite3_body.hpp).  q, v: 3 planes of n (either may
+ * be NULL); in_range[n] (may be NULL) is 0 where the timeline does not cover t
+ * (the reference CHECKs), and the outputs are NaN there. */
+pb_status_t pb_downsampler_evaluate(pb_downsampler_t* downsampler, double t,
+                                    double* q, double* v, int32_t* in_range);
+pb_status_t pb_downsampler_evaluate_device(pb_downsampler_t* downsampler,
+                                           double t, double* q, double* v,
+                                           int32_t* in_range, void* stream);
 
 /* ---- Series in the Чебышёв basis.
  * PolynomialInЧебышёвBasis<Value, Instant, degree>::operator() and

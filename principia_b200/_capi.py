@@ -197,6 +197,9 @@ SYMBOLS = [
      [_vp, _i64, _vp, _vp, _vp, _vp]),
     ('pb_downsampler_get', _i32,
      [_vp, c_int64_p, c_double_p, c_double_p, c_double_p]),
+    ('pb_downsampler_evaluate', _i32,
+     [_vp, _d, c_double_p, c_double_p, c_int32_p]),
+    ('pb_downsampler_evaluate_device', _i32, [_vp, _d, _vp, _vp, _vp, _vp]),
     ('pb_chebyshev_series_evaluate', _i32,
      [_i32, _i64, _i32, c_int32_p, c_double_p, c_double_p, c_double_p, _i64,
       c_int32_p, c_double_p, c_double_p, c_double_p]),

@@ -78,6 +78,75 @@ pb_status_t LaunchDownsample(pb_downsampler* d, long long const n_samples,
 
 }  // namespace
 
+namespace {
+
+// DiscreteTrajectorySegment::EvaluatePosition / EvaluateVelocity,
+// physics/discrete_trajectory_segment_body.hpp:132-155, for every timeline at
+// one time: lower_bound(t), the point itself if its time is t, else the
+// Hermite interpolation between the previous point and it (get_hermite3,
+// :493-509).  A timeline that does not cover t (the reference CHECKs
+// t_min() <= t <= t_max()) gets NaNs and in_range[i] = 0.
+__global__ void __launch_bounds__(128)
+DownsamplerEvaluateKernel(DownsamplerView const d, double const t,
+                          double* __restrict__ q, double* __restrict__ v,
+                          int32_t* __restrict__ in_range) {
+  long long const i =
+      static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= d.n) {
+    return;
+  }
+  long long const n = d.n;
+  long long const count = d.counts[i] < d.capacity ? d.counts[i] : d.capacity;
+  double const nan = __longlong_as_double(0x7ff8000000000000LL);
+  Vec3 position{nan, nan, nan};
+  Vec3 velocity{nan, nan, nan};
+  bool ok = count > 0 && t >= d.times[i] && t <= d.times[(count - 1) * n + i];
+  if (ok) {
+    long long lo = 0;
+    long long hi = count;
+    while (lo < hi) {
+      long long const mid = (lo + hi) / 2;
+      if (d.times[mid * n + i] < t) {
+        lo = mid + 1;
+      } else {
+        hi = mid;
+      }
+    }
+    auto const load = [&](long long const slot, int const plane) {
+      return d.points[(slot * 6 + plane) * n + i];
+    };
+    double const t2 = d.times[lo * n + i];
+    Vec3 const q2{load(lo, 0), load(lo, 1), load(lo, 2)};
+    Vec3 const v2{load(lo, 3), load(lo, 4), load(lo, 5)};
+    if (t2 == t) {
+      position = q2;
+      velocity = v2;
+    } else {
+      double const t1 = d.times[(lo - 1) * n + i];
+      Vec3 const q1{load(lo - 1, 0), load(lo - 1, 1), load(lo - 1, 2)};
+      Vec3 const v1{load(lo - 1, 3), load(lo - 1, 4), load(lo - 1, 5)};
+      Hermite3 const h = MakeHermite3(t1, t2, q1, q2, v1, v2);
+      position = Hermite3Evaluate(h, t);
+      velocity = Hermite3EvaluateDerivative(h, t);
+    }
+  }
+  if (q != nullptr) {
+    q[i] = position.x;
+    q[n + i] = position.y;
+    q[2 * n + i] = position.z;
+  }
+  if (v != nullptr) {
+    v[i] = velocity.x;
+    v[n + i] = velocity.y;
+    v[2 * n + i] = velocity.z;
+  }
+  if (in_range != nullptr) {
+    in_range[i] = ok ? 1 : 0;
+  }
+}
+
+}  // namespace
+
 extern "C" {
 
 pb_status_t pb_downsampler_create(int32_t cuda_device, int64_t n,
@@ -230,6 +299,54 @@ pb_status_t pb_downsampler_get(pb_downsampler_t* d, int64_t* counts,
       return Fail(PB_RESOURCE_EXHAUSTED,
                   "a timeline outgrew the capacity of the downsampler");
     }
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_downsampler_evaluate_device(pb_downsampler_t* d, double t,
+                                           double* q, double* v,
+                                           int32_t* in_range, void* stream) {
+  if (d == nullptr || (q == nullptr && v == nullptr)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(d->device));
+  if (d->n > 0) {
+    DownsamplerEvaluateKernel<<<static_cast<unsigned>((d->n + 127) / 128), 128,
+                                0, static_cast<cudaStream_t>(stream)>>>(
+        d->View(), t, q, v, in_range);
+    PB_LAUNCHED();
+  }
+  return PB_OK;
+}
+
+pb_status_t pb_downsampler_evaluate(pb_downsampler_t* d, double t, double* q,
+                                    double* v, int32_t* in_range) {
+  if (d == nullptr || (q == nullptr && v == nullptr)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(d->device));
+  std::size_t const n = static_cast<std::size_t>(d->n);
+  if (n == 0) {
+    return PB_OK;
+  }
+  // staged_samples: q then v; the flags after them.
+  PB_RETURN_IF_ERROR(d->staged_samples.Reserve(7 * n));
+  double* const device_q = d->staged_samples.data;
+  double* const device_v = device_q + 3 * n;
+  int32_t* const device_flags = reinterpret_cast<int32_t*>(device_v + 3 * n);
+  PB_RETURN_IF_ERROR(pb_downsampler_evaluate_device(
+      d, t, device_q, device_v, device_flags, nullptr));
+  if (q != nullptr) {
+    PB_CUDA(cudaMemcpy(q, device_q, 3 * n * sizeof(double),
+                       cudaMemcpyDeviceToHost));
+  }
+  if (v != nullptr) {
+    PB_CUDA(cudaMemcpy(v, device_v, 3 * n * sizeof(double),
+                       cudaMemcpyDeviceToHost));
+  }
+  if (in_range != nullptr) {
+    PB_CUDA(cudaMemcpy(in_range, device_flags, n * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost));
   }
   return PB_OK;
 }

@@ -54,3 +54,19 @@ class Downsampler:
         self.handle, counts.ctypes.data_as(_capi.c_int64_p), _dptr(times),
         _dptr(points), _dptr(errors)))
     return counts, times, points, errors
+
+  def evaluate(self, t):
+    """DiscreteTrajectory::EvaluatePosition / EvaluateVelocity of every
+    timeline at t: ((3, n) positions, (3, n) velocities, (n,) in_range)."""
+    q = np.zeros((3, self.n))
+    v = np.zeros((3, self.n))
+    in_range = np.zeros(self.n, dtype=np.int32)
+    _check(self.lib.pb_downsampler_evaluate(
+        self.handle, t, _dptr(q), _dptr(v),
+        in_range.ctypes.data_as(_capi.c_int32_p)))
+    return q, v, in_range.astype(bool)
+
+  def evaluate_device(self, t, q_pointer, v_pointer, in_range_pointer=None,
+                      stream=None):
+    _check(self.lib.pb_downsampler_evaluate_device(
+        self.handle, t, q_pointer, v_pointer, in_range_pointer, stream))

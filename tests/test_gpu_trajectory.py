@@ -43,6 +43,21 @@ def test_reference_circle_and_straight_line():
     assert_bitwise_equal(points[:c, 0:3, k], expected['q'])
     assert_bitwise_equal(points[:c, 3:6, k], expected['v'])
     assert_bitwise_equal(errors[:c, k], expected['errors'])
+  # Evaluation: at a kept point, between kept points, at both ends, outside
+  # (discrete_trajectory_segment_test.cpp:283-300 evaluates every millisecond).
+  evaluation_times = np.concatenate(
+      [np.arange(0.0, 10.0, 0.1237), [0.0, kept_times[3, 0], times[-1]]])
+  for k, (_, q, v) in enumerate((circle, line)):
+    expected = oracle_downsample(times, q, v, 1e-3, evaluation_times)
+    for j, t in enumerate(evaluation_times):
+      eq, ev, in_range = downsampler.evaluate(float(t))
+      assert in_range.all()
+      assert_bitwise_equal(eq[:, k], expected['evaluated_q'][j], 'q at %r' % t)
+      assert_bitwise_equal(ev[:, k], expected['evaluated_v'][j], 'v at %r' % t)
+  eq, ev, in_range = downsampler.evaluate(10.5)
+  assert not in_range.any() and np.isnan(eq).all() and np.isnan(ev).all()
+  eq, ev, in_range = downsampler.evaluate(-1e-9)
+  assert not in_range.any()
 
 
 def test_flow_samples_are_downsampled_like_the_oracle(sol_system, sol_gpu):
