@@ -65,6 +65,12 @@ class ClockSampler:
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
+      # nvidia-smi takes a second to initialise NVML (and disturbs launches
+      # while it does): wait for its first sample, so that the timed region
+      # only sees the periodic queries.
+      deadline = time.perf_counter() + 5.0
+      while not self.lines and time.perf_counter() < deadline:
+        time.sleep(0.01)
     except OSError:
       self.process = None
 
@@ -247,8 +253,8 @@ def run_native(args):
     resident_step()
   sampler = ClockSampler(local_rank)
   launches_before = kernel_launch_count()
-  barrier()
   sampler.start()
+  barrier()
   start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
   kernel_ms = 0.0
   kernel_launches = 0
