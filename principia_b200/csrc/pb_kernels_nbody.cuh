@@ -111,6 +111,115 @@ static __device__ __noinline__ Vec3 AccelerationOnBodyOfSystem(
   return a;
 }
 
+// The same acceleration when the block integrates ONE system (the Sol
+// ephemeris of Ephemeris::Prolong: 34 bodies, a single lane of every warp would
+// work): the lanes of the warp that owns body b take the partners
+// j = lane, lane + 32, compute the addends of their pair -- the point-mass
+// term, the harmonics of b1, the harmonics of b2, each with the sign it has in
+// the sequential form -- and the warp then adds them to the acceleration in the
+// reference's order (j ascending, the three addends of a pair in order), one
+// shuffle per addend.  a - x is a + (-x) bit for bit, and an addend that the
+// sequential form skips (a body that is not oblate) is skipped here too, so
+// the result is the sequential one; the latency is that of one pair plus the
+// ordered sum instead of n - 1 pairs in a row.  All 32 lanes hold the same
+// system (the callers clamp the system index), every lane returns the sum.
+template<int kMaxThreads>
+static __device__ __noinline__ Vec3 CooperativeAccelerationOnBody(
+    EphemerisView const& e, double const* const frames,
+    double const* const positions, int const b, int const lane) {
+  constexpr int kSets = kMaxEnsembleBodies / kEnsembleLanes;
+  int const n = e.n_bodies;
+  DeviceBody const& body_b = e.bodies[b];
+  Vec3 const q_b{positions[(3 * b + 0) * kEnsembleLanes + lane],
+                 positions[(3 * b + 1) * kEnsembleLanes + lane],
+                 positions[(3 * b + 2) * kEnsembleLanes + lane]};
+  Vec3 addend[kSets][3];
+  unsigned present[kSets];
+#pragma unroll
+  for (int set = 0; set < kSets; ++set) {
+    present[set] = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      addend[set][k] = {0.0, 0.0, 0.0};
+    }
+    int const j = lane + set * kEnsembleLanes;
+    if (j >= n || j == b) {
+      continue;
+    }
+    DeviceBody const& body_j = e.bodies[j];
+    Vec3 const q_j{positions[(3 * j + 0) * kEnsembleLanes + lane],
+                   positions[(3 * j + 1) * kEnsembleLanes + lane],
+                   positions[(3 * j + 2) * kEnsembleLanes + lane]};
+    bool const b_is_b2 = j < b;
+    Vec3 const dq = b_is_b2 ? q_j - q_b : q_b - q_j;  // q_b1 - q_b2.
+    double const dq2 = Norm2(dq);
+    bool const in_range = InFastRange(dq2);
+    double const dq_norm = in_range ? FastSqrt(dq2) : sqrt(dq2);
+    double const one_over_dq3 = in_range ? FastDivide(dq_norm, dq2 * dq2)
+                                         : dq_norm / (dq2 * dq2);
+    double const mu_j = body_j.mu;
+    double const mu_j_over_dq3 = mu_j * one_over_dq3;
+    Vec3 const point_mass = dq * mu_j_over_dq3;
+    addend[set][0] = b_is_b2 ? point_mass : -point_mass;
+    present[set] = 1u;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
+      bool const source_is_b = (which == 0) != b_is_b2;
+      int const source = source_is_b ? b : j;
+      DeviceBody const& source_body = source_is_b ? body_b : body_j;
+      if (!source_body.is_oblate) {
+        continue;
+      }
+      GeopotentialBody const g = MakeGeopotentialBody(e, source);
+      FrameSource const frame{source_body.frame_slot >= 0
+                                  ? frames + 6 * source_body.frame_slot
+                                  : nullptr,
+                              0.0};
+      Vec3 const effect = GeneralSphericalHarmonicsAcceleration<true, 3>(
+          g, frame, which == 0 ? -dq : dq, dq_norm, dq2, one_over_dq3);
+      Vec3 const scaled = mu_j * effect;
+      bool const subtract = (which == 0) != b_is_b2;
+      addend[set][1 + which] = subtract ? -scaled : scaled;
+      present[set] |= 2u << which;
+    }
+  }
+  __syncwarp();
+  Vec3 a{0.0, 0.0, 0.0};
+#pragma unroll
+  for (int set = 0; set < kSets; ++set) {
+    int const count = n - set * kEnsembleLanes < kEnsembleLanes
+                          ? n - set * kEnsembleLanes
+                          : kEnsembleLanes;
+#pragma unroll 1
+    for (int source = 0; source < count; ++source) {
+      unsigned const mask = __shfl_sync(0xffffffffu, present[set], source);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        Vec3 const x{__shfl_sync(0xffffffffu, addend[set][k].x, source),
+                     __shfl_sync(0xffffffffu, addend[set][k].y, source),
+                     __shfl_sync(0xffffffffu, addend[set][k].z, source)};
+        if (mask & (1u << k)) {
+          a = a + x;
+        }
+      }
+    }
+  }
+  return a;
+}
+
+// A block that integrates a single system takes the cooperative form.
+template<int kMaxThreads>
+__device__ __forceinline__ Vec3 AccelerationOnBody(
+    EphemerisView const& e, double const* const frames,
+    double const* const positions, int const b, int const lane,
+    long long const n_systems) {
+  return n_systems == 1
+             ? CooperativeAccelerationOnBody<kMaxThreads>(e, frames, positions,
+                                                          b, lane)
+             : AccelerationOnBodyOfSystem<kMaxThreads>(e, frames, positions, b,
+                                                       lane);
+}
+
 // Index into an ensemble plane set: [plane][body][system].
 __device__ __forceinline__ long long EnsembleIndex(int const plane,
                                                    int const body,
@@ -182,9 +291,9 @@ EnsembleSrknStepKernel(EphemerisView const e,
     for (int o = 0; o < kOwn; ++o) {
       int const b = warp + o * warps;
       if (b < n) {
-        Vec3 const g = AccelerationOnBodyOfSystem<kMaxThreads>(
+        Vec3 const g = AccelerationOnBody<kMaxThreads>(
             e, frames + (st - tableau.first_stage) * frame_stride, positions, b,
-            lane);
+            lane, n_systems);
         dv[o].x += hb * g.x;
         dv[o].y += hb * g.y;
         dv[o].z += hb * g.z;
@@ -286,8 +395,8 @@ EnsembleFillStepKernel(EphemerisView const e,
   for (int o = 0; o < kOwn; ++o) {
     int const b = warp + o * warps;
     if (b < n) {
-      Vec3 const a = AccelerationOnBodyOfSystem<kMaxThreads>(e, frames,
-                                                             positions, b, lane);
+      Vec3 const a = AccelerationOnBody<kMaxThreads>(e, frames, positions, b,
+                                                     lane, n_systems);
       if (active) {
         history.acceleration[HistoryIndex(slot, 0, b, n, n_systems, s)] = a.x;
         history.acceleration[HistoryIndex(slot, 1, b, n, n_systems, s)] = a.y;
@@ -378,8 +487,8 @@ EnsembleMultistepStepKernel(
   for (int o = 0; o < kOwn; ++o) {
     int const b = warp + o * warps;
     if (b < n) {
-      Vec3 const acceleration = AccelerationOnBodyOfSystem<kMaxThreads>(
-          e, frames, positions, b, lane);
+      Vec3 const acceleration = AccelerationOnBody<kMaxThreads>(
+          e, frames, positions, b, lane, n_systems);
       double const a[3] = {acceleration.x, acceleration.y, acceleration.z};
       if (active) {
 #pragma unroll
