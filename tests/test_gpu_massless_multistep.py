@@ -251,3 +251,31 @@ def test_multistep_flow_rejects_backward_steps(sol_system, sol_gpu):
   with pytest.raises(Exception):
     sol_gpu.flow_with_fixed_step(_capi.QUINLAN_1999_ORDER_8A, -10.0, -100.0,
                                  state, np.zeros(2))
+
+
+def test_full_size_multistep_flow_is_sliced_consistently(sol_system, sol_oracle,
+                                                         sol_gpu):
+  """At 40 000 probes the call is cut into probe slices and step sub-chunks on
+  helper streams (principia_b200.cu); probes are independent, so any subset
+  equals the oracle bit for bit, samples across slice boundaries included."""
+  n = 40000
+  method = _capi.QUINLAN_1999_ORDER_8A
+  state0 = leo(sol_system, n, seed=9)
+  state = state0.copy()
+  time = np.zeros(2)
+  t_final = 455.0  # Startup (7 steps) + 38 multistep steps: 4 sub-chunks.
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, t_final, state, time,
+                                        sample_every=9, max_samples=8)
+  assert result['n_steps'] == 45 and result['status'] == 0
+  subset = np.r_[0:33, 9990:10030, 19999:20001, 29950:29990, n - 33:n]
+  expected_state = np.ascontiguousarray(state0[:, subset])
+  expected_time = np.zeros(2)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, t_final,
+                                             expected_state, expected_time,
+                                             sample_every=9, max_samples=8)
+  assert expected['n_steps'] == 45
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state[:, subset], expected_state, 'subset')
+  assert_bitwise_equal(result['sample_times'], expected['sample_times'])
+  assert_bitwise_equal(result['samples'][:, :, subset], expected['samples'],
+                       'subset samples')
