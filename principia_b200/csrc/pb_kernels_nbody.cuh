@@ -192,13 +192,15 @@ static __device__ __noinline__ Vec3 CooperativeAccelerationOnBody(
                           : kEnsembleLanes;
 #pragma unroll 1
     for (int source = 0; source < count; ++source) {
+      // The mask is the same in every lane, so the branches are uniform and
+      // an absent addend costs no shuffle.
       unsigned const mask = __shfl_sync(0xffffffffu, present[set], source);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        Vec3 const x{__shfl_sync(0xffffffffu, addend[set][k].x, source),
-                     __shfl_sync(0xffffffffu, addend[set][k].y, source),
-                     __shfl_sync(0xffffffffu, addend[set][k].z, source)};
         if (mask & (1u << k)) {
+          Vec3 const x{__shfl_sync(0xffffffffu, addend[set][k].x, source),
+                       __shfl_sync(0xffffffffu, addend[set][k].y, source),
+                       __shfl_sync(0xffffffffu, addend[set][k].z, source)};
           a = a + x;
         }
       }
