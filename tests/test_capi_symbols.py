@@ -42,3 +42,33 @@ def test_fails_loudly_without_a_device():
   assert status == _capi.PB_FAILED_PRECONDITION
   assert b'no CPU fallback' in lib.pb_last_error()
   assert not handle.value
+
+
+def test_argument_validation_needs_no_device():
+  """Contract violations are reported as PB_INVALID_ARGUMENT with a message
+  (where the reference would CHECK), before any CUDA call."""
+  lib = _capi.library()
+  null = ctypes.c_void_p()
+  d3 = (ctypes.c_double * 3)()
+  handle = ctypes.c_void_p()
+  assert lib.pb_continuous_trajectories_create(
+      0, 0, 600.0, 1e-3, 4, ctypes.byref(handle)) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_continuous_trajectories_create(
+      0, 8, -1.0, 1e-3, 4, ctypes.byref(handle)) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_continuous_trajectories_create(
+      0, 8, 600.0, 1e-3, 0, ctypes.byref(handle)) == _capi.PB_INVALID_ARGUMENT
+  assert not handle.value
+  assert lib.pb_continuous_trajectories_append(
+      null, 0.0, d3, d3) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_continuous_trajectories_status(null) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_compute_gravitational_jerk_on_massless_bodies(
+      null, 0.0, 1, d3, d3, d3) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_compute_gravitational_jerk_and_jacobian_on_massive_bodies(
+      null, 0.0, None, None, d3, None) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_ephemeris_evaluate_all_velocities(
+      null, 0.0, d3) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_downsampler_evaluate(null, 0.0, d3, d3,
+                                     None) == _capi.PB_INVALID_ARGUMENT
+  assert lib.pb_nbody_ensemble_solve_to_trajectories(
+      null, 0.0, null, None) == _capi.PB_INVALID_ARGUMENT
+  assert len(lib.pb_last_error()) > 0
