@@ -107,6 +107,60 @@ def bench_adaptive(args):
         'sink_mean_timeline_points': timeline_points}))
 
 
+def bench_single(args):
+  """Config 1 (the reference's own CPU-runnable case, ephemeris_benchmark.cpp
+  :201-219): ONE LEO probe in the Sol field, SRKN14A at 10 s.  Sequential in
+  time: it does not shard (replicas only) and is latency-bound on a GPU; the
+  oracle on one host core is timed beside it."""
+  torch, dist, world, rank, local_rank = dist_setup()
+  if rank != 0:
+    return
+  from principia_b200 import _capi
+  from principia_b200 import workloads
+  from principia_b200.ephemeris import Ephemeris
+  from oracle_lib import OracleEphemeris
+  system = workloads.sol_system()
+  ephemeris = Ephemeris(system, device=local_rank)
+  workloads.upload_sol_ephemeris(ephemeris)
+  oracle = OracleEphemeris(system)
+  for body, segments in enumerate(workloads.load_sol_ephemeris_segments()):
+    oracle.append_segments(body, segments)
+  earth = system.bodies[system.index('Earth')]
+  # Radius 6371 km + 100 nautical miles, circular, in the equatorial plane of
+  # the frame (the benchmark's probe).
+  r = 6371e3 + 100 * 1852.0
+  state0 = np.zeros((12, 1))
+  state0[0:3, 0] = np.array(earth['q']) + [r, 0.0, 0.0]
+  state0[6:9, 0] = np.array(earth['v']) + [0.0, math.sqrt(earth['mu'] / r), 0.0]
+  method = _capi.BLANES_MOAN_2002_SRKN_14A
+  span = args.span  # Seconds; the golden ephemeris covers two days.
+  steps = int(span / 10.0)
+  ephemeris.flow_with_fixed_step(method, 10.0, 100.0, state0.copy(),
+                                 np.zeros(2))  # Warm-up.
+  state = state0.copy()
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  result = ephemeris.flow_with_fixed_step(method, 10.0, span, state,
+                                          np.zeros(2))
+  gpu_seconds = time.perf_counter() - t0
+  assert result['n_steps'] == steps
+  expected = state0.copy()
+  t0 = time.perf_counter()
+  oracle.flow_with_fixed_step(method, 10.0, span, expected, np.zeros(2),
+                              threads=1)
+  cpu_seconds = time.perf_counter() - t0
+  assert np.array_equal(state.view(np.int64), expected.view(np.int64))
+  print(json.dumps({
+      'config': 'config 1: one LEO probe, Sol field, SRKN14A at 10 s '
+                '(sequential: replicas only)',
+      'span_seconds': span, 'steps': steps,
+      'gpu_seconds': gpu_seconds,
+      'gpu_probe_stages_per_second': steps * 14 / gpu_seconds,
+      'cpu_oracle_one_core_seconds': cpu_seconds,
+      'cpu_probe_stages_per_second': steps * 14 / cpu_seconds,
+      'bitwise_equal': True}))
+
+
 def bench_history(args):
   """The plugin's history integrator on the config-2 probes: 10^5 LEO probes,
   Quinlan1999Order8A at 10 s (ksp_plugin/integrators.cpp:66-72), one
@@ -374,6 +428,8 @@ def main():
   args = parser.parse_args()
   if args.config in ('adaptive', 'all'):
     bench_adaptive(args)
+  if args.config in ('single',):
+    bench_single(args)
   if args.config in ('history', 'all'):
     bench_history(args)
   if args.config in ('ensemble', 'all'):
