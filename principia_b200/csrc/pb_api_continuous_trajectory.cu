@@ -214,6 +214,8 @@ pb_status_t pb_continuous_trajectories_status(pb_continuous_trajectories_t* h) {
     return Fail(PB_INVALID_ARGUMENT, "null argument");
   }
   PB_CUDA(cudaSetDevice(h->device));
+  // The appends may be in flight on any stream.
+  PB_CUDA(cudaDeviceSynchronize());
   int32_t word = 0;
   PB_CUDA(cudaMemcpy(&word, h->status_word.data, sizeof(word),
                      cudaMemcpyDeviceToHost));
