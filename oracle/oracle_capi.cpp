@@ -120,6 +120,57 @@ int32_t orc_kat_fixed_step_oscillator(int32_t method, double t_final,
   return status;
 }
 
+// The same oscillator from any initial state, with the states appended
+// (time, q, v values) returned: the shape of the Symplecticity, Convergence,
+// TimeReversibility and Termination tests of
+// symplectic_runge_kutta_nyström_integrator_test.cpp:349-587 and
+// symmetric_linear_multistep_integrator_test.cpp:161-336.  Returns the status
+// of Solve; at most `capacity` states are stored, *n_states counts them all.
+int32_t orc_oscillator_solve(int32_t method, double t0, double q0, double q0_error,
+                             double v0, double v0_error, double t_final,
+                             double step, std::int64_t capacity, double* times,
+                             double* q, double* v, double* final_state,
+                             std::int64_t* n_states,
+                             std::int64_t* evaluations) {
+  std::int64_t evals = 0;
+  RightHandSide rhs = [&evals](double, std::vector<double> const& q,
+                               std::vector<double>& g) {
+    g[0] = -q[0] * 1.0;
+    ++evals;
+    return static_cast<int32_t>(kOk);
+  };
+  State state;
+  state.time = {t0, 0.0};
+  state.positions.resize(1);
+  state.velocities.resize(1);
+  state.positions[0] = {q0, q0_error};
+  state.velocities[0] = {v0, v0_error};
+  std::int64_t count = 0;
+  State last = state;
+  AppendState append = [&](State const& s) {
+    if (count < capacity) {
+      times[count] = s.time.value;
+      q[count] = s.positions[0].value;
+      v[count] = s.velocities[0].value;
+    }
+    last = s;
+    ++count;
+  };
+  FixedStepInstance instance(method, rhs, state, append, step);
+  int32_t const status = instance.Solve(t_final);
+  if (final_state != nullptr) {
+    final_state[0] = last.time.value;
+    final_state[1] = last.time.error;
+    final_state[2] = last.positions[0].value;
+    final_state[3] = last.positions[0].error;
+    final_state[4] = last.velocities[0].value;
+    final_state[5] = last.velocities[0].error;
+  }
+  *n_states = count;
+  *evaluations = evals;
+  return status;
+}
+
 // embedded_explicit_runge_kutta_nyström_integrator_test.cpp:75-182.  Runs
 // forward from (q0, v0, t0) to t_final; outputs the final state so that the
 // backward leg can be chained.

@@ -20,6 +20,9 @@ _dp, _i32p, _i64p = _capi.c_double_p, _capi.c_int32_p, _capi.c_int64_p
 _SYMBOLS = [
     ('orc_kat_fixed_step_oscillator', _i32,
      [_i32, _d, _d, _dp, _dp, _i64p, _i64p]),
+    ('orc_oscillator_solve', _i32,
+     [_i32, _d, _d, _d, _d, _d, _d, _d, _i64, _dp, _dp, _dp, _dp, _i64p,
+      _i64p]),
     ('orc_kat_adaptive_oscillator', _i32,
      [_d, _d, _d, _d, _d, _d, _d, _d, _i64p, _i64p, _i64p, _i64p, _dp]),
     ('orc_cr_sin', _d, [_d]),

@@ -1094,3 +1094,132 @@ def test_newhall_approximation_in_monomial_basis(case):
   expected = case['value_error_with_fma'] or case['value_error']
   assert near(value_error, expected), (value_error, expected)
   assert near(variation_error, case['variation_error']), variation_error
+
+
+# ---------------------------------------------------------------------------
+# The other tests of the reference's fixed-step integrators on the harmonic
+# oscillator: integrators/symplectic_runge_kutta_nyström_integrator_test.cpp
+# :349-587 (instances :142-182) and symmetric_linear_multistep_integrator_test
+# .cpp:161-336 (instances :112-142).
+
+def _oscillator_solve(method, t_final, step, t0=0.0, q0=(1.0, 0.0),
+                      v0=(0.0, 0.0), capacity=0):
+  lib = oracle_lib.library()
+  times, q, v = (np.zeros(max(capacity, 1)) for _ in range(3))
+  final = np.zeros(6)
+  n, evaluations = ctypes.c_int64(), ctypes.c_int64()
+  dptr = oracle_lib.dptr
+  status = lib.orc_oscillator_solve(
+      method, t0, q0[0], q0[1], v0[0], v0[1], t_final, step, capacity,
+      dptr(times), dptr(q), dptr(v), dptr(final), ctypes.byref(n),
+      ctypes.byref(evaluations))
+  count = min(n.value, capacity)
+  return dict(status=status, n=n.value, evaluations=evaluations.value,
+              times=times[:count], q=q[:count], v=v[:count], final=final)
+
+
+def _slope_and_correlation(x, y):
+  x, y = np.asarray(x), np.asarray(y)
+  slope = np.polyfit(x, y, 1)[0]
+  return slope, np.corrcoef(x, y)[0, 1]
+
+
+_OSCILLATOR_INSTANCES = [
+    # method, order, evaluations per step, beginning of convergence, expected
+    # energy error (EXPECT_EQ), multistep.
+    (_capi.BLANES_MOAN_2002_SRKN_14A, 6, 14, 1.0, 6.29052365752613700e-13,
+     False),
+    (_capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, 5, 6, 1.1,
+     3.06327349042234690e-08, False),
+    (_capi.QUINLAN_1999_ORDER_8A, 8, 1, 0.07, 3.93946996135596805e-08, True),
+    (_capi.QUINLAN_TREMAINE_1990_ORDER_12, 12, 1, 0.21,
+     4.14703826834283973e-11, True),
+]
+_OSCILLATOR_IDS = ['SRKN14A', 'McLachlanAtela1992Order5Optimal',
+                   'Quinlan1999Order8A', 'QuinlanTremaine1990Order12']
+
+
+@pytest.mark.parametrize('instance', _OSCILLATOR_INSTANCES,
+                         ids=_OSCILLATOR_IDS)
+def test_oscillator_symplecticity(instance):
+  method, _, _, _, expected_energy_error, multistep = instance
+  solution = _oscillator_solve(method, 500.0, 0.2, capacity=2500)
+  assert solution['status'] == 0
+  q, v = solution['q'], solution['v']
+  # 0.5 * m * Pow<2>(v) + 0.5 * k * Pow<2>(q), m = 1 kg, k = 1 N/m.
+  energy = 0.5 * 1.0 * (v * v) + 0.5 * 1.0 * (q * q)
+  initial_energy = 0.5 * 1.0 * 0.0 + 0.5 * 1.0 * 1.0
+  energy_error = np.abs(initial_energy - energy)
+  slope, correlation = _slope_and_correlation(solution['times'], energy_error)
+  assert correlation < (0.011 if multistep else 2e-3)
+  assert abs(slope) < 2e-6
+  # Bit-exact: the reference's EXPECT_EQ.
+  assert energy_error.max() == expected_energy_error
+
+
+@pytest.mark.parametrize('instance', _OSCILLATOR_INSTANCES,
+                         ids=_OSCILLATOR_IDS)
+def test_oscillator_convergence(instance):
+  method, order, _, step, _, multistep = instance
+  log_steps, log_q_errors, log_p_errors = [], [], []
+  for _ in range(50):
+    final = _oscillator_solve(method, 100.0, step)['final']
+    t, q, v = final[0], final[2], final[4]
+    log_q_error = math.log10(abs(q - math.cos(t)))
+    log_p_error = math.log10(abs(v + math.sin(t)))
+    if log_q_error <= -13 or log_p_error <= -13:
+      break
+    log_steps.append(math.log10(step))
+    log_q_errors.append(log_q_error)
+    log_p_errors.append(log_p_error)
+    step /= 1.1
+  q_order, q_correlation = _slope_and_correlation(log_steps, log_q_errors)
+  v_order, v_correlation = _slope_and_correlation(log_steps, log_p_errors)
+  if multistep:
+    assert abs(q_order - order) / order < 0.02
+    assert 0.9997 < q_correlation <= 1
+    assert abs(v_order - order) / order < 0.02
+    assert 0.99993 < v_correlation <= 1
+  else:
+    assert abs(q_order - order) < 0.10
+    assert 0.993 < q_correlation <= 1
+    # "SPRKs with odd convergence order have a higher convergence order in p."
+    assert abs(v_order - (order + order % 2)) < 0.16
+    assert 0.994 < v_correlation <= 1
+
+
+@pytest.mark.parametrize('instance', _OSCILLATOR_INSTANCES[:2],
+                         ids=_OSCILLATOR_IDS[:2])
+def test_oscillator_time_reversibility(instance):
+  method = instance[0]
+  forward = _oscillator_solve(method, 100.0, 0.5)['final']
+  backward = _oscillator_solve(method, 0.0, -0.5, t0=forward[0],
+                               q0=(forward[2], forward[3]),
+                               v0=(forward[4], forward[5]))['final']
+  assert backward[0] == 0.0
+  # Both methods are time-reversible (methods.hpp:379-419,922-949 ...): within
+  # 30 ULPs of the start, the velocity vanishes before 1 m/s within 70 ULPs.
+  if method == _capi.BLANES_MOAN_2002_SRKN_14A:
+    assert ulp_distance(backward[2], 1.0) <= 30
+    assert ulp_distance(1.0 + backward[4], 1.0) <= 70
+  else:
+    # McLachlanAtela1992Order5Optimal is not time-reversible.
+    assert abs(backward[2] - 1.0) > 1e-6
+    assert abs(backward[4]) > 1e-6
+
+
+@pytest.mark.parametrize('instance', _OSCILLATOR_INSTANCES,
+                         ids=_OSCILLATOR_IDS)
+def test_oscillator_termination(instance):
+  method, _, evaluations, _, _, multistep = instance
+  t_final = 1630.0 if multistep else 163.0
+  steps = int(math.floor(t_final / 42.0))
+  solution = _oscillator_solve(method, t_final, 42.0, capacity=64)
+  assert solution['status'] == 0
+  assert solution['n'] == steps
+  assert t_final - 42.0 < solution['times'][-1] <= t_final
+  if not multistep:
+    # BA and ABA compositions: steps * evaluations.
+    assert solution['evaluations'] == steps * evaluations
+  for i, t in enumerate(solution['times']):
+    assert t == (i + 1) * 42.0  # AlmostEquals(..., 0).
