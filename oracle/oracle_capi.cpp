@@ -174,6 +174,13 @@ int32_t orc_oscillator_solve(int32_t method, double t0, double q0, double q0_err
 // embedded_explicit_runge_kutta_nyström_integrator_test.cpp:75-182.  Runs
 // forward from (q0, v0, t0) to t_final; outputs the final state so that the
 // backward leg can be chained.
+int32_t orc_kat_adaptive_oscillator_max_steps(
+    double t0, double q0, double q0_error, double v0, double v0_error,
+    double t_final, double length_tolerance, double speed_tolerance,
+    std::int64_t max_steps, std::int64_t* n_states, std::int64_t* evaluations,
+    std::int64_t* initial_rejections, std::int64_t* subsequent_rejections,
+    double* final_state /* t, q, qe, v, ve */);
+
 int32_t orc_kat_adaptive_oscillator(double t0, double q0, double q0_error,
                                     double v0, double v0_error, double t_final,
                                     double length_tolerance,
@@ -183,6 +190,20 @@ int32_t orc_kat_adaptive_oscillator(double t0, double q0, double q0_error,
                                     std::int64_t* initial_rejections,
                                     std::int64_t* subsequent_rejections,
                                     double* final_state /* t, q, qe, v, ve */) {
+  return orc_kat_adaptive_oscillator_max_steps(
+      t0, q0, q0_error, v0, v0_error, t_final, length_tolerance,
+      speed_tolerance, std::numeric_limits<std::int64_t>::max(), n_states,
+      evaluations, initial_rejections, subsequent_rejections, final_state);
+}
+
+// The same with the max_steps of the integrator's parameters (the MaxSteps test,
+// :184-270).
+int32_t orc_kat_adaptive_oscillator_max_steps(
+    double t0, double q0, double q0_error, double v0, double v0_error,
+    double t_final, double length_tolerance, double speed_tolerance,
+    std::int64_t max_steps, std::int64_t* n_states, std::int64_t* evaluations,
+    std::int64_t* initial_rejections, std::int64_t* subsequent_rejections,
+    double* final_state /* t, q, qe, v, ve */) {
   std::int64_t evals = 0;
   RightHandSide rhs = [&evals](double, std::vector<double> const& q,
                                std::vector<double>& g) {
@@ -222,6 +243,7 @@ int32_t orc_kat_adaptive_oscillator(double t0, double q0, double q0_error,
   };
   AdaptiveParameters parameters;
   parameters.first_step = t_final - t0;
+  parameters.max_steps = max_steps;
   ErknInstance instance(DormandElMikkawyPrince1986RKN434FM(), rhs, state,
                         append, ratio, parameters);
   int32_t const status = instance.Solve(t_final);
@@ -235,6 +257,79 @@ int32_t orc_kat_adaptive_oscillator(double t0, double q0, double q0_error,
   final_state[3] = last.velocities[0].value;
   final_state[4] = last.velocities[0].error;
   return status;
+}
+
+// embedded_explicit_runge_kutta_nyström_integrator_test.cpp:338-439 (Restart):
+// the oscillator over `duration` with last_step_is_exact = false, then the same
+// instance continued to 2 * duration; and again in one call to Solve.
+// sizes[0..1]: appended states after the first and the second Solve;
+// last_steps[0..1]: the last time differences at those two points; returns 1
+// if the one-call solution equals the restarted one state for state.
+int32_t orc_kat_adaptive_oscillator_restart(double duration,
+                                            double length_tolerance,
+                                            double speed_tolerance,
+                                            std::int64_t* sizes,
+                                            double* last_steps) {
+  auto const make_rhs = [] {
+    return RightHandSide([](double, std::vector<double> const& q,
+                            std::vector<double>& g) {
+      g[0] = -q[0] * 1.0;
+      return static_cast<int32_t>(kOk);
+    });
+  };
+  ToleranceToErrorRatio const ratio = [&](double, State const&,
+                                          StateError const& error) {
+    return std::min(length_tolerance / std::abs(error.position_error[0]),
+                    speed_tolerance / std::abs(error.velocity_error[0]));
+  };
+  State initial;
+  initial.positions.resize(1);
+  initial.velocities.resize(1);
+  initial.positions[0].value = 1.0;
+  AdaptiveParameters parameters;
+  parameters.first_step = duration;
+  parameters.last_step_is_exact = false;
+  std::vector<State> solution1, solution2;
+  {
+    ErknInstance instance(
+        DormandElMikkawyPrince1986RKN434FM(), make_rhs(), initial,
+        [&](State const& s) { solution1.push_back(s); }, ratio, parameters);
+    if (instance.Solve(0.0 + duration) != kOk) {
+      return -1;
+    }
+    sizes[0] = static_cast<std::int64_t>(solution1.size());
+    last_steps[0] = solution1[solution1.size() - 1].time.value -
+                    solution1[solution1.size() - 2].time.value;
+    if (instance.Solve(0.0 + 2.0 * duration) != kOk) {
+      return -1;
+    }
+    sizes[1] = static_cast<std::int64_t>(solution1.size());
+    last_steps[1] = solution1[solution1.size() - 1].time.value -
+                    solution1[solution1.size() - 2].time.value;
+  }
+  {
+    ErknInstance instance(
+        DormandElMikkawyPrince1986RKN434FM(), make_rhs(), initial,
+        [&](State const& s) { solution2.push_back(s); }, ratio, parameters);
+    if (instance.Solve(0.0 + 2.0 * duration) != kOk) {
+      return -1;
+    }
+  }
+  if (solution1.size() != solution2.size()) {
+    return 0;
+  }
+  for (std::size_t i = 0; i < solution1.size(); ++i) {
+    State const& a = solution1[i];
+    State const& b = solution2[i];
+    if (a.time.value != b.time.value || a.time.error != b.time.error ||
+        a.positions[0].value != b.positions[0].value ||
+        a.positions[0].error != b.positions[0].error ||
+        a.velocities[0].value != b.velocities[0].value ||
+        a.velocities[0].error != b.velocities[0].error) {
+      return 0;
+    }
+  }
+  return 1;
 }
 
 double orc_cr_sin(double x) { return CrSin(x); }

@@ -25,6 +25,9 @@ _SYMBOLS = [
       _i64p]),
     ('orc_kat_adaptive_oscillator', _i32,
      [_d, _d, _d, _d, _d, _d, _d, _d, _i64p, _i64p, _i64p, _i64p, _dp]),
+    ('orc_kat_adaptive_oscillator_restart', _i32, [_d, _d, _d, _i64p, _dp]),
+    ('orc_kat_adaptive_oscillator_max_steps', _i32,
+     [_d, _d, _d, _d, _d, _d, _d, _d, _i64, _i64p, _i64p, _i64p, _i64p, _dp]),
     ('orc_cr_sin', _d, [_d]),
     ('orc_cr_cos', _d, [_d]),
     ('orc_root', _d, [_i32, _d]),

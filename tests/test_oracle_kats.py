@@ -82,6 +82,49 @@ def test_adaptive_harmonic_oscillator_back_and_forth():
   assert 2.45e-3 < abs(fs[3]) < 2.65e-3
 
 
+# integrators/embedded_explicit_runge_kutta_nyström_integrator_test.cpp:184-270.
+def test_adaptive_harmonic_oscillator_max_steps():
+  lib = oracle_lib.library()
+  n, ev = ctypes.c_int64(), ctypes.c_int64()
+  ir, sr = ctypes.c_int64(), ctypes.c_int64()
+  fs = (ctypes.c_double * 5)()
+  t_final = 0.0 + 10 * (2 * math.pi)
+  status = lib.orc_kat_adaptive_oscillator_max_steps(
+      0.0, 1.0, 0.0, 0.0, 0.0, t_final, 1e-3, 1e-3, 100, n, ev, ir, sr, fs)
+  assert status == _capi.PB_RESOURCE_EXHAUSTED  # ReachedMaximalStepCount.
+  assert n.value == 100
+  assert fs[0] < t_final
+  assert is_near(abs(fs[1] - math.cos(fs[0])), 9.0e-4)
+  assert is_near(abs(fs[3] + math.sin(fs[0])), 1.9e-3)
+  # A max_steps at or above the unconstrained number of steps has no effect.
+  for max_steps in (132, 132 + 1234):
+    status = lib.orc_kat_adaptive_oscillator_max_steps(
+        0.0, 1.0, 0.0, 0.0, 0.0, t_final, 1e-3, 1e-3, max_steps, n, ev, ir, sr,
+        fs)
+    assert status == 0
+    assert is_near(abs(fs[1] - 1.0), 3.6e-4)
+    assert is_near(abs(fs[3]), 2.8e-3)
+    assert fs[0] == t_final
+    assert n.value == 132
+
+
+# integrators/embedded_explicit_runge_kutta_nyström_integrator_test.cpp:338-439:
+# the step size survives a restart of Solve (pinned to the bit, AlmostEquals(·,
+# 0), which pins the whole step control including the fourth root), and two
+# calls to Solve equal one.
+def test_adaptive_harmonic_oscillator_restart():
+  lib = oracle_lib.library()
+  sizes = np.zeros(2, dtype=np.int64)
+  last_steps = np.zeros(2)
+  same = lib.orc_kat_adaptive_oscillator_restart(
+      10 * (2 * math.pi), 1e-3, 1e-3,
+      sizes.ctypes.data_as(_capi.c_int64_p), oracle_lib.dptr(last_steps))
+  assert same == 1
+  assert list(sizes) == [131, 261]
+  assert last_steps[0] == 0.509363975335290320
+  assert last_steps[1] == 0.506410259195249068
+
+
 def test_correctly_rounded_functions_against_mpmath():
   import mpmath
   mpmath.mp.prec = 400
