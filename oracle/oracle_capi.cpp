@@ -332,6 +332,47 @@ int32_t orc_kat_adaptive_oscillator_restart(double duration,
   return 1;
 }
 
+// embedded_explicit_runge_kutta_nyström_integrator_test.cpp:271-336
+// (Singularity): the ideal rocket x"(t) = m' I_sp / (m0 - t m') with unit
+// constants, integrated across its singularity at t = 1 s.
+int32_t orc_kat_adaptive_rocket(double length_tolerance, double speed_tolerance,
+                                std::int64_t* n_states, double* final_time,
+                                double* final_position) {
+  double const mass_flow = 1, initial_mass = 1, specific_impulse = 1;
+  double const t_initial = 0;
+  double const t_final = t_initial + 2 * initial_mass / mass_flow;
+  RightHandSide rhs = [&](double const t, std::vector<double> const&,
+                          std::vector<double>& g) {
+    double const mass = initial_mass - (t - t_initial) * mass_flow;
+    g.back() = mass_flow * specific_impulse / mass;
+    return static_cast<int32_t>(kOk);
+  };
+  ToleranceToErrorRatio const ratio = [&](double, State const&,
+                                          StateError const& error) {
+    return std::min(length_tolerance / std::abs(error.position_error[0]),
+                    speed_tolerance / std::abs(error.velocity_error[0]));
+  };
+  State state;
+  state.positions.resize(1);
+  state.velocities.resize(1);
+  std::int64_t count = 0;
+  State last = state;
+  AdaptiveParameters parameters;
+  parameters.first_step = t_final - t_initial;
+  ErknInstance instance(
+      DormandElMikkawyPrince1986RKN434FM(), rhs, state,
+      [&](State const& s) {
+        last = s;
+        ++count;
+      },
+      ratio, parameters);
+  int32_t const status = instance.Solve(t_final);
+  *n_states = count;
+  *final_time = last.time.value;
+  *final_position = last.positions.back().value;
+  return status;
+}
+
 double orc_cr_sin(double x) { return CrSin(x); }
 double orc_cr_cos(double x) { return CrCos(x); }
 double orc_root(int32_t n, double x) { return Root(n, x); }

@@ -125,6 +125,24 @@ def test_adaptive_harmonic_oscillator_restart():
   assert last_steps[1] == 0.506410259195249068
 
 
+# integrators/embedded_explicit_runge_kutta_nyström_integrator_test.cpp:271-336:
+# the rocket equation across its singularity: VanishingStepSize after 132
+# steps, at the singular time within 15 ULPs, position within 540 ULPs of
+# I_sp m0 / m'.
+def test_adaptive_singularity():
+  lib = oracle_lib.library()
+  n = ctypes.c_int64()
+  t, x = ctypes.c_double(), ctypes.c_double()
+  status = lib.orc_kat_adaptive_rocket(1e-3, 1e-3, ctypes.byref(n),
+                                       ctypes.byref(t), ctypes.byref(x))
+  assert status == _capi.PB_FAILED_PRECONDITION  # VanishingStepSize.
+  assert n.value == 132
+  # The reference's bounds are the distances its own binary produced; the
+  # oracle lands on them exactly.
+  assert ulp_distance(t.value, 1.0) == 15
+  assert ulp_distance(x.value, 1.0) == 540
+
+
 def test_correctly_rounded_functions_against_mpmath():
   import mpmath
   mpmath.mp.prec = 400
