@@ -373,6 +373,32 @@ int32_t orc_kat_adaptive_rocket(double length_tolerance, double speed_tolerance,
   return status;
 }
 
+// numerics/hermite3_body.hpp as the trajectory sink uses it: the interpolant of
+// (q1, v1) at t1 and (q2, v2) at t2 evaluated with its derivative at n times
+// (AoS outputs), and its LInfinityL₂Norm (meaningful when q1 and v1 vanish:
+// :154-194).
+void orc_hermite3(double t1, double t2, double const* q1, double const* q2,
+                  double const* v1, double const* v2, std::int64_t n,
+                  double const* times, double* values, double* derivatives,
+                  double* l_infinity_l2_norm) {
+  Hermite3 const h = MakeHermite3(t1, t2, {q1[0], q1[1], q1[2]},
+                                  {q2[0], q2[1], q2[2]}, {v1[0], v1[1], v1[2]},
+                                  {v2[0], v2[1], v2[2]});
+  for (std::int64_t i = 0; i < n; ++i) {
+    Vec3 const q = Evaluate(h, times[i]);
+    Vec3 const v = EvaluateDerivative(h, times[i]);
+    values[3 * i] = q.x;
+    values[3 * i + 1] = q.y;
+    values[3 * i + 2] = q.z;
+    derivatives[3 * i] = v.x;
+    derivatives[3 * i + 1] = v.y;
+    derivatives[3 * i + 2] = v.z;
+  }
+  if (l_infinity_l2_norm != nullptr) {
+    *l_infinity_l2_norm = LInfinityL2Norm(h);
+  }
+}
+
 double orc_cr_sin(double x) { return CrSin(x); }
 double orc_cr_cos(double x) { return CrCos(x); }
 double orc_root(int32_t n, double x) { return Root(n, x); }

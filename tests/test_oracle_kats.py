@@ -620,6 +620,51 @@ def is_near(value, expected, digits=2):
   return expected - unit * (1 + 1e-9) <= value <= expected + unit * (1 + 1e-9)
 
 
+def _hermite3_oracle(t1, t2, q1, q2, v1, v2, times):
+  lib = oracle_lib.library()
+  arrays = [np.ascontiguousarray(x, dtype=np.float64)
+            for x in (q1, q2, v1, v2, times)]
+  n = len(times)
+  values, derivatives = np.zeros((n, 3)), np.zeros((n, 3))
+  norm = ctypes.c_double()
+  dptr = oracle_lib.dptr
+  lib.orc_hermite3(t1, t2, dptr(arrays[0]), dptr(arrays[1]), dptr(arrays[2]),
+                   dptr(arrays[3]), n, dptr(arrays[4]), dptr(values),
+                   dptr(derivatives), ctypes.byref(norm))
+  return values, derivatives, norm.value
+
+
+# numerics/hermite3_test.cpp:44-64,97-140: the interpolant of the trajectory
+# sink, EXPECT_EQ known answers.
+def test_hermite3_known_answers():
+  # Precomputed.
+  times = [1.0, 1.25, 1.5, 1.75, 2.0]
+  values, derivatives, _ = _hermite3_oracle(
+      1.0, 2.0, [33.0, 0, 0], [40.0, 0, 0], [-5.0, 0, 0], [6.0, 0, 0], times)
+  assert list(values[:, 0]) == [33.0, 33.109375, 35.125, 37.828125, 40.0]
+  assert list(derivatives[:, 0]) == [-5.0, 5.0625, 10.25, 10.5625, 6.0]
+  # Conditioning: the computed position at the end of the interval is negative.
+  t1, t2 = 19418861.806896236, 19418869.842261545
+  values, derivatives, _ = _hermite3_oracle(
+      t1, t2, [-2.1383610158805017e-12, 0, 0], [0.0, 0, 0],
+      [2.3308208035605881e-12, 0, 0], [-1.6875631840376598e-12, 0, 0],
+      [t1, t2])
+  assert values[0, 0] == -2.1383610158805017e-12
+  assert values[1, 0] < 0
+  assert derivatives[0, 0] == 2.3308208035605881e-12
+  # LInfinityL₂NormMass: exactly 5.
+  _, _, norm = _hermite3_oracle(0.0, 3.0, [0.0, 0, 0], [-5.0, 0, 0],
+                                [0.0, 0, 0], [-1.0, 0, 0], [0.0])
+  assert norm == 5.0
+  # LInfinityL₂NormDisplacement: within 2 ULPs of the closed form.
+  _, _, norm = _hermite3_oracle(0.0, 3.0, [0.0, 0.0, 0.0], [4.0, -5.0, 6.0],
+                                [0.0, 0.0, 0.0], [-10.0, 11.0, 12.0], [0.0])
+  expected = (32.0 * math.sqrt((89585829490348391.0 +
+                                94266519982393.0 * math.sqrt(74917.0)) /
+                               3869.0)) / 14969161.0
+  assert ulp_distance(norm, expected) <= 2
+
+
 # physics/discrete_trajectory_segment_test.cpp:252-324.
 def test_downsampling_circle_and_straight_line():
   import trajectory_factories
