@@ -399,6 +399,20 @@ void orc_hermite3(double t1, double t2, double const* q1, double const* q2,
   }
 }
 
+// HarmonicDamping(s0).ComputeDampedRadialQuantities along x,
+// physics/harmonic_damping_body.hpp:16-60.
+void orc_harmonic_damping(double s0, double r, double R_over_r, double R_prime,
+                          double* thresholds, double* sigma_R_over_r,
+                          double* grad_sigma_R_x) {
+  HarmonicDamping const damping(s0);
+  thresholds[0] = damping.inner_threshold;
+  thresholds[1] = damping.outer_threshold;
+  Vec3 grad;
+  damping.ComputeDampedRadialQuantities(r, r * r, {1, 0, 0}, R_over_r, R_prime,
+                                        *sigma_R_over_r, grad);
+  *grad_sigma_R_x = grad.x;
+}
+
 double orc_cr_sin(double x) { return CrSin(x); }
 double orc_cr_cos(double x) { return CrCos(x); }
 double orc_root(int32_t n, double x) { return Root(n, x); }

@@ -447,6 +447,28 @@ def test_geopotential_potential_against_acceleration_on_the_reference_sample():
   assert low < 3.5e-9 and high > 8.2e-6, (low, high)
 
 
+# physics/harmonic_damping_test.cpp:27-70 (AccelerationQuantities), all Eq.
+def test_harmonic_damping_known_answers():
+  lib = oracle_lib.library()
+  R_over_r, R_prime = 5.0, 17.0
+
+  def damped(r):
+    thresholds = np.zeros(2)
+    value, grad = ctypes.c_double(), ctypes.c_double()
+    lib.orc_harmonic_damping(1.0, r, R_over_r, R_prime,
+                             oracle_lib.dptr(thresholds), ctypes.byref(value),
+                             ctypes.byref(grad))
+    assert list(thresholds) == [1.0, 3.0]
+    return value.value, grad.value
+
+  assert damped(3.0) == (0.0, 0.0)
+  # r = 2: sigma = 1/2, sigma' = -3/4, R = R_over_r * r.
+  assert damped(2.0) == (R_over_r / 2, (-3 / 4) * (R_over_r * 2.0) +
+                         R_prime * 0.5)
+  assert damped(1.0) == (R_over_r, R_prime)
+  assert damped(0.5) == (R_over_r, R_prime)
+
+
 # physics/geopotential_test.cpp:398-560.
 def test_geopotential_threshold_computation():
   system = _test_earth(5)
