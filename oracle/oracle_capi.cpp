@@ -413,6 +413,42 @@ void orc_harmonic_damping(double s0, double r, double R_over_r, double R_prime,
   *grad_sigma_R_x = grad.x;
 }
 
+// numerics/double_precision_body.hpp: the primitives the steppers use, on
+// {value, error} pairs.  op: 0 Increment(x, a[0]); 1 TwoSum(a[0], b[0]);
+// 2 QuickTwoSum; 3 TwoDifference; 4 x + y; 5 x - y; 6 Scale(a[0], y).
+void orc_double_precision(int32_t op, double const* a, double const* b,
+                          double* out) {
+  DP x{a[0], a[1]};
+  DP const y{b[0], b[1]};
+  DP result{0.0, 0.0};
+  switch (op) {
+    case 0:
+      Increment(x, b[0]);
+      result = x;
+      break;
+    case 1:
+      result = TwoSum(a[0], b[0]);
+      break;
+    case 2:
+      result = QuickTwoSum(a[0], b[0]);
+      break;
+    case 3:
+      result = TwoDifference(a[0], b[0]);
+      break;
+    case 4:
+      result = x + y;
+      break;
+    case 5:
+      result = x - y;
+      break;
+    case 6:
+      result = Scale(a[0], y);
+      break;
+  }
+  out[0] = result.value;
+  out[1] = result.error;
+}
+
 double orc_cr_sin(double x) { return CrSin(x); }
 double orc_cr_cos(double x) { return CrCos(x); }
 double orc_root(int32_t n, double x) { return Root(n, x); }

@@ -30,6 +30,7 @@ _SYMBOLS = [
     ('orc_hermite3', None,
      [_d, _d, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp, _dp]),
     ('orc_harmonic_damping', None, [_d, _d, _d, _d, _dp, _dp, _dp]),
+    ('orc_double_precision', None, [_i32, _dp, _dp, _dp]),
     ('orc_kat_adaptive_oscillator_max_steps', _i32,
      [_d, _d, _d, _d, _d, _d, _d, _d, _i64, _i64p, _i64p, _i64p, _i64p, _dp]),
     ('orc_cr_sin', _d, [_d]),

@@ -447,6 +447,70 @@ def test_geopotential_potential_against_acceleration_on_the_reference_sample():
   assert low < 3.5e-9 and high > 8.2e-6, (low, high)
 
 
+def _dp(op, a, b=(0.0, 0.0)):
+  a = np.array(a if np.ndim(a) else [a, 0.0], dtype=np.float64)
+  b = np.array(b if np.ndim(b) else [b, 0.0], dtype=np.float64)
+  out = np.zeros(2)
+  oracle_lib.library().orc_double_precision(op, oracle_lib.dptr(a),
+                                            oracle_lib.dptr(b),
+                                            oracle_lib.dptr(out))
+  return (out[0], out[1])
+
+
+# numerics/double_precision_test.cpp:94-108,133-224: the
+# compensated summation of the steppers, all Eq / AlmostEquals(·, 0).
+def test_double_precision_known_answers():
+  INCREMENT, TWO_SUM, QUICK_TWO_SUM, TWO_DIFFERENCE, ADD, SUBTRACT = range(6)
+  eps = np.finfo(np.float64).eps
+  # CompensatedSummationIncrement / Decrement (Decrement is Increment of the
+  # opposite: error - right = error + (-right)).
+  for sign, expected in ((+1, 1 + eps), (-1, 1 - eps)):
+    accumulator = (1.0, 0.0)
+    for i in range(4):
+      accumulator = _dp(INCREMENT, accumulator, sign * eps / 4)
+      if i < (2 if sign > 0 else 1):
+        assert accumulator[0] == 1.0
+    assert accumulator == (expected, 0.0)
+  # IllConditionedCompensatedSummationIncrement / Decrement.
+  x = 1 + eps
+  for sign in (+1, -1):
+    for cancellation in (True, False):
+      y = eps * x if cancellation else math.pi * x
+      accumulator = (0.0, 0.0)
+      for term in (+x, -y, +x, -y, -x, +y, -x, +y):
+        accumulator = _dp(INCREMENT, accumulator, sign * term)
+      assert accumulator == ((sign * eps * eps) if cancellation else 0.0, 0.0)
+  # LongAdd.
+  for cancellation in (True, False):
+    y = eps * x if cancellation else math.pi * x
+    accumulator = (0.0, 0.0)
+    accumulator = _dp(ADD, accumulator, _dp(TWO_SUM, +x, -y))
+    accumulator = _dp(SUBTRACT, accumulator, _dp(TWO_SUM, -x, +y))
+    accumulator = _dp(SUBTRACT, accumulator, _dp(TWO_SUM, +x, -y))
+    accumulator = _dp(ADD, accumulator, _dp(TWO_SUM, -x, +y))
+    assert accumulator == (0.0, 0.0)
+  # LongAddPositions, coordinate by coordinate.
+  for value, error, expected in ((1.0, eps / 4, 1 + eps),
+                                 (2.0, eps / 2, 2 + 2 * eps),
+                                 (3.0, eps / 2, 3 + 2 * eps)):
+    delta = _dp(TWO_SUM, error, value)
+    assert delta == (value, error)
+    accumulator = (0.0, 0.0)
+    for i in range(4):
+      accumulator = _dp(ADD, accumulator, delta)
+    for i in range(3):
+      accumulator = _dp(SUBTRACT, accumulator, (value, 0.0))
+    assert _dp(SUBTRACT, accumulator, (0.0, 0.0)) == (expected, 0.0)
+  # QuickTwoSumSuccess: QuickTwoSum equals TwoSum when |a| >= |b| (and for the
+  # exceptions the reference lists: zeros, equal magnitudes).
+  for biggish, smallish in ((1.0, eps), (1.0, -eps / 3), (-2.5, 1.0), (0.0, 0.0),
+                            (1.0, -1.0), (3.0, 0.0), (1e300, 1e280)):
+    assert _dp(QUICK_TWO_SUM, biggish, smallish) == _dp(TWO_SUM, biggish,
+                                                        smallish)
+  # TwoDifference(a, b) is TwoSum(a, -b).
+  assert _dp(TWO_DIFFERENCE, 1.0, eps / 3) == _dp(TWO_SUM, 1.0, -eps / 3)
+
+
 # physics/harmonic_damping_test.cpp:27-70 (AccelerationQuantities), all Eq.
 def test_harmonic_damping_known_answers():
   lib = oracle_lib.library()
