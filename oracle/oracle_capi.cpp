@@ -565,6 +565,53 @@ int32_t orc_newhall_fixed_degree(int32_t degree, double const* q,
   return kOk;
 }
 
+// ContinuousTrajectoryTest.BestNewhallApproximation,
+// physics/continuous_trajectory_test.cpp:234-441: ComputeBestNewhallApproximation
+// driven by scripted error estimates.  calls[c] fits are consumed by call c,
+// in order: the degree each fit must be asked for and the estimate it yields.
+// After each call: degree_, adjusted_tolerance_, is_unstable_; `reset_after[c]`
+// applies ResetBestNewhallApproximation.  Returns 0, or 1 + the index of the
+// first fit requested out of script.
+int32_t orc_kat_best_newhall(double step, double tolerance, int32_t n_calls,
+                             int32_t const* fits_per_call,
+                             int32_t const* scripted_degrees,
+                             double const* scripted_estimates,
+                             int32_t const* reset_after, int32_t* degrees,
+                             double* adjusted_tolerances,
+                             int32_t* is_unstable, int32_t* statuses) {
+  ContinuousTrajectory trajectory(step, tolerance);
+  trajectory.Append(0.0, Vec3{}, Vec3{});
+  int32_t next = 0;
+  int32_t limit = 0;
+  int32_t mismatch = 0;
+  trajectory.mock_error_estimate = [&](int const degree) {
+    if (mismatch == 0 && (next >= limit || scripted_degrees[next] != degree)) {
+      mismatch = 1 + next;
+    }
+    Vec3 const estimate{scripted_estimates[3 * next],
+                        scripted_estimates[3 * next + 1],
+                        scripted_estimates[3 * next + 2]};
+    ++next;
+    return estimate;
+  };
+  double t = 0.0;
+  for (int32_t c = 0; c < n_calls; ++c) {
+    limit = next + fits_per_call[c];
+    t += step;
+    statuses[c] = trajectory.ComputeBestNewhallApproximation(t, {});
+    if (mismatch == 0 && next != limit) {
+      mismatch = 1 + next;
+    }
+    degrees[c] = trajectory.degree();
+    adjusted_tolerances[c] = trajectory.adjusted_tolerance();
+    is_unstable[c] = trajectory.is_unstable() ? 1 : 0;
+    if (reset_after[c] != 0) {
+      trajectory.ResetBestNewhallApproximation();
+    }
+  }
+  return mismatch;
+}
+
 // A ContinuousTrajectory of its own (physics/continuous_trajectory_body.hpp):
 // Append, t_min / t_max, EvaluatePosition / EvaluateVelocity.
 struct orc_continuous_trajectory {

@@ -11,6 +11,7 @@
 #include <memory>
 #include <queue>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "generated_tables.h"
@@ -772,6 +773,21 @@ class ContinuousTrajectory {
     }
     double const t_min = last_points_.front().time;
     Vec3 displacement_error_estimate;
+    // The reference's tests replace the fit by a mock that scripts the error
+    // estimates (continuous_trajectory_test.cpp:60-110).
+    auto const Newhall = [this](int const degree,
+                                std::vector<std::pair<Vec3, Vec3>> const& qvs,
+                                double const t_min, double const t_max,
+                                Vec3& error_estimate) {
+      if (mock_error_estimate) {
+        error_estimate = mock_error_estimate(degree);
+        Segment s{};
+        s.t_max = t_max;
+        s.degree = degree;
+        return s;
+      }
+      return this->Newhall(degree, qvs, t_min, t_max, error_estimate);
+    };
     segments_.push_back(
         Newhall(degree_, all, t_min, time, displacement_error_estimate));
 
@@ -813,6 +829,16 @@ class ContinuousTrajectory {
     }
   }
 
+  // Testing hooks (TestableContinuousTrajectory of the reference's tests).
+  std::function<Vec3(int degree)> mock_error_estimate;
+  int degree() const { return degree_; }
+  double adjusted_tolerance() const { return adjusted_tolerance_; }
+  bool is_unstable() const { return is_unstable_; }
+  void ResetBestNewhallApproximation() {
+    degree_age_ = std::numeric_limits<int>::max();
+  }
+
+ private:
   double step_;
   double tolerance_;
   double adjusted_tolerance_;

@@ -1089,6 +1089,63 @@ def fill_trajectory(orc, number_of_steps, step, position, velocity, t0,
   return trajectory
 
 
+# physics/continuous_trajectory_test.cpp:234-441 (BestNewhallApproximation): the
+# degree selection of ComputeBestNewhallApproximation -- what NewhallFitKernel
+# runs on the device -- driven by the reference's scripted error estimates.
+def test_best_newhall_approximation_state_machine():
+  low = (0.1, 0.1, 0.1)
+  # (fits [(degree, estimate)], reset after, expected degree, adjusted
+  # tolerance, is_unstable).
+  calls = [
+      # The errors smoothly decrease.
+      ([(3, (3, 4, 5)), (4, (2, 1, 2)), (5, (0.1, 2, 0)),
+        (6, (0.5, 0.5, 0.1))], True, 6, 1.0, False),
+      # The errors increase before the tolerance is reached...
+      ([(3, (3, 4, 5)), (4, (2, 1, 2)), (5, (0.1, 2, 0)), (6, (1, 3, 1))],
+       False, 5, math.sqrt(4.01), True),
+      # ... then the error decreases...
+      ([(5, (0.1, 1.5, 0))], False, 5, math.sqrt(4.01), True),
+      # ... then it increases, back to square one...
+      ([(5, (0.1, 2, 0.5)), (3, (3, 4, 5)), (4, (2, 1, 2)), (5, (1, 2, 1)),
+        (6, (1, 1.5, 1)), (7, (1, 1.2, 1)), (8, (1, 1.3, 1))], False, 7,
+       math.sqrt(3.44), True),
+      # ... again, but then the computation becomes stable.
+      ([(7, (1, 1.3, 1)), (3, (3, 4, 5)), (4, (0.1, 0.5, 0.2))], True, 4, 1.0,
+       False),
+      # The errors force degree 6...
+      ([(3, (3, 3, 3)), (4, (2, 2, 2)), (5, (1, 1, 1)), (6, low)], False, 6,
+       1.0, False),
+  ]
+  # ... low errors for a long time...
+  calls += [([(6, low)], False, 6, 1.0, False)] * 99
+  # ... then all the degrees are tried again (max_degree_age) and 5 works.
+  calls += [([(3, (3, 3, 3)), (4, (2, 2, 2)), (5, (0.2, 0.2, 0.2))], True, 5,
+             1.0, False)]
+  fits_per_call = np.array([len(c[0]) for c in calls], dtype=np.int32)
+  scripted_degrees = np.array([d for c in calls for d, _ in c[0]],
+                              dtype=np.int32)
+  scripted_estimates = np.array([e for c in calls for _, e in c[0]],
+                                dtype=np.float64)
+  reset_after = np.array([int(c[1]) for c in calls], dtype=np.int32)
+  n = len(calls)
+  degrees = np.zeros(n, dtype=np.int32)
+  tolerances = np.zeros(n)
+  unstable = np.zeros(n, dtype=np.int32)
+  statuses = np.zeros(n, dtype=np.int32)
+  i32p = lambda a: a.ctypes.data_as(_capi.c_int32_p)
+  mismatch = oracle_lib.library().orc_kat_best_newhall(
+      1.0, 1.0, n, i32p(fits_per_call), i32p(scripted_degrees),
+      oracle_lib.dptr(scripted_estimates), i32p(reset_after), i32p(degrees),
+      oracle_lib.dptr(tolerances), i32p(unstable), i32p(statuses))
+  # Every fit was requested at the scripted degree, in the scripted order.
+  assert mismatch == 0
+  assert not statuses.any()
+  for c, (_, _, degree, tolerance, is_unstable) in enumerate(calls):
+    assert degrees[c] == degree, c
+    assert tolerances[c] == tolerance, c  # EXPECT_EQ.
+    assert bool(unstable[c]) == is_unstable, c
+
+
 # physics/continuous_trajectory_test.cpp:443-488: a trajectory defined by a
 # degree-1 polynomial is reproduced within 11 ULPs (positions) and 4 ULPs
 # (velocities).
