@@ -458,6 +458,11 @@ double orc_estrin(double const* coefficients, int32_t degree, double x) {
   return EstrinEvaluate(coefficients, 1, 0, degree, x);
 }
 
+double orc_estrin_derivative(double const* coefficients, int32_t degree,
+                             double x) {
+  return EstrinEvaluateDerivative(coefficients, 1, 1, degree - 1, x);
+}
+
 // Чебышёв series (numerics/polynomial_in_чебышёв_basis_body.hpp:151-202).
 double orc_chebyshev_evaluate(double const* coefficients, int32_t degree,
                               double lower_bound, double upper_bound,

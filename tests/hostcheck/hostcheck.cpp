@@ -26,6 +26,9 @@ double hc_cr_root4(double x) { return CrRoot4(x); }
 double hc_estrin(double const* c, int32_t degree, double x) {
   return EstrinEvaluate<1>(c, degree, x);
 }
+double hc_estrin_derivative(double const* c, int32_t degree, double x) {
+  return EstrinEvaluateDerivative<1>(c, degree, x);
+}
 double hc_pow_int(double x, int32_t k) { return PowInt(x, k); }
 
 // DownsamplerAppend on one trajectory (q, v: [n_points][3]); returns the size

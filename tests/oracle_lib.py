@@ -39,6 +39,7 @@ _SYMBOLS = [
     ('orc_cr_cos', _d, [_d]),
     ('orc_root', _d, [_i32, _d]),
     ('orc_estrin', _d, [_dp, _i32, _d]),
+    ('orc_estrin_derivative', _d, [_dp, _i32, _d]),
     ('orc_downsample', _i64,
      [_i64, _dp, _dp, _dp, _d, _dp, _dp, _dp, _dp, _i64, _dp, _dp, _dp]),
     ('orc_continuous_trajectory_create', _vp, [_d, _d]),

@@ -35,6 +35,8 @@ def hc():
   lib.hc_cr_root4.argtypes = [_d]
   lib.hc_estrin.restype = _d
   lib.hc_estrin.argtypes = [_dp, _i32, _d]
+  lib.hc_estrin_derivative.restype = _d
+  lib.hc_estrin_derivative.argtypes = [_dp, _i32, _d]
   lib.hc_estrin_padded.argtypes = [_dp, _i32, _d, _d, _dp, _dp]
   lib.hc_chebyshev.argtypes = [_dp, _i32, _d, _d, _d, _dp, _dp]
   lib.hc_downsample.restype = ctypes.c_int64
@@ -102,6 +104,38 @@ def test_estrin_matches_oracle(hc):
       y2 = y * y
       return y2 * x if e % 2 else y2
     assert hc.hc_pow_int(x, k) == peasant(x, k)
+
+
+# numerics/polynomial_evaluators_test.cpp:26-67 (PolynomialEvaluatorTest.Estrin):
+# (x + 1)^degree from its binomial coefficients at the integers of
+# [-degree, degree], value and derivative, EXPECT_EQ -- the oracle and the host
+# build of the device header.
+def test_estrin_binomial_known_answers(hc):
+  orc = oracle_lib.library()
+  for degree in range(1, 15):
+    c = np.zeros(18)
+    c[:degree + 1] = [math.comb(degree, k) for k in range(degree + 1)]
+    for argument in range(-degree, degree + 1):
+      x = float(argument)
+      value = float((argument + 1)**degree)
+      derivative = float(degree * (argument + 1)**(degree - 1))
+      assert orc.orc_estrin(oracle_lib.dptr(c), degree, x) == value
+      assert orc.orc_estrin_derivative(oracle_lib.dptr(c), degree,
+                                       x) == derivative
+      assert hc.hc_estrin(oracle_lib.dptr(c), degree, x) == value
+      assert hc.hc_estrin_derivative(oracle_lib.dptr(c), degree,
+                                     x) == derivative
+
+
+def test_estrin_derivative_matches_oracle(hc):
+  orc = oracle_lib.library()
+  rng = np.random.default_rng(4)
+  for degree in range(0, 18):
+    for _ in range(200):
+      c = rng.normal(size=18) * 10.0**rng.uniform(-5, 5, 18)
+      x = rng.uniform(-3000, 3000)
+      assert (hc.hc_estrin_derivative(oracle_lib.dptr(c), degree, x) ==
+              orc.orc_estrin_derivative(oracle_lib.dptr(c), degree, x))
 
 
 def test_chebyshev_series_match_oracle(hc):
