@@ -38,6 +38,8 @@ int32_t ft_prolong(void* e, double t) {
 }
 
 double ft_t_max(void* e) { return static_cast<Ephemeris*>(e)->t_max(); }
+double ft_t_min(void* e) { return static_cast<Ephemeris*>(e)->t_min(); }
+int32_t ft_empty(void* e) { return static_cast<Ephemeris*>(e)->empty() ? 1 : 0; }
 
 int32_t ft_segment_count(void* e, int32_t body) {
   return static_cast<int32_t>(

@@ -39,6 +39,9 @@ def shim():
   lib.ft_prolong.argtypes = [_vp, _d]
   lib.ft_t_max.restype = _d
   lib.ft_t_max.argtypes = [_vp]
+  lib.ft_t_min.restype = _d
+  lib.ft_t_min.argtypes = [_vp]
+  lib.ft_empty.argtypes = [_vp]
   lib.ft_segment_count.argtypes = [_vp, _i32]
   lib.ft_get_segments.argtypes = [_vp, _i32, _dp, _dp, _i32p, _dp]
   lib.ft_flow_with_fixed_step.argtypes = [_vp, _i32, _dp, _dp, _d, _i32, _d,
@@ -222,4 +225,60 @@ def test_facade_prolongs_the_reference_earth_moon_system(shim, sol_system,
     valid = np.arange(18)[None, :, None] <= degree[:, None, None]
     assert_bitwise_equal(np.where(valid, coefficients, 0.0),
                          np.where(valid, expected['coefficients'], 0.0))
+  shim.ft_destroy(handle)
+
+
+@pytest.mark.parametrize('integrator', [
+    _capi.MCLACHLAN_ATELA_1992_ORDER_5_OPTIMAL, _capi.QUINLAN_1999_ORDER_8A])
+def test_facade_special_cases_of_the_reference(shim, sol_system, integrator):
+  """EphemerisTest.ProlongSpecialCases and .FlowWithAdaptiveStepSpecialCase
+  (physics/ephemeris_test.cpp:180-266) through the facade."""
+  import earth_probe
+  system, positions, velocities, _, period = earth_probe.set_up_earth_moon(
+      sol_system)
+  t0 = earth_probe.T0
+  bodies, keep = system.c_bodies()
+  q0 = np.ascontiguousarray(positions)
+  v0 = np.ascontiguousarray(velocities)
+  handle = shim.ft_create(len(system.bodies), bodies, oracle_lib.dptr(q0),
+                          oracle_lib.dptr(v0), t0, 5e-3, 2.0**-24, integrator,
+                          period / 100)
+  assert handle
+  # ProlongSpecialCases.
+  assert shim.ft_t_max(handle) == -np.inf  # InfinitePast.
+  assert shim.ft_t_min(handle) == np.inf   # InfiniteFuture.
+  assert shim.ft_empty(handle) == 1
+  assert shim.ft_prolong(handle, t0 + period) == 0
+  assert shim.ft_empty(handle) == 0
+  assert shim.ft_t_min(handle) == t0
+  t_max = shim.ft_t_max(handle)
+  assert t0 + period <= t_max
+  assert shim.ft_prolong(handle, t0 + period / 2) == 0
+  assert shim.ft_t_max(handle) == t_max
+  last_t = ((t0 + period) + t_max) / 2
+  shim.ft_prolong(handle, last_t)
+  assert shim.ft_t_max(handle) == t_max
+  # FlowWithAdaptiveStepSpecialCase: a probe 10^9 m from the Earth flowed over a
+  # period, then "flowed" to the time it is already at.
+  q = positions[0] + np.array([0.0, 1e9, 0.0])
+  v = np.array([1e3, 1e3, 1e3])
+  capacity = 32768
+  count = ctypes.c_int64()
+  times = np.zeros(capacity)
+  dofs = np.zeros((capacity, 6))
+  assert shim.ft_flow_with_adaptive_step(
+      handle, oracle_lib.dptr(q), oracle_lib.dptr(v), t0, t0 + period, 1e-9,
+      2.6e-15, 2**62, capacity, ctypes.byref(count), oracle_lib.dptr(times),
+      oracle_lib.dptr(dofs)) == 0
+  assert 0 < count.value <= capacity
+  back_time = times[count.value - 1]
+  assert back_time == t0 + period
+  back_q = np.ascontiguousarray(dofs[count.value - 1, 0:3])
+  back_v = np.ascontiguousarray(dofs[count.value - 1, 3:6])
+  again = ctypes.c_int64(-1)
+  assert shim.ft_flow_with_adaptive_step(
+      handle, oracle_lib.dptr(back_q), oracle_lib.dptr(back_v), back_time,
+      back_time, 1e-9, 2.6e-15, 2**62, capacity, ctypes.byref(again),
+      oracle_lib.dptr(times), oracle_lib.dptr(dofs)) == 0
+  assert again.value == 0
   shim.ft_destroy(handle)
