@@ -1472,3 +1472,58 @@ def test_oscillator_termination(instance):
     assert solution['evaluations'] == steps * evaluations
   for i, t in enumerate(solution['times']):
     assert t == (i + 1) * 42.0  # AlmostEquals(..., 0).
+
+
+# physics/body_test.cpp:350-414 (BodyTest.SolarNoon): the Sol ephemeris
+# (QuinlanTremaine1990Order12 at 10 min, fitting tolerance 5 mm) prolonged to
+# October 2010, the Earth's rotation (FromSurfaceFrame) and the Earth-Sun
+# direction give the solar noons at Greenwich and Istanbul.  UTC - TT is
+# -64.184 s in 2000 and -66.184 s in 2010 (astronomy/time_scales).
+def test_solar_noon():
+  import datetime
+  system = SolarSystem.from_fixture('sol_jd2451545')
+  oracle = OracleEphemeris(system, fitting_tolerance=5e-3)
+  j2000 = datetime.datetime(2000, 1, 1, 12)
+
+  def utc(year, month, day, hour=0, minute=0):
+    offset = 64.184 if year < 2006 else 66.184
+    return (datetime.datetime(year, month, day, hour, minute) -
+            j2000).total_seconds() + offset
+
+  assert oracle.prolong(utc(2010, 10, 1, 12)) == 0
+  earth, sun = system.index('Earth'), system.index('Sun')
+
+  def to_cartesian(latitude, longitude):  # SphericalCoordinates::ToCartesian.
+    latitude, longitude = math.radians(latitude), math.radians(longitude)
+    return np.array([math.cos(longitude) * math.cos(latitude),
+                     math.sin(longitude) * math.cos(latitude),
+                     math.sin(latitude)])
+
+  def solar_noon(location, a, b):
+    def oriented(t):  # The sign of OrientedAngleBetween(earth_sun, location, z).
+      positions = oracle.evaluate_all_positions(t)
+      earth_sun = positions[sun] - positions[earth]
+      w = oracle.surface_frame_rotate(earth, t, location)
+      z = oracle.surface_frame_rotate(earth, t, [0.0, 0.0, 1.0])
+      return np.dot(np.cross(earth_sun, w), z)
+    fa = oriented(a)
+    assert fa * oriented(b) < 0
+    while b - a > 1e-7:
+      m = 0.5 * (a + b)
+      fm = oriented(m)
+      if fa * fm <= 0:
+        b = m
+      else:
+        a, fa = m, fm
+    return 0.5 * (a + b)
+
+  greenwich = to_cartesian(51.4826, -0.0077)
+  istanbul = to_cartesian(41.0082, 28.9784)
+  noon = solar_noon(greenwich, utc(2000, 1, 2, 8), utc(2000, 1, 2, 16))
+  assert is_near(noon - utc(2000, 1, 2, 12, 4), -15e-3)   # -15(1) ms.
+  noon = solar_noon(greenwich, utc(2010, 9, 30, 8), utc(2010, 9, 30, 16))
+  assert is_near(noon - utc(2010, 9, 30, 11, 51), -58.0)  # -58(1) s.
+  noon = solar_noon(istanbul, utc(2000, 1, 2, 8), utc(2000, 1, 2, 16))
+  assert is_near(noon - utc(2000, 1, 2, 10, 8), 1.05, digits=3)
+  noon = solar_noon(istanbul, utc(2010, 9, 30, 8), utc(2010, 9, 30, 16))
+  assert is_near(noon - utc(2010, 9, 30, 9, 55), -53.0)   # -53(1) s.
