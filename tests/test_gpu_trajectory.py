@@ -195,3 +195,38 @@ def test_capacity_overflow_is_reported():
   counts, kept_times, _, _ = downsampler.timelines()
   assert counts[0] == 1001
   assert_bitwise_equal(kept_times[:, 0], times)
+
+
+def test_reference_evaluate_on_the_device():
+  """physics/discrete_trajectory_segment_test.cpp:224-250 (Evaluate) through
+  pb_downsampler_evaluate: 1001 points on a circle, no downsampling, evaluated
+  every millisecond: errors 4.2(1) nm and 10.4(1) nm/s, and the oracle's bits."""
+  from test_oracle_kats import is_near
+  times, q, v = trajectory_factories.circular_timeline(3.0, 2.0, 10e-3, 0.0,
+                                                       10.0)
+  samples = np.zeros((len(times), 6, 1))
+  samples[:, 0:3, 0] = q
+  samples[:, 3:6, 0] = v
+  downsampler = Downsampler(1, -1.0, 1001)
+  downsampler.append(times, samples)
+  counts, _, _, _ = downsampler.timelines()
+  assert list(counts) == [1001]
+  evaluation_times = []
+  t = times[0]
+  while t <= times[-1]:
+    evaluation_times.append(t)
+    t += 1e-3
+  expected = oracle_downsample(times, q, v, -1.0, np.array(evaluation_times))
+  position_error = velocity_error = 0.0
+  for j, t in enumerate(evaluation_times):
+    eq, ev, in_range = downsampler.evaluate(t)
+    assert in_range.all()
+    if j % 7 == 0:
+      assert_bitwise_equal(eq[:, 0], expected['evaluated_q'][j])
+      assert_bitwise_equal(ev[:, 0], expected['evaluated_v'][j])
+    position_error = max(position_error,
+                         abs(np.linalg.norm(eq[:, 0]) - 2.0))
+    velocity_error = max(velocity_error,
+                         abs(np.linalg.norm(ev[:, 0]) - 6.0))
+  assert is_near(position_error, 4.2e-9)
+  assert is_near(velocity_error, 10.4e-9, digits=3)

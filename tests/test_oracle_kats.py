@@ -1527,3 +1527,48 @@ def test_solar_noon():
   assert is_near(noon - utc(2000, 1, 2, 10, 8), 1.05, digits=3)
   noon = solar_noon(istanbul, utc(2010, 9, 30, 8), utc(2010, 9, 30, 16))
   assert is_near(noon - utc(2010, 9, 30, 9, 55), -53.0)   # -53(1) s.
+
+
+# physics/discrete_trajectory_segment_test.cpp:224-250 (Evaluate): 1001 points
+# on a circle, no downsampling, the Hermite interpolation evaluated every
+# millisecond: errors 4.2(1) nm and 10.4(1) nm/s.
+def test_discrete_trajectory_evaluate():
+  import trajectory_factories
+  times, q, v = trajectory_factories.circular_timeline(3.0, 2.0, 10e-3, 0.0,
+                                                       10.0)
+  assert len(times) == 1001
+  evaluation_times = []
+  t = times[0]
+  while t <= times[-1]:
+    evaluation_times.append(t)
+    t += 1e-3
+  result = oracle_downsample(times, q, v, -1.0, np.array(evaluation_times))
+  assert len(result['times']) == 1001
+  position_errors = np.abs(
+      np.linalg.norm(result['evaluated_q'], axis=1) - 2.0)
+  velocity_errors = np.abs(
+      np.linalg.norm(result['evaluated_v'], axis=1) - 2.0 * 3.0)
+  assert is_near(position_errors.max(), 4.2e-9)
+  assert is_near(velocity_errors.max(), 10.4e-9, digits=3)
+
+
+# numerics/newhall_test.cpp:799-815 (NonConstantDegree): the degree-10 fit of
+# the first test function reproduces it at t_min within 9(1)e-13, relative.
+def test_newhall_non_constant_degree():
+  t_min, t_max = -1.0, 3.0
+  length = lambda t: 0.5 + 2 * math.sin((t - t_min) / 0.3) * math.exp(
+      (t - t_min) / 1)
+  speed = lambda t: ((2 / 0.3) * math.cos((t - t_min) / 0.3) + 2 * math.sin(
+      (t - t_min) / 0.3)) * math.exp((t - t_min) / 1)
+  nodes = [t_min + 0.5 * i for i in range(9)]
+  q = np.array([length(t) for t in nodes])
+  v = np.array([speed(t) for t in nodes])
+  times = np.array([t_min])
+  values, derivatives = np.zeros(1), np.zeros(1)
+  estimate = ctypes.c_double()
+  dptr = oracle_lib.dptr
+  assert oracle_lib.library().orc_newhall_fixed_degree(
+      10, dptr(q), dptr(v), t_min, t_max, ctypes.byref(estimate), 1,
+      dptr(times), dptr(values), dptr(derivatives)) == 0
+  relative_error = abs(values[0] - length(t_min)) / abs(length(t_min))
+  assert is_near(relative_error, 9e-13, digits=1)
