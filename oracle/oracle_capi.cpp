@@ -726,6 +726,24 @@ int32_t orc_geopotential_damping(orc_ephemeris const* e, int32_t body,
 }
 
 // Geopotential::GeneralSphericalHarmonicsAcceleration on one displacement.
+// Geopotential::GeneralSphericalHarmonicsAcceleration with every argument
+// given by the caller (physics/geopotential_test.cpp:651-656 passes r, r * r
+// and 1 / Pow<3>(r) for the vector r * direction).
+int32_t orc_geopotential_acceleration_explicit(orc_ephemeris const* e,
+                                               int32_t body, double t,
+                                               double const* r, double r_norm,
+                                               double r2, double one_over_r3,
+                                               double* out) {
+  int const internal = e->internal_of_caller[body];
+  Vec3 const a =
+      e->e->geopotential(internal).GeneralSphericalHarmonicsAcceleration(
+          t, {r[0], r[1], r[2]}, r_norm, r2, one_over_r3);
+  out[0] = a.x;
+  out[1] = a.y;
+  out[2] = a.z;
+  return kOk;
+}
+
 // Geopotential::GeneralSphericalHarmonicsPotential with the arguments the
 // reference's tests form (physics/geopotential_test.cpp:109-119).
 double orc_geopotential_potential(orc_ephemeris const* e, int32_t body, double t,

@@ -71,6 +71,8 @@ _SYMBOLS = [
     ('orc_geopotential_damping', _i32, [_vp, _i32, _i32p, _dp, _dp]),
     ('orc_geopotential_acceleration', _i32, [_vp, _i32, _d, _dp, _dp]),
     ('orc_surface_frame_rotate', _i32, [_vp, _i32, _d, _i32, _dp, _dp]),
+    ('orc_geopotential_acceleration_explicit', _i32,
+     [_vp, _i32, _d, _dp, _d, _d, _d, _dp]),
     ('orc_geopotential_potential', _d, [_vp, _i32, _d, _dp]),
     ('orc_ephemeris_prolong', _i32, [_vp, _d]),
     ('orc_ephemeris_instance_state', _i32, [_vp, _dp, _dp, _dp]),
@@ -178,6 +180,14 @@ class OracleEphemeris:
   def geopotential_potential(self, body, t, r):
     r = np.ascontiguousarray(r, dtype=np.float64)
     return self.lib.orc_geopotential_potential(self.handle, body, t, dptr(r))
+
+  def geopotential_acceleration_explicit(self, body, t, r, r_norm, r2,
+                                         one_over_r3):
+    r = np.ascontiguousarray(r, dtype=np.float64)
+    out = np.zeros(3)
+    self.lib.orc_geopotential_acceleration_explicit(
+        self.handle, body, t, dptr(r), r_norm, r2, one_over_r3, dptr(out))
+    return out
 
   def surface_frame_rotate(self, body, t, v, inverse=False):
     v = np.ascontiguousarray(v, dtype=np.float64)

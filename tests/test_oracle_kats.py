@@ -396,6 +396,100 @@ def test_geopotential_j3():
   assert a[2] < 0
 
 
+# physics/geopotential_test.cpp:562-800 (GeopotentialTest.DampedForces): the
+# full Earth with tolerance 2^-24 against its undamped parts (tolerance 0) at
+# the midpoints of the sigmoids, ULP windows.
+def test_geopotential_damped_forces():
+  def variant(keep, tolerance):
+    system = _test_earth(10)
+    earth = system.bodies[0]
+    for n in range(earth['degree'] + 1):
+      for m in range(n + 1):
+        if not keep(n, m):
+          earth['cos'][n * (n + 1) // 2 + m] = 0.0
+          earth['sin'][n * (n + 1) // 2 + m] = 0.0
+    # OblateBody::Parameters::ReadFromMessage, oblate_body_body.hpp:88-97.
+    earth['zonal'] = all(
+        earth['cos'][n * (n + 1) // 2 + m] == 0 and
+        earth['sin'][n * (n + 1) // 2 + m] == 0
+        for n in range(earth['degree'] + 1) for m in range(1, n + 1))
+    return OracleEphemeris(system, geopotential_tolerance=tolerance)
+
+  earth = variant(lambda n, m: True, 2.0**-24)
+  degree = {n: variant(lambda k, m, n=n: k == n, 0.0) for n in (2, 3)}
+  j2 = variant(lambda n, m: n == 2 and m == 0, 0.0)
+  c22_s22 = variant(lambda n, m: n == 2 and m != 0, 0.0)
+
+  norm = math.sqrt(1.0 * 1.0 + 2.0 * 2.0 + 5.0 * 5.0)
+  direction = np.array([1.0, 2.0, 5.0]) / norm
+  down = -direction
+
+  def acceleration(geopotential, r):
+    return geopotential.geopotential_acceleration_explicit(
+        0, 0.0, r * direction, r, r * r, 1 / (r * r * r))
+
+  def dot(a, b):
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+
+  def radial(geopotential, r):
+    return dot(acceleration(geopotential, r), down)
+
+  def latitudinal(geopotential, r):
+    north = np.array([0.0, 0.0, 1.0])
+    normalized = direction / math.sqrt(dot(direction, direction))
+    local_north = north - dot(north, normalized) * normalized
+    return dot(acceleration(geopotential, r), local_north)
+
+  def longitudinal(geopotential, r):
+    north = np.array([0.0, 0.0, 1.0])
+    local_east = np.array([down[1] * north[2] - down[2] * north[1],
+                           down[2] * north[0] - down[0] * north[2],
+                           down[0] * north[1] - down[1] * north[0]])
+    return dot(acceleration(geopotential, r), local_east)
+
+  def within(actual, expected, low, high):
+    return low <= ulp_distance(actual, expected) <= high
+
+  inner, sectoral_inner = earth.damping(0)
+  # Above the outer threshold for J2.
+  assert np.linalg.norm(acceleration(earth, 5e12)) == 0
+  # The J2 sigmoid.
+  s0, s1 = inner[2], 3 * inner[2]
+  assert is_near(s0, 1.5e9) and is_near(s1, 4.5e9)
+  mid = (s0 + s1) / 2
+  assert within(radial(earth, mid) / radial(j2, mid), 1.0, 0, 0)
+  harmonic = 2 * s0 * s1 / (s0 + s1)
+  assert within(radial(earth, harmonic) / radial(j2, harmonic), 1.125, 0, 2)
+  assert within(latitudinal(earth, mid) / latitudinal(j2, mid), 0.5, 0, 2)
+  # Below the inner threshold for J2, above all other outer thresholds.
+  assert inner[2] > 1e9 and 3 * sectoral_inner < 1e9 and 3 * inner[3] < 1e9
+  assert np.array_equal(acceleration(earth, 1e9), acceleration(j2, 1e9))
+  # The C22 / S22 sigmoid.
+  s0, s1 = sectoral_inner, 3 * sectoral_inner
+  assert is_near(s0, 105e6, digits=3) and is_near(s1, 317e6, digits=3)
+  assert s0 < 3 * inner[3] < (s0 + s1) / 2
+  mid = (s0 + s1) / 2
+  assert within((radial(earth, mid) - radial(j2, mid)) / radial(c22_s22, mid),
+                1.0, 111, 1142)
+  assert within((latitudinal(earth, mid) - latitudinal(j2, mid)) /
+                latitudinal(c22_s22, mid), 0.5, 920, 2781)
+  assert within(longitudinal(earth, mid) / longitudinal(c22_s22, mid), 0.5, 1,
+                114)
+  # The degree-3 sigmoid.
+  s0, s1 = inner[3], 3 * inner[3]
+  assert is_near(s0, 43e6) and is_near(s1, 129e6, digits=3)
+  assert s0 < 3 * inner[4] and s1 > sectoral_inner
+  mid = (s0 + s1) / 2
+  assert 3 * inner[4] < mid < sectoral_inner
+  assert within((radial(earth, mid) - radial(degree[2], mid)) /
+                radial(degree[3], mid), 0.875, 277, 3044)
+  assert within((latitudinal(earth, mid) - latitudinal(degree[2], mid)) /
+                latitudinal(degree[3], mid), 0.5, 26512, 46843)
+  assert within((longitudinal(earth, mid) - longitudinal(degree[2], mid)) /
+                longitudinal(degree[3], mid), 0.5, 342, 2130)
+  assert 3 * inner[5] > inner[3]
+
+
 # physics/geopotential_test.cpp:802-858 (GeopotentialTest.Potential): the
 # degree-9 Earth with tolerance 2^-24, potential against acceleration by finite
 # differences at the reference's own 1000 points; relative errors pinned in
