@@ -435,3 +435,45 @@ def test_geopotential_test_bodies_on_the_device(shape, tolerance):
     # included.
     a, _ = gpu.compute_gravitational_acceleration_on_massless_bodies(0.0, q)
     assert a[0, 1] / a[1, 1] == 0.75
+
+
+def test_sin_cos_hard_cases_on_the_device():
+  """numerics/sin_cos_test.cpp:363-413 (HardRounding, HardReduction within the
+  supported range): the device's correctly rounded sine and cosine on the
+  reference's hard-to-round arguments, AlmostEquals(·, 0)."""
+  sines = {
+      1.777288458404935767021016: 0.9787561457198967196367773,
+      5.528810471911395296729097: -0.6848332450871304488693046,
+      2.670333644894535396474566: 0.4540084183741445456039384,
+      -2.496680544289484160458414: -0.6011282027544306294509797,
+      3.348980952786005715893225: -0.2059048676737040700634683,
+      3.523452575387961971387085: -0.3726470704519433130297035,
+      1.881458091523454001503524: 0.9521314843257784876761001,
+      -1.763163156774038675678185: -0.9815544881044536151825223,
+      -2.58105062034143273308473: -0.5316453603071467637339815,
+      1.657419885978818285821035: 0.99625052493662308306103561,
+      5.094301519947547873812255: -0.9279535374988051033005616,
+      5.262137362438826571064965: -0.8526560125576488347044409,
+      float.fromhex('0x5ad7bcep-8'): 0.99999999999999999818,
+  }
+  cosines = {
+      3.912491942337291916942377: -0.7172843528140595004137653,
+      1.486604973422413600303571: 0.0840919279825555407437241,
+      -6.265702600230396157598989: 0.99984718137127853720984932,
+      -3.885819786017697730073905: -0.7356116652133562472394118,
+      -5.026994177012682030181168: 0.3094410694753661206223057,
+      0.2388111698570396512764091: 0.9716198764286143041422587,
+      float.fromhex('0x5ad7bcep-8'): 1.9060601347136373148e-9,
+  }
+  lib = _capi.library()
+  x = np.array(list(sines) + list(cosines))
+  n = len(x)
+  s, c, r = np.zeros(n), np.zeros(n), np.zeros(n)
+  f = lib.pb_internal_elementary_functions
+  f.argtypes = [ctypes.c_int32, ctypes.c_int64] + [_capi.c_double_p] * 4
+  assert f(0, n, oracle_lib.dptr(x), oracle_lib.dptr(s), oracle_lib.dptr(c),
+           oracle_lib.dptr(r)) == 0
+  for i, (argument, expected) in enumerate(sines.items()):
+    assert s[i] == expected, argument
+  for i, (argument, expected) in enumerate(cosines.items()):
+    assert c[len(sines) + i] == expected, argument

@@ -336,3 +336,47 @@ def test_std_mt19937_64():
   for _ in range(9999):
     random()
   assert random() == 9981545732273789042
+
+
+# numerics/sin_cos_test.cpp:363-413 (HardRounding, HardReduction): arguments
+# whose sine or cosine is hard to round, AlmostEquals(·, 0), for the oracle
+# (binary128) and the host build of the device's CrSinCos (|x| < 2^31 only).
+def test_sin_cos_hard_cases(hc):
+  orc = oracle_lib.library()
+  sin_cases = [
+      (1.777288458404935767021016, 0.9787561457198967196367773),
+      (5.528810471911395296729097, -0.6848332450871304488693046),
+      (2.670333644894535396474566, 0.4540084183741445456039384),
+      (-2.496680544289484160458414, -0.6011282027544306294509797),
+      (3.348980952786005715893225, -0.2059048676737040700634683),
+      (3.523452575387961971387085, -0.3726470704519433130297035),
+      (1.881458091523454001503524, 0.9521314843257784876761001),
+      (-1.763163156774038675678185, -0.9815544881044536151825223),
+      (-2.58105062034143273308473, -0.5316453603071467637339815),
+      (1.657419885978818285821035, 0.99625052493662308306103561),
+      (5.094301519947547873812255, -0.9279535374988051033005616),
+      (5.262137362438826571064965, -0.8526560125576488347044409),
+      (float.fromhex('0x5ad7bcep-8'), 0.99999999999999999818),
+  ]
+  cos_cases = [
+      (3.912491942337291916942377, -0.7172843528140595004137653),
+      (1.486604973422413600303571, 0.0840919279825555407437241),
+      (-6.265702600230396157598989, 0.99984718137127853720984932),
+      (-3.885819786017697730073905, -0.7356116652133562472394118),
+      (-5.026994177012682030181168, 0.3094410694753661206223057),
+      (0.2388111698570396512764091, 0.9716198764286143041422587),
+      (float.fromhex('0x5ad7bcep-8'), 1.9060601347136373148e-9),
+  ]
+  s, c = ctypes.c_double(), ctypes.c_double()
+  for x, expected in sin_cases:
+    assert orc.orc_cr_sin(x) == expected, x
+    hc.hc_cr_sincos(x, ctypes.byref(s), ctypes.byref(c))
+    assert s.value == expected, x
+  for x, expected in cos_cases:
+    assert orc.orc_cr_cos(x) == expected, x
+    hc.hc_cr_sincos(x, ctypes.byref(s), ctypes.byref(c))
+    assert c.value == expected, x
+  # Muller's bad angle (beyond the device's range).
+  muller = float.fromhex('0x16ac5b262ca1ffp797')
+  assert orc.orc_cr_sin(muller) == 1.0
+  assert orc.orc_cr_cos(muller) == -4.687165924254627611122582801963884e-19
