@@ -25,6 +25,11 @@ struct State {
 using RightHandSide = std::function<int32_t(
     double t, std::vector<double> const& q, std::vector<double>& g)>;
 using AppendState = std::function<void(State const&)>;
+// ExplicitSecondOrderOrdinaryDifferentialEquation: the right-hand side also
+// takes the velocities (integrators/ordinary_differential_equations.hpp).
+using GeneralizedRightHandSide = std::function<int32_t(
+    double t, std::vector<double> const& q, std::vector<double> const& v,
+    std::vector<double>& g)>;
 
 // ---------------------------------------------------------------------------
 // Tableaux, integrators/methods.hpp.
@@ -105,7 +110,12 @@ struct ErknMethod {
   std::vector<double> c;
   std::vector<double> a;  // Strictly lower triangular, (i, j) -> i(i-1)/2 + j.
   std::vector<double> b_hat, b_hat_prime, b, b_prime;
+  // The velocity stages of a *generalized* method (empty otherwise).
+  std::vector<double> a_prime;
   double A(int const i, int const j) const { return a[i * (i - 1) / 2 + j]; }
+  double APrime(int const i, int const j) const {
+    return a_prime[i * (i - 1) / 2 + j];
+  }
 };
 
 inline ErknMethod const& DormandElMikkawyPrince1986RKN434FM() {
@@ -146,6 +156,10 @@ inline ErknMethod const& Fine1987RKNG34() {
            1 / 36.0,   1 / 36.0,
            9 / 128.0,  0.0,        27 / 128.0,
            11 / 60.0,  -3 / 20.0,  9 / 25.0,  8 / 75.0};
+    m.a_prime = {2 / 9.0,
+                 1 / 12.0,     1 / 4.0,
+                 69 / 128.0,   -234 / 128.0,  135 / 64.0,
+                 -17 / 12.0,   27 / 4.0,      -27 / 5.0,   16 / 15.0};
     m.b_hat = {19 / 180.0, 0.0, 63 / 200.0, 16 / 225.0, 1 / 120.0};
     m.b_hat_prime = {1 / 9.0, 0.0, 9 / 20.0, 16 / 45.0, 1 / 12.0};
     std::vector<double> const delta = {25 / 1116.0, 0.0, -63 / 1240.0,
@@ -318,6 +332,9 @@ class ErknInstance {
   State const& state() const { return state_; }
   std::int64_t evaluations = 0;
   std::int64_t rejections = 0;
+  // If set (and the method has velocity stages), the right-hand side of the
+  // generalized integrator; rhs_ is then unused.
+  GeneralizedRightHandSide generalized_rhs;
 
   int32_t Solve(double const t_final) {
     auto const& m = method_;
@@ -334,6 +351,7 @@ class ErknInstance {
     error_estimate.position_error.resize(dimension);
     error_estimate.velocity_error.resize(dimension);
     std::vector<double> q_stage(dimension);
+    std::vector<double> v_stage(dimension);
     std::vector<std::vector<double>> g(stages, std::vector<double>(dimension));
 
     bool at_end = false;
@@ -383,7 +401,20 @@ class ErknInstance {
             q_stage[k] = q_hat[k].value + h * m.c[i] * v_hat[k].value +
                          h2 * sum;
           }
-          Update(step_status, rhs_(t_stage, q_stage, g[i]));
+          if (generalized_rhs) {
+            // embedded_explicit_generalized_runge_kutta_nyström_integrator_
+            // body.hpp:186-201: the velocity stage.
+            for (int k = 0; k < dimension; ++k) {
+              double sum_prime = 0;
+              for (int j = 0; j < i; ++j) {
+                sum_prime += m.APrime(i, j) * g[j][k];
+              }
+              v_stage[k] = v_hat[k].value + h * sum_prime;
+            }
+            Update(step_status, generalized_rhs(t_stage, q_stage, v_stage, g[i]));
+          } else {
+            Update(step_status, rhs_(t_stage, q_stage, g[i]));
+          }
           ++evaluations;
         }
 

@@ -449,6 +449,76 @@ void orc_double_precision(int32_t op, double const* a, double const* b,
   out[1] = result.error;
 }
 
+// embedded_explicit_generalized_runge_kutta_nyström_integrator_test.cpp:71-154
+// (Legendre): Fine1987RKNG34 on the Legendre differential equation of degree
+// 15, p" = (2 x p' - n (n + 1) p) / (1 - x²) (testing_utilities/
+// integration_body.hpp:95-110), a right-hand side that depends on the velocity.
+int32_t orc_kat_legendre(double tolerance, double derivative_tolerance,
+                         std::int64_t capacity, double* times, double* values,
+                         double* derivatives, std::int64_t* n_states,
+                         std::int64_t* evaluations,
+                         std::int64_t* initial_rejections,
+                         std::int64_t* subsequent_rejections) {
+  constexpr int n = 15;
+  std::int64_t evals = 0;
+  GeneralizedRightHandSide rhs = [&evals](double const t,
+                                          std::vector<double> const& p,
+                                          std::vector<double> const& pv,
+                                          std::vector<double>& pa) {
+    double const x = t - 0.0;
+    double const x2 = x * x;
+    pa[0] = (2 * x * pv[0] - n * (n + 1) * p[0]) / (1 * 1.0 - x2);
+    ++evals;
+    return static_cast<int32_t>(kOk);
+  };
+  std::int64_t initial = 0, subsequent = 0;
+  bool first_step = true;
+  ToleranceToErrorRatio const ratio = [&](double, State const&,
+                                          StateError const& error) {
+    double const r =
+        std::min(tolerance / std::abs(error.position_error[0]),
+                 derivative_tolerance / std::abs(error.velocity_error[0]));
+    bool const tolerable = r > 1.0;
+    if (!tolerable) {
+      if (first_step) {
+        ++initial;
+      } else {
+        ++subsequent;
+      }
+    } else if (first_step) {
+      first_step = false;
+    }
+    return r;
+  };
+  State state;
+  state.positions.resize(1);
+  state.velocities.resize(1);
+  state.positions[0].value = 0;
+  state.velocities[0].value = -6435 / (2048 * 1.0);
+  double const t_final = 0.0 + 0.99 * 1.0;
+  std::int64_t count = 0;
+  AdaptiveParameters parameters;
+  parameters.first_step = t_final - 0.0;
+  ErknInstance instance(
+      Fine1987RKNG34(), RightHandSide(), state,
+      [&](State const& s) {
+        if (count < capacity) {
+          times[count] = s.time.value;
+          values[count] = s.positions[0].value;
+          derivatives[count] = s.velocities[0].value;
+        }
+        ++count;
+      },
+      ratio, parameters);
+  instance.generalized_rhs = rhs;
+  int32_t const status = instance.Solve(t_final);
+  *n_states = count;
+  *evaluations = evals;
+  *initial_rejections = initial;
+  *subsequent_rejections = subsequent;
+  return status;
+}
+
 double orc_cr_sin(double x) { return CrSin(x); }
 double orc_cr_cos(double x) { return CrCos(x); }
 double orc_root(int32_t n, double x) { return Root(n, x); }

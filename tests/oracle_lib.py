@@ -33,6 +33,8 @@ _SYMBOLS = [
     ('orc_double_precision', None, [_i32, _dp, _dp, _dp]),
     ('orc_kat_best_newhall', _i32,
      [_d, _d, _i32, _i32p, _i32p, _dp, _i32p, _i32p, _dp, _i32p, _i32p]),
+    ('orc_kat_legendre', _i32,
+     [_d, _d, _i64, _dp, _dp, _dp, _i64p, _i64p, _i64p, _i64p]),
     ('orc_kat_adaptive_oscillator_max_steps', _i32,
      [_d, _d, _d, _d, _d, _d, _d, _d, _i64, _i64p, _i64p, _i64p, _i64p, _dp]),
     ('orc_cr_sin', _d, [_d]),

@@ -143,6 +143,36 @@ def test_adaptive_singularity():
   assert ulp_distance(x.value, 1.0) == 540
 
 
+# integrators/embedded_explicit_generalized_runge_kutta_nyström_integrator_test
+# .cpp:71-154 (Legendre): Fine1987RKNG34 with a right-hand side that depends on
+# the velocity (the velocity stages of the generalized integrator), on the
+# Legendre equation of degree 15 over [0, 0.99]: errors 295(1)e-6 and 16.2(1)e-3.
+def test_generalized_adaptive_legendre():
+  from numpy.polynomial import legendre
+  lib = oracle_lib.library()
+  capacity = 4096
+  times, values, derivatives = (np.zeros(capacity) for _ in range(3))
+  n, ev = ctypes.c_int64(), ctypes.c_int64()
+  ir, sr = ctypes.c_int64(), ctypes.c_int64()
+  dptr = oracle_lib.dptr
+  status = lib.orc_kat_legendre(1e-6, 1e-6, capacity, dptr(times), dptr(values),
+                                dptr(derivatives), ctypes.byref(n),
+                                ctypes.byref(ev), ctypes.byref(ir),
+                                ctypes.byref(sr))
+  assert status == 0
+  count = n.value
+  assert 0 < count <= capacity
+  p15 = legendre.Legendre.basis(15)
+  error = np.abs(p15(times[:count]) - values[:count]).max()
+  derivative_error = np.abs(p15.deriv()(times[:count]) -
+                            derivatives[:count]).max()
+  assert is_near(error, 295e-6, digits=3)
+  assert is_near(derivative_error, 16.2e-3, digits=3)
+  assert times[count - 1] == 0.99
+  # 5 stages, no FSAL: every attempt costs 5 evaluations.
+  assert ev.value == 5 * (count + ir.value + sr.value)
+
+
 def test_correctly_rounded_functions_against_mpmath():
   import mpmath
   mpmath.mp.prec = 400
