@@ -45,14 +45,55 @@ WORKLOAD = ('config 2: 10^5 LEO probes per GPU, Sol 34 bodies, Earth '
 
 
 class ClockSampler:
-  """nvidia-smi clocks during the timed region (B200_PROFILING.md)."""
+  """SM clock and throttle reasons during the timed region
+  (B200_PROFILING.md).  In-process NVML (pynvml), one light query every 50 ms:
+  an `nvidia-smi -lms` child was measured to stall kernel launches for tens of
+  milliseconds per query on an 8-GPU box (value 1.9e9 instead of 2.8e9 in one
+  run out of five); nvidia-smi remains the fallback."""
 
   def __init__(self, index):
     self.index = index
+    self.samples = []  # (sm MHz, max MHz, reasons bitmask).
+    self.thread = None
+    self.stop_event = threading.Event()
     self.process = None
     self.lines = []
 
+  def _nvml_loop(self, nvml, handle):
+    while not self.stop_event.is_set():
+      try:
+        sm = nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)
+        sm_max = nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM)
+        try:
+          reasons = nvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+        except AttributeError:
+          reasons = nvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+        self.samples.append((float(sm), float(sm_max), int(reasons)))
+      except Exception:  # An NVML hiccup must not end the bench.
+        pass
+      self.stop_event.wait(0.05)
+
   def start(self):
+    try:
+      import pynvml as nvml
+      nvml.nvmlInit()
+      visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+      index = self.index
+      if visible:
+        entries = [v for v in visible.split(',') if v.strip()]
+        if self.index < len(entries) and entries[self.index].strip().isdigit():
+          index = int(entries[self.index])
+      handle = nvml.nvmlDeviceGetHandleByIndex(index)
+      self.nvml = nvml
+      self.thread = threading.Thread(target=self._nvml_loop,
+                                     args=(nvml, handle), daemon=True)
+      self.thread.start()
+      deadline = time.perf_counter() + 2.0
+      while not self.samples and time.perf_counter() < deadline:
+        time.sleep(0.005)
+      return
+    except Exception:
+      self.thread = None
     try:
       self.process = subprocess.Popen(
           ['nvidia-smi', '-i', str(self.index),
@@ -65,9 +106,6 @@ class ClockSampler:
           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
       self.thread = threading.Thread(target=self._read, daemon=True)
       self.thread.start()
-      # nvidia-smi takes a second to initialise NVML (and disturbs launches
-      # while it does): wait for its first sample, so that the timed region
-      # only sees the periodic queries.
       deadline = time.perf_counter() + 5.0
       while not self.lines and time.perf_counter() < deadline:
         time.sleep(0.01)
@@ -79,14 +117,36 @@ class ClockSampler:
       self.lines.append(line.strip())
 
   def stop(self):
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    if self.process is None and self.thread is not None:
+      # NVML path.
+      self.stop_event.set()
+      self.thread.join(timeout=2)
+      nvml = self.nvml
+      bits = {
+          'hw_slowdown': nvml.nvmlClocksEventReasonHwSlowdown,
+          'hw_thermal_slowdown': nvml.nvmlClocksEventReasonHwThermalSlowdown,
+          'sw_thermal_slowdown': nvml.nvmlClocksEventReasonSwThermalSlowdown,
+          'sw_power_cap': nvml.nvmlClocksEventReasonSwPowerCap,
+      }
+      reasons = set()
+      for _, _, mask in self.samples:
+        for name in names:
+          if mask & bits[name]:
+            reasons.add(name)
+      sm = [s[0] for s in self.samples]
+      sm_max = [s[1] for s in self.samples]
+      return {'sm_mhz': float(np.median(sm)) if sm else None,
+              'sm_max_mhz': max(sm_max) if sm_max else None,
+              'samples': len(sm), 'reasons': sorted(reasons),
+              'source': 'nvml'}
     if self.process is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
     time.sleep(0.25)
     self.process.terminate()
     self.thread.join(timeout=2)
     sm, sm_max, reasons = [], [], set()
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-             'sw_power_cap']
     for line in self.lines:
       parts = [p.strip() for p in line.split(',')]
       if len(parts) < 7:
@@ -101,7 +161,8 @@ class ClockSampler:
           reasons.add(name)
     return {'sm_mhz': float(np.median(sm)) if sm else None,
             'sm_max_mhz': max(sm_max) if sm_max else None,
-            'samples': len(sm), 'reasons': sorted(reasons)}
+            'samples': len(sm), 'reasons': sorted(reasons),
+            'source': 'nvidia-smi'}
 
 
 def host_cores():
