@@ -1696,3 +1696,61 @@ def test_newhall_non_constant_degree():
       dptr(times), dptr(values), dptr(derivatives)) == 0
   relative_error = abs(values[0] - length(t_min)) / abs(length(t_min))
   assert is_near(relative_error, 9e-13, digits=1)
+
+
+# astronomy/mercury_perihelion_test.cpp:49-60,160-205 (Year1960): the Sol system
+# of 1950 (fixture sol_jd2433282, tools/make_system_fixtures.py) integrated over
+# ten years with QuinlanTremaine1990Order12 at 10 min; the osculating elements
+# of Mercury against the ones the reference holds (HORIZONS): the Newtonian
+# ephemeris lacks the relativistic precession, 4.206(1)" of argument of
+# periapsis per decade, and lags by 17.03(1)" in mean anomaly.
+def test_mercury_perihelion_1960():
+  system = SolarSystem.from_fixture('sol_jd2433282')
+  oracle = OracleEphemeris(system, fitting_tolerance=5e-3)
+  t_1960 = (2436934.5 - 2451545.0) * 86400.0
+  assert oracle.prolong(t_1960) == 0
+  sun, mercury = system.index('Sun'), system.index('Mercury')
+  positions = oracle.evaluate_all_positions(t_1960)
+  velocities = oracle.evaluate_all_velocities(t_1960)
+  r = positions[mercury] - positions[sun]
+  v = velocities[mercury] - velocities[sun]
+  mu = system.bodies[sun]['mu'] + system.bodies[mercury]['mu']
+  # Osculating elements (physics/kepler_orbit_body.hpp, from the degrees of
+  # freedom): textbook formulae, in the ICRS equator.
+  h = np.cross(r, v)
+  h_hat = h / np.linalg.norm(h)
+  e_vector = np.cross(v, h) / mu - r / np.linalg.norm(r)
+  eccentricity = np.linalg.norm(e_vector)
+  semimajor_axis = 1 / (2 / np.linalg.norm(r) - np.dot(v, v) / mu)
+  mean_motion = math.sqrt(mu / semimajor_axis**3)
+  inclination = math.acos(h_hat[2])
+  node = np.cross([0.0, 0.0, 1.0], h)
+  longitude_of_ascending_node = math.atan2(node[1], node[0])
+  argument_of_periapsis = math.atan2(
+      np.dot(np.cross(node, e_vector), h_hat), np.dot(node, e_vector))
+  true_anomaly = math.atan2(np.dot(np.cross(e_vector, r), h_hat),
+                            np.dot(e_vector, r))
+  eccentric_anomaly = 2 * math.atan(
+      math.sqrt((1 - eccentricity) / (1 + eccentricity)) *
+      math.tan(true_anomaly / 2))
+  mean_anomaly = (eccentric_anomaly -
+                  eccentricity * math.sin(eccentric_anomaly)) % (2 * math.pi)
+  degree = math.pi / 180
+  arc_second = degree / 3600
+
+  def relative_error(actual, expected):
+    return abs(actual - expected) / abs(expected)
+
+  assert is_near(relative_error(eccentricity, 2.056305163902087e-01), 5.3e-7)
+  assert is_near(relative_error(semimajor_axis, 5.790908221204869e+10),
+                 1.1e-7)
+  assert is_near(relative_error(mean_motion,
+                                4.736510044238512e-05 * degree), 1.6e-7)
+  assert is_near(relative_error(inclination, 2.855025264340049e+01 * degree),
+                 9.3e-10)
+  assert is_near(relative_error(longitude_of_ascending_node,
+                                1.100120089390144e+01 * degree), 7.5e-9)
+  assert is_near((6.748880915164143e+01 * degree - argument_of_periapsis) /
+                 arc_second, 4.206, digits=4)
+  assert is_near((mean_anomaly - 1.437427180144607e+02 * degree) / arc_second,
+                 17.03, digits=4)

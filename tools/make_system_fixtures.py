@@ -305,6 +305,9 @@ def main():
   for name, gravity, state in (
       ('sol_jd2451545', 'sol_gravity_model.proto.txt',
        'sol_initial_state_jd_2451545_000000000.proto.txt'),
+      # The epoch of astronomy/mercury_perihelion_test.cpp (1950-01-01).
+      ('sol_jd2433282', 'sol_gravity_model.proto.txt',
+       'sol_initial_state_jd_2433282_500000000.proto.txt'),
       ('trappist_jd2457000', 'trappist_gravity_model.proto.txt',
        'trappist_initial_state_jd_2457000_000000000.proto.txt')):
     system = make_system(gravity, state)
