@@ -250,3 +250,43 @@ def test_full_size_fit_reproduces_the_appended_points():
     assert np.all(np.isfinite(q)) and np.all(np.isfinite(v))
   sampled = degrees[:, ::n // 64]
   assert sampled.min() >= 3 and sampled.max() <= 17
+
+
+def test_sol_ephemeris_produced_on_the_device(sol_system):
+  """Ephemeris::Prolong without the host: the Sol system (one system, the
+  cooperative single-system kernel) integrated with QuinlanTremaine1990Order12
+  at 10 min over three days, every state fitted on the device; the polynomials
+  of every body are the oracle's ContinuousTrajectory's, bit for bit."""
+  from oracle_lib import OracleEphemeris
+  system = sol_system
+  gpu = Ephemeris(system)
+  order, _ = gpu.internal_order()
+  n, h = len(order), 600.0
+  state = np.zeros((12, n, 1))
+  state[0:3, :, 0] = system.initial_positions()[order].T
+  state[6:9, :, 0] = system.initial_velocities()[order].T
+  t_final = 3 * 86400.0
+  trajectories = ContinuousTrajectories(n, h, 1e-3, 64)
+  ensemble = NBodyEnsemble(gpu, _capi.QUINLAN_TREMAINE_1990_ORDER_12, h, state,
+                           0.0)
+  t = t_final
+  while trajectories.t_max() < t_final:  # Ephemeris::Prolong.
+    ensemble.solve_to_trajectories(t, trajectories)
+    t += h
+  oracle = OracleEphemeris(system)
+  assert oracle.prolong(t_final) == 0
+  assert trajectories.t_max() == oracle.t_max()
+  for internal, caller in enumerate(order):
+    actual = trajectories.segments(internal)
+    expected = oracle.segments(int(caller))
+    assert actual['t_min'] == expected['t_min'] == 0.0
+    assert_bitwise_equal(actual['t_max'], expected['t_max'])
+    assert_bitwise_equal(actual['origin'], expected['origin'])
+    assert list(actual['degree']) == list(expected['degree'])
+    valid = np.arange(18)[None, :, None] <= actual['degree'][:, None, None]
+    assert_bitwise_equal(np.where(valid, actual['coefficients'], 0.0),
+                         np.where(valid, expected['coefficients'], 0.0),
+                         system.bodies[int(caller)]['name'])
+  q, v = trajectories.evaluate(123456.7)
+  assert_bitwise_equal(q, oracle.evaluate_all_positions(123456.7)[order].T)
+  assert_bitwise_equal(v, oracle.evaluate_all_velocities(123456.7)[order].T)
