@@ -96,7 +96,7 @@ struct EnsembleLaunch {
 };
 
 EnsembleLaunch MakeEnsembleLaunch(pb_nbody_ensemble const* s) {
-  EnsembleShape const shape = MakeEnsembleShape(s->n_bodies);
+  EnsembleShape const shape = MakeEnsembleShape(s->n_bodies, s->n_systems);
   EnsembleLaunch launch;
   launch.grid = static_cast<unsigned>((s->n_systems + kEnsembleLanes - 1) /
                                       kEnsembleLanes);
@@ -138,6 +138,7 @@ pb_status_t SrknStep(pb_nbody_ensemble* s, double const h,
   PB_RETURN_IF_ERROR(BuildFrames(s, times, stream));
   EnsembleLaunch const launch = MakeEnsembleLaunch(s);
   auto const kernel = launch.own == 4       ? EnsembleSrknStepKernel<4, 512>
+                      : launch.own == 2     ? EnsembleSrknStepKernel<2, 576>
                       : launch.block <= 256 ? EnsembleSrknStepKernel<1, 256>
                                             : EnsembleSrknStepKernel<1, 512>;
   kernel<<<launch.grid, launch.block, launch.shared_bytes, stream>>>(
@@ -154,6 +155,7 @@ pb_status_t FillStep(pb_nbody_ensemble* s, int const slot,
   PB_RETURN_IF_ERROR(BuildFrames(s, {s->time.value}, stream));
   EnsembleLaunch const launch = MakeEnsembleLaunch(s);
   auto const kernel = launch.own == 4       ? EnsembleFillStepKernel<4, 512>
+                      : launch.own == 2     ? EnsembleFillStepKernel<2, 576>
                       : launch.block <= 256 ? EnsembleFillStepKernel<1, 256>
                                             : EnsembleFillStepKernel<1, 512>;
   kernel<<<launch.grid, launch.block, launch.shared_bytes, stream>>>(
@@ -171,9 +173,11 @@ pb_status_t MultistepStep(pb_nbody_ensemble* s, cudaStream_t stream) {
   auto const kernel =
       s->multistep.order == 8
           ? (launch.own == 4         ? EnsembleMultistepStepKernel<4, 512, 8>
+             : launch.own == 2       ? EnsembleMultistepStepKernel<2, 576, 8>
              : launch.block <= 256   ? EnsembleMultistepStepKernel<1, 256, 8>
                                      : EnsembleMultistepStepKernel<1, 512, 8>)
           : (launch.own == 4         ? EnsembleMultistepStepKernel<4, 512, 12>
+             : launch.own == 2       ? EnsembleMultistepStepKernel<2, 576, 12>
              : launch.block <= 256   ? EnsembleMultistepStepKernel<1, 256, 12>
                                      : EnsembleMultistepStepKernel<1, 512, 12>);
   kernel<<<launch.grid, launch.block, launch.shared_bytes, stream>>>(

@@ -40,9 +40,14 @@ struct EnsembleShape {
   int own;    // Bodies per warp.
 };
 
-inline EnsembleShape MakeEnsembleShape(int const n_bodies) {
+// A single system (the cooperative form of the right-hand side: the lanes of a
+// warp share out the partners of its body) is latency-bound, so its bodies are
+// spread over as many warps as a block holds: 2 per warp above 16 bodies (17
+// warps for the 34 bodies of the Sol system) instead of 4.
+inline EnsembleShape MakeEnsembleShape(int const n_bodies,
+                                       long long const n_systems = 0) {
   EnsembleShape shape;
-  shape.own = n_bodies <= 16 ? 1 : 4;
+  shape.own = n_bodies <= 16 ? 1 : n_systems == 1 && n_bodies <= 36 ? 2 : 4;
   shape.warps = (n_bodies + shape.own - 1) / shape.own;
   return shape;
 }
