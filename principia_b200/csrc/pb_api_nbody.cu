@@ -78,6 +78,11 @@ struct pb_nbody_ensemble {
   DeviceBuffer<double> state;
   DeviceBuffer<double> displacement_value, displacement_error, acceleration;
   DeviceBuffer<double> frame_times, frames;
+  // The multistep steps build the surface frames of the next steps in one go:
+  // the times frames.data holds (6 n_frames doubles each), and the entry the
+  // next step expects to use.  Any other use of `frames` empties the cache.
+  std::vector<double> frame_cache_times;
+  std::size_t frame_cache_next = 0;
   MultistepHistory History() {
     return {displacement_value.data, displacement_error.data,
             acceleration.data};
@@ -110,6 +115,7 @@ EnsembleLaunch MakeEnsembleLaunch(pb_nbody_ensemble const* s) {
 // Surface-frame axes at the given times -> ensemble->frames.
 pb_status_t BuildFrames(pb_nbody_ensemble* s, std::vector<double> const& times,
                         cudaStream_t stream) {
+  s->frame_cache_times.clear();
   EphemerisView const view = s->ephemeris->View();
   std::size_t const size =
       std::max<std::size_t>(1, times.size() * 6 * view.n_frames);
@@ -168,7 +174,24 @@ pb_status_t MultistepStep(pb_nbody_ensemble* s, cudaStream_t stream) {
   EphemerisView const view = s->ephemeris->View();
   DP t = s->time;
   Increment(t, s->step);
-  PB_RETURN_IF_ERROR(BuildFrames(s, {t.value}, stream));
+  // The frames at the times of this step and of the 63 that follow it (the
+  // compensated increments the steps will perform), built once.
+  std::size_t index = s->frame_cache_next;
+  if (!(index < s->frame_cache_times.size() &&
+        s->frame_cache_times[index] == t.value)) {
+    std::vector<double> times;
+    DP future = s->time;
+    for (int k = 0; k < 64; ++k) {
+      Increment(future, s->step);
+      times.push_back(future.value);
+    }
+    PB_RETURN_IF_ERROR(BuildFrames(s, times, stream));
+    s->frame_cache_times = times;
+    index = 0;
+  }
+  s->frame_cache_next = index + 1;
+  double const* const step_frames =
+      s->frames.data + index * 6 * static_cast<std::size_t>(view.n_frames);
   EnsembleLaunch const launch = MakeEnsembleLaunch(s);
   auto const kernel =
       s->multistep.order == 8
@@ -181,7 +204,7 @@ pb_status_t MultistepStep(pb_nbody_ensemble* s, cudaStream_t stream) {
              : launch.block <= 256   ? EnsembleMultistepStepKernel<1, 256, 12>
                                      : EnsembleMultistepStepKernel<1, 512, 12>);
   kernel<<<launch.grid, launch.block, launch.shared_bytes, stream>>>(
-      view, s->multistep, s->step, s->frames.data, s->n_systems, s->state.data,
+      view, s->multistep, s->step, step_frames, s->n_systems, s->state.data,
       s->History(), s->oldest);
   PB_LAUNCHED();
   s->oldest = (s->oldest + 1) % s->multistep.order;
