@@ -370,15 +370,18 @@ def bench_allpairs(args):
   n = args.bodies
   mu, q, v = random_cluster(n, seed=42)
   begin, end = sharding.equal_block_range(n, rank, world)
-  exchange = None
-  if world > 1:
-    exchange = sharding.AllGatherExchange(n, dist, device)
   system = NBodyAllPairs(_capi.BLANES_MOAN_2002_SRKN_14A, 3600.0, mu, q, v,
-                         0.0, i_begin=begin, i_end=end, device=local_rank,
-                         exchange=exchange)
+                         0.0, i_begin=begin, i_end=end, device=local_rank)
+  communicator = None
+  if world > 1:
+    communicator = sharding.NcclCommunicator(dist, local_rank)
+    system.set_nccl(communicator)
+  if args.arithmetic == 'contracted':
+    system.set_arithmetic(_capi.PB_ARITHMETIC_CONTRACTED)
   system.accelerations()  # Warm-up.
   torch.cuda.synchronize()
   force_ms = []
+  exchange_ms = []
   walls = []
   for _ in range(args.steps):
     if world > 1:
@@ -389,6 +392,7 @@ def bench_allpairs(args):
     torch.cuda.synchronize()
     walls.append(time.perf_counter() - t0)
     force_ms.append(system.last_force_ms())
+    exchange_ms.append(system.last_exchange_ms())
   kernel_s = max_over_ranks(torch, dist, world, float(np.mean(force_ms)) * 1e-3,
                             device)
   wall = max_over_ranks(torch, dist, world, float(np.mean(walls)), device)
@@ -406,8 +410,9 @@ def bench_allpairs(args):
   if rank == 0:
     print(json.dumps({
         'config': 'config 5: all-pairs point masses, i-block sharded',
-        'n_gpus': world, 'n_bodies': n,
+        'n_gpus': world, 'n_bodies': n, 'arithmetic': args.arithmetic,
         'force_kernel_seconds': kernel_s,
+        'exchange_seconds': float(np.mean(exchange_ms)) * 1e-3,
         'force_call_seconds_with_exchange': wall,
         'pair_interactions_per_second': interactions / kernel_s,
         'algorithmic_tflops': flops / kernel_s / 1e12,
@@ -425,6 +430,8 @@ def main():
   parser.add_argument('--steps', type=int, default=20)
   parser.add_argument('--bodies', type=int, default=2**17)
   parser.add_argument('--sink-capacity', type=int, default=0)
+  parser.add_argument('--arithmetic', default='exact',
+                      choices=['exact', 'contracted'])
   args = parser.parse_args()
   if args.config in ('adaptive', 'all'):
     bench_adaptive(args)

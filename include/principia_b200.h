@@ -60,6 +60,17 @@ enum {
   PB_FINE_1987_RKNG_34 = 17
 };
 
+/* Arithmetic of the fixed-step flows and of the all-pairs force.
+ * PB_ARITHMETIC_EXACT: IEEE binary64 without contraction, the operations of
+ * the reference in the reference's order (its -ffp-contract=off build,
+ * Makefile:123-169 there); results are bit-identical to the CPU oracle.
+ * PB_ARITHMETIC_CONTRACTED (opt-in): the same formulae compiled with fused
+ * multiply-adds (and, in the all-pairs force, r^-3 from a refined reciprocal
+ * square root): not bit-identical, within BASELINE.json's tolerance (relative
+ * position error <= 1e-12 after 10^4 steps).  The adaptive flows are always
+ * exact (identical accepted-step sequence). */
+enum { PB_ARITHMETIC_EXACT = 0, PB_ARITHMETIC_CONTRACTED = 1 };
+
 /* One massive body: MassiveBody / RotatingBody / OblateBody parameters
  * (physics/massive_body.hpp, rotating_body.hpp:45-77, oblate_body.hpp:39-75).
  * `cos`/`sin` are the fully normalised coefficients, lower triangular,
@@ -457,16 +468,24 @@ pb_status_t pb_nbody_ensemble_solve_to_trajectories(
 
 /* ---- Large-N all-pairs point-mass system (synthetic; the same
  * ComputeGravitationalAccelerationBetweenAllMassiveBodies with only spherical
- * bodies, ephemeris_body.hpp:1342-1380,1503-1552), Quinlan-Tremaine / SRKN.
+ * bodies, ephemeris_body.hpp:1342-1380,1503-1552), Quinlan-Tremaine / SRKN
+ * (integrators/symmetric_linear_multistep_integrator_body.hpp:22-152).
  * Sharded by target block across ranks: this rank owns targets
- * [i_begin, i_end) of n.  `exchange` (may be NULL when the rank owns every
- * target) is called after every position update with the device pointer of
- * the full position array (3 planes of n) whose [i_begin, i_end) slices this
- * rank has just written; it must return once every other rank's slices are
- * visible in that array (an NCCL all-gather on `stream`). */
-typedef void (*pb_exchange_positions_t)(void* user, double* positions_device,
-                                        int64_t n, int64_t i_begin,
-                                        int64_t i_end, void* stream);
+ * [i_begin, i_end) of n.  Every force evaluation needs all positions, so after
+ * every position update the owned slices are exchanged:
+ *  - pb_nbody_allpairs_set_nccl: ONE in-place ncclAllGather on the force
+ *    stream, issued by the library (equal blocks in rank order);
+ *  - or the `exchange` callback (may be NULL when the rank owns every target):
+ *    it receives the device pointer of the source array, [n][4] doubles
+ *    {x, y, z, mu} whose rows [i_begin, i_end) this rank has just written, and
+ *    must return once every other rank's rows are visible in that array (work
+ *    enqueued on `stream` counts).  A non-OK return aborts the solve.
+ * A target's acceleration has the same bits whichever rank owns it (the
+ * summation order depends on n only, pb_kernels_allpairs.cuh). */
+typedef pb_status_t (*pb_exchange_positions_t)(void* user,
+                                               double* sources_device,
+                                               int64_t n, int64_t i_begin,
+                                               int64_t i_end, void* stream);
 typedef struct pb_nbody_allpairs pb_nbody_allpairs_t;
 pb_status_t pb_nbody_allpairs_create(int32_t cuda_device, int32_t method,
                                      double step, int64_t n, int64_t i_begin,
@@ -479,6 +498,24 @@ pb_status_t pb_nbody_allpairs_create(int32_t cuda_device, int32_t method,
                                      void* exchange_user,
                                      pb_nbody_allpairs_t** system);
 void pb_nbody_allpairs_destroy(pb_nbody_allpairs_t* system);
+/* `nccl_comm` is the caller's ncclComm_t (not owned; NULL detaches): its size
+ * and this rank's index must match the sharding, n = size x (i_end - i_begin),
+ * i_begin = rank x (i_end - i_begin).  NCCL is resolved at run time from the
+ * copy already loaded in the process (else libnccl.so.2 on the library path). */
+pb_status_t pb_nbody_allpairs_set_nccl(pb_nbody_allpairs_t* system,
+                                       void* nccl_comm);
+/* For hosts that have no communicator of their own: ncclGetUniqueId /
+ * ncclCommInitRank / ncclCommDestroy through the same run-time binding.
+ * `unique_id` is 128 bytes, created on one rank and handed to the others by the
+ * host (the Python mirror broadcasts it with torch.distributed). */
+pb_status_t pb_nccl_get_unique_id(char* unique_id);
+pb_status_t pb_nccl_comm_create(const char* unique_id, int32_t world,
+                                int32_t rank, int32_t cuda_device,
+                                void** nccl_comm);
+void pb_nccl_comm_destroy(void* nccl_comm);
+/* PB_ARITHMETIC_EXACT (default) or PB_ARITHMETIC_CONTRACTED, see the enum. */
+pb_status_t pb_nbody_allpairs_set_arithmetic(pb_nbody_allpairs_t* system,
+                                             int32_t arithmetic);
 pb_status_t pb_nbody_allpairs_solve(pb_nbody_allpairs_t* system, double t_final,
                                     int64_t* n_steps,
                                     int64_t* n_force_evaluations);
@@ -489,8 +526,10 @@ pb_status_t pb_nbody_allpairs_get_state(pb_nbody_allpairs_t* system, double* q,
  * accelerations of the owned targets, 3 planes of (i_end - i_begin). */
 pb_status_t pb_nbody_allpairs_accelerations(pb_nbody_allpairs_t* system,
                                             double* a);
-/* Milliseconds spent in the last solve's force kernels (CUDA events). */
+/* Milliseconds spent in the force kernels, resp. in the position exchanges,
+ * of the last solve / accelerations call (CUDA events on the force stream). */
 double pb_nbody_allpairs_last_force_ms(const pb_nbody_allpairs_t* system);
+double pb_nbody_allpairs_last_exchange_ms(const pb_nbody_allpairs_t* system);
 
 /* ---- The trajectory sink: DiscreteTrajectorySegment::SetDownsampling +
  * Append (physics/discrete_trajectory_segment_body.hpp:414-479; tolerances in

@@ -1305,6 +1305,75 @@ int32_t orc_nbody_ensemble_flow(orc_ephemeris* e, int32_t method, double step,
   return kOk;
 }
 
+// The large-N all-pairs force for a subset of the targets, in the summation
+// order of the product's kernel (principia_b200/csrc/pb_kernels_allpairs.cuh;
+// the arithmetic of one interaction is ephemeris_body.hpp:1366-1374): the
+// sources are cut into L = clamp(2^23 / n, 8, 64) contiguous sub-ranges of
+// `chunk` = ceil(n / L) rounded up to a multiple of 64 sources; each sub-range
+// is summed sequentially (the target itself skipped), the sub-ranges are
+// folded in order by groups of 8, and the groups are folded in order.  This is
+// NOT the reference's pair order (scattered third-law updates), which a subset
+// of targets cannot follow; the tests compare that order to a tolerance at
+// small n.  q: 3 planes of n; targets: n_targets indices; a: [target][xyz].
+int32_t orc_allpairs_target_accelerations(int64_t n, double const* mu,
+                                          double const* q, int64_t n_targets,
+                                          int64_t const* targets, double* a) {
+  int sub_ranges = 64;
+  while (sub_ranges > 8 &&
+         static_cast<int64_t>(sub_ranges) * n > (int64_t{1} << 23)) {
+    sub_ranges /= 2;
+  }
+  int64_t const per_range = (n + sub_ranges - 1) / sub_ranges;
+  int64_t const chunk = (per_range + 63) / 64 * 64;
+  double const* const qx = q;
+  double const* const qy = q + n;
+  double const* const qz = q + 2 * n;
+#pragma omp parallel for schedule(dynamic)
+  for (int64_t k = 0; k < n_targets; ++k) {
+    int64_t const i = targets[k];
+    double total[3] = {0.0, 0.0, 0.0};
+    for (int group = 0; group < sub_ranges / 8; ++group) {
+      double group_sum[3] = {0.0, 0.0, 0.0};
+      for (int w = 0; w < 8; ++w) {
+        int64_t const j_begin = (static_cast<int64_t>(group) * 8 + w) * chunk;
+        int64_t const j_end = std::min(j_begin + chunk, n);
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int64_t j = j_begin; j < j_end; ++j) {
+          if (j == i) {
+            continue;
+          }
+          double const dx = qx[j] - qx[i];
+          double const dy = qy[j] - qy[i];
+          double const dz = qz[j] - qz[i];
+          double const d2 = dx * dx + dy * dy + dz * dz;
+          double const d = std::sqrt(d2);
+          double const one_over_d3 = d / (d2 * d2);
+          double const mu_over_d3 = mu[j] * one_over_d3;
+          ax += dx * mu_over_d3;
+          ay += dy * mu_over_d3;
+          az += dz * mu_over_d3;
+        }
+        if (w == 0) {
+          group_sum[0] = ax;
+          group_sum[1] = ay;
+          group_sum[2] = az;
+        } else {
+          group_sum[0] = group_sum[0] + ax;
+          group_sum[1] = group_sum[1] + ay;
+          group_sum[2] = group_sum[2] + az;
+        }
+      }
+      for (int c = 0; c < 3; ++c) {
+        total[c] = group == 0 ? group_sum[c] : total[c] + group_sum[c];
+      }
+    }
+    a[3 * k] = total[0];
+    a[3 * k + 1] = total[1];
+    a[3 * k + 2] = total[2];
+  }
+  return 0;
+}
+
 int32_t orc_max_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

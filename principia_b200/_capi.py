@@ -92,7 +92,11 @@ class AdaptiveStepFlow(ctypes.Structure):
   ]
 
 
-EXCHANGE_POSITIONS = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p,
+PB_ARITHMETIC_EXACT = 0
+PB_ARITHMETIC_CONTRACTED = 1
+
+EXCHANGE_POSITIONS = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p,
+                                      ctypes.c_void_p,
                                       ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_void_p)
 
@@ -187,6 +191,13 @@ SYMBOLS = [
      [_vp, c_double_p, c_double_p, c_double_p]),
     ('pb_nbody_allpairs_accelerations', _i32, [_vp, c_double_p]),
     ('pb_nbody_allpairs_last_force_ms', _d, [_vp]),
+    ('pb_nbody_allpairs_last_exchange_ms', _d, [_vp]),
+    ('pb_nbody_allpairs_set_nccl', _i32, [_vp, _vp]),
+    ('pb_nbody_allpairs_set_arithmetic', _i32, [_vp, _i32]),
+    ('pb_nccl_get_unique_id', _i32, [ctypes.c_char_p]),
+    ('pb_nccl_comm_create', _i32,
+     [ctypes.c_char_p, _i32, _i32, _i32, ctypes.POINTER(_vp)]),
+    ('pb_nccl_comm_destroy', None, [_vp]),
     ('pb_downsampler_create', _i32,
      [_i32, _i64, _d, _i64, ctypes.POINTER(_vp)]),
     ('pb_downsampler_destroy', None, [_vp]),

@@ -5,10 +5,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../include/principia_b200.h"
+#include "pb_kernels_allpairs.cuh"
 #include "pb_kernels_nbody.cuh"
+#include "pb_nccl.hpp"
 #include "pb_runtime.cuh"
 
 using namespace pb;
@@ -32,7 +35,7 @@ struct AllPairsView {
   double* g;
   double* new_value;
   double* new_error;
-  double* positions;  // 3 * n, every rank's slices.
+  double* sources;    // [n][4]: x, y, z, mu; every rank's slices.
   MultistepHistory history;  // [slot][component][n_local].
 };
 
@@ -55,8 +58,8 @@ __global__ void ApBeginStepKernel(AllPairsView const v, double const ha0,
   }
 }
 
-// q_stage = q.value + dq into the shared position array (dq == nullptr: the
-// state's own positions).
+// q_stage = q.value + dq into the owned slice of the source array
+// (with_increment false: the state's own positions).
 __global__ void ApStagePositionsKernel(AllPairsView const v,
                                        bool const with_increment) {
   long long const i =
@@ -67,7 +70,7 @@ __global__ void ApStagePositionsKernel(AllPairsView const v,
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     double const q = v.state[c * v.n_local + i];
-    v.positions[c * v.n + v.i_begin + i] =
+    v.sources[kApSourceDoubles * (v.i_begin + i) + c] =
         with_increment ? q + v.dq[c * v.n_local + i] : q;
   }
 }
@@ -167,7 +170,7 @@ __global__ void ApPredictKernel(AllPairsView const v,
     DP const position = Add(DP{0.0, 0.0}, sum);
     v.state[c * v.n_local + i] = position.value;
     v.state[(3 + c) * v.n_local + i] = position.error;
-    v.positions[c * v.n + v.i_begin + i] = position.value;
+    v.sources[kApSourceDoubles * (v.i_begin + i) + c] = position.value;
   }
 }
 
@@ -227,11 +230,19 @@ struct pb_nbody_allpairs {
   int oldest = 0;
   pb_exchange_positions_t exchange = nullptr;
   void* exchange_user = nullptr;
-  DeviceBuffer<double> state, dq, dv, g, new_value, new_error, positions, mu;
+  // The communicator of pb_nbody_allpairs_set_nccl (not owned), or null.
+  NcclComm nccl_comm = nullptr;
+  int32_t arithmetic = PB_ARITHMETIC_EXACT;
+  AllPairsSplit split;
+  DeviceBuffer<double> state, dq, dv, g, new_value, new_error, sources;
+  // Group partials of the force kernel when the sources are cut into more
+  // than one group of sub-ranges.
+  DeviceBuffer<double> partials;
   DeviceBuffer<double> displacement_value, displacement_error, acceleration;
   std::vector<cudaEvent_t> events;
   std::size_t events_used = 0;
   double last_force_ms = 0;
+  double last_exchange_ms = 0;
   long long force_evaluations = 0;
 
   ~pb_nbody_allpairs() {
@@ -251,7 +262,7 @@ struct pb_nbody_allpairs {
     v.g = g.data;
     v.new_value = new_value.data;
     v.new_error = new_error.data;
-    v.positions = positions.data;
+    v.sources = sources.data;
     v.history = {displacement_value.data, displacement_error.data,
                  acceleration.data};
     return v;
@@ -265,36 +276,72 @@ unsigned ElementwiseGrid(long long const n) {
                                kElementwiseThreads);
 }
 
-// Makes the other ranks' slices of the position array visible, then evaluates
-// the accelerations of the owned targets into g.
+// Makes the other ranks' slices of the source array visible -- one in-place
+// ncclAllGather of the owned [i_begin, i_end) x {x, y, z, mu} slices on the
+// force stream, or the caller's callback -- then evaluates the accelerations
+// of the owned targets into g.  Events: [exchange begin, force begin, force
+// end] per evaluation.
 pb_status_t Force(pb_nbody_allpairs* s, cudaStream_t stream) {
-  if (s->exchange != nullptr) {
-    s->exchange(s->exchange_user, s->positions.data, s->n, s->i_begin,
-                s->i_end, stream);
+  while (s->events.size() < s->events_used + 3) {
+    cudaEvent_t event;
+    PB_CUDA(cudaEventCreate(&event));
+    s->events.push_back(event);
   }
-  if (s->events.size() < s->events_used + 2) {
-    for (int k = 0; k < 2; ++k) {
-      cudaEvent_t event;
-      PB_CUDA(cudaEventCreate(&event));
-      s->events.push_back(event);
-    }
-  }
-  bool const timed = s->events_used < 4096;
+  bool const timed = s->events_used < 3 * 4096;
   if (timed) {
     PB_CUDA(cudaEventRecord(s->events[s->events_used], stream));
   }
   long long const n_local = s->n_local();
-  AllPairsAccelerationKernel<<<static_cast<unsigned>(
-                                   (n_local + kAllPairsThreads - 1) /
-                                   kAllPairsThreads),
-                               kAllPairsThreads, 0, stream>>>(
-      s->n, s->i_begin, s->i_end, s->positions.data,
-      s->positions.data + s->n, s->positions.data + 2 * s->n, s->mu.data,
-      s->g.data, s->g.data + n_local, s->g.data + 2 * n_local);
-  PB_LAUNCHED();
+  if (s->nccl_comm != nullptr) {
+    int const result = Nccl().all_gather(
+        s->sources.data + kApSourceDoubles * s->i_begin, s->sources.data,
+        static_cast<std::size_t>(kApSourceDoubles * n_local), kNcclFloat64,
+        s->nccl_comm, stream);
+    if (result != kNcclSuccess) {
+      return Fail(PB_INTERNAL,
+                  std::string("ncclAllGather: ") +
+                      (Nccl().get_error_string != nullptr
+                           ? Nccl().get_error_string(result)
+                           : "error"));
+    }
+  } else if (s->exchange != nullptr) {
+    pb_status_t const status =
+        s->exchange(s->exchange_user, s->sources.data, s->n, s->i_begin,
+                    s->i_end, stream);
+    if (status != PB_OK) {
+      return Fail(status, "the position exchange callback failed");
+    }
+  }
   if (timed) {
     PB_CUDA(cudaEventRecord(s->events[s->events_used + 1], stream));
-    s->events_used += 2;
+  }
+  int const groups = s->split.sub_ranges / kApWarps;
+  long long const tiles = (n_local + kApTargets - 1) / kApTargets;
+  AllPairsForceView view;
+  view.n = s->n;
+  view.i_begin = s->i_begin;
+  view.n_local = n_local;
+  view.split = s->split;
+  view.sources = s->sources.data;
+  view.out = groups == 1 ? s->g.data : s->partials.data;
+  unsigned const grid = static_cast<unsigned>(tiles * groups);
+  if (s->arithmetic == PB_ARITHMETIC_CONTRACTED) {
+    AllPairsAccelerationKernel<ContractedInteraction>
+        <<<grid, kApThreads, kApSharedBytes, stream>>>(view);
+  } else {
+    AllPairsAccelerationKernel<ExactInteraction>
+        <<<grid, kApThreads, kApSharedBytes, stream>>>(view);
+  }
+  PB_LAUNCHED();
+  if (groups > 1) {
+    AllPairsCombineKernel<<<ElementwiseGrid(3 * n_local), kElementwiseThreads,
+                            0, stream>>>(n_local, groups, s->partials.data,
+                                         s->g.data);
+    PB_LAUNCHED();
+  }
+  if (timed) {
+    PB_CUDA(cudaEventRecord(s->events[s->events_used + 2], stream));
+    s->events_used += 3;
   }
   ++s->force_evaluations;
   return PB_OK;
@@ -351,9 +398,12 @@ pb_status_t MultistepStep(pb_nbody_allpairs* s, cudaStream_t stream) {
 pb_status_t CollectForceTime(pb_nbody_allpairs* s, cudaStream_t stream) {
   PB_CUDA(cudaStreamSynchronize(stream));
   s->last_force_ms = 0;
-  for (std::size_t k = 0; k + 1 < s->events_used; k += 2) {
+  s->last_exchange_ms = 0;
+  for (std::size_t k = 0; k + 3 <= s->events_used; k += 3) {
     float elapsed = 0;
     PB_CUDA(cudaEventElapsedTime(&elapsed, s->events[k], s->events[k + 1]));
+    s->last_exchange_ms += elapsed;
+    PB_CUDA(cudaEventElapsedTime(&elapsed, s->events[k + 1], s->events[k + 2]));
     s->last_force_ms += elapsed;
   }
   s->events_used = 0;
@@ -400,6 +450,24 @@ pb_status_t pb_nbody_allpairs_create(
   }
   ComputeNodes(s->tableau, s->nodes);
   std::size_t const n_local = static_cast<std::size_t>(i_end - i_begin);
+  s->split = MakeAllPairsSplit(n);
+  {
+    // The dynamic shared memory of the force kernel (stages + partials +
+    // barriers) is below the 48 KiB default; opt in all the same so that a
+    // deeper ring only needs the constant changed.
+    cudaError_t error = cudaFuncSetAttribute(
+        AllPairsAccelerationKernel<ExactInteraction>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, kApSharedBytes);
+    if (error == cudaSuccess) {
+      error = cudaFuncSetAttribute(
+          AllPairsAccelerationKernel<ContractedInteraction>,
+          cudaFuncAttributeMaxDynamicSharedMemorySize, kApSharedBytes);
+    }
+    if (error != cudaSuccess) {
+      delete s;
+      return Fail(PB_INTERNAL, cudaGetErrorString(error));
+    }
+  }
   std::vector<double> state(12 * n_local, 0.0);
   for (int c = 0; c < 3; ++c) {
     std::memcpy(&state[c * n_local], q + c * n + i_begin,
@@ -407,10 +475,20 @@ pb_status_t pb_nbody_allpairs_create(
     std::memcpy(&state[(6 + c) * n_local], v + c * n + i_begin,
                 n_local * sizeof(double));
   }
+  // [n][4]: x, y, z, mu.
+  std::vector<double> sources(kApSourceDoubles * static_cast<std::size_t>(n));
+  for (int64_t j = 0; j < n; ++j) {
+    for (int c = 0; c < 3; ++c) {
+      sources[kApSourceDoubles * j + c] = q[c * n + j];
+    }
+    sources[kApSourceDoubles * j + 3] = gravitational_parameters[j];
+  }
   pb_status_t status = s->state.Upload(state, nullptr);
-  if (status == PB_OK) status = s->positions.Upload(q, 3 * n, nullptr);
-  if (status == PB_OK) {
-    status = s->mu.Upload(gravitational_parameters, n, nullptr);
+  if (status == PB_OK) status = s->sources.Upload(sources, nullptr);
+  if (status == PB_OK && s->split.sub_ranges > kApWarps) {
+    std::size_t const tiles = (n_local + kApTargets - 1) / kApTargets;
+    status = s->partials.Reserve(tiles * (s->split.sub_ranges / kApWarps) * 3 *
+                                 kApTargets);
   }
   if (status == PB_OK) status = s->dq.Reserve(3 * n_local);
   if (status == PB_OK) status = s->dv.Reserve(3 * n_local);
@@ -543,6 +621,100 @@ pb_status_t pb_nbody_allpairs_accelerations(pb_nbody_allpairs_t* s, double* a) {
 
 double pb_nbody_allpairs_last_force_ms(const pb_nbody_allpairs_t* s) {
   return s->last_force_ms;
+}
+
+double pb_nbody_allpairs_last_exchange_ms(const pb_nbody_allpairs_t* s) {
+  return s->last_exchange_ms;
+}
+
+pb_status_t pb_nbody_allpairs_set_arithmetic(pb_nbody_allpairs_t* s,
+                                             int32_t arithmetic) {
+  if (s == nullptr || (arithmetic != PB_ARITHMETIC_EXACT &&
+                       arithmetic != PB_ARITHMETIC_CONTRACTED)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  s->arithmetic = arithmetic;
+  return PB_OK;
+}
+
+pb_status_t pb_nbody_allpairs_set_nccl(pb_nbody_allpairs_t* s,
+                                       void* nccl_comm) {
+  if (s == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null system");
+  }
+  if (nccl_comm == nullptr) {
+    s->nccl_comm = nullptr;
+    return PB_OK;
+  }
+  if (!Nccl().loaded) {
+    return Fail(PB_FAILED_PRECONDITION,
+                "libnccl.so.2 is neither loaded in this process nor on the "
+                "library path");
+  }
+  NcclComm const comm = static_cast<NcclComm>(nccl_comm);
+  int world = 0, rank = -1;
+  if (Nccl().comm_count(comm, &world) != kNcclSuccess ||
+      Nccl().comm_user_rank(comm, &rank) != kNcclSuccess) {
+    return Fail(PB_INVALID_ARGUMENT, "not a usable NCCL communicator");
+  }
+  // The in-place all-gather needs equal contributions in rank order.
+  long long const n_local = s->n_local();
+  if (n_local * world != s->n || s->i_begin != rank * n_local) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "the NCCL exchange needs n = world size x block and "
+                "i_begin = rank x block");
+  }
+  s->nccl_comm = comm;
+  return PB_OK;
+}
+
+pb_status_t pb_nccl_get_unique_id(char* unique_id) {
+  if (unique_id == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null argument");
+  }
+  if (!Nccl().loaded) {
+    return Fail(PB_FAILED_PRECONDITION, "libnccl.so.2 not available");
+  }
+  NcclUniqueId id;
+  int const result = Nccl().get_unique_id(&id);
+  if (result != kNcclSuccess) {
+    return Fail(PB_INTERNAL, "ncclGetUniqueId failed");
+  }
+  std::memcpy(unique_id, id.internal, kNcclUniqueIdBytes);
+  return PB_OK;
+}
+
+pb_status_t pb_nccl_comm_create(const char* unique_id, int32_t world,
+                                int32_t rank, int32_t cuda_device,
+                                void** nccl_comm) {
+  if (unique_id == nullptr || nccl_comm == nullptr || world <= 0 || rank < 0 ||
+      rank >= world) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  *nccl_comm = nullptr;
+  if (!Nccl().loaded) {
+    return Fail(PB_FAILED_PRECONDITION, "libnccl.so.2 not available");
+  }
+  PB_CUDA(cudaSetDevice(cuda_device));
+  NcclUniqueId id;
+  std::memcpy(id.internal, unique_id, kNcclUniqueIdBytes);
+  NcclComm comm = nullptr;
+  int const result = Nccl().comm_init_rank(&comm, world, id, rank);
+  if (result != kNcclSuccess) {
+    return Fail(PB_INTERNAL,
+                std::string("ncclCommInitRank: ") +
+                    (Nccl().get_error_string != nullptr
+                         ? Nccl().get_error_string(result)
+                         : "error"));
+  }
+  *nccl_comm = comm;
+  return PB_OK;
+}
+
+void pb_nccl_comm_destroy(void* nccl_comm) {
+  if (nccl_comm != nullptr && Nccl().loaded) {
+    Nccl().comm_destroy(static_cast<NcclComm>(nccl_comm));
+  }
 }
 
 }  // extern "C"

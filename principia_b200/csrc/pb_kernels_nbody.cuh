@@ -558,103 +558,4 @@ static __global__ void FrameTableKernel(EphemerisView const e,
   }
 }
 
-// ===========================================================================
-// Large-N all-pairs point masses.  One thread per target i, sources staged in
-// shared memory tile by tile; every ordered interaction is evaluated (no
-// third-law sharing across threads): 18 algorithmic flops each
-// (3 sub, 5 norm², sqrt, mul, div, mul, 3 mul, 3 add).  The arithmetic of one
-// interaction is the reference's (ephemeris_body.hpp:1366-1374); the
-// summation runs over sources j = 0..N-1 in increasing order per target, which
-// differs from the reference's pair order (b1 < b2 with scattered updates), so
-// parity with the oracle is to a tolerance, stated in the tests.
-constexpr int kAllPairsThreads = 128;
-
-// positions / mu: full arrays (3 planes of n / n).  Targets [i_begin, i_end).
-static __global__ void __launch_bounds__(kAllPairsThreads, 4)
-AllPairsAccelerationKernel(long long const n, long long const i_begin,
-                           long long const i_end,
-                           double const* __restrict__ qx,
-                           double const* __restrict__ qy,
-                           double const* __restrict__ qz,
-                           double const* __restrict__ mu,
-                           double* __restrict__ ax, double* __restrict__ ay,
-                           double* __restrict__ az) {
-  __shared__ double sx[kAllPairsThreads];
-  __shared__ double sy[kAllPairsThreads];
-  __shared__ double sz[kAllPairsThreads];
-  __shared__ double sm[kAllPairsThreads];
-  long long const i =
-      i_begin + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  bool const active = i < i_end;
-  double const xi = active ? qx[i] : 0.0;
-  double const yi = active ? qy[i] : 0.0;
-  double const zi = active ? qz[i] : 0.0;
-  double accx = 0.0, accy = 0.0, accz = 0.0;
-  bool in_range = true;
-  for (long long tile = 0; tile < n; tile += kAllPairsThreads) {
-    long long const j = tile + threadIdx.x;
-    if (j < n) {
-      sx[threadIdx.x] = qx[j];
-      sy[threadIdx.x] = qy[j];
-      sz[threadIdx.x] = qz[j];
-      sm[threadIdx.x] = mu[j];
-    }
-    __syncthreads();
-    int const count =
-        static_cast<int>(n - tile < kAllPairsThreads ? n - tile
-                                                     : kAllPairsThreads);
-    if (active) {
-      int const self = static_cast<int>(i - tile);  // Index of i in the tile.
-#pragma unroll 4
-      for (int jj = 0; jj < count; ++jj) {
-        // Δq = position of the source - position of the target: the
-        // acceleration on b2 = i due to b1 = j.  Branch-free: the square root
-        // and the division are the correctly rounded FastSqrt / FastDivide
-        // (pb_math.cuh), so that the scheduler interleaves four interactions;
-        // the self-interaction is computed and discarded by a select.
-        bool const is_self = jj == self;
-        double const dx = sx[jj] - xi;
-        double const dy = sy[jj] - yi;
-        double const dz = sz[jj] - zi;
-        double const d2 = dx * dx + dy * dy + dz * dz;
-        in_range = in_range && (InFastRange(d2) || is_self);
-        double const d = FastSqrt(d2);
-        double const one_over_d3 = FastDivide(d, d2 * d2);
-        double const mu_over_d3 = is_self ? 0.0 : sm[jj] * one_over_d3;
-        accx += is_self ? 0.0 : dx * mu_over_d3;
-        accy += is_self ? 0.0 : dy * mu_over_d3;
-        accz += is_self ? 0.0 : dz * mu_over_d3;
-      }
-    }
-    __syncthreads();
-  }
-  if (active && !in_range) {
-    // Some distance is outside the range of the branch-free operators (two
-    // bodies at the same place, non-finite state): redo this target with the
-    // IEEE operators.
-    accx = accy = accz = 0.0;
-    for (long long j = 0; j < n; ++j) {
-      if (j == i) {
-        continue;
-      }
-      double const dx = qx[j] - xi;
-      double const dy = qy[j] - yi;
-      double const dz = qz[j] - zi;
-      double const d2 = dx * dx + dy * dy + dz * dz;
-      double const d = sqrt(d2);
-      double const one_over_d3 = d / (d2 * d2);
-      double const mu_over_d3 = mu[j] * one_over_d3;
-      accx += dx * mu_over_d3;
-      accy += dy * mu_over_d3;
-      accz += dz * mu_over_d3;
-    }
-  }
-  if (active) {
-    long long const o = i - i_begin;
-    ax[o] = accx;
-    ay[o] = accy;
-    az[o] = accz;
-  }
-}
-
 }  // namespace pb

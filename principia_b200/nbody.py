@@ -138,8 +138,10 @@ class NBodyAllPairs:
 
   def __init__(self, method, step, mu, q, v, initial_time, i_begin=0,
                i_end=None, device=0, exchange=None):
-    """mu: (n,), q, v: (3, n).  `exchange(positions_device_pointer, n, i_begin,
-    i_end, stream)` is called after every position update when given."""
+    """mu: (n,), q, v: (3, n).  `exchange(sources_device_pointer, n, i_begin,
+    i_end, stream)` is called after every position update when given (the
+    sources are [n][4] doubles x, y, z, mu); prefer set_nccl, which makes the
+    library issue one ncclAllGather itself."""
     self.lib = _capi.library()
     mu = np.ascontiguousarray(mu, dtype=np.float64)
     q = np.ascontiguousarray(q, dtype=np.float64)
@@ -150,8 +152,18 @@ class NBodyAllPairs:
     if exchange is None:
       self._callback = ctypes.cast(None, _capi.EXCHANGE_POSITIONS)
     else:
-      def trampoline(user, positions, n, begin, end, stream):
-        exchange(positions, n, begin, end, stream)
+      self._exchange_error = None
+
+      def trampoline(user, sources, n, begin, end, stream):
+        # An exception must not escape into ctypes (it would only be printed
+        # and the force would run on stale positions): report it through the
+        # status and re-raise it once the C call has returned.
+        try:
+          exchange(sources, n, begin, end, stream)
+          return _capi.PB_OK
+        except BaseException as error:  # noqa: B902
+          self._exchange_error = error
+          return _capi.PB_ABORTED
       self._callback = _capi.EXCHANGE_POSITIONS(trampoline)
     handle = _vp()
     _check(self.lib.pb_nbody_allpairs_create(
@@ -168,11 +180,30 @@ class NBodyAllPairs:
   def __del__(self):
     self.close()
 
+  def _checked(self, code):
+    error = getattr(self, '_exchange_error', None)
+    if error is not None:
+      self._exchange_error = None
+      raise error
+    _check(code)
+
+  def set_nccl(self, communicator):
+    """`communicator`: a sharding.NcclCommunicator (or None to detach): the
+    library then all-gathers the owned slices itself, one ncclAllGather per
+    force evaluation on the force stream."""
+    self._communicator = communicator  # Keeps it alive.
+    _check(self.lib.pb_nbody_allpairs_set_nccl(
+        self.handle, None if communicator is None else communicator.handle))
+
+  def set_arithmetic(self, arithmetic):
+    """_capi.PB_ARITHMETIC_EXACT (default) or PB_ARITHMETIC_CONTRACTED."""
+    _check(self.lib.pb_nbody_allpairs_set_arithmetic(self.handle, arithmetic))
+
   def solve(self, t_final):
     n_steps, n_forces = ctypes.c_int64(), ctypes.c_int64()
-    _check(self.lib.pb_nbody_allpairs_solve(self.handle, t_final,
-                                            ctypes.byref(n_steps),
-                                            ctypes.byref(n_forces)))
+    self._checked(self.lib.pb_nbody_allpairs_solve(self.handle, t_final,
+                                                   ctypes.byref(n_steps),
+                                                   ctypes.byref(n_forces)))
     return n_steps.value, n_forces.value
 
   def state(self):
@@ -184,8 +215,12 @@ class NBodyAllPairs:
 
   def accelerations(self):
     a = np.zeros((3, self.i_end - self.i_begin))
-    _check(self.lib.pb_nbody_allpairs_accelerations(self.handle, _dptr(a)))
+    self._checked(self.lib.pb_nbody_allpairs_accelerations(self.handle,
+                                                           _dptr(a)))
     return a
 
   def last_force_ms(self):
     return self.lib.pb_nbody_allpairs_last_force_ms(self.handle)
+
+  def last_exchange_ms(self):
+    return self.lib.pb_nbody_allpairs_last_exchange_ms(self.handle)

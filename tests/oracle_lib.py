@@ -100,6 +100,8 @@ _SYMBOLS = [
      [_vp, ctypes.POINTER(_capi.AdaptiveStepFlow), _i32]),
     ('orc_nbody_ensemble_flow', _i32,
      [_vp, _i32, _d, _i64, _dp, _dp, _d, _i64p, _i32]),
+    ('orc_allpairs_target_accelerations', _i32,
+     [_i64, _dp, _dp, _i64, _i64p, _dp]),
     ('orc_max_threads', _i32, []),
 ]
 
@@ -126,6 +128,20 @@ def library():
 
 def dptr(a):
   return a.ctypes.data_as(_dp)
+
+
+def allpairs_target_accelerations(mu, q, targets):
+  """Accelerations (3, len(targets)) of the given targets of an all-pairs
+  point-mass system (mu (n,), q (3, n)), in the product kernel's summation
+  order: bit-comparable with NBodyAllPairs.accelerations()."""
+  mu = np.ascontiguousarray(mu, dtype=np.float64)
+  q = np.ascontiguousarray(q, dtype=np.float64)
+  targets = np.ascontiguousarray(targets, dtype=np.int64)
+  out = np.zeros((len(targets), 3))
+  library().orc_allpairs_target_accelerations(
+      len(mu), dptr(mu), dptr(q), len(targets),
+      targets.ctypes.data_as(_i64p), dptr(out))
+  return np.ascontiguousarray(out.T)
 
 
 class OracleEphemeris:

@@ -32,13 +32,12 @@ def _worker(rank, world, port, n, results):
   dist.init_process_group('gloo', rank=rank, world_size=world)
   try:
     rng = np.random.default_rng(5)
-    truth = torch.from_numpy(rng.normal(size=3 * n))
+    truth = torch.from_numpy(rng.normal(size=4 * n))
     begin, end = sharding.equal_block_range(n, rank, world)
-    # Each rank only knows its own slices; the rest is garbage.
-    full = torch.full((3 * n,), float('nan'), dtype=torch.float64)
-    for c in range(3):
-      full[c * n + begin:c * n + end] = truth[c * n + begin:c * n + end]
-    sharding.gather_planes(full, None, n, begin, end, dist)
+    # Each rank only knows its own rows; the rest is garbage.
+    full = torch.full((4 * n,), float('nan'), dtype=torch.float64)
+    full[4 * begin:4 * end] = truth[4 * begin:4 * end]
+    sharding.gather_sources(full, n, begin, end, dist)
     results[rank] = bool(torch.equal(full, truth))
     # Probe sharding needs no collective: the union of the blocks is the batch.
     b, e = sharding.block_range(1001, rank, world)
