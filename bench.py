@@ -44,6 +44,16 @@ WORKLOAD = ('config 2: 10^5 LEO probes per GPU, Sol 34 bodies, Earth '
             'geopotential 10x10, BlanesMoan2002SRKN14A h=10 s')
 
 
+def bench_config(probes):
+  """The `config` of both arms (the CPU arm flows a bounded sample of it per
+  step, stated in its cpu_baseline.sample)."""
+  return {'workload': WORKLOAD, 'probes_per_gpu': probes,
+          'integrator_steps_per_step': FLOW_STEPS,
+          'step_seconds': STEP_SECONDS,
+          'parallelism': 'probes sharded by rank, no collective',
+          'l2': 'flushed (256 MiB write) before every timed step'}
+
+
 class ClockSampler:
   """SM clock and throttle reasons during the timed region
   (B200_PROFILING.md).  In-process NVML (pynvml), one light query every 50 ms:
@@ -169,6 +179,25 @@ def host_cores():
   return len(os.sched_getaffinity(0))
 
 
+def profile_counters(name):
+  """profiles/current_<name>.json (tools/ncu_to_json.py): the ncu-derived
+  figures of the roofline entry, with the capture they come from."""
+  path = os.path.join(REPO, 'profiles', 'current_%s.json' % name)
+  try:
+    with open(path) as f:
+      data = json.load(f)
+  except (OSError, ValueError):
+    return {'traffic': None, 'ncu': None}
+  return {'traffic': data.get('dram_bytes_per_launch'),
+          'ncu': {k: data.get(k) for k in (
+              'source', 'kernel', 'launch', 'duration_ms',
+              'fp64_pipe_active_pct', 'issue_active_pct',
+              'warps_active_pct', 'registers_per_thread',
+              'fp64_instructions_per_probe_stage',
+              'instructions_per_probe_stage',
+              'frac_at_full_fp64_pipe')}}
+
+
 def make_workload(n, seed):
   from principia_b200 import workloads
   system = workloads.sol_system()
@@ -233,8 +262,7 @@ def run_reference(args):
       'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
       'data': 'synthetic',
-      'config': {'workload': WORKLOAD, 'probes_per_step': n,
-                 'integrator_steps_per_step': FLOW_STEPS},
+      'config': bench_config(args.probes),
       'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads,
                        'kind': 'port', 'sample': sample},
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
@@ -365,23 +393,11 @@ def run_native(args):
   roofline = {
       'bound': 'fp64', 'achieved': achieved, 'peak': peak_flops / 1e12,
       'unit': 'TFLOP/s', 'frac': achieved / (peak_flops / 1e12),
-      # DRAM bytes of one SrknFlowKernel launch as bench.py issues them
-      # (dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full
-      # capture summarised in profiles/r01h_ncu_srkn_flow.txt: 2.71 MB + 2.17 MB
-      # for 25 088 probes x 10 steps; algorithmic 4.8 MB of state): the kernel
-      # is FP64-pipe bound, HBM traffic is negligible.  (A single launch of
-      # 75 776 probes x 100 steps, whose thread-local scratch no longer fits
-      # the L2, writes 10.5 GB in 37.9 ms = 0.28 TB/s:
-      # profiles/r01h_ncu_srkn_flow_full_wave.txt.)
-      'traffic': 4.88e6,
-      # The full-wave capture: FP64 pipe 67.8 % active at 16 warps per SM;
-      # 4 379 FP64-pipe instructions (2 497 DMUL, 1 260 DADD, 550 DFMA,
-      # 72 DSETP; profiles/r01f_ncu_srkn_flow.txt) per probe-stage for 3 739
-      # algorithmic flops (the reference forbids contraction: an add or a
-      # multiply takes a DFMA slot for one flop), so 100 % of the pipe would be
-      # frac 0.427.
-      'fp64_pipe_active_ncu': 0.678,
-      'frac_at_full_fp64_pipe': 0.427,
+      # Counters that only a profiler sees (DRAM traffic per launch, FP64-pipe
+      # activity, executed FP64 instructions per probe-stage) are read from the
+      # committed summary that tools/ncu_to_json.py wrote from the ncu capture
+      # of this kernel -- never literals here; absent file: null.
+      **profile_counters('srkn_flow'),
       'kernel': 'SrknFlowKernel',
       'kernel_ms': average_kernel_ms,
       'kernel_launches_per_step': kernel_launches / args.steps,
@@ -406,6 +422,12 @@ def run_native(args):
                   'oracle restatement on %d OpenMP threads' %
                   (n_cpu, FLOW_STEPS, seconds, threads)}
 
+  secondary = None
+  if not args.no_secondary:
+    import bench_secondary
+    secondary = bench_secondary.run_secondary(torch, dist, world, rank,
+                                              local_rank, peak_flops, args)
+
   if rank == 0:
     print(json.dumps({
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
@@ -413,11 +435,7 @@ def run_native(args):
         'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'probes_per_gpu': n,
-                   'integrator_steps_per_step': FLOW_STEPS,
-                   'step_seconds': STEP_SECONDS,
-                   'parallelism': 'probes sharded by rank, no collective',
-                   'l2': 'flushed (256 MiB write) before every timed step'},
+        'config': bench_config(n),
         'probe_steps_per_second': value / EVALUATIONS,
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT,
@@ -426,7 +444,8 @@ def run_native(args):
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(launches_timed),
         'roofline': roofline,
-        'cpu_baseline': cpu_baseline}))
+        'cpu_baseline': cpu_baseline,
+        'secondary': secondary}))
   if world > 1:
     dist.destroy_process_group()
 
@@ -440,6 +459,12 @@ def main():
                       choices=['native', 'reference'])
   parser.add_argument('--probes', type=int, default=PROBES_PER_GPU)
   parser.add_argument('--no-cpu-baseline', action='store_true')
+  parser.add_argument('--no-secondary', action='store_true',
+                      help='skip configs 3, 4 and 5 (the `secondary` block)')
+  parser.add_argument('--adaptive-probes', type=int, default=100000)
+  parser.add_argument('--ensemble-systems', type=int, default=100000)
+  parser.add_argument('--allpairs-bodies', type=int, default=2**20)
+  parser.add_argument('--allpairs-flow-bodies', type=int, default=2**17)
   args = parser.parse_args()
   if args.impl == 'reference':
     run_reference(args)

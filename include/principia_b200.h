@@ -104,8 +104,37 @@ pb_status_t pb_ephemeris_create(int32_t n_bodies,
                                 double geopotential_tolerance,
                                 int32_t cuda_device,
                                 pb_ephemeris_t** ephemeris);
+/* Refuses (and records an error for pb_last_error) while instances or
+ * ensembles created from the ephemeris are alive: destroy those first. */
 void pb_ephemeris_destroy(pb_ephemeris_t* ephemeris);
+/* The message of the last non-OK status returned on the calling thread. */
 const char* pb_last_error(void);
+
+/* ---- Threading (physics/ephemeris.hpp:64-66: "const methods are
+ * thread-safe; flows on distinct objects may run concurrently").  Every entry
+ * point may be called from any thread.  Calls on one ephemeris run
+ * concurrently -- each leases its own scratch, staging buffers and stream --
+ * except that pb_ephemeris_append_segments waits for the flows and queries in
+ * progress and holds the new ones back while it runs.  One call at a time per
+ * pb_fixed_step_instance_t / pb_nbody_ensemble_t / pb_nbody_allpairs_t
+ * (enforced by a lock per handle).  The fixed-step flow kernels keep the hot
+ * body's harmonics in a __constant__ bank: two fixed-step flows run
+ * concurrently when they use the same ephemeris and hot body, otherwise the
+ * second waits for the first.
+ *
+ * ---- Cooperative cancellation (RETURN_IF_STOPPED after every step,
+ * integrators/symplectic_runge_kutta_nyström_integrator_body.hpp:137,
+ * embedded_explicit_runge_kutta_nyström_integrator_body.hpp:243,
+ * symmetric_linear_multistep_integrator_body.hpp:149): after
+ * pb_ephemeris_request_stop (any thread, lock-free), the flows in progress on
+ * the ephemeris and on its instances and ensembles return PB_CANCELLED with
+ * the state, time and sinks of the last completed step -- the fixed-step
+ * massless flows at the next boundary between chunks of at most 256 steps, the
+ * ensembles after the current step, the adaptive flow after the current
+ * accepted step of every trajectory (per-trajectory status PB_CANCELLED).  The
+ * request stays in force until pb_ephemeris_clear_stop. */
+pb_status_t pb_ephemeris_request_stop(pb_ephemeris_t* ephemeris);
+pb_status_t pb_ephemeris_clear_stop(pb_ephemeris_t* ephemeris);
 
 /* order[i] = caller index of the body at internal position i; returns the
  * number of oblate bodies through *n_oblate (may be NULL). */
@@ -605,6 +634,15 @@ pb_status_t pb_chebyshev_series_evaluate(
  * number. */
 double pb_ephemeris_last_flow_kernel_ms(const pb_ephemeris_t* ephemeris,
                                         int64_t* launches);
+/* Which code path the last fixed-step flow on this ephemeris took.  *hot_body:
+ * the caller index of the oblate body whose harmonics were served from the
+ * constant bank (-1: none) -- chosen from the first probe of the first flow
+ * and kept; *generic_harmonics != 0: some probe evaluated harmonics of degree
+ * > 3 of ANOTHER body (same bits, several times slower), in which case the
+ * next flow chooses its hot body afresh. */
+pb_status_t pb_ephemeris_last_flow_path(const pb_ephemeris_t* ephemeris,
+                                        int32_t* hot_body,
+                                        int32_t* generic_harmonics);
 /* Register-resident DFMA chain: returns the achieved FP64 FLOP/s on the
  * device (2 flop per FMA) and the kernel time through *ms. */
 pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,

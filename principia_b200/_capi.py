@@ -215,6 +215,9 @@ SYMBOLS = [
      [_i32, _i64, _i32, c_int32_p, c_double_p, c_double_p, c_double_p, _i64,
       c_int32_p, c_double_p, c_double_p, c_double_p]),
     ('pb_ephemeris_last_flow_kernel_ms', _d, [_vp, c_int64_p]),
+    ('pb_ephemeris_last_flow_path', _i32, [_vp, c_int32_p, c_int32_p]),
+    ('pb_ephemeris_request_stop', _i32, [_vp]),
+    ('pb_ephemeris_clear_stop', _i32, [_vp]),
     ('pb_measure_fp64_peak', _i32, [_i32, c_double_p, c_double_p]),
     ('pb_kernel_launch_count', _i64, []),
 ]

@@ -118,7 +118,7 @@ PB_HD Vec3 EvaluateSegmentPadded(EphemerisView const& e, int const segment,
 PB_HD void FillStageEntry(EphemerisView const& e, int const b, double const t,
                           double* const entry) {
   int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
-                                  e.segment_offset[b + 1], t);
+                                  e.segment_end[b], t);
   Vec3 const position = EvaluateSegment(e, segment, t);
   entry[3 * b] = position.x;
   entry[3 * b + 1] = position.y;

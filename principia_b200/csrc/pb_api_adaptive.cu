@@ -27,32 +27,22 @@ int AdaptiveMinBlocks() {
   return value;
 }
 
-}  // namespace
+// The constant bank of this translation unit (c_adaptive_bodies).
+ConstantBank& AdaptiveConstantBank() {
+  static ConstantBank bank;
+  return bank;
+}
 
-extern "C" {
-
-pb_status_t pb_flow_with_adaptive_step_device(
-    pb_ephemeris_t* e, const pb_adaptive_step_flow_t* flow,
-    void* stream_pointer) {
-  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
-  if (e == nullptr || flow == nullptr || flow->n < 0 ||
-      (flow->n > 0 && (flow->state == nullptr || flow->time == nullptr))) {
-    return Fail(PB_INVALID_ARGUMENT, "bad argument");
-  }
-  if (flow->method != PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM &&
-      flow->method != PB_FINE_1987_RKNG_34) {
-    return Fail(PB_INVALID_ARGUMENT,
-                "adaptive massless flow supports "
-                "DormandElMikkawyPrince1986RKN434FM and Fine1987RKNG34");
-  }
-  PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
-  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
+// The flow on device arrays.  The caller holds the workspace and the segments.
+pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
+                               const pb_adaptive_step_flow_t* flow,
+                               cudaStream_t stream) {
   AdaptiveParameters parameters;
   parameters.t_requested = flow->t_final;
   // FlowODEWithAdaptiveStep: t_final = min(t, t_max()) (after Prolong, which is
   // the facade's job here).
   parameters.t_final = std::min(flow->t_final, EphemerisTMax(e));
+  parameters.t_min = EphemerisTMin(e);
   parameters.length_integration_tolerance = flow->length_integration_tolerance;
   parameters.speed_integration_tolerance = flow->speed_integration_tolerance;
   parameters.max_steps = flow->max_steps;
@@ -71,56 +61,6 @@ pb_status_t pb_flow_with_adaptive_step_device(
   if (n_bodies > kMaxConstantBodies) {
     return Fail(PB_INVALID_ARGUMENT, "too many bodies for the flow kernel");
   }
-  static BodyScalars scalars;
-  for (int b = 0; b < n_bodies; ++b) {
-    DeviceBody const& body = e->model.bodies[b];
-    scalars.mu[b] = body.mu;
-    scalars.collision_radius[b] = body.collision_radius;
-    scalars.outer_threshold_degree_2[b] =
-        body.is_oblate && body.n_damping > 2
-            ? e->model.dampings[body.damping_offset + 2].outer_threshold
-            : -std::numeric_limits<double>::infinity();
-  }
-  PB_CUDA(cudaMemcpyToSymbolAsync(c_adaptive_bodies, &scalars, sizeof(scalars),
-                                  0, cudaMemcpyHostToDevice, stream));
-  PB_CUDA(cudaStreamSynchronize(stream));
-
-  // Execution order: decreasing estimated cost.
-  PB_RETURN_IF_ERROR(e->adaptive_cost.Reserve(2 * static_cast<std::size_t>(n)));
-  PB_RETURN_IF_ERROR(e->adaptive_order.Reserve(2 * static_cast<std::size_t>(n)));
-  PB_RETURN_IF_ERROR(e->adaptive_queue.Reserve(1));
-  float* const cost_in = e->adaptive_cost.data;
-  float* const cost_out = cost_in + n;
-  int* const index_in = e->adaptive_order.data;
-  int* const order = index_in + n;
-  std::size_t sort_bytes = 0;
-  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
-      nullptr, sort_bytes, cost_in, cost_out, index_in, order, n, 0, 32,
-      stream));
-  PB_RETURN_IF_ERROR(e->adaptive_sort_storage.Reserve(sort_bytes));
-  sort_bytes = e->adaptive_sort_storage.capacity;
-  AdaptiveCostKernel<<<(n + 127) / 128, 128, 0, stream>>>(
-      e->View(), parameters.t_final, flow->n, flow->state, flow->time, cost_in,
-      index_in);
-  PB_LAUNCHED();
-  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
-      e->adaptive_sort_storage.data, sort_bytes, cost_in, cost_out, index_in,
-      order, n, 0, 32, stream));
-  PB_CUDA(cudaMemsetAsync(e->adaptive_queue.data, 0,
-                          sizeof(unsigned long long), stream));
-  int sm_count = 0;
-  PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
-                                 e->device));
-  int const min_blocks = AdaptiveMinBlocks();
-  unsigned const blocks = static_cast<unsigned>(
-      std::min<long long>((flow->n + kAdaptiveThreads - 1) / kAdaptiveThreads,
-                          static_cast<long long>(sm_count) * min_blocks));
-  while (e->timing_events.size() < 2) {
-    cudaEvent_t event;
-    PB_CUDA(cudaEventCreate(&event));
-    e->timing_events.push_back(event);
-  }
-  PB_CUDA(cudaEventRecord(e->timing_events[0], stream));
   DownsamplerView sink{};
   if (flow->sink != nullptr) {
     sink = PbDownsamplerView(flow->sink);
@@ -129,6 +69,63 @@ pb_status_t pb_flow_with_adaptive_step_device(
                   "the sink must have one timeline per trajectory");
     }
   }
+  ConstantBankLease constants;
+  PB_RETURN_IF_ERROR(AdaptiveConstantBank().Acquire(
+      e->serial, 0, [&]() -> pb_status_t {
+        static BodyScalars scalars;
+        for (int b = 0; b < n_bodies; ++b) {
+          DeviceBody const& body = e->model.bodies[b];
+          scalars.mu[b] = body.mu;
+          scalars.collision_radius[b] = body.collision_radius;
+          scalars.outer_threshold_degree_2[b] =
+              body.is_oblate && body.n_damping > 2
+                  ? e->model.dampings[body.damping_offset + 2].outer_threshold
+                  : -std::numeric_limits<double>::infinity();
+        }
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_adaptive_bodies, &scalars,
+                                        sizeof(scalars), 0,
+                                        cudaMemcpyHostToDevice, stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        return PB_OK;
+      }));
+  constants.Adopt(&AdaptiveConstantBank());
+
+  // Execution order: decreasing estimated cost.
+  PB_RETURN_IF_ERROR(w->adaptive_cost.Reserve(2 * static_cast<std::size_t>(n)));
+  PB_RETURN_IF_ERROR(w->adaptive_order.Reserve(2 * static_cast<std::size_t>(n)));
+  PB_RETURN_IF_ERROR(w->adaptive_queue.Reserve(1));
+  float* const cost_in = w->adaptive_cost.data;
+  float* const cost_out = cost_in + n;
+  int* const index_in = w->adaptive_order.data;
+  int* const order = index_in + n;
+  std::size_t sort_bytes = 0;
+  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
+      nullptr, sort_bytes, cost_in, cost_out, index_in, order, n, 0, 32,
+      stream));
+  PB_RETURN_IF_ERROR(w->adaptive_sort_storage.Reserve(sort_bytes));
+  sort_bytes = w->adaptive_sort_storage.capacity;
+  AdaptiveCostKernel<<<(n + 127) / 128, 128, 0, stream>>>(
+      e->View(), parameters.t_final, flow->n, flow->state, flow->time, cost_in,
+      index_in);
+  PB_LAUNCHED();
+  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
+      w->adaptive_sort_storage.data, sort_bytes, cost_in, cost_out, index_in,
+      order, n, 0, 32, stream));
+  PB_CUDA(cudaMemsetAsync(w->adaptive_queue.data, 0,
+                          sizeof(unsigned long long), stream));
+  int sm_count = 0;
+  PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
+                                 e->device));
+  int const min_blocks = AdaptiveMinBlocks();
+  unsigned const blocks = static_cast<unsigned>(
+      std::min<long long>((flow->n + kAdaptiveThreads - 1) / kAdaptiveThreads,
+                          static_cast<long long>(sm_count) * min_blocks));
+  while (w->timing_events.size() < 2) {
+    cudaEvent_t event;
+    PB_CUDA(cudaEventCreate(&event));
+    w->timing_events.push_back(event);
+  }
+  PB_CUDA(cudaEventRecord(w->timing_events[0], stream));
   auto const kernel =
       flow->method == PB_FINE_1987_RKNG_34
           ? (min_blocks == 2 ? ErknFlowKernel<Fine1987RKNG34, 2>
@@ -137,114 +134,178 @@ pb_status_t pb_flow_with_adaptive_step_device(
                  ? ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 2>
                  : ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 3>);
   kernel<<<blocks, kAdaptiveThreads, 0, stream>>>(
-      e->View(), parameters, flow->n, order, e->adaptive_queue.data,
-      flow->state, flow->time, flow->status,
+      e->View(), parameters, flow->n, order, w->adaptive_queue.data,
+      e->stop_word_device, flow->state, flow->time, flow->status,
       reinterpret_cast<long long*>(flow->accepted_steps),
       reinterpret_cast<long long*>(flow->rejected_steps),
       reinterpret_cast<long long*>(flow->evaluations), flow->step_log,
       flow->state_log, sink, flow->burns);
   PB_LAUNCHED();
-  PB_CUDA(cudaEventRecord(e->timing_events[1], stream));
+  PB_CUDA(cudaEventRecord(w->timing_events[1], stream));
   PB_CUDA(cudaStreamSynchronize(stream));
   float elapsed = 0;
-  PB_CUDA(cudaEventElapsedTime(&elapsed, e->timing_events[0],
-                               e->timing_events[1]));
-  e->last_flow_kernel_ms = elapsed;
-  e->last_flow_kernel_launches = 1;
-  return PB_OK;
+  PB_CUDA(cudaEventElapsedTime(&elapsed, w->timing_events[0],
+                               w->timing_events[1]));
+  {
+    std::lock_guard<std::mutex> const lock(e->statistics_mutex);
+    e->last_flow_kernel_ms = elapsed;
+    e->last_flow_kernel_launches = 1;
+  }
+  // RETURN_IF_STOPPED (embedded_explicit_runge_kutta_nyström_integrator_body
+  // .hpp:243): the trajectories that were cut short carry PB_CANCELLED in their
+  // status and the state of their last accepted step.
+  return e->stop_requested.load() != 0 ? Fail(PB_CANCELLED, "stop requested")
+                                       : PB_OK;
 }
 
-pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
-                                       const pb_adaptive_step_flow_t* flow) {
-  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
+pb_status_t ValidateAdaptiveFlow(pb_ephemeris_t* e,
+                                 const pb_adaptive_step_flow_t* flow) {
   if (e == nullptr || flow == nullptr || flow->n < 0 ||
       (flow->n > 0 && (flow->state == nullptr || flow->time == nullptr))) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
   }
-  PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
-  std::size_t const n = static_cast<std::size_t>(flow->n);
-  DeviceBuffer<double> state, time, step_log, state_log;
-  DeviceBuffer<int32_t> status;
-  DeviceBuffer<long long> counters;
-  PB_RETURN_IF_ERROR(state.Upload(flow->state, 12 * n, stream));
-  PB_RETURN_IF_ERROR(time.Upload(flow->time, 2 * n, stream));
-  PB_RETURN_IF_ERROR(status.Reserve(n + 1));
-  PB_RETURN_IF_ERROR(counters.Reserve(3 * n + 1));
-  pb_adaptive_step_flow_t device_flow = *flow;
-  DeviceBuffer<double> burns;
-  if (flow->burns != nullptr) {
-    PB_RETURN_IF_ERROR(burns.Upload(flow->burns, PB_BURN_PLANES * n, stream));
-    device_flow.burns = burns.data;
+  if (flow->method != PB_DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM &&
+      flow->method != PB_FINE_1987_RKNG_34) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "adaptive massless flow supports "
+                "DormandElMikkawyPrince1986RKN434FM and Fine1987RKNG34");
   }
-  device_flow.state = state.data;
-  device_flow.time = time.data;
-  device_flow.status = status.data;
-  device_flow.accepted_steps = reinterpret_cast<int64_t*>(counters.data);
-  device_flow.rejected_steps = reinterpret_cast<int64_t*>(counters.data + n);
-  device_flow.evaluations = reinterpret_cast<int64_t*>(counters.data + 2 * n);
+  // AdaptiveStepParameters: CHECK_LT(0, max_steps), tolerances positive
+  // (physics/ephemeris_body.hpp:62-75).
+  if (!(flow->max_steps > 0)) {
+    return Fail(PB_INVALID_ARGUMENT, "CHECK_LT(0, max_steps)");
+  }
+  if (!(flow->length_integration_tolerance > 0) ||
+      !(flow->speed_integration_tolerance > 0)) {
+    return Fail(PB_INVALID_ARGUMENT, "the tolerances must be positive");
+  }
+  if (flow->t_final != flow->t_final) {
+    return Fail(PB_INVALID_ARGUMENT, "NaN time");
+  }
+  return PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+pb_status_t pb_flow_with_adaptive_step_device(
+    pb_ephemeris_t* e, const pb_adaptive_step_flow_t* flow,
+    void* stream_pointer) {
+  PB_API_RANGE();
+  PB_RETURN_IF_ERROR(ValidateAdaptiveFlow(e, flow));
+  PB_CUDA(cudaSetDevice(e->device));
+  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
+  WorkspaceLease w;
+  PB_RETURN_IF_ERROR(w.Acquire(e, true, stream));
+  SegmentsReadLock segments;
+  PB_RETURN_IF_ERROR(segments.Acquire(e));
+  return AdaptiveFlowDevice(e, w.get(), flow, stream);
+}
+
+pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
+                                       const pb_adaptive_step_flow_t* flow) {
+  PB_API_RANGE();
+  PB_RETURN_IF_ERROR(ValidateAdaptiveFlow(e, flow));
+  PB_CUDA(cudaSetDevice(e->device));
+  WorkspaceLease w;
+  PB_RETURN_IF_ERROR(w.Acquire(e, false, nullptr));
+  SegmentsReadLock segments;
+  PB_RETURN_IF_ERROR(segments.Acquire(e));
+  cudaStream_t const stream = w.stream();
+  std::size_t const n = static_cast<std::size_t>(flow->n);
+  // The workspace's grow-only scratch: scratch_a the state (12 n) and the times
+  // (2 n), scratch_b the step log, scratch_c the state log, counters the three
+  // per-trajectory counts and (as 32-bit words behind them) the statuses.
+  PB_RETURN_IF_ERROR(w->scratch_a.Reserve(14 * n + 1));
+  PB_RETURN_IF_ERROR(w->counters.Reserve(4 * n + 1));
+  double* const state = w->scratch_a.data;
+  double* const time = state + 12 * n;
+  long long* const counters = w->counters.data;
+  int32_t* const status = reinterpret_cast<int32_t*>(counters + 3 * n);
+  if (n > 0) {
+    PB_CUDA(cudaMemcpyAsync(state, flow->state, 12 * n * sizeof(double),
+                            cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemcpyAsync(time, flow->time, 2 * n * sizeof(double),
+                            cudaMemcpyHostToDevice, stream));
+  }
+  pb_adaptive_step_flow_t device_flow = *flow;
+  if (flow->burns != nullptr) {
+    PB_RETURN_IF_ERROR(
+        w->burns_scratch.Upload(flow->burns, PB_BURN_PLANES * n, stream));
+    device_flow.burns = w->burns_scratch.data;
+  }
+  device_flow.state = state;
+  device_flow.time = time;
+  device_flow.status = status;
+  device_flow.accepted_steps = reinterpret_cast<int64_t*>(counters);
+  device_flow.rejected_steps = reinterpret_cast<int64_t*>(counters + n);
+  device_flow.evaluations = reinterpret_cast<int64_t*>(counters + 2 * n);
   bool const logging = flow->step_log != nullptr && flow->step_log_capacity > 0;
   if (logging) {
     std::size_t const size = static_cast<std::size_t>(flow->step_log_capacity) * n;
-    PB_RETURN_IF_ERROR(step_log.Upload(flow->step_log, size, stream));
-    device_flow.step_log = step_log.data;
+    PB_RETURN_IF_ERROR(w->scratch_b.Upload(flow->step_log, size, stream));
+    device_flow.step_log = w->scratch_b.data;
   } else {
     device_flow.step_log = nullptr;
   }
   bool const logging_states =
       flow->state_log != nullptr && flow->step_log_capacity > 0;
   if (logging_states) {
-    PB_RETURN_IF_ERROR(state_log.Reserve(
+    PB_RETURN_IF_ERROR(w->scratch_c.Reserve(
         static_cast<std::size_t>(flow->step_log_capacity) * 6 * n));
-    device_flow.state_log = state_log.data;
+    device_flow.state_log = w->scratch_c.data;
   } else {
     device_flow.state_log = nullptr;
   }
   if (!logging && !logging_states) {
     device_flow.step_log_capacity = 0;
   }
-  PB_RETURN_IF_ERROR(
-      pb_flow_with_adaptive_step_device(e, &device_flow, stream));
+  pb_status_t const result =
+      AdaptiveFlowDevice(e, w.get(), &device_flow, stream);
+  if (result != PB_OK && result != PB_CANCELLED) {
+    return result;
+  }
   if (n > 0) {
-    PB_CUDA(cudaMemcpyAsync(flow->state, state.data, 12 * n * sizeof(double),
+    PB_CUDA(cudaMemcpyAsync(flow->state, state, 12 * n * sizeof(double),
                             cudaMemcpyDeviceToHost, stream));
-    PB_CUDA(cudaMemcpyAsync(flow->time, time.data, 2 * n * sizeof(double),
+    PB_CUDA(cudaMemcpyAsync(flow->time, time, 2 * n * sizeof(double),
                             cudaMemcpyDeviceToHost, stream));
     if (flow->status != nullptr) {
-      PB_CUDA(cudaMemcpyAsync(flow->status, status.data, n * sizeof(int32_t),
+      PB_CUDA(cudaMemcpyAsync(flow->status, status, n * sizeof(int32_t),
                               cudaMemcpyDeviceToHost, stream));
     }
     if (flow->accepted_steps != nullptr) {
-      PB_CUDA(cudaMemcpyAsync(flow->accepted_steps, counters.data,
+      PB_CUDA(cudaMemcpyAsync(flow->accepted_steps, counters,
                               n * sizeof(int64_t), cudaMemcpyDeviceToHost,
                               stream));
     }
     if (flow->rejected_steps != nullptr) {
-      PB_CUDA(cudaMemcpyAsync(flow->rejected_steps, counters.data + n,
+      PB_CUDA(cudaMemcpyAsync(flow->rejected_steps, counters + n,
                               n * sizeof(int64_t), cudaMemcpyDeviceToHost,
                               stream));
     }
     if (flow->evaluations != nullptr) {
-      PB_CUDA(cudaMemcpyAsync(flow->evaluations, counters.data + 2 * n,
+      PB_CUDA(cudaMemcpyAsync(flow->evaluations, counters + 2 * n,
                               n * sizeof(int64_t), cudaMemcpyDeviceToHost,
                               stream));
     }
     if (logging) {
       PB_CUDA(cudaMemcpyAsync(
-          flow->step_log, step_log.data,
+          flow->step_log, w->scratch_b.data,
           static_cast<std::size_t>(flow->step_log_capacity) * n * sizeof(double),
           cudaMemcpyDeviceToHost, stream));
     }
     if (logging_states) {
       PB_CUDA(cudaMemcpyAsync(
-          flow->state_log, state_log.data,
+          flow->state_log, w->scratch_c.data,
           static_cast<std::size_t>(flow->step_log_capacity) * 6 * n *
               sizeof(double),
           cudaMemcpyDeviceToHost, stream));
     }
   }
   PB_CUDA(cudaStreamSynchronize(stream));
-  return PB_OK;
+  return result;
 }
 
 }  // extern "C"

@@ -60,6 +60,11 @@ bool MakeMultistepMethod(int32_t const method, MultistepMethod& m) {
 
 struct pb_nbody_ensemble {
   pb_ephemeris* ephemeris = nullptr;
+  int device = 0;
+  // The ensemble's own non-blocking stream: distinct ensembles flow
+  // concurrently.  One Solve at a time per ensemble.
+  cudaStream_t stream = nullptr;
+  std::mutex mutex;
   int32_t method = 0;
   bool is_multistep = false;
   SrknTableau tableau;          // The method itself, or the SRKN14A starter.
@@ -232,6 +237,7 @@ pb_status_t pb_nbody_ensemble_create(pb_ephemeris_t* e, int32_t method,
   PB_CUDA(cudaSetDevice(e->device));
   auto* s = new pb_nbody_ensemble;
   s->ephemeris = e;
+  s->device = e->device;
   s->method = method;
   s->step = step;
   s->n_systems = n_systems;
@@ -257,17 +263,31 @@ pb_status_t pb_nbody_ensemble_create(pb_ephemeris_t* e, int32_t method,
   if (status == PB_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) {
     status = Fail(PB_INTERNAL, "upload failed");
   }
+  if (status == PB_OK &&
+      cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) !=
+          cudaSuccess) {
+    status = Fail(PB_INTERNAL, "stream creation failed");
+  }
   if (status != PB_OK) {
     delete s;
     return status;
   }
+  e->dependants.fetch_add(1);
   *ensemble = s;
   return PB_OK;
 }
 
 void pb_nbody_ensemble_destroy(pb_nbody_ensemble_t* ensemble) {
+  PB_API_RANGE();
   if (ensemble != nullptr) {
-    cudaSetDevice(ensemble->ephemeris->device);
+    // The ensemble's own copy of the ordinal; the ephemeris outlives its
+    // dependants (pb_ephemeris_destroy refuses otherwise).
+    cudaSetDevice(ensemble->device);
+    if (ensemble->stream != nullptr) {
+      cudaStreamSynchronize(ensemble->stream);
+      cudaStreamDestroy(ensemble->stream);
+    }
+    ensemble->ephemeris->dependants.fetch_sub(1);
     delete ensemble;
   }
 }
@@ -314,12 +334,21 @@ static pb_status_t RecordStep(pb_nbody_ensemble* s, EnsembleRecorder* recorder,
 static pb_status_t SolveEnsemble(pb_nbody_ensemble* s, double t_final,
                                  int64_t* n_steps,
                                  EnsembleRecorder* recorder) {
-  PB_CUDA(cudaSetDevice(s->ephemeris->device));
-  cudaStream_t const stream = nullptr;
+  PB_CUDA(cudaSetDevice(s->device));
+  cudaStream_t const stream = s->stream;
   int64_t steps = 0;
   double const h = s->step;
+  // A full recorder, or a stop request (RETURN_IF_STOPPED after every step,
+  // symmetric_linear_multistep_integrator_body.hpp:149): either way Solve
+  // returns with the state of the last completed step.
   auto full = [&] {
-    return recorder != nullptr && recorder->count >= recorder->capacity;
+    return (recorder != nullptr && recorder->count >= recorder->capacity) ||
+           s->ephemeris->stop_requested.load() != 0;
+  };
+  auto result = [&]() -> pb_status_t {
+    return s->ephemeris->stop_requested.load() != 0
+               ? Fail(PB_CANCELLED, "stop requested")
+               : PB_OK;
   };
   if (!s->is_multistep) {
     // SymplecticRungeKuttaNyströmIntegrator::Instance::Solve.
@@ -363,7 +392,7 @@ static pb_status_t SolveEnsemble(pb_nbody_ensemble* s, double t_final,
         if (n_steps != nullptr) {
           *n_steps = steps;
         }
-        return PB_OK;
+        return result();
       }
       s->startup_target_valid = false;
       if (s->previous_steps < order) {
@@ -371,7 +400,7 @@ static pb_status_t SolveEnsemble(pb_nbody_ensemble* s, double t_final,
         if (n_steps != nullptr) {
           *n_steps = steps;
         }
-        return PB_OK;  // "we'll continue the next time Solve is called".
+        return result();  // "we'll continue the next time Solve is called".
       }
       s->oldest = 0;
     }
@@ -385,14 +414,16 @@ static pb_status_t SolveEnsemble(pb_nbody_ensemble* s, double t_final,
   if (n_steps != nullptr) {
     *n_steps = steps;
   }
-  return PB_OK;
+  return result();
 }
 
 pb_status_t pb_nbody_ensemble_solve(pb_nbody_ensemble_t* s, double t_final,
                                     int64_t* n_steps) {
+  PB_API_RANGE();
   if (s == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null ensemble");
   }
+  std::lock_guard<std::mutex> const lock(s->mutex);
   return SolveEnsemble(s, t_final, n_steps, nullptr);
 }
 
@@ -404,6 +435,8 @@ pb_status_t pb_nbody_ensemble_solve_recording(pb_nbody_ensemble_t* s,
       states == nullptr || n_recorded == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
   }
+  PB_API_RANGE();
+  std::lock_guard<std::mutex> const lock(s->mutex);
   EnsembleRecorder recorder{capacity, times, states, 0};
   pb_status_t const status = SolveEnsemble(s, t_final, nullptr, &recorder);
   *n_recorded = recorder.count;
@@ -422,13 +455,15 @@ pb_status_t pb_nbody_ensemble_solve_to_trajectories(
     return Fail(PB_INVALID_ARGUMENT,
                 "one trajectory per body of every system is needed");
   }
-  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  PB_API_RANGE();
+  std::lock_guard<std::mutex> const lock(s->mutex);
+  PB_CUDA(cudaSetDevice(s->device));
   if (ContinuousTrajectoriesEmpty(trajectories)) {
     // The initial state, as the Ephemeris constructor appends it
     // (ephemeris_body.hpp:136).
     PB_RETURN_IF_ERROR(ContinuousTrajectoriesAppendDevice(
         trajectories, s->time.value, s->state.data, s->state.data + 6 * plane,
-        nullptr));
+        s->stream));
   }
   EnsembleRecorder recorder{std::numeric_limits<int64_t>::max(), nullptr,
                             nullptr, 0, trajectories};
@@ -444,7 +479,8 @@ pb_status_t pb_nbody_ensemble_get_state(pb_nbody_ensemble_t* s, double* state,
   if (s == nullptr || state == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null argument");
   }
-  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  std::lock_guard<std::mutex> const lock(s->mutex);
+  PB_CUDA(cudaSetDevice(s->device));
   std::size_t const size = 12 * static_cast<std::size_t>(s->n_bodies) *
                            static_cast<std::size_t>(s->n_systems);
   PB_CUDA(cudaMemcpy(state, s->state.data, size * sizeof(double),

@@ -36,7 +36,7 @@ __device__ __forceinline__ int32_t AccelerationOnMasslessBodyAtTime(
     DeviceBody const& body1 = e.bodies[b1];
     double const mu1 = body1.mu;
     int const begin = e.segment_offset[b1];
-    int const end = e.segment_offset[b1 + 1];
+    int const end = e.segment_end[b1];
     int segment = begin + hint;
     // First segment with t <= t_max (continuous_trajectory_body.hpp:860-885).
     if (!(segment < end && t <= e.segment_t_max[segment] &&
@@ -66,6 +66,7 @@ __device__ __forceinline__ int32_t AccelerationOnMasslessBodyAtTime(
 struct AdaptiveParameters {
   double t_requested;  // The caller's t.
   double t_final;      // min(t, t_max of the ephemeris).
+  double t_min;        // Of the ephemeris.
   double length_integration_tolerance;
   double speed_integration_tolerance;
   long long max_steps;
@@ -123,7 +124,7 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
   if (uniform) {
     // One lookup for all bodies: first segment with t <= t_max
     // (continuous_trajectory_body.hpp:860-885).
-    int const end = __ldg(e.segment_offset + 1);
+    int const end = __ldg(e.segment_end);
     if (!(hint < end && t <= __ldg(e.segment_t_max + hint) &&
           (hint == 0 || __ldg(e.segment_t_max + hint - 1) < t))) {
       hint = FindSegment(e.segment_t_max, 0, end, t);
@@ -134,7 +135,7 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
     int const begin = __ldg(e.segment_offset + b1);
     int segment = begin + hint;
     if (!uniform) {
-      int const end = __ldg(e.segment_offset + b1 + 1);
+      int const end = __ldg(e.segment_end + b1);
       if (!(segment < end && t <= __ldg(e.segment_t_max + segment) &&
             (segment == begin || __ldg(e.segment_t_max + segment - 1) < t))) {
         segment = FindSegment(e.segment_t_max, begin, end, t);
@@ -213,7 +214,7 @@ static __global__ void AdaptiveCostKernel(EphemerisView const e,
   Vec3 best_dq{0.0, 0.0, 0.0}, best_dv{0.0, 0.0, 0.0};
   for (int b = 0; b < e.n_bodies; ++b) {
     int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
-                                    e.segment_offset[b + 1], t);
+                                    e.segment_end[b], t);
     Vec3 const p0 = EvaluateSegment(e, segment, t);
     Vec3 const dq = q - p0;
     double const r2 = Norm2(dq);
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(kAdaptiveThreads, kMinBlocks)
 ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                long long const n, int const* __restrict__ order,
                unsigned long long* __restrict__ queue,
+               int32_t const* __restrict__ stop_word,
                double* __restrict__ state, double* __restrict__ time,
                int32_t* __restrict__ status_out,
                long long* __restrict__ accepted_out,
@@ -359,7 +361,19 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
       tolerance_to_error_ratio = 0.0;
       busy = true;
       // FlowODEWithAdaptiveStep, ephemeris_body.hpp:1634-1637.
-      if (t.value == parameters.t_requested) {
+      if (*reinterpret_cast<int32_t const volatile*>(stop_word) != 0) {
+        // RETURN_IF_STOPPED before the first step: the trajectory is left
+        // where it was.
+        final_status = PB_CANCELLED;
+        finished = true;
+        flowed = false;
+      } else if (t.value == parameters.t_requested) {
+        finished = true;
+        flowed = false;
+      } else if (!(t.value >= parameters.t_min)) {
+        // CHECK_LE(t_min(), time) in
+        // ContinuousTrajectory::EvaluatePositionLocked (also a NaN time).
+        final_status = PB_INVALID_ARGUMENT;
         finished = true;
         flowed = false;
       } else {
@@ -499,6 +513,14 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
         } else if (accepted == parameters.max_steps) {
           final_status = PB_RESOURCE_EXHAUSTED;  // ReachedMaximalStepCount.
           finished = true;
+        } else if (*reinterpret_cast<int32_t const volatile*>(stop_word) !=
+                   0) {
+          // RETURN_IF_STOPPED after the step,
+          // embedded_explicit_runge_kutta_nyström_integrator_body.hpp:243: the
+          // state is that of the last accepted step.
+          final_status = PB_CANCELLED;
+          finished = true;
+          flowed = false;
         }
       }
     }

@@ -88,24 +88,36 @@ struct AllPairsForceView {
 // One interaction with the reference's operations (the branch-free correctly
 // rounded square root and division of pb_math.cuh).
 struct ExactInteraction {
+  // kMaybeSelf: the source may be the target itself; its interaction is
+  // computed and discarded by a select, so that the loop has no branch (its
+  // Δq is exactly zero, so a zero factor makes its addends +0.0, which leave
+  // the sums unchanged).  Stages that cannot contain the target run without
+  // the test and the select.
+  template<bool kMaybeSelf>
   __device__ __forceinline__ static void Accumulate(
       double const sx, double const sy, double const sz, double const smu,
       double const xi, double const yi, double const zi, bool const is_self,
       bool& in_range, double& ax, double& ay, double& az) {
     // Δq = position of the source - position of the target: the acceleration
-    // on b2 = i due to b1 = j.  The self-interaction is computed and discarded
-    // by a select, so that the loop has no branch.
+    // on b2 = i due to b1 = j.
     double const dx = sx - xi;
     double const dy = sy - yi;
     double const dz = sz - zi;
     double const d2 = dx * dx + dy * dy + dz * dz;
-    in_range = in_range && (InFastRange(d2) || is_self);
+    if constexpr (kMaybeSelf) {
+      in_range = in_range && (InFastRange(d2) || is_self);
+    } else {
+      in_range = in_range && InFastRange(d2);
+    }
     double const d = FastSqrt(d2);
     double const one_over_d3 = FastDivide(d, d2 * d2);
-    double const mu_over_d3 = is_self ? 0.0 : smu * one_over_d3;
-    ax += is_self ? 0.0 : dx * mu_over_d3;
-    ay += is_self ? 0.0 : dy * mu_over_d3;
-    az += is_self ? 0.0 : dz * mu_over_d3;
+    double mu_over_d3 = smu * one_over_d3;
+    if constexpr (kMaybeSelf) {
+      mu_over_d3 = is_self ? 0.0 : mu_over_d3;
+    }
+    ax += dx * mu_over_d3;
+    ay += dy * mu_over_d3;
+    az += dz * mu_over_d3;
   }
   // The IEEE operators, for the targets that met a distance outside the range
   // of the branch-free ones.
@@ -132,6 +144,7 @@ struct ExactInteraction {
 // per interaction instead of 40.  Not bit-identical to the reference; within
 // BASELINE.json's tolerance (tests/test_gpu_contracted.py).
 struct ContractedInteraction {
+  template<bool kMaybeSelf>
   __device__ __forceinline__ static void Accumulate(
       double const sx, double const sy, double const sz, double const smu,
       double const xi, double const yi, double const zi, bool const is_self,
@@ -140,14 +153,20 @@ struct ContractedInteraction {
     double const dy = sy - yi;
     double const dz = sz - zi;
     double const d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    in_range = in_range && (InFastRange(d2) || is_self);
+    if constexpr (kMaybeSelf) {
+      in_range = in_range && (InFastRange(d2) || is_self);
+    } else {
+      in_range = in_range && InFastRange(d2);
+    }
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(d2));
     double const e = fma(d2 * y0, -y0, 1.0);
     double const p = fma(e, 0.375, 0.5);
     double const y1 = fma(p, y0 * e, y0);
-    double const one_over_d3 = y1 * y1 * y1;
-    double const mu_over_d3 = is_self ? 0.0 : smu * one_over_d3;
+    double mu_over_d3 = smu * (y1 * y1 * y1);
+    if constexpr (kMaybeSelf) {
+      mu_over_d3 = is_self ? 0.0 : mu_over_d3;
+    }
     ax = fma(dx, mu_over_d3, ax);
     ay = fma(dy, mu_over_d3, ay);
     az = fma(dz, mu_over_d3, az);
@@ -235,20 +254,26 @@ AllPairsAccelerationKernel(AllPairsForceView const v) {
                          : -1;
     double2 const* const stage = reinterpret_cast<double2 const*>(
         stages + slot * kApStageSources * kApSourceDoubles);
-    if (count == kApStageSources) {
+    // `self` differs between the lanes, but a stage holds the target of every
+    // lane or of none when the tile lies inside it, and of no lane in all the
+    // other stages: the vote keeps the warp on one path.
+    if (count == kApStageSources && __all_sync(0xffffffffu, self < 0)) {
 #pragma unroll 4
       for (int jj = 0; jj < kApStageSources; ++jj) {
         double2 const xy = stage[2 * jj];
         double2 const zm = stage[2 * jj + 1];
-        Interaction::Accumulate(xy.x, xy.y, zm.x, zm.y, xi, yi, zi, jj == self,
-                                in_range, ax, ay, az);
+        Interaction::template Accumulate<false>(xy.x, xy.y, zm.x, zm.y, xi, yi,
+                                                zi, false, in_range, ax, ay,
+                                                az);
       }
     } else {
+#pragma unroll 2
       for (int jj = 0; jj < count; ++jj) {
         double2 const xy = stage[2 * jj];
         double2 const zm = stage[2 * jj + 1];
-        Interaction::Accumulate(xy.x, xy.y, zm.x, zm.y, xi, yi, zi, jj == self,
-                                in_range, ax, ay, az);
+        Interaction::template Accumulate<true>(xy.x, xy.y, zm.x, zm.y, xi, yi,
+                                               zi, jj == self, in_range, ax,
+                                               ay, az);
       }
     }
     // Every lane has read the stage: it may be refilled.

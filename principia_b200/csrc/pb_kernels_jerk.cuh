@@ -36,7 +36,7 @@ static __global__ void VelocityTableKernel(EphemerisView const e,
     return;
   }
   int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
-                                  e.segment_offset[b + 1], t);
+                                  e.segment_end[b], t);
   Vec3 const v = EvaluateSegmentDerivative(e, segment, t);
   velocities[3 * b] = v.x;
   velocities[3 * b + 1] = v.y;

@@ -61,15 +61,24 @@ struct EphemerisView {
   // Legendre normalisation factors, (n, m) -> n(n+1)/2 + m.
   double const* normalization;
   // ContinuousTrajectory segments, per body [segment_offset[b],
-  // segment_offset[b + 1]).
+  // segment_end[b]).
   int32_t const* segment_offset;
+  int32_t const* segment_end;
   double const* segment_t_max;
   double const* segment_origin;
   int32_t const* segment_degree;
   // [segment][xyz][18]: the host API's [segment][18][3] transposed, so that the
   // coefficients of one coordinate are contiguous (16-byte loads of pairs).
   double const* segment_coefficients;
+  // Where a flow kernel reports the code paths it took (kPathGenericHarmonics),
+  // or null.
+  int32_t* path_flags;
 };
+
+// Set in *EphemerisView::path_flags by a flow kernel when some probe evaluated
+// harmonics of degree > 3 of a body other than the hot one (the
+// thread-local-memory path: same bits, several times slower).
+constexpr int32_t kPathGenericHarmonics = 0x100;
 
 // Layout of one entry of a stage table (all bodies evaluated at one time):
 //   [0, 3 n_bodies)            positions, body-major xyz, internal order;

@@ -4,10 +4,15 @@
 
 #include <cuda_runtime.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -32,14 +37,79 @@ inline std::uint64_t NextSerial() {
   return ++serial;
 }
 
-// The flow entry points share the constant bank of their kernels (per-body
-// scalars, hot-body tables) and the scratch buffers of the ephemeris: they are
-// serialised.  (The reference lets flows on distinct objects run concurrently,
-// ephemeris.hpp:64-66; here concurrency is inside a call, across the probes.)
-inline std::recursive_mutex& FlowMutex() {
-  static std::recursive_mutex mutex;
-  return mutex;
-}
+// An NVTX range per C-ABI call (nsys / ncu timelines name the entry points).
+struct ApiRange {
+  explicit ApiRange(char const* const name) { nvtxRangePushA(name); }
+  ~ApiRange() { nvtxRangePop(); }
+  ApiRange(ApiRange const&) = delete;
+  ApiRange& operator=(ApiRange const&) = delete;
+};
+#define PB_API_RANGE() ::pb::ApiRange const pb_api_range(__func__)
+
+// A bank of __constant__ tables that several kernels of one translation unit
+// read as instruction operands (per-body scalars, the hot body's harmonics).
+// Calls that need the same contents (the same ephemeris, the same hot body)
+// share it and run concurrently; a call that needs other contents waits until
+// no kernel that reads the current ones is in flight (every reader
+// synchronises its stream before it releases the bank), then rewrites it.
+class ConstantBank {
+ public:
+  // `upload` copies the tables to the symbols and synchronises; it runs under
+  // the bank's lock, only when the contents change.
+  template<typename Upload>
+  pb_status_t Acquire(std::uint64_t const ephemeris_serial, int const variant,
+                      Upload&& upload) {
+    std::unique_lock<std::mutex> lock(mutex_);
+    changed_.wait(lock, [&] {
+      return readers_ == 0 ||
+             (valid_ && serial_ == ephemeris_serial && variant_ == variant);
+    });
+    if (!(valid_ && serial_ == ephemeris_serial && variant_ == variant)) {
+      valid_ = false;
+      pb_status_t const status = upload();
+      if (status != PB_OK) {
+        return status;
+      }
+      valid_ = true;
+      serial_ = ephemeris_serial;
+      variant_ = variant;
+    }
+    ++readers_;
+    return PB_OK;
+  }
+  void Release() {
+    std::lock_guard<std::mutex> const lock(mutex_);
+    if (--readers_ == 0) {
+      changed_.notify_all();
+    }
+  }
+
+ private:
+  std::mutex mutex_;
+  std::condition_variable changed_;
+  bool valid_ = false;
+  std::uint64_t serial_ = 0;
+  int variant_ = 0;
+  int readers_ = 0;
+};
+
+// Releases a ConstantBank on scope exit.
+class ConstantBankLease {
+ public:
+  ConstantBankLease() = default;
+  ~ConstantBankLease() {
+    if (bank_ != nullptr) {
+      bank_->Release();
+    }
+  }
+  ConstantBankLease(ConstantBankLease const&) = delete;
+  ConstantBankLease& operator=(ConstantBankLease const&) = delete;
+  void Adopt(ConstantBank* const bank) { bank_ = bank; }
+  bool held() const { return bank_ != nullptr; }
+
+ private:
+  ConstantBank* bank_ = nullptr;
+};
 
 inline pb_status_t Fail(pb_status_t const status, std::string const& message) {
   LastError() = message;
@@ -101,6 +171,15 @@ struct DeviceBuffer {
     return PB_OK;
   }
 
+  void Swap(DeviceBuffer& other) {
+    T* const d = data;
+    std::size_t const c = capacity;
+    data = other.data;
+    capacity = other.capacity;
+    other.data = d;
+    other.capacity = c;
+  }
+
   pb_status_t Upload(T const* const host, std::size_t const n,
                      cudaStream_t const stream) {
     PB_RETURN_IF_ERROR(Reserve(n));
@@ -150,55 +229,58 @@ struct HostTrajectory {
   std::vector<double> t_max;
   std::vector<double> origin;
   std::vector<int32_t> degree;
-  std::vector<double> coefficients;  // [segment][18][3].
+  // [segment][xyz][18]: the device layout (the host API's [segment][18][3]
+  // transposed), the slots above the degree holding -0.0.
+  std::vector<double> coefficients;
 };
 
 }  // namespace pb
 
-// The opaque handle of the C ABI.
-struct pb_ephemeris {
-  int device = 0;
-  // Distinguishes handles whose storage the allocator reuses (caches of
-  // constant-bank uploads are keyed by it).
-  std::uint64_t const serial = pb::NextSerial();
-  pb::HostModel model;
-  std::vector<pb::HostTrajectory> trajectories;  // Internal order.
-  bool segments_dirty = true;
-  bool uniform_segments = false;  // Set by UploadSegments.
+namespace pb {
 
-  pb::DeviceBuffer<pb::DeviceBody> bodies;
-  pb::DeviceBuffer<pb::Damping> dampings;
-  pb::DeviceBuffer<double> cos, sin, normalization;
-  pb::DeviceBuffer<int32_t> segment_offset;
-  pb::DeviceBuffer<double> segment_t_max, segment_origin, segment_coefficients;
-  pb::DeviceBuffer<int32_t> segment_degree;
+// Everything one call on an ephemeris needs besides the ephemeris itself:
+// scratch buffers, staging, events, helper streams.  Calls lease a workspace
+// from the ephemeris' pool for their duration, so that calls on distinct
+// objects (two flows, a flow and a query) run concurrently
+// (physics/ephemeris.hpp:64-66).
+struct FlowWorkspace {
+  // The stream of the host-pointer entry points (the *_device ones run on the
+  // caller's).  Non-blocking: it does not synchronise with the legacy default
+  // stream.
+  cudaStream_t stream = nullptr;
+  // Recorded on the stream of the last user when the lease ends; the next user
+  // makes its stream wait for it (the asynchronous *_device queries return
+  // while their kernels still read the scratch).
+  cudaEvent_t last_use = nullptr;
+  bool used = false;
 
-  // Scratch.
-  pb::DeviceBuffer<double> stage_times;
-  pb::DeviceBuffer<double> stage_table;
-  pb::DeviceBuffer<double> scratch_a, scratch_b, scratch_c;
-  pb::DeviceBuffer<double> burns_scratch;
-  pb::DeviceBuffer<int32_t> status_word;
-  pb::DeviceBuffer<long long> counters;
-  pb::PinnedBuffer<double> pinned_times;
-  pb::PinnedBuffer<int32_t> pinned_status;
+  DeviceBuffer<double> stage_times;
+  DeviceBuffer<double> stage_table;
+  DeviceBuffer<double> scratch_a, scratch_b, scratch_c;
+  DeviceBuffer<double> burns_scratch;
+  // [0]: OR of the right-hand-side status codes; [1]: path flags
+  // (kPathGenericHarmonics).
+  DeviceBuffer<int32_t> status_word;
+  DeviceBuffer<long long> counters;
+  PinnedBuffer<double> pinned_times;
+  PinnedBuffer<int32_t> pinned_status;
 
   // Adaptive flow: scheduling keys, execution order, sort storage, queue head.
-  pb::DeviceBuffer<float> adaptive_cost;
-  pb::DeviceBuffer<int> adaptive_order;
-  pb::DeviceBuffer<unsigned char> adaptive_sort_storage;
-  pb::DeviceBuffer<unsigned long long> adaptive_queue;
+  DeviceBuffer<float> adaptive_cost;
+  DeviceBuffer<int> adaptive_order;
+  DeviceBuffer<unsigned char> adaptive_sort_storage;
+  DeviceBuffer<unsigned long long> adaptive_queue;
 
-  // CUDA-event timing of the dominant kernel of the last flow call.
+  // CUDA-event timing of the dominant kernel of a flow call.
   std::vector<cudaEvent_t> timing_events;
-  double last_flow_kernel_ms = 0;
-  std::int64_t last_flow_kernel_launches = 0;
-
   // Helper streams of the sliced flow launches and their join events.
   std::vector<cudaStream_t> flow_streams;
   std::vector<cudaEvent_t> flow_events;
 
-  ~pb_ephemeris() {
+  FlowWorkspace() = default;
+  FlowWorkspace(FlowWorkspace const&) = delete;
+  FlowWorkspace& operator=(FlowWorkspace const&) = delete;
+  ~FlowWorkspace() {
     for (cudaEvent_t event : timing_events) {
       cudaEventDestroy(event);
     }
@@ -207,6 +289,83 @@ struct pb_ephemeris {
     }
     for (cudaStream_t helper : flow_streams) {
       cudaStreamDestroy(helper);
+    }
+    if (last_use != nullptr) {
+      cudaEventDestroy(last_use);
+    }
+    if (stream != nullptr) {
+      cudaStreamDestroy(stream);
+    }
+  }
+};
+
+}  // namespace pb
+
+// The opaque handle of the C ABI.
+struct pb_ephemeris {
+  int device = 0;
+  // Distinguishes handles whose storage the allocator reuses (the constant
+  // banks are keyed by it).
+  std::uint64_t const serial = pb::NextSerial();
+  pb::HostModel model;
+
+  // The ContinuousTrajectory segments: host copy (internal order) and device
+  // arrays.  Readers (flows, queries) hold `segments_mutex` shared for the
+  // whole call; pb_ephemeris_append_segments and the upload hold it exclusive.
+  mutable std::shared_mutex segments_mutex;
+  std::vector<pb::HostTrajectory> trajectories;
+  bool segments_dirty = true;
+  bool uniform_segments = false;  // Set by UploadSegments.
+  bool uniform_broken = false;    // Some boundary differs between bodies.
+  std::size_t uniform_prefix = 0; // Boundaries compared so far.
+  // Device layout: body b's segments at [b * segment_capacity, ... + count).
+  int32_t segment_capacity = 0;
+  std::vector<int32_t> uploaded_segments;  // Per body.
+
+  pb::DeviceBuffer<pb::DeviceBody> bodies;
+  pb::DeviceBuffer<pb::Damping> dampings;
+  pb::DeviceBuffer<double> cos, sin, normalization;
+  pb::DeviceBuffer<int32_t> segment_offset, segment_end;
+  pb::DeviceBuffer<double> segment_t_max, segment_origin, segment_coefficients;
+  pb::DeviceBuffer<int32_t> segment_degree;
+
+  // Workspaces not in use.
+  std::mutex pool_mutex;
+  std::vector<std::unique_ptr<pb::FlowWorkspace>> idle_workspaces;
+
+  // Cooperative cancellation (RETURN_IF_STOPPED): set by
+  // pb_ephemeris_request_stop from any thread; the fixed-step flows poll the
+  // host flag between chunks of steps, the adaptive kernel polls the device
+  // word after every accepted step.
+  std::atomic<int> stop_requested{0};
+  int32_t* stop_word_device = nullptr;
+  cudaStream_t control_stream = nullptr;
+
+  // The hot oblate body of the fixed-step flow kernels (internal index, -1:
+  // none), chosen from the first probe of the first flow and kept until a flow
+  // reports kPathGenericHarmonics.
+  std::mutex hot_mutex;
+  bool hot_body_valid = false;
+  int hot_body = -1;
+
+  // Measurement of the last completed flow call.
+  mutable std::mutex statistics_mutex;
+  double last_flow_kernel_ms = 0;
+  std::int64_t last_flow_kernel_launches = 0;
+  int32_t last_flow_hot_body = -1;  // Caller index.
+  int32_t last_flow_path_flags = 0;
+
+  // Live pb_fixed_step_instance / pb_nbody_ensemble handles: the ephemeris
+  // refuses to be destroyed under them.
+  std::atomic<int> dependants{0};
+
+  ~pb_ephemeris() {
+    idle_workspaces.clear();
+    if (stop_word_device != nullptr) {
+      cudaFree(stop_word_device);
+    }
+    if (control_stream != nullptr) {
+      cudaStreamDestroy(control_stream);
     }
   }
 
@@ -223,21 +382,96 @@ struct pb_ephemeris {
     v.sin = sin.data;
     v.normalization = normalization.data;
     v.segment_offset = segment_offset.data;
+    v.segment_end = segment_end.data;
     v.segment_t_max = segment_t_max.data;
     v.segment_origin = segment_origin.data;
     v.segment_degree = segment_degree.data;
     v.segment_coefficients = segment_coefficients.data;
+    v.path_flags = nullptr;
     return v;
   }
 };
 
 namespace pb {
-// Defined in principia_b200.cu.
-pb_status_t UploadSegments(pb_ephemeris* e, cudaStream_t stream);
+
+// A workspace of `e` for the duration of a call whose device work is ordered
+// on `stream` (null: the workspace's own stream, see stream()).
+class WorkspaceLease {
+ public:
+  WorkspaceLease() = default;
+  ~WorkspaceLease() { Release(); }
+  WorkspaceLease(WorkspaceLease const&) = delete;
+  WorkspaceLease& operator=(WorkspaceLease const&) = delete;
+
+  // `user_stream_given`: the call runs on the caller's stream
+  // (`user_stream`, possibly the legacy default stream) rather than on the
+  // workspace's own.
+  pb_status_t Acquire(pb_ephemeris* const e, bool const user_stream_given,
+                      cudaStream_t const user_stream) {
+    e_ = e;
+    {
+      std::lock_guard<std::mutex> const lock(e->pool_mutex);
+      if (!e->idle_workspaces.empty()) {
+        w_ = std::move(e->idle_workspaces.back());
+        e->idle_workspaces.pop_back();
+      }
+    }
+    if (w_ == nullptr) {
+      w_ = std::make_unique<FlowWorkspace>();
+      PB_CUDA(cudaStreamCreateWithFlags(&w_->stream, cudaStreamNonBlocking));
+      PB_CUDA(cudaEventCreateWithFlags(&w_->last_use, cudaEventDisableTiming));
+      PB_RETURN_IF_ERROR(w_->status_word.Reserve(4));
+      PB_RETURN_IF_ERROR(w_->pinned_status.Reserve(4));
+    }
+    stream_ = user_stream_given ? user_stream : w_->stream;
+    if (w_->used) {
+      PB_CUDA(cudaStreamWaitEvent(stream_, w_->last_use, 0));
+    }
+    return PB_OK;
+  }
+
+  void Release() {
+    if (w_ == nullptr) {
+      return;
+    }
+    cudaEventRecord(w_->last_use, stream_);
+    w_->used = true;
+    std::lock_guard<std::mutex> const lock(e_->pool_mutex);
+    e_->idle_workspaces.push_back(std::move(w_));
+  }
+
+  FlowWorkspace* get() const { return w_.get(); }
+  FlowWorkspace* operator->() const { return w_.get(); }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  pb_ephemeris* e_ = nullptr;
+  std::unique_ptr<FlowWorkspace> w_;
+  cudaStream_t stream_ = nullptr;
+};
+
+// Shared ownership of the segments for the duration of a call, with the device
+// copy up to date.
+class SegmentsReadLock {
+ public:
+  SegmentsReadLock() = default;
+  SegmentsReadLock(SegmentsReadLock const&) = delete;
+  SegmentsReadLock& operator=(SegmentsReadLock const&) = delete;
+  pb_status_t Acquire(pb_ephemeris* e);
+
+ private:
+  std::shared_lock<std::shared_mutex> lock_;
+};
+
+}  // namespace pb
+
+namespace pb {
+// Defined in principia_b200.cu.  The callers hold a SegmentsReadLock.
 double EphemerisTMin(pb_ephemeris const* e);
 double EphemerisTMax(pb_ephemeris const* e);
-pb_status_t BuildStageTable(pb_ephemeris* e, double const* times_host,
-                            int n_times, double* table, cudaStream_t stream);
+pb_status_t BuildStageTable(pb_ephemeris* e, FlowWorkspace* w,
+                            double const* times_host, int n_times,
+                            double* table, cudaStream_t stream);
 // Defined in pb_api_continuous_trajectory.cu.
 pb_status_t ContinuousTrajectoriesAppendDevice(pb_continuous_trajectories* h,
                                                double time, double const* q,

@@ -24,55 +24,128 @@ using namespace pb;
 
 namespace pb {
 
-pb_status_t UploadSegments(pb_ephemeris* e, cudaStream_t stream) {
+// Brings the device copy of the segments up to date: only the segments
+// appended since the last upload travel.  Body b's segments live at
+// [b * capacity, b * capacity + count_b) of every array; when a body outgrows
+// the capacity the arrays are reallocated at twice the size and the old rows
+// copied device to device.  The caller holds e->segments_mutex exclusively.
+pb_status_t UploadSegments(pb_ephemeris* e) {
   if (!e->segments_dirty) {
     return PB_OK;
   }
   int const n = static_cast<int>(e->trajectories.size());
-  std::vector<int32_t> offset(n + 1, 0);
-  std::vector<double> t_max, origin, coefficients;
-  std::vector<int32_t> degree;
+  cudaStream_t const stream = nullptr;
+  if (static_cast<int>(e->uploaded_segments.size()) != n) {
+    e->uploaded_segments.assign(n, 0);
+  }
+  std::size_t longest = 0;
+  for (auto const& tr : e->trajectories) {
+    longest = std::max(longest, tr.t_max.size());
+  }
+  if (longest > static_cast<std::size_t>(e->segment_capacity)) {
+    // Asynchronous queries may still read the old arrays.
+    PB_CUDA(cudaDeviceSynchronize());
+    std::size_t const old_capacity = e->segment_capacity;
+    std::size_t const capacity =
+        std::max<std::size_t>({2 * old_capacity, longest, 64});
+    DeviceBuffer<double> t_max, origin, coefficients;
+    DeviceBuffer<int32_t> degree;
+    PB_RETURN_IF_ERROR(t_max.Reserve(capacity * n));
+    PB_RETURN_IF_ERROR(origin.Reserve(capacity * n));
+    PB_RETURN_IF_ERROR(degree.Reserve(capacity * n));
+    PB_RETURN_IF_ERROR(
+        coefficients.Reserve(capacity * n * 3 * kSegmentCoefficients));
+    if (old_capacity > 0) {
+      auto grow = [&](void* const to, void const* const from,
+                      std::size_t const element_bytes) {
+        return cudaMemcpy2DAsync(to, capacity * element_bytes, from,
+                                 old_capacity * element_bytes,
+                                 old_capacity * element_bytes, n,
+                                 cudaMemcpyDeviceToDevice, stream);
+      };
+      PB_CUDA(grow(t_max.data, e->segment_t_max.data, sizeof(double)));
+      PB_CUDA(grow(origin.data, e->segment_origin.data, sizeof(double)));
+      PB_CUDA(grow(degree.data, e->segment_degree.data, sizeof(int32_t)));
+      PB_CUDA(grow(coefficients.data, e->segment_coefficients.data,
+                   3 * kSegmentCoefficients * sizeof(double)));
+      PB_CUDA(cudaStreamSynchronize(stream));
+    }
+    e->segment_t_max.Swap(t_max);
+    e->segment_origin.Swap(origin);
+    e->segment_degree.Swap(degree);
+    e->segment_coefficients.Swap(coefficients);
+    e->segment_capacity = static_cast<int32_t>(capacity);
+  }
+  std::size_t const capacity = e->segment_capacity;
+  std::vector<int32_t> offset(n), end(n);
   for (int b = 0; b < n; ++b) {
     HostTrajectory const& tr = e->trajectories[b];
-    offset[b] = static_cast<int32_t>(t_max.size());
-    t_max.insert(t_max.end(), tr.t_max.begin(), tr.t_max.end());
-    origin.insert(origin.end(), tr.origin.begin(), tr.origin.end());
-    degree.insert(degree.end(), tr.degree.begin(), tr.degree.end());
-    // Host [segment][18][3] -> device [segment][3][18].
-    std::size_t const n_segments = tr.t_max.size();
-    std::size_t const base = coefficients.size();
-    coefficients.resize(base + n_segments * 3 * kSegmentCoefficients);
-    for (std::size_t segment = 0; segment < n_segments; ++segment) {
-      double const* const in =
-          tr.coefficients.data() + segment * 3 * kSegmentCoefficients;
-      double* const out =
-          coefficients.data() + base + segment * 3 * kSegmentCoefficients;
-      for (int k = 0; k < kSegmentCoefficients; ++k) {
-        for (int c = 0; c < 3; ++c) {
-          out[c * kSegmentCoefficients + k] = in[3 * k + c];
-        }
+    std::size_t const first = e->uploaded_segments[b];
+    std::size_t const count = tr.t_max.size() - first;
+    offset[b] = static_cast<int32_t>(b * capacity);
+    end[b] = static_cast<int32_t>(b * capacity + tr.t_max.size());
+    if (count == 0) {
+      continue;
+    }
+    std::size_t const at = b * capacity + first;
+    // Pageable host memory: these copies are synchronous with the host.
+    PB_CUDA(cudaMemcpyAsync(e->segment_t_max.data + at, tr.t_max.data() + first,
+                            count * sizeof(double), cudaMemcpyHostToDevice,
+                            stream));
+    PB_CUDA(cudaMemcpyAsync(e->segment_origin.data + at,
+                            tr.origin.data() + first, count * sizeof(double),
+                            cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemcpyAsync(e->segment_degree.data + at,
+                            tr.degree.data() + first, count * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, stream));
+    PB_CUDA(cudaMemcpyAsync(
+        e->segment_coefficients.data + at * 3 * kSegmentCoefficients,
+        tr.coefficients.data() + first * 3 * kSegmentCoefficients,
+        count * 3 * kSegmentCoefficients * sizeof(double),
+        cudaMemcpyHostToDevice, stream));
+    e->uploaded_segments[b] = static_cast<int32_t>(tr.t_max.size());
+  }
+  // Bodies appended in lock step (Ephemeris::Prolong) share their segment
+  // boundaries; kernels then look a time up once for all bodies.  Only the new
+  // boundaries are compared; a mismatch is for ever.
+  bool same_counts = n > 0;
+  for (int b = 1; b < n; ++b) {
+    same_counts = same_counts && e->trajectories[b].t_max.size() ==
+                                     e->trajectories[0].t_max.size();
+  }
+  if (same_counts && !e->uniform_broken) {
+    std::vector<double> const& reference = e->trajectories[0].t_max;
+    for (int b = 1; b < n && !e->uniform_broken; ++b) {
+      std::vector<double> const& other = e->trajectories[b].t_max;
+      if (!std::equal(reference.begin() + e->uniform_prefix, reference.end(),
+                      other.begin() + e->uniform_prefix)) {
+        e->uniform_broken = true;
       }
     }
+    e->uniform_prefix = reference.size();
   }
-  offset[n] = static_cast<int32_t>(t_max.size());
-  // Bodies appended in lock step (Ephemeris::Prolong) share their segment
-  // boundaries; kernels then look a time up once for all bodies.
-  e->uniform_segments = n > 0;
-  for (int b = 1; b < n; ++b) {
-    if (e->trajectories[b].t_max != e->trajectories[0].t_max) {
-      e->uniform_segments = false;
-    }
-  }
-  // The copies below are from pageable memory and therefore synchronous with
-  // respect to the host, so the temporaries may die at the end of this scope.
+  e->uniform_segments = same_counts && !e->uniform_broken;
+  // After the data, so that a kernel in flight never sees an end beyond what
+  // has arrived.
   PB_RETURN_IF_ERROR(e->segment_offset.Upload(offset, stream));
-  PB_RETURN_IF_ERROR(e->segment_t_max.Upload(t_max, stream));
-  PB_RETURN_IF_ERROR(e->segment_origin.Upload(origin, stream));
-  PB_RETURN_IF_ERROR(e->segment_degree.Upload(degree, stream));
-  PB_RETURN_IF_ERROR(e->segment_coefficients.Upload(coefficients, stream));
+  PB_RETURN_IF_ERROR(e->segment_end.Upload(end, stream));
   PB_CUDA(cudaStreamSynchronize(stream));
   e->segments_dirty = false;
   return PB_OK;
+}
+
+pb_status_t SegmentsReadLock::Acquire(pb_ephemeris* const e) {
+  for (;;) {
+    {
+      std::shared_lock<std::shared_mutex> shared(e->segments_mutex);
+      if (!e->segments_dirty) {
+        lock_ = std::move(shared);
+        return PB_OK;
+      }
+    }
+    std::unique_lock<std::shared_mutex> exclusive(e->segments_mutex);
+    PB_RETURN_IF_ERROR(UploadSegments(e));
+  }
 }
 
 double EphemerisTMin(pb_ephemeris const* e) {
@@ -98,9 +171,9 @@ double EphemerisTMax(pb_ephemeris const* e) {
 }
 
 // Fills `table` (device, n_times entries) for `times` (host).
-pb_status_t BuildStageTable(pb_ephemeris* e, double const* times_host,
-                            int n_times, double* table, cudaStream_t stream) {
-  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
+pb_status_t BuildStageTable(pb_ephemeris* e, FlowWorkspace* w,
+                            double const* times_host, int n_times,
+                            double* table, cudaStream_t stream) {
   double lo = std::numeric_limits<double>::infinity();
   double hi = -lo;
   for (int i = 0; i < n_times; ++i) {
@@ -116,12 +189,12 @@ pb_status_t BuildStageTable(pb_ephemeris* e, double const* times_host,
     return Fail(PB_INVALID_ARGUMENT,
                 "time outside [t_min, t_max] of the ephemeris: Prolong first");
   }
-  PB_RETURN_IF_ERROR(e->stage_times.Upload(times_host, n_times, stream));
+  PB_RETURN_IF_ERROR(w->stage_times.Upload(times_host, n_times, stream));
   EphemerisView const view = e->View();
   long long const threads = static_cast<long long>(n_times) * view.n_bodies;
   int const block = 128;
   StageTableKernel<<<static_cast<unsigned>((threads + block - 1) / block),
-                     block, 0, stream>>>(view, e->stage_times.data, n_times,
+                     block, 0, stream>>>(view, w->stage_times.data, n_times,
                                          table);
   PB_LAUNCHED();
   return PB_OK;
@@ -140,29 +213,12 @@ void ComputeNodes(SrknTableau const& tableau, double* c) {
   }
 }
 
-// Uploads the constant-bank tables of the flow kernel: per-body scalars and the
-// tables of the "hot" oblate body -- the body of degree <= kHotDegree with the
-// highest limiting degree at the distance of the first probe (the Earth for
-// LEO probes).  The choice only affects speed: both paths compute the same
-// bits.
-pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
-                                long long const n, double const* state_device,
-                                cudaStream_t stream) {
-  int const n_bodies = static_cast<int>(e->model.bodies.size());
-  if (n_bodies > kMaxConstantBodies) {
-    return Fail(PB_INVALID_ARGUMENT, "too many bodies for the flow kernel");
-  }
-  static std::uint64_t uploaded_for = 0;
-  static int uploaded_hot = -2;
-  // Position of the first probe.
-  double probe[3] = {0.0, 0.0, 0.0};
-  if (n > 0) {
-    for (int c = 0; c < 3; ++c) {
-      PB_CUDA(cudaMemcpyAsync(&probe[c], state_device + c * n, sizeof(double),
-                              cudaMemcpyDeviceToHost, stream));
-    }
-    PB_CUDA(cudaStreamSynchronize(stream));
-  }
+// The "hot" oblate body of the flow kernels -- the body of degree <=
+// kHotDegree with the highest limiting degree at the distance of `probe` (the
+// Earth for LEO probes); -1 if no harmonics above degree 2 are active there.
+// The choice only affects speed: both paths compute the same bits.
+int ChooseHotBody(pb_ephemeris const* e, double const t,
+                  double const* const probe) {
   int hot = -1;
   int best_degree = 2;
   for (int b = 0; b < e->model.n_oblate; ++b) {
@@ -182,7 +238,8 @@ pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
     double const* const c = &tr.coefficients[segment * 3 * kSegmentCoefficients];
     double d2 = 0;
     for (int k = 0; k < 3; ++k) {
-      double const p = EstrinEvaluate<3>(c + k, tr.degree[segment], x);
+      double const p = EstrinEvaluate<1>(c + k * kSegmentCoefficients,
+                                         tr.degree[segment], x);
       d2 += (p - probe[k]) * (p - probe[k]);
     }
     int const limiting = LimitingDegree(
@@ -193,48 +250,120 @@ pb_status_t UploadFlowConstants(pb_ephemeris* e, double const t,
       hot = b;
     }
   }
-  if (uploaded_for == e->serial && uploaded_hot == hot) {
-    return PB_OK;
+  return hot;
+}
+
+// The constant bank of this translation unit's flow kernels (c_bodies, c_hot).
+ConstantBank& FlowConstantBank() {
+  static ConstantBank bank;
+  return bank;
+}
+
+// Makes the constant bank hold the per-body scalars of `e` and the tables of
+// its hot body, choosing the hot body if it has not been chosen yet (or if the
+// previous flow reported that the choice was poor).  `probe_host` is the
+// position of the first probe if the caller has it on the host, else it is
+// read from `state_device` (a synchronisation, once per choice).  The lease
+// must outlive every kernel launched under it.
+pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
+                                 long long const n,
+                                 double const* const state_device,
+                                 double const* const probe_host,
+                                 cudaStream_t stream,
+                                 ConstantBankLease& lease, int* hot_out) {
+  int const n_bodies = static_cast<int>(e->model.bodies.size());
+  if (n_bodies > kMaxConstantBodies) {
+    return Fail(PB_INVALID_ARGUMENT, "too many bodies for the flow kernel");
   }
-  static BodyScalars scalars;
-  static HotBody hot_body;
-  for (int b = 0; b < n_bodies; ++b) {
-    DeviceBody const& body = e->model.bodies[b];
-    scalars.mu[b] = body.mu;
-    scalars.collision_radius[b] = body.collision_radius;
-    scalars.outer_threshold_degree_2[b] =
-        body.is_oblate && body.n_damping > 2
-            ? e->model.dampings[body.damping_offset + 2].outer_threshold
-            : -std::numeric_limits<double>::infinity();
+  int hot;
+  {
+    std::lock_guard<std::mutex> const lock(e->hot_mutex);
+    if (!e->hot_body_valid) {
+      double probe[3] = {0.0, 0.0, 0.0};
+      if (n > 0) {
+        if (probe_host != nullptr) {
+          for (int c = 0; c < 3; ++c) {
+            probe[c] = probe_host[c * n];
+          }
+        } else {
+          for (int c = 0; c < 3; ++c) {
+            PB_CUDA(cudaMemcpyAsync(&probe[c], state_device + c * n,
+                                    sizeof(double), cudaMemcpyDeviceToHost,
+                                    stream));
+          }
+          PB_CUDA(cudaStreamSynchronize(stream));
+        }
+      }
+      e->hot_body = ChooseHotBody(e, t, probe);
+      e->hot_body_valid = n > 0;
+    }
+    hot = e->hot_body;
   }
-  std::memset(&hot_body, 0, sizeof(hot_body));
-  hot_body.body = hot;
-  if (hot >= 0) {
-    DeviceBody const& body = e->model.bodies[hot];
-    int const size = (body.degree + 1) * (body.degree + 2) / 2;
-    hot_body.n_damping = body.n_damping;
-    for (int k = 0; k < size; ++k) {
-      hot_body.cos[k] = e->model.cos[body.coefficient_offset + k];
-      hot_body.sin[k] = e->model.sin[body.coefficient_offset + k];
-    }
-    for (int k = 0; k < kHotSize; ++k) {
-      hot_body.normalization[k] = pb_legendre_normalization_factor[k];
-    }
-    for (int d = 0; d < body.n_damping; ++d) {
-      hot_body.degree_damping[d] = e->model.dampings[body.damping_offset + d];
-    }
-    hot_body.sectoral = body.sectoral;
+  *hot_out = hot;
+  // Variant 0 is "no hot body".
+  pb_status_t const status = FlowConstantBank().Acquire(
+      e->serial, hot + 1, [&]() -> pb_status_t {
+        static BodyScalars scalars;
+        static HotBody hot_body;
+        for (int b = 0; b < n_bodies; ++b) {
+          DeviceBody const& body = e->model.bodies[b];
+          scalars.mu[b] = body.mu;
+          scalars.collision_radius[b] = body.collision_radius;
+          scalars.outer_threshold_degree_2[b] =
+              body.is_oblate && body.n_damping > 2
+                  ? e->model.dampings[body.damping_offset + 2].outer_threshold
+                  : -std::numeric_limits<double>::infinity();
+        }
+        std::memset(&hot_body, 0, sizeof(hot_body));
+        hot_body.body = hot;
+        if (hot >= 0) {
+          DeviceBody const& body = e->model.bodies[hot];
+          int const size = (body.degree + 1) * (body.degree + 2) / 2;
+          hot_body.n_damping = body.n_damping;
+          for (int k = 0; k < size; ++k) {
+            hot_body.cos[k] = e->model.cos[body.coefficient_offset + k];
+            hot_body.sin[k] = e->model.sin[body.coefficient_offset + k];
+          }
+          for (int k = 0; k < kHotSize; ++k) {
+            hot_body.normalization[k] = pb_legendre_normalization_factor[k];
+          }
+          for (int d = 0; d < body.n_damping; ++d) {
+            hot_body.degree_damping[d] =
+                e->model.dampings[body.damping_offset + d];
+          }
+          hot_body.sectoral = body.sectoral;
+        }
+        // No kernel reads the bank now (ConstantBank::Acquire).
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_bodies, &scalars, sizeof(scalars), 0,
+                                        cudaMemcpyHostToDevice, stream));
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_hot, &hot_body, sizeof(hot_body), 0,
+                                        cudaMemcpyHostToDevice, stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        return PB_OK;
+      });
+  if (status == PB_OK) {
+    lease.Adopt(&FlowConstantBank());
   }
-  // The previous launch may still read the symbols on this stream: the copies
-  // are stream-ordered.
-  PB_CUDA(cudaMemcpyToSymbolAsync(c_bodies, &scalars, sizeof(scalars), 0,
-                                  cudaMemcpyHostToDevice, stream));
-  PB_CUDA(cudaMemcpyToSymbolAsync(c_hot, &hot_body, sizeof(hot_body), 0,
-                                  cudaMemcpyHostToDevice, stream));
-  PB_CUDA(cudaStreamSynchronize(stream));
-  uploaded_for = e->serial;
-  uploaded_hot = hot;
-  return PB_OK;
+  return status;
+}
+
+// What a flow leaves for pb_ephemeris_last_flow_*: its kernel time, and the
+// code paths it took.  A flow that met the slow generic harmonics makes the
+// next one choose its hot body afresh.
+void RecordFlowStatistics(pb_ephemeris* e, double const kernel_ms,
+                          std::int64_t const launches, int const hot,
+                          int32_t const path_flags) {
+  {
+    std::lock_guard<std::mutex> const lock(e->statistics_mutex);
+    e->last_flow_kernel_ms = kernel_ms;
+    e->last_flow_kernel_launches = launches;
+    e->last_flow_hot_body = hot >= 0 ? e->model.order[hot] : -1;
+    e->last_flow_path_flags = path_flags;
+  }
+  if ((path_flags & kPathGenericHarmonics) != 0) {
+    std::lock_guard<std::mutex> const lock(e->hot_mutex);
+    e->hot_body_valid = false;
+  }
 }
 
 // Slicing of a flow launch across helper streams (PB_FLOW_GROUPS = 1 disables
@@ -351,6 +480,7 @@ pb_status_t pb_ephemeris_create(int32_t n_bodies, const pb_body_t* bodies,
                                 double geopotential_tolerance,
                                 int32_t cuda_device,
                                 pb_ephemeris_t** ephemeris) {
+  PB_API_RANGE();
   if (ephemeris == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null output");
   }
@@ -390,19 +520,27 @@ pb_status_t pb_ephemeris_create(int32_t n_bodies, const pb_body_t* bodies,
     cos.push_back(0.0);
     sin.push_back(0.0);
   }
+  auto cuda_ok = [](cudaError_t const error) {
+    return error == cudaSuccess ? PB_OK
+                                : Fail(PB_INTERNAL, cudaGetErrorString(error));
+  };
   status = e->bodies.Upload(e->model.bodies, stream);
   if (status == PB_OK) status = e->dampings.Upload(dampings, stream);
   if (status == PB_OK) status = e->cos.Upload(cos, stream);
   if (status == PB_OK) status = e->sin.Upload(sin, stream);
   if (status == PB_OK) status = e->normalization.Upload(normalization, stream);
-  if (status == PB_OK) status = e->status_word.Reserve(4);
-  if (status == PB_OK) status = e->pinned_status.Reserve(4);
   if (status == PB_OK) {
-    cudaError_t const sync_error = cudaStreamSynchronize(stream);
-    if (sync_error != cudaSuccess) {
-      status = Fail(PB_INTERNAL, cudaGetErrorString(sync_error));
-    }
+    status = cuda_ok(cudaMalloc(&e->stop_word_device, sizeof(int32_t)));
   }
+  if (status == PB_OK) {
+    status = cuda_ok(
+        cudaMemsetAsync(e->stop_word_device, 0, sizeof(int32_t), stream));
+  }
+  if (status == PB_OK) {
+    status = cuda_ok(cudaStreamCreateWithFlags(&e->control_stream,
+                                               cudaStreamNonBlocking));
+  }
+  if (status == PB_OK) status = cuda_ok(cudaStreamSynchronize(stream));
   if (status != PB_OK) {
     delete e;
     return status;
@@ -412,10 +550,50 @@ pb_status_t pb_ephemeris_create(int32_t n_bodies, const pb_body_t* bodies,
 }
 
 void pb_ephemeris_destroy(pb_ephemeris_t* ephemeris) {
-  if (ephemeris != nullptr) {
-    cudaSetDevice(ephemeris->device);
-    delete ephemeris;
+  PB_API_RANGE();
+  if (ephemeris == nullptr) {
+    return;
   }
+  if (ephemeris->dependants.load() != 0) {
+    // Instances and ensembles hold a pointer to their ephemeris: destroying it
+    // under them would leave them dangling.  The handle leaks instead, and the
+    // error is recorded.
+    Fail(PB_FAILED_PRECONDITION,
+         "pb_ephemeris_destroy: instances or ensembles of this ephemeris are "
+         "still alive; destroy them first");
+    return;
+  }
+  cudaSetDevice(ephemeris->device);
+  cudaDeviceSynchronize();
+  delete ephemeris;
+}
+
+pb_status_t pb_ephemeris_request_stop(pb_ephemeris_t* e) {
+  PB_API_RANGE();
+  if (e == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null ephemeris");
+  }
+  // No lock: this is called while a flow holds them.
+  e->stop_requested.store(1);
+  PB_CUDA(cudaSetDevice(e->device));
+  static int32_t const one = 1;
+  PB_CUDA(cudaMemcpyAsync(e->stop_word_device, &one, sizeof(int32_t),
+                          cudaMemcpyHostToDevice, e->control_stream));
+  PB_CUDA(cudaStreamSynchronize(e->control_stream));
+  return PB_OK;
+}
+
+pb_status_t pb_ephemeris_clear_stop(pb_ephemeris_t* e) {
+  PB_API_RANGE();
+  if (e == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null ephemeris");
+  }
+  e->stop_requested.store(0);
+  PB_CUDA(cudaSetDevice(e->device));
+  PB_CUDA(cudaMemsetAsync(e->stop_word_device, 0, sizeof(int32_t),
+                          e->control_stream));
+  PB_CUDA(cudaStreamSynchronize(e->control_stream));
+  return PB_OK;
 }
 
 pb_status_t pb_ephemeris_internal_order(const pb_ephemeris_t* e, int32_t* order,
@@ -457,19 +635,31 @@ pb_status_t pb_ephemeris_append_segments(pb_ephemeris_t* e, int32_t body,
                                          const double* origin,
                                          const int32_t* degree,
                                          const double* coefficients) {
+  PB_API_RANGE();
   if (e == nullptr || body < 0 ||
-      body >= static_cast<int32_t>(e->model.bodies.size()) || n_segments < 0) {
+      body >= static_cast<int32_t>(e->model.bodies.size()) || n_segments < 0 ||
+      (n_segments > 0 && (t_max == nullptr || origin == nullptr ||
+                          degree == nullptr || coefficients == nullptr))) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
   }
-  HostTrajectory& tr = e->trajectories[e->model.internal_of_caller[body]];
+  // Validate before mutating anything: a rejected call leaves the trajectory
+  // as it was.
   for (int s = 0; s < n_segments; ++s) {
     if (degree[s] < 0 || degree[s] >= kSegmentCoefficients) {
       return Fail(PB_INVALID_ARGUMENT, "segment degree out of range");
     }
-    double const previous = tr.t_max.empty() ? t_min : tr.t_max.back();
+  }
+  // Waits for the flows and queries in progress.
+  std::unique_lock<std::shared_mutex> const lock(e->segments_mutex);
+  HostTrajectory& tr = e->trajectories[e->model.internal_of_caller[body]];
+  double previous = tr.t_max.empty() ? t_min : tr.t_max.back();
+  for (int s = 0; s < n_segments; ++s) {
     if (!(t_max[s] > previous)) {
       return Fail(PB_INVALID_ARGUMENT, "segments must be appended in order");
     }
+    previous = t_max[s];
+  }
+  for (int s = 0; s < n_segments; ++s) {
     if (!tr.has_t_min) {
       tr.has_t_min = true;
       tr.t_min = t_min;
@@ -477,37 +667,49 @@ pb_status_t pb_ephemeris_append_segments(pb_ephemeris_t* e, int32_t body,
     tr.t_max.push_back(t_max[s]);
     tr.origin.push_back(origin[s]);
     tr.degree.push_back(degree[s]);
-    tr.coefficients.insert(tr.coefficients.end(),
-                           coefficients + 3 * kSegmentCoefficients * s,
-                           coefficients + 3 * kSegmentCoefficients * (s + 1));
-    // The slots above the degree are padding: -0.0, the neutral element that
-    // EvaluateSegmentPadded relies on (pb_accel.cuh).
-    double* const slots =
-        tr.coefficients.data() + tr.coefficients.size() -
-        3 * kSegmentCoefficients;
-    for (int k = 3 * (degree[s] + 1); k < 3 * kSegmentCoefficients; ++k) {
-      slots[k] = -0.0;
+    // Host API [18][3] -> device layout [xyz][18]; the slots above the degree
+    // are padding: -0.0, the neutral element that EvaluateSegmentPadded relies
+    // on (pb_accel.cuh).
+    std::size_t const base = tr.coefficients.size();
+    tr.coefficients.resize(base + 3 * kSegmentCoefficients, -0.0);
+    double const* const in = coefficients + 3 * kSegmentCoefficients * s;
+    for (int k = 0; k <= degree[s]; ++k) {
+      for (int c = 0; c < 3; ++c) {
+        tr.coefficients[base + c * kSegmentCoefficients + k] = in[3 * k + c];
+      }
     }
   }
   e->segments_dirty = true;
   return PB_OK;
 }
 
-double pb_ephemeris_t_min(const pb_ephemeris_t* e) { return EphemerisTMin(e); }
-double pb_ephemeris_t_max(const pb_ephemeris_t* e) { return EphemerisTMax(e); }
+double pb_ephemeris_t_min(const pb_ephemeris_t* e) {
+  std::shared_lock<std::shared_mutex> const lock(e->segments_mutex);
+  return EphemerisTMin(e);
+}
+double pb_ephemeris_t_max(const pb_ephemeris_t* e) {
+  std::shared_lock<std::shared_mutex> const lock(e->segments_mutex);
+  return EphemerisTMax(e);
+}
 
 pb_status_t pb_ephemeris_evaluate_all_positions(pb_ephemeris_t* e, double t,
                                                 double* positions) {
+  PB_API_RANGE();
   if (e == nullptr || positions == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null argument");
   }
   PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
+  WorkspaceLease w;
+  PB_RETURN_IF_ERROR(w.Acquire(e, false, nullptr));
+  SegmentsReadLock segments;
+  PB_RETURN_IF_ERROR(segments.Acquire(e));
+  cudaStream_t const stream = w.stream();
   EphemerisView const view = e->View();
-  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
-  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+  PB_RETURN_IF_ERROR(w->stage_table.Reserve(view.stage_stride));
+  PB_RETURN_IF_ERROR(
+      BuildStageTable(e, w.get(), &t, 1, w->stage_table.data, stream));
   std::vector<double> entry(view.stage_stride);
-  PB_CUDA(cudaMemcpyAsync(entry.data(), e->stage_table.data,
+  PB_CUDA(cudaMemcpyAsync(entry.data(), w->stage_table.data,
                           entry.size() * sizeof(double), cudaMemcpyDeviceToHost,
                           stream));
   PB_CUDA(cudaStreamSynchronize(stream));
@@ -520,50 +722,77 @@ pb_status_t pb_ephemeris_evaluate_all_positions(pb_ephemeris_t* e, double t,
   return PB_OK;
 }
 
-pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies_device(
-    pb_ephemeris_t* e, double t, int64_t n, const double* q, double* a,
-    int32_t* status_device, void* stream_pointer) {
-  if (e == nullptr || n < 0 || (n > 0 && (q == nullptr || a == nullptr))) {
-    return Fail(PB_INVALID_ARGUMENT, "bad argument");
-  }
-  PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
+}  // extern "C"
+
+namespace {
+
+// ...ByAllMassiveBodiesOnMasslessBodies on device arrays, asynchronous on
+// `stream`; the caller holds the workspace and the segments.
+pb_status_t MasslessAccelerations(pb_ephemeris* e, FlowWorkspace* w, double t,
+                                  int64_t n, const double* q, double* a,
+                                  int32_t* status, cudaStream_t stream) {
   EphemerisView const view = e->View();
-  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
-  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
-  int32_t* const status =
-      status_device != nullptr ? status_device : e->status_word.data;
+  PB_RETURN_IF_ERROR(w->stage_table.Reserve(view.stage_stride));
+  PB_RETURN_IF_ERROR(BuildStageTable(e, w, &t, 1, w->stage_table.data, stream));
   if (n > 0) {
     MasslessAccelerationKernel<true>
         <<<static_cast<unsigned>((n + kFlowThreads - 1) / kFlowThreads),
-           kFlowThreads, 0, stream>>>(view, e->stage_table.data, n, q, a,
+           kFlowThreads, 0, stream>>>(view, w->stage_table.data, n, q, a,
                                       status);
     PB_LAUNCHED();
   }
   return PB_OK;
 }
 
-pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies(
+}  // namespace
+
+extern "C" {
+
+pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies_device(
     pb_ephemeris_t* e, double t, int64_t n, const double* q, double* a,
-    pb_status_t* status) {
+    int32_t* status_device, void* stream_pointer) {
+  PB_API_RANGE();
   if (e == nullptr || n < 0 || (n > 0 && (q == nullptr || a == nullptr))) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
   }
   PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
-  PB_RETURN_IF_ERROR(e->scratch_a.Upload(q, 3 * n, stream));
-  PB_RETURN_IF_ERROR(e->scratch_b.Reserve(3 * n));
-  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
-  PB_RETURN_IF_ERROR(
-      pb_compute_gravitational_acceleration_on_massless_bodies_device(
-          e, t, n, e->scratch_a.data, e->scratch_b.data, e->status_word.data,
-          stream));
+  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
+  WorkspaceLease w;
+  PB_RETURN_IF_ERROR(w.Acquire(e, true, stream));
+  SegmentsReadLock segments;
+  PB_RETURN_IF_ERROR(segments.Acquire(e));
+  // Asynchronous: the workspace is handed back with an event that the next
+  // user waits for.
+  return MasslessAccelerations(
+      e, w.get(), t, n, q, a,
+      status_device != nullptr ? status_device : w->status_word.data, stream);
+}
+
+pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies(
+    pb_ephemeris_t* e, double t, int64_t n, const double* q, double* a,
+    pb_status_t* status) {
+  PB_API_RANGE();
+  if (e == nullptr || n < 0 || (n > 0 && (q == nullptr || a == nullptr))) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  PB_CUDA(cudaSetDevice(e->device));
+  WorkspaceLease w;
+  PB_RETURN_IF_ERROR(w.Acquire(e, false, nullptr));
+  SegmentsReadLock segments;
+  PB_RETURN_IF_ERROR(segments.Acquire(e));
+  cudaStream_t const stream = w.stream();
+  PB_RETURN_IF_ERROR(w->scratch_a.Upload(q, 3 * n, stream));
+  PB_RETURN_IF_ERROR(w->scratch_b.Reserve(3 * n));
+  PB_CUDA(cudaMemsetAsync(w->status_word.data, 0, sizeof(int32_t), stream));
+  PB_RETURN_IF_ERROR(MasslessAccelerations(e, w.get(), t, n, w->scratch_a.data,
+                                           w->scratch_b.data,
+                                           w->status_word.data, stream));
   if (n > 0) {
-    PB_CUDA(cudaMemcpyAsync(a, e->scratch_b.data, 3 * n * sizeof(double),
+    PB_CUDA(cudaMemcpyAsync(a, w->scratch_b.data, 3 * n * sizeof(double),
                             cudaMemcpyDeviceToHost, stream));
   }
   int32_t word = 0;
-  PB_CUDA(cudaMemcpyAsync(&word, e->status_word.data, sizeof(int32_t),
+  PB_CUDA(cudaMemcpyAsync(&word, w->status_word.data, sizeof(int32_t),
                           cudaMemcpyDeviceToHost, stream));
   PB_CUDA(cudaStreamSynchronize(stream));
   if (status != nullptr) {
@@ -575,25 +804,31 @@ pb_status_t pb_compute_gravitational_acceleration_on_massless_bodies(
 pb_status_t pb_compute_gravitational_potential(pb_ephemeris_t* e, double t,
                                                int64_t n, const double* q,
                                                double* potential) {
+  PB_API_RANGE();
   if (e == nullptr || n < 0 ||
       (n > 0 && (q == nullptr || potential == nullptr))) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
   }
   PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
+  WorkspaceLease w;
+  PB_RETURN_IF_ERROR(w.Acquire(e, false, nullptr));
+  SegmentsReadLock segments;
+  PB_RETURN_IF_ERROR(segments.Acquire(e));
+  cudaStream_t const stream = w.stream();
   EphemerisView const view = e->View();
-  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
-  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
-  PB_RETURN_IF_ERROR(e->scratch_a.Upload(q, 3 * n, stream));
-  PB_RETURN_IF_ERROR(e->scratch_b.Reserve(n));
+  PB_RETURN_IF_ERROR(w->stage_table.Reserve(view.stage_stride));
+  PB_RETURN_IF_ERROR(
+      BuildStageTable(e, w.get(), &t, 1, w->stage_table.data, stream));
+  PB_RETURN_IF_ERROR(w->scratch_a.Upload(q, 3 * n, stream));
+  PB_RETURN_IF_ERROR(w->scratch_b.Reserve(n));
   if (n > 0) {
     PotentialKernel<<<static_cast<unsigned>((n + kFlowThreads - 1) /
                                             kFlowThreads),
-                      kFlowThreads, 0, stream>>>(view, e->stage_table.data, n,
-                                                 e->scratch_a.data,
-                                                 e->scratch_b.data);
+                      kFlowThreads, 0, stream>>>(view, w->stage_table.data, n,
+                                                 w->scratch_a.data,
+                                                 w->scratch_b.data);
     PB_LAUNCHED();
-    PB_CUDA(cudaMemcpyAsync(potential, e->scratch_b.data, n * sizeof(double),
+    PB_CUDA(cudaMemcpyAsync(potential, w->scratch_b.data, n * sizeof(double),
                             cudaMemcpyDeviceToHost, stream));
   }
   PB_CUDA(cudaStreamSynchronize(stream));
@@ -603,16 +838,22 @@ pb_status_t pb_compute_gravitational_potential(pb_ephemeris_t* e, double t,
 pb_status_t pb_compute_gravitational_acceleration_on_massive_bodies(
     pb_ephemeris_t* e, double t, const double* positions,
     double* accelerations) {
+  PB_API_RANGE();
   if (e == nullptr || accelerations == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null argument");
   }
   PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
+  WorkspaceLease w;
+  PB_RETURN_IF_ERROR(w.Acquire(e, false, nullptr));
+  SegmentsReadLock segments;
+  PB_RETURN_IF_ERROR(segments.Acquire(e));
+  cudaStream_t const stream = w.stream();
   EphemerisView const view = e->View();
   int const n = view.n_bodies;
-  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
+  PB_RETURN_IF_ERROR(w->stage_table.Reserve(view.stage_stride));
   if (positions == nullptr) {
-    PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+    PB_RETURN_IF_ERROR(
+        BuildStageTable(e, w.get(), &t, 1, w->stage_table.data, stream));
   } else {
     std::vector<double> internal(3 * n);
     for (int b = 0; b < n; ++b) {
@@ -621,20 +862,20 @@ pb_status_t pb_compute_gravitational_acceleration_on_massive_bodies(
         internal[3 * b + c] = positions[3 * caller + c];
       }
     }
-    PB_CUDA(cudaMemcpyAsync(e->stage_table.data, internal.data(),
+    PB_CUDA(cudaMemcpyAsync(w->stage_table.data, internal.data(),
                             internal.size() * sizeof(double),
                             cudaMemcpyHostToDevice, stream));
     PB_CUDA(cudaStreamSynchronize(stream));
     FramesKernel<<<(n + 63) / 64, 64, 0, stream>>>(view, t,
-                                                  e->stage_table.data);
+                                                  w->stage_table.data);
     PB_LAUNCHED();
   }
-  PB_RETURN_IF_ERROR(e->scratch_b.Reserve(3 * n));
+  PB_RETURN_IF_ERROR(w->scratch_b.Reserve(3 * n));
   MassiveAccelerationKernel<<<(n + 31) / 32, 32, 0, stream>>>(
-      view, e->stage_table.data, e->scratch_b.data);
+      view, w->stage_table.data, w->scratch_b.data);
   PB_LAUNCHED();
   std::vector<double> internal(3 * n);
-  PB_CUDA(cudaMemcpyAsync(internal.data(), e->scratch_b.data,
+  PB_CUDA(cudaMemcpyAsync(internal.data(), w->scratch_b.data,
                           internal.size() * sizeof(double),
                           cudaMemcpyDeviceToHost, stream));
   PB_CUDA(cudaStreamSynchronize(stream));
@@ -651,14 +892,116 @@ pb_status_t pb_compute_gravitational_acceleration_on_massive_bodies(
 
 namespace {
 
-pb_status_t MultistepFlowDevice(pb_ephemeris_t* e,
-                                const pb_fixed_step_flow_t* flow,
-                                cudaStream_t stream);
+// What one fixed-step flow call holds for its duration: a workspace, the
+// segments, the constant bank; and what it accumulates.
+struct FlowContext {
+  pb_ephemeris* e = nullptr;
+  // Declared in the order in which they must be released LAST to FIRST: the
+  // constant bank and the segments go before the workspace is handed back.
+  WorkspaceLease workspace;
+  SegmentsReadLock segments;
+  ConstantBankLease constants;
+  cudaStream_t stream = nullptr;
+  int hot = -1;
+  // RETURN_IF_STOPPED: set when the flow stopped at a chunk boundary because
+  // pb_ephemeris_request_stop was called.
+  bool cancelled = false;
+  double kernel_ms = 0;
+  std::int64_t launches = 0;
+  std::size_t phases = 0;
 
-// pb_flow_with_fixed_step_device for the SRKN methods, at most `max_steps`
-// steps (the Starter of the multistep integrators runs it in groups of 16).
-pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
-                           void* stream_pointer, long long const max_steps) {
+  FlowWorkspace* w() const { return workspace.get(); }
+
+  // `probe_host`: the first probe's position if the caller has it on the host
+  // (3 values at stride n), else null and `state_device` is read.
+  pb_status_t Begin(pb_ephemeris* const ephemeris, bool const user_stream_given,
+                    cudaStream_t const user_stream) {
+    e = ephemeris;
+    PB_CUDA(cudaSetDevice(e->device));
+    PB_RETURN_IF_ERROR(workspace.Acquire(e, user_stream_given, user_stream));
+    stream = workspace.stream();
+    PB_RETURN_IF_ERROR(segments.Acquire(e));
+    // [0]: right-hand-side status, [1]: path flags.
+    PB_CUDA(cudaMemsetAsync(w()->status_word.data, 0, 2 * sizeof(int32_t),
+                            stream));
+    return PB_OK;
+  }
+
+  pb_status_t AcquireConstants(double const t, long long const n,
+                               double const* const state_device,
+                               double const* const probe_host) {
+    if (constants.held()) {
+      return PB_OK;
+    }
+    return AcquireFlowConstants(e, t, n, state_device, probe_host, stream,
+                                constants, &hot);
+  }
+
+  EphemerisView View() const {
+    EphemerisView view = e->View();
+    view.path_flags = w()->status_word.data + 1;
+    return view;
+  }
+
+  // Sums the device time of the kernel phases recorded since the last call.
+  pb_status_t CollectKernelTime() {
+    for (std::size_t i = 0; i < phases; ++i) {
+      float elapsed = 0;
+      PB_CUDA(cudaEventElapsedTime(&elapsed, w()->timing_events[2 * i],
+                                   w()->timing_events[2 * i + 1]));
+      kernel_ms += elapsed;
+    }
+    phases = 0;
+    return PB_OK;
+  }
+
+  // Reads the status words (the stream is synchronised) and publishes the
+  // statistics of the call.  *rhs_status: 0 or PB_OUT_OF_RANGE.
+  pb_status_t Finish(pb_status_t* const rhs_status) {
+    PB_CUDA(cudaMemcpyAsync(w()->pinned_status.data, w()->status_word.data,
+                            2 * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                            stream));
+    PB_CUDA(cudaStreamSynchronize(stream));
+    PB_RETURN_IF_ERROR(CollectKernelTime());
+    RecordFlowStatistics(e, kernel_ms, launches, hot,
+                         w()->pinned_status.data[1]);
+    if (rhs_status != nullptr) {
+      // The only error the right-hand side reports is the collision
+      // (ephemeris_body.hpp:383-384).
+      *rhs_status = w()->pinned_status.data[0] != 0 ? PB_OUT_OF_RANGE : PB_OK;
+    }
+    return PB_OK;
+  }
+
+  pb_status_t EnsureHelpers(int const groups) {
+    FlowWorkspace* const ws = w();
+    while (static_cast<int>(ws->flow_streams.size()) < groups) {
+      cudaStream_t helper;
+      PB_CUDA(cudaStreamCreateWithFlags(&helper, cudaStreamNonBlocking));
+      ws->flow_streams.push_back(helper);
+      cudaEvent_t event;
+      PB_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
+      ws->flow_events.push_back(event);
+    }
+    while (ws->timing_events.size() < 2 * (phases + 1)) {
+      cudaEvent_t event;
+      PB_CUDA(cudaEventCreate(&event));
+      ws->timing_events.push_back(event);
+    }
+    return PB_OK;
+  }
+};
+
+// The steps of an SRKN flow on device state, at most `max_steps` of them (the
+// Starter of the multistep integrators runs groups of 16).  The context has
+// been begun and holds the constants.  Does not read the status back
+// (FlowContext::Finish does).  On return flow->time and *flow->n_steps /
+// n_samples are updated; c.cancelled tells whether the flow stopped early.
+pb_status_t SrknSteps(FlowContext& c, const pb_fixed_step_flow_t* flow,
+                      long long const max_steps) {
+  pb_ephemeris* const e = c.e;
+  FlowWorkspace* const w = c.w();
+  cudaStream_t const stream = c.stream;
   SrknTableau tableau;
   if (!MakeSrknTableau(flow->method, tableau)) {
     return Fail(PB_INVALID_ARGUMENT, "unsupported fixed-step method");
@@ -666,11 +1009,9 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
   if (flow->step == 0 || flow->step != flow->step) {
     return Fail(PB_INVALID_ARGUMENT, "CHECK_NE(Time(), step)");
   }
-  PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = static_cast<cudaStream_t>(stream_pointer);
-  EphemerisView const view = e->View();
-  double c[16];
-  ComputeNodes(tableau, c);
+  EphemerisView const view = c.View();
+  double nodes[16];
+  ComputeNodes(tableau, nodes);
   int const evaluations = tableau.stages - tableau.first_stage;
   double const h = flow->step;
   double const abs_h = h < 0 ? -h : h;
@@ -678,34 +1019,42 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
   double const t_final = flow->t_final;
   bool const sampling = flow->samples != nullptr && flow->sample_every > 0;
 
-  // Steps per launch: bounds the stage table (evaluations * stride doubles per
-  // step).
+  // Steps per launch phase: bounds the stage table (evaluations * stride
+  // doubles per step), and is the granularity of cancellation.
   int const chunk_steps = 256;
   std::size_t const table_doubles =
       static_cast<std::size_t>(chunk_steps) * evaluations * view.stage_stride;
-  PB_RETURN_IF_ERROR(e->stage_table.Reserve(table_doubles));
-  PB_RETURN_IF_ERROR(
-      e->pinned_times.Reserve(static_cast<std::size_t>(chunk_steps) *
-                              evaluations));
-  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
-  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
-  PB_RETURN_IF_ERROR(UploadFlowConstants(e, t.value, flow->n, flow->state, stream));
+  PB_RETURN_IF_ERROR(w->stage_table.Reserve(table_doubles));
+  PB_RETURN_IF_ERROR(w->pinned_times.Reserve(
+      static_cast<std::size_t>(chunk_steps) * evaluations));
+  int sm_count = 0;
+  PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
+                                 e->device));
 
   long long steps_done = 0;
   long long samples_done = 0;
-  std::size_t launches = 0;
-  std::size_t phases = 0;
+  bool first_chunk = true;
   while (steps_done < max_steps &&
          abs_h <= std::abs((t_final - t.value) - t.error)) {
+    if (!first_chunk) {
+      // The pinned staging buffer is reused across chunks, and this is where
+      // a stop request is honoured: the state is that of the last completed
+      // step (RETURN_IF_STOPPED,
+      // symplectic_runge_kutta_nyström_integrator_body.hpp:137).
+      PB_CUDA(cudaStreamSynchronize(stream));
+    }
+    if (e->stop_requested.load() != 0) {
+      c.cancelled = true;
+      break;
+    }
+    first_chunk = false;
     int steps = 0;
-    double* const times = e->pinned_times.data;
-    // The pinned staging buffer is reused across chunks.
-    PB_CUDA(cudaStreamSynchronize(stream));
+    double* const times = w->pinned_times.data;
     while (steps < chunk_steps && steps_done + steps < max_steps &&
            abs_h <= std::abs((t_final - t.value) - t.error)) {
       for (int st = tableau.first_stage; st < tableau.stages; ++st) {
         times[steps * evaluations + (st - tableau.first_stage)] =
-            t.value + (t.error + c[st] * h);
+            t.value + (t.error + nodes[st] * h);
       }
       Increment(t, h);
       ++steps;
@@ -717,22 +1066,14 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
         ++samples_done;
       }
     }
-    PB_RETURN_IF_ERROR(BuildStageTable(e, times, steps * evaluations,
-                                       e->stage_table.data, stream));
+    PB_RETURN_IF_ERROR(BuildStageTable(e, w, times, steps * evaluations,
+                                       w->stage_table.data, stream));
     if (flow->n > 0) {
-      while (e->timing_events.size() < 2 * (phases + 1)) {
-        cudaEvent_t event;
-        PB_CUDA(cudaEventCreate(&event));
-        e->timing_events.push_back(event);
-      }
       // The probes are cut into `groups` slices and the steps into sub-chunks;
       // slice g runs its sub-chunks in order on helper stream g.  Whole
       // launches of 10^5 probes leave 12 % of the SM slots idle in their last
       // wave (782 CTAs on 444 slots); short launches from several streams keep
       // the slots full, and no kernel ever waits on another one.
-      int sm_count = 0;
-      PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
-                                     e->device));
       int const variant = SrknVariant(flow->n, sm_count);
       int const threads =
           variant == 5 ? 256 : variant >= 2 ? 384 : kFlowThreads;
@@ -740,20 +1081,13 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
       int const groups = static_cast<int>(
           std::min<long long>(FlowGroups(), std::max<long long>(1, blocks / 64)));
       int const sub_steps = groups > 1 ? FlowSubSteps() : steps;
-      while (static_cast<int>(e->flow_streams.size()) < groups) {
-        cudaStream_t helper;
-        PB_CUDA(cudaStreamCreateWithFlags(&helper, cudaStreamNonBlocking));
-        e->flow_streams.push_back(helper);
-        cudaEvent_t event;
-        PB_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
-        e->flow_events.push_back(event);
-      }
-      cudaEvent_t const fork = e->timing_events[2 * phases];
-      cudaEvent_t const join = e->timing_events[2 * phases + 1];
+      PB_RETURN_IF_ERROR(c.EnsureHelpers(groups));
+      cudaEvent_t const fork = w->timing_events[2 * c.phases];
+      cudaEvent_t const join = w->timing_events[2 * c.phases + 1];
       PB_CUDA(cudaEventRecord(fork, stream));
       long long const every = sampling ? flow->sample_every : 0;
       for (int g = 0; g < groups; ++g) {
-        cudaStream_t const helper = groups > 1 ? e->flow_streams[g] : stream;
+        cudaStream_t const helper = groups > 1 ? w->flow_streams[g] : stream;
         if (groups > 1) {
           PB_CUDA(cudaStreamWaitEvent(helper, fork, 0));
         }
@@ -765,17 +1099,17 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
         for (int s0 = 0; s0 < steps; s0 += sub_steps) {
           int const n_sub = std::min(sub_steps, steps - s0);
           double const* const table =
-              e->stage_table.data +
+              w->stage_table.data +
               static_cast<std::size_t>(s0) * evaluations * view.stage_stride;
-          double const* const times =
-              e->stage_times.data + static_cast<std::size_t>(s0) * evaluations;
+          double const* const stage_times =
+              w->stage_times.data + static_cast<std::size_t>(s0) * evaluations;
 #define PB_LAUNCH_SRKN(kThreads, kMinBlocks)                                  \
   (flow->burns != nullptr ? SrknFlowKernel<kThreads, kMinBlocks, true>        \
                           : SrknFlowKernel<kThreads, kMinBlocks, false>)      \
       <<<grid, kThreads, 0, helper>>>(                                        \
-          view, tableau, h, table, times, flow->burns, n_sub, flow->n,        \
+          view, tableau, h, table, stage_times, flow->burns, n_sub, flow->n,  \
           i_begin, i_end, flow->state, steps_done + s0, every,                \
-          flow->max_samples, flow->samples, e->status_word.data)
+          flow->max_samples, flow->samples, w->status_word.data)
           if (variant == 5) {
             PB_LAUNCH_SRKN(256, 2);
           } else if (variant >= 2) {
@@ -789,30 +1123,17 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
           }
 #undef PB_LAUNCH_SRKN
           PB_LAUNCHED();
-          ++launches;
+          ++c.launches;
         }
         if (groups > 1) {
-          PB_CUDA(cudaEventRecord(e->flow_events[g], helper));
-          PB_CUDA(cudaStreamWaitEvent(stream, e->flow_events[g], 0));
+          PB_CUDA(cudaEventRecord(w->flow_events[g], helper));
+          PB_CUDA(cudaStreamWaitEvent(stream, w->flow_events[g], 0));
         }
       }
       PB_CUDA(cudaEventRecord(join, stream));
-      ++phases;
+      ++c.phases;
     }
     steps_done += steps;
-  }
-  PB_CUDA(cudaMemcpyAsync(e->pinned_status.data, e->status_word.data,
-                          sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  PB_CUDA(cudaStreamSynchronize(stream));
-  e->last_flow_kernel_ms = 0;
-  e->last_flow_kernel_launches = static_cast<std::int64_t>(launches);
-  // Device time of the flow-kernel phases (fork to join on the caller's
-  // stream; the kernels of one phase overlap each other).
-  for (std::size_t i = 0; i < phases; ++i) {
-    float elapsed = 0;
-    PB_CUDA(cudaEventElapsedTime(&elapsed, e->timing_events[2 * i],
-                                 e->timing_events[2 * i + 1]));
-    e->last_flow_kernel_ms += elapsed;
   }
   flow->time[0] = t.value;
   flow->time[1] = t.error;
@@ -821,11 +1142,6 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
   }
   if (flow->n_samples != nullptr) {
     *flow->n_samples = samples_done;
-  }
-  if (flow->status != nullptr) {
-    // The only error the right-hand side reports is the collision
-    // (ephemeris_body.hpp:383-384).
-    *flow->status = e->pinned_status.data[0] != 0 ? PB_OUT_OF_RANGE : PB_OK;
   }
   return PB_OK;
 }
@@ -837,6 +1153,9 @@ pb_status_t SrknFlowDevice(pb_ephemeris_t* e, const pb_fixed_step_flow_t* flow,
 // multistep integrators, previous_steps_.
 struct pb_fixed_step_instance {
   pb_ephemeris* ephemeris = nullptr;
+  int device = 0;
+  // Counted in ephemeris->dependants (handles created through the C ABI).
+  bool registered = false;
   int32_t method = 0;
   bool is_multistep = false;
   MultistepMethod multistep;
@@ -845,6 +1164,8 @@ struct pb_fixed_step_instance {
   DP time{0.0, 0.0};
   double* state = nullptr;  // 12 planes of n: owned_state or the caller's.
   DeviceBuffer<double> owned_state;
+  // One Solve at a time per instance.
+  std::mutex mutex;
   // Tabulated intrinsic accelerations (8 planes of n), or null.
   double const* burns = nullptr;
   DeviceBuffer<double> owned_burns;
@@ -884,19 +1205,21 @@ pb_status_t PrepareInstance(pb_fixed_step_instance* s) {
 }
 
 // Starter::FillStepFromState at the instance's current state and time.
-pb_status_t MasslessFillStep(pb_fixed_step_instance* s, int const slot,
-                             cudaStream_t stream) {
-  pb_ephemeris* const e = s->ephemeris;
-  EphemerisView const view = e->View();
-  PB_RETURN_IF_ERROR(e->stage_table.Reserve(view.stage_stride));
+pb_status_t MasslessFillStep(FlowContext& c, pb_fixed_step_instance* s,
+                             int const slot) {
+  pb_ephemeris* const e = c.e;
+  FlowWorkspace* const w = c.w();
+  EphemerisView const view = c.View();
+  PB_RETURN_IF_ERROR(w->stage_table.Reserve(view.stage_stride));
   double const t = s->time.value;
-  PB_RETURN_IF_ERROR(BuildStageTable(e, &t, 1, e->stage_table.data, stream));
+  PB_RETURN_IF_ERROR(
+      BuildStageTable(e, w, &t, 1, w->stage_table.data, c.stream));
   if (s->n > 0) {
     MasslessFillStepKernel<<<static_cast<unsigned>((s->n + kFlowThreads - 1) /
                                                    kFlowThreads),
-                             kFlowThreads, 0, stream>>>(
-        view, e->stage_table.data, t, s->burns, s->n, s->state, s->History(),
-        slot, e->status_word.data);
+                             kFlowThreads, 0, c.stream>>>(
+        view, w->stage_table.data, t, s->burns, s->n, s->state, s->History(),
+        slot, w->status_word.data);
     PB_LAUNCHED();
   }
   return PB_OK;
@@ -928,21 +1251,20 @@ pb_status_t AppendInstanceState(pb_fixed_step_instance* s, InstanceSink* sink,
 
 // Integrator::Instance::Solve(t_final) for a massless multistep instance:
 // integrators/starter_body.hpp:23-74, then
-// symmetric_linear_multistep_integrator_body.hpp:69-149.
-pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
-                                   double const t_final, InstanceSink* sink,
-                                   cudaStream_t stream) {
-  pb_ephemeris* const e = s->ephemeris;
+// symmetric_linear_multistep_integrator_body.hpp:69-149.  The context has been
+// begun and holds the constants.
+pb_status_t SolveMultistepInstance(FlowContext& c, pb_fixed_step_instance* s,
+                                   double const t_final, InstanceSink* sink) {
+  pb_ephemeris* const e = c.e;
+  FlowWorkspace* const w = c.w();
+  cudaStream_t const stream = c.stream;
   PB_RETURN_IF_ERROR(PrepareInstance(s));
-  PB_RETURN_IF_ERROR(UploadSegments(e, stream));
-  PB_RETURN_IF_ERROR(
-      UploadFlowConstants(e, s->time.value, s->n, s->state, stream));
-  EphemerisView const view = e->View();
+  EphemerisView const view = c.View();
   double const h = s->step;
   int const order = s->multistep.order;
   if (s->previous_steps < order) {
     if (s->previous_steps == 0) {
-      PB_RETURN_IF_ERROR(MasslessFillStep(s, 0, stream));
+      PB_RETURN_IF_ERROR(MasslessFillStep(c, s, 0));
       s->previous_steps = 1;
     }
     double const startup_step = h / kStartupStepDivisor;
@@ -961,7 +1283,6 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
           kStartupStepDivisor - s->startup_step_index % kStartupStepDivisor;
       double time[2] = {s->time.value, s->time.error};
       int64_t steps_taken = 0;
-      pb_status_t flow_status = PB_OK;
       pb_fixed_step_flow_t flow{};
       flow.method = PB_BLANES_MOAN_2002_SRKN_14A;
       flow.step = startup_step;
@@ -970,13 +1291,16 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
       flow.state = s->state;
       flow.time = time;
       flow.n_steps = &steps_taken;
-      flow.status = &flow_status;
       flow.burns = s->burns;
-      PB_RETURN_IF_ERROR(SrknFlowDevice(e, &flow, stream, wanted));
+      PB_RETURN_IF_ERROR(SrknSteps(c, &flow, wanted));
       s->time = {time[0], time[1]};
       s->startup_step_index += steps_taken;
+      if (c.cancelled) {
+        // The startup target stays: the next Solve continues towards it.
+        return PB_OK;
+      }
       if (steps_taken == wanted) {
-        PB_RETURN_IF_ERROR(MasslessFillStep(s, s->previous_steps, stream));
+        PB_RETURN_IF_ERROR(MasslessFillStep(c, s, s->previous_steps));
         ++s->previous_steps;
         PB_RETURN_IF_ERROR(AppendInstanceState(s, sink, stream));
       } else {
@@ -993,18 +1317,26 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
   // (startup_instance->Solve(...).IgnoreError(), starter_body.hpp:68-73) and of
   // FillStepFromState (symmetric_linear_multistep_integrator_body.hpp:258-261):
   // only the steps below report collisions.
-  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
+  PB_CUDA(cudaMemsetAsync(w->status_word.data, 0, sizeof(int32_t), stream));
   // Multistep steps, fused `chunk_steps` at a time.
   int const chunk_steps = 256;
-  PB_RETURN_IF_ERROR(e->stage_table.Reserve(
+  PB_RETURN_IF_ERROR(w->stage_table.Reserve(
       static_cast<std::size_t>(chunk_steps) * view.stage_stride));
-  PB_RETURN_IF_ERROR(e->pinned_times.Reserve(chunk_steps));
-  std::size_t phases = 0;
-  e->last_flow_kernel_launches = 0;
+  PB_RETURN_IF_ERROR(w->pinned_times.Reserve(chunk_steps));
+  int sm_count = 0;
+  PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
+                                 e->device));
   while (h <= (t_final - s->time.value) - s->time.error) {
-    int steps = 0;
-    double* const times = e->pinned_times.data;
+    // The pinned staging buffer is reused across chunks; a stop request is
+    // honoured here, between chunks (RETURN_IF_STOPPED,
+    // symmetric_linear_multistep_integrator_body.hpp:149).
     PB_CUDA(cudaStreamSynchronize(stream));
+    if (e->stop_requested.load() != 0) {
+      c.cancelled = true;
+      break;
+    }
+    int steps = 0;
+    double* const times = w->pinned_times.data;
     long long const appended_before = sink->appended;
     DP t = s->time;
     while (steps < chunk_steps && h <= (t_final - t.value) - t.error) {
@@ -1023,37 +1355,22 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
       }
     }
     PB_RETURN_IF_ERROR(
-        BuildStageTable(e, times, steps, e->stage_table.data, stream));
+        BuildStageTable(e, w, times, steps, w->stage_table.data, stream));
     if (s->n > 0) {
-      while (e->timing_events.size() < 2 * (phases + 1)) {
-        cudaEvent_t event;
-        PB_CUDA(cudaEventCreate(&event));
-        e->timing_events.push_back(event);
-      }
       // Probe slices x step sub-chunks on helper streams, as in the SRKN flow
       // (no last-wave tail: 1.91 -> 2.04 10^9 probe-steps/s on 10^5 probes).
-      int sm_count = 0;
-      PB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount,
-                                     e->device));
       bool const wide = MultistepWide(s->n, sm_count);
       int const threads = wide ? 256 : kFlowThreads;
       long long const blocks = (s->n + threads - 1) / threads;
       int const groups = static_cast<int>(
           std::min<long long>(FlowGroups(), std::max<long long>(1, blocks / 64)));
       int const sub_steps = groups > 1 ? FlowSubSteps() : steps;
-      while (static_cast<int>(e->flow_streams.size()) < groups) {
-        cudaStream_t helper;
-        PB_CUDA(cudaStreamCreateWithFlags(&helper, cudaStreamNonBlocking));
-        e->flow_streams.push_back(helper);
-        cudaEvent_t event;
-        PB_CUDA(cudaEventCreateWithFlags(&event, cudaEventDisableTiming));
-        e->flow_events.push_back(event);
-      }
-      cudaEvent_t const fork = e->timing_events[2 * phases];
+      PB_RETURN_IF_ERROR(c.EnsureHelpers(groups));
+      cudaEvent_t const fork = w->timing_events[2 * c.phases];
       PB_CUDA(cudaEventRecord(fork, stream));
       bool const sampling = sink->samples != nullptr && sink->sample_every > 0;
       for (int g = 0; g < groups; ++g) {
-        cudaStream_t const helper = groups > 1 ? e->flow_streams[g] : stream;
+        cudaStream_t const helper = groups > 1 ? w->flow_streams[g] : stream;
         if (groups > 1) {
           PB_CUDA(cudaStreamWaitEvent(helper, fork, 0));
         }
@@ -1068,12 +1385,12 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
   MasslessMultistepFlowKernel<kOrder, kThreads, kMinBlocks>                   \
       <<<grid, kThreads, 0, helper>>>(                                        \
           view, s->multistep, h,                                              \
-          e->stage_table.data +                                               \
+          w->stage_table.data +                                               \
               static_cast<std::size_t>(s0) * view.stage_stride,               \
-          e->stage_times.data + s0, s->burns, n_sub, s->n, i_begin, i_end,    \
+          w->stage_times.data + s0, s->burns, n_sub, s->n, i_begin, i_end,    \
           s->state, s->History(), (s->oldest + s0) % order,                   \
           appended_before + s0, sampling ? sink->sample_every : 0,            \
-          sink->max_samples, sink->samples, e->status_word.data)
+          sink->max_samples, sink->samples, w->status_word.data)
           if (order == 8) {
             if (wide) {
               PB_LAUNCH_MULTISTEP(8, 256, 2);
@@ -1089,35 +1406,29 @@ pb_status_t SolveMultistepInstance(pb_fixed_step_instance* s,
           }
 #undef PB_LAUNCH_MULTISTEP
           PB_LAUNCHED();
-          ++e->last_flow_kernel_launches;
+          ++c.launches;
         }
         if (groups > 1) {
-          PB_CUDA(cudaEventRecord(e->flow_events[g], helper));
-          PB_CUDA(cudaStreamWaitEvent(stream, e->flow_events[g], 0));
+          PB_CUDA(cudaEventRecord(w->flow_events[g], helper));
+          PB_CUDA(cudaStreamWaitEvent(stream, w->flow_events[g], 0));
         }
       }
-      PB_CUDA(cudaEventRecord(e->timing_events[2 * phases + 1], stream));
-      ++phases;
+      PB_CUDA(cudaEventRecord(w->timing_events[2 * c.phases + 1], stream));
+      ++c.phases;
     }
     s->oldest = (s->oldest + steps) % order;
     s->time = t;
-  }
-  PB_CUDA(cudaStreamSynchronize(stream));
-  e->last_flow_kernel_ms = 0;
-  for (std::size_t i = 0; i < phases; ++i) {
-    float elapsed = 0;
-    PB_CUDA(cudaEventElapsedTime(&elapsed, e->timing_events[2 * i],
-                                 e->timing_events[2 * i + 1]));
-    e->last_flow_kernel_ms += elapsed;
   }
   return PB_OK;
 }
 
 // Instance::Solve(t_final) for either family; the outs of `flow` are filled.
-pb_status_t SolveInstance(pb_fixed_step_instance* s,
-                          const pb_fixed_step_flow_t* flow,
-                          cudaStream_t stream) {
-  pb_ephemeris* const e = s->ephemeris;
+// Returns PB_CANCELLED if a stop request cut the flow short (the instance is
+// then at its last completed step and can be solved further).
+pb_status_t SolveInstance(FlowContext& c, pb_fixed_step_instance* s,
+                          const pb_fixed_step_flow_t* flow) {
+  PB_RETURN_IF_ERROR(
+      c.AcquireConstants(s->time.value, s->n, s->state, nullptr));
   if (!s->is_multistep) {
     pb_fixed_step_flow_t srkn = *flow;
     srkn.method = s->method;
@@ -1125,42 +1436,39 @@ pb_status_t SolveInstance(pb_fixed_step_instance* s,
     srkn.n = s->n;
     srkn.state = s->state;
     srkn.burns = s->burns;
+    srkn.status = nullptr;
     double time[2] = {s->time.value, s->time.error};
     srkn.time = time;
-    PB_RETURN_IF_ERROR(SrknFlowDevice(e, &srkn, stream,
-                                      std::numeric_limits<long long>::max()));
+    PB_RETURN_IF_ERROR(
+        SrknSteps(c, &srkn, std::numeric_limits<long long>::max()));
     s->time = {time[0], time[1]};
-    return PB_OK;
+    PB_RETURN_IF_ERROR(c.Finish(flow->status));
+    return c.cancelled ? Fail(PB_CANCELLED, "stop requested") : PB_OK;
   }
-  PB_CUDA(cudaMemsetAsync(e->status_word.data, 0, sizeof(int32_t), stream));
   InstanceSink sink{flow->sample_every, flow->max_samples, flow->samples,
                     flow->sample_times};
-  PB_RETURN_IF_ERROR(SolveMultistepInstance(s, flow->t_final, &sink, stream));
-  PB_CUDA(cudaMemcpyAsync(e->pinned_status.data, e->status_word.data,
-                          sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-  PB_CUDA(cudaStreamSynchronize(stream));
+  PB_RETURN_IF_ERROR(SolveMultistepInstance(c, s, flow->t_final, &sink));
+  PB_RETURN_IF_ERROR(c.Finish(flow->status));
   if (flow->n_steps != nullptr) {
     *flow->n_steps = sink.appended;
   }
   if (flow->n_samples != nullptr) {
     *flow->n_samples = sink.recorded;
   }
-  if (flow->status != nullptr) {
-    *flow->status = e->pinned_status.data[0] != 0 ? PB_OUT_OF_RANGE : PB_OK;
-  }
-  return PB_OK;
+  return c.cancelled ? Fail(PB_CANCELLED, "stop requested") : PB_OK;
 }
 
-pb_status_t MultistepFlowDevice(pb_ephemeris_t* e,
-                                const pb_fixed_step_flow_t* flow,
-                                cudaStream_t stream) {
+// NewInstance + FlowWithFixedStep in one call for a multistep method: the
+// instance (and the history it would keep) lives for this call only.
+pb_status_t MultistepFlowDevice(FlowContext& c,
+                                const pb_fixed_step_flow_t* flow) {
   if (!(flow->step > 0)) {
     return Fail(PB_INVALID_ARGUMENT,
                 "the multistep massless flow integrates forward");
   }
-  PB_CUDA(cudaSetDevice(e->device));
   pb_fixed_step_instance instance;
-  instance.ephemeris = e;
+  instance.ephemeris = c.e;
+  instance.device = c.e->device;
   instance.method = flow->method;
   instance.is_multistep = true;
   MakeMultistepMethod(flow->method, instance.multistep);
@@ -1169,12 +1477,10 @@ pb_status_t MultistepFlowDevice(pb_ephemeris_t* e,
   instance.time = {flow->time[0], flow->time[1]};
   instance.state = flow->state;
   instance.burns = flow->burns;
-  PB_RETURN_IF_ERROR(e->pinned_status.Reserve(1));
-  PB_RETURN_IF_ERROR(e->status_word.Reserve(1));
-  PB_RETURN_IF_ERROR(SolveInstance(&instance, flow, stream));
+  pb_status_t const status = SolveInstance(c, &instance, flow);
   flow->time[0] = instance.time.value;
   flow->time[1] = instance.time.error;
-  return PB_OK;
+  return status;
 }
 
 }  // namespace
@@ -1197,6 +1503,7 @@ pb_status_t pb_fixed_step_instance_create(pb_ephemeris_t* e, int32_t method,
   PB_CUDA(cudaSetDevice(e->device));
   auto* s = new pb_fixed_step_instance;
   s->ephemeris = e;
+  s->device = e->device;
   s->method = method;
   s->step = step;
   s->n = n;
@@ -1223,13 +1530,22 @@ pb_status_t pb_fixed_step_instance_create(pb_ephemeris_t* e, int32_t method,
     return status;
   }
   s->state = s->owned_state.data;
+  s->registered = true;
+  e->dependants.fetch_add(1);
   *instance = s;
   return PB_OK;
 }
 
 void pb_fixed_step_instance_destroy(pb_fixed_step_instance_t* instance) {
+  PB_API_RANGE();
   if (instance != nullptr) {
-    cudaSetDevice(instance->ephemeris->device);
+    // The device ordinal is the instance's own copy; the ephemeris cannot have
+    // been destroyed under a registered instance (pb_ephemeris_destroy
+    // refuses).
+    cudaSetDevice(instance->device);
+    if (instance->registered) {
+      instance->ephemeris->dependants.fetch_sub(1);
+    }
     delete instance;
   }
 }
@@ -1239,7 +1555,7 @@ pb_status_t pb_fixed_step_instance_set_intrinsic_accelerations(
   if (s == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null instance");
   }
-  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  PB_CUDA(cudaSetDevice(s->device));
   if (burns == nullptr) {
     s->burns = nullptr;
     return PB_OK;
@@ -1257,13 +1573,16 @@ pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* s,
                                         double* sample_times,
                                         int64_t* n_steps, int64_t* n_samples,
                                         pb_status_t* flow_status) {
-  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
+  PB_API_RANGE();
   if (s == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null instance");
   }
-  pb_ephemeris* const e = s->ephemeris;
-  PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
+  // An instance is not a concurrent object (one Solve at a time, as in the
+  // reference); distinct instances flow concurrently.
+  std::lock_guard<std::mutex> const instance_lock(s->mutex);
+  FlowContext c;
+  PB_RETURN_IF_ERROR(c.Begin(s->ephemeris, false, nullptr));
+  FlowWorkspace* const w = c.w();
   std::size_t const n = static_cast<std::size_t>(s->n);
   bool const sampling =
       samples != nullptr && sample_every > 0 && max_samples > 0;
@@ -1278,36 +1597,39 @@ pb_status_t pb_fixed_step_instance_flow(pb_fixed_step_instance_t* s,
   flow.status = flow_status;
   if (sampling) {
     PB_RETURN_IF_ERROR(
-        e->scratch_c.Reserve(static_cast<std::size_t>(max_samples) * 6 * n));
-    flow.samples = e->scratch_c.data;
+        w->scratch_c.Reserve(static_cast<std::size_t>(max_samples) * 6 * n));
+    flow.samples = w->scratch_c.data;
   }
-  PB_RETURN_IF_ERROR(e->pinned_status.Reserve(1));
-  PB_RETURN_IF_ERROR(e->status_word.Reserve(1));
-  PB_RETURN_IF_ERROR(SolveInstance(s, &flow, stream));
+  pb_status_t const status = SolveInstance(c, s, &flow);
+  if (status != PB_OK && status != PB_CANCELLED) {
+    return status;
+  }
   if (sampling && recorded > 0 && n > 0) {
     PB_CUDA(cudaMemcpyAsync(
-        samples, e->scratch_c.data,
+        samples, w->scratch_c.data,
         static_cast<std::size_t>(recorded) * 6 * n * sizeof(double),
-        cudaMemcpyDeviceToHost, stream));
+        cudaMemcpyDeviceToHost, c.stream));
   }
-  PB_CUDA(cudaStreamSynchronize(stream));
+  PB_CUDA(cudaStreamSynchronize(c.stream));
   if (n_samples != nullptr) {
     *n_samples = recorded;
   }
-  return PB_OK;
+  return status;
 }
 
 pb_status_t pb_fixed_step_instance_flow_to_downsampler(
     pb_fixed_step_instance_t* s, double t_final,
     pb_downsampler_t* downsampler, int64_t* n_steps,
     pb_status_t* flow_status) {
-  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
+  PB_API_RANGE();
   if (s == nullptr || downsampler == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null argument");
   }
-  pb_ephemeris* const e = s->ephemeris;
-  PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
+  std::lock_guard<std::mutex> const instance_lock(s->mutex);
+  FlowContext c;
+  PB_RETURN_IF_ERROR(c.Begin(s->ephemeris, false, nullptr));
+  FlowWorkspace* const w = c.w();
+  cudaStream_t const stream = c.stream;
   std::size_t const n = static_cast<std::size_t>(s->n);
   // States per chunk: at most 64 MiB of samples on the device.
   long long const chunk = std::max<long long>(
@@ -1317,12 +1639,11 @@ pb_status_t pb_fixed_step_instance_flow_to_downsampler(
   // instance sits between two steps of a multistep startup.
   long long const slots = chunk + 2;
   PB_RETURN_IF_ERROR(
-      e->scratch_c.Reserve(static_cast<std::size_t>(slots) * 6 * n + 1));
-  PB_RETURN_IF_ERROR(e->pinned_status.Reserve(1));
-  PB_RETURN_IF_ERROR(e->status_word.Reserve(1));
+      w->scratch_c.Reserve(static_cast<std::size_t>(slots) * 6 * n + 1));
   std::vector<double> sample_times(slots);
   int64_t total_steps = 0;
   pb_status_t overall = PB_OK;
+  pb_status_t result = PB_OK;
   double const abs_step = std::abs(s->step);
   for (;;) {
     // Instance::Solve(t) for the next `chunk` steps at most; during the startup
@@ -1342,7 +1663,7 @@ pb_status_t pb_fixed_step_instance_flow_to_downsampler(
     flow.t_final = t_chunk;
     flow.sample_every = 1;
     flow.max_samples = slots;
-    flow.samples = e->scratch_c.data;
+    flow.samples = w->scratch_c.data;
     flow.sample_times = sample_times.data();
     int64_t steps = 0, recorded = 0;
     pb_status_t status = PB_OK;
@@ -1350,28 +1671,33 @@ pb_status_t pb_fixed_step_instance_flow_to_downsampler(
     flow.n_samples = &recorded;
     flow.status = &status;
     DP const before = s->time;
-    PB_RETURN_IF_ERROR(SolveInstance(s, &flow, stream));
+    result = SolveInstance(c, s, &flow);
+    if (result != PB_OK && result != PB_CANCELLED) {
+      return result;
+    }
     if (recorded != steps) {
       return Fail(PB_INTERNAL, "more states appended than the chunk holds");
     }
     PB_RETURN_IF_ERROR(pb_downsampler_append_device(
-        downsampler, recorded, sample_times.data(), e->scratch_c.data,
+        downsampler, recorded, sample_times.data(), w->scratch_c.data,
         stream));
     total_steps += steps;
     if (overall == PB_OK) {
       overall = status;
     }
-    if (s->time.value == before.value && s->time.error == before.error) {
-      break;  // No progress: t_final is closer than one step.
+    if (result == PB_CANCELLED ||
+        (s->time.value == before.value && s->time.error == before.error)) {
+      break;  // Stopped, or no progress: t_final is closer than one step.
     }
   }
+  PB_CUDA(cudaStreamSynchronize(stream));
   if (n_steps != nullptr) {
     *n_steps = total_steps;
   }
   if (flow_status != nullptr) {
     *flow_status = overall;
   }
-  return PB_OK;
+  return result;
 }
 
 // The checkpoint of an instance: a header of kCheckpointHeader doubles, the
@@ -1401,11 +1727,12 @@ int64_t pb_fixed_step_instance_checkpoint_size(
 
 pb_status_t pb_fixed_step_instance_write_checkpoint(
     pb_fixed_step_instance_t* s, double* checkpoint) {
+  PB_API_RANGE();
   if (s == nullptr || checkpoint == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null argument");
   }
-  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
-  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  std::lock_guard<std::mutex> const instance_lock(s->mutex);
+  PB_CUDA(cudaSetDevice(s->device));
   std::size_t const n = static_cast<std::size_t>(s->n);
   bool const has_history =
       s->is_multistep && s->displacement_value.data != nullptr;
@@ -1515,7 +1842,8 @@ pb_status_t pb_fixed_step_instance_get_state(pb_fixed_step_instance_t* s,
   if (s == nullptr) {
     return Fail(PB_INVALID_ARGUMENT, "null instance");
   }
-  PB_CUDA(cudaSetDevice(s->ephemeris->device));
+  std::lock_guard<std::mutex> const instance_lock(s->mutex);
+  PB_CUDA(cudaSetDevice(s->device));
   if (s->n > 0 && state != nullptr) {
     PB_CUDA(cudaMemcpy(state, s->state,
                        12 * static_cast<std::size_t>(s->n) * sizeof(double),
@@ -1528,10 +1856,12 @@ pb_status_t pb_fixed_step_instance_get_state(pb_fixed_step_instance_t* s,
   return PB_OK;
 }
 
-pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
-                                           const pb_fixed_step_flow_t* flow,
-                                           void* stream_pointer) {
-  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
+}  // extern "C"
+
+namespace {
+
+pb_status_t ValidateFixedStepFlow(pb_ephemeris_t* e,
+                                  const pb_fixed_step_flow_t* flow) {
   if (e == nullptr || flow == nullptr || flow->n < 0 || flow->time == nullptr ||
       (flow->n > 0 && flow->state == nullptr)) {
     return Fail(PB_INVALID_ARGUMENT, "bad argument");
@@ -1539,53 +1869,84 @@ pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
   if (flow->step == 0 || flow->step != flow->step) {
     return Fail(PB_INVALID_ARGUMENT, "CHECK_NE(Time(), step)");
   }
+  if (flow->time[0] != flow->time[0] || flow->t_final != flow->t_final) {
+    return Fail(PB_INVALID_ARGUMENT, "NaN time");
+  }
+  return PB_OK;
+}
+
+// NewInstance + FlowWithFixedStep on device state.  `probe_host`: see
+// AcquireFlowConstants.
+pb_status_t FixedStepFlowDevice(FlowContext& c,
+                                const pb_fixed_step_flow_t* flow,
+                                double const* const probe_host) {
+  PB_RETURN_IF_ERROR(
+      c.AcquireConstants(flow->time[0], flow->n, flow->state, probe_host));
   MultistepMethod multistep;
   if (MakeMultistepMethod(flow->method, multistep)) {
-    // NewInstance + FlowWithFixedStep in one call: the instance (and the
-    // history it would keep) lives for this call only.
-    return MultistepFlowDevice(e, flow,
-                               static_cast<cudaStream_t>(stream_pointer));
+    return MultistepFlowDevice(c, flow);
   }
-  return SrknFlowDevice(e, flow, stream_pointer,
-                        std::numeric_limits<long long>::max());
+  pb_fixed_step_flow_t srkn = *flow;
+  srkn.status = nullptr;
+  PB_RETURN_IF_ERROR(
+      SrknSteps(c, &srkn, std::numeric_limits<long long>::max()));
+  PB_RETURN_IF_ERROR(c.Finish(flow->status));
+  return c.cancelled ? Fail(PB_CANCELLED, "stop requested") : PB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+pb_status_t pb_flow_with_fixed_step_device(pb_ephemeris_t* e,
+                                           const pb_fixed_step_flow_t* flow,
+                                           void* stream_pointer) {
+  PB_API_RANGE();
+  PB_RETURN_IF_ERROR(ValidateFixedStepFlow(e, flow));
+  FlowContext c;
+  PB_RETURN_IF_ERROR(
+      c.Begin(e, true, static_cast<cudaStream_t>(stream_pointer)));
+  return FixedStepFlowDevice(c, flow, nullptr);
 }
 
 pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* e,
                                     const pb_fixed_step_flow_t* flow) {
-  std::lock_guard<std::recursive_mutex> const flow_lock(FlowMutex());
-  if (e == nullptr || flow == nullptr || flow->n < 0 ||
-      (flow->n > 0 && flow->state == nullptr)) {
-    return Fail(PB_INVALID_ARGUMENT, "bad argument");
-  }
-  PB_CUDA(cudaSetDevice(e->device));
-  cudaStream_t const stream = nullptr;
+  PB_API_RANGE();
+  PB_RETURN_IF_ERROR(ValidateFixedStepFlow(e, flow));
+  FlowContext c;
+  PB_RETURN_IF_ERROR(c.Begin(e, false, nullptr));
+  FlowWorkspace* const w = c.w();
+  cudaStream_t const stream = c.stream;
   std::size_t const n = static_cast<std::size_t>(flow->n);
-  PB_RETURN_IF_ERROR(e->scratch_a.Upload(flow->state, 12 * n, stream));
+  PB_RETURN_IF_ERROR(w->scratch_a.Upload(flow->state, 12 * n, stream));
   pb_fixed_step_flow_t device_flow = *flow;
-  device_flow.state = e->scratch_a.data;
+  device_flow.state = w->scratch_a.data;
   if (flow->burns != nullptr) {
     PB_RETURN_IF_ERROR(
-        e->burns_scratch.Upload(flow->burns, PB_BURN_PLANES * n, stream));
-    device_flow.burns = e->burns_scratch.data;
+        w->burns_scratch.Upload(flow->burns, PB_BURN_PLANES * n, stream));
+    device_flow.burns = w->burns_scratch.data;
   }
   bool const sampling = flow->samples != nullptr && flow->sample_every > 0 &&
                         flow->max_samples > 0;
   if (sampling) {
-    PB_RETURN_IF_ERROR(e->scratch_c.Reserve(
+    PB_RETURN_IF_ERROR(w->scratch_c.Reserve(
         static_cast<std::size_t>(flow->max_samples) * 6 * n));
-    device_flow.samples = e->scratch_c.data;
+    device_flow.samples = w->scratch_c.data;
   } else {
     device_flow.samples = nullptr;
   }
   int64_t n_samples = 0;
   device_flow.n_samples = &n_samples;
-  PB_RETURN_IF_ERROR(pb_flow_with_fixed_step_device(e, &device_flow, stream));
+  pb_status_t const status = FixedStepFlowDevice(c, &device_flow, flow->state);
+  if (status != PB_OK && status != PB_CANCELLED) {
+    return status;
+  }
   if (n > 0) {
-    PB_CUDA(cudaMemcpyAsync(flow->state, e->scratch_a.data,
+    PB_CUDA(cudaMemcpyAsync(flow->state, w->scratch_a.data,
                             12 * n * sizeof(double), cudaMemcpyDeviceToHost,
                             stream));
     if (sampling && n_samples > 0) {
-      PB_CUDA(cudaMemcpyAsync(flow->samples, e->scratch_c.data,
+      PB_CUDA(cudaMemcpyAsync(flow->samples, w->scratch_c.data,
                               static_cast<std::size_t>(n_samples) * 6 * n *
                                   sizeof(double),
                               cudaMemcpyDeviceToHost, stream));
@@ -1595,15 +1956,33 @@ pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* e,
   if (flow->n_samples != nullptr) {
     *flow->n_samples = n_samples;
   }
-  return PB_OK;
+  return status;
 }
 
 double pb_ephemeris_last_flow_kernel_ms(const pb_ephemeris_t* e,
                                         int64_t* launches) {
+  std::lock_guard<std::mutex> const lock(e->statistics_mutex);
   if (launches != nullptr) {
     *launches = e->last_flow_kernel_launches;
   }
   return e->last_flow_kernel_ms;
+}
+
+pb_status_t pb_ephemeris_last_flow_path(const pb_ephemeris_t* e,
+                                        int32_t* hot_body,
+                                        int32_t* generic_harmonics) {
+  if (e == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "null ephemeris");
+  }
+  std::lock_guard<std::mutex> const lock(e->statistics_mutex);
+  if (hot_body != nullptr) {
+    *hot_body = e->last_flow_hot_body;
+  }
+  if (generic_harmonics != nullptr) {
+    *generic_harmonics =
+        (e->last_flow_path_flags & kPathGenericHarmonics) != 0 ? 1 : 0;
+  }
+  return PB_OK;
 }
 
 pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,

@@ -26,6 +26,15 @@ def _check(code):
     raise StatusError(code, _capi.last_error())
 
 
+def _check_flow(code):
+  """A flow cut short by request_stop is not an error: its outputs describe the
+  last completed step.  Returns whether the flow was cancelled."""
+  if code == _capi.PB_CANCELLED:
+    return True
+  _check(code)
+  return False
+
+
 def _dptr(array):
   return array.ctypes.data_as(_capi.c_double_p)
 
@@ -207,6 +216,8 @@ class Ephemeris:
     time: (2,) float64; both updated in place (host buffers).  burns: the
     intrinsic accelerations, tabulated (8, n), or None."""
     assert state.flags.c_contiguous and state.dtype == np.float64
+    assert time.flags.c_contiguous and time.dtype == np.float64
+    assert state.shape[0] == 12 and time.shape == (2,)
     n = state.shape[1]
     samples = sample_times = None
     if sample_every > 0 and max_samples > 0:
@@ -220,9 +231,10 @@ class Ephemeris:
       burns = np.ascontiguousarray(burns, dtype=np.float64)
       assert burns.shape == (8, n)
       flow.burns = burns.ctypes.data
-    _check(self.lib.pb_flow_with_fixed_step(self.handle, ctypes.byref(flow)))
+    cancelled = _check_flow(
+        self.lib.pb_flow_with_fixed_step(self.handle, ctypes.byref(flow)))
     n_samples, n_steps, status = (o.value for o in outs)
-    return dict(n_steps=n_steps, status=status,
+    return dict(n_steps=n_steps, status=status, cancelled=cancelled,
                 samples=None if samples is None else samples[:n_samples],
                 sample_times=None if samples is None
                 else sample_times[:n_samples])
@@ -233,9 +245,10 @@ class Ephemeris:
     doubles)."""
     flow, outs = self._fixed_step_flow(method, step, t_final, n, state_pointer,
                                        time, 0, 0, None, None)
-    _check(self.lib.pb_flow_with_fixed_step_device(self.handle,
-                                                   ctypes.byref(flow), stream))
-    return dict(n_steps=outs[1].value, status=outs[2].value)
+    cancelled = _check_flow(self.lib.pb_flow_with_fixed_step_device(
+        self.handle, ctypes.byref(flow), stream))
+    return dict(n_steps=outs[1].value, status=outs[2].value,
+                cancelled=cancelled)
 
   def new_instance(self, method, step, state, time):
     """Ephemeris::NewInstance over n massless trajectories (state (12, n),
@@ -249,6 +262,22 @@ class Ephemeris:
                                                    ctypes.byref(launches))
     return ms, launches.value
 
+  def last_flow_path(self):
+    """(hot body (caller index, -1: none), whether some probe took the slow
+    generic harmonics) of the last fixed-step flow."""
+    hot, generic = ctypes.c_int32(), ctypes.c_int32()
+    _check(self.lib.pb_ephemeris_last_flow_path(self.handle, ctypes.byref(hot),
+                                                ctypes.byref(generic)))
+    return hot.value, bool(generic.value)
+
+  def request_stop(self):
+    """RETURN_IF_STOPPED: the flows in progress return PB_CANCELLED with the
+    state of their last completed step.  Any thread."""
+    _check(self.lib.pb_ephemeris_request_stop(self.handle))
+
+  def clear_stop(self):
+    _check(self.lib.pb_ephemeris_clear_stop(self.handle))
+
   def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
                               speed_tolerance, max_steps=2**62,
                               step_log_capacity=0, sink=None, burns=None,
@@ -256,6 +285,8 @@ class Ephemeris:
     """FlowWithAdaptiveStep, one trajectory per probe.  state: (12, n),
     time: (2, n); updated in place (host buffers)."""
     assert state.flags.c_contiguous and time.flags.c_contiguous
+    assert state.dtype == np.float64 and time.dtype == np.float64
+    assert state.shape[0] == 12 and time.shape == (2, state.shape[1])
     n = state.shape[1]
     flow = _capi.AdaptiveStepFlow()
     flow.method = method
@@ -289,10 +320,11 @@ class Ephemeris:
       # A trajectory.Downsampler: every accepted state is appended to it inside
       # the kernel.
       flow.sink = sink.handle
-    _check(self.lib.pb_flow_with_adaptive_step(self.handle,
-                                               ctypes.byref(flow)))
+    cancelled = _check_flow(
+        self.lib.pb_flow_with_adaptive_step(self.handle, ctypes.byref(flow)))
     return dict(status=status, accepted=accepted, rejected=rejected,
-                evaluations=evaluations, step_log=step_log)
+                evaluations=evaluations, step_log=step_log,
+                cancelled=cancelled)
 
 
 class FixedStepInstance:
@@ -353,12 +385,13 @@ class FixedStepInstance:
       sample_times = np.zeros(max_samples)
     n_steps, n_samples = ctypes.c_int64(), ctypes.c_int64()
     status = ctypes.c_int32()
-    _check(self.lib.pb_fixed_step_instance_flow(
+    cancelled = _check_flow(self.lib.pb_fixed_step_instance_flow(
         self.handle, t_final, sample_every, max_samples,
         None if samples is None else _dptr(samples),
         None if samples is None else _dptr(sample_times),
         ctypes.byref(n_steps), ctypes.byref(n_samples), ctypes.byref(status)))
     return dict(n_steps=n_steps.value, status=status.value,
+                cancelled=cancelled,
                 samples=None if samples is None
                 else samples[:n_samples.value],
                 sample_times=None if samples is None

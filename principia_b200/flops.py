@@ -108,3 +108,79 @@ if __name__ == '__main__':
   print('geopotential zonal J2 damped', geopotential(2, True, (2,)))
   print('probe-stage (Sol, LEO)', massless_probe_stage_sol_leo())
   print('SRKN14A probe-step', srkn14a_probe_step_sol_leo())
+
+
+# ---------------------------------------------------------------------------
+# Secondary configurations (bench.py `secondary`).
+
+ALL_PAIRS_INTERACTION = 18  # POINT_MASS_PAIR without the collision test.
+
+# DoublePrecision arithmetic (pb_math.cuh): TwoSum / TwoDifference 6,
+# QuickTwoSum 3, Add / Subtract = 2 x 6 + 1 + 3 + 1 + 3, Scale 2, Increment 4.
+DP_ADD = 20
+DP_SCALE = 2
+DP_INCREMENT = 4
+
+
+def multistep_component_step(order):
+  """One coordinate of one body through one step of
+  SymmetricLinearMultistepIntegrator::Instance::Solve
+  (pb_kernels_nbody.cuh EnsembleMultistepStepKernel): the double-double sum of
+  the displacements, the weighted accelerations, the new position and the
+  Cohen-Hubbard-Oesterwinter velocity."""
+  half = order // 2
+  flops = DP_SCALE + 1                                  # j = 0.
+  flops += (half - 1) * (2 * (DP_SCALE + DP_ADD) + 3)   # j paired with k - j.
+  flops += DP_SCALE + DP_ADD + 2                        # j = k / 2.
+  flops += 3 + DP_INCREMENT                             # h² Σ / denominator.
+  flops += DP_ADD                                       # Position.
+  flops += DP_ADD + 2 + 2 * order + 3                   # Velocity.
+  return flops
+
+
+def ensemble_system_step(n_bodies, order, active_harmonics, damped_harmonics,
+                         idle_harmonics):
+  """One multistep step of one system of an ensemble: every ordered pair's
+  point-mass term (the kernel evaluates each pair from both bodies), the
+  degree-2 zonal harmonics of the oblate sources within their outer threshold
+  (`damped_harmonics` of the `active_harmonics` beyond the inner threshold),
+  the range tests of the others, and the multistep arithmetic."""
+  flops = n_bodies * (n_bodies - 1) * ALL_PAIRS_INTERACTION
+  undamped = active_harmonics - damped_harmonics
+  flops += undamped * (geopotential(2, zonal=True) + 6)
+  flops += damped_harmonics * (geopotential(2, zonal=True,
+                                            damped_degrees=(2,)) + 6)
+  flops += idle_harmonics * (2 + 6)
+  flops += 3 * n_bodies * multistep_component_step(order)
+  return flops
+
+
+def ensemble_system_step_bytes(n_bodies, order):
+  """HBM bytes of the same step: the history ring (displacement value, error
+  and acceleration of `order` steps) is read once for the sum and its
+  accelerations once more for the velocity; one slot and the 12 planes of the
+  state are written."""
+  per_component = (3 * order + order + 2) * 8 + 3 * 8 + 4 * 8
+  return 3 * n_bodies * per_component
+
+
+ERKN_STEP_OVERHEAD = 4 * 3 * 8 + 2 * 3 * 4 + 2 * 6 + 7 * DP_INCREMENT + 30
+
+
+def adaptive_rhs_evaluation(earth_degree, polynomial_degree, n_bodies=34,
+                            moon_j2=True):
+  """One right-hand-side evaluation of the adaptive flow at a per-probe time:
+  the Estrin evaluation of every body's three polynomials (2 flops per
+  coefficient), the point masses, the Earth's field truncated at
+  `earth_degree` (0: beyond the outer threshold of degree 2) and the stage
+  arithmetic."""
+  flops = n_bodies * (3 * 2 * polynomial_degree + 1 + POINT_MASS_PAIR)
+  if earth_degree >= 2:
+    flops += geopotential(earth_degree, zonal=False) + 6
+  else:
+    flops += 2 + 6
+  if moon_j2:
+    flops += geopotential(2, zonal=True, damped_degrees=(2,)) + 6
+  flops += 9 * (2 + 6)
+  flops += 3 * 8 + 9  # q_stage from the stage sums.
+  return flops
