@@ -1033,21 +1033,19 @@ pb_status_t SrknSteps(FlowContext& c, const pb_fixed_step_flow_t* flow,
 
   long long steps_done = 0;
   long long samples_done = 0;
-  bool first_chunk = true;
   while (steps_done < max_steps &&
          abs_h <= std::abs((t_final - t.value) - t.error)) {
-    if (!first_chunk) {
-      // The pinned staging buffer is reused across chunks, and this is where
-      // a stop request is honoured: the state is that of the last completed
-      // step (RETURN_IF_STOPPED,
-      // symplectic_runge_kutta_nyström_integrator_body.hpp:137).
-      PB_CUDA(cudaStreamSynchronize(stream));
-    }
+    // The pinned staging buffer is reused across chunks and across calls (the
+    // startup of a multistep instance calls this every 16 steps): its previous
+    // upload must have completed.  This is also where a stop request is
+    // honoured: the state is that of the last completed step
+    // (RETURN_IF_STOPPED,
+    // symplectic_runge_kutta_nyström_integrator_body.hpp:137).
+    PB_CUDA(cudaStreamSynchronize(stream));
     if (e->stop_requested.load() != 0) {
       c.cancelled = true;
       break;
     }
-    first_chunk = false;
     int steps = 0;
     double* const times = w->pinned_times.data;
     while (steps < chunk_steps && steps_done + steps < max_steps &&
