@@ -278,11 +278,17 @@ def config5_allpairs(timer, torch, dist, local_rank, rank, world, peak_flops,
     if communicator is not None:
       system.set_nccl(communicator)
     # Warm-up on a small system of its own (a force evaluation at this size
-    # costs seconds on one GPU).
+    # costs seconds on one GPU), sharded the same way so that the first
+    # all-gather of the communicator (connection set-up) is not in the timing.
+    small_n = 4096 * world
+    small_begin, small_end = sharding.equal_block_range(small_n, rank, world)
     small = NBodyAllPairs(_capi.QUINLAN_TREMAINE_1990_ORDER_12, 3600.0,
-                          mu[:4096], q[:, :4096], v[:, :4096], 0.0,
+                          mu[:small_n], q[:, :small_n], v[:, :small_n], 0.0,
+                          i_begin=small_begin, i_end=small_end,
                           device=local_rank)
     small.set_arithmetic(arithmetic)
+    if communicator is not None:
+      small.set_nccl(communicator)
     small.accelerations()
     small.close()
     force_ms = exchange_ms = 0.0
