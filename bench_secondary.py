@@ -1,9 +1,9 @@
 """The `secondary` block of bench.py's JSON line: BASELINE.json configs 3, 4
 and 5, each bounded to a few seconds, each with its own roofline from the
-static counts of principia_b200/flops.py.  Device times are CUDA events on the
-launching stream (the library launches on the legacy default stream, which is
-torch's current stream here), bracketed by a barrier + synchronize, max over
-ranks.
+static counts of principia_b200/flops.py.  Kernel times are the library's own
+CUDA events on the streams it launches on; whole-call times are CUDA events
+around host-synchronous calls, bracketed by a barrier + device synchronize,
+max over ranks.
 
   config 3  adaptive RKN434FM, 10^5 eccentric probes per GPU     weak
   config 4  TRAPPIST-1 ensemble, 10^5 systems per GPU            weak
@@ -140,7 +140,7 @@ def config3_adaptive(timer, local_rank, rank, world, peak_flops, probes, span):
                                         result['evaluations'],
                                         polynomial_degree)
   flop = timer.sum(flop)
-  achieved = flop / (kernel_ms * 1e-3) / 1e12
+  achieved = flop / (kernel_ms * 1e-3) / 1e12 / world  # Per GPU.
   ephemeris.close()
   return {
       'config': 'config 3: eccentric probes (a 6.6e6..4e8 m, e <= 0.7) in the '
