@@ -312,7 +312,7 @@ def run_native(args):
   pristine_device = state_device.clone()
   counters = {'resident': 0, 'e2e': 0}
 
-  def resident_step():
+  def resident_step(arithmetic=_capi.PB_ARITHMETIC_EXACT):
     k = counters['resident'] % WRAP
     if k == 0 and counters['resident'] > 0:
       state_device.copy_(pristine_device)
@@ -320,7 +320,7 @@ def run_native(args):
     time_dp = np.array([k * span, 0.0])
     result = ephemeris.flow_with_fixed_step_device(
         method, STEP_SECONDS, (k + 1) * span, n, state_device.data_ptr(),
-        time_dp, stream)
+        time_dp, stream, arithmetic=arithmetic)
     assert result['n_steps'] == FLOW_STEPS and result['status'] == 0, result
     return result
 
@@ -408,6 +408,39 @@ def run_native(args):
                      '(pb_measure_fp64_peak, %.2f ms); MEASURED_PEAKS.json '
                      'has no FP64 figure; nominal 37.2 TFLOP/s' % peak_ms}
 
+  # The opt-in contracted arithmetic (fused multiply-adds; within 1e-12 of the
+  # reference, tests/test_gpu_contracted.py): the same workload, resident.  The
+  # headline (`value`, `e2e`, `roofline`) stays the exact arithmetic.
+  for k in range(2):
+    resident_step(_capi.PB_ARITHMETIC_CONTRACTED)
+  barrier()
+  contracted_kernel_ms = 0.0
+  start.record()
+  for k in range(args.steps):
+    flush.fill_(k & 0xff)
+    resident_step(_capi.PB_ARITHMETIC_CONTRACTED)
+    contracted_kernel_ms += ephemeris.last_flow_kernel_ms()[0]
+  stop.record()
+  barrier()
+  contracted_ms = torch.tensor([start.elapsed_time(stop)], device=device,
+                               dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(contracted_ms, op=dist.ReduceOp.MAX)
+  contracted_ms = float(contracted_ms.item())
+  contracted_achieved = (call_flops /
+                         (contracted_kernel_ms / args.steps * 1e-3) / 1e12)
+  roofline_contracted = {
+      'arithmetic': 'PB_ARITHMETIC_CONTRACTED (opt-in; not bit-identical, '
+                    'relative position error <= 1e-12 after 10^4 steps)',
+      'value': args.steps * stages_per_step / (contracted_ms * 1e-3),
+      'unit': UNIT, 'ms_per_step': contracted_ms / args.steps,
+      'bound': 'fp64', 'achieved': contracted_achieved,
+      'peak': peak_flops / 1e12, 'unit_achieved': 'TFLOP/s',
+      'frac': contracted_achieved / (peak_flops / 1e12),
+      'kernel': 'SrknFlowKernel (pb_contracted.cu, --fmad=true)',
+      'kernel_ms': contracted_kernel_ms / args.steps,
+      **profile_counters('srkn_flow_contracted')}
+
   cpu_baseline = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     threads = host_cores()
@@ -444,6 +477,7 @@ def run_native(args):
                 'ms_per_step': e2e_ms / args.steps},
         'gpu_launches': int(launches_timed),
         'roofline': roofline,
+        'roofline_contracted': roofline_contracted,
         'cpu_baseline': cpu_baseline,
         'secondary': secondary}))
   if world > 1:

@@ -273,6 +273,9 @@ typedef struct pb_fixed_step_flow_t {
    * form: NULL, or an inertially fixed burn per probe, 8 planes of n laid out
    * as in pb_adaptive_step_flow_t.burns. */
   const double* burns;
+  /* PB_ARITHMETIC_EXACT (0, the default of a zero-initialised struct) or
+   * PB_ARITHMETIC_CONTRACTED. */
+  int32_t arithmetic;
 } pb_fixed_step_flow_t;
 pb_status_t pb_flow_with_fixed_step(pb_ephemeris_t* ephemeris,
                                     const pb_fixed_step_flow_t* flow);
@@ -303,6 +306,10 @@ void pb_fixed_step_instance_destroy(pb_fixed_step_instance_t* instance);
  * pb_fixed_step_flow_t.burns (host memory, copied), or NULL for none. */
 pb_status_t pb_fixed_step_instance_set_intrinsic_accelerations(
     pb_fixed_step_instance_t* instance, const double* burns);
+/* PB_ARITHMETIC_EXACT (default) or PB_ARITHMETIC_CONTRACTED for the flows of
+ * this instance. */
+pb_status_t pb_fixed_step_instance_set_arithmetic(
+    pb_fixed_step_instance_t* instance, int32_t arithmetic);
 /* FlowWithFixedStep(t_final, instance) = Instance::Solve(t_final).  Every
  * `sample_every`-th state appended by this call goes to samples[s][6][n]
  * (host), sample_times[s]; *n_steps = states appended; *flow_status as in

@@ -66,6 +66,7 @@ class FixedStepFlow(ctypes.Structure):
       ('n_steps', c_int64_p),
       ('status', c_int32_p),
       ('burns', ctypes.c_void_p),
+      ('arithmetic', ctypes.c_int32),
   ]
 
 
@@ -161,6 +162,7 @@ SYMBOLS = [
     ('pb_fixed_step_instance_destroy', None, [_vp]),
     ('pb_fixed_step_instance_set_intrinsic_accelerations', _i32,
      [_vp, c_double_p]),
+    ('pb_fixed_step_instance_set_arithmetic', _i32, [_vp, _i32]),
     ('pb_fixed_step_instance_flow', _i32,
      [_vp, _d, _i64, _i64, c_double_p, c_double_p, c_int64_p, c_int64_p,
       c_int32_p]),

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/principia_b200.h"
+#include "pb_contracted.h"
 #include "pb_kernels_massless.cuh"
 #include "pb_kernels_massless_multistep.cuh"
 #include "pb_runtime.cuh"
@@ -253,8 +254,13 @@ int ChooseHotBody(pb_ephemeris const* e, double const t,
   return hot;
 }
 
-// The constant bank of this translation unit's flow kernels (c_bodies, c_hot).
+// The constant bank of this translation unit's flow kernels (c_bodies, c_hot),
+// and that of the kernels compiled with contraction (pb_contracted.cu).
 ConstantBank& FlowConstantBank() {
+  static ConstantBank bank;
+  return bank;
+}
+ConstantBank& ContractedConstantBank() {
   static ConstantBank bank;
   return bank;
 }
@@ -269,6 +275,7 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
                                  long long const n,
                                  double const* const state_device,
                                  double const* const probe_host,
+                                 int32_t const arithmetic,
                                  cudaStream_t stream,
                                  ConstantBankLease& lease, int* hot_out) {
   int const n_bodies = static_cast<int>(e->model.bodies.size());
@@ -300,8 +307,11 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
     hot = e->hot_body;
   }
   *hot_out = hot;
+  bool const contracted = arithmetic == PB_ARITHMETIC_CONTRACTED;
+  ConstantBank& bank =
+      contracted ? ContractedConstantBank() : FlowConstantBank();
   // Variant 0 is "no hot body".
-  pb_status_t const status = FlowConstantBank().Acquire(
+  pb_status_t const status = bank.Acquire(
       e->serial, hot + 1, [&]() -> pb_status_t {
         static BodyScalars scalars;
         static HotBody hot_body;
@@ -334,6 +344,11 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
           hot_body.sectoral = body.sectoral;
         }
         // No kernel reads the bank now (ConstantBank::Acquire).
+        if (contracted) {
+          PB_CUDA(pb_contracted_api::UploadConstants(
+              &scalars, sizeof(scalars), &hot_body, sizeof(hot_body), stream));
+          return PB_OK;
+        }
         PB_CUDA(cudaMemcpyToSymbolAsync(c_bodies, &scalars, sizeof(scalars), 0,
                                         cudaMemcpyHostToDevice, stream));
         PB_CUDA(cudaMemcpyToSymbolAsync(c_hot, &hot_body, sizeof(hot_body), 0,
@@ -342,7 +357,7 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
         return PB_OK;
       });
   if (status == PB_OK) {
-    lease.Adopt(&FlowConstantBank());
+    lease.Adopt(&bank);
   }
   return status;
 }
@@ -903,6 +918,7 @@ struct FlowContext {
   ConstantBankLease constants;
   cudaStream_t stream = nullptr;
   int hot = -1;
+  int32_t arithmetic = PB_ARITHMETIC_EXACT;
   // RETURN_IF_STOPPED: set when the flow stopped at a chunk boundary because
   // pb_ephemeris_request_stop was called.
   bool cancelled = false;
@@ -929,13 +945,20 @@ struct FlowContext {
 
   pb_status_t AcquireConstants(double const t, long long const n,
                                double const* const state_device,
-                               double const* const probe_host) {
+                               double const* const probe_host,
+                               int32_t const flow_arithmetic) {
     if (constants.held()) {
       return PB_OK;
     }
-    return AcquireFlowConstants(e, t, n, state_device, probe_host, stream,
-                                constants, &hot);
+    if (flow_arithmetic != PB_ARITHMETIC_EXACT &&
+        flow_arithmetic != PB_ARITHMETIC_CONTRACTED) {
+      return Fail(PB_INVALID_ARGUMENT, "unknown arithmetic");
+    }
+    arithmetic = flow_arithmetic;
+    return AcquireFlowConstants(e, t, n, state_device, probe_host, arithmetic,
+                                stream, constants, &hot);
   }
+  bool contracted() const { return arithmetic == PB_ARITHMETIC_CONTRACTED; }
 
   EphemerisView View() const {
     EphemerisView view = e->View();
@@ -1108,7 +1131,29 @@ pb_status_t SrknSteps(FlowContext& c, const pb_fixed_step_flow_t* flow,
           view, tableau, h, table, stage_times, flow->burns, n_sub, flow->n,  \
           i_begin, i_end, flow->state, steps_done + s0, every,                \
           flow->max_samples, flow->samples, w->status_word.data)
-          if (variant == 5) {
+          if (c.contracted()) {
+            pb_contracted_api::SrknLaunch launch;
+            launch.view = &view;
+            launch.tableau = &tableau;
+            launch.h = h;
+            launch.stage_table = table;
+            launch.stage_times = stage_times;
+            launch.burns = flow->burns;
+            launch.n_steps = n_sub;
+            launch.n = flow->n;
+            launch.i_begin = i_begin;
+            launch.i_end = i_end;
+            launch.state = flow->state;
+            launch.steps_before = steps_done + s0;
+            launch.sample_every = every;
+            launch.max_samples = flow->max_samples;
+            launch.samples = flow->samples;
+            launch.status = w->status_word.data;
+            launch.threads = threads;
+            launch.grid = grid;
+            launch.stream = helper;
+            PB_CUDA(pb_contracted_api::LaunchSrkn(launch));
+          } else if (variant == 5) {
             PB_LAUNCH_SRKN(256, 2);
           } else if (variant >= 2) {
             PB_LAUNCH_SRKN(384, 1);
@@ -1164,6 +1209,7 @@ struct pb_fixed_step_instance {
   DeviceBuffer<double> owned_state;
   // One Solve at a time per instance.
   std::mutex mutex;
+  int32_t arithmetic = PB_ARITHMETIC_EXACT;
   // Tabulated intrinsic accelerations (8 planes of n), or null.
   double const* burns = nullptr;
   DeviceBuffer<double> owned_burns;
@@ -1212,7 +1258,14 @@ pb_status_t MasslessFillStep(FlowContext& c, pb_fixed_step_instance* s,
   double const t = s->time.value;
   PB_RETURN_IF_ERROR(
       BuildStageTable(e, w, &t, 1, w->stage_table.data, c.stream));
-  if (s->n > 0) {
+  if (s->n > 0 && c.contracted()) {
+    MasslessHistory const history = s->History();
+    pb_contracted_api::FillStepLaunch launch{
+        &view, w->stage_table.data, t, s->burns, s->n, s->state, &history,
+        slot, w->status_word.data, c.stream};
+    PB_CUDA(pb_contracted_api::LaunchFillStep(launch));
+    LaunchCount().fetch_add(1);
+  } else if (s->n > 0) {
     MasslessFillStepKernel<<<static_cast<unsigned>((s->n + kFlowThreads - 1) /
                                                    kFlowThreads),
                              kFlowThreads, 0, c.stream>>>(
@@ -1357,7 +1410,7 @@ pb_status_t SolveMultistepInstance(FlowContext& c, pb_fixed_step_instance* s,
     if (s->n > 0) {
       // Probe slices x step sub-chunks on helper streams, as in the SRKN flow
       // (no last-wave tail: 1.91 -> 2.04 10^9 probe-steps/s on 10^5 probes).
-      bool const wide = MultistepWide(s->n, sm_count);
+      bool const wide = !c.contracted() && MultistepWide(s->n, sm_count);
       int const threads = wide ? 256 : kFlowThreads;
       long long const blocks = (s->n + threads - 1) / threads;
       int const groups = static_cast<int>(
@@ -1389,7 +1442,34 @@ pb_status_t SolveMultistepInstance(FlowContext& c, pb_fixed_step_instance* s,
           s->state, s->History(), (s->oldest + s0) % order,                   \
           appended_before + s0, sampling ? sink->sample_every : 0,            \
           sink->max_samples, sink->samples, w->status_word.data)
-          if (order == 8) {
+          if (c.contracted()) {
+            MasslessHistory const history = s->History();
+            pb_contracted_api::MultistepLaunch launch;
+            launch.view = &view;
+            launch.method = &s->multistep;
+            launch.h = h;
+            launch.stage_table =
+                w->stage_table.data +
+                static_cast<std::size_t>(s0) * view.stage_stride;
+            launch.stage_times = w->stage_times.data + s0;
+            launch.burns = s->burns;
+            launch.n_steps = n_sub;
+            launch.n = s->n;
+            launch.i_begin = i_begin;
+            launch.i_end = i_end;
+            launch.state = s->state;
+            launch.history = &history;
+            launch.oldest = (s->oldest + s0) % order;
+            launch.steps_before = appended_before + s0;
+            launch.sample_every = sampling ? sink->sample_every : 0;
+            launch.max_samples = sink->max_samples;
+            launch.samples = sink->samples;
+            launch.status = w->status_word.data;
+            launch.order = order;
+            launch.grid = grid;
+            launch.stream = helper;
+            PB_CUDA(pb_contracted_api::LaunchMultistep(launch));
+          } else if (order == 8) {
             if (wide) {
               PB_LAUNCH_MULTISTEP(8, 256, 2);
             } else {
@@ -1425,8 +1505,8 @@ pb_status_t SolveMultistepInstance(FlowContext& c, pb_fixed_step_instance* s,
 // then at its last completed step and can be solved further).
 pb_status_t SolveInstance(FlowContext& c, pb_fixed_step_instance* s,
                           const pb_fixed_step_flow_t* flow) {
-  PB_RETURN_IF_ERROR(
-      c.AcquireConstants(s->time.value, s->n, s->state, nullptr));
+  PB_RETURN_IF_ERROR(c.AcquireConstants(s->time.value, s->n, s->state,
+                                        nullptr, s->arithmetic));
   if (!s->is_multistep) {
     pb_fixed_step_flow_t srkn = *flow;
     srkn.method = s->method;
@@ -1475,6 +1555,7 @@ pb_status_t MultistepFlowDevice(FlowContext& c,
   instance.time = {flow->time[0], flow->time[1]};
   instance.state = flow->state;
   instance.burns = flow->burns;
+  instance.arithmetic = flow->arithmetic;
   pb_status_t const status = SolveInstance(c, &instance, flow);
   flow->time[0] = instance.time.value;
   flow->time[1] = instance.time.error;
@@ -1562,6 +1643,17 @@ pb_status_t pb_fixed_step_instance_set_intrinsic_accelerations(
       burns, PB_BURN_PLANES * static_cast<std::size_t>(s->n), nullptr));
   PB_CUDA(cudaStreamSynchronize(nullptr));
   s->burns = s->owned_burns.data;
+  return PB_OK;
+}
+
+pb_status_t pb_fixed_step_instance_set_arithmetic(
+    pb_fixed_step_instance_t* s, int32_t arithmetic) {
+  if (s == nullptr || (arithmetic != PB_ARITHMETIC_EXACT &&
+                       arithmetic != PB_ARITHMETIC_CONTRACTED)) {
+    return Fail(PB_INVALID_ARGUMENT, "bad argument");
+  }
+  std::lock_guard<std::mutex> const instance_lock(s->mutex);
+  s->arithmetic = arithmetic;
   return PB_OK;
 }
 
@@ -1878,8 +1970,8 @@ pb_status_t ValidateFixedStepFlow(pb_ephemeris_t* e,
 pb_status_t FixedStepFlowDevice(FlowContext& c,
                                 const pb_fixed_step_flow_t* flow,
                                 double const* const probe_host) {
-  PB_RETURN_IF_ERROR(
-      c.AcquireConstants(flow->time[0], flow->n, flow->state, probe_host));
+  PB_RETURN_IF_ERROR(c.AcquireConstants(flow->time[0], flow->n, flow->state,
+                                        probe_host, flow->arithmetic));
   MultistepMethod multistep;
   if (MakeMultistepMethod(flow->method, multistep)) {
     return MultistepFlowDevice(c, flow);

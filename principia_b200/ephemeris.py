@@ -192,8 +192,9 @@ class Ephemeris:
   # -- flows ----------------------------------------------------------------
   def _fixed_step_flow(self, method, step, t_final, n, state_pointer, time,
                        sample_every, max_samples, samples_pointer,
-                       sample_times):
+                       sample_times, arithmetic=_capi.PB_ARITHMETIC_EXACT):
     flow = _capi.FixedStepFlow()
+    flow.arithmetic = arithmetic
     flow.method = method
     flow.step = step
     flow.t_final = t_final
@@ -211,10 +212,13 @@ class Ephemeris:
     return flow, outs
 
   def flow_with_fixed_step(self, method, step, t_final, state, time,
-                           sample_every=0, max_samples=0, burns=None):
+                           sample_every=0, max_samples=0, burns=None,
+                           arithmetic=_capi.PB_ARITHMETIC_EXACT):
     """NewInstance + FlowWithFixedStep on n probes.  state: (12, n) float64,
     time: (2,) float64; both updated in place (host buffers).  burns: the
-    intrinsic accelerations, tabulated (8, n), or None."""
+    intrinsic accelerations, tabulated (8, n), or None.  arithmetic:
+    PB_ARITHMETIC_EXACT (bit-identical to the reference's arithmetic) or
+    PB_ARITHMETIC_CONTRACTED (fused multiply-adds, within 1e-12)."""
     assert state.flags.c_contiguous and state.dtype == np.float64
     assert time.flags.c_contiguous and time.dtype == np.float64
     assert state.shape[0] == 12 and time.shape == (2,)
@@ -226,7 +230,7 @@ class Ephemeris:
     flow, outs = self._fixed_step_flow(
         method, step, t_final, n, state.ctypes.data, time, sample_every,
         max_samples, None if samples is None else samples.ctypes.data,
-        sample_times)
+        sample_times, arithmetic)
     if burns is not None:
       burns = np.ascontiguousarray(burns, dtype=np.float64)
       assert burns.shape == (8, n)
@@ -240,11 +244,12 @@ class Ephemeris:
                 else sample_times[:n_samples])
 
   def flow_with_fixed_step_device(self, method, step, t_final, n,
-                                  state_pointer, time, stream=None):
+                                  state_pointer, time, stream=None,
+                                  arithmetic=_capi.PB_ARITHMETIC_EXACT):
     """Same, state already resident in HBM (device pointer to 12 * n
     doubles)."""
     flow, outs = self._fixed_step_flow(method, step, t_final, n, state_pointer,
-                                       time, 0, 0, None, None)
+                                       time, 0, 0, None, None, arithmetic)
     cancelled = _check_flow(self.lib.pb_flow_with_fixed_step_device(
         self.handle, ctypes.byref(flow), stream))
     return dict(n_steps=outs[1].value, status=outs[2].value,
@@ -369,6 +374,11 @@ class FixedStepInstance:
     if getattr(self, 'handle', None):
       self.lib.pb_fixed_step_instance_destroy(self.handle)
       self.handle = None
+
+  def set_arithmetic(self, arithmetic):
+    """PB_ARITHMETIC_EXACT (default) or PB_ARITHMETIC_CONTRACTED."""
+    _check(self.lib.pb_fixed_step_instance_set_arithmetic(self.handle,
+                                                          arithmetic))
 
   def set_intrinsic_accelerations(self, burns):
     """The intrinsic_accelerations of NewInstance, tabulated: (8, n) or None."""
