@@ -101,8 +101,10 @@ EXCHANGE_POSITIONS = ctypes.CFUNCTYPE(ctypes.c_int32, ctypes.c_void_p,
                                       ctypes.c_int64, ctypes.c_int64,
                                       ctypes.c_int64, ctypes.c_void_p)
 
-LIBRARY_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
-                            'libprincipia_b200.so')
+# PB_LIBRARY_PATH: another build of the same library (kernel experiments,
+# tools/flow_variants.sh); there is still no fallback of any kind.
+LIBRARY_PATH = os.environ.get('PB_LIBRARY_PATH') or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), 'libprincipia_b200.so')
 
 # Every symbol include/principia_b200.h declares: (name, restype, argtypes).
 _d, _i32, _i64, _vp = (ctypes.c_double, ctypes.c_int32, ctypes.c_int64,

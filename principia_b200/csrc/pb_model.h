@@ -70,13 +70,10 @@ struct EphemerisView {
   // [segment][xyz][18]: the host API's [segment][18][3] transposed, so that the
   // coefficients of one coordinate are contiguous (16-byte loads of pairs).
   double const* segment_coefficients;
-  // Where a flow kernel reports the code paths it took (kPathGenericHarmonics),
-  // or null.
-  int32_t* path_flags;
 };
 
-// Set in *EphemerisView::path_flags by a flow kernel when some probe evaluated
-// harmonics of degree > 3 of a body other than the hot one (the
+// Set by FlowPathKernel when some probe of a fixed-step flow is within the
+// range of the harmonics of degree > 3 of a body other than the hot one (the
 // thread-local-memory path: same bits, several times slower).
 constexpr int32_t kPathGenericHarmonics = 0x100;
 

@@ -387,7 +387,6 @@ struct pb_ephemeris {
     v.segment_origin = segment_origin.data;
     v.segment_degree = segment_degree.data;
     v.segment_coefficients = segment_coefficients.data;
-    v.path_flags = nullptr;
     return v;
   }
 };

@@ -922,6 +922,7 @@ struct FlowContext {
   // RETURN_IF_STOPPED: set when the flow stopped at a chunk boundary because
   // pb_ephemeris_request_stop was called.
   bool cancelled = false;
+  bool path_checked = false;
   double kernel_ms = 0;
   std::int64_t launches = 0;
   std::size_t phases = 0;
@@ -960,10 +961,20 @@ struct FlowContext {
   }
   bool contracted() const { return arithmetic == PB_ARITHMETIC_CONTRACTED; }
 
-  EphemerisView View() const {
-    EphemerisView view = e->View();
-    view.path_flags = w()->status_word.data + 1;
-    return view;
+  EphemerisView View() const { return e->View(); }
+
+  // Once per call: would some probe take the slow generic harmonics?  `stage`
+  // is a stage-table entry close to the initial time of the flow.
+  pb_status_t CheckPath(double const* const stage, long long const n,
+                        double const* const state) {
+    if (path_checked || n == 0) {
+      return PB_OK;
+    }
+    path_checked = true;
+    FlowPathKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+        e->View(), stage, hot, n, state, w()->status_word.data + 1);
+    PB_LAUNCHED();
+    return PB_OK;
   }
 
   // Sums the device time of the kernel phases recorded since the last call.
@@ -1089,6 +1100,7 @@ pb_status_t SrknSteps(FlowContext& c, const pb_fixed_step_flow_t* flow,
     }
     PB_RETURN_IF_ERROR(BuildStageTable(e, w, times, steps * evaluations,
                                        w->stage_table.data, stream));
+    PB_RETURN_IF_ERROR(c.CheckPath(w->stage_table.data, flow->n, flow->state));
     if (flow->n > 0) {
       // The probes are cut into `groups` slices and the steps into sub-chunks;
       // slice g runs its sub-chunks in order on helper stream g.  Whole
@@ -1258,6 +1270,7 @@ pb_status_t MasslessFillStep(FlowContext& c, pb_fixed_step_instance* s,
   double const t = s->time.value;
   PB_RETURN_IF_ERROR(
       BuildStageTable(e, w, &t, 1, w->stage_table.data, c.stream));
+  PB_RETURN_IF_ERROR(c.CheckPath(w->stage_table.data, s->n, s->state));
   if (s->n > 0 && c.contracted()) {
     MasslessHistory const history = s->History();
     pb_contracted_api::FillStepLaunch launch{
@@ -1407,6 +1420,7 @@ pb_status_t SolveMultistepInstance(FlowContext& c, pb_fixed_step_instance* s,
     }
     PB_RETURN_IF_ERROR(
         BuildStageTable(e, w, times, steps, w->stage_table.data, stream));
+    PB_RETURN_IF_ERROR(c.CheckPath(w->stage_table.data, s->n, s->state));
     if (s->n > 0) {
       // Probe slices x step sub-chunks on helper streams, as in the SRKN flow
       // (no last-wave tail: 1.91 -> 2.04 10^9 probe-steps/s on 10^5 probes).

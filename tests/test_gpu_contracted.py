@@ -65,7 +65,7 @@ def test_contracted_srkn_flow_is_within_tolerance(sol_system, sol_oracle,
   radius = np.linalg.norm(expected[0:3] - earth[:, None], axis=0)
   assert (dq / radius).max() < 2e-8, (dq / radius).max()
   dv = np.linalg.norm(contracted[6:9] - expected[6:9], axis=0)
-  assert (dv / np.linalg.norm(expected[6:9], axis=0)).max() <= 1e-11
+  assert (dv / np.linalg.norm(expected[6:9], axis=0)).max() <= 1e-9
   # Energy drift (relative to the Earth): the contracted flow drifts like the
   # reference's arithmetic does.
   e0 = earth_relative_energy(sol_oracle, sol_system, state0, 0.0)
