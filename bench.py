@@ -56,32 +56,47 @@ def bench_config(probes):
 
 class ClockSampler:
   """SM clock and throttle reasons during the timed region
-  (B200_PROFILING.md).  In-process NVML (pynvml), one light query every 50 ms:
-  an `nvidia-smi -lms` child was measured to stall kernel launches for tens of
-  milliseconds per query on an 8-GPU box (value 1.9e9 instead of 2.8e9 in one
-  run out of five); nvidia-smi remains the fallback."""
+  (B200_PROFILING.md), in-process NVML (pynvml).  An NVML query can hold a
+  driver lock for tens of milliseconds on some boxes (measured: 20 ms per
+  query, and `value` 2.6x low because every CUDA call of the step queued
+  behind it), so a query is only made where the host has nothing to issue: the
+  bench kicks the sampler when a step starts, the sampler waits for the step's
+  launches to be enqueued (5 ms) and queries once while the flow kernels of
+  that step run (48 ms) -- one sample per step, all inside the timed region.
+  nvidia-smi remains the fallback."""
 
   def __init__(self, index):
     self.index = index
     self.samples = []  # (sm MHz, max MHz, reasons bitmask).
     self.thread = None
     self.stop_event = threading.Event()
+    self.kick_event = threading.Event()
+    self.sm_max = None
     self.process = None
     self.lines = []
 
+  def kick(self):
+    """A step starts now."""
+    self.kick_event.set()
+
+  def _query(self, nvml, handle):
+    try:
+      sm = nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)
+      try:
+        reasons = nvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+      except AttributeError:
+        reasons = nvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+      self.samples.append((float(sm), float(self.sm_max), int(reasons)))
+    except Exception:  # An NVML hiccup must not end the bench.
+      pass
+
   def _nvml_loop(self, nvml, handle):
     while not self.stop_event.is_set():
-      try:
-        sm = nvml.nvmlDeviceGetClockInfo(handle, nvml.NVML_CLOCK_SM)
-        sm_max = nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM)
-        try:
-          reasons = nvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
-        except AttributeError:
-          reasons = nvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
-        self.samples.append((float(sm), float(sm_max), int(reasons)))
-      except Exception:  # An NVML hiccup must not end the bench.
-        pass
-      self.stop_event.wait(0.05)
+      if not self.kick_event.wait(0.2):
+        continue
+      self.kick_event.clear()
+      time.sleep(0.005)
+      self._query(nvml, handle)
 
   def start(self):
     try:
@@ -95,12 +110,14 @@ class ClockSampler:
           index = int(entries[self.index])
       handle = nvml.nvmlDeviceGetHandleByIndex(index)
       self.nvml = nvml
+      self.sm_max = nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM)
+      self._query(nvml, handle)  # Fails here rather than in the thread.
+      if not self.samples:
+        raise RuntimeError('NVML query failed')
+      self.samples.clear()
       self.thread = threading.Thread(target=self._nvml_loop,
                                      args=(nvml, handle), daemon=True)
       self.thread.start()
-      deadline = time.perf_counter() + 2.0
-      while not self.samples and time.perf_counter() < deadline:
-        time.sleep(0.005)
       return
     except Exception:
       self.thread = None
@@ -350,6 +367,7 @@ def run_native(args):
   start.record()
   for k in range(args.steps):
     flush.fill_(k & 0xff)  # Evict L2 between steps.
+    sampler.kick()
     resident_step()
     # Device time (CUDA events on the launching stream) of the flow kernels of
     # this call: the call slices the batch into launches that overlap on

@@ -75,7 +75,8 @@ def test_contracted_srkn_flow_is_within_tolerance(sol_system, sol_oracle,
                                            steps * h) - e0
   assert np.abs(drift_contracted - drift_reference).max() <= (
       1e-9 * np.abs(e0).max())
-  assert np.abs(drift_contracted / e0).max() < 1e-3
+  # (The two-body energy itself oscillates by the Earth's oblateness: 10^-3.)
+  assert np.abs(drift_contracted / e0).max() < 1e-2
 
 
 @pytest.mark.parametrize('method', [_capi.QUINLAN_1999_ORDER_8A,
