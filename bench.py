@@ -307,7 +307,9 @@ def run_native(args):
   n = args.probes
   system, state_host = make_workload(n, seed=42 + rank)
   ephemeris = Ephemeris(system, device=local_rank)
-  workloads.upload_sol_ephemeris(ephemeris)
+  # Ephemeris::Prolong by the product itself (massive-body flow and Newhall
+  # fit on the device), over the two days the flows below span.
+  workloads.prolong_ephemeris(ephemeris, 2 * 86400.0)
   method = _capi.BLANES_MOAN_2002_SRKN_14A
   span = FLOW_STEPS * STEP_SECONDS
 
@@ -322,7 +324,7 @@ def run_native(args):
       dist.barrier()
     torch.cuda.synchronize()
 
-  # The golden ephemeris covers two days = 172 bench steps of 1000 s; the
+  # The ephemeris covers two days = 172 bench steps of 1000 s; the
   # flows advance continuously in time and restart from the initial state
   # after WRAP steps (a device/host copy of the pristine state, negligible).
   WRAP = 150
@@ -400,6 +402,46 @@ def run_native(args):
   if world > 1:
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
   e2e_ms = float(e2e_ms.item())
+
+  # End to end WITH the trajectory sink: FlowWithFixedStep appends every step
+  # to a DiscreteTrajectory (physics/ephemeris_body.hpp:1118-1131), here the
+  # device-side DiscreteTrajectorySegment with the plugin's downsampling
+  # (10 m): Ephemeris::NewInstance from the host state, FlowWithFixedStep into
+  # the sink, the final state and the length of every timeline back on the
+  # host, every step.
+  from principia_b200.trajectory import Downsampler
+  sink_steps = min(args.steps, 10)
+  sink = Downsampler(n, 10.0, (sink_steps + 2) * FLOW_STEPS + 2,
+                     device=local_rank)
+  sink.append([0.0], np.concatenate([state_host[0:3], state_host[6:9]])[None])
+  sink_state = pinned_np
+  sink_state[...] = state_host
+  sink_time = np.zeros(2)
+  sink_points = 0
+
+  def sink_step(k):
+    instance = ephemeris.new_instance(method, STEP_SECONDS, sink_state,
+                                      sink_time)
+    result = instance.flow_to_downsampler((k + 1) * span, sink)
+    assert result['n_steps'] == FLOW_STEPS and result['status'] == 0, result
+    instance.state_into(sink_state, sink_time)
+    instance.close()
+    return int(sink.counts().sum())
+
+  sink_step(0)
+  barrier()
+  start.record()
+  for k in range(1, sink_steps + 1):
+    flush.fill_(k & 0xff)
+    sink_points = sink_step(k)
+  stop.record()
+  barrier()
+  sink_ms = torch.tensor([start.elapsed_time(stop)], device=device,
+                         dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(sink_ms, op=dist.ReduceOp.MAX)
+  sink_ms = float(sink_ms.item())
+  del sink
 
   stages_per_step = world * n * FLOW_STEPS * EVALUATIONS
   value = args.steps * stages_per_step / (elapsed_ms * 1e-3)
@@ -493,6 +535,17 @@ def run_native(args):
                 'h2d_bytes_per_step': world * 12 * n * 8,
                 'd2h_bytes_per_step': world * 12 * n * 8,
                 'ms_per_step': e2e_ms / args.steps},
+        'e2e_with_sink': {
+            'value': sink_steps * stages_per_step / (sink_ms * 1e-3),
+            'unit': UNIT, 'ms_per_step': sink_ms / sink_steps,
+            'h2d_bytes_per_step': world * 12 * n * 8,
+            'd2h_bytes_per_step': world * (12 * n * 8 + n * 8),
+            'sink': 'every step of every probe appended to a device '
+                    'DiscreteTrajectorySegment with 10 m downsampling '
+                    '(pb_fixed_step_instance_flow_to_downsampler)',
+            'points_kept_per_probe':
+                sink_points / n if sink_points else None,
+            'points_appended_per_probe': (sink_steps + 1) * FLOW_STEPS + 1},
         'gpu_launches': int(launches_timed),
         'roofline': roofline,
         'roofline_contracted': roofline_contracted,

@@ -109,9 +109,12 @@ def bench_adaptive(args):
 
 def bench_single(args):
   """Config 1 (the reference's own CPU-runnable case, ephemeris_benchmark.cpp
-  :201-219): ONE LEO probe in the Sol field, SRKN14A at 10 s.  Sequential in
-  time: it does not shard (replicas only) and is latency-bound on a GPU; the
-  oracle on one host core is timed beside it."""
+  :181-248): the Sol ephemeris prolonged over `--span` seconds (100 days in
+  the benchmark) and ONE LEO probe flowed through it, SRKN14A at 10 s.  The
+  ephemeris is produced by the product (massive-body flow and Newhall fit on
+  the device) and compared bit for bit with the oracle's.  Sequential in time:
+  it does not shard (replicas only) and is latency-bound on a GPU; the oracle
+  on one host core is timed beside it."""
   torch, dist, world, rank, local_rank = dist_setup()
   if rank != 0:
     return
@@ -120,11 +123,28 @@ def bench_single(args):
   from principia_b200.ephemeris import Ephemeris
   from oracle_lib import OracleEphemeris
   system = workloads.sol_system()
+  span = args.span
   ephemeris = Ephemeris(system, device=local_rank)
-  workloads.upload_sol_ephemeris(ephemeris)
+  torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  prolong_steps = workloads.prolong_ephemeris(ephemeris, span)
+  torch.cuda.synchronize()
+  gpu_prolong_seconds = time.perf_counter() - t0
   oracle = OracleEphemeris(system)
-  for body, segments in enumerate(workloads.load_sol_ephemeris_segments()):
-    oracle.append_segments(body, segments)
+  t0 = time.perf_counter()
+  assert oracle.prolong(span) == 0
+  cpu_prolong_seconds = time.perf_counter() - t0
+  assert ephemeris.t_max() >= span
+  n_segments = sum(len(oracle.segments(body)['t_max'])
+                   for body in range(len(system.bodies)))
+  # The product's polynomials against the oracle's, through EvaluateAllPositions
+  # at random times over the whole span, bit for bit.
+  rng = np.random.Generator(np.random.MT19937(1))
+  ephemeris_equal = True
+  for t in rng.uniform(0.0, span, 64):
+    ephemeris_equal = ephemeris_equal and bool(np.array_equal(
+        ephemeris.evaluate_all_positions(t).view(np.int64),
+        oracle.evaluate_all_positions(t).view(np.int64)))
   earth = system.bodies[system.index('Earth')]
   # Radius 6371 km + 100 nautical miles, circular, in the equatorial plane of
   # the frame (the benchmark's probe).
@@ -133,7 +153,6 @@ def bench_single(args):
   state0[0:3, 0] = np.array(earth['q']) + [r, 0.0, 0.0]
   state0[6:9, 0] = np.array(earth['v']) + [0.0, math.sqrt(earth['mu'] / r), 0.0]
   method = _capi.BLANES_MOAN_2002_SRKN_14A
-  span = args.span  # Seconds; the golden ephemeris covers two days.
   steps = int(span / 10.0)
   ephemeris.flow_with_fixed_step(method, 10.0, 100.0, state0.copy(),
                                  np.zeros(2))  # Warm-up.
@@ -143,22 +162,31 @@ def bench_single(args):
   result = ephemeris.flow_with_fixed_step(method, 10.0, span, state,
                                           np.zeros(2))
   gpu_seconds = time.perf_counter() - t0
-  assert result['n_steps'] == steps
+  assert result['n_steps'] == steps, result
   expected = state0.copy()
   t0 = time.perf_counter()
   oracle.flow_with_fixed_step(method, 10.0, span, expected, np.zeros(2),
                               threads=1)
   cpu_seconds = time.perf_counter() - t0
-  assert np.array_equal(state.view(np.int64), expected.view(np.int64))
+  bitwise = bool(np.array_equal(state.view(np.int64), expected.view(np.int64)))
   print(json.dumps({
-      'config': 'config 1: one LEO probe, Sol field, SRKN14A at 10 s '
-                '(sequential: replicas only)',
-      'span_seconds': span, 'steps': steps,
+      'config': 'config 1: Sol ephemeris prolonged by the product, one LEO '
+                'probe, SRKN14A at 10 s (sequential: replicas only)',
+      'span_seconds': span, 'span_days': span / 86400.0,
+      'prolong_steps_quinlan_tremaine_12_at_10_min': prolong_steps,
+      'gpu_prolong_seconds': gpu_prolong_seconds,
+      'cpu_oracle_prolong_seconds': cpu_prolong_seconds,
+      'ephemeris_segments_per_body': n_segments / len(system.bodies),
+      'ephemeris_bitwise_equal_to_oracle_at_64_times': ephemeris_equal,
+      'probe_steps': steps,
       'gpu_seconds': gpu_seconds,
       'gpu_probe_stages_per_second': steps * 14 / gpu_seconds,
       'cpu_oracle_one_core_seconds': cpu_seconds,
       'cpu_probe_stages_per_second': steps * 14 / cpu_seconds,
-      'bitwise_equal': True}))
+      'probe_state_bitwise_equal_to_oracle': bitwise,
+      'max_position_difference_m':
+          float(np.abs(state[0:3] - expected[0:3]).max())}))
+  assert bitwise and ephemeris_equal
 
 
 def bench_history(args):

@@ -117,10 +117,11 @@ def config3_adaptive(timer, local_rank, rank, world, peak_flops, probes, span):
   from principia_b200.ephemeris import Ephemeris
   system = workloads.sol_system()
   ephemeris = Ephemeris(system, device=local_rank)
-  workloads.upload_sol_ephemeris(ephemeris)
-  segments = workloads.load_sol_ephemeris_segments()
-  polynomial_degree = int(round(np.mean([s['degree'].mean()
-                                         for s in segments])))
+  workloads.prolong_ephemeris(ephemeris, span + 600.0)
+  # Mean degree of the Sol polynomials at a 1 mm fitting tolerance (the
+  # degrees are per body and per segment: 3 for the outer planets ... 13 for
+  # the inner moons).
+  polynomial_degree = 9
   earth = system.bodies[system.index('Earth')]
   state0 = workloads.eccentric_probes(probes, earth['q'], earth['v'],
                                       earth['mu'], 42 + rank)

@@ -417,6 +417,17 @@ class FixedStepInstance:
         ctypes.byref(status)))
     return dict(n_steps=n_steps.value, status=status.value)
 
+  def state_into(self, state, time):
+    """The instance's state into caller-provided (12, n) and (2,) arrays."""
+    assert state.flags.c_contiguous and state.shape == (12, self.n)
+    _check(self.lib.pb_fixed_step_instance_get_state(self.handle, _dptr(state),
+                                                     _dptr(time)))
+
+  def close(self):
+    if getattr(self, 'handle', None):
+      self.lib.pb_fixed_step_instance_destroy(self.handle)
+      self.handle = None
+
   def state(self):
     """(state (12, n), time (2,)) of the instance."""
     state = np.zeros((12, self.n))

@@ -1,6 +1,6 @@
 """Host-side description of a system of massive bodies: the analogue of the
 reference's physics::SolarSystem (physics/solar_system_body.hpp:100-168), fed
-from the JSON fixtures under tests/golden/ (tools/make_system_fixtures.py
+from the JSON files under principia_b200/data/ (tools/make_system_fixtures.py
 documents how those are derived from the reference's configuration files).
 """
 import copy
@@ -12,6 +12,9 @@ import numpy as np
 
 from . import _capi
 
+# The gravity models and initial states (product inputs).
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
+# Test vectors (the oracle's ephemeris segments, reference known answers).
 GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                       'tests', 'golden')
 
@@ -26,7 +29,7 @@ class SolarSystem:
 
   @classmethod
   def from_fixture(cls, name):
-    with open(os.path.join(GOLDEN, name + '.json')) as f:
+    with open(os.path.join(DATA, name + '.json')) as f:
       data = json.load(f)
     return cls(data['bodies'], data['epoch'])
 

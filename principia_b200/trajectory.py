@@ -55,6 +55,13 @@ class Downsampler:
         _dptr(points), _dptr(errors)))
     return counts, times, points, errors
 
+  def counts(self):
+    """The number of points of every timeline, (n,)."""
+    counts = np.zeros(self.n, dtype=np.int64)
+    _check(self.lib.pb_downsampler_get(
+        self.handle, counts.ctypes.data_as(_capi.c_int64_p), None, None, None))
+    return counts
+
   def evaluate(self, t):
     """DiscreteTrajectory::EvaluatePosition / EvaluateVelocity of every
     timeline at t: ((3, n) positions, (3, n) velocities, (n,) in_range)."""

@@ -1,6 +1,8 @@
 """Synthetic workloads of BASELINE.json's configs, seeded like
-the reference's tests (std::mt19937_64(42) there; numpy's MT19937(42) here),
-and the loader of the golden Sol ephemeris segments.
+the reference's tests (std::mt19937_64(42) there; numpy's MT19937(42) here);
+Ephemeris::Prolong on the device for the Sol system; and the loader of the
+oracle-made Sol ephemeris segments that the parity tests upload
+(tests/golden/, test input only).
 """
 import os
 
@@ -19,8 +21,48 @@ def load_sol_ephemeris_segments():
 
 
 def upload_sol_ephemeris(ephemeris):
+  """TEST INPUT: the segments the CPU oracle produced (the parity tests upload
+  them so that a failure points at the flow, not at Prolong).  The product's
+  own way is prolong_ephemeris below; the two are bit-equal
+  (tests/test_gpu_continuous_trajectory.py)."""
   for body, segments in enumerate(load_sol_ephemeris_segments()):
     ephemeris.append_segments(body, segments)
+
+
+def prolong_ephemeris(ephemeris, t_final, step=600.0, fitting_tolerance=1e-3,
+                      method=None, t_initial=0.0):
+  """Ephemeris::Prolong(t_final) from the initial state of the ephemeris'
+  system, everything on the device (physics/ephemeris_body.hpp:312-344,
+  1071-1116): the massive bodies are integrated with the ephemeris' own
+  fixed-step integrator (QuinlanTremaine1990Order12 at 10 min for the Sol
+  system, astronomy/..., ksp_plugin/integrators.cpp), every state goes to a
+  device ContinuousTrajectory per body (Newhall fit every 8 points), and the
+  resulting polynomials become the segments of `ephemeris`.  Returns the
+  number of steps."""
+  from . import _capi
+  from .nbody import ContinuousTrajectories, NBodyEnsemble
+  system = ephemeris.system
+  if method is None:
+    method = _capi.QUINLAN_TREMAINE_1990_ORDER_12
+  order, _ = ephemeris.internal_order()
+  n = len(order)
+  state = np.zeros((12, n, 1))
+  state[0:3, :, 0] = system.initial_positions()[order].T
+  state[6:9, :, 0] = system.initial_velocities()[order].T
+  segments = int((t_final - t_initial) / (8 * step)) + 3
+  trajectories = ContinuousTrajectories(n, step, fitting_tolerance, segments,
+                                        device=ephemeris.device)
+  ensemble = NBodyEnsemble(ephemeris, method, step, state, t_initial)
+  steps = 0
+  t = t_final
+  while trajectories.t_max() < t_final:  # A whole segment beyond t_final.
+    steps += ensemble.solve_to_trajectories(t, trajectories)
+    t += step
+  for internal, caller in enumerate(order):
+    ephemeris.append_segments(int(caller), trajectories.segments(internal))
+  ensemble.close()
+  trajectories.close()
+  return steps
 
 
 def rotation(inclination, node, argument):

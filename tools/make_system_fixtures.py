@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Turns the reference's gravity-model / initial-state configuration files into
-the compact JSON fixtures under tests/golden/ that the oracle, the tests and
+the compact JSON files under principia_b200/data/ that the oracle, the tests and
 bench.py load (the reference tree does not exist on the GPU box).
 
 Run in the build container only:
@@ -301,7 +301,7 @@ def make_system(gravity_file, state_file):
 
 
 def main():
-  golden = os.path.join(REPO, 'tests', 'golden')
+  golden = os.path.join(REPO, 'principia_b200', 'data')
   for name, gravity, state in (
       ('sol_jd2451545', 'sol_gravity_model.proto.txt',
        'sol_initial_state_jd_2451545_000000000.proto.txt'),
