@@ -395,6 +395,19 @@ typedef struct pb_adaptive_step_flow_t {
    * 8 planes of n: direction xyz, thrust, initial_mass, mass_flow,
    * initial_time, final_time (SI). */
   const double* burns;
+  /* The GeneralizedIntrinsicAcceleration of the generalized overload
+   * (ephemeris.hpp:209-215, ephemeris_body.hpp:446-478; needs
+   * PB_FINE_1987_RKNG_34, whose velocity stages a' then feed the right-hand
+   * side): if != NULL, n body indices (caller order; in device memory for the
+   * _device variant); probe i with frenet_centres[i] >= 0 fires a burn whose
+   * `direction` is expressed in the Frenet frame (tangent, normal, binormal)
+   * of its trajectory in the body-centred non-rotating frame of that body,
+   * Manoeuvre::FrenetIntrinsicAcceleration (ksp_plugin/manœuvre_body.hpp:
+   * 310-321,383-393; physics/reference_frame_body.hpp:38-54): tangent along
+   * the velocity relative to the body, normal along the part of the geometric
+   * acceleration (gravitational acceleration of the probe minus that of the
+   * body) orthogonal to it.  -1: inertially fixed as above. */
+  const int32_t* frenet_centres;
 } pb_adaptive_step_flow_t;
 enum { PB_BURN_PLANES = 8 };
 pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* ephemeris,

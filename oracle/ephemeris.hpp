@@ -390,15 +390,72 @@ class Ephemeris {
   struct Burn {
     Vec3 direction;
     double thrust, initial_mass, mass_flow, initial_time, final_time;
+    // >= 0: `direction` is expressed in the Frenet frame of the trajectory in
+    // the body-centred non-rotating frame of this body (internal index):
+    // Manœuvre::FrenetIntrinsicAcceleration, a velocity-dependent intrinsic
+    // acceleration.  -1: inertially fixed.
+    int frenet_centre = -1;
     Vec3 IntrinsicAcceleration(double const t) const {
+      return IntrinsicAcceleration(t, direction);
+    }
+    // Manœuvre::ComputeIntrinsicAcceleration(t, direction),
+    // ksp_plugin/manœuvre_body.hpp:395-406.
+    Vec3 IntrinsicAcceleration(double const t,
+                               Vec3 const& inertial_direction) const {
       if (t >= initial_time && t <= final_time) {
-        return direction * thrust /
+        return inertial_direction * thrust /
                (initial_mass - (t - initial_time) * mass_flow);
       } else {
         return {0.0, 0.0, 0.0};
       }
     }
   };
+
+  // The inertial direction of a Frenet-frame burn for a trajectory at
+  // (t, q, v) whose gravitational acceleration is `gravitational`:
+  // Manœuvre::ComputeFrenetFrame (ksp_plugin/manœuvre_body.hpp:383-393) for a
+  // BodyCentredNonRotatingReferenceFrame (physics/
+  // body_centred_non_rotating_reference_frame_body.hpp:73-88,118-140):
+  // ReferenceFrame::FrenetFrame (physics/reference_frame_body.hpp:38-54) has
+  //   tangent  = Normalize(velocity),
+  //   normal   = Normalize(acceleration.OrthogonalizationAgainst(velocity)),
+  //   binormal = Wedge(tangent, normal),
+  // velocity and geometric acceleration (RigidReferenceFrame::
+  // GeometricAcceleration, rigid_reference_frame_body.hpp:59-78,364-398: the
+  // gravitational acceleration at the point minus the acceleration of the
+  // centre; the rotational terms vanish with the angular velocity) RELATIVE to
+  // the centre.  The reference rotates the degrees of freedom into the axes of
+  // the centre's celestial frame, builds the trihedron there and rotates the
+  // direction back (two quaternion rotations, and the gravitational
+  // acceleration re-evaluated at the position carried there and back); the
+  // trihedron is covariant under that rotation, so it is formed here directly
+  // in the inertial axes, from the acceleration the right-hand side has just
+  // computed.  Same frame, same formulae; the results differ from the
+  // reference's by the rounding of the two rotations (no known answer of the
+  // reference pins this routine: its tests use mock frames).
+  Vec3 FrenetDirection(Burn const& burn, double const t, Vec3 const& v,
+                       Vec3 const& gravitational) const {
+    int const n = size();
+    std::vector<Vec3> positions(n);
+    for (int b = 0; b < n; ++b) {
+      positions[b] = trajectories_[b]->EvaluatePosition(t);
+    }
+    int const c = burn.frenet_centre;
+    Vec3 const centre_velocity = trajectories_[c]->EvaluateVelocity(t);
+    Vec3 const centre_acceleration =
+        ComputeGravitationalAccelerationOnMassiveBody(c, positions, t);
+    Vec3 const velocity = v - centre_velocity;
+    Vec3 const acceleration = gravitational - centre_acceleration;
+    Vec3 const tangent = velocity / Norm(velocity);
+    // OrthogonalizationAgainst, geometry/r3_element_body.hpp:186-190.
+    Vec3 const normal_acceleration =
+        acceleration - Dot(acceleration, tangent) * tangent;
+    Vec3 const normal = normal_acceleration / Norm(normal_acceleration);
+    Vec3 const binormal = Cross(tangent, normal);
+    // Rotation(tangent, normal, binormal) applied to the Frenet coordinates.
+    return burn.direction.x * tangent + burn.direction.y * normal +
+           burn.direction.z * binormal;
+  }
 
   int32_t FlowWithAdaptiveStep(State& state, double t, double length_tolerance,
                                double speed_tolerance, std::int64_t max_steps,
@@ -448,6 +505,25 @@ class Ephemeris {
                                        error);
         },
         parameters);
+    if (generalized && burn != nullptr && burn->frenet_centre >= 0) {
+      // ephemeris_body.hpp:446-478: the generalized overload, whose intrinsic
+      // acceleration sees the degrees of freedom.
+      instance.generalized_rhs =
+          [this, &gravitation, burn](double const t,
+                                     std::vector<double> const& q,
+                                     std::vector<double> const& v,
+                                     std::vector<double>& g) -> int32_t {
+        int32_t const error = gravitation(t, q, g);
+        Vec3 acceleration{g[0], g[1], g[2]};
+        Vec3 const direction =
+            FrenetDirection(*burn, t, Vec3{v[0], v[1], v[2]}, acceleration);
+        acceleration += burn->IntrinsicAcceleration(t, direction);
+        g[0] = acceleration.x;
+        g[1] = acceleration.y;
+        g[2] = acceleration.z;
+        return error;
+      };
+    }
     int32_t status = instance.Solve(t_final);
     state = last;
     if (evaluations != nullptr) {

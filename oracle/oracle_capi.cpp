@@ -1220,6 +1220,9 @@ int32_t orc_flow_with_adaptive_step(orc_ephemeris* e,
       double const* const b = flow->burns + i;
       burn = {{b[0], b[n], b[2 * n]}, b[3 * n], b[4 * n], b[5 * n], b[6 * n],
               b[7 * n]};
+      if (flow->frenet_centres != nullptr && flow->frenet_centres[i] >= 0) {
+        burn.frenet_centre = e->internal_of_caller[flow->frenet_centres[i]];
+      }
     }
     int32_t const status = e->e->FlowWithAdaptiveStep(
         state, flow->t_final, flow->length_integration_tolerance,

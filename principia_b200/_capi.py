@@ -90,6 +90,7 @@ class AdaptiveStepFlow(ctypes.Structure):
       ('state_log', ctypes.c_void_p),
       ('sink', ctypes.c_void_p),
       ('burns', ctypes.c_void_p),
+      ('frenet_centres', ctypes.c_void_p),
   ]
 
 

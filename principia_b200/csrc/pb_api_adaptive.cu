@@ -126,10 +126,21 @@ pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
     w->timing_events.push_back(event);
   }
   PB_CUDA(cudaEventRecord(w->timing_events[0], stream));
+  // A velocity-dependent intrinsic acceleration takes the generalized Solve
+  // (the velocity stages exist only there).
+  bool const generalized =
+      flow->burns != nullptr && flow->frenet_centres != nullptr;
+  if (generalized && flow->method != PB_FINE_1987_RKNG_34) {
+    return Fail(PB_INVALID_ARGUMENT,
+                "Frenet burns need the generalized integrator "
+                "(PB_FINE_1987_RKNG_34)");
+  }
   auto const kernel =
       flow->method == PB_FINE_1987_RKNG_34
-          ? (min_blocks == 2 ? ErknFlowKernel<Fine1987RKNG34, 2>
-                             : ErknFlowKernel<Fine1987RKNG34, 3>)
+          ? (generalized
+                 ? ErknFlowKernel<Fine1987RKNG34, 2, true>
+                 : (min_blocks == 2 ? ErknFlowKernel<Fine1987RKNG34, 2>
+                                    : ErknFlowKernel<Fine1987RKNG34, 3>))
           : (min_blocks == 2
                  ? ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 2>
                  : ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 3>);
@@ -139,7 +150,8 @@ pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
       reinterpret_cast<long long*>(flow->accepted_steps),
       reinterpret_cast<long long*>(flow->rejected_steps),
       reinterpret_cast<long long*>(flow->evaluations), flow->step_log,
-      flow->state_log, sink, flow->burns);
+      flow->state_log, sink, flow->burns,
+      generalized ? flow->frenet_centres : nullptr);
   PB_LAUNCHED();
   PB_CUDA(cudaEventRecord(w->timing_events[1], stream));
   PB_CUDA(cudaStreamSynchronize(stream));
@@ -181,6 +193,9 @@ pb_status_t ValidateAdaptiveFlow(pb_ephemeris_t* e,
   }
   if (flow->t_final != flow->t_final) {
     return Fail(PB_INVALID_ARGUMENT, "NaN time");
+  }
+  if (flow->frenet_centres != nullptr && flow->burns == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "Frenet centres without burns");
   }
   return PB_OK;
 }
@@ -234,6 +249,17 @@ pb_status_t pb_flow_with_adaptive_step(pb_ephemeris_t* e,
     PB_RETURN_IF_ERROR(
         w->burns_scratch.Upload(flow->burns, PB_BURN_PLANES * n, stream));
     device_flow.burns = w->burns_scratch.data;
+  }
+  if (flow->frenet_centres != nullptr) {
+    int32_t const n_bodies = static_cast<int32_t>(e->model.bodies.size());
+    for (std::size_t i = 0; i < n; ++i) {
+      if (flow->frenet_centres[i] >= n_bodies) {
+        return Fail(PB_INVALID_ARGUMENT, "Frenet centre out of range");
+      }
+    }
+    PB_RETURN_IF_ERROR(
+        w->frenet_scratch.Upload(flow->frenet_centres, n, stream));
+    device_flow.frenet_centres = w->frenet_scratch.data;
   }
   device_flow.state = state;
   device_flow.time = time;

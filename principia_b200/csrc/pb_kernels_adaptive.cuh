@@ -13,6 +13,7 @@
 
 #include "pb_accel.cuh"
 #include "pb_downsampling.cuh"
+#include "pb_kernels_jerk.cuh"
 #include "pb_model.h"
 
 namespace pb {
@@ -240,6 +241,105 @@ static __global__ void AdaptiveCostKernel(EphemerisView const e,
   index[i] = static_cast<int>(i);
 }
 
+// The inertial direction of a burn given in the Frenet frame of the trajectory
+// in the body-centred non-rotating frame of body `centre` (internal index):
+// Manœuvre::ComputeFrenetFrame, ksp_plugin/manœuvre_body.hpp:383-393, with
+// ReferenceFrame::FrenetFrame, physics/reference_frame_body.hpp:38-54 --
+// tangent = Normalize(velocity), normal = Normalize(acceleration
+// .OrthogonalizationAgainst(velocity)), binormal = Wedge(tangent, normal) --
+// on the velocity and the geometric acceleration relative to the centre
+// (RigidReferenceFrame::GeometricAcceleration, rigid_reference_frame_body.hpp
+// :59-78,364-398: the gravitational acceleration at the point, `gravitational`,
+// minus the acceleration of the centre,
+// Ephemeris::ComputeGravitationalAccelerationOnMassiveBody,
+// ephemeris_body.hpp:1249-1315).  Formed directly in the inertial axes (the
+// trihedron is covariant under the rotation to the centre's celestial frame
+// that the reference applies and undoes); the oracle does the same operations
+// in the same order (oracle/ephemeris.hpp FrenetDirection).  A cold path: it
+// evaluates every body's polynomial and the full force on the centre.
+__device__ __noinline__ Vec3 FrenetDirection(EphemerisView const& e,
+                                             double const t, int const centre,
+                                             Vec3 const& direction,
+                                             Vec3 const& v,
+                                             Vec3 const& gravitational) {
+  // One stage-table entry in thread-local memory: positions, then frames.
+  double entry[3 * kMaxConstantBodies + 6 * 8];
+  int const n = e.n_bodies;
+  Vec3 centre_velocity{0.0, 0.0, 0.0};
+  for (int b = 0; b < n; ++b) {
+    int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
+                                    e.segment_end[b], t);
+    Vec3 const p = EvaluateSegment(e, segment, t);
+    entry[3 * b] = p.x;
+    entry[3 * b + 1] = p.y;
+    entry[3 * b + 2] = p.z;
+    if (b == centre) {
+      centre_velocity = EvaluateSegmentDerivative(e, segment, t);
+    }
+    int const slot = e.bodies[b].frame_slot;
+    if (slot >= 0 && slot < 8) {
+      Vec3 x_hat, y_hat;
+      SurfaceFrameAxes(e.bodies[b], t, x_hat, y_hat);
+      double* const frame = entry + 3 * n + 6 * slot;
+      frame[0] = x_hat.x;
+      frame[1] = x_hat.y;
+      frame[2] = x_hat.z;
+      frame[3] = y_hat.x;
+      frame[4] = y_hat.y;
+      frame[5] = y_hat.z;
+    }
+  }
+  // ComputeGravitationalAccelerationOnMassiveBody(centre, t): the other bodies
+  // in increasing internal order (MassiveAccelerationKernel).
+  double const* const frames = entry + 3 * n;
+  Vec3 const q1{entry[3 * centre], entry[3 * centre + 1],
+                entry[3 * centre + 2]};
+  Vec3 centre_acceleration{0.0, 0.0, 0.0};
+  for (int b2 = 0; b2 < n; ++b2) {
+    if (b2 == centre) {
+      continue;
+    }
+    Vec3 const q2{entry[3 * b2], entry[3 * b2 + 1], entry[3 * b2 + 2]};
+    Vec3 unused{0.0, 0.0, 0.0};
+    MassivePairInteraction<false>(e, centre, b2, frames, q1, q2,
+                                  centre_acceleration, unused);
+  }
+  Vec3 const velocity = v - centre_velocity;
+  Vec3 const acceleration = gravitational - centre_acceleration;
+  Vec3 const tangent = velocity / sqrt(Norm2(velocity));
+  Vec3 const normal_acceleration =
+      acceleration - Dot(acceleration, tangent) * tangent;
+  Vec3 const normal = normal_acceleration / sqrt(Norm2(normal_acceleration));
+  Vec3 const binormal = Cross(tangent, normal);
+  return direction.x * tangent + direction.y * normal + direction.z * binormal;
+}
+
+// Manœuvre::ComputeIntrinsicAcceleration with the direction resolved by the
+// caller: for a Frenet burn the direction is only needed while the engine
+// fires.
+__device__ __forceinline__ Vec3 GeneralizedBurnIntrinsicAcceleration(
+    EphemerisView const& e, double const* const burns,
+    int32_t const* const frenet_centres, long long const n, long long const i,
+    double const t, Vec3 const& v, Vec3 const& gravitational) {
+  int const caller = frenet_centres != nullptr ? frenet_centres[i] : -1;
+  if (caller < 0) {
+    return BurnIntrinsicAcceleration(burns, n, i, t);
+  }
+  double const initial_time = burns[6 * n + i];
+  double const final_time = burns[7 * n + i];
+  if (t >= initial_time && t <= final_time) {
+    Vec3 const frenet{burns[i], burns[n + i], burns[2 * n + i]};
+    Vec3 const direction = FrenetDirection(e, t, e.internal_of_caller[caller],
+                                           frenet, v, gravitational);
+    double const thrust = burns[3 * n + i];
+    double const initial_mass = burns[4 * n + i];
+    double const mass_flow = burns[5 * n + i];
+    return direction * thrust / (initial_mass - (t - initial_time) * mass_flow);
+  } else {
+    return {0.0, 0.0, 0.0};
+  }
+}
+
 // The embedded methods, integrators/methods.hpp.  a is strictly lower
 // triangular, (i, j) -> i (i - 1) / 2 + j.
 // DormandالمكاوىPrince1986RKN434FM, :574-597: 4 stages, first same as last.
@@ -256,6 +356,8 @@ struct DormandElMikkawyPrince1986RKN434FM {
   PB_METHOD_TABLE(a, 6, 1.0 / 32.0,
                   7.0 / 1000.0, 119.0 / 500.0,
                   1.0 / 14.0, 8.0 / 27.0, 25.0 / 189.0)
+  // Not a generalized method: no velocity stages.
+  PB_METHOD_TABLE(a_prime, 6, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0)
   PB_METHOD_TABLE(b_hat, 4, 1.0 / 14.0, 8.0 / 27.0, 25.0 / 189.0, 0.0)
   PB_METHOD_TABLE(b_hat_prime, 4, 1.0 / 14.0, 32.0 / 81.0, 250.0 / 567.0,
                   5.0 / 54.0)
@@ -281,6 +383,12 @@ struct Fine1987RKNG34 {
                   1 / 36.0, 1 / 36.0,
                   9 / 128.0, 0.0, 27 / 128.0,
                   11 / 60.0, -3 / 20.0, 9 / 25.0, 8 / 75.0)
+  // The velocity stages of the generalized method (used when the right-hand
+  // side depends on the velocity).
+  PB_METHOD_TABLE(a_prime, 10, 2 / 9.0,
+                  1 / 12.0, 1 / 4.0,
+                  69 / 128.0, -234 / 128.0, 135 / 64.0,
+                  -17 / 12.0, 27 / 4.0, -27 / 5.0, 16 / 15.0)
   PB_METHOD_TABLE(b_hat, 5, 19 / 180.0, 0.0, 63 / 200.0, 16 / 225.0,
                   1 / 120.0)
   PB_METHOD_TABLE(b_hat_prime, 5, 1 / 9.0, 0.0, 9 / 20.0, 16 / 45.0, 1 / 12.0)
@@ -297,7 +405,10 @@ struct Fine1987RKNG34 {
 // state: 12 planes of n; time: 2 planes of n (value, error).  `order` lists
 // the trajectories in the order in which the lanes take them; `queue` is the
 // number of trajectories taken so far (zeroed by the host).
-template<typename Method, int kMinBlocks>
+// kGeneralized: the generalized Solve (embedded_explicit_generalized_runge_
+// kutta_nyström_integrator_body.hpp:44-300): the velocity stages a' are formed
+// and the intrinsic acceleration sees them (Frenet burns).
+template<typename Method, int kMinBlocks, bool kGeneralized = false>
 __global__ void __launch_bounds__(kAdaptiveThreads, kMinBlocks)
 ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                long long const n, int const* __restrict__ order,
@@ -310,7 +421,8 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                long long* __restrict__ evaluations_out,
                double* __restrict__ step_log,
                double* __restrict__ state_log, DownsamplerView const sink,
-               double const* __restrict__ burns) {
+               double const* __restrict__ burns,
+               int32_t const* __restrict__ frenet_centres) {
   constexpr int kStages = Method::kStages;
   constexpr double safety_factor = 0.9;
   double const t_final = parameters.t_final;
@@ -425,7 +537,24 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
         Vec3 acceleration;
         int32_t const rhs_error =
             FastAccelerationAtTime(e, t_stage, q_stage, acceleration, hint);
-        if (burns != nullptr) {
+        if constexpr (kGeneralized) {
+          if (burns != nullptr) {
+            // :186-201 of the generalized integrator: the velocity stage, then
+            // ephemeris_body.hpp:462-470.
+            Vec3 sum_prime{0.0, 0.0, 0.0};
+#pragma unroll
+            for (int j = 0; j < kStages - 1; ++j) {
+              if (j < s) {
+                sum_prime += Method::a_prime(row + j) * g[j];
+              }
+            }
+            Vec3 const v_stage{v[0].value + h * sum_prime.x,
+                               v[1].value + h * sum_prime.y,
+                               v[2].value + h * sum_prime.z};
+            acceleration += GeneralizedBurnIntrinsicAcceleration(
+                e, burns, frenet_centres, n, i, t_stage, v_stage, acceleration);
+          }
+        } else if (burns != nullptr) {
           // ephemeris_body.hpp:430-432.
           acceleration += BurnIntrinsicAcceleration(burns, n, i, t_stage);
         }

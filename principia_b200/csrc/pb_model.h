@@ -70,6 +70,8 @@ struct EphemerisView {
   // [segment][xyz][18]: the host API's [segment][18][3] transposed, so that the
   // coefficients of one coordinate are contiguous (16-byte loads of pairs).
   double const* segment_coefficients;
+  // Caller index -> internal index.
+  int32_t const* internal_of_caller;
 };
 
 // Set by FlowPathKernel when some probe of a fixed-step flow is within the

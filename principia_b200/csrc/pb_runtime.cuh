@@ -262,6 +262,7 @@ struct FlowWorkspace {
   // (kPathGenericHarmonics).
   DeviceBuffer<int32_t> status_word;
   DeviceBuffer<long long> counters;
+  DeviceBuffer<int32_t> frenet_scratch;
   PinnedBuffer<double> pinned_times;
   PinnedBuffer<int32_t> pinned_status;
 
@@ -325,6 +326,7 @@ struct pb_ephemeris {
   pb::DeviceBuffer<pb::DeviceBody> bodies;
   pb::DeviceBuffer<pb::Damping> dampings;
   pb::DeviceBuffer<double> cos, sin, normalization;
+  pb::DeviceBuffer<int32_t> internal_of_caller;
   pb::DeviceBuffer<int32_t> segment_offset, segment_end;
   pb::DeviceBuffer<double> segment_t_max, segment_origin, segment_coefficients;
   pb::DeviceBuffer<int32_t> segment_degree;
@@ -387,6 +389,7 @@ struct pb_ephemeris {
     v.segment_origin = segment_origin.data;
     v.segment_degree = segment_degree.data;
     v.segment_coefficients = segment_coefficients.data;
+    v.internal_of_caller = internal_of_caller.data;
     return v;
   }
 };

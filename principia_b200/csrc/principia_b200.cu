@@ -545,6 +545,11 @@ pb_status_t pb_ephemeris_create(int32_t n_bodies, const pb_body_t* bodies,
   if (status == PB_OK) status = e->sin.Upload(sin, stream);
   if (status == PB_OK) status = e->normalization.Upload(normalization, stream);
   if (status == PB_OK) {
+    std::vector<int32_t> const internal_of_caller(
+        e->model.internal_of_caller.begin(), e->model.internal_of_caller.end());
+    status = e->internal_of_caller.Upload(internal_of_caller, stream);
+  }
+  if (status == PB_OK) {
     status = cuda_ok(cudaMalloc(&e->stop_word_device, sizeof(int32_t)));
   }
   if (status == PB_OK) {

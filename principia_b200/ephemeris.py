@@ -286,9 +286,12 @@ class Ephemeris:
   def flow_with_adaptive_step(self, t_final, state, time, length_tolerance,
                               speed_tolerance, max_steps=2**62,
                               step_log_capacity=0, sink=None, burns=None,
-                              method=_capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM):
+                              method=_capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM,
+                              frenet_centres=None):
     """FlowWithAdaptiveStep, one trajectory per probe.  state: (12, n),
-    time: (2, n); updated in place (host buffers)."""
+    time: (2, n); updated in place (host buffers).  frenet_centres: (n,) body
+    indices (-1: inertially fixed) for burns given in the Frenet frame of the
+    body-centred non-rotating frame of that body (needs FINE_1987_RKNG_34)."""
     assert state.flags.c_contiguous and time.flags.c_contiguous
     assert state.dtype == np.float64 and time.dtype == np.float64
     assert state.shape[0] == 12 and time.shape == (2, state.shape[1])
@@ -321,6 +324,10 @@ class Ephemeris:
       burns = np.ascontiguousarray(burns, dtype=np.float64)
       assert burns.shape == (8, n)
       flow.burns = burns.ctypes.data
+    if frenet_centres is not None:
+      frenet_centres = np.ascontiguousarray(frenet_centres, dtype=np.int32)
+      assert frenet_centres.shape == (n,) and burns is not None
+      flow.frenet_centres = frenet_centres.ctypes.data
     if sink is not None:
       # A trajectory.Downsampler: every accepted state is appended to it inside
       # the kernel.

@@ -367,7 +367,8 @@ class OracleEphemeris:
                               speed_tolerance, max_steps=2**62,
                               step_log_capacity=0, threads=0,
                               state_log=False, burns=None,
-                              method=_capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM):
+                              method=_capi.DORMAND_ELMIKKAWY_PRINCE_1986_RKN_434FM,
+                              frenet_centres=None):
     """state: (12, n), time: (2, n); updated in place."""
     n = state.shape[1]
     flow = _capi.AdaptiveStepFlow()
@@ -396,6 +397,9 @@ class OracleEphemeris:
       burns = np.ascontiguousarray(burns, dtype=np.float64)
       assert burns.shape == (8, n)
       flow.burns = burns.ctypes.data
+    if frenet_centres is not None:
+      frenet_centres = np.ascontiguousarray(frenet_centres, dtype=np.int32)
+      flow.frenet_centres = frenet_centres.ctypes.data
     states = None
     if state_log and step_log_capacity > 0:
       states = np.full((step_log_capacity, 6, n), np.nan)

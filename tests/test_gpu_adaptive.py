@@ -278,3 +278,80 @@ def test_reference_elephant_at_the_pole(sol_system, integrator):
       time[0, 0], np.ascontiguousarray(state[0:3]))
   assert -2.1e-18 <= acceleration[0, 0] <= -1.9e-18
   assert abs(acceleration[2, 0] + 9.832) / 9.832 < 6.7e-6
+
+
+def test_frenet_burns_match_oracle(sol_system, sol_oracle, sol_gpu):
+  """The generalized FlowWithAdaptiveStep (ephemeris_body.hpp:446-478) with a
+  velocity-dependent intrinsic acceleration: burns given in the Frenet frame
+  of the body-centred non-rotating frame of the Earth (or of the Moon)
+  (Manœuvre::FrenetIntrinsicAcceleration, ksp_plugin/manœuvre_body.hpp:
+  310-321), integrated with Fine1987RKNG34, whose velocity stages a' now feed
+  the right-hand side.  Same accepted steps and states as the oracle's
+  generalized integrator (itself pinned to the reference's Legendre test), and
+  a prograde burn does what a prograde burn does."""
+  n = 48
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  moon_index = sol_system.index('Moon')
+  earth_index = sol_system.index('Earth')
+  state = workloads.eccentric_probes(n, earth['q'], earth['v'], earth['mu'],
+                                     23)
+  rng = np.random.default_rng(6)
+  burns = np.zeros((8, n))
+  direction = rng.normal(size=(3, n))
+  burns[0:3] = direction / np.linalg.norm(direction, axis=0)
+  burns[0:3, 0] = [1.0, 0.0, 0.0]            # Prograde.
+  burns[0:3, 1] = [-1.0, 0.0, 0.0]           # Retrograde.
+  burns[0:3, 2] = [0.0, 0.0, 1.0]            # Along the orbit normal.
+  burns[3] = rng.uniform(1e3, 5e5, n)        # Thrust, N.
+  burns[4] = rng.uniform(5e3, 5e4, n)        # Initial mass, kg.
+  burns[5] = burns[3] / (9.80665 * 320.0)    # Mass flow at 320 s.
+  burns[6] = rng.uniform(-200.0, 3000.0, n)  # Initial time.
+  burns[7] = burns[6] + rng.uniform(10.0, 400.0, n)
+  burns[3:8, 0:3] = np.array([2e4, 2e4, 2e3, 100.0, 400.0])[:, None]
+  burns[5, 0:3] = burns[3, 0:3] / (9.80665 * 320.0)
+  centres = np.full(n, earth_index, dtype=np.int32)
+  centres[5::7] = moon_index
+  centres[3::5] = -1  # Inertially fixed burns in the same batch.
+  method = _capi.FINE_1987_RKNG_34
+  t_final = 6000.0
+  time = np.zeros((2, n))
+  expected_state, expected_time = state.copy(), time.copy()
+  initial = state.copy()
+  result = sol_gpu.flow_with_adaptive_step(
+      t_final, state, time, 1e-3, 1e-3, step_log_capacity=96, burns=burns,
+      method=method, frenet_centres=centres)
+  expected = sol_oracle.flow_with_adaptive_step(
+      t_final, expected_state, expected_time, 1e-3, 1e-3,
+      step_log_capacity=96, burns=burns, method=method,
+      frenet_centres=centres)
+  assert np.all(expected['status'] == 0)
+  assert list(result['status']) == list(expected['status'])
+  assert list(result['accepted']) == list(expected['accepted'])
+  assert list(result['rejected']) == list(expected['rejected'])
+  assert list(result['evaluations']) == list(expected['evaluations'])
+  assert_bitwise_equal(result['step_log'], expected['step_log'], 'step log')
+  assert_bitwise_equal(time, expected_time, 'time')
+  assert_bitwise_equal(state, expected_state, 'state')
+  # The Frenet burns differ from the same burns held inertially fixed.
+  fixed_state, fixed_time = initial.copy(), np.zeros((2, n))
+  sol_oracle.flow_with_adaptive_step(t_final, fixed_state, fixed_time, 1e-3,
+                                     1e-3, burns=burns, method=method)
+  frenet = centres >= 0
+  assert np.all(np.linalg.norm((state - fixed_state)[0:3, frenet], axis=0) > 1.0)
+  assert_bitwise_equal(state[:, ~frenet], fixed_state[:, ~frenet])
+  # Physics: against the unpowered flow, the prograde burn (300 s at 1 to
+  # 1.3 m/s^2) raises the orbital energy relative to the Earth, the retrograde
+  # one lowers it, the normal one changes it much less.
+  coast_state, coast_time = initial.copy(), np.zeros((2, n))
+  sol_oracle.flow_with_adaptive_step(t_final, coast_state, coast_time, 1e-3,
+                                     1e-3, method=method)
+  q_earth = sol_oracle.evaluate_all_positions(t_final)[earth_index]
+  v_earth = sol_oracle.evaluate_all_velocities(t_final)[earth_index]
+
+  def energy(s):
+    q = s[0:3] - q_earth[:, None]
+    v = s[6:9] - v_earth[:, None]
+    return 0.5 * (v * v).sum(axis=0) - earth['mu'] / np.linalg.norm(q, axis=0)
+  gain = energy(state) - energy(coast_state)
+  assert gain[0] > 0 and gain[1] < 0
+  assert abs(gain[2]) < 0.05 * min(gain[0], -gain[1])
