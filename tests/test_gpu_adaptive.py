@@ -302,9 +302,12 @@ def test_frenet_burns_match_oracle(sol_system, sol_oracle, sol_gpu):
   burns[0:3, 0] = [1.0, 0.0, 0.0]            # Prograde.
   burns[0:3, 1] = [-1.0, 0.0, 0.0]           # Retrograde.
   burns[0:3, 2] = [0.0, 0.0, 1.0]            # Along the orbit normal.
-  burns[3] = rng.uniform(1e3, 5e5, n)        # Thrust, N.
   burns[4] = rng.uniform(5e3, 5e4, n)        # Initial mass, kg.
-  burns[5] = burns[3] / (9.80665 * 320.0)    # Mass flow at 320 s.
+  # 0.1 to 3 m/s^2 at ignition; at most 400 s at 320 s of specific impulse
+  # burn 38 % of the mass (a burn that exhausts the mass is singular and the
+  # step control then crawls for ever, here as in the reference).
+  burns[3] = burns[4] * rng.uniform(0.1, 3.0, n)
+  burns[5] = burns[3] / (9.80665 * 320.0)    # Mass flow.
   burns[6] = rng.uniform(-200.0, 3000.0, n)  # Initial time.
   burns[7] = burns[6] + rng.uniform(10.0, 400.0, n)
   burns[3:8, 0:3] = np.array([2e4, 2e4, 2e3, 100.0, 400.0])[:, None]
@@ -319,11 +322,11 @@ def test_frenet_burns_match_oracle(sol_system, sol_oracle, sol_gpu):
   initial = state.copy()
   result = sol_gpu.flow_with_adaptive_step(
       t_final, state, time, 1e-3, 1e-3, step_log_capacity=96, burns=burns,
-      method=method, frenet_centres=centres)
+      method=method, frenet_centres=centres, max_steps=50000)
   expected = sol_oracle.flow_with_adaptive_step(
       t_final, expected_state, expected_time, 1e-3, 1e-3,
       step_log_capacity=96, burns=burns, method=method,
-      frenet_centres=centres)
+      frenet_centres=centres, max_steps=50000)
   assert np.all(expected['status'] == 0)
   assert list(result['status']) == list(expected['status'])
   assert list(result['accepted']) == list(expected['accepted'])
