@@ -340,7 +340,9 @@ def test_frenet_burns_match_oracle(sol_system, sol_oracle, sol_gpu):
   sol_oracle.flow_with_adaptive_step(t_final, fixed_state, fixed_time, 1e-3,
                                      1e-3, burns=burns, method=method)
   frenet = centres >= 0
-  assert np.all(np.linalg.norm((state - fixed_state)[0:3, frenet], axis=0) > 1.0)
+  fired = frenet & (burns[7] > 0.0)  # The others end before the flow starts.
+  assert fired.sum() > 20
+  assert np.all(np.linalg.norm((state - fixed_state)[0:3, fired], axis=0) > 1.0)
   assert_bitwise_equal(state[:, ~frenet], fixed_state[:, ~frenet])
   # Physics: against the unpowered flow, the prograde burn (300 s at 1 to
   # 1.3 m/s^2) raises the orbital energy relative to the Earth, the retrograde
