@@ -502,7 +502,41 @@ struct LocalScratch {
   }
   template<int n> PB_HD Vec3 DegreeSum() const { return degree_sum[n]; }
   template<int n> PB_HD void SetDegreeSum(Vec3 const& x) { degree_sum[n] = x; }
+  // The division by the degree in the Legendre recurrences, and whether the
+  // evaluation has to be abandoned (never, with the checked division).
+  PB_HD double Divide(double const x, int const n, double const reciprocal) {
+    return DivideBySmallInteger(x, n, reciprocal);
+  }
+  PB_HD constexpr bool Failed() const { return false; }
 };
+
+#if defined(__CUDACC__)
+// The same scratch with the branch-free division: DivideBySmallInteger's fast
+// path unconditionally, its operand test folded into a running maximum (two
+// integer instructions).  Without the 64 branches of an evaluation the
+// recurrences of a degree are one basic block that the scheduler can
+// interleave.  When Failed() the results are garbage and the caller evaluates
+// again with the checked division; the unrolled evaluation tests it once per
+// degree, which also keeps the degrees apart in the instruction stream (a
+// single block for all of them makes ptxas hoist far too much and spill).
+template<int kMaxDegree>
+struct FlaggedScratch : LocalScratch<kMaxDegree> {
+  unsigned flag = 0;
+  __device__ __forceinline__ double Divide(double const x, int const n,
+                                           double const reciprocal) {
+    // exponent < 0x036 or exponent == 0x7ff <=> offset >= 0x7c900000.
+    flag = __viaddmax_u32(
+        static_cast<unsigned>(__double2hiint(x)) & 0x7ff00000u,
+        0u - 0x03600000u, flag);
+    double const q0 = x * reciprocal;
+    double const r = fma(-static_cast<double>(n), q0, x);
+    return fma(r, reciprocal, q0);
+  }
+  __device__ __forceinline__ bool Failed() const {
+    return flag >= 0x7c900000u;
+  }
+};
+#endif
 
 PB_HD constexpr int Tri(int const n, int const m) {
   return n * (n + 1) / 2 + m;
@@ -540,22 +574,22 @@ PB_HD void UnrolledUpdateOrder(double const sin_beta,
     }
     constexpr double one_over_n = 1.0 / n;
     if constexpr (m == 0) {
-      p.P[Tri(n, 0)] = DivideBySmallInteger(
+      p.P[Tri(n, 0)] = w.Divide(
           (2 * n - 1) * sin_beta * p.P[Tri(n - 1, 0)] -
               (n - 1) * p.P[Tri(n - 2, 0)],
           n, one_over_n);
     }
     if constexpr (m == n) {
     } else if constexpr (m == n - 1) {
-      p.P[Tri(n, m + 1)] = DivideBySmallInteger(
+      p.P[Tri(n, m + 1)] = w.Divide(
           (2 * n - 1) * (m + 1) * p.P[Tri(n - 1, m)], n, one_over_n);
     } else if constexpr (m == n - 2) {
-      p.P[Tri(n, m + 1)] = DivideBySmallInteger(
+      p.P[Tri(n, m + 1)] = w.Divide(
           (2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
                          (m + 1) * p.P[Tri(n - 1, m)]),
           n, one_over_n);
     } else {
-      p.P[Tri(n, m + 1)] = DivideBySmallInteger(
+      p.P[Tri(n, m + 1)] = w.Divide(
           (2 * n - 1) * (sin_beta * p.P[Tri(n - 1, m + 1)] +
                          (m + 1) * p.P[Tri(n - 1, m)]) -
               (n - 1) * p.P[Tri(n - 2, m + 1)],
@@ -621,6 +655,9 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
   StaticForRange<2, kMaxDegree + 1>([&](auto n_constant) {
     constexpr int n = decltype(n_constant)::value;
     constexpr int size = kZonal ? 1 : n + 1;
+    if (w.Failed()) {
+      return;
+    }
     if constexpr (n % 2 == 0) {
       constexpr int h = n / 2;
       p.R_over_r[n] = p.R_over_r[h] * p.R_over_r[h] * s.r2;
@@ -655,6 +692,11 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
       StaticForRange<0, size>([&](auto m_constant) {
         UnrolledUpdateOrder<n, decltype(m_constant)::value>(s.sin_beta, p, w);
       });
+#if defined(PB_H_FENCE_TERMS)
+      if (w.Failed()) {
+        return;
+      }
+#endif
       Vec3 sum =
           UnrolledTerm<n, size - 1>(g, sigma_R_over_r, grad_sigma_R, s, p, w);
       StaticForRange<0, size - 1>([&](auto i_constant) {

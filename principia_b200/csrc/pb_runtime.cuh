@@ -349,6 +349,7 @@ struct pb_ephemeris {
   std::mutex hot_mutex;
   bool hot_body_valid = false;
   int hot_body = -1;
+  int warm_body = -1;  // See HotBody, pb_kernels_massless.cuh.
 
   // Measurement of the last completed flow call.
   mutable std::mutex statistics_mutex;

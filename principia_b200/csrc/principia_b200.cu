@@ -216,17 +216,17 @@ void ComputeNodes(SrknTableau const& tableau, double* c) {
 
 // The "hot" oblate body of the flow kernels -- the body of degree <=
 // kHotDegree with the highest limiting degree at the distance of `probe` (the
-// Earth for LEO probes); -1 if no harmonics above degree 2 are active there.
-// The choice only affects speed: both paths compute the same bits.
-int ChooseHotBody(pb_ephemeris const* e, double const t,
-                  double const* const probe) {
-  int hot = -1;
-  int best_degree = 2;
-  for (int b = 0; b < e->model.n_oblate; ++b) {
+// Earth for LEO probes); -1 if no harmonics above degree 2 are active there --
+// and the "warm" one: another body whose harmonics are active there, up to
+// degree kWarmDegree (the damped J2 of the Sun); -1 if none.  The choice only
+// affects speed: every path computes the same bits.
+void ChooseHotBodies(pb_ephemeris const* e, double const t,
+                     double const* const probe, int* const hot_out,
+                     int* const warm_out) {
+  int const n_oblate = e->model.n_oblate;
+  std::vector<int> max_degree(n_oblate, 1);
+  for (int b = 0; b < n_oblate; ++b) {
     DeviceBody const& body = e->model.bodies[b];
-    if (body.degree > kHotDegree) {
-      continue;
-    }
     HostTrajectory const& tr = e->trajectories[b];
     if (tr.t_max.empty()) {
       continue;
@@ -243,15 +243,30 @@ int ChooseHotBody(pb_ephemeris const* e, double const t,
                                          tr.degree[segment], x);
       d2 += (p - probe[k]) * (p - probe[k]);
     }
-    int const limiting = LimitingDegree(
+    max_degree[b] = LimitingDegree(
         e->model.dampings.data() + body.damping_offset, body.n_damping,
-        std::sqrt(d2));
-    if (limiting - 1 > best_degree) {
-      best_degree = limiting - 1;
+        std::sqrt(d2)) - 1;
+  }
+  int hot = -1;
+  int best_degree = 2;
+  for (int b = 0; b < n_oblate; ++b) {
+    if (e->model.bodies[b].degree <= kHotDegree &&
+        max_degree[b] > best_degree) {
+      best_degree = max_degree[b];
       hot = b;
     }
   }
-  return hot;
+  int warm = -1;
+  best_degree = 1;
+  for (int b = 0; b < n_oblate; ++b) {
+    if (b != hot && max_degree[b] <= kWarmDegree &&
+        max_degree[b] > best_degree) {
+      best_degree = max_degree[b];
+      warm = b;
+    }
+  }
+  *hot_out = hot;
+  *warm_out = warm;
 }
 
 // The constant bank of this translation unit's flow kernels (c_bodies, c_hot),
@@ -277,12 +292,14 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
                                  double const* const probe_host,
                                  int32_t const arithmetic,
                                  cudaStream_t stream,
-                                 ConstantBankLease& lease, int* hot_out) {
+                                 ConstantBankLease& lease, int* hot_out,
+                                 int* warm_out) {
   int const n_bodies = static_cast<int>(e->model.bodies.size());
   if (n_bodies > kMaxConstantBodies) {
     return Fail(PB_INVALID_ARGUMENT, "too many bodies for the flow kernel");
   }
   int hot;
+  int warm;
   {
     std::lock_guard<std::mutex> const lock(e->hot_mutex);
     if (!e->hot_body_valid) {
@@ -301,18 +318,21 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
           PB_CUDA(cudaStreamSynchronize(stream));
         }
       }
-      e->hot_body = ChooseHotBody(e, t, probe);
+      ChooseHotBodies(e, t, probe, &e->hot_body, &e->warm_body);
       e->hot_body_valid = n > 0;
     }
     hot = e->hot_body;
+    warm = e->warm_body;
   }
   *hot_out = hot;
+  *warm_out = warm;
   bool const contracted = arithmetic == PB_ARITHMETIC_CONTRACTED;
   ConstantBank& bank =
       contracted ? ContractedConstantBank() : FlowConstantBank();
-  // Variant 0 is "no hot body".
+  // Variant 0 is "no hot body, no warm body".
   pb_status_t const status = bank.Acquire(
-      e->serial, hot + 1, [&]() -> pb_status_t {
+      e->serial, (hot + 1) + (kMaxConstantBodies + 1) * (warm + 1),
+      [&]() -> pb_status_t {
         static BodyScalars scalars;
         static HotBody hot_body;
         for (int b = 0; b < n_bodies; ++b) {
@@ -326,6 +346,25 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
         }
         std::memset(&hot_body, 0, sizeof(hot_body));
         hot_body.body = hot;
+        hot_body.warm_body = warm;
+        for (int k = 0; k < kHotSize; ++k) {
+          hot_body.normalization[k] = pb_legendre_normalization_factor[k];
+        }
+        if (warm >= 0) {
+          DeviceBody const& body = e->model.bodies[warm];
+          hot_body.warm_data = body;
+          hot_body.warm_n_damping = std::min(body.n_damping, kWarmDampings);
+          for (int d = 0; d < hot_body.warm_n_damping; ++d) {
+            hot_body.warm_degree_damping[d] =
+                e->model.dampings[body.damping_offset + d];
+          }
+          int const size =
+              std::min((body.degree + 1) * (body.degree + 2) / 2, kWarmSize);
+          for (int k = 0; k < size; ++k) {
+            hot_body.warm_cos[k] = e->model.cos[body.coefficient_offset + k];
+            hot_body.warm_sin[k] = e->model.sin[body.coefficient_offset + k];
+          }
+        }
         if (hot >= 0) {
           DeviceBody const& body = e->model.bodies[hot];
           int const size = (body.degree + 1) * (body.degree + 2) / 2;
@@ -333,9 +372,6 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
           for (int k = 0; k < size; ++k) {
             hot_body.cos[k] = e->model.cos[body.coefficient_offset + k];
             hot_body.sin[k] = e->model.sin[body.coefficient_offset + k];
-          }
-          for (int k = 0; k < kHotSize; ++k) {
-            hot_body.normalization[k] = pb_legendre_normalization_factor[k];
           }
           for (int d = 0; d < body.n_damping; ++d) {
             hot_body.degree_damping[d] =
@@ -923,6 +959,7 @@ struct FlowContext {
   ConstantBankLease constants;
   cudaStream_t stream = nullptr;
   int hot = -1;
+  int warm = -1;
   int32_t arithmetic = PB_ARITHMETIC_EXACT;
   // RETURN_IF_STOPPED: set when the flow stopped at a chunk boundary because
   // pb_ephemeris_request_stop was called.
@@ -962,7 +999,7 @@ struct FlowContext {
     }
     arithmetic = flow_arithmetic;
     return AcquireFlowConstants(e, t, n, state_device, probe_host, arithmetic,
-                                stream, constants, &hot);
+                                stream, constants, &hot, &warm);
   }
   bool contracted() const { return arithmetic == PB_ARITHMETIC_CONTRACTED; }
 
@@ -977,7 +1014,7 @@ struct FlowContext {
     }
     path_checked = true;
     FlowPathKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-        e->View(), stage, hot, n, state, w()->status_word.data + 1);
+        e->View(), stage, hot, warm, n, state, w()->status_word.data + 1);
     PB_LAUNCHED();
     return PB_OK;
   }
