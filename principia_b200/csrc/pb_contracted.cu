@@ -12,6 +12,7 @@
 #define pb pb_contracted
 #include "pb_kernels_massless.cuh"
 #include "pb_kernels_massless_multistep.cuh"
+#include "pb_kernels_massless_specialized.cuh"
 #undef pb
 
 #include "pb_contracted.h"
@@ -46,12 +47,39 @@ cudaError_t LaunchSrkn(SrknLaunch const& l) {
   auto const& view = *static_cast<k::EphemerisView const*>(l.view);
   auto const& tableau = *static_cast<k::SrknTableau const*>(l.tableau);
 #define PB_LAUNCH(kThreads, kMinBlocks)                                       \
+  {                                                                           \
+    cudaError_t const attribute =                                             \
+        k::SrknStageCacheAttribute<kThreads, kMinBlocks>();                   \
+    if (attribute != cudaSuccess) {                                           \
+      return attribute;                                                       \
+    }                                                                         \
+  }                                                                           \
   (l.burns != nullptr ? k::SrknFlowKernel<kThreads, kMinBlocks, true>         \
                       : k::SrknFlowKernel<kThreads, kMinBlocks, false>)       \
-      <<<l.grid, kThreads, 0, l.stream>>>(                                    \
+      <<<l.grid, kThreads,                                                    \
+         k::SrknStageCacheBytes(kThreads, view.stage_stride), l.stream>>>(    \
           view, tableau, l.h, l.stage_table, l.stage_times, l.burns,          \
           l.n_steps, l.n, l.i_begin, l.i_end, l.state, l.steps_before,        \
-          l.sample_every, l.max_samples, l.samples, l.status)
+          l.sample_every, l.max_samples, l.samples, l.status, l.skip_blocks)
+  if (l.specialized) {
+    static cudaError_t const attribute = cudaFuncSetAttribute(
+        k::SrknFlowSpecializedKernel<0>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize,
+        static_cast<int>(sizeof(k::SpecializedShared)));
+    if (attribute != cudaSuccess) {
+      return attribute;
+    }
+    k::SrknFlowSpecializedKernel<0>
+        <<<l.grid, k::kSpecializedThreads, sizeof(k::SpecializedShared),
+           l.stream>>>(view, tableau, l.h, l.stage_table, l.n_steps, l.n,
+                       l.i_begin, l.i_end, l.state, l.sample_every,
+                       l.sample_every > 0
+                           ? l.sample_every - l.steps_before % l.sample_every
+                           : 0,
+                       l.sample_every > 0 ? l.steps_before / l.sample_every : 0,
+                       l.max_samples, l.samples, l.status, l.block_done);
+    return cudaGetLastError();
+  }
   switch (l.threads) {
     case 256: PB_LAUNCH(256, 2); break;
     case 384: PB_LAUNCH(384, 1); break;

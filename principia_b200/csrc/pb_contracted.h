@@ -35,6 +35,11 @@ struct SrknLaunch {
   int threads;  // 256 (2 blocks per SM), 384 (1) or 128 (3).
   unsigned grid;
   cudaStream_t stream;
+  // SrknFlowSpecializedKernel (256 threads; writes block_done) instead of
+  // SrknFlowKernel (which skips the blocks of skip_blocks, if any).
+  bool specialized = false;
+  std::int32_t* block_done = nullptr;
+  std::int32_t const* skip_blocks = nullptr;
 };
 cudaError_t LaunchSrkn(SrknLaunch const& launch);
 

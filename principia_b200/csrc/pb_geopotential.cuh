@@ -699,6 +699,9 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
 #endif
       Vec3 sum =
           UnrolledTerm<n, size - 1>(g, sigma_R_over_r, grad_sigma_R, s, p, w);
+      // (Evaluating two to four orders in lock step, operation by operation,
+      // to interleave their dependency chains was measured 30 % slower at 128
+      // registers and 5 % slower at 192: the spills outweigh the latency.)
       StaticForRange<0, size - 1>([&](auto i_constant) {
         constexpr int m = size - 2 - decltype(i_constant)::value;
         sum = UnrolledTerm<n, m>(g, sigma_R_over_r, grad_sigma_R, s, p, w) + sum;

@@ -84,7 +84,8 @@ constexpr int32_t kPathGenericHarmonics = 0x100;
 //   [3 n_bodies, + 6 n_frames) surface-frame x and y axes of the bodies that
 //                              have a frame_slot.
 PB_HD int StageStride(int const n_bodies, int const n_frames) {
-  return 3 * n_bodies + 6 * n_frames;
+  // Even: the entries are copied 16 bytes at a time (SrknFlowKernel).
+  return (3 * n_bodies + 6 * n_frames + 1) / 2 * 2;
 }
 
 // Tableau of a symplectic Runge-Kutta-Nyström method, integrators/methods.hpp.

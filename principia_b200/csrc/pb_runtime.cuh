@@ -261,6 +261,8 @@ struct FlowWorkspace {
   // [0]: OR of the right-hand-side status codes; [1]: path flags
   // (kPathGenericHarmonics).
   DeviceBuffer<int32_t> status_word;
+  // Per launch of SrknFlowSpecializedKernel, per block: completed there.
+  DeviceBuffer<int32_t> block_done;
   DeviceBuffer<long long> counters;
   DeviceBuffer<int32_t> frenet_scratch;
   PinnedBuffer<double> pinned_times;

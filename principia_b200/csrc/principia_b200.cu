@@ -19,6 +19,7 @@
 #include "pb_contracted.h"
 #include "pb_kernels_massless.cuh"
 #include "pb_kernels_massless_multistep.cuh"
+#include "pb_kernels_massless_specialized.cuh"
 #include "pb_runtime.cuh"
 
 using namespace pb;
@@ -378,6 +379,7 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
                 e->model.dampings[body.damping_offset + d];
           }
           hot_body.sectoral = body.sectoral;
+          hot_body.hot_data = body;
         }
         // No kernel reads the bank now (ConstantBank::Acquire).
         if (contracted) {
@@ -447,11 +449,35 @@ int SrknMinBlocks() {
   return value;
 }
 
+// The warp-specialised kernel ahead of the general one
+// (pb_kernels_massless_specialized.cuh): opt-in with PB_SRKN_SPECIALIZED=1; it
+// is bit-identical and measured slower (57.3 against 45.6 ms per 100 steps of
+// 10^5 probes, profiles/r02w_*).
+bool SrknSpecialized() {
+  static bool const value = [] {
+    char const* const text = std::getenv("PB_SRKN_SPECIALIZED");
+    return text != nullptr && std::atoi(text) != 0;
+  }();
+  return value;
+}
+
+// For a launch that starts after `steps_before` steps of a flow sampled every
+// `every` steps (sample k, k >= 1, is taken after step k * every and goes to
+// slot k - 1): the step of the launch, counted from 1, after which its first
+// sample is due, and the slot of that sample.
+long long FirstSampleStep(long long const steps_before, long long const every) {
+  return every > 0 ? every - steps_before % every : 0;
+}
+long long FirstSampleSlot(long long const steps_before, long long const every) {
+  return every > 0 ? steps_before / every : 0;
+}
+
 // Shape of the flow kernel: 0 = 128 threads x SrknMinBlocks() blocks per SM;
 // 3 = 384 threads x 1 block (168 registers, 12 warps per SM); 5 = 256 threads x
 // 2 blocks (128 registers, 16 warps per SM).  Measured on 10^5 probes: 56.2,
 // 50.7 and 48.4 ms per 100 steps (a block barrier per stage did not help; 18,
-// 20 and 24 warps per SM at 96 and 80 registers: 69, 66 and 74 ms), so a launch
+// 20 and 24 warps per SM at 96 and 80 registers: 69, 66 and 74 ms -- 18 warps
+// cannot have more than 96 registers, one scheduler holds 5 of them), so a launch
 // that fills every SM takes shape 5, a smaller one shape 3 or 0 (more, smaller
 // blocks).  PB_SRKN_VARIANT overrides the choice (tools/flow_variants.sh).
 int SrknVariant(long long const n_probes, int const sm_count) {
@@ -1157,6 +1183,11 @@ pb_status_t SrknSteps(FlowContext& c, const pb_fixed_step_flow_t* flow,
           std::min<long long>(FlowGroups(), std::max<long long>(1, blocks / 64)));
       int const sub_steps = groups > 1 ? FlowSubSteps() : steps;
       PB_RETURN_IF_ERROR(c.EnsureHelpers(groups));
+      // One entry per block of every launch of this chunk of steps (the same
+      // entries, on the same streams, serve the next chunk).
+      PB_RETURN_IF_ERROR(w->block_done.Reserve(static_cast<std::size_t>(
+          (blocks + groups) * ((steps + sub_steps - 1) / sub_steps))));
+      std::size_t done_offset = 0;
       cudaEvent_t const fork = w->timing_events[2 * c.phases];
       cudaEvent_t const join = w->timing_events[2 * c.phases + 1];
       PB_CUDA(cudaEventRecord(fork, stream));
@@ -1179,12 +1210,40 @@ pb_status_t SrknSteps(FlowContext& c, const pb_fixed_step_flow_t* flow,
           double const* const stage_times =
               w->stage_times.data + static_cast<std::size_t>(s0) * evaluations;
 #define PB_LAUNCH_SRKN(kThreads, kMinBlocks)                                  \
+  PB_CUDA((SrknStageCacheAttribute<kThreads, kMinBlocks>()));                 \
   (flow->burns != nullptr ? SrknFlowKernel<kThreads, kMinBlocks, true>        \
                           : SrknFlowKernel<kThreads, kMinBlocks, false>)      \
-      <<<grid, kThreads, 0, helper>>>(                                        \
+      <<<grid, kThreads, SrknStageCacheBytes(kThreads, view.stage_stride),    \
+         helper>>>(                                                           \
           view, tableau, h, table, stage_times, flow->burns, n_sub, flow->n,  \
           i_begin, i_end, flow->state, steps_done + s0, every,                \
-          flow->max_samples, flow->samples, w->status_word.data)
+          flow->max_samples, flow->samples, w->status_word.data, skip)
+          // The warp-specialised kernel first (pb_kernels_massless_specialized
+          // .cuh); the general one then flows the blocks it gave up on.
+          bool const specialized = variant == 5 && flow->burns == nullptr &&
+                                   c.hot >= 0 && SrknSpecialized();
+          int32_t* skip = nullptr;
+          if (specialized) {
+            skip = w->block_done.data + done_offset;
+            done_offset += grid;
+          }
+          if (specialized && !c.contracted()) {
+            static cudaError_t const attribute = cudaFuncSetAttribute(
+                SrknFlowSpecializedKernel<0>,
+                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                static_cast<int>(sizeof(SpecializedShared)));
+            PB_CUDA(attribute);
+            SrknFlowSpecializedKernel<0>
+                <<<grid, kSpecializedThreads, sizeof(SpecializedShared),
+                   helper>>>(view, tableau, h, table, n_sub, flow->n, i_begin,
+                             i_end, flow->state, every,
+                             FirstSampleStep(steps_done + s0, every),
+                             FirstSampleSlot(steps_done + s0, every),
+                             flow->max_samples, flow->samples,
+                             w->status_word.data, skip);
+            PB_LAUNCHED();
+            ++c.launches;
+          }
           if (c.contracted()) {
             pb_contracted_api::SrknLaunch launch;
             launch.view = &view;
@@ -1206,6 +1265,15 @@ pb_status_t SrknSteps(FlowContext& c, const pb_fixed_step_flow_t* flow,
             launch.threads = threads;
             launch.grid = grid;
             launch.stream = helper;
+            if (specialized) {
+              launch.specialized = true;
+              launch.block_done = skip;
+              PB_CUDA(pb_contracted_api::LaunchSrkn(launch));
+              PB_LAUNCHED();
+              ++c.launches;
+              launch.specialized = false;
+              launch.skip_blocks = skip;
+            }
             PB_CUDA(pb_contracted_api::LaunchSrkn(launch));
           } else if (variant == 5) {
             PB_LAUNCH_SRKN(256, 2);

@@ -351,6 +351,60 @@ def test_full_size_flow_properties(sol_system, sol_oracle, sol_gpu):
   assert np.max(displacement) < 1e-2
 
 
+def mixed_batch(system, n):
+  """LEO probes with, scattered among them, probes in low lunar orbit (the
+  Moon's degree-30 field: neither the hot nor the warm body of the batch, whose
+  first probe is in LEO) and probes far from everything (no harmonics at
+  all)."""
+  state = leo(system, n)
+  moon = system.bodies[system.index('Moon')]
+  earth = system.bodies[system.index('Earth')]
+  lunar = workloads.leo_probes(n, moon['q'], moon['v'], moon['mu'], seed=7)
+  # Scale the LEO-sized orbits (6.6e6 .. 8e6 m) down to 1.8e6 .. 2.2e6 m.
+  k = 1.8e6 / 6.6e6
+  lunar_q = np.asarray(moon['q'])[:, None] + k * (
+      lunar[0:3] - np.asarray(moon['q'])[:, None])
+  lunar_v = np.asarray(moon['v'])[:, None] + (
+      lunar[6:9] - np.asarray(moon['v'])[:, None]) / math.sqrt(k)
+  far = workloads.eccentric_probes(n, earth['q'], earth['v'], earth['mu'],
+                                   seed=11)
+  special = np.zeros(n, dtype=int)
+  special[5::997] = 1   # Lunar.
+  special[11::1499] = 2  # Eccentric, up to 4e8 m from the Earth.
+  state[0:3, special == 1] = lunar_q[:, special == 1]
+  state[6:9, special == 1] = lunar_v[:, special == 1]
+  state[:, special == 2] = far[:, special == 2]
+  return state, special
+
+
+@pytest.mark.parametrize('method', [
+    _capi.BLANES_MOAN_2002_SRKN_14A,
+    _capi.QUINLAN_1999_ORDER_8A,
+])
+def test_mixed_batch_takes_every_path(sol_system, sol_oracle, sol_gpu, method):
+  """A batch whose probes need different evaluations of the right-hand side:
+  harmonics of the hot and warm bodies (LEO), of a body that is neither (low
+  lunar orbit: the body-by-body evaluation and the thread-local-memory
+  harmonics), none at all.  The kernels pick the path per probe (per block for
+  the warp-specialised one); the bits do not depend on it."""
+  n = 80000  # Enough for the widest kernel shape (512 probes per SM).
+  state0, special = mixed_batch(sol_system, n)
+  state = state0.copy()
+  time = np.zeros(2)
+  result = sol_gpu.flow_with_fixed_step(method, 10.0, 200.0, state, time)
+  assert result['n_steps'] == 20 and result['status'] == 0
+  assert sol_gpu.last_flow_path()[1]  # Some probe took the generic path.
+  subset = np.unique(np.concatenate(
+      [np.flatnonzero(special == 1)[:40], np.flatnonzero(special == 2)[:20],
+       np.r_[0:30, 40000:40030, n - 30:n]]))
+  expected_state = np.ascontiguousarray(state0[:, subset])
+  expected_time = np.zeros(2)
+  expected = sol_oracle.flow_with_fixed_step(method, 10.0, 200.0,
+                                             expected_state, expected_time)
+  assert expected['n_steps'] == 20
+  assert_bitwise_equal(state[:, subset], expected_state, 'mixed subset')
+
+
 def test_branch_free_sqrt_and_division_are_ieee():
   """FastSqrt / FastDivide (pb_math.cuh) against the IEEE operators on the
   device: 2e9 operand sets, no mismatch allowed."""
