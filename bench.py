@@ -56,27 +56,40 @@ def bench_config(probes):
 
 class ClockSampler:
   """SM clock and throttle reasons during the timed region
-  (B200_PROFILING.md), in-process NVML (pynvml).  An NVML query can hold a
-  driver lock for tens of milliseconds on some boxes (measured: 20 ms per
-  query, and `value` 2.6x low because every CUDA call of the step queued
-  behind it), so a query is only made where the host has nothing to issue: the
-  bench kicks the sampler when a step starts, the sampler waits for the step's
-  launches to be enqueued (5 ms) and queries once while the flow kernels of
-  that step run (48 ms) -- one sample per step, all inside the timed region.
-  nvidia-smi remains the fallback."""
+  (B200_PROFILING.md).  Two instruments:
+   * the SM clock of EVERY timed step is measured on the device
+     (pb_measure_sm_clock: one warp reads the cycle counter against the global
+     timer for 200 us while the flow kernels of the step run) -- no driver
+     query, no interference;
+   * the throttle reasons (and NVML's own clocks.sm) come from in-process NVML
+     (pynvml) queries: one while the last warm-up step runs, ONE while the first
+     timed step runs, one right after the timed region.  An NVML query can hold
+     a driver lock for tens of milliseconds on some boxes (measured: 3 ms
+     typically, 100 ms now and then, every CUDA call of the step queued behind
+     it), which is measurement overhead, not flow time: hence a single query
+     inside the region.
+  The bench kicks the sampler when a step starts; the sampler waits for the
+  step's launches to be enqueued (5 ms) and samples while the flow kernels of
+  that step run (45 ms).  nvidia-smi remains the fallback."""
 
   def __init__(self, index):
     self.index = index
-    self.samples = []  # (sm MHz, max MHz, reasons bitmask).
+    self.samples = []  # (sm MHz, max MHz, reasons bitmask), NVML.
+    self.device_mhz = []  # Device-measured SM clock, one per kicked step.
     self.thread = None
     self.stop_event = threading.Event()
     self.kick_event = threading.Event()
+    self.query_requested = False
+    self.timed_step = True
     self.sm_max = None
     self.process = None
     self.lines = []
 
-  def kick(self):
-    """A step starts now."""
+  def kick(self, query=False, timed=True):
+    """A step starts now; `query`: also query NVML during it; `timed`: the
+    step is inside the timed region (its device clock is reported)."""
+    self.query_requested = query
+    self.timed_step = timed
     self.kick_event.set()
 
   def _query(self, nvml, handle):
@@ -91,12 +104,22 @@ class ClockSampler:
       pass
 
   def _nvml_loop(self, nvml, handle):
+    from principia_b200.ephemeris import measure_sm_clock
     while not self.stop_event.is_set():
       if not self.kick_event.wait(0.2):
         continue
       self.kick_event.clear()
+      query = self.query_requested
+      timed = self.timed_step
       time.sleep(0.005)
-      self._query(nvml, handle)
+      try:
+        mhz = measure_sm_clock(self.index, 200.0)
+        if timed:
+          self.device_mhz.append(mhz)
+      except Exception:  # A measurement hiccup must not end the bench.
+        pass
+      if query:
+        self._query(nvml, handle)
 
   def start(self):
     try:
@@ -110,6 +133,7 @@ class ClockSampler:
           index = int(entries[self.index])
       handle = nvml.nvmlDeviceGetHandleByIndex(index)
       self.nvml = nvml
+      self.handle = handle
       self.sm_max = nvml.nvmlDeviceGetMaxClockInfo(handle, nvml.NVML_CLOCK_SM)
       self._query(nvml, handle)  # Fails here rather than in the thread.
       if not self.samples:
@@ -151,6 +175,7 @@ class ClockSampler:
       self.stop_event.set()
       self.thread.join(timeout=2)
       nvml = self.nvml
+      self._query(nvml, self.handle)  # Right after the timed region.
       bits = {
           'hw_slowdown': nvml.nvmlClocksEventReasonHwSlowdown,
           'hw_thermal_slowdown': nvml.nvmlClocksEventReasonHwThermalSlowdown,
@@ -164,10 +189,19 @@ class ClockSampler:
             reasons.add(name)
       sm = [s[0] for s in self.samples]
       sm_max = [s[1] for s in self.samples]
-      return {'sm_mhz': float(np.median(sm)) if sm else None,
+      device = self.device_mhz
+      return {'sm_mhz': float(np.median(device)) if device else (
+                  float(np.median(sm)) if sm else None),
+              'sm_min_mhz': float(np.min(device)) if device else None,
               'sm_max_mhz': max(sm_max) if sm_max else None,
-              'samples': len(sm), 'reasons': sorted(reasons),
-              'source': 'nvml'}
+              'samples': len(device), 'reasons': sorted(reasons),
+              'nvml_sm_mhz': float(np.median(sm)) if sm else None,
+              'nvml_samples': len(sm),
+              'source': 'SM clock of every timed step measured on the device '
+                        '(pb_measure_sm_clock); throttle reasons and '
+                        'nvml_sm_mhz from NVML during the last warm-up step, '
+                        'during the first timed step and right after the '
+                        'timed region'}
     if self.process is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
     time.sleep(0.25)
@@ -357,25 +391,21 @@ def run_native(args):
   # FP64 roofline denominator, measured on this device, before the timed runs.
   peak_flops, peak_ms = measure_fp64_peak(local_rank)
 
-  for k in range(args.warmup):
-    resident_step()
   sampler = ClockSampler(local_rank)
-  launches_before = kernel_launch_count()
   sampler.start()
+  for k in range(args.warmup):
+    if k == args.warmup - 1:
+      sampler.kick(query=True, timed=False)
+    resident_step()
+  launches_before = kernel_launch_count()
   barrier()
   start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
   kernel_ms = 0.0
   kernel_launches = 0
   start.record()
-  # A clock sample on about four of the timed steps (first, last, two between):
-  # an NVML query costs the step that hosts it ~3 ms of host-side
-  # serialisation on this pool (the flow call's own synchronisation queues
-  # behind the driver lock), which is measurement overhead, not flow time.
-  sampled_steps = {round(j * (args.steps - 1) / 3) for j in range(4)}
   for k in range(args.steps):
     flush.fill_(k & 0xff)  # Evict L2 between steps.
-    if k in sampled_steps:
-      sampler.kick()
+    sampler.kick(query=(k == 0))
     resident_step()
     # Device time (CUDA events on the launching stream) of the flow kernels of
     # this call: the call slices the batch into launches that overlap on

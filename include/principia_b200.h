@@ -667,6 +667,13 @@ pb_status_t pb_ephemeris_last_flow_path(const pb_ephemeris_t* ephemeris,
  * device (2 flop per FMA) and the kernel time through *ms. */
 pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,
                                  double* ms);
+/* The SM clock (MHz) of the device under its current load, measured ON the
+ * device: one warp reads the cycle counter against the nanosecond global timer
+ * for `microseconds`.  For benchmarks: the `clocks.sm` that nvidia-smi / NVML
+ * report (/opt/skills/guides/B200_PROFILING.md), without a driver query in
+ * the timed region.  Any thread; runs on a stream of its own. */
+pb_status_t pb_measure_sm_clock(int32_t cuda_device, double microseconds,
+                                double* mhz);
 /* Kernels launched by this library since load (all entry points). */
 int64_t pb_kernel_launch_count(void);
 

@@ -168,6 +168,43 @@ PB_HD void InitializeSetup(DeviceBody const& body, Vec3 const& x_hat,
   p.R1_over_r = body.reference_radius * one_over_r3;
 }
 
+#if defined(__CUDACC__)
+// InitializeSetup with the branch-free square root and divisions (the same
+// bits for operands in their range, pb_math.cuh): no slow-path branches in the
+// prologue of the hot evaluation.  Returns false -- and garbage -- when an
+// operand is out of range (a point on the polar axis: r_equatorial == 0); the
+// caller then evaluates with InitializeSetup.
+__device__ __forceinline__ bool InitializeSetupFast(
+    DeviceBody const& body, Vec3 const& x_hat, Vec3 const& y_hat,
+    Vec3 const& r, double const r_norm, double const r2,
+    double const one_over_r3, GeopotentialSetup& p) {
+  Vec3 const z_hat = body.polar_axis;
+  p.r_norm = r_norm;
+  p.r2 = r2;
+  double const x = Dot(r, x_hat);
+  double const y = Dot(r, y_hat);
+  double const z = Dot(r, z_hat);
+  double const x2_plus_y2 = x * x + y * y;
+  bool const in_range = InFastRange(x2_plus_y2) && InFastRange(r2);
+  double const r_equatorial = FastSqrt(in_range ? x2_plus_y2 : 1.0);
+  // r_equatorial > 0 here.
+  double const one_over_r_equatorial = FastDivide(1.0, r_equatorial);
+  double const cos_lambda = x * one_over_r_equatorial;
+  double const sin_lambda = y * one_over_r_equatorial;
+  double const one_over_r_norm = FastDivide(1.0, in_range ? r_norm : 1.0);
+  p.r_normalized = r * one_over_r_norm;
+  p.cos_beta = r_equatorial * one_over_r_norm;
+  p.sin_beta = z * one_over_r_norm;
+  p.cos_lambda = cos_lambda;
+  p.sin_lambda = sin_lambda;
+  p.grad_B_vector = (-p.sin_beta * cos_lambda) * x_hat -
+                    (p.sin_beta * sin_lambda) * y_hat + p.cos_beta * z_hat;
+  p.grad_L_vector = cos_lambda * y_hat - sin_lambda * x_hat;
+  p.R1_over_r = body.reference_radius * one_over_r3;
+  return in_range;
+}
+#endif
+
 // ===========================================================================
 // Generic path: run-time loops.
 
@@ -759,6 +796,12 @@ PB_HD Vec3 GeopotentialUnrolledDispatchWithScratch(Tables const& g,
                                                    int const max_degree,
                                                    GeopotentialSetup const& s,
                                                    Scratch& w) {
+  // The full degree first: it is the common case of a hot body, and every
+  // test of the chain below is a jump over tens of kB of unrolled code (an
+  // instruction-cache miss each).
+  if (max_degree >= kLimit) {
+    return GeopotentialUnrolledAcceleration<kLimit, kZonal>(g, s, w);
+  }
 #define PB_UNROLLED_CASE(d)                                           \
   if constexpr (kLimit > (d)) {                                       \
     if (max_degree == (d)) {                                          \

@@ -2242,4 +2242,43 @@ pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,
   return PB_OK;
 }
 
+pb_status_t pb_measure_sm_clock(int32_t cuda_device, double microseconds,
+                                double* mhz) {
+  if (mhz == nullptr || !(microseconds > 0) || microseconds > 1e5) {
+    return Fail(PB_INVALID_ARGUMENT, "pb_measure_sm_clock: bad arguments");
+  }
+  int device_count = 0;
+  if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count == 0) {
+    return Fail(PB_FAILED_PRECONDITION, "no CUDA device");
+  }
+  PB_CUDA(cudaSetDevice(cuda_device));
+  // A stream and a mapped result of its own per calling thread: nothing here
+  // waits on, or is waited on by, the flows in progress.
+  struct Probe {
+    cudaStream_t stream = nullptr;
+    double* result = nullptr;
+    int device = -1;
+  };
+  thread_local Probe probe;
+  if (probe.device != cuda_device) {
+    if (probe.stream != nullptr) {
+      cudaStreamDestroy(probe.stream);
+      cudaFreeHost(probe.result);
+      probe = Probe();
+    }
+    int least = 0, greatest = 0;
+    PB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    PB_CUDA(cudaStreamCreateWithPriority(&probe.stream, cudaStreamNonBlocking,
+                                         greatest));
+    PB_CUDA(cudaMallocHost(&probe.result, sizeof(double)));
+    probe.device = cuda_device;
+  }
+  SmClockKernel<<<1, 32, 0, probe.stream>>>(
+      static_cast<unsigned long long>(microseconds * 1e3), probe.result);
+  PB_LAUNCHED();
+  PB_CUDA(cudaStreamSynchronize(probe.stream));
+  *mhz = *probe.result;
+  return PB_OK;
+}
+
 }  // extern "C"

@@ -452,5 +452,13 @@ def measure_fp64_peak(device=0):
   return flops.value, ms.value
 
 
+def measure_sm_clock(device=0, microseconds=200.0):
+  """SM clock in MHz under the current load, measured on the device."""
+  mhz = ctypes.c_double()
+  _check(_capi.library().pb_measure_sm_clock(device, microseconds,
+                                             ctypes.byref(mhz)))
+  return mhz.value
+
+
 def kernel_launch_count():
   return _capi.library().pb_kernel_launch_count()
