@@ -62,12 +62,14 @@ class ClockSampler:
      timer for 200 us while the flow kernels of the step run) -- no driver
      query, no interference;
    * the throttle reasons (and NVML's own clocks.sm) come from in-process NVML
-     (pynvml) queries: one while the last warm-up step runs, ONE while the first
-     timed step runs, one right after the timed region.  An NVML query can hold
-     a driver lock for tens of milliseconds on some boxes (measured: 3 ms
-     typically, 100 ms now and then, every CUDA call of the step queued behind
-     it), which is measurement overhead, not flow time: hence a single query
-     inside the region.
+     (pynvml) queries that BRACKET the region under the same load: one while
+     the last warm-up step runs, one while an extra, untimed step runs right
+     after the timed region.  None inside it: an NVML query can hold a driver
+     lock for tens of milliseconds on some boxes (measured here: 3 ms
+     typically, 40-100 ms in one run out of six, every CUDA call of the step
+     queued behind it), which would be charged to `value` as if it were flow
+     time.  A throttle event inside the region would show in the per-step
+     device clocks (sm_min_mhz).
   The bench kicks the sampler when a step starts; the sampler waits for the
   step's launches to be enqueued (5 ms) and samples while the flow kernels of
   that step run (45 ms).  nvidia-smi remains the fallback."""
@@ -175,7 +177,6 @@ class ClockSampler:
       self.stop_event.set()
       self.thread.join(timeout=2)
       nvml = self.nvml
-      self._query(nvml, self.handle)  # Right after the timed region.
       bits = {
           'hw_slowdown': nvml.nvmlClocksEventReasonHwSlowdown,
           'hw_thermal_slowdown': nvml.nvmlClocksEventReasonHwThermalSlowdown,
@@ -199,9 +200,9 @@ class ClockSampler:
               'nvml_samples': len(sm),
               'source': 'SM clock of every timed step measured on the device '
                         '(pb_measure_sm_clock); throttle reasons and '
-                        'nvml_sm_mhz from NVML during the last warm-up step, '
-                        'during the first timed step and right after the '
-                        'timed region'}
+                        'nvml_sm_mhz from NVML queries that bracket the timed '
+                        'region under the same load (during the last warm-up '
+                        'step and during an untimed step right after it)'}
     if self.process is None:
       return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
     time.sleep(0.25)
@@ -405,7 +406,7 @@ def run_native(args):
   start.record()
   for k in range(args.steps):
     flush.fill_(k & 0xff)  # Evict L2 between steps.
-    sampler.kick(query=(k == 0))
+    sampler.kick()
     resident_step()
     # Device time (CUDA events on the launching stream) of the flow kernels of
     # this call: the call slices the batch into launches that overlap on
@@ -415,8 +416,11 @@ def run_native(args):
     kernel_launches += launches
   stop.record()
   barrier()
-  clocks = sampler.stop()
   launches_timed = kernel_launch_count() - launches_before
+  # The closing NVML sample, under the same load, outside the timed region.
+  sampler.kick(query=True, timed=False)
+  resident_step()
+  clocks = sampler.stop()
   elapsed_ms = torch.tensor([start.elapsed_time(stop)], device=device,
                             dtype=torch.float64)
   if world > 1:

@@ -10,6 +10,9 @@
 // position error <= 1e-12 after 10^4 steps, tests/test_gpu_contracted.py) and
 // execute ~30 % fewer FP64 instructions.  Opt-in, per call.
 #define pb pb_contracted
+// Selects the cheaper formulations that only the contracted arithmetic may
+// use (NormAndInverseCube, FlaggedScratch::Divide).
+#define PB_CONTRACTED_BUILD 1
 #include "pb_kernels_massless.cuh"
 #include "pb_kernels_massless_multistep.cuh"
 #include "pb_kernels_massless_specialized.cuh"

@@ -562,12 +562,18 @@ struct FlaggedScratch : LocalScratch<kMaxDegree> {
   __device__ __forceinline__ double Divide(double const x, int const n,
                                            double const reciprocal) {
     // exponent < 0x036 or exponent == 0x7ff <=> offset >= 0x7c900000.
+#if defined(PB_CONTRACTED_BUILD)
+    // Contracted arithmetic: the product with RN(1 / n), within one ulp of the
+    // quotient for any operand.
+    return x * reciprocal;
+#else
     flag = __viaddmax_u32(
         static_cast<unsigned>(__double2hiint(x)) & 0x7ff00000u,
         0u - 0x03600000u, flag);
     double const q0 = x * reciprocal;
     double const r = fma(-static_cast<double>(n), q0, x);
     return fma(r, reciprocal, q0);
+#endif
   }
   __device__ __forceinline__ bool Failed() const {
     return flag >= 0x7c900000u;
