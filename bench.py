@@ -21,6 +21,7 @@ by FLOW_STEPS integrator steps (14 right-hand-side evaluations each).
          instance per thread over a bounded sample of the same workload.
 """
 import argparse
+import gc
 import ctypes
 import json
 import os
@@ -58,9 +59,10 @@ class ClockSampler:
   """SM clock and throttle reasons during the timed region
   (B200_PROFILING.md).  Two instruments:
    * the SM clock of EVERY timed step is measured on the device
-     (pb_measure_sm_clock: one warp reads the cycle counter against the global
-     timer for 200 us while the flow kernels of the step run) -- no driver
-     query, no interference;
+     (pb_sm_clock_probe_start / _read: one warp reads the cycle counter against
+     the global timer for 1 ms, 8 ms into the step; enqueued by the bench's own
+     thread right before the step's launches) -- no driver query, no second
+     thread, no synchronisation inside the step;
    * the throttle reasons (and NVML's own clocks.sm) come from in-process NVML
      (pynvml) queries that BRACKET the region under the same load: one while
      the last warm-up step runs, one while an extra, untimed step runs right
@@ -70,9 +72,10 @@ class ClockSampler:
      queued behind it), which would be charged to `value` as if it were flow
      time.  A throttle event inside the region would show in the per-step
      device clocks (sm_min_mhz).
-  The bench kicks the sampler when a step starts; the sampler waits for the
-  step's launches to be enqueued (5 ms) and samples while the flow kernels of
-  that step run (45 ms).  nvidia-smi remains the fallback."""
+  For an NVML sample the bench kicks the sampler thread when the step starts;
+  the thread waits for the step's launches to be enqueued (5 ms) and queries
+  while the flow kernels of that step run (45 ms).  nvidia-smi remains the
+  fallback."""
 
   def __init__(self, index):
     self.index = index
@@ -82,17 +85,27 @@ class ClockSampler:
     self.stop_event = threading.Event()
     self.kick_event = threading.Event()
     self.query_requested = False
-    self.timed_step = True
     self.sm_max = None
     self.process = None
     self.lines = []
 
-  def kick(self, query=False, timed=True):
-    """A step starts now; `query`: also query NVML during it; `timed`: the
-    step is inside the timed region (its device clock is reported)."""
+  def kick(self, query=True):
+    """A step starts now: query NVML while it runs (sampler thread)."""
     self.query_requested = query
-    self.timed_step = timed
     self.kick_event.set()
+
+  def probe_start(self):
+    """A TIMED step starts now: enqueue, from this thread, the device-side
+    clock measurement: 1 ms of cycles against the global timer, starting 8 ms
+    from now -- in the middle of the flow kernels that the step launches right
+    after."""
+    from principia_b200.ephemeris import sm_clock_probe_start
+    sm_clock_probe_start(self.index, 8000.0, 1000.0)
+
+  def probe_read(self):
+    """The step is complete: collect the measurement (long finished)."""
+    from principia_b200.ephemeris import sm_clock_probe_read
+    self.device_mhz.append(sm_clock_probe_read(self.index))
 
   def _query(self, nvml, handle):
     try:
@@ -106,20 +119,12 @@ class ClockSampler:
       pass
 
   def _nvml_loop(self, nvml, handle):
-    from principia_b200.ephemeris import measure_sm_clock
     while not self.stop_event.is_set():
       if not self.kick_event.wait(0.2):
         continue
       self.kick_event.clear()
       query = self.query_requested
-      timed = self.timed_step
       time.sleep(0.005)
-      try:
-        mhz = measure_sm_clock(self.index, 200.0)
-        if timed:
-          self.device_mhz.append(mhz)
-      except Exception:  # A measurement hiccup must not end the bench.
-        pass
       if query:
         self._query(nvml, handle)
 
@@ -199,7 +204,8 @@ class ClockSampler:
               'nvml_sm_mhz': float(np.median(sm)) if sm else None,
               'nvml_samples': len(sm),
               'source': 'SM clock of every timed step measured on the device '
-                        '(pb_measure_sm_clock); throttle reasons and '
+                        'for 1 ms, 8 ms into the step (pb_sm_clock_probe_*); throttle '
+                        'reasons and '
                         'nvml_sm_mhz from NVML queries that bracket the timed '
                         'region under the same load (during the last warm-up '
                         'step and during an untimed step right after it)'}
@@ -352,6 +358,11 @@ def run_native(args):
   pinned = torch.from_numpy(state_host.copy()).pin_memory()
   pinned_np = pinned.numpy()
   flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+  # A stream of our own for the flush, the timing events and the resident
+  # flows: on the legacy default stream (torch's current stream at start-up)
+  # one run in four had steps of 60-100 ms around kernels of 44 ms -- that
+  # stream synchronises implicitly with every blocking stream of the process.
+  torch.cuda.set_stream(torch.cuda.Stream(device=device))
   stream = torch.cuda.current_stream().cuda_stream
 
   def barrier():
@@ -396,18 +407,31 @@ def run_native(args):
   sampler.start()
   for k in range(args.warmup):
     if k == args.warmup - 1:
-      sampler.kick(query=True, timed=False)
+      sampler.kick()
+    # (The flush belongs to the warm-up too: the first launch of torch's fill
+    # kernel loads its module, 8 ms with a warm file cache and up to 0.8 s on a
+    # fresh box, which used to land in the first timed step.)
+    flush.fill_(k & 0xff)
     resident_step()
   launches_before = kernel_launch_count()
   barrier()
   start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
   kernel_ms = 0.0
   kernel_launches = 0
+  # No cyclic garbage collection inside the timed regions: with torch loaded a
+  # full collection is a ~100 ms pause of the host thread, which showed up as
+  # one slow run in five.
+  gc.collect()
+  gc.disable()
+  step_wall_ms = []  # Host wall clock of each timed flow call (diagnostic).
   start.record()
   for k in range(args.steps):
     flush.fill_(k & 0xff)  # Evict L2 between steps.
-    sampler.kick()
+    sampler.probe_start()
+    t0 = time.perf_counter()
     resident_step()
+    step_wall_ms.append((time.perf_counter() - t0) * 1e3)
+    sampler.probe_read()
     # Device time (CUDA events on the launching stream) of the flow kernels of
     # this call: the call slices the batch into launches that overlap on
     # helper streams, so the figure is per call, not per launch.
@@ -418,7 +442,7 @@ def run_native(args):
   barrier()
   launches_timed = kernel_launch_count() - launches_before
   # The closing NVML sample, under the same load, outside the timed region.
-  sampler.kick(query=True, timed=False)
+  sampler.kick()
   resident_step()
   clocks = sampler.stop()
   elapsed_ms = torch.tensor([start.elapsed_time(stop)], device=device,
@@ -470,10 +494,13 @@ def run_native(args):
 
   sink_step(0)
   barrier()
+  sink_step_ms = []
   start.record()
   for k in range(1, sink_steps + 1):
     flush.fill_(k & 0xff)
-    sink_points = sink_step(k)
+    t0 = time.perf_counter()
+    sink_points = sink_step(k)  # Ends with a device-to-host read.
+    sink_step_ms.append((time.perf_counter() - t0) * 1e3)
   stop.record()
   barrier()
   sink_ms = torch.tensor([start.elapsed_time(stop)], device=device,
@@ -578,6 +605,10 @@ def run_native(args):
         'e2e_with_sink': {
             'value': sink_steps * stages_per_step / (sink_ms * 1e-3),
             'unit': UNIT, 'ms_per_step': sink_ms / sink_steps,
+            # Host wall clock of the individual steps on this rank (every
+            # step creates and destroys an integrator instance).
+            'ms_per_step_median': float(np.median(sink_step_ms)),
+            'ms_per_step_max': float(np.max(sink_step_ms)),
             'h2d_bytes_per_step': world * 12 * n * 8,
             'd2h_bytes_per_step': world * (12 * n * 8 + n * 8),
             'sink': 'every step of every probe appended to a device '
@@ -586,6 +617,7 @@ def run_native(args):
             'points_kept_per_probe':
                 sink_points / n if sink_points else None,
             'points_appended_per_probe': (sink_steps + 1) * FLOW_STEPS + 1},
+        'step_wall_ms': [round(x, 2) for x in step_wall_ms],
         'gpu_launches': int(launches_timed),
         'roofline': roofline,
         'roofline_contracted': roofline_contracted,

@@ -674,6 +674,15 @@ pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,
  * the timed region.  Any thread; runs on a stream of its own. */
 pb_status_t pb_measure_sm_clock(int32_t cuda_device, double microseconds,
                                 double* mhz);
+/* The same in two halves, for a caller that wants the measurement to overlap
+ * work it is about to launch from the same thread: _start enqueues the probe
+ * (it waits `delay_microseconds`, then measures over `microseconds`) and
+ * returns at once, _read waits for it and returns its figure.  One probe in
+ * flight per thread. */
+pb_status_t pb_sm_clock_probe_start(int32_t cuda_device,
+                                    double delay_microseconds,
+                                    double microseconds);
+pb_status_t pb_sm_clock_probe_read(int32_t cuda_device, double* mhz);
 /* Kernels launched by this library since load (all entry points). */
 int64_t pb_kernel_launch_count(void);
 

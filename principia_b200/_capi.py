@@ -225,6 +225,9 @@ SYMBOLS = [
     ('pb_ephemeris_clear_stop', _i32, [_vp]),
     ('pb_measure_fp64_peak', _i32, [_i32, c_double_p, c_double_p]),
     ('pb_measure_sm_clock', _i32, [_i32, ctypes.c_double, c_double_p]),
+    ('pb_sm_clock_probe_start', _i32,
+     [_i32, ctypes.c_double, ctypes.c_double]),
+    ('pb_sm_clock_probe_read', _i32, [_i32, c_double_p]),
     ('pb_kernel_launch_count', _i64, []),
 ]
 

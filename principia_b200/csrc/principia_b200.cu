@@ -2242,43 +2242,72 @@ pb_status_t pb_measure_fp64_peak(int32_t cuda_device, double* flops_per_second,
   return PB_OK;
 }
 
-pb_status_t pb_measure_sm_clock(int32_t cuda_device, double microseconds,
-                                double* mhz) {
-  if (mhz == nullptr || !(microseconds > 0) || microseconds > 1e5) {
-    return Fail(PB_INVALID_ARGUMENT, "pb_measure_sm_clock: bad arguments");
-  }
+namespace {
+// A stream and a mapped result of its own per calling thread: nothing here
+// waits on, or is waited on by, the flows in progress.
+struct SmClockProbe {
+  cudaStream_t stream = nullptr;
+  double* result = nullptr;
+  int device = -1;
+};
+pb_status_t AcquireSmClockProbe(int32_t const cuda_device,
+                                SmClockProbe*& out) {
   int device_count = 0;
   if (cudaGetDeviceCount(&device_count) != cudaSuccess || device_count == 0) {
     return Fail(PB_FAILED_PRECONDITION, "no CUDA device");
   }
   PB_CUDA(cudaSetDevice(cuda_device));
-  // A stream and a mapped result of its own per calling thread: nothing here
-  // waits on, or is waited on by, the flows in progress.
-  struct Probe {
-    cudaStream_t stream = nullptr;
-    double* result = nullptr;
-    int device = -1;
-  };
-  thread_local Probe probe;
+  thread_local SmClockProbe probe;
   if (probe.device != cuda_device) {
     if (probe.stream != nullptr) {
       cudaStreamDestroy(probe.stream);
       cudaFreeHost(probe.result);
-      probe = Probe();
+      probe = SmClockProbe();
     }
     int least = 0, greatest = 0;
     PB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     PB_CUDA(cudaStreamCreateWithPriority(&probe.stream, cudaStreamNonBlocking,
                                          greatest));
     PB_CUDA(cudaMallocHost(&probe.result, sizeof(double)));
+    *probe.result = 0.0;
     probe.device = cuda_device;
   }
-  SmClockKernel<<<1, 32, 0, probe.stream>>>(
-      static_cast<unsigned long long>(microseconds * 1e3), probe.result);
-  PB_LAUNCHED();
-  PB_CUDA(cudaStreamSynchronize(probe.stream));
-  *mhz = *probe.result;
+  out = &probe;
   return PB_OK;
+}
+}  // namespace
+
+pb_status_t pb_sm_clock_probe_start(int32_t cuda_device,
+                                    double delay_microseconds,
+                                    double microseconds) {
+  if (!(microseconds > 0) || microseconds > 1e5 ||
+      !(delay_microseconds >= 0) || delay_microseconds > 1e5) {
+    return Fail(PB_INVALID_ARGUMENT, "pb_sm_clock_probe_start: bad duration");
+  }
+  SmClockProbe* probe = nullptr;
+  PB_RETURN_IF_ERROR(AcquireSmClockProbe(cuda_device, probe));
+  SmClockKernel<<<1, 32, 0, probe->stream>>>(
+      static_cast<unsigned long long>(delay_microseconds * 1e3),
+      static_cast<unsigned long long>(microseconds * 1e3), probe->result);
+  PB_LAUNCHED();
+  return PB_OK;
+}
+
+pb_status_t pb_sm_clock_probe_read(int32_t cuda_device, double* mhz) {
+  if (mhz == nullptr) {
+    return Fail(PB_INVALID_ARGUMENT, "pb_sm_clock_probe_read: null result");
+  }
+  SmClockProbe* probe = nullptr;
+  PB_RETURN_IF_ERROR(AcquireSmClockProbe(cuda_device, probe));
+  PB_CUDA(cudaStreamSynchronize(probe->stream));
+  *mhz = *probe->result;
+  return PB_OK;
+}
+
+pb_status_t pb_measure_sm_clock(int32_t cuda_device, double microseconds,
+                                double* mhz) {
+  PB_RETURN_IF_ERROR(pb_sm_clock_probe_start(cuda_device, 0.0, microseconds));
+  return pb_sm_clock_probe_read(cuda_device, mhz);
 }
 
 }  // extern "C"

@@ -460,5 +460,20 @@ def measure_sm_clock(device=0, microseconds=200.0):
   return mhz.value
 
 
+def sm_clock_probe_start(device=0, delay_microseconds=5000.0,
+                         microseconds=1000.0):
+  """Enqueues a device-side SM clock measurement over `microseconds`, starting
+  `delay_microseconds` from now; returns at once."""
+  _check(_capi.library().pb_sm_clock_probe_start(device, delay_microseconds,
+                                                 microseconds))
+
+
+def sm_clock_probe_read(device=0):
+  """MHz measured by the probe started last on this thread."""
+  mhz = ctypes.c_double()
+  _check(_capi.library().pb_sm_clock_probe_read(device, ctypes.byref(mhz)))
+  return mhz.value
+
+
 def kernel_launch_count():
   return _capi.library().pb_kernel_launch_count()
