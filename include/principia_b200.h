@@ -656,10 +656,12 @@ double pb_ephemeris_last_flow_kernel_ms(const pb_ephemeris_t* ephemeris,
                                         int64_t* launches);
 /* Which code path the last fixed-step flow on this ephemeris took.  *hot_body:
  * the caller index of the oblate body whose harmonics were served from the
- * constant bank (-1: none) -- chosen from the first probe of the first flow
- * and kept; *generic_harmonics != 0: some probe evaluated harmonics of degree
- * > 3 of ANOTHER body (same bits, several times slower), in which case the
- * next flow chooses its hot body afresh. */
+ * constant bank (-1: none) -- the body whose harmonics of degree >= 3 the most
+ * probes of the first flow needed (every probe votes), kept for the later
+ * flows; a second, "warm" body (harmonics up to degree 3, e.g. the damped J2 of
+ * the Sun) is chosen the same way.  *generic_harmonics != 0: some probe
+ * evaluated harmonics that neither serves (same bits, several times slower),
+ * in which case the next flow chooses afresh. */
 pb_status_t pb_ephemeris_last_flow_path(const pb_ephemeris_t* ephemeris,
                                         int32_t* hot_body,
                                         int32_t* generic_harmonics);

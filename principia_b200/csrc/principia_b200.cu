@@ -216,21 +216,31 @@ void ComputeNodes(SrknTableau const& tableau, double* c) {
 }
 
 // The "hot" oblate body of the flow kernels -- the body of degree <=
-// kHotDegree with the highest limiting degree at the distance of `probe` (the
-// Earth for LEO probes); -1 if no harmonics above degree 2 are active there --
-// and the "warm" one: another body whose harmonics are active there, up to
-// degree kWarmDegree (the damped J2 of the Sun); -1 if none.  The choice only
-// affects speed: every path computes the same bits.
-void ChooseHotBodies(pb_ephemeris const* e, double const t,
-                     double const* const probe, int* const hot_out,
-                     int* const warm_out) {
-  int const n_oblate = e->model.n_oblate;
-  std::vector<int> max_degree(n_oblate, 1);
+// kHotDegree whose harmonics of degree >= 3 the most probes of the batch need
+// (the Earth for LEO probes); -1 if none -- and the "warm" one: another body
+// whose harmonics up to degree kWarmDegree the most probes need (the damped J2
+// of the Sun); -1 if none.  Every probe votes (HotBodyVoteKernel), so that an
+// unrepresentative first probe does not send the batch down the slow paths.
+// The choice only affects speed: every path computes the same bits.
+pb_status_t ChooseHotBodies(pb_ephemeris const* e, double const t,
+                            long long const n,
+                            double const* const state_device,
+                            cudaStream_t const stream, int* const hot_out,
+                            int* const warm_out) {
+  *hot_out = -1;
+  *warm_out = -1;
+  int const n_oblate = std::min(e->model.n_oblate, 32);
+  if (n_oblate == 0 || n <= 0) {
+    return PB_OK;
+  }
+  // Positions of the oblate bodies at t, from the host copy of the segments.
+  std::vector<double> positions(3 * n_oblate, 0.0);
   for (int b = 0; b < n_oblate; ++b) {
-    DeviceBody const& body = e->model.bodies[b];
     HostTrajectory const& tr = e->trajectories[b];
     if (tr.t_max.empty()) {
-      continue;
+      // No ephemeris yet for this body: nothing to choose (the flow itself
+      // will fail its own precondition).
+      return PB_OK;
     }
     std::size_t segment =
         std::lower_bound(tr.t_max.begin(), tr.t_max.end(), t) -
@@ -238,36 +248,49 @@ void ChooseHotBodies(pb_ephemeris const* e, double const t,
     segment = std::min(segment, tr.t_max.size() - 1);
     double const x = t - tr.origin[segment];
     double const* const c = &tr.coefficients[segment * 3 * kSegmentCoefficients];
-    double d2 = 0;
     for (int k = 0; k < 3; ++k) {
-      double const p = EstrinEvaluate<1>(c + k * kSegmentCoefficients,
-                                         tr.degree[segment], x);
-      d2 += (p - probe[k]) * (p - probe[k]);
+      positions[3 * b + k] = EstrinEvaluate<1>(c + k * kSegmentCoefficients,
+                                               tr.degree[segment], x);
     }
-    max_degree[b] = LimitingDegree(
-        e->model.dampings.data() + body.damping_offset, body.n_damping,
-        std::sqrt(d2)) - 1;
   }
-  int hot = -1;
-  int best_degree = 2;
+  DeviceBuffer<double> positions_device;
+  DeviceBuffer<int32_t> votes_device;
+  PB_RETURN_IF_ERROR(positions_device.Upload(positions, stream));
+  PB_RETURN_IF_ERROR(votes_device.Reserve(n_oblate * kVoteBins));
+  PB_CUDA(cudaMemsetAsync(votes_device.data, 0,
+                          n_oblate * kVoteBins * sizeof(int32_t), stream));
+  HotBodyVoteKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+      e->View(), positions_device.data, n, state_device, votes_device.data);
+  PB_LAUNCHED();
+  std::vector<int32_t> votes(n_oblate * kVoteBins);
+  PB_CUDA(cudaMemcpyAsync(votes.data(), votes_device.data,
+                          votes.size() * sizeof(int32_t),
+                          cudaMemcpyDeviceToHost, stream));
+  PB_CUDA(cudaStreamSynchronize(stream));
+  auto const count = [&](int const b, int const first, int const last) {
+    long long total = 0;
+    for (int d = first; d <= last; ++d) {
+      total += votes[b * kVoteBins + d];
+    }
+    return total;
+  };
+  long long best = 0;
   for (int b = 0; b < n_oblate; ++b) {
-    if (e->model.bodies[b].degree <= kHotDegree &&
-        max_degree[b] > best_degree) {
-      best_degree = max_degree[b];
-      hot = b;
+    long long const deep = count(b, 3, kVoteBins - 1);
+    if (e->model.bodies[b].degree <= kHotDegree && deep > best) {
+      best = deep;
+      *hot_out = b;
     }
   }
-  int warm = -1;
-  best_degree = 1;
+  best = 0;
   for (int b = 0; b < n_oblate; ++b) {
-    if (b != hot && max_degree[b] <= kWarmDegree &&
-        max_degree[b] > best_degree) {
-      best_degree = max_degree[b];
-      warm = b;
+    long long const shallow = count(b, 2, kWarmDegree);
+    if (b != *hot_out && shallow > best) {
+      best = shallow;
+      *warm_out = b;
     }
   }
-  *hot_out = hot;
-  *warm_out = warm;
+  return PB_OK;
 }
 
 // The constant bank of this translation unit's flow kernels (c_bodies, c_hot),
@@ -282,11 +305,10 @@ ConstantBank& ContractedConstantBank() {
 }
 
 // Makes the constant bank hold the per-body scalars of `e` and the tables of
-// its hot body, choosing the hot body if it has not been chosen yet (or if the
-// previous flow reported that the choice was poor).  `probe_host` is the
-// position of the first probe if the caller has it on the host, else it is
-// read from `state_device` (a synchronisation, once per choice).  The lease
-// must outlive every kernel launched under it.
+// its hot and warm bodies, choosing them if they have not been chosen yet (or
+// if the previous flow reported that the choice was poor) by a vote of the
+// probes in `state_device` (a small kernel and a synchronisation, once per
+// choice).  The lease must outlive every kernel launched under it.
 pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
                                  long long const n,
                                  double const* const state_device,
@@ -304,22 +326,8 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
   {
     std::lock_guard<std::mutex> const lock(e->hot_mutex);
     if (!e->hot_body_valid) {
-      double probe[3] = {0.0, 0.0, 0.0};
-      if (n > 0) {
-        if (probe_host != nullptr) {
-          for (int c = 0; c < 3; ++c) {
-            probe[c] = probe_host[c * n];
-          }
-        } else {
-          for (int c = 0; c < 3; ++c) {
-            PB_CUDA(cudaMemcpyAsync(&probe[c], state_device + c * n,
-                                    sizeof(double), cudaMemcpyDeviceToHost,
-                                    stream));
-          }
-          PB_CUDA(cudaStreamSynchronize(stream));
-        }
-      }
-      ChooseHotBodies(e, t, probe, &e->hot_body, &e->warm_body);
+      PB_RETURN_IF_ERROR(ChooseHotBodies(e, t, n, state_device, stream,
+                                         &e->hot_body, &e->warm_body));
       e->hot_body_valid = n > 0;
     }
     hot = e->hot_body;

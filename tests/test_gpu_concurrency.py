@@ -324,8 +324,25 @@ def test_argument_validation_of_the_flows(sol_system, sol_gpu):
   assert info.value.code == _capi.PB_INVALID_ARGUMENT
 
 
+def test_hot_body_is_chosen_by_all_the_probes(sol_system):
+  """The probes of a batch vote for the hot and warm bodies: a first probe
+  that is nowhere near the others does not send the batch down the generic
+  path."""
+  gpu = Ephemeris(sol_system)
+  workloads.upload_sol_ephemeris(gpu)
+  earth = sol_system.bodies[sol_system.index('Earth')]
+  state = leo(sol_system, 4096, 23)
+  far = workloads.eccentric_probes(64, earth['q'], earth['v'], earth['mu'], 5)
+  distance = np.linalg.norm(far[0:3] - np.array(earth['q'])[:, None], axis=0)
+  state[:, 0] = far[:, int(np.argmax(distance))]
+  assert distance.max() > 1.0e8  # Beyond every harmonic of the Earth but J2.
+  gpu.flow_with_fixed_step(SRKN, 10.0, 100.0, state, np.zeros(2))
+  assert gpu.last_flow_path() == (sol_system.index('Earth'), False)
+  gpu.close()
+
+
 def test_hot_body_choice_is_reported_and_revised(sol_system):
-  """The hot body is chosen from the first probe of the first flow and kept;
+  """The hot body is chosen by the probes of the first flow and kept;
   a later batch around another body takes the generic harmonics, which the
   flow reports, and the next flow chooses afresh.  Same bits either way."""
   gpu = Ephemeris(sol_system)
