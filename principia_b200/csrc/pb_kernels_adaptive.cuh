@@ -133,7 +133,9 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
     }
   }
   auto const position_of = [&](int const b1) {
-    int const begin = __ldg(e.segment_offset + b1);
+    // The segments of body b1 start at b1 * segment_capacity: no load between
+    // the hint and the addresses of the coefficients.
+    int const begin = b1 * e.segment_capacity;
     int segment = begin + hint;
     if (!uniform) {
       int const end = __ldg(e.segment_end + b1);
@@ -143,6 +145,9 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
         hint = segment - begin;
       }
     }
+    // (Prefetching the next body's coefficients into the L1 while this one is
+    // evaluated changed nothing: the wait at the first use is the issue of the
+    // 27 loads plus an L1 hit, not a miss.)
     return EvaluateSegmentPadded(e, segment, t);
   };
   // kTwoPhase: the polynomials of all the bodies first, in a loop of their own

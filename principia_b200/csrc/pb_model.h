@@ -54,6 +54,8 @@ struct EphemerisView {
   int32_t stage_stride;  // Doubles per time in a stage table.
   // 1 if all bodies have the same segment boundaries (t_max arrays).
   int32_t uniform_segments;
+  // Body b's segments start at b * segment_capacity (== segment_offset[b]).
+  int32_t segment_capacity;
   DeviceBody const* bodies;
   Damping const* dampings;
   double const* cos;  // Normalised, (n, m) -> n(n+1)/2 + m per body.
