@@ -643,6 +643,13 @@ def main():
   parser.add_argument('--allpairs-bodies', type=int, default=2**20)
   parser.add_argument('--allpairs-flow-bodies', type=int, default=2**17)
   args = parser.parse_args()
+  # The timing rules ask for at least three warm-up steps (module loads, the
+  # choice of the hot bodies, clocks): fewer are not accepted silently.
+  if args.impl == 'native' and args.warmup < 3:
+    print('bench.py: --warmup %d raised to 3' % args.warmup, file=sys.stderr)
+    args.warmup = 3
+  if args.steps < 1:
+    raise SystemExit('bench.py: --steps must be at least 1')
   if args.impl == 'reference':
     run_reference(args)
   else:
