@@ -25,6 +25,28 @@ def earth_state(system, oracle, t=0.0):
   raise NotImplementedError
 
 
+def test_sm_clock_measured_on_the_device():
+  """pb_measure_sm_clock and its two halves (what bench.py reports as
+  clocks.sm_mhz): a plausible clock, no larger than the maximum NVML states
+  plus the granularity of the global timer."""
+  from principia_b200.ephemeris import (measure_sm_clock,
+                                        sm_clock_probe_read,
+                                        sm_clock_probe_start)
+  mhz = measure_sm_clock(0, 500.0)
+  assert 200.0 < mhz < 3000.0
+  sm_clock_probe_start(0, 100.0, 500.0)
+  again = sm_clock_probe_read(0)
+  assert 200.0 < again < 3000.0
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    handle = pynvml.nvmlDeviceGetHandleByIndex(0)
+    maximum = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+    assert mhz <= maximum * 1.01 and again <= maximum * 1.01
+  except ImportError:
+    pass
+
+
 def test_elementary_functions_on_device():
   lib = _capi.library()
   orc = oracle_lib.library()
