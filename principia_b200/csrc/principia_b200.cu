@@ -391,6 +391,16 @@ pb_status_t AcquireFlowConstants(pb_ephemeris* e, double const t,
         }
         // No kernel reads the bank now (ConstantBank::Acquire).
         if (contracted) {
+          // The contracted kernels read the normalisation factor as 1 (see
+          // HotTables): fold it into the coefficients here.
+          for (int k = 0; k < kHotSize; ++k) {
+            hot_body.cos[k] *= hot_body.normalization[k];
+            hot_body.sin[k] *= hot_body.normalization[k];
+          }
+          for (int k = 0; k < kWarmSize; ++k) {
+            hot_body.warm_cos[k] *= hot_body.normalization[k];
+            hot_body.warm_sin[k] *= hot_body.normalization[k];
+          }
           PB_CUDA(pb_contracted_api::UploadConstants(
               &scalars, sizeof(scalars), &hot_body, sizeof(hot_body), stream));
           return PB_OK;
