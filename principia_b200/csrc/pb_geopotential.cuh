@@ -186,12 +186,28 @@ __device__ __forceinline__ bool InitializeSetupFast(
   double const z = Dot(r, z_hat);
   double const x2_plus_y2 = x * x + y * y;
   bool const in_range = InFastRange(x2_plus_y2) && InFastRange(r2);
+#if defined(PB_CONTRACTED_BUILD)
+  // Contracted arithmetic: one reciprocal square root (hardware seed and a
+  // third-order correction, ~1e-16) gives r_equatorial and its inverse;
+  // 1 / r = r^2 / r^3.
+  double const safe = in_range ? x2_plus_y2 : 1.0;
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(safe));
+  double const residual = fma(safe, -(y0 * y0), 1.0);
+  double const one_over_r_equatorial =
+      fma(fma(residual, 0.375, 0.5), y0 * residual, y0);
+  double const r_equatorial = safe * one_over_r_equatorial;
+  double const cos_lambda = x * one_over_r_equatorial;
+  double const sin_lambda = y * one_over_r_equatorial;
+  double const one_over_r_norm = r2 * one_over_r3;
+#else
   double const r_equatorial = FastSqrt(in_range ? x2_plus_y2 : 1.0);
   // r_equatorial > 0 here.
   double const one_over_r_equatorial = FastDivide(1.0, r_equatorial);
   double const cos_lambda = x * one_over_r_equatorial;
   double const sin_lambda = y * one_over_r_equatorial;
   double const one_over_r_norm = FastDivide(1.0, in_range ? r_norm : 1.0);
+#endif
   p.r_normalized = r * one_over_r_norm;
   p.cos_beta = r_equatorial * one_over_r_norm;
   p.sin_beta = z * one_over_r_norm;
