@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/principia_b200.h"
+#include "generated_tables.h"
 #include "pb_kernels_nbody.cuh"
 #include "pb_runtime.cuh"
 
@@ -88,6 +89,14 @@ struct pb_nbody_ensemble {
   // next step expects to use.  Any other use of `frames` empties the cache.
   std::vector<double> frame_cache_times;
   std::size_t frame_cache_next = 0;
+  // True while a Solve of this ensemble holds the constant bank with the
+  // tables of its bodies (c_ensemble).
+  bool constant_tables = false;
+  EphemerisView View() const {
+    EphemerisView view = ephemeris->View();
+    view.ensemble_tables = constant_tables ? 1 : 0;
+    return view;
+  }
   MultistepHistory History() {
     return {displacement_value.data, displacement_error.data,
             acceleration.data};
@@ -141,6 +150,10 @@ pb_status_t BuildFrames(pb_nbody_ensemble* s, std::vector<double> const& times,
 // One SRKN step of size h from the current time; updates the time.
 pb_status_t SrknStep(pb_nbody_ensemble* s, double const h,
                      cudaStream_t stream) {
+  // (Without the constant-bank tables: the 14 evaluations of a launch find the
+  // body records in the L1 after the first one, and the tables were measured
+  // 48 % slower here -- while they gain 14 % on the one evaluation per launch
+  // of the multistep step.)
   EphemerisView const view = s->ephemeris->View();
   std::vector<double> times;
   for (int st = s->tableau.first_stage; st < s->tableau.stages; ++st) {
@@ -162,7 +175,7 @@ pb_status_t SrknStep(pb_nbody_ensemble* s, double const h,
 // FillStepFromState into ring slot `slot`.
 pb_status_t FillStep(pb_nbody_ensemble* s, int const slot,
                      cudaStream_t stream) {
-  EphemerisView const view = s->ephemeris->View();
+  EphemerisView const view = s->View();
   PB_RETURN_IF_ERROR(BuildFrames(s, {s->time.value}, stream));
   EnsembleLaunch const launch = MakeEnsembleLaunch(s);
   auto const kernel = launch.own == 4       ? EnsembleFillStepKernel<4, 512>
@@ -176,7 +189,7 @@ pb_status_t FillStep(pb_nbody_ensemble* s, int const slot,
 }
 
 pb_status_t MultistepStep(pb_nbody_ensemble* s, cudaStream_t stream) {
-  EphemerisView const view = s->ephemeris->View();
+  EphemerisView const view = s->View();
   DP t = s->time;
   Increment(t, s->step);
   // The frames at the times of this step and of the 63 that follow it (the
@@ -331,11 +344,78 @@ static pb_status_t RecordStep(pb_nbody_ensemble* s, EnsembleRecorder* recorder,
 
 // Integrator::Instance::Solve(t_final); with a recorder, returns as soon as
 // the recorder is full (call again to continue).
+// The constant bank of the ensemble kernels (c_ensemble): the bodies of one
+// ephemeris at a time, shared by the Solves that need the same ones.
+static ConstantBank& EnsembleConstantBank() {
+  static ConstantBank bank;
+  return bank;
+}
+
+// Resets pb_nbody_ensemble::constant_tables on scope exit.
+struct ConstantTablesScope {
+  pb_nbody_ensemble* ensemble;
+  ~ConstantTablesScope() { ensemble->constant_tables = false; }
+};
+
+static pb_status_t AcquireEnsembleConstants(pb_nbody_ensemble* s,
+                                            cudaStream_t const stream,
+                                            ConstantBankLease& lease) {
+  pb_ephemeris const* const e = s->ephemeris;
+  int const n = static_cast<int>(e->model.bodies.size());
+  if (n > kEnsembleTableBodies) {
+    return PB_OK;  // The pointer path.
+  }
+  ConstantBank& bank = EnsembleConstantBank();
+  pb_status_t const status =
+      bank.Acquire(e->serial, 1, [&]() -> pb_status_t {
+        static EnsembleConstants constants;
+        std::memset(&constants, 0, sizeof(constants));
+        for (int k = 0; k < kEnsembleTableSize; ++k) {
+          constants.normalization[k] = pb_legendre_normalization_factor[k];
+        }
+        for (int b = 0; b < n; ++b) {
+          DeviceBody const& body = e->model.bodies[b];
+          EnsembleBodyTables& tables = constants.bodies[b];
+          tables.data = body;
+          if (!body.is_oblate) {
+            continue;
+          }
+          tables.n_damping = std::min(body.n_damping, kEnsembleTableDampings);
+          for (int d = 0; d < tables.n_damping; ++d) {
+            tables.degree_damping[d] =
+                e->model.dampings[body.damping_offset + d];
+          }
+          int const size = std::min((body.degree + 1) * (body.degree + 2) / 2,
+                                    kEnsembleTableSize);
+          for (int k = 0; k < size; ++k) {
+            tables.cos[k] = e->model.cos[body.coefficient_offset + k];
+            tables.sin[k] = e->model.sin[body.coefficient_offset + k];
+          }
+        }
+        // No kernel reads the bank now (ConstantBank::Acquire).
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_ensemble, &constants,
+                                        sizeof(constants), 0,
+                                        cudaMemcpyHostToDevice, stream));
+        PB_CUDA(cudaStreamSynchronize(stream));
+        return PB_OK;
+      });
+  if (status == PB_OK) {
+    lease.Adopt(&bank);
+    s->constant_tables = true;
+  }
+  return status;
+}
+
 static pb_status_t SolveEnsemble(pb_nbody_ensemble* s, double t_final,
                                  int64_t* n_steps,
                                  EnsembleRecorder* recorder) {
   PB_CUDA(cudaSetDevice(s->device));
   cudaStream_t const stream = s->stream;
+  // Every return below follows a synchronisation of the stream: the lease
+  // outlives the kernels launched under it.
+  ConstantBankLease constants;
+  ConstantTablesScope const scope{s};
+  PB_RETURN_IF_ERROR(AcquireEnsembleConstants(s, stream, constants));
   int64_t steps = 0;
   double const h = s->step;
   // A full recorder, or a stop request (RETURN_IF_STOPPED after every step,

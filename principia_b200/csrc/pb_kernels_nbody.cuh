@@ -52,6 +52,104 @@ inline EnsembleShape MakeEnsembleShape(int const n_bodies,
   return shape;
 }
 
+// The bodies of a small system (TRAPPIST-1: 8) in the constant bank: the body
+// records and, for the oblate ones, what their harmonics up to degree
+// kEnsembleTableDegree need (the damped J2 of every pair of an ensemble member
+// is evaluated through these).  Through the pointers of the EphemerisView every
+// pair costs a chain of dependent global loads -- the body record, the
+// threshold search, the coefficients -- that the arithmetic does not hide.
+constexpr int kEnsembleTableBodies = 16;
+constexpr int kEnsembleTableDegree = 3;
+constexpr int kEnsembleTableSize =
+    (kEnsembleTableDegree + 1) * (kEnsembleTableDegree + 2) / 2;
+// The thresholds up to degree kEnsembleTableDegree + 1 tell whether the
+// degree exceeds kEnsembleTableDegree.
+constexpr int kEnsembleTableDampings = kEnsembleTableDegree + 2;
+
+struct EnsembleBodyTables {
+  DeviceBody data;
+  Damping degree_damping[kEnsembleTableDampings];
+  int32_t n_damping;  // min(n_damping, kEnsembleTableDampings).
+  int32_t pad;
+  double cos[kEnsembleTableSize];
+  double sin[kEnsembleTableSize];
+};
+
+struct EnsembleConstants {
+  double normalization[kEnsembleTableSize];
+  EnsembleBodyTables bodies[kEnsembleTableBodies];
+};
+
+static __constant__ EnsembleConstants c_ensemble;
+
+struct EnsembleTables {
+  int b;
+  __device__ __forceinline__ double Cos(int const k) const {
+    return c_ensemble.bodies[b].cos[k];
+  }
+  __device__ __forceinline__ double Sin(int const k) const {
+    return c_ensemble.bodies[b].sin[k];
+  }
+  __device__ __forceinline__ double Normalization(int const k) const {
+    return c_ensemble.normalization[k];
+  }
+  __device__ __forceinline__ Damping const& DegreeDamping(int const n) const {
+    return c_ensemble.bodies[b].degree_damping[n];
+  }
+  __device__ __forceinline__ Damping const& SectoralDamping() const {
+    return c_ensemble.bodies[b].data.sectoral;
+  }
+};
+
+// GeneralSphericalHarmonicsAcceleration<true, 3> of body `source` with the
+// operands of the constant bank: the same operations, hence the same bits.
+__device__ __forceinline__ Vec3 EnsembleHarmonics(
+    EphemerisView const& e, int const source, double const* const frames,
+    Vec3 const& r, double const r_norm, double const r2,
+    double const one_over_r3) {
+  EnsembleBodyTables const& tables = c_ensemble.bodies[source];
+  if (r_norm == r_norm) {
+    // LimitingDegree over the first thresholds is min(LimitingDegree,
+    // kEnsembleTableDampings): exact whenever it says degree <= 3.
+    int const max_degree =
+        LimitingDegree(tables.degree_damping, tables.n_damping, r_norm) - 1;
+    if (max_degree <= kEnsembleTableDegree) {
+      if (max_degree == 1) {
+        return {0.0, 0.0, 0.0};
+      }
+      DeviceBody const& body = tables.data;
+      bool const is_zonal =
+          body.is_zonal || r_norm > body.sectoral.outer_threshold;
+      Vec3 x_hat, y_hat;
+      if (is_zonal) {
+        x_hat = body.equatorial;
+        y_hat = body.biequatorial;
+      } else {
+        double const* const axes = frames + 6 * body.frame_slot;
+        x_hat = {axes[0], axes[1], axes[2]};
+        y_hat = {axes[3], axes[4], axes[5]};
+      }
+      GeopotentialSetup s;
+      InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
+      EnsembleTables const g{source};
+      return is_zonal
+                 ? GeopotentialUnrolledDispatch<true, EnsembleTables,
+                                                kEnsembleTableDegree>(
+                       g, max_degree, s)
+                 : GeopotentialUnrolledDispatch<false, EnsembleTables,
+                                                kEnsembleTableDegree>(
+                       g, max_degree, s);
+    }
+  }
+  // A NaN distance, or harmonics above degree 3: the pointer path.
+  DeviceBody const& body = e.bodies[source];
+  GeopotentialBody const g = MakeGeopotentialBody(e, source);
+  FrameSource const frame{
+      body.frame_slot >= 0 ? frames + 6 * body.frame_slot : nullptr, 0.0};
+  return GeneralSphericalHarmonicsAcceleration<true, 3>(g, frame, r, r_norm, r2,
+                                                        one_over_r3);
+}
+
 // Acceleration on body b of this lane's system.  A template so that every
 // kernel shape gets a copy compiled for its own register budget.
 template<int kMaxThreads>
@@ -59,7 +157,8 @@ static __device__ __noinline__ Vec3 AccelerationOnBodyOfSystem(
     EphemerisView const& e, double const* const frames,
     double const* const positions, int const b, int const lane) {
   int const n = e.n_bodies;
-  DeviceBody const& body_b = e.bodies[b];
+  bool const tables = e.ensemble_tables != 0;
+  DeviceBody const& body_b = tables ? c_ensemble.bodies[b].data : e.bodies[b];
   Vec3 const q_b{positions[(3 * b + 0) * kEnsembleLanes + lane],
                  positions[(3 * b + 1) * kEnsembleLanes + lane],
                  positions[(3 * b + 2) * kEnsembleLanes + lane]};
@@ -69,7 +168,8 @@ static __device__ __noinline__ Vec3 AccelerationOnBodyOfSystem(
     if (j == b) {
       continue;
     }
-    DeviceBody const& body_j = e.bodies[j];
+    DeviceBody const& body_j =
+        tables ? c_ensemble.bodies[j].data : e.bodies[j];
     Vec3 const q_j{positions[(3 * j + 0) * kEnsembleLanes + lane],
                    positions[(3 * j + 1) * kEnsembleLanes + lane],
                    positions[(3 * j + 2) * kEnsembleLanes + lane]};
@@ -98,14 +198,20 @@ static __device__ __noinline__ Vec3 AccelerationOnBodyOfSystem(
       if (!source_body.is_oblate) {
         continue;
       }
-      GeopotentialBody const g = MakeGeopotentialBody(e, source);
-      FrameSource const frame{source_body.frame_slot >= 0
-                                  ? frames + 6 * source_body.frame_slot
-                                  : nullptr,
-                              0.0};
       // b1's field at b2: r = -dq; b2's field at b1: r = dq.
-      Vec3 const effect = GeneralSphericalHarmonicsAcceleration<true, 3>(
-          g, frame, which == 0 ? -dq : dq, dq_norm, dq2, one_over_dq3);
+      Vec3 effect;
+      if (tables) {
+        effect = EnsembleHarmonics(e, source, frames, which == 0 ? -dq : dq,
+                                   dq_norm, dq2, one_over_dq3);
+      } else {
+        GeopotentialBody const g = MakeGeopotentialBody(e, source);
+        FrameSource const frame{source_body.frame_slot >= 0
+                                    ? frames + 6 * source_body.frame_slot
+                                    : nullptr,
+                                0.0};
+        effect = GeneralSphericalHarmonicsAcceleration<true, 3>(
+            g, frame, which == 0 ? -dq : dq, dq_norm, dq2, one_over_dq3);
+      }
       // b1 oblate: a1 -= mu2 effect, a2 += mu1 effect;
       // b2 oblate: a1 += mu2 effect, a2 -= mu1 effect.
       Vec3 const scaled = mu_j * effect;

@@ -56,6 +56,9 @@ struct EphemerisView {
   int32_t uniform_segments;
   // Body b's segments start at b * segment_capacity (== segment_offset[b]).
   int32_t segment_capacity;
+  // 1: the ensemble kernels may read the bodies from their constant bank
+  // (c_ensemble, pb_kernels_nbody.cuh): set by a caller that holds it.
+  int32_t ensemble_tables;
   DeviceBody const* bodies;
   Damping const* dampings;
   double const* cos;  // Normalised, (n, m) -> n(n+1)/2 + m per body.

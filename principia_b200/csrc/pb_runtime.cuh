@@ -439,6 +439,7 @@ struct pb_ephemeris {
     v.stage_stride = pb::StageStride(v.n_bodies, v.n_frames);
     v.uniform_segments = uniform_segments ? 1 : 0;
     v.segment_capacity = segment_capacity;
+    v.ensemble_tables = 0;
     v.bodies = bodies.data;
     v.dampings = dampings.data;
     v.cos = cos.data;
