@@ -8,7 +8,10 @@
 
 #include <cub/device/device_radix_sort.cuh>
 
+#include <cstring>
+
 #include "../../include/principia_b200.h"
+#include "generated_tables.h"
 #include "pb_kernels_adaptive.cuh"
 #include "pb_runtime.cuh"
 
@@ -84,6 +87,32 @@ pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
         }
         PB_CUDA(cudaMemcpyToSymbolAsync(c_adaptive_bodies, &scalars,
                                         sizeof(scalars), 0,
+                                        cudaMemcpyHostToDevice, stream));
+        // The oblate bodies' records and degree <= 3 harmonics.
+        static AdaptiveConstants tables;
+        std::memset(&tables, 0, sizeof(tables));
+        tables.n_tables = std::min(e->model.n_oblate, kAdaptiveTableBodies);
+        for (int k = 0; k < kAdaptiveTableSize; ++k) {
+          tables.normalization[k] = pb_legendre_normalization_factor[k];
+        }
+        for (int b = 0; b < tables.n_tables; ++b) {
+          DeviceBody const& body = e->model.bodies[b];
+          AdaptiveBodyTables& entry = tables.bodies[b];
+          entry.data = body;
+          entry.n_damping = std::min(body.n_damping, kAdaptiveTableDampings);
+          for (int d = 0; d < entry.n_damping; ++d) {
+            entry.degree_damping[d] =
+                e->model.dampings[body.damping_offset + d];
+          }
+          int const size = std::min((body.degree + 1) * (body.degree + 2) / 2,
+                                    kAdaptiveTableSize);
+          for (int k = 0; k < size; ++k) {
+            entry.cos[k] = e->model.cos[body.coefficient_offset + k];
+            entry.sin[k] = e->model.sin[body.coefficient_offset + k];
+          }
+        }
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_adaptive_tables, &tables,
+                                        sizeof(tables), 0,
                                         cudaMemcpyHostToDevice, stream));
         PB_CUDA(cudaStreamSynchronize(stream));
         return PB_OK;

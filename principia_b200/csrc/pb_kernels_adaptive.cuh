@@ -22,6 +22,57 @@ constexpr int kAdaptiveThreads = 128;
 
 static __constant__ BodyScalars c_adaptive_bodies;
 
+// The oblate bodies (the first of the internal order) with what their
+// harmonics up to degree kAdaptiveTableDegree need, in the constant bank: the
+// damped J2 of the Sun at every evaluation, the Earth beyond 23 000 km.  Through
+// the pointers of the EphemerisView the same evaluation is a chain of
+// dependent global loads (the body record, the threshold search, the
+// coefficients) that two warps per scheduler do not hide.
+constexpr int kAdaptiveTableBodies = 16;
+constexpr int kAdaptiveTableDegree = 3;
+constexpr int kAdaptiveTableSize =
+    (kAdaptiveTableDegree + 1) * (kAdaptiveTableDegree + 2) / 2;
+// The thresholds up to degree kAdaptiveTableDegree + 1 tell whether the degree
+// exceeds kAdaptiveTableDegree.
+constexpr int kAdaptiveTableDampings = kAdaptiveTableDegree + 2;
+
+struct AdaptiveBodyTables {
+  DeviceBody data;
+  Damping degree_damping[kAdaptiveTableDampings];
+  int32_t n_damping;  // min(n_damping, kAdaptiveTableDampings).
+  int32_t pad;
+  double cos[kAdaptiveTableSize];
+  double sin[kAdaptiveTableSize];
+};
+
+struct AdaptiveConstants {
+  int32_t n_tables;  // Bodies [0, n_tables) have an entry.
+  int32_t pad;
+  double normalization[kAdaptiveTableSize];
+  AdaptiveBodyTables bodies[kAdaptiveTableBodies];
+};
+
+static __constant__ AdaptiveConstants c_adaptive_tables;
+
+struct AdaptiveTables {
+  int b;
+  __device__ __forceinline__ double Cos(int const k) const {
+    return c_adaptive_tables.bodies[b].cos[k];
+  }
+  __device__ __forceinline__ double Sin(int const k) const {
+    return c_adaptive_tables.bodies[b].sin[k];
+  }
+  __device__ __forceinline__ double Normalization(int const k) const {
+    return c_adaptive_tables.normalization[k];
+  }
+  __device__ __forceinline__ Damping const& DegreeDamping(int const n) const {
+    return c_adaptive_tables.bodies[b].degree_damping[n];
+  }
+  __device__ __forceinline__ Damping const& SectoralDamping() const {
+    return c_adaptive_tables.bodies[b].data.sectoral;
+  }
+};
+
 // Right-hand side at a per-probe time: every massive body's polynomial is
 // evaluated here (the stage-table trick of the fixed-step kernel needs a time
 // shared by all probes).  `hint` caches the segment index relative to the
@@ -103,6 +154,40 @@ __device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
                                                double const dq_norm,
                                                double const dq2,
                                                double const one_over_dq3) {
+  if (b1 < c_adaptive_tables.n_tables && dq_norm == dq_norm) {
+    AdaptiveBodyTables const& tables = c_adaptive_tables.bodies[b1];
+    // LimitingDegree over the first thresholds is min(LimitingDegree,
+    // kAdaptiveTableDampings): exact whenever it says degree <= 3.
+    int const max_degree =
+        LimitingDegree(tables.degree_damping, tables.n_damping, dq_norm) - 1;
+    if (max_degree <= kAdaptiveTableDegree) {
+      // The operations of GeneralSphericalHarmonicsAccelerationRolled (the
+      // unrolled and the rolled evaluation of a degree have the same ones).
+      if (max_degree == 1) {
+        return {0.0, 0.0, 0.0};
+      }
+      DeviceBody const& body = tables.data;
+      bool const is_zonal =
+          body.is_zonal || dq_norm > body.sectoral.outer_threshold;
+      Vec3 x_hat, y_hat;
+      if (is_zonal) {
+        x_hat = body.equatorial;
+        y_hat = body.biequatorial;
+      } else {
+        SurfaceFrameAxes(body, t, x_hat, y_hat);
+      }
+      GeopotentialSetup s;
+      InitializeSetup(body, x_hat, y_hat, -dq, dq_norm, dq2, one_over_dq3, s);
+      AdaptiveTables const g{b1};
+      return is_zonal
+                 ? GeopotentialUnrolledDispatch<true, AdaptiveTables,
+                                                kAdaptiveTableDegree>(
+                       g, max_degree, s)
+                 : GeopotentialUnrolledDispatch<false, AdaptiveTables,
+                                                kAdaptiveTableDegree>(
+                       g, max_degree, s);
+    }
+  }
   GeopotentialBody const g = MakeGeopotentialBody(e, b1);
   return GeneralSphericalHarmonicsAccelerationRolled(g, t, -dq, dq_norm, dq2,
                                                      one_over_dq3);
