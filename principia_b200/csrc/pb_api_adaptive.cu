@@ -72,9 +72,51 @@ pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
                   "the sink must have one timeline per trajectory");
     }
   }
+  // Execution order: decreasing estimated cost.
+  PB_RETURN_IF_ERROR(w->adaptive_cost.Reserve(2 * static_cast<std::size_t>(n)));
+  PB_RETURN_IF_ERROR(w->adaptive_order.Reserve(2 * static_cast<std::size_t>(n)));
+  PB_RETURN_IF_ERROR(w->adaptive_queue.Reserve(1));
+  float* const cost_in = w->adaptive_cost.data;
+  float* const cost_out = cost_in + n;
+  int* const index_in = w->adaptive_order.data;
+  int* const order = index_in + n;
+  std::size_t sort_bytes = 0;
+  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
+      nullptr, sort_bytes, cost_in, cost_out, index_in, order, n, 0, 32,
+      stream));
+  PB_RETURN_IF_ERROR(w->adaptive_sort_storage.Reserve(sort_bytes));
+  sort_bytes = w->adaptive_sort_storage.capacity;
+  PB_RETURN_IF_ERROR(w->adaptive_votes.Reserve(kMaxConstantBodies));
+  PB_CUDA(cudaMemsetAsync(w->adaptive_votes.data, 0,
+                          kMaxConstantBodies * sizeof(int32_t), stream));
+  AdaptiveCostKernel<<<(n + 127) / 128, 128, 0, stream>>>(
+      e->View(), parameters.t_final, flow->n, flow->state, flow->time, cost_in,
+      index_in, w->adaptive_votes.data);
+  PB_LAUNCHED();
+  // The deep body: among the oblate bodies whose model fits the tables, the
+  // one that is the strongest tide of most trajectories.  Only the speed
+  // depends on the choice.
+  int deep = -1;
+  {
+    int32_t votes[kMaxConstantBodies];
+    PB_CUDA(cudaMemcpyAsync(votes, w->adaptive_votes.data, sizeof(votes),
+                            cudaMemcpyDeviceToHost, stream));
+    PB_CUDA(cudaStreamSynchronize(stream));
+    int32_t best = 0;
+    int const n_candidates = std::min(e->model.n_oblate, kAdaptiveTableBodies);
+    for (int b = 0; b < n_candidates; ++b) {
+      DeviceBody const& body = e->model.bodies[b];
+      if (body.degree > kAdaptiveTableDegree &&
+          body.degree <= kMaxUnrolledDegree &&
+          body.n_damping <= kMaxUnrolledDegree + 1 && votes[b] > best) {
+        best = votes[b];
+        deep = b;
+      }
+    }
+  }
   ConstantBankLease constants;
   PB_RETURN_IF_ERROR(AdaptiveConstantBank().Acquire(
-      e->serial, 0, [&]() -> pb_status_t {
+      e->serial, deep + 1, [&]() -> pb_status_t {
         static BodyScalars scalars;
         for (int b = 0; b < n_bodies; ++b) {
           DeviceBody const& body = e->model.bodies[b];
@@ -114,29 +156,31 @@ pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
         PB_CUDA(cudaMemcpyToSymbolAsync(c_adaptive_tables, &tables,
                                         sizeof(tables), 0,
                                         cudaMemcpyHostToDevice, stream));
+        static AdaptiveDeepBody deep_body;
+        std::memset(&deep_body, 0, sizeof(deep_body));
+        deep_body.body = deep;
+        if (deep >= 0) {
+          DeviceBody const& body = e->model.bodies[deep];
+          deep_body.n_damping = body.n_damping;
+          for (int d = 0; d < body.n_damping; ++d) {
+            deep_body.degree_damping[d] =
+                e->model.dampings[body.damping_offset + d];
+          }
+          int const size = (body.degree + 1) * (body.degree + 2) / 2;
+          for (int k = 0; k < size; ++k) {
+            deep_body.cos[k] = e->model.cos[body.coefficient_offset + k];
+            deep_body.sin[k] = e->model.sin[body.coefficient_offset + k];
+            deep_body.normalization[k] = pb_legendre_normalization_factor[k];
+          }
+        }
+        PB_CUDA(cudaMemcpyToSymbolAsync(c_adaptive_deep, &deep_body,
+                                        sizeof(deep_body), 0,
+                                        cudaMemcpyHostToDevice, stream));
         PB_CUDA(cudaStreamSynchronize(stream));
         return PB_OK;
       }));
   constants.Adopt(&AdaptiveConstantBank());
 
-  // Execution order: decreasing estimated cost.
-  PB_RETURN_IF_ERROR(w->adaptive_cost.Reserve(2 * static_cast<std::size_t>(n)));
-  PB_RETURN_IF_ERROR(w->adaptive_order.Reserve(2 * static_cast<std::size_t>(n)));
-  PB_RETURN_IF_ERROR(w->adaptive_queue.Reserve(1));
-  float* const cost_in = w->adaptive_cost.data;
-  float* const cost_out = cost_in + n;
-  int* const index_in = w->adaptive_order.data;
-  int* const order = index_in + n;
-  std::size_t sort_bytes = 0;
-  PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
-      nullptr, sort_bytes, cost_in, cost_out, index_in, order, n, 0, 32,
-      stream));
-  PB_RETURN_IF_ERROR(w->adaptive_sort_storage.Reserve(sort_bytes));
-  sort_bytes = w->adaptive_sort_storage.capacity;
-  AdaptiveCostKernel<<<(n + 127) / 128, 128, 0, stream>>>(
-      e->View(), parameters.t_final, flow->n, flow->state, flow->time, cost_in,
-      index_in);
-  PB_LAUNCHED();
   PB_CUDA(cub::DeviceRadixSort::SortPairsDescending(
       w->adaptive_sort_storage.data, sort_bytes, cost_in, cost_out, index_in,
       order, n, 0, 32, stream));

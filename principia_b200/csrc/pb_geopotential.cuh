@@ -1027,9 +1027,10 @@ PB_HD Vec3 GeneralSphericalHarmonicsAcceleration(GeopotentialBody const& g,
 // same bits), with the special orders (m = 0, n - 2, n - 1, n) peeled off the
 // loops, rotating row pointers instead of n % 3, and running table indices.
 // RN(1 / n) for DivideBySmallInteger.
-template<int kSize>
+// `Tables`: PointerTables or a kernel's constant-bank equivalent.
+template<int kSize, typename Tables>
 PB_HD_NOINLINE Vec3 GeopotentialRolledAcceleration(
-    GeopotentialBody const& g, int const max_degree, bool const is_zonal,
+    Tables const& g, int const max_degree, bool const is_zonal,
     GeopotentialSetup const& s) {
   double R_over_r_[kSize];
   double cos_m_lambda[kSize];
@@ -1060,9 +1061,6 @@ PB_HD_NOINLINE Vec3 GeopotentialRolledAcceleration(
     }
     double const R_over_r = R_over_r_[n];
     double const R_prime = -(n + 1) * R_over_r;
-    double const* const cos_n = g.cos + row;
-    double const* const sin_n = g.sin + row;
-    double const* const normalization_n = g.normalization + row;
     double sigma_R_over_r;
     Vec3 grad_sigma_R;
     // One term; `m`'s relation to 0 and n is known at each call site.
@@ -1070,8 +1068,9 @@ PB_HD_NOINLINE Vec3 GeopotentialRolledAcceleration(
                           double const cos_beta_to_the_m_minus_1) {
       return OrderTermAcceleration(
           n, m, Pn[m], Pnm1, cos_m_lambda[m], sin_m_lambda[m],
-          cos_beta_to_the_m[m], cos_beta_to_the_m_minus_1, cos_n[m], sin_n[m],
-          normalization_n[m], sigma_R_over_r, grad_sigma_R, s);
+          cos_beta_to_the_m[m], cos_beta_to_the_m_minus_1, g.Cos(row + m),
+          g.Sin(row + m), g.Normalization(row + m), sigma_R_over_r,
+          grad_sigma_R, s);
     };
     // m = 0 of DegreeNOrderM::UpdatePrecomputations: DmPn(n, 0), DmPn(n, 1).
     Pn[0] = DivideBySmallInteger(
@@ -1085,12 +1084,12 @@ PB_HD_NOINLINE Vec3 GeopotentialRolledAcceleration(
           one_over_n);
     }
     if (is_zonal) {
-      ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+      ComputeDampedRadialQuantities(g.DegreeDamping(n), s.r_norm, s.r2,
                                     s.r_normalized, R_over_r, R_prime,
                                     sigma_R_over_r, grad_sigma_R);
       degree_sum[n] = OrderTermAcceleration(
-          n, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0, cos_n[0], sin_n[0],
-          normalization_n[0], sigma_R_over_r, grad_sigma_R, s);
+          n, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0, g.Cos(row), g.Sin(row),
+          g.Normalization(row), sigma_R_over_r, grad_sigma_R, s);
     } else {
       // Orders 1 .. n - 3 (general recurrence), n - 2, n - 1.
       for (int m = 1; m <= n - 3; ++m) {
@@ -1133,19 +1132,19 @@ PB_HD_NOINLINE Vec3 GeopotentialRolledAcceleration(
         }
       }
       if (n == 2) {
-        ComputeDampedRadialQuantities(g.degree_damping[2], s.r_norm, s.r2,
+        ComputeDampedRadialQuantities(g.DegreeDamping(2), s.r_norm, s.r2,
                                       s.r_normalized, R_over_r, R_prime,
                                       sigma_R_over_r, grad_sigma_R);
         Vec3 const j2_acceleration = OrderTermAcceleration(
-            2, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0, cos_n[0], sin_n[0],
-            normalization_n[0], sigma_R_over_r, grad_sigma_R, s);
-        ComputeDampedRadialQuantities(g.body->sectoral, s.r_norm, s.r2,
+            2, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0, g.Cos(row), g.Sin(row),
+            g.Normalization(row), sigma_R_over_r, grad_sigma_R, s);
+        ComputeDampedRadialQuantities(g.SectoralDamping(), s.r_norm, s.r2,
                                       s.r_normalized, R_over_r, R_prime,
                                       sigma_R_over_r, grad_sigma_R);
         Vec3 const c22_s22_acceleration = term(2, 0.0, cos_beta_to_the_m[1]);
         degree_sum[n] = j2_acceleration + c22_s22_acceleration;
       } else {
-        ComputeDampedRadialQuantities(g.degree_damping[n], s.r_norm, s.r2,
+        ComputeDampedRadialQuantities(g.DegreeDamping(n), s.r_norm, s.r2,
                                       s.r_normalized, R_over_r, R_prime,
                                       sigma_R_over_r, grad_sigma_R);
         Vec3 sum = term(n, 0.0, cos_beta_to_the_m[n - 1]);
@@ -1153,7 +1152,7 @@ PB_HD_NOINLINE Vec3 GeopotentialRolledAcceleration(
           sum = term(m, Pn[m + 1], cos_beta_to_the_m[m - 1]) + sum;
         }
         sum = OrderTermAcceleration(n, 0, Pn[0], Pn[1], 0.0, 0.0, 1.0, 0.0,
-                                    cos_n[0], sin_n[0], normalization_n[0],
+                                    g.Cos(row), g.Sin(row), g.Normalization(row),
                                     sigma_R_over_r, grad_sigma_R, s) +
               sum;
         degree_sum[n] = sum;
@@ -1207,15 +1206,16 @@ PB_HD Vec3 GeneralSphericalHarmonicsAccelerationRolled(
   }
   GeopotentialSetup s;
   InitializeSetup(body, x_hat, y_hat, r, r_norm, r2, one_over_r3, s);
+  PointerTables const tables{g};
   if (max_degree <= kMaxUnrolledDegree) {
     // (A variant with the degrees rolled and the orders unrolled, per-order
     // state in registers, was measured 5 % slower here and 50 % slower than
     // the fully unrolled body in the fixed-step kernel: its 19 kB loop body
     // misses the instruction cache next to the rest of the kernel.)
     return GeopotentialRolledAcceleration<kMaxUnrolledDegree + 1>(
-        g, max_degree, is_zonal, s);
+        tables, max_degree, is_zonal, s);
   }
-  return GeopotentialRolledAcceleration<kGeopotentialSize>(g, max_degree,
+  return GeopotentialRolledAcceleration<kGeopotentialSize>(tables, max_degree,
                                                            is_zonal, s);
 }
 

@@ -54,6 +54,44 @@ struct AdaptiveConstants {
 
 static __constant__ AdaptiveConstants c_adaptive_tables;
 
+// The *deep* body: the one oblate body of degree 4 .. kMaxUnrolledDegree that
+// most trajectories of the call are closest to (the Earth of a batch of Earth
+// orbiters), with all its thresholds and coefficients in the constant bank.
+// The rolled evaluation walks the tables with run-time indices, which the
+// constant bank serves (LDC) without a round trip through the L1 that the
+// evaluation's own thread-local scratch keeps evicting.
+constexpr int kAdaptiveDeepSize =
+    (kMaxUnrolledDegree + 1) * (kMaxUnrolledDegree + 2) / 2;
+
+struct AdaptiveDeepBody {
+  int32_t body;       // Internal index < kAdaptiveTableBodies, or -1.
+  int32_t n_damping;  // The body's own.
+  Damping degree_damping[kMaxUnrolledDegree + 1];
+  double cos[kAdaptiveDeepSize];
+  double sin[kAdaptiveDeepSize];
+  double normalization[kAdaptiveDeepSize];
+};
+
+static __constant__ AdaptiveDeepBody c_adaptive_deep;
+
+struct AdaptiveDeepTables {
+  __device__ __forceinline__ double Cos(int const k) const {
+    return c_adaptive_deep.cos[k];
+  }
+  __device__ __forceinline__ double Sin(int const k) const {
+    return c_adaptive_deep.sin[k];
+  }
+  __device__ __forceinline__ double Normalization(int const k) const {
+    return c_adaptive_deep.normalization[k];
+  }
+  __device__ __forceinline__ Damping const& DegreeDamping(int const n) const {
+    return c_adaptive_deep.degree_damping[n];
+  }
+  __device__ __forceinline__ Damping const& SectoralDamping() const {
+    return c_adaptive_tables.bodies[c_adaptive_deep.body].data.sectoral;
+  }
+};
+
 struct AdaptiveTables {
   int b;
   __device__ __forceinline__ double Cos(int const k) const {
@@ -156,11 +194,17 @@ __device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
                                                double const one_over_dq3) {
   if (b1 < c_adaptive_tables.n_tables && dq_norm == dq_norm) {
     AdaptiveBodyTables const& tables = c_adaptive_tables.bodies[b1];
+    bool const deep = b1 == c_adaptive_deep.body;
     // LimitingDegree over the first thresholds is min(LimitingDegree,
-    // kAdaptiveTableDampings): exact whenever it says degree <= 3.
+    // kAdaptiveTableDampings): exact whenever it says degree <= 3.  The deep
+    // body has all its thresholds here.
     int const max_degree =
-        LimitingDegree(tables.degree_damping, tables.n_damping, dq_norm) - 1;
-    if (max_degree <= kAdaptiveTableDegree) {
+        (deep ? LimitingDegree(c_adaptive_deep.degree_damping,
+                               c_adaptive_deep.n_damping, dq_norm)
+              : LimitingDegree(tables.degree_damping, tables.n_damping,
+                               dq_norm)) -
+        1;
+    if (deep || max_degree <= kAdaptiveTableDegree) {
       // The operations of GeneralSphericalHarmonicsAccelerationRolled (the
       // unrolled and the rolled evaluation of a degree have the same ones).
       if (max_degree == 1) {
@@ -178,6 +222,10 @@ __device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
       }
       GeopotentialSetup s;
       InitializeSetup(body, x_hat, y_hat, -dq, dq_norm, dq2, one_over_dq3, s);
+      if (max_degree > kAdaptiveTableDegree) {
+        return GeopotentialRolledAcceleration<kMaxUnrolledDegree + 1>(
+            AdaptiveDeepTables{}, max_degree, is_zonal, s);
+      }
       AdaptiveTables const g{b1};
       return is_zonal
                  ? GeopotentialUnrolledDispatch<true, AdaptiveTables,
@@ -311,51 +359,68 @@ __device__ __noinline__ void AppendToSink(DownsamplerView const& sink,
 // state.  With a 4th-order error estimate the step scales like
 // (tolerance / a)^(1/4) / n (n the mean motion), so the cost over a span is
 // proportional to span * n * a^(1/4).  Only the order of execution depends on
-// it, never a result.
+// it, never a result.  votes[b]: how many trajectories have body b as their
+// strongest tide (the host chooses the deep body from them).
 static __global__ void AdaptiveCostKernel(EphemerisView const e,
                                           double const t_final,
                                           long long const n,
                                           double const* __restrict__ state,
                                           double const* __restrict__ time,
                                           float* __restrict__ cost,
-                                          int* __restrict__ index) {
+                                          int* __restrict__ index,
+                                          int32_t* __restrict__ votes) {
+  __shared__ int32_t block_votes[kMaxConstantBodies];
+  for (int b = threadIdx.x; b < kMaxConstantBodies; b += blockDim.x) {
+    block_votes[b] = 0;
+  }
+  __syncthreads();
   long long const i =
       static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) {
-    return;
-  }
-  double const t = time[i];
-  Vec3 const q{state[i], state[n + i], state[2 * n + i]};
-  Vec3 const v{state[6 * n + i], state[7 * n + i], state[8 * n + i]};
-  double best_tide = -1.0;
-  double best_mu = 0.0;
-  Vec3 best_dq{0.0, 0.0, 0.0}, best_dv{0.0, 0.0, 0.0};
-  for (int b = 0; b < e.n_bodies; ++b) {
-    int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
-                                    e.segment_end[b], t);
-    Vec3 const p0 = EvaluateSegment(e, segment, t);
-    Vec3 const dq = q - p0;
-    double const r2 = Norm2(dq);
-    double const mu = e.bodies[b].mu;
-    double const tide = mu / (r2 * sqrt(r2));
-    if (tide > best_tide) {
-      Vec3 const p1 = EvaluateSegment(e, segment, t + 1.0);
-      best_tide = tide;
-      best_mu = mu;
-      best_dq = dq;
-      best_dv = v - (p1 - p0);
+  if (i < n) {
+    double const t = time[i];
+    Vec3 const q{state[i], state[n + i], state[2 * n + i]};
+    Vec3 const v{state[6 * n + i], state[7 * n + i], state[8 * n + i]};
+    double best_tide = -1.0;
+    double best_mu = 0.0;
+    int best_body = 0;
+    Vec3 best_dq{0.0, 0.0, 0.0}, best_dv{0.0, 0.0, 0.0};
+    for (int b = 0; b < e.n_bodies; ++b) {
+      int const segment = FindSegment(e.segment_t_max, e.segment_offset[b],
+                                      e.segment_end[b], t);
+      Vec3 const p0 = EvaluateSegment(e, segment, t);
+      Vec3 const dq = q - p0;
+      double const r2 = Norm2(dq);
+      double const mu = e.bodies[b].mu;
+      double const tide = mu / (r2 * sqrt(r2));
+      if (tide > best_tide) {
+        Vec3 const p1 = EvaluateSegment(e, segment, t + 1.0);
+        best_tide = tide;
+        best_mu = mu;
+        best_body = b;
+        best_dq = dq;
+        best_dv = v - (p1 - p0);
+      }
+    }
+    double const r = sqrt(Norm2(best_dq));
+    double const energy = 0.5 * Norm2(best_dv) - best_mu / r;
+    double a = r;
+    if (energy < 0.0) {
+      a = -0.5 * best_mu / energy;
+    }
+    double const mean_motion = sqrt(best_mu / (a * a * a));
+    double const steps = fabs(t_final - t) * mean_motion * sqrt(sqrt(a));
+    cost[i] = steps == steps ? static_cast<float>(steps) : 0.0f;
+    index[i] = static_cast<int>(i);
+    if (best_body < kMaxConstantBodies) {
+      atomicAdd(block_votes + best_body, 1);
     }
   }
-  double const r = sqrt(Norm2(best_dq));
-  double const energy = 0.5 * Norm2(best_dv) - best_mu / r;
-  double a = r;
-  if (energy < 0.0) {
-    a = -0.5 * best_mu / energy;
+  __syncthreads();
+  for (int b = threadIdx.x; b < kMaxConstantBodies; b += blockDim.x) {
+    if (block_votes[b] != 0) {
+      atomicAdd(votes + b, block_votes[b]);
+    }
   }
-  double const mean_motion = sqrt(best_mu / (a * a * a));
-  double const steps = fabs(t_final - t) * mean_motion * sqrt(sqrt(a));
-  cost[i] = steps == steps ? static_cast<float>(steps) : 0.0f;
-  index[i] = static_cast<int>(i);
 }
 
 // The inertial direction of a burn given in the Frenet frame of the trajectory

@@ -330,6 +330,7 @@ struct FlowWorkspace {
   DeviceBuffer<int> adaptive_order;
   DeviceBuffer<unsigned char> adaptive_sort_storage;
   DeviceBuffer<unsigned long long> adaptive_queue;
+  DeviceBuffer<int32_t> adaptive_votes;
 
   // CUDA-event timing of the dominant kernel of a flow call.
   std::vector<cudaEvent_t> timing_events;
