@@ -808,12 +808,19 @@ __device__ __forceinline__ Vec3 GeopotentialUnrolledAccelerationFactored(
 }
 #endif
 
-template<int kMaxDegree, bool kZonal, typename Tables, typename Scratch>
+// kCapped: the degrees above the run-time `max_degree` (2 <= max_degree <=
+// kMaxDegree) are skipped and left out of the fold, which gives the operations
+// of GeopotentialUnrolledAcceleration<max_degree>: ONE straight-line body for
+// the lanes of a warp that evaluate different degrees (the adaptive flow),
+// where the dispatch on the degree would run one body per distinct degree.
+template<int kMaxDegree, bool kZonal, bool kCapped = false, typename Tables,
+         typename Scratch>
 PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
                                             GeopotentialSetup const& s,
-                                            Scratch& w) {
+                                            Scratch& w,
+                                            int const max_degree = kMaxDegree) {
 #if defined(PB_CONTRACTED_BUILD) && defined(__CUDA_ARCH__)
-  if constexpr (Scratch::kFactored) {
+  if constexpr (Scratch::kFactored && !kCapped) {
     return GeopotentialUnrolledAccelerationFactored<kMaxDegree, kZonal>(g, s,
                                                                         w);
   }
@@ -832,6 +839,12 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
     constexpr int size = kZonal ? 1 : n + 1;
     if (w.Failed()) {
       return;
+    }
+    if constexpr (kCapped) {
+      if (n > max_degree) {
+        w.template SetDegreeSum<n>(Vec3{0.0, 0.0, 0.0});
+        return;
+      }
     }
     if constexpr (n % 2 == 0) {
       constexpr int h = n / 2;
@@ -887,7 +900,18 @@ PB_HD Vec3 GeopotentialUnrolledAcceleration(Tables const& g,
   Vec3 sum = w.template DegreeSum<kMaxDegree>();
   StaticForRange<0, kMaxDegree - 2>([&](auto i_constant) {
     constexpr int n = kMaxDegree - 1 - decltype(i_constant)::value;
-    sum = w.template DegreeSum<n>() + sum;
+    if constexpr (kCapped) {
+      // The fold starts at max_degree.
+      Vec3 const own = w.template DegreeSum<n>();
+      Vec3 const folded = own + sum;
+      bool const start = n == max_degree;
+      bool const below = n < max_degree;
+      sum = {start ? own.x : (below ? folded.x : sum.x),
+             start ? own.y : (below ? folded.y : sum.y),
+             start ? own.z : (below ? folded.z : sum.z)};
+    } else {
+      sum = w.template DegreeSum<n>() + sum;
+    }
   });
   Vec3 const zero{0.0, 0.0, 0.0};
   sum = zero + sum;
