@@ -30,19 +30,6 @@ int AdaptiveMinBlocks() {
   return value;
 }
 
-// Shared memory per block for the segment window (two blocks per SM; what is
-// left of the 256 kB is the L1 that serves the thread-local scratch).
-// PB_ADAPTIVE_WINDOW_BYTES=0 turns the window off.
-std::size_t AdaptiveWindowBytes() {
-  static std::size_t const value = [] {
-    char const* const text = std::getenv("PB_ADAPTIVE_WINDOW_BYTES");
-    long long const v = text != nullptr ? std::atoll(text) : 0;
-    return static_cast<std::size_t>(std::min<long long>(
-        std::max<long long>(v, 0), 100 * 1024));
-  }();
-  return value;
-}
-
 // The constant bank of this translation unit (c_adaptive_bodies).
 ConstantBank& AdaptiveConstantBank() {
   static ConstantBank bank;
@@ -66,7 +53,6 @@ pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
       flow->step_log != nullptr || flow->state_log != nullptr
           ? flow->step_log_capacity
           : 0;
-  parameters.window = SegmentWindow{0, 0, 0};
   if (flow->n == 0) {
     return PB_OK;
   }
@@ -231,42 +217,7 @@ pb_status_t AdaptiveFlowDevice(pb_ephemeris_t* e, FlowWorkspace* w,
           : (min_blocks == 2
                  ? ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 2>
                  : ErknFlowKernel<DormandElMikkawyPrince1986RKN434FM, 3>);
-  // The segment window (pb_kernels_adaptive.cuh): the segments up to that of
-  // t_final, as many as fit the budget of shared memory.
-  std::size_t window_bytes = 0;
-  if (AdaptiveWindowBytes() > 0 && e->uniform_segments && n_bodies > 0 &&
-      !e->trajectories[0].t_max.empty()) {
-    std::vector<double> const& t_max = e->trajectories[0].t_max;
-    int const n_segments = static_cast<int>(t_max.size());
-    int const last = std::min<int>(
-        std::lower_bound(t_max.begin(), t_max.end(), parameters.t_final) -
-            t_max.begin(),
-        n_segments - 1);
-    std::size_t const segment_bytes =
-        static_cast<std::size_t>(n_bodies) * kWindowRecord * sizeof(double);
-    int const count = static_cast<int>(std::min<std::size_t>(
-        {AdaptiveWindowBytes() / segment_bytes, 8,
-         static_cast<std::size_t>(last + 1)}));
-    if (count > 0) {
-      SegmentWindow& window = parameters.window;
-      window.first = last + 1 - count;
-      window.count = count;
-      window.bodies = 0;
-      for (int b = 0; b < n_bodies; ++b) {
-        std::vector<int32_t> const& degree = e->trajectories[b].degree;
-        bool low = static_cast<int>(degree.size()) == n_segments;
-        for (int k = 0; low && k < count; ++k) {
-          low = degree[window.first + k] < kWindowSlots;
-        }
-        window.bodies |= static_cast<unsigned long long>(low) << b;
-      }
-      window_bytes = count * segment_bytes;
-    }
-  }
-  PB_CUDA(cudaFuncSetAttribute(kernel,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(AdaptiveWindowBytes())));
-  kernel<<<blocks, kAdaptiveThreads, window_bytes, stream>>>(
+  kernel<<<blocks, kAdaptiveThreads, 0, stream>>>(
       e->View(), parameters, flow->n, order, w->adaptive_queue.data,
       e->stop_word_device, flow->state, flow->time, flow->status,
       reinterpret_cast<long long*>(flow->accepted_steps),

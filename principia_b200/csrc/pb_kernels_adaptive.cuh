@@ -29,10 +29,6 @@ constexpr int kAdaptiveThreads = 128;
 #if !defined(PB_ADAPTIVE_DEEP_UNROLLED)
 #define PB_ADAPTIVE_DEEP_UNROLLED 1
 #endif
-// Whether the polynomials are read from the shared-memory segment window.
-#if !defined(PB_ADAPTIVE_WINDOW)
-#define PB_ADAPTIVE_WINDOW 1
-#endif
 
 static __constant__ BodyScalars c_adaptive_bodies;
 
@@ -167,29 +163,6 @@ __device__ __forceinline__ int32_t AccelerationOnMasslessBodyAtTime(
   return error;
 }
 
-// The segment window: the low coefficients, origins and degrees of the
-// segments [first, first + count) of every body, copied to shared memory by
-// each block when it starts.  The lanes of a warp advance at their own pace and
-// sit in half a dozen different segments, and the thread-local scratch of the
-// harmonics (7.7 kB of traffic per evaluation and lane) flushes the L1 between
-// two evaluations, so that from global memory the 14 loads of a body's
-// polynomials cost a round trip to the L2 more often than not (ncu, r03w: 18 %
-// of the kernel's warp time waits on them).  Record of (body, segment):
-// kWindowSlots slots of x, of y, of z, the origin, the degree (as the bits of
-// an integer): 208 bytes, [body][segment], so that the records of eight
-// consecutive segments of a body start in different banks.  Only for
-// ephemerides whose bodies were appended in lock step (uniform_segments);
-// `bodies`: the bodies whose degree stays below kWindowSlots over the window
-// (the others, and times outside the window, read global memory as before).
-constexpr int kWindowSlots = 8;
-constexpr int kWindowRecord = 3 * kWindowSlots + 2;
-
-struct SegmentWindow {
-  int32_t first;
-  int32_t count;  // 0: no window.
-  unsigned long long bodies;
-};
-
 struct AdaptiveParameters {
   double t_requested;  // The caller's t.
   double t_final;      // min(t, t_max of the ephemeris).
@@ -198,7 +171,6 @@ struct AdaptiveParameters {
   double speed_integration_tolerance;
   long long max_steps;
   long long step_log_capacity;
-  SegmentWindow window;
 };
 
 // std::max / std::min of the reference, NaN behaviour included.
@@ -260,21 +232,27 @@ __device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
       }
       GeopotentialSetup s;
       InitializeSetup(body, x_hat, y_hat, -dq, dq_norm, dq2, one_over_dq3, s);
-      if (max_degree > kAdaptiveTableDegree) {
 #if PB_ADAPTIVE_DEEP_UNROLLED
-        // The tesseral evaluation of the deep body: the unrolled body of the
-        // full degree, every lane leaving at its own degree.  Coefficients
-        // are constant-bank operands, Legendre values live in registers.
-        if (!is_zonal) {
-          FlaggedScratch<kMaxUnrolledDegree> w;
-          Vec3 const acceleration =
-              GeopotentialUnrolledAcceleration<kMaxUnrolledDegree, false, true>(
-                  AdaptiveDeepTables{}, s, w, max_degree);
-          if (!w.Failed()) {
-            return acceleration;
-          }
+      // The deep body: the unrolled evaluation of the full degree, every lane
+      // leaving at its own degree (the lanes of a warp near the body walk ONE
+      // body of code whatever their degrees).  Coefficients are constant-bank
+      // operands, the Legendre values live in registers.
+      if (deep) {
+        FlaggedScratch<kMaxUnrolledDegree> w;
+        Vec3 const acceleration =
+            is_zonal
+                ? GeopotentialUnrolledAcceleration<kMaxUnrolledDegree, true,
+                                                   true>(AdaptiveDeepTables{},
+                                                         s, w, max_degree)
+                : GeopotentialUnrolledAcceleration<kMaxUnrolledDegree, false,
+                                                   true>(AdaptiveDeepTables{},
+                                                         s, w, max_degree);
+        if (!w.Failed()) {
+          return acceleration;
         }
+      }
 #endif
+      if (max_degree > kAdaptiveTableDegree) {
         return GeopotentialRolledAcceleration<kMaxUnrolledDegree + 1>(
             AdaptiveDeepTables{}, max_degree, is_zonal, s);
       }
@@ -293,61 +271,6 @@ __device__ __noinline__ Vec3 AdaptiveHarmonics(EphemerisView const& e,
                                                      one_over_dq3);
 }
 
-__device__ __forceinline__ double* SegmentWindowStorage() {
-  extern __shared__ double2 segment_window_storage[];
-  return reinterpret_cast<double*>(segment_window_storage);
-}
-
-__device__ __forceinline__ void FillSegmentWindow(EphemerisView const& e,
-                                                  SegmentWindow const& window) {
-  double* const storage = SegmentWindowStorage();
-  int const size = e.n_bodies * window.count * kWindowRecord;
-  for (int index = threadIdx.x; index < size; index += blockDim.x) {
-    int const record = index / kWindowRecord;
-    int const k = index - record * kWindowRecord;
-    int const b = record / window.count;
-    int const segment =
-        b * e.segment_capacity + window.first + (record - b * window.count);
-    double value;
-    if (k < 3 * kWindowSlots) {
-      value = e.segment_coefficients[static_cast<long long>(segment) * 3 *
-                                         kSegmentCoefficients +
-                                     (k / kWindowSlots) * kSegmentCoefficients +
-                                     k % kWindowSlots];
-    } else if (k == 3 * kWindowSlots) {
-      value = e.segment_origin[segment];
-    } else {
-      value = __longlong_as_double(e.segment_degree[segment]);
-    }
-    storage[index] = value;
-  }
-  __syncthreads();
-}
-
-// EvaluateSegmentPadded on a record of the window (degree < kWindowSlots: the
-// first block of the tree is the whole tree).
-__device__ __forceinline__ Vec3 EvaluateWindowRecord(double const* const record,
-                                                     double const t) {
-  double2 const* const pairs = reinterpret_cast<double2 const*>(record);
-  double2 const tail = pairs[3 * kWindowSlots / 2];
-  double const x = t - tail.x;
-  int const degree = __double2loint(tail.y);
-  double const x2 = x * x;
-  double const x4 = x2 * x2;
-  auto const block = [&](int const coordinate) {
-    auto const leaf = [&](int const k) {
-      double2 const pair = pairs[coordinate * (kWindowSlots / 2) + k / 2];
-      return k + 1 <= degree ? fma(pair.y, x, pair.x) : pair.x;
-    };
-    double const l0 = leaf(0);
-    double const l1 = leaf(2);
-    double const l2 = leaf(4);
-    double const l3 = leaf(6);
-    return fma(fma(l3, x2, l2), x4, fma(l1, x2, l0));
-  };
-  return {block(0), block(1), block(2)};
-}
-
 // AccelerationOnMasslessBodyAtTime with the padded Estrin tree, the
 // branch-free square root and division (pb_math.cuh) and the early exit for
 // oblate bodies beyond their degree-2 outer threshold: the same arithmetic,
@@ -355,8 +278,8 @@ __device__ __forceinline__ Vec3 EvaluateWindowRecord(double const* const record,
 // previous evaluation (relative to the body's first segment).
 template<bool kTwoPhase>
 __device__ __forceinline__ int32_t FastAccelerationAtTime(
-    EphemerisView const& e, SegmentWindow const& window, double const t,
-    Vec3 const& q, Vec3& acceleration, int& hint) {
+    EphemerisView const& e, double const t, Vec3 const& q, Vec3& acceleration,
+    int& hint) {
   double ax = 0.0, ay = 0.0, az = 0.0;
   int32_t error = 0;
   bool in_range = true;
@@ -372,19 +295,7 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
       hint = FindSegment(e.segment_t_max, 0, end, t);
     }
   }
-  // window.count != 0 only with uniform segments: the hint is final here.
-  unsigned const window_index = static_cast<unsigned>(hint - window.first);
-  bool const in_window = window_index < static_cast<unsigned>(window.count);
   auto const position_of = [&](int const b1) {
-#if PB_ADAPTIVE_WINDOW
-    if (in_window && ((window.bodies >> b1) & 1) != 0) {
-      return EvaluateWindowRecord(
-          SegmentWindowStorage() +
-              (b1 * window.count + static_cast<int>(window_index)) *
-                  kWindowRecord,
-          t);
-    }
-#endif
     // The segments of body b1 start at b1 * segment_capacity: no load between
     // the hint and the addresses of the coefficients.
     int const begin = b1 * e.segment_capacity;
@@ -398,8 +309,12 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
       }
     }
     // (Prefetching the next body's coefficients into the L1 while this one is
-    // evaluated changed nothing: the wait at the first use is the issue of the
-    // 27 loads plus an L1 hit, not a miss.)
+    // evaluated changed nothing.  Serving them from a window of the last 3 to
+    // 8 segments copied to shared memory -- the lanes of a warp sit in half a
+    // dozen different segments, ncu attributes 18 % of the warp time to these
+    // loads -- was 3 to 9 % SLOWER, the more so the larger the window: what it
+    // takes from the L1 is missed by the thread-local scratch of the
+    // harmonics.)
     return EvaluateSegmentPadded(e, segment, t);
   };
   // kTwoPhase: the polynomials of all the bodies first, in a loop of their own
@@ -420,12 +335,11 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
     }
   }
   // The geometry of a body -- its polynomials, the distance, 1 / distance^3 --
-  // does not depend on the running sum: two bodies at a time, so that the
-  // coefficient loads of the second (an L2 round trip more often than not:
-  // the lanes of a warp sit in half a dozen different segments and the
-  // scratch of the harmonics keeps evicting them from the L1) and its square
-  // root and division chains overlap those of the first.  The terms are added
-  // body by body in the reference's order.
+  // does not depend on the running sum.  PB_ADAPTIVE_PAIRS evaluates it for
+  // two bodies at a time, so that the coefficient loads and the square root
+  // and division chains of the second overlap those of the first; measured
+  // 4 % SLOWER (registers) and off.  The terms are added body by body in the
+  // reference's order either way.
   struct Geometry {
     double dx, dy, dz, dq2, dq_norm, one_over_dq3;
   };
@@ -756,9 +670,6 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
   constexpr int kStages = Method::kStages;
   constexpr double safety_factor = 0.9;
   double const t_final = parameters.t_final;
-  if (parameters.window.count != 0) {
-    FillSegmentWindow(e, parameters.window);
-  }
 
   // The trajectory of this lane.
   bool busy = false;
@@ -869,8 +780,8 @@ ErknFlowKernel(EphemerisView const e, AdaptiveParameters const parameters,
                            q[2].value + h * c_s * v[2].value + h2 * sum.z};
         Vec3 acceleration;
         int32_t const rhs_error =
-            FastAccelerationAtTime<kTwoPhase>(e, parameters.window, t_stage,
-                                              q_stage, acceleration, hint);
+            FastAccelerationAtTime<kTwoPhase>(e, t_stage, q_stage, acceleration,
+                                              hint);
         if constexpr (kGeneralized) {
           if (burns != nullptr) {
             // :186-201 of the generalized integrator: the velocity stage, then
