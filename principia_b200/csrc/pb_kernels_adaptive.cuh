@@ -336,10 +336,11 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
   }
   // The geometry of a body -- its polynomials, the distance, 1 / distance^3 --
   // does not depend on the running sum.  PB_ADAPTIVE_PAIRS evaluates it for
-  // two bodies at a time, so that the coefficient loads and the square root
-  // and division chains of the second overlap those of the first; measured
-  // 4 % SLOWER (registers) and off.  The terms are added body by body in the
-  // reference's order either way.
+  // two spherical bodies at a time, so that the coefficient loads and the
+  // square root and division chains of the second overlap those of the first:
+  // measured no faster (9.6-9.9 against 10.0 10^8 evaluations/s; with the
+  // oblate bodies paired as well, 4 % slower) and off.  The terms are added
+  // body by body in the reference's order either way.
   struct Geometry {
     double dx, dy, dz, dq2, dq_norm, one_over_dq3;
   };
@@ -361,44 +362,53 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
     g.one_over_dq3 = FastDivide(g.dq_norm, g.dq2 * g.dq2);
     return g;
   };
-  auto const add_body = [&](int const b1, Geometry const& g) {
+  auto const add_point_mass = [&](int const b1, Geometry const& g) {
     double const mu1 = c_adaptive_bodies.mu[b1];
     error |= g.dq_norm > c_adaptive_bodies.collision_radius[b1] ? 0 : 11;
     double const mu1_over_dq3 = mu1 * g.one_over_dq3;
     ax += g.dx * mu1_over_dq3;
     ay += g.dy * mu1_over_dq3;
     az += g.dz * mu1_over_dq3;
-    if (b1 < n_oblate) {
-      // A NaN distance fails the comparison and takes the full path.
-      if (!(g.dq_norm >= c_adaptive_bodies.outer_threshold_degree_2[b1])) {
-        Vec3 const effect =
-            AdaptiveHarmonics(e, b1, t, Vec3{g.dx, g.dy, g.dz}, g.dq_norm,
-                              g.dq2, g.one_over_dq3);
-        ax += mu1 * effect.x;
-        ay += mu1 * effect.y;
-        az += mu1 * effect.z;
-      } else {
-        // The reference adds mu1 * (zero vector) here.
-        double const zero = mu1 * 0.0;
-        ax += zero;
-        ay += zero;
-        az += zero;
-      }
-    }
+    return mu1;
   };
+  // The oblate bodies come first in the internal order; the spherical ones
+  // have a loop of their own without the call and the reconvergence point of
+  // the harmonics (ncu, r04a: 4 % of the warp time sat on the instruction
+  // after that point and 2 % on the reload of the loop bound after the call,
+  // for all 34 bodies).
   int b1 = 0;
+#pragma unroll 1
+  for (; b1 < n_oblate; ++b1) {
+    Geometry const g = geometry_of(b1);
+    double const mu1 = add_point_mass(b1, g);
+    // A NaN distance fails the comparison and takes the full path.
+    if (!(g.dq_norm >= c_adaptive_bodies.outer_threshold_degree_2[b1])) {
+      Vec3 const effect =
+          AdaptiveHarmonics(e, b1, t, Vec3{g.dx, g.dy, g.dz}, g.dq_norm, g.dq2,
+                            g.one_over_dq3);
+      ax += mu1 * effect.x;
+      ay += mu1 * effect.y;
+      az += mu1 * effect.z;
+    } else {
+      // The reference adds mu1 * (zero vector) here.
+      double const zero = mu1 * 0.0;
+      ax += zero;
+      ay += zero;
+      az += zero;
+    }
+  }
 #if PB_ADAPTIVE_PAIRS
 #pragma unroll 1
   for (; b1 + 1 < n_bodies; b1 += 2) {
     Geometry const first = geometry_of(b1);
     Geometry const second = geometry_of(b1 + 1);
-    add_body(b1, first);
-    add_body(b1 + 1, second);
+    add_point_mass(b1, first);
+    add_point_mass(b1 + 1, second);
   }
 #endif
 #pragma unroll 1
   for (; b1 < n_bodies; ++b1) {
-    add_body(b1, geometry_of(b1));
+    add_point_mass(b1, geometry_of(b1));
   }
   if (!in_range) {
     return SlowAccelerationAtTime(e, t, q, acceleration);
