@@ -154,6 +154,39 @@ int32_t hc_geopotential_acceleration(hc_model const* m, int32_t body, double t,
   double const r2 = Norm2(rv);
   double const r_norm = sqrt(r2);
   double const one_over_r3 = r_norm / (r2 * r2);
+  if (unrolled == 3) {
+    // The capped unrolled evaluation of the adaptive flow's deep body
+    // (pb_kernels_adaptive.cuh AdaptiveHarmonics): the body of degree
+    // kMaxUnrolledDegree left at the limiting degree of this distance.
+    int const max_degree =
+        LimitingDegree(g.degree_damping, g.body->n_damping, r_norm) - 1;
+    Vec3 a{0.0, 0.0, 0.0};
+    if (max_degree > kMaxUnrolledDegree) {
+      return PB_INVALID_ARGUMENT;
+    }
+    if (max_degree != 1) {
+      bool const is_zonal =
+          g.body->is_zonal || r_norm > g.body->sectoral.outer_threshold;
+      if (is_zonal) {
+        x_hat = g.body->equatorial;
+        y_hat = g.body->biequatorial;
+      } else {
+        SurfaceFrameAxes(*g.body, t, x_hat, y_hat);
+      }
+      GeopotentialSetup s;
+      InitializeSetup(*g.body, x_hat, y_hat, rv, r_norm, r2, one_over_r3, s);
+      PointerTables const tables{g};
+      LocalScratch<kMaxUnrolledDegree> w;
+      a = is_zonal ? GeopotentialUnrolledAcceleration<kMaxUnrolledDegree, true,
+                                                      true>(tables, s, w,
+                                                            max_degree)
+                   : GeopotentialUnrolledAcceleration<kMaxUnrolledDegree, false,
+                                                      true>(tables, s, w,
+                                                            max_degree);
+    }
+    out[0] = a.x; out[1] = a.y; out[2] = a.z;
+    return PB_OK;
+  }
   Vec3 const a =
       unrolled == 2
           ? GeneralSphericalHarmonicsAccelerationRolled(g, t, rv, r_norm, r2,

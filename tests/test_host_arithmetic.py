@@ -254,8 +254,12 @@ def test_model_order_and_dampings_match_oracle(hc):
   hc.hc_model_destroy(handle)
 
 
-@pytest.mark.parametrize('unrolled', [0, 1, 2])
+@pytest.mark.parametrize('unrolled', [0, 1, 2, 3])
 def test_geopotential_matches_oracle_bitwise(hc, unrolled):
+  """0: generic loops; 1: unrolled bodies dispatched on the degree; 2: run-time
+  loops with peeled orders; 3: the unrolled body of degree 10 capped at the
+  limiting degree (the adaptive flow's deep body), for the bodies whose model
+  has degree <= 10."""
   system = SolarSystem.from_fixture('sol_jd2451545')
   oracle = OracleEphemeris(system)
   handle, keep = make_model(hc, system, 2.0**-24)
@@ -264,6 +268,8 @@ def test_geopotential_matches_oracle_bitwise(hc, unrolled):
   checked = 0
   for i, b in enumerate(system.bodies):
     if not b['oblate']:
+      continue
+    if unrolled == 3 and b['degree'] > 10:
       continue
     inner, sectoral = oracle.damping(i)
     radius = b['mean_radius']
