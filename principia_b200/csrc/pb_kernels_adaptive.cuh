@@ -314,7 +314,10 @@ __device__ __forceinline__ int32_t FastAccelerationAtTime(
     // dozen different segments, ncu attributes 18 % of the warp time to these
     // loads -- was 3 to 9 % SLOWER, the more so the larger the window: what it
     // takes from the L1 is missed by the thread-local scratch of the
-    // harmonics.)
+    // harmonics.  Skipping the loads and selects of the leaves that are
+    // padding in every segment of a body -- a per-body bound passed with the
+    // kernel's parameters -- was 14 % slower: the loads then wait for the
+    // bound.)
     return EvaluateSegmentPadded(e, segment, t);
   };
   // kTwoPhase: the polynomials of all the bodies first, in a loop of their own
